@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the MPNN forward hot path (BASELINE.json metric: ion-pair graphs/s, viscosity model).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+One "step" = one forward of the whole viscosity MPNN over one packed batch of synthetic ion pairs.
+Workload at N GPUs (weak scaling): BASELINE.json configs[2] -- the viscosity inference sweep -- with
+``--pairs-per-gpu`` pairs resident on every GPU (default 2,097,152 => 16.8 M pairs at 8 GPUs, the config's 16 M).
+Pairs are independent, so ranks shard them with no data-path collective.
+
+value   = pairs processed by all ranks / max-over-ranks device time, inputs already resident in HBM.
+e2e     = same metric through MPNNModel.predict-style calls from PINNED HOST buffers: per step the packed
+          batch is copied host->device, the kernels run, and the predictions are copied device->host.
+roofline= the dominant kernel (largest share of the step), algorithmic bytes per launch / its CUDA-event time,
+          against MEASURED_PEAKS.json.
+cpu_baseline = oracle/ref_model.py (torch fp32 port of the reference's TF graph; TensorFlow is not installable
+          here) on the host cores, on a bounded sample of the same workload, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ion_pair_graphs_per_s"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="visc_sweep", choices=["visc_sweep", "mp64k"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=None)
+    ap.add_argument("--skewed", action="store_true", help="Zipf(1.2) bond types instead of uniform")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=4000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    if args.workload == "visc_sweep":
+        P = args.pairs_per_gpu or 2_097_152
+        kind = "viscosity"
+        name = ("BASELINE configs[2]: viscosity MPNN inference sweep (atom_dim 32, bond_dim 8, 4 steps, vocab 123/71, "
+                "10-40 atoms/ion), weak scaling")
+    else:
+        P = args.pairs_per_gpu or 65_536
+        kind = "melting_point"
+        name = "BASELINE configs[1]: melting-point MPNN forward, 64k pairs per GPU (atom_dim 32, bond_dim 1024, 4 steps)"
+    return P, kind, name
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------ reference arm / cpu baseline
+def cpu_reference_run(kind, n_pairs, steps, warmup, skewed):
+    """Times oracle/ref_model.py (fp32, all host threads) the way the reference predicts: padded inputs,
+    ``model.predict(x)`` with Keras' default batch size 32 (train_viscosity.py:366)."""
+    import torch
+
+    from ionic_mpnn_b200 import synth
+    from oracle import ref_inputs, ref_model
+
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    recs = synth.make_records(n_pairs, seed=1002, skewed=skewed, label="log_eta" if kind == "viscosity" else "mp")
+    spec = ref_model.make_spec(kind)
+    params = ref_model.init_params(spec, seed=1)
+    x = ref_inputs.build_inputs(recs, with_temperature=kind == "viscosity")
+    best = None
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        ref_model.predict(spec, params, x, dtype=torch.float32, batch_size=32)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return {"value": n_pairs / mean, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_pairs} synthetic pairs (seed 1002), padded as the reference pads, predict(batch_size=32), "
+                      f"torch fp32 CPU port of models/layers.py, mean of {len(times)} runs after {warmup} warm-up",
+            "ms_per_step": mean * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    P, kind, name = workload_config(args)
+    warm = max(1, min(args.warmup, 2))
+    steps = max(1, min(args.steps, 5))
+    r = cpu_reference_run(kind, args.cpu_sample_pairs, steps, warm, args.skewed)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "sample_pairs_per_step": args.cpu_sample_pairs},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def stage_bytes(batch, d, S, s=4):
+    """Algorithmic bytes per launch (each operand once, weights / tables amortised to 0, int32 indices)."""
+    N, Eu, P = batch.n_atoms, batch.n_unique, batch.n_pairs
+    return {
+        "embed_atoms": 4 * N + N * d * s,
+        "message_agg": 2 * N * d * s + 8 * Eu + 4 * N,   # h in, agg out, (src, bond|mult) per unique entry, row_ptr
+        "gated_update": 3 * N * d * s,                    # h, agg in; h out
+        "pool_head": N * d * s + 4 * N + 8 * P + 8 * P,   # h, atom_id, mol_ptr (2 towers), T + out
+    }
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from ionic_mpnn_b200 import graph
+    from ionic_mpnn_b200.model import MPNNModel, make_spec
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P, kind, name = workload_config(args)
+    spec = make_spec(kind)
+    model = MPNNModel(spec, device=f"cuda:{local}", seed=0)
+    d, S = spec["atom_dim"], spec["num_steps"]
+
+    t_pack0 = time.perf_counter()
+    batch, _, _ = graph.synth_batch(P, seed=1003 + rank, skewed=args.skewed, with_temperature=(kind == "viscosity"))
+    t_pack = time.perf_counter() - t_pack0
+    batch.to(f"cuda:{local}")
+    model.refresh_tables()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    for _ in range(args.warmup):
+        model.forward_packed(batch)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        out = model.forward_packed(batch)
+    ev1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    barrier()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = P * world * args.steps / (ms_total * 1e-3)
+
+    # ---- per-kernel timing (rank 0): CUDA events around every launch of one more pass -----------
+    per_kernel = {}
+    if rank == 0:
+        import ctypes as C
+
+        from ionic_mpnn_b200 import _lib
+        real_call = _lib.call
+        events = []
+
+        def timed_call(name, *a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            real_call(name, *a)
+            e1.record()
+            events.append((name, e0, e1))
+
+        import ionic_mpnn_b200.model as mm
+        mm._lib.call = timed_call
+        try:
+            for _ in range(2):
+                model.forward_packed(batch)
+        finally:
+            mm._lib.call = real_call
+        torch.cuda.synchronize()
+        for name, e0, e1 in events:
+            per_kernel.setdefault(name.replace("imp_", ""), []).append(e0.elapsed_time(e1))
+    barrier()
+
+    # ---- end-to-end from pinned host buffers --------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pinned = {k: torch.from_numpy(batch.host[k]).pin_memory() for k in graph.GRAPH_FIELDS}
+        pinned_T = torch.from_numpy(batch.temperature).pin_memory() if batch.temperature is not None else None
+        out_host = torch.empty(P, dtype=torch.float32).pin_memory()
+        h2d = sum(t.numel() * 4 for t in pinned.values()) + (pinned_T.numel() * 4 if pinned_T is not None else 0)
+
+        def e2e_step():
+            for k in graph.GRAPH_FIELDS:
+                batch.dev[k].copy_(pinned[k], non_blocking=True)
+            if pinned_T is not None:
+                batch.dev_T.copy_(pinned_T, non_blocking=True)
+            o = model.forward_packed(batch)
+            out_host.copy_(o, non_blocking=True)
+
+        for _ in range(max(1, args.warmup - 1)):
+            e2e_step()
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        ev1.record()
+        torch.cuda.synchronize()
+        barrier()
+        ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        e2e = {"value": P * world * args.steps / (float(ms2.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": P * 4, "ms_per_step": float(ms2.item()) / args.steps,
+               "note": "pinned host packed batch -> H2D -> kernels -> D2H predictions, per step, per GPU"}
+
+    if rank == 0:
+        hbm_peak, tf_peak, peak_src = measured_peaks()
+        sb = stage_bytes(batch, d, S)
+        mean_ms = {k: sum(v) / len(v) for k, v in per_kernel.items()}
+        tot_ms = {k: sum(v) / 2 for k, v in per_kernel.items()}  # two instrumented passes
+        dom = max(tot_ms, key=tot_ms.get) if tot_ms else None
+        roofline = None
+        if dom:
+            ach = sb.get(dom, 0) / (mean_ms[dom] * 1e-3) / 1e9
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": sb.get(dom), "avg_launch_ms": mean_ms[dom],
+                        "share_of_step": tot_ms[dom] / sum(tot_ms.values()),
+                        "per_kernel": {k: {"avg_ms": mean_ms[k], "launches_per_step": len(per_kernel[k]) // 2,
+                                           "share": tot_ms[k] / sum(tot_ms.values()),
+                                           "GBps": (sb[k] / (mean_ms[k] * 1e-3) / 1e9) if k in sb else None}
+                                       for k in mean_ms}}
+        cpu = None
+        if not args.no_cpu_baseline:
+            r = cpu_reference_run(kind, args.cpu_sample_pairs, 3, 1, args.skewed)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": name, "pairs_per_gpu": P, "atoms_per_gpu": batch.n_atoms,
+                           "edges_per_gpu": batch.n_edges, "unique_edges_per_gpu": batch.n_unique,
+                           "bond_types": "zipf1.2" if args.skewed else "uniform",
+                           "l2_policy": "inputs larger than L2 (activations %.1f GB per GPU)" % (3 * batch.n_atoms * d * 4 / 1e9),
+                           "parallelism": f"pairs sharded over {world} GPU(s), no collective",
+                           "host_synth_and_pack_s": round(t_pack, 2)},
+                "edges_per_s": batch.n_edges * world * args.steps / (ms_total * 1e-3),
+                "gpu_launches": model.launches_per_forward() * args.steps,
+                "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

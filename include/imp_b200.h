@@ -1,0 +1,176 @@
+/*
+ * imp_b200.h -- C ABI of the B200-native (sm_100a) ionic-mpnn MPNN hot path.
+ *
+ * The reference (goalheart/ionic-mpnn) has no native interface: the path sits behind the Keras
+ * Layer protocol of models/layers.py.  Each entry point below names the reference code it
+ * replaces (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes binding
+ * a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns int: 0 = OK, >0 = a cudaError_t, <0 = IMP_ERR_* (argument / shape);
+ *     imp_last_error_string() describes the last failure on the calling thread.
+ *   - no allocation and no exceptions cross the boundary: the caller owns every buffer and passes raw
+ *     pointers + sizes.  "d_" = device pointer, "h_" = host pointer.
+ *   - kernels are enqueue-only on `stream` (a cudaStream_t passed as void*); no hidden synchronisation;
+ *     re-entrant across streams.  The device is the caller's current device.
+ *   - float tensors are row-major fp32 unless a name says bf16; index tensors are int32.
+ *   - atoms of a batch are tower-major (all cation atoms, then all anion atoms); `n_cat_atoms` splits
+ *     them.  Per-tower weights are passed as two pointers / two structs, [0] = cation, [1] = anion
+ *     (the reference instantiates separate layers per tower and step: train_viscosity.py:176-189).
+ */
+#ifndef IMP_B200_H
+#define IMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMP_VERSION 100
+
+#define IMP_ERR_ARG (-1)         /* null pointer / negative size / inconsistent sizes   */
+#define IMP_ERR_DIM (-2)         /* atom_dim / fp / mix size not supported by the kernels */
+#define IMP_ERR_INDEX (-3)       /* edge endpoint or id out of range (host packer)       */
+#define IMP_ERR_CAPACITY (-4)    /* caller-provided output capacity too small            */
+#define IMP_ERR_UNSUPPORTED (-5) /* needs sm_100a / feature not built                     */
+
+#define IMP_TILE_M 128 /* row tile of the bond-bucketed message GEMM */
+
+int imp_version(void);
+const char* imp_last_error_string(void);
+/* 1 if the current device is sm_100 (B200); the tcgen05 entry points refuse to run otherwise. */
+int imp_device_is_sm100(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph batch.  Replaces the padded tensors of build_inputs (train_viscosity.py:291-314):
+ * pad_sequences_1d (:52-59) + preprocess_edges_and_bonds (:76-110) + the masks applied later in
+ * BondMatrixMessage (models/layers.py:114-115) and Reduce (models/layers.py:74-76).
+ * Bit-exact specification: oracle/ref_pack.py.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_ions;           /* = number of pairs                                              */
+  const int32_t* atom_ptr;  /* [n_ions+1] offsets into atom_ids                               */
+  const int32_t* atom_ids;  /* vocabulary ids                                                  */
+  const int32_t* edge_ptr;  /* [n_ions+1] offsets into edge_src / edge_dst / bond_ids          */
+  const int32_t* edge_src;  /* ion-local, 0-based (src/featurize.py:60-63 emits both directions) */
+  const int32_t* edge_dst;
+  const int32_t* bond_ids;
+} imp_ions_t;
+
+typedef struct {
+  int32_t n_pairs;
+  int32_t n_atoms;     /* N: atoms of both towers                               */
+  int32_t n_cat_atoms; /* atoms [0, n_cat_atoms) belong to the cation tower     */
+  int32_t n_unique;    /* Eu: unique live (dst, bond, src) entries              */
+  int32_t n_edges;     /* E: live entries counted with multiplicity */
+  int32_t bond_vocab;  /* V_b (embedding rows, incl. the padding row 0)         */
+  int32_t* mol_ptr;     /* [2*n_pairs+1]                                         */
+  int32_t* atom_id;     /* [N] shifted ids; id 0 = "not pooled" (models/layers.py:163) */
+  int32_t* row_ptr;     /* [N+1] CSR over destination atoms                      */
+  int32_t* col_src;     /* [Eu] global source atom; rows sorted by (bond, src)   */
+  int32_t* edge_bm;     /* [Eu] bond id | multiplicity << 16                     */
+  int32_t* bucket_ptr;  /* [2*V_b+1] entries grouped by (tower, bond)            */
+  int32_t* bucket_perm; /* [Eu] entry indices in bucket order (stable)           */
+} imp_graph_t;
+
+/* flags for imp_pack_host */
+#define IMP_PACK_DOUBLE_EDGES 1 /* append the reverse of every entry (train_viscosity.py:87-91)      */
+#define IMP_PACK_SHIFT_IDS 2    /* +1 on atom and bond ids (train_viscosity.py:255-262)             */
+
+/* Host packer.  `out` arrays are caller-allocated: mol_ptr[2P+1], atom_id[N], row_ptr[N+1],
+ * bucket_ptr[2*V_b+1], and col_src / edge_bm / bucket_perm with capacity `edge_capacity` entries
+ * (an upper bound is the number of input entries, doubled when IMP_PACK_DOUBLE_EDGES).  max_edges < 0
+ * disables the reference's truncation to 2*max_edges entries per ion.  Counts are returned in `out`. */
+int imp_pack_host(const imp_ions_t* cation, const imp_ions_t* anion, int32_t bond_vocab, int32_t max_edges,
+                  int32_t flags, int32_t edge_capacity, imp_graph_t* out, int32_t n_threads);
+
+/* Benchmark-sized synthetic ions (recipe of SURVEY 8d; splitmix64 stream, see synth.py).  Two-phase:
+ * call with all output pointers NULL to get *n_atoms / *n_entries, then again with buffers. */
+int imp_synth_ions(uint64_t seed, int32_t n_ions, int32_t n_min, int32_t n_max, int32_t atom_types,
+                   int32_t bond_types, int32_t skewed, int32_t* atom_ptr, int32_t* atom_ids, int32_t* edge_ptr,
+                   int32_t* edge_src, int32_t* edge_dst, int32_t* bond_ids, int64_t* n_atoms, int64_t* n_entries);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  Embedding(atom)                        train_viscosity.py:163,171 ; train_melting_point.py:149,157
+ *     d_h0[v,:] = d_atom_emb[atom_id[v],:]
+ * ------------------------------------------------------------------------------------------- */
+int imp_embed_atoms(const float* d_atom_emb, int32_t atom_vocab, const int32_t* d_atom_id, int32_t n_atoms,
+                    int32_t d, float* d_h0, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  bond-matrix table.  Replaces Embedding(bond) + the per-edge tf.tensordot of
+ *     BondMatrixMessage.call (models/layers.py:108): table[v,l,m] = sum_k bond_emb[v,k] * W[k,l,m],
+ *     once per (tower, step) instead of once per padded edge.  `n_tables` weight tensors are processed
+ *     in one launch.  Outputs (either may be NULL):
+ *       d_table[i]     [V_b, d, d]  row-major, A[l,m] as in the reference
+ *       d_table_il[i]  [V_b, d/4, d, 4]  "lane-interleaved" copy read by imp_message_agg
+ * ------------------------------------------------------------------------------------------- */
+#define IMP_MAX_TABLES 32
+int imp_bond_table(const float* d_bond_emb, int32_t bond_vocab, int32_t bond_dim, int32_t d, int32_t n_tables,
+                   const float* const* h_W /* host array of n_tables device pointers [K,d,d] */,
+                   float* const* h_table, float* const* h_table_il, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3+K4 fused  BondMatrixMessage o Reduce (models/layers.py:100-117 + :57-83; the fused signature of
+ *     models/bond_matrix_message.py:37-65):  agg[v] = sum_{e in row v} mult_e * table[bond_e] @ h[src_e]
+ *     Deterministic (fixed CSR order), no message tensor is materialised.
+ * ------------------------------------------------------------------------------------------- */
+int imp_message_agg(const imp_graph_t* g /* host struct, device arrays */, const float* d_h, int32_t d,
+                    const float* d_table_il_cat, const float* d_table_il_an, float* d_agg, void* stream);
+
+/* K3  BondMatrixMessage.call (models/layers.py:100-117): per-entry messages in CSR order,
+ *     msg[e] = mult_e * table[bond_e] @ h[src_e], computed bucket by bucket (tower, bond). */
+int imp_edge_messages(const imp_graph_t* g, const float* d_h, int32_t d, const float* d_table_cat,
+                      const float* d_table_an, float* d_msg /* [Eu, d] */, void* stream);
+
+/* K4  Reduce.call (models/layers.py:57-83): agg[v] = sum of msg rows row_ptr[v]..row_ptr[v+1]. */
+int imp_segment_sum(const imp_graph_t* g, const float* d_msg, int32_t d, float* d_agg, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5  GatedUpdate.call (models/layers.py:142-156): z, r gates, candidate, blend, LayerNormalization
+ *     (eps = 1e-3, biased variance), residual.  Dense kernels are (2d, d): rows [0,d) multiply h (or
+ *     r*h), rows [d,2d) multiply agg (concat order, models/layers.py:144,150).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float *Wz, *bz, *Wr, *br, *Wh, *bh, *gamma, *beta;
+} imp_gru_weights_t;
+
+int imp_gated_update(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
+                     const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_h_out,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K6  GlobalSumPool (models/layers.py:161-164) + Dense(fp, relu) (train_viscosity.py:189) +
+ *     Dense(mix, relu) x2 + AddTwoTensors (:197-201) + head:
+ *       viscosity   Dense(3) -> A, B = clip(softplus,0,20), C = clip(softplus,0.1,50),
+ *                   log_eta = A + B / (T/100 + C + 1e-6)      (:204-214, models/layers.py:10-42)
+ *       melting pt  Dense(fp2, relu) -> Dense(1)               (train_melting_point.py:191-198)
+ * ------------------------------------------------------------------------------------------- */
+/* GlobalSumPool.call alone (models/layers.py:161-164): out[m,:] = sum of h rows of molecule m whose
+ * atom_id > 0.  `n_mols` molecules delimited by d_mol_ptr[n_mols+1]. */
+int imp_global_sum_pool(const int32_t* d_mol_ptr, const int32_t* d_atom_id, int32_t n_mols, const float* d_h, int32_t d,
+                        float* d_out /* [n_mols, d] */, void* stream);
+
+typedef struct {
+  const float *W_fp, *b_fp;   /* [d, fp], [fp]   */
+  const float *W_mix, *b_mix; /* [fp, mix], [mix] */
+} imp_readout_weights_t;
+
+int imp_pool_head_visc(const imp_graph_t* g, const float* d_h, int32_t d, int32_t fp, int32_t mix,
+                       const imp_readout_weights_t* w_cat, const imp_readout_weights_t* w_an,
+                       const float* d_W_head /* [mix,3] */, const float* d_b_head /* [3] */,
+                       const float* d_T /* [P] kelvin */, float* d_out /* [P] */,
+                       float* d_aux /* optional [P, 2*d + 2*fp + mix + 3]: pools, fps, mixed, (A,B,C) */,
+                       void* stream);
+
+int imp_pool_head_mp(const imp_graph_t* g, const float* d_h, int32_t d, int32_t fp, int32_t mix, int32_t fp2,
+                     const imp_readout_weights_t* w_cat, const imp_readout_weights_t* w_an,
+                     const float* d_W1 /* [mix,fp2] */, const float* d_b1, const float* d_W2 /* [fp2,1] */,
+                     const float* d_b2, float* d_out /* [P] */, float* d_aux /* optional, as above w/o (A,B,C) */,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMP_B200_H */

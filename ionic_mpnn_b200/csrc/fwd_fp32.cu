@@ -1,0 +1,629 @@
+// fp32 SIMT forward kernels of the MPNN hot path (the 1e-5 parity path).
+//
+//   K1 embed_atoms        Embedding(atom)                       train_viscosity.py:163,171
+//   K2 bond_table         Embedding(bond) + tf.tensordot        models/layers.py:108
+//   K3+K4 message_agg     BondMatrixMessage o Reduce (fused)    models/layers.py:100-117, 57-83
+//   K3 edge_messages      BondMatrixMessage                     models/layers.py:100-117
+//   K4 segment_sum        Reduce                                models/layers.py:57-83
+//   K5 gated_update       GatedUpdate                           models/layers.py:142-156
+//   K6 pool_head          GlobalSumPool + Dense/mix/head        models/layers.py:161-164, 10-42;
+//                                                               train_viscosity.py:189-214
+//
+// All arithmetic is plain fp32 FMA with full-precision expf / tanhf / sqrtf so that the result stays
+// within 1e-5 of the fp64 oracle.  Summation orders are fixed (CSR order), so every kernel is
+// deterministic run to run -- unlike the reference's scatter_nd on a GPU.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace imp {
+
+// ----------------------------------------------------------------------------------------- K1
+__global__ void embed_atoms_kernel(const float4* __restrict__ emb, const int* __restrict__ atom_id,
+                                   int64_t total4, int d4, int atom_vocab, float4* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  int64_t v = i / d4;
+  int c = (int)(i - v * d4);
+  int id = atom_id[v];
+  id = min(max(id, 0), atom_vocab - 1);  // ids are validated by the packer; never read out of bounds
+  out[i] = emb[(int64_t)id * d4 + c];
+}
+
+// ----------------------------------------------------------------------------------------- K2
+// table[t][v][j] = sum_k bond_emb[v][k] * W_t[k][j],  j = l*d + m in [0, d*d).
+// One CTA: all V_b rows x 64 consecutive columns of one table; bond_emb chunk + W chunk staged in smem.
+struct TablePtrs {
+  const float* W[IMP_MAX_TABLES];
+  float* table[IMP_MAX_TABLES];
+  float* table_il[IMP_MAX_TABLES];
+};
+
+constexpr int K2_COLS = 64;
+constexpr int K2_KC = 32;
+constexpr int K2_MAXV = 128;  // bond vocabulary rows handled per CTA pass
+
+__global__ void __launch_bounds__(256) bond_table_kernel(const float* __restrict__ bond_emb, int V, int K, int d,
+                                                          TablePtrs ptrs) {
+  __shared__ float sA[K2_MAXV][K2_KC + 1];
+  __shared__ float sB[K2_KC][K2_COLS];
+  const int t = blockIdx.y;
+  const int col0 = blockIdx.x * K2_COLS;
+  const int dd = d * d;
+  const float* __restrict__ W = ptrs.W[t];
+  const int tx = threadIdx.x % K2_COLS;  // column within the tile
+  const int ty = threadIdx.x / K2_COLS;  // 0..3, row phase
+  for (int v0 = 0; v0 < V; v0 += K2_MAXV) {
+    const int nv = min(K2_MAXV, V - v0);
+    float acc[K2_MAXV / 4];
+#pragma unroll
+    for (int i = 0; i < K2_MAXV / 4; ++i) acc[i] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += K2_KC) {
+      const int nk = min(K2_KC, K - k0);
+      for (int i = threadIdx.x; i < nv * K2_KC; i += blockDim.x) {
+        int r = i / K2_KC, c = i % K2_KC;
+        sA[r][c] = c < nk ? bond_emb[(int64_t)(v0 + r) * K + k0 + c] : 0.f;
+      }
+      for (int i = threadIdx.x; i < K2_KC * K2_COLS; i += blockDim.x) {
+        int r = i / K2_COLS, c = i % K2_COLS;
+        sB[r][c] = (r < nk && col0 + c < dd) ? W[(int64_t)(k0 + r) * dd + col0 + c] : 0.f;
+      }
+      __syncthreads();
+      for (int k = 0; k < K2_KC; ++k) {
+        float b = sB[k][tx];
+#pragma unroll
+        for (int i = 0; i < K2_MAXV / 4; ++i) acc[i] = fmaf(sA[ty + 4 * i][k], b, acc[i]);
+      }
+      __syncthreads();
+    }
+    const int j = col0 + tx;
+    if (j < dd) {
+      const int l = j / d, m = j % d;
+#pragma unroll
+      for (int i = 0; i < K2_MAXV / 4; ++i) {
+        int v = v0 + ty + 4 * i;
+        if (ty + 4 * i < nv) {
+          if (ptrs.table[t]) ptrs.table[t][(int64_t)v * dd + j] = acc[i];
+          if (ptrs.table_il[t])  // [v][m/4][l][m%4]
+            ptrs.table_il[t][(((int64_t)v * (d / 4) + m / 4) * d + l) * 4 + (m & 3)] = acc[i];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ K3 + K4
+// One thread per (destination atom v, output component l).  The table is read in the lane-interleaved
+// layout so that the D threads of a destination read consecutive float4s; h[src] is a warp-uniform
+// (broadcast) 16-byte read.
+template <int D>
+__device__ __forceinline__ float bond_matvec_row(const float4* __restrict__ trow, const float4* __restrict__ hrow) {
+  float s = 0.f;
+#pragma unroll
+  for (int m4 = 0; m4 < D / 4; ++m4) {
+    float4 tv = __ldg(trow + m4 * D);
+    float4 hv = __ldg(hrow + m4);
+    s = fmaf(tv.x, hv.x, s);
+    s = fmaf(tv.y, hv.y, s);
+    s = fmaf(tv.z, hv.z, s);
+    s = fmaf(tv.w, hv.w, s);
+  }
+  return s;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) message_agg_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_src,
+                                                           const int* __restrict__ edge_bm, const float* __restrict__ h,
+                                                           const float* __restrict__ tab_cat,
+                                                           const float* __restrict__ tab_an, int n_atoms, int n_cat,
+                                                           float* __restrict__ agg) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int v = (int)(t / D), l = (int)(t % D);
+  if (v >= n_atoms) return;
+  const float* tab = v < n_cat ? tab_cat : tab_an;
+  float acc = 0.f;
+  const int e1 = row_ptr[v + 1];
+  for (int e = row_ptr[v]; e < e1; ++e) {
+    const int src = col_src[e];
+    const int bm = edge_bm[e];
+    const float4* trow = reinterpret_cast<const float4*>(tab + (int64_t)(bm & 0xFFFF) * D * D) + l;
+    const float4* hrow = reinterpret_cast<const float4*>(h + (int64_t)src * D);
+    acc = fmaf((float)(bm >> 16), bond_matvec_row<D>(trow, hrow), acc);
+  }
+  agg[(int64_t)v * D + l] = acc;
+}
+
+// K3 alone: messages bucket by bucket, written at the entry's CSR position.  Uses the row-major table.
+template <int D>
+__global__ void __launch_bounds__(256) edge_messages_kernel(const int* __restrict__ bucket_perm, const int* __restrict__ col_src,
+                                                             const int* __restrict__ edge_bm, const float* __restrict__ h,
+                                                             const float* __restrict__ tab_cat,
+                                                             const float* __restrict__ tab_an, int n_unique,
+                                                             const int* __restrict__ first_anion_slot_ptr,
+                                                             float* __restrict__ msg) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int i = (int)(t / D), l = (int)(t % D);
+  if (i >= n_unique) return;
+  const int first_anion_slot = __ldg(first_anion_slot_ptr);  // = bucket_ptr[V_b]: cation buckets come first
+  const int e = bucket_perm[i];
+  const int bm = edge_bm[e];
+  const float* tab = (i < first_anion_slot ? tab_cat : tab_an) + (int64_t)(bm & 0xFFFF) * D * D + (int64_t)l * D;
+  const float4* trow = reinterpret_cast<const float4*>(tab);
+  const float4* hrow = reinterpret_cast<const float4*>(h + (int64_t)col_src[e] * D);
+  float s = 0.f;
+#pragma unroll
+  for (int m4 = 0; m4 < D / 4; ++m4) {
+    float4 tv = __ldg(trow + m4);
+    float4 hv = __ldg(hrow + m4);
+    s = fmaf(tv.x, hv.x, s);
+    s = fmaf(tv.y, hv.y, s);
+    s = fmaf(tv.z, hv.z, s);
+    s = fmaf(tv.w, hv.w, s);
+  }
+  msg[(int64_t)e * D + l] = (float)(bm >> 16) * s;
+}
+
+// K4: contiguous segment sum over CSR rows, one thread per (v, float4 column).
+__global__ void segment_sum_kernel(const int* __restrict__ row_ptr, const float4* __restrict__ msg, int n_atoms, int d4,
+                                   float4* __restrict__ agg) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int v = (int)(t / d4), c = (int)(t % d4);
+  if (v >= n_atoms) return;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int e1 = row_ptr[v + 1];
+  for (int e = row_ptr[v]; e < e1; ++e) {
+    float4 m = __ldg(msg + (int64_t)e * d4 + c);
+    a.x += m.x;
+    a.y += m.y;
+    a.z += m.z;
+    a.w += m.w;
+  }
+  agg[(int64_t)v * d4 + c] = a;
+}
+
+// ----------------------------------------------------------------------------------------- K5
+// One thread per atom, 128 atoms per CTA, one tower per CTA.  The three (2D x D) kernels live in shared
+// memory and are read as warp-uniform float4 broadcasts; the thread's own h / agg / r*h rows sit in
+// padded (conflict-free) shared tiles.  All gate math, LayerNorm and the residual are thread-local.
+constexpr int K5_TILE = 128;
+
+template <int D>
+struct K5Smem {
+  float Wz[2 * D * D], Wr[2 * D * D], Wh[2 * D * D];
+  float bz[D], br[D], bh[D], gamma[D], beta[D];
+  float hs[K5_TILE][D + 1], as[K5_TILE][D + 1], xs[K5_TILE][D + 1];
+};
+
+template <int D>
+__device__ __forceinline__ void k5_dense(float (&acc)[D], const float* __restrict__ W /* smem [2D][D] */,
+                                         const float* __restrict__ bias, const float* __restrict__ x0 /* own row, D */,
+                                         const float* __restrict__ x1 /* own row, D */) {
+#pragma unroll
+  for (int j = 0; j < D; ++j) acc[j] = bias[j];
+#pragma unroll 4
+  for (int k = 0; k < D; ++k) {
+    const float x = x0[k];
+    const float4* w = reinterpret_cast<const float4*>(W + k * D);
+#pragma unroll
+    for (int j4 = 0; j4 < D / 4; ++j4) {
+      float4 wv = w[j4];
+      acc[4 * j4 + 0] = fmaf(x, wv.x, acc[4 * j4 + 0]);
+      acc[4 * j4 + 1] = fmaf(x, wv.y, acc[4 * j4 + 1]);
+      acc[4 * j4 + 2] = fmaf(x, wv.z, acc[4 * j4 + 2]);
+      acc[4 * j4 + 3] = fmaf(x, wv.w, acc[4 * j4 + 3]);
+    }
+  }
+#pragma unroll 4
+  for (int k = 0; k < D; ++k) {
+    const float x = x1[k];
+    const float4* w = reinterpret_cast<const float4*>(W + (D + k) * D);
+#pragma unroll
+    for (int j4 = 0; j4 < D / 4; ++j4) {
+      float4 wv = w[j4];
+      acc[4 * j4 + 0] = fmaf(x, wv.x, acc[4 * j4 + 0]);
+      acc[4 * j4 + 1] = fmaf(x, wv.y, acc[4 * j4 + 1]);
+      acc[4 * j4 + 2] = fmaf(x, wv.z, acc[4 * j4 + 2]);
+      acc[4 * j4 + 3] = fmaf(x, wv.w, acc[4 * j4 + 3]);
+    }
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int D>
+__global__ void __launch_bounds__(K5_TILE) gated_update_kernel(const float* __restrict__ h, const float* __restrict__ agg,
+                                                               int n_atoms, int n_cat, int tiles_cat,
+                                                               imp_gru_weights_t wc, imp_gru_weights_t wa, float eps,
+                                                               float* __restrict__ h_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  K5Smem<D>& s = *reinterpret_cast<K5Smem<D>*>(smem_raw);
+  const bool is_cat = (int)blockIdx.x < tiles_cat;
+  const imp_gru_weights_t& w = is_cat ? wc : wa;
+  const int a0 = is_cat ? blockIdx.x * K5_TILE : n_cat + (blockIdx.x - tiles_cat) * K5_TILE;
+  const int a_end = is_cat ? n_cat : n_atoms;
+  const int rows = min(K5_TILE, a_end - a0);
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < 2 * D * D / 4; i += K5_TILE) {
+    reinterpret_cast<float4*>(s.Wz)[i] = __ldg(reinterpret_cast<const float4*>(w.Wz) + i);
+    reinterpret_cast<float4*>(s.Wr)[i] = __ldg(reinterpret_cast<const float4*>(w.Wr) + i);
+    reinterpret_cast<float4*>(s.Wh)[i] = __ldg(reinterpret_cast<const float4*>(w.Wh) + i);
+  }
+  for (int i = tid; i < D; i += K5_TILE) {
+    s.bz[i] = w.bz[i];
+    s.br[i] = w.br[i];
+    s.bh[i] = w.bh[i];
+    s.gamma[i] = w.gamma[i];
+    s.beta[i] = w.beta[i];
+  }
+  // coalesced tile loads: consecutive threads read consecutive float4s of the [rows, D] slab
+  const float4* hg = reinterpret_cast<const float4*>(h + (int64_t)a0 * D);
+  const float4* ag = reinterpret_cast<const float4*>(agg + (int64_t)a0 * D);
+  for (int i = tid; i < rows * (D / 4); i += K5_TILE) {
+    const int r = i / (D / 4), c = (i % (D / 4)) * 4;
+    float4 hv = __ldg(hg + i), av = __ldg(ag + i);
+    s.hs[r][c] = hv.x, s.hs[r][c + 1] = hv.y, s.hs[r][c + 2] = hv.z, s.hs[r][c + 3] = hv.w;
+    s.as[r][c] = av.x, s.as[r][c + 1] = av.y, s.as[r][c + 2] = av.z, s.as[r][c + 3] = av.w;
+  }
+  __syncthreads();
+
+  if (tid < rows) {
+    float acc[D], g[D];
+    // r gate -> r * h into the xs tile (own row only; no cross-thread hazard)
+    k5_dense<D>(acc, s.Wr, s.br, s.hs[tid], s.as[tid]);
+#pragma unroll
+    for (int j = 0; j < D; ++j) s.xs[tid][j] = sigmoidf_precise(acc[j]) * s.hs[tid][j];
+    // candidate
+    k5_dense<D>(g, s.Wh, s.bh, s.xs[tid], s.as[tid]);
+#pragma unroll
+    for (int j = 0; j < D; ++j) g[j] = tanhf(g[j]);
+    // z gate and blend
+    k5_dense<D>(acc, s.Wz, s.bz, s.hs[tid], s.as[tid]);
+    float mean = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const float z = sigmoidf_precise(acc[j]);
+      const float hj = s.hs[tid][j];
+      g[j] = (1.0f - z) * hj + z * g[j];
+      mean += g[j];
+    }
+    mean *= (1.0f / D);
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const float c = g[j] - mean;
+      var = fmaf(c, c, var);
+    }
+    const float inv = 1.0f / sqrtf(var * (1.0f / D) + eps);
+#pragma unroll
+    for (int j = 0; j < D; ++j) s.xs[tid][j] = (g[j] - mean) * inv * s.gamma[j] + s.beta[j] + s.hs[tid][j];
+  }
+  __syncthreads();
+  float4* og = reinterpret_cast<float4*>(h_out + (int64_t)a0 * D);
+  for (int i = tid; i < rows * (D / 4); i += K5_TILE) {
+    const int r = i / (D / 4), c = (i % (D / 4)) * 4;
+    og[i] = make_float4(s.xs[r][c], s.xs[r][c + 1], s.xs[r][c + 2], s.xs[r][c + 3]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------- K6
+// One warp per ion pair.  Pool: lanes stride over feature columns (coalesced row reads).  The tiny dense
+// layers run out of per-warp shared scratch.  Readout weights are staged in shared memory per CTA.
+constexpr int K6_WARPS = 8;
+constexpr int K6_MAXV = 64;  // max of d, fp, mix, fp2
+
+struct K6Args {
+  const int* mol_ptr;
+  const int* atom_id;
+  const float* h;
+  int n_pairs, d, fp, mix, fp2;  // fp2 = 0 -> viscosity head
+  imp_readout_weights_t wc, wa;
+  const float *W1, *b1, *W2, *b2;  // viscosity: W1 = [mix,3] head, b1 = [3]; mp: W1 [mix,fp2], W2 [fp2,1]
+  const float* T;
+  float* out;
+  float* aux;
+};
+
+__device__ __forceinline__ float softplusf_precise(float x) {
+  return x > 0.f ? x + log1pf(expf(-x)) : log1pf(expf(x));
+}
+
+__device__ void k6_dense(const float* __restrict__ W /* smem [n_in][n_out] */, const float* __restrict__ b,
+                         const float* __restrict__ x /* smem [n_in] */, float* __restrict__ y, int n_in, int n_out,
+                         bool relu, int lane) {
+  for (int o = lane; o < n_out; o += 32) {
+    float a = b[o];
+    for (int k = 0; k < n_in; ++k) a = fmaf(x[k], W[k * n_out + o], a);
+    y[o] = relu ? fmaxf(a, 0.f) : a;
+  }
+  __syncwarp();
+}
+
+// GlobalSumPool alone: one warp per molecule.
+__global__ void global_sum_pool_kernel(const int* __restrict__ mol_ptr, const int* __restrict__ atom_id, int n_mols,
+                                       const float* __restrict__ h, int d, float* __restrict__ out) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (m >= n_mols) return;
+  const int v0 = mol_ptr[m], v1 = mol_ptr[m + 1];
+  for (int j = lane; j < d; j += 32) {
+    float sacc = 0.f;
+    for (int v = v0; v < v1; ++v)
+      if (atom_id[v] > 0) sacc += h[(int64_t)v * d + j];
+    out[(int64_t)m * d + j] = sacc;
+  }
+}
+
+__global__ void __launch_bounds__(K6_WARPS * 32) pool_head_kernel(K6Args a) {
+  extern __shared__ __align__(16) float sm[];
+  const int d = a.d, fp = a.fp, mix = a.mix, fp2 = a.fp2;
+  const int n_head_out = fp2 > 0 ? fp2 : 3;
+  // weight staging
+  float* Wfp[2] = {sm, sm + d * fp};
+  float* p = sm + 2 * d * fp;
+  float* bfp[2] = {p, p + fp};
+  p += 2 * fp;
+  float* Wmx[2] = {p, p + fp * mix};
+  p += 2 * fp * mix;
+  float* bmx[2] = {p, p + mix};
+  p += 2 * mix;
+  float* W1 = p;
+  p += mix * n_head_out;
+  float* b1 = p;
+  p += n_head_out;
+  float* W2 = p;
+  p += (fp2 > 0 ? fp2 : 0);
+  float* scratch = p + (threadIdx.x / 32) * (4 * K6_MAXV);
+  for (int t = 0; t < 2; ++t) {
+    const imp_readout_weights_t& w = t == 0 ? a.wc : a.wa;
+    for (int i = threadIdx.x; i < d * fp; i += blockDim.x) Wfp[t][i] = w.W_fp[i];
+    for (int i = threadIdx.x; i < fp; i += blockDim.x) bfp[t][i] = w.b_fp[i];
+    for (int i = threadIdx.x; i < fp * mix; i += blockDim.x) Wmx[t][i] = w.W_mix[i];
+    for (int i = threadIdx.x; i < mix; i += blockDim.x) bmx[t][i] = w.b_mix[i];
+  }
+  for (int i = threadIdx.x; i < mix * n_head_out; i += blockDim.x) W1[i] = a.W1[i];
+  for (int i = threadIdx.x; i < n_head_out; i += blockDim.x) b1[i] = a.b1[i];
+  if (fp2 > 0)
+    for (int i = threadIdx.x; i < fp2; i += blockDim.x) W2[i] = a.W2[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * K6_WARPS + (threadIdx.x >> 5);
+  const int n_warps = gridDim.x * K6_WARPS;
+  float* pool = scratch;             // [d]
+  float* v1 = scratch + K6_MAXV;     // [fp]
+  float* v2 = scratch + 2 * K6_MAXV; // [mix]
+  float* mixed = scratch + 3 * K6_MAXV;
+  const int aux_stride = 2 * d + 2 * fp + mix + (fp2 > 0 ? 0 : 3);
+  for (int pair = warp_global; pair < a.n_pairs; pair += n_warps) {
+    for (int t = 0; t < 2; ++t) {
+      const int m = t * a.n_pairs + pair;
+      const int v0 = a.mol_ptr[m], v1e = a.mol_ptr[m + 1];
+      for (int j = lane; j < d; j += 32) {
+        float sacc = 0.f;
+        for (int v = v0; v < v1e; ++v)
+          if (a.atom_id[v] > 0) sacc += a.h[(int64_t)v * d + j];  // models/layers.py:163 mask
+        pool[j] = sacc;
+      }
+      __syncwarp();
+      k6_dense(Wfp[t], bfp[t], pool, v1, d, fp, true, lane);
+      k6_dense(Wmx[t], bmx[t], v1, v2, fp, mix, true, lane);
+      for (int j = lane; j < mix; j += 32) mixed[j] = t == 0 ? v2[j] : mixed[j] + v2[j];
+      if (a.aux) {
+        float* ax = a.aux + (int64_t)pair * aux_stride;
+        for (int j = lane; j < d; j += 32) ax[t * d + j] = pool[j];
+        for (int j = lane; j < fp; j += 32) ax[2 * d + t * fp + j] = v1[j];
+      }
+      __syncwarp();
+    }
+    if (a.aux)
+      for (int j = lane; j < mix; j += 32) a.aux[(int64_t)pair * aux_stride + 2 * d + 2 * fp + j] = mixed[j];
+    if (fp2 == 0) {
+      k6_dense(W1, b1, mixed, v1, mix, 3, false, lane);
+      if (lane == 0) {
+        const float A = v1[0];
+        const float B = fminf(fmaxf(softplusf_precise(v1[1]), 0.0f), 20.0f);
+        const float C = fminf(fmaxf(softplusf_precise(v1[2]), 0.1f), 50.0f);
+        const float Ts = a.T[pair] / 100.0f;
+        a.out[pair] = A + B / (Ts + C + 1e-6f);
+        if (a.aux) {
+          float* ax = a.aux + (int64_t)pair * aux_stride + 2 * d + 2 * fp + mix;
+          ax[0] = A, ax[1] = B, ax[2] = C;
+        }
+      }
+    } else {
+      k6_dense(W1, b1, mixed, v1, mix, fp2, true, lane);
+      float part = 0.f;
+      for (int k = lane; k < fp2; k += 32) part = fmaf(v1[k], W2[k], part);
+      // fixed-order reduction: gather the 32 partials in lane order
+      float tot = 0.f;
+      for (int l = 0; l < 32; ++l) tot += __shfl_sync(0xffffffffu, part, l);
+      if (lane == 0) a.out[pair] = tot + a.b2[0];
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace imp
+
+// =========================================================================================== ABI
+using namespace imp;
+
+static bool dim_ok(int d) { return d == 8 || d == 16 || d == 32 || d == 64; }
+
+extern "C" int imp_embed_atoms(const float* d_atom_emb, int32_t atom_vocab, const int32_t* d_atom_id, int32_t n_atoms,
+                               int32_t d, float* d_h0, void* stream) {
+  IMP_REQUIRE(n_atoms >= 0 && atom_vocab > 0, IMP_ERR_ARG, "imp_embed_atoms: bad sizes");
+  IMP_REQUIRE(d > 0 && d % 4 == 0, IMP_ERR_DIM, "imp_embed_atoms: atom_dim %d must be a multiple of 4", d);
+  if (n_atoms == 0) return 0;
+  IMP_REQUIRE(d_atom_emb && d_atom_id && d_h0, IMP_ERR_ARG, "imp_embed_atoms: null pointer");
+  const int64_t total4 = (int64_t)n_atoms * (d / 4);
+  embed_atoms_kernel<<<(unsigned)ceil_div(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(d_atom_emb), d_atom_id, total4, d / 4, atom_vocab, reinterpret_cast<float4*>(d_h0));
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int imp_bond_table(const float* d_bond_emb, int32_t bond_vocab, int32_t bond_dim, int32_t d, int32_t n_tables,
+                              const float* const* h_W, float* const* h_table, float* const* h_table_il, void* stream) {
+  IMP_REQUIRE(d_bond_emb && h_W && (h_table || h_table_il), IMP_ERR_ARG, "imp_bond_table: null pointer");
+  IMP_REQUIRE(n_tables > 0 && n_tables <= IMP_MAX_TABLES, IMP_ERR_ARG, "imp_bond_table: n_tables %d not in 1..%d",
+              n_tables, IMP_MAX_TABLES);
+  IMP_REQUIRE(bond_vocab > 0 && bond_dim > 0, IMP_ERR_ARG, "imp_bond_table: bad sizes");
+  IMP_REQUIRE(d > 0 && d % 4 == 0, IMP_ERR_DIM, "imp_bond_table: atom_dim %d must be a multiple of 4", d);
+  TablePtrs p;
+  for (int i = 0; i < IMP_MAX_TABLES; ++i) {
+    p.W[i] = i < n_tables ? h_W[i] : nullptr;
+    p.table[i] = (i < n_tables && h_table) ? h_table[i] : nullptr;
+    p.table_il[i] = (i < n_tables && h_table_il) ? h_table_il[i] : nullptr;
+    IMP_REQUIRE(i >= n_tables || p.W[i], IMP_ERR_ARG, "imp_bond_table: W[%d] is null", i);
+  }
+  dim3 grid((unsigned)ceil_div((int64_t)d * d, K2_COLS), (unsigned)n_tables);
+  bond_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_bond_emb, bond_vocab, bond_dim, d, p);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+static int check_graph(const imp_graph_t* g, const char* who) {
+  IMP_REQUIRE(g, IMP_ERR_ARG, "%s: graph is null", who);
+  IMP_REQUIRE(g->n_atoms >= 0 && g->n_unique >= 0 && g->n_pairs >= 0 && g->n_cat_atoms >= 0 &&
+                  g->n_cat_atoms <= g->n_atoms && g->bond_vocab > 0,
+              IMP_ERR_ARG, "%s: inconsistent graph sizes", who);
+  return 0;
+}
+
+#define IMP_DISPATCH_D(d, CALL)            \
+  switch (d) {                             \
+    case 8: { constexpr int D = 8; CALL; } break;   \
+    case 16: { constexpr int D = 16; CALL; } break; \
+    case 32: { constexpr int D = 32; CALL; } break; \
+    case 64: { constexpr int D = 64; CALL; } break; \
+    default: break;                        \
+  }
+
+extern "C" int imp_message_agg(const imp_graph_t* g, const float* d_h, int32_t d, const float* d_table_il_cat,
+                               const float* d_table_il_an, float* d_agg, void* stream) {
+  if (int rc = check_graph(g, "imp_message_agg")) return rc;
+  IMP_REQUIRE(dim_ok(d), IMP_ERR_DIM, "imp_message_agg: atom_dim %d not in {8,16,32,64} (fp32 path)", d);
+  if (g->n_atoms == 0) return 0;
+  IMP_REQUIRE(d_h && d_table_il_cat && d_table_il_an && d_agg && g->row_ptr && (g->n_unique == 0 || (g->col_src && g->edge_bm)),
+              IMP_ERR_ARG, "imp_message_agg: null pointer");
+  const int64_t threads = (int64_t)g->n_atoms * d;
+  const unsigned blocks = (unsigned)ceil_div(threads, 256);
+  IMP_DISPATCH_D(d, (message_agg_kernel<D><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                        g->row_ptr, g->col_src, g->edge_bm, d_h, d_table_il_cat, d_table_il_an, g->n_atoms,
+                        g->n_cat_atoms, d_agg)));
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int imp_edge_messages(const imp_graph_t* g, const float* d_h, int32_t d, const float* d_table_cat,
+                                 const float* d_table_an, float* d_msg, void* stream) {
+  if (int rc = check_graph(g, "imp_edge_messages")) return rc;
+  IMP_REQUIRE(dim_ok(d), IMP_ERR_DIM, "imp_edge_messages: atom_dim %d not in {8,16,32,64} (fp32 path)", d);
+  if (g->n_unique == 0) return 0;
+  IMP_REQUIRE(d_h && d_table_cat && d_table_an && d_msg && g->col_src && g->edge_bm && g->bucket_perm && g->bucket_ptr, IMP_ERR_ARG,
+              "imp_edge_messages: null pointer");
+  const int64_t threads = (int64_t)g->n_unique * d;
+  const unsigned blocks = (unsigned)ceil_div(threads, 256);
+  IMP_DISPATCH_D(d, (edge_messages_kernel<D><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                        g->bucket_perm, g->col_src, g->edge_bm, d_h, d_table_cat, d_table_an, g->n_unique,
+                        g->bucket_ptr + g->bond_vocab, d_msg)));
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int imp_segment_sum(const imp_graph_t* g, const float* d_msg, int32_t d, float* d_agg, void* stream) {
+  if (int rc = check_graph(g, "imp_segment_sum")) return rc;
+  IMP_REQUIRE(d > 0 && d % 4 == 0, IMP_ERR_DIM, "imp_segment_sum: atom_dim %d must be a multiple of 4", d);
+  if (g->n_atoms == 0) return 0;
+  IMP_REQUIRE(d_agg && g->row_ptr && (g->n_unique == 0 || d_msg), IMP_ERR_ARG, "imp_segment_sum: null pointer");
+  const int64_t threads = (int64_t)g->n_atoms * (d / 4);
+  segment_sum_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+      g->row_ptr, reinterpret_cast<const float4*>(d_msg), g->n_atoms, d / 4, reinterpret_cast<float4*>(d_agg));
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int D>
+static int launch_k5(const float* h, const float* agg, int n_atoms, int n_cat, const imp_gru_weights_t* wc,
+                     const imp_gru_weights_t* wa, float eps, float* out, cudaStream_t st) {
+  const int tiles_cat = (int)ceil_div(n_cat, K5_TILE), tiles_an = (int)ceil_div(n_atoms - n_cat, K5_TILE);
+  const size_t smem = sizeof(K5Smem<D>);
+  IMP_CUDA(cudaFuncSetAttribute(gated_update_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gated_update_kernel<D><<<tiles_cat + tiles_an, K5_TILE, smem, st>>>(h, agg, n_atoms, n_cat, tiles_cat, *wc, *wa, eps, out);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+static bool gru_ok(const imp_gru_weights_t* w) {
+  return w && w->Wz && w->bz && w->Wr && w->br && w->Wh && w->bh && w->gamma && w->beta;
+}
+
+extern "C" int imp_gated_update(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
+                                const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_h_out,
+                                void* stream) {
+  IMP_REQUIRE(n_atoms >= 0 && n_cat_atoms >= 0 && n_cat_atoms <= n_atoms, IMP_ERR_ARG, "imp_gated_update: bad sizes");
+  IMP_REQUIRE(dim_ok(d), IMP_ERR_DIM, "imp_gated_update: atom_dim %d not in {8,16,32,64} (fp32 path)", d);
+  if (n_atoms == 0) return 0;
+  IMP_REQUIRE(d_h && d_agg && d_h_out && gru_ok(w_cat) && gru_ok(w_an), IMP_ERR_ARG, "imp_gated_update: null pointer");
+  int rc = IMP_ERR_DIM;
+  IMP_DISPATCH_D(d, rc = launch_k5<D>(d_h, d_agg, n_atoms, n_cat_atoms, w_cat, w_an, eps, d_h_out, (cudaStream_t)stream));
+  return rc;
+}
+
+static int launch_k6(const imp_graph_t* g, const float* d_h, int d, int fp, int mix, int fp2,
+                     const imp_readout_weights_t* wc, const imp_readout_weights_t* wa, const float* W1, const float* b1,
+                     const float* W2, const float* b2, const float* T, float* out, float* aux, void* stream,
+                     const char* who) {
+  if (int rc = check_graph(g, who)) return rc;
+  IMP_REQUIRE(d > 0 && fp > 0 && mix > 0 && d <= K6_MAXV && fp <= K6_MAXV && mix <= K6_MAXV && fp2 <= K6_MAXV, IMP_ERR_DIM,
+              "%s: d/fp/mix/fp2 = %d/%d/%d/%d must be in 1..%d", who, d, fp, mix, fp2, K6_MAXV);
+  if (g->n_pairs == 0) return 0;
+  IMP_REQUIRE(d_h && out && g->mol_ptr && g->atom_id && wc && wa && wc->W_fp && wc->b_fp && wc->W_mix && wc->b_mix &&
+                  wa->W_fp && wa->b_fp && wa->W_mix && wa->b_mix && W1 && b1,
+              IMP_ERR_ARG, "%s: null pointer", who);
+  K6Args a;
+  a.mol_ptr = g->mol_ptr, a.atom_id = g->atom_id, a.h = d_h, a.n_pairs = g->n_pairs;
+  a.d = d, a.fp = fp, a.mix = mix, a.fp2 = fp2, a.wc = *wc, a.wa = *wa;
+  a.W1 = W1, a.b1 = b1, a.W2 = W2, a.b2 = b2, a.T = T, a.out = out, a.aux = aux;
+  const int n_head_out = fp2 > 0 ? fp2 : 3;
+  const size_t smem = sizeof(float) * (2 * d * fp + 2 * fp + 2 * fp * mix + 2 * mix + mix * n_head_out + n_head_out +
+                                       (fp2 > 0 ? fp2 : 0) + K6_WARPS * 4 * K6_MAXV);
+  IMP_CUDA(cudaFuncSetAttribute(pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  IMP_REQUIRE(smem <= 96 * 1024, IMP_ERR_DIM, "%s: readout weights need %zu B of shared memory", who, smem);
+  int blocks = (int)ceil_div(g->n_pairs, K6_WARPS);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pool_head_kernel<<<blocks, K6_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int imp_global_sum_pool(const int32_t* d_mol_ptr, const int32_t* d_atom_id, int32_t n_mols, const float* d_h,
+                                   int32_t d, float* d_out, void* stream) {
+  IMP_REQUIRE(n_mols >= 0 && d > 0, IMP_ERR_ARG, "imp_global_sum_pool: bad sizes");
+  if (n_mols == 0) return 0;
+  IMP_REQUIRE(d_mol_ptr && d_atom_id && d_h && d_out, IMP_ERR_ARG, "imp_global_sum_pool: null pointer");
+  global_sum_pool_kernel<<<(unsigned)ceil_div(n_mols, 8), 256, 0, (cudaStream_t)stream>>>(d_mol_ptr, d_atom_id, n_mols, d_h,
+                                                                                          d, d_out);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int imp_pool_head_visc(const imp_graph_t* g, const float* d_h, int32_t d, int32_t fp, int32_t mix,
+                                  const imp_readout_weights_t* w_cat, const imp_readout_weights_t* w_an,
+                                  const float* d_W_head, const float* d_b_head, const float* d_T, float* d_out,
+                                  float* d_aux, void* stream) {
+  IMP_REQUIRE(d_T, IMP_ERR_ARG, "imp_pool_head_visc: temperature is null");
+  return launch_k6(g, d_h, d, fp, mix, 0, w_cat, w_an, d_W_head, d_b_head, nullptr, nullptr, d_T, d_out, d_aux, stream,
+                   "imp_pool_head_visc");
+}
+
+extern "C" int imp_pool_head_mp(const imp_graph_t* g, const float* d_h, int32_t d, int32_t fp, int32_t mix, int32_t fp2,
+                                const imp_readout_weights_t* w_cat, const imp_readout_weights_t* w_an, const float* d_W1,
+                                const float* d_b1, const float* d_W2, const float* d_b2, float* d_out, float* d_aux,
+                                void* stream) {
+  IMP_REQUIRE(fp2 > 0 && d_W2 && d_b2, IMP_ERR_ARG, "imp_pool_head_mp: head weights missing");
+  return launch_k6(g, d_h, d, fp, mix, fp2, w_cat, w_an, d_W1, d_b1, d_W2, d_b2, nullptr, d_out, d_aux, stream,
+                   "imp_pool_head_mp");
+}

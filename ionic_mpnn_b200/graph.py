@@ -1,0 +1,190 @@
+"""Packed CSR graph batches -- the replacement for the reference's padded inputs.
+
+The reference pads every ion to data-set maxima in ``build_inputs`` (train_viscosity.py:291-314:
+``pad_sequences_1d`` :52-59, ``preprocess_edges_and_bonds`` :76-110) and masks padding later
+(models/layers.py:74-76,114-115,163).  ``PackedGraphBatch`` holds the same information without padding;
+its exact layout is specified by ``oracle/ref_pack.py`` and produced here by ``imp_pack_host`` (C++).
+
+Three ways in, all ending in the same packer:
+  * ``pack_records``  -- list of dicts in the ``src/dataset.py:15-20,51-62`` schema (ids unshifted)
+  * ``pack_padded``   -- the reference's own padded input dict (drop-in for ``model.predict(x)``)
+  * ``pack_flat``     -- flat ragged arrays (``FlatIons``), what ``synth_flat`` generates for benchmarks
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+I32 = np.int32
+
+
+@dataclass
+class FlatIons:
+    """One tower as ragged int32 arrays (the flat equivalent of the record lists)."""
+    atom_ptr: np.ndarray
+    atom_ids: np.ndarray
+    edge_ptr: np.ndarray
+    edge_src: np.ndarray
+    edge_dst: np.ndarray
+    bond_ids: np.ndarray
+
+    @property
+    def n_ions(self):
+        return len(self.atom_ptr) - 1
+
+    def c_struct(self):
+        for f in ("atom_ptr", "atom_ids", "edge_ptr", "edge_src", "edge_dst", "bond_ids"):
+            a = getattr(self, f)
+            assert a.dtype == I32 and a.flags.c_contiguous, f
+        return _lib.Ions(self.n_ions, *(getattr(self, f).ctypes.data for f in
+                                        ("atom_ptr", "atom_ids", "edge_ptr", "edge_src", "edge_dst", "bond_ids")))
+
+    @staticmethod
+    def from_ion_dicts(ions):
+        atom_ptr = np.zeros(len(ions) + 1, I32)
+        edge_ptr = np.zeros(len(ions) + 1, I32)
+        for i, ion in enumerate(ions):
+            atom_ptr[i + 1] = atom_ptr[i] + len(ion["atom_ids"])
+            edge_ptr[i + 1] = edge_ptr[i] + min(len(ion["edge_indices"]), len(ion["bond_ids"]))  # zip semantics
+        atom_ids = np.zeros(atom_ptr[-1], I32)
+        src = np.zeros(edge_ptr[-1], I32)
+        dst = np.zeros(edge_ptr[-1], I32)
+        bond = np.zeros(edge_ptr[-1], I32)
+        for i, ion in enumerate(ions):
+            atom_ids[atom_ptr[i]:atom_ptr[i + 1]] = ion["atom_ids"]
+            ne = edge_ptr[i + 1] - edge_ptr[i]
+            if ne:
+                e = np.asarray(ion["edge_indices"][:ne], dtype=I32).reshape(ne, 2)
+                src[edge_ptr[i]:edge_ptr[i + 1]] = e[:, 0]
+                dst[edge_ptr[i]:edge_ptr[i + 1]] = e[:, 1]
+                bond[edge_ptr[i]:edge_ptr[i + 1]] = ion["bond_ids"][:ne]
+        return FlatIons(atom_ptr, atom_ids, edge_ptr, src, dst, bond)
+
+    @staticmethod
+    def from_padded(atom, bond, conn):
+        """One tower of the reference's padded dict: atom (B,N), bond (B,E), conn (B,E,2); ids already
+        shifted, edges already doubled.  Atoms kept per sample: up to the last non-zero id or the last
+        atom a live edge touches (id-0 atoms inside that range stay, unpooled, as in the reference)."""
+        atom = np.ascontiguousarray(atom, I32)
+        bond = np.ascontiguousarray(bond, I32)
+        conn = np.ascontiguousarray(conn, I32)
+        B, N = atom.shape
+        live = (conn[:, :, 0] > 0) & (conn[:, :, 1] > 0)
+        last_id = np.where((atom > 0).any(1), N - np.argmax((atom > 0)[:, ::-1], axis=1), 0)
+        last_edge = np.where(live.any(1), (conn.max(axis=2) * live).max(axis=1) + 1, 0)
+        n = np.minimum(np.maximum(last_id, last_edge), N).astype(np.int64)
+        atom_ptr = np.zeros(B + 1, I32)
+        atom_ptr[1:] = np.cumsum(n)
+        keep = np.arange(N)[None, :] < n[:, None]
+        edge_ptr = np.zeros(B + 1, I32)
+        edge_ptr[1:] = np.cumsum(live.sum(1))
+        return FlatIons(atom_ptr, np.ascontiguousarray(atom[keep]), edge_ptr, np.ascontiguousarray(conn[:, :, 0][live]),
+                        np.ascontiguousarray(conn[:, :, 1][live]), np.ascontiguousarray(bond[live]))
+
+
+GRAPH_FIELDS = ("mol_ptr", "atom_id", "row_ptr", "col_src", "edge_bm", "bucket_ptr", "bucket_perm")
+
+
+class PackedGraphBatch:
+    """Host (numpy) arrays plus, after ``.to(device)``, their device copies (torch int32 tensors)."""
+
+    def __init__(self, arrays, counts, temperature=None, target=None):
+        self.host = arrays
+        self.n_pairs, self.n_atoms, self.n_cat_atoms, self.n_unique, self.n_edges, self.bond_vocab = counts
+        self.temperature = None if temperature is None else np.ascontiguousarray(temperature, np.float32).reshape(-1)
+        self.target = None if target is None else np.ascontiguousarray(target, np.float32).reshape(-1)
+        self.dev = None
+        self.dev_T = None
+        self.dev_y = None
+        self.device = None
+
+    # -- device side ------------------------------------------------------------------------
+    def to(self, device, non_blocking=False, pinned=False):
+        import torch
+
+        self.device = torch.device(device)
+        self.dev = {}
+        for k in GRAPH_FIELDS:
+            t = torch.from_numpy(self.host[k])
+            if pinned:
+                t = t.pin_memory()
+            self.dev[k] = t.to(self.device, non_blocking=non_blocking)
+        if self.temperature is not None:
+            self.dev_T = torch.from_numpy(self.temperature).to(self.device, non_blocking=non_blocking)
+        if self.target is not None:
+            self.dev_y = torch.from_numpy(self.target).to(self.device, non_blocking=non_blocking)
+        return self
+
+    def c_struct(self):
+        if self.dev is None:
+            raise _lib.ImpError("PackedGraphBatch is not on a device: call .to('cuda') first")
+        return _lib.Graph(self.n_pairs, self.n_atoms, self.n_cat_atoms, self.n_unique, self.n_edges, self.bond_vocab,
+                          *(self.dev[k].data_ptr() for k in GRAPH_FIELDS))
+
+    def nbytes(self):
+        n = sum(self.host[k].nbytes for k in GRAPH_FIELDS)
+        return n + (0 if self.temperature is None else self.temperature.nbytes)
+
+
+def pack_flat(cation: FlatIons, anion: FlatIons, bond_vocab_size, max_edges=None, double_edges=True, shift_ids=True,
+              temperature=None, target=None, n_threads=0):
+    assert cation.n_ions == anion.n_ions
+    P = cation.n_ions
+    N = int(cation.atom_ptr[-1]) + int(anion.atom_ptr[-1])
+    cap = (int(cation.edge_ptr[-1]) + int(anion.edge_ptr[-1])) * (2 if double_edges else 1)
+    arrays = {
+        "mol_ptr": np.zeros(2 * P + 1, I32), "atom_id": np.zeros(N, I32), "row_ptr": np.zeros(N + 1, I32),
+        "col_src": np.zeros(cap, I32), "edge_bm": np.zeros(cap, I32),
+        "bucket_ptr": np.zeros(2 * bond_vocab_size + 1, I32), "bucket_perm": np.zeros(cap, I32),
+    }
+    g = _lib.Graph(0, 0, 0, 0, 0, 0, *(arrays[k].ctypes.data for k in GRAPH_FIELDS))
+    flags = (_lib.PACK_DOUBLE_EDGES if double_edges else 0) | (_lib.PACK_SHIFT_IDS if shift_ids else 0)
+    cs, an = cation.c_struct(), anion.c_struct()
+    _lib.call("imp_pack_host", C.byref(cs), C.byref(an), bond_vocab_size, -1 if max_edges is None else int(max_edges),
+              flags, cap, C.byref(g), n_threads)
+    for k in ("col_src", "edge_bm", "bucket_perm"):
+        arrays[k] = arrays[k][: g.n_unique]
+    counts = (g.n_pairs, g.n_atoms, g.n_cat_atoms, g.n_unique, g.n_edges, g.bond_vocab)
+    return PackedGraphBatch(arrays, counts, temperature, target)
+
+
+def pack_records(records, bond_vocab_size, max_edges=None, label=None):
+    cat = FlatIons.from_ion_dicts([r["cation"] for r in records])
+    an = FlatIons.from_ion_dicts([r["anion"] for r in records])
+    T = np.array([r["T"] for r in records], np.float32) if records and "T" in records[0] else None
+    y = np.array([r[label] for r in records], np.float32) if label else None
+    return pack_flat(cat, an, bond_vocab_size, max_edges=max_edges, temperature=T, target=y)
+
+
+def pack_padded(x, bond_vocab_size):
+    """``x``: the reference's input dict (train_viscosity.py:306-314; ``temperature`` optional)."""
+    cat = FlatIons.from_padded(x["cat_atom"], x["cat_bond"], x["cat_connectivity"])
+    an = FlatIons.from_padded(x["an_atom"], x["an_bond"], x["an_connectivity"])
+    T = np.asarray(x["temperature"], np.float32).reshape(-1) if "temperature" in x else None
+    return pack_flat(cat, an, bond_vocab_size, double_edges=False, shift_ids=False, temperature=T)
+
+
+def synth_flat(n_ions, seed, n_min=10, n_max=40, atom_types=123, bond_types=71, skewed=False):
+    """Benchmark-sized synthetic tower via ``imp_synth_ions`` (same recipe as synth.make_ion)."""
+    na, ne = C.c_int64(0), C.c_int64(0)
+    _lib.call("imp_synth_ions", seed, n_ions, n_min, n_max, atom_types, bond_types, int(skewed), None, None, None, None,
+              None, None, C.byref(na), C.byref(ne))
+    ions = FlatIons(np.zeros(n_ions + 1, I32), np.zeros(na.value, I32), np.zeros(n_ions + 1, I32),
+                    np.zeros(ne.value, I32), np.zeros(ne.value, I32), np.zeros(ne.value, I32))
+    _lib.call("imp_synth_ions", seed, n_ions, n_min, n_max, atom_types, bond_types, int(skewed), ions.atom_ptr.ctypes.data,
+              ions.atom_ids.ctypes.data, ions.edge_ptr.ctypes.data, ions.edge_src.ctypes.data, ions.edge_dst.ctypes.data,
+              ions.bond_ids.ctypes.data, C.byref(na), C.byref(ne))
+    return ions
+
+
+def synth_batch(n_pairs, seed, n_min=10, n_max=40, skewed=False, bond_vocab_size=72, with_temperature=True):
+    cat = synth_flat(n_pairs, 2 * seed + 1, n_min, n_max, skewed=skewed)
+    an = synth_flat(n_pairs, 2 * seed + 2, n_min, n_max, skewed=skewed)
+    T = None
+    if with_temperature:
+        T = np.random.default_rng(seed).uniform(273.15, 373.15, size=n_pairs).astype(np.float32)
+    return pack_flat(cat, an, bond_vocab_size, temperature=T), cat, an

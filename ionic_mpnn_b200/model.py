@@ -1,0 +1,256 @@
+"""Host-side model: the reference's ``build_model`` graphs executed as one packed two-tower batch.
+
+Mirrors ``train_viscosity.py:139-231`` (``build_model`` with the same keyword defaults) and
+``train_melting_point.py:137-215``.  Weight inventory, names-by-structure and shapes follow SURVEY 8b:
+two shared embeddings; per tower x step one ``bond_transform (K,d,d)`` and the eight GatedUpdate
+variables; per tower ``Dense(fp)`` and ``Dense(mix)``; the head.  Nothing is shared between towers or
+steps (train_viscosity.py:176-189).
+
+Everything numeric happens in ``libimp_b200.so`` through ctypes (``_lib``); torch is used for device
+memory and streams only.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from .graph import PackedGraphBatch, pack_padded, pack_records
+
+TOWERS = ("cat", "an")
+
+
+def _stream():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def param_shapes(spec):
+    d, K, S = spec["atom_dim"], spec["bond_dim"], spec["num_steps"]
+    fp, mix = spec["fp_size"], spec["mixing_size"]
+    shapes = {"atom_emb": (spec["atom_vocab_size"], d), "bond_emb": (spec["bond_vocab_size"], K)}
+    for t in TOWERS:
+        for i in range(S):
+            shapes[f"{t}_bmm_{i}.bond_transform"] = (K, d, d)
+            for g in ("dense_z", "dense_r", "dense_h"):
+                shapes[f"{t}_gu_{i}.{g}.kernel"] = (2 * d, d)
+                shapes[f"{t}_gu_{i}.{g}.bias"] = (d,)
+            shapes[f"{t}_gu_{i}.layernorm.gamma"] = (d,)
+            shapes[f"{t}_gu_{i}.layernorm.beta"] = (d,)
+        shapes[f"{t}_fp.kernel"] = (d, fp)
+        shapes[f"{t}_fp.bias"] = (fp,)
+    for t in TOWERS:
+        shapes[f"{t}_mix.kernel"] = (fp, mix)
+        shapes[f"{t}_mix.bias"] = (mix,)
+    if spec["kind"] == "viscosity":
+        shapes["head.kernel"] = (mix, 3)
+        shapes["head.bias"] = (3,)
+    else:
+        shapes["head1.kernel"] = (mix, fp)
+        shapes["head1.bias"] = (fp,)
+        shapes["head2.kernel"] = (fp, 1)
+        shapes["head2.bias"] = (1,)
+    return shapes
+
+
+def keras_default_init(spec, seed=0):
+    """Keras default initialisers: Embedding U(-0.05,0.05); glorot_uniform kernels (rank-3
+    ``bond_transform``: fans multiplied by K); zero biases; LayerNorm gamma 1, beta 0."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shp in param_shapes(spec).items():
+        leaf = name.split(".")[-1]
+        if name in ("atom_emb", "bond_emb"):
+            w = rng.uniform(-0.05, 0.05, size=shp)
+        elif leaf in ("kernel", "bond_transform"):
+            rf = int(np.prod(shp[:-2])) if len(shp) > 2 else 1
+            lim = math.sqrt(6.0 / ((shp[-2] + shp[-1]) * rf))
+            w = rng.uniform(-lim, lim, size=shp)
+        elif leaf == "gamma":
+            w = np.ones(shp)
+        else:
+            w = np.zeros(shp)
+        out[name] = w.astype(np.float32)
+    return out
+
+
+class MPNNModel:
+    """Object returned by ``build_model``: ``predict(x)`` like the Keras model, on the B200 kernels."""
+
+    LN_EPS = 1e-3  # Keras LayerNormalization default (models/layers.py:139)
+
+    def __init__(self, spec, device="cuda", seed=0):
+        import torch
+
+        _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.ImpError("ionic_mpnn_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.spec = dict(spec)
+        self.device = torch.device(device)
+        self.params = {}
+        self.set_weights(keras_default_init(spec, seed))
+        self._ws = {}
+        self._tables_valid = False
+
+    # -- weights ----------------------------------------------------------------------------
+    def set_weights(self, weights):
+        import torch
+
+        shapes = param_shapes(self.spec)
+        for k, shp in shapes.items():
+            if k not in weights:
+                raise KeyError(f"missing weight {k}")
+            w = np.ascontiguousarray(np.asarray(weights[k], dtype=np.float32))
+            if tuple(w.shape) != tuple(shp):
+                raise ValueError(f"{k}: shape {w.shape} != {shp}")
+            self.params[k] = torch.from_numpy(w).to(self.device)
+        self._tables_valid = False
+
+    def get_weights(self):
+        return {k: v.detach().cpu().numpy() for k, v in self.params.items()}
+
+    def count_params(self):
+        return sum(int(np.prod(s)) for s in param_shapes(self.spec).values())
+
+    # -- workspace ---------------------------------------------------------------------------
+    def _buf(self, name, numel, dtype=None):
+        import torch
+
+        dtype = dtype or torch.float32
+        t = self._ws.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty(max(numel, 1), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t
+
+    def _ptr(self, name):
+        return C.c_void_p(self.params[name].data_ptr())
+
+    def _gru_struct(self, t, i):
+        p = f"{t}_gu_{i}"
+        return _lib.GruWeights(*(self.params[f"{p}.{n}"].data_ptr() for n in
+                                 ("dense_z.kernel", "dense_z.bias", "dense_r.kernel", "dense_r.bias", "dense_h.kernel",
+                                  "dense_h.bias", "layernorm.gamma", "layernorm.beta")))
+
+    def _readout_struct(self, t):
+        return _lib.ReadoutWeights(*(self.params[n].data_ptr() for n in
+                                     (f"{t}_fp.kernel", f"{t}_fp.bias", f"{t}_mix.kernel", f"{t}_mix.bias")))
+
+    def refresh_tables(self):
+        """K2 for all (tower, step) in one launch; called once per weight set (once per step in training)."""
+        s = self.spec
+        S, d, Vb, K = s["num_steps"], s["atom_dim"], s["bond_vocab_size"], s["bond_dim"]
+        n = 2 * S
+        per = Vb * d * d
+        tab = self._buf("table", n * per)
+        tab_il = self._buf("table_il", n * per)
+        W = (C.c_void_p * n)(*[self.params[f"{t}_bmm_{i}.bond_transform"].data_ptr() for t in TOWERS for i in range(S)])
+        T0 = (C.c_void_p * n)(*[tab.data_ptr() + 4 * per * j for j in range(n)])
+        T1 = (C.c_void_p * n)(*[tab_il.data_ptr() + 4 * per * j for j in range(n)])
+        _lib.call("imp_bond_table", self._ptr("bond_emb"), Vb, K, d, n, W, T0, T1, _stream())
+        self._tables_valid = True
+
+    def table_ptr(self, tower, step, interleaved):
+        s = self.spec
+        per = s["bond_vocab_size"] * s["atom_dim"] ** 2
+        j = tower * s["num_steps"] + step
+        base = self._ws["table_il" if interleaved else "table"].data_ptr()
+        return C.c_void_p(base + 4 * per * j)
+
+    # -- forward -----------------------------------------------------------------------------
+    def forward_packed(self, batch: PackedGraphBatch, keep=False, unfused_messages=False):
+        """Runs the whole graph on a device-resident packed batch.  Returns a device tensor [P] (and, with
+        ``keep``, a dict of device tensors of every intermediate).  ``unfused_messages`` routes the message
+        step through K3 (imp_edge_messages) + K4 (imp_segment_sum) instead of the fused imp_message_agg."""
+        import torch
+
+        s = self.spec
+        d, S = s["atom_dim"], s["num_steps"]
+        if batch.dev is None:
+            batch.to(self.device)
+        if batch.bond_vocab != s["bond_vocab_size"]:
+            raise ValueError("batch was packed for a different bond vocabulary")
+        g = batch.c_struct()
+        N, P = batch.n_atoms, batch.n_pairs
+        st = _stream()
+        if not self._tables_valid:
+            self.refresh_tables()
+        inter = {}
+        if keep:
+            h = [torch.empty(N * d, dtype=torch.float32, device=self.device) for _ in range(S + 1)]
+            aggs = [torch.empty(N * d, dtype=torch.float32, device=self.device) for _ in range(S)]
+        else:
+            hb = [self._buf("h0", N * d), self._buf("h1", N * d)]
+            h = [hb[i % 2] for i in range(S + 1)]
+            aggs = [self._buf("agg", N * d)] * S
+        _lib.call("imp_embed_atoms", self._ptr("atom_emb"), s["atom_vocab_size"], batch.dev["atom_id"].data_ptr(), N, d,
+                  h[0].data_ptr(), st)
+        for i in range(S):
+            if unfused_messages:
+                msg = self._buf("msg", batch.n_unique * d)
+                _lib.call("imp_edge_messages", C.byref(g), h[i].data_ptr(), d, self.table_ptr(0, i, False),
+                          self.table_ptr(1, i, False), msg.data_ptr(), st)
+                _lib.call("imp_segment_sum", C.byref(g), msg.data_ptr(), d, aggs[i].data_ptr(), st)
+            else:
+                _lib.call("imp_message_agg", C.byref(g), h[i].data_ptr(), d, self.table_ptr(0, i, True),
+                          self.table_ptr(1, i, True), aggs[i].data_ptr(), st)
+            wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
+            _lib.call("imp_gated_update", h[i].data_ptr(), aggs[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc),
+                      C.byref(wa), C.c_float(self.LN_EPS), h[i + 1].data_ptr(), st)
+        out = torch.empty(P, dtype=torch.float32, device=self.device)
+        fp, mix = s["fp_size"], s["mixing_size"]
+        visc = s["kind"] == "viscosity"
+        aux = None
+        if keep:
+            aux = torch.empty(P * (2 * d + 2 * fp + mix + (3 if visc else 0)), dtype=torch.float32, device=self.device)
+        rc, ra = self._readout_struct("cat"), self._readout_struct("an")
+        auxp = C.c_void_p(aux.data_ptr()) if keep else None
+        if visc:
+            if batch.dev_T is None:
+                raise ValueError("viscosity model needs batch.temperature")
+            _lib.call("imp_pool_head_visc", C.byref(g), h[S].data_ptr(), d, fp, mix, C.byref(rc), C.byref(ra),
+                      self._ptr("head.kernel"), self._ptr("head.bias"), batch.dev_T.data_ptr(), out.data_ptr(), auxp, st)
+        else:
+            _lib.call("imp_pool_head_mp", C.byref(g), h[S].data_ptr(), d, fp, mix, fp, C.byref(rc), C.byref(ra),
+                      self._ptr("head1.kernel"), self._ptr("head1.bias"), self._ptr("head2.kernel"),
+                      self._ptr("head2.bias"), out.data_ptr(), auxp, st)
+        if keep:
+            inter = {"h": [t.view(N, d) for t in h], "agg": [t.view(N, d) for t in aggs],
+                     "aux": aux.view(P, -1)}
+        return (out, inter) if keep else out
+
+    def launches_per_forward(self):
+        """Kernels enqueued by forward_packed (fused message path, tables already valid)."""
+        return 1 + 2 * self.spec["num_steps"] + 1
+
+    # -- Keras-like surface ---------------------------------------------------------------------
+    def pack(self, x):
+        if isinstance(x, PackedGraphBatch):
+            return x
+        if isinstance(x, dict):
+            return pack_padded(x, self.spec["bond_vocab_size"])
+        return pack_records(x, self.spec["bond_vocab_size"])
+
+    def predict(self, x, batch_size=None, verbose=0):
+        """``x``: the reference's padded input dict (train_viscosity.py:306-314), a list of records, or a
+        PackedGraphBatch.  Returns numpy ``(P, 1)`` like Keras.  ``batch_size`` is accepted for signature
+        compatibility; the packed batch runs in one pass."""
+        import torch
+
+        batch = self.pack(x)
+        out = self.forward_packed(batch)
+        torch.cuda.current_stream().synchronize()
+        return out.cpu().numpy().reshape(-1, 1)
+
+    __call__ = predict
+
+
+def make_spec(kind="viscosity", atom_vocab_size=124, bond_vocab_size=72, atom_dim=32, bond_dim=8, fp_size=32,
+              mixing_size=20, num_steps=4):
+    if kind == "melting_point":
+        bond_dim = atom_dim * atom_dim  # train_melting_point.py:146
+    return dict(kind=kind, atom_vocab_size=atom_vocab_size, bond_vocab_size=bond_vocab_size, atom_dim=atom_dim,
+                bond_dim=bond_dim, fp_size=fp_size, mixing_size=mixing_size, num_steps=num_steps)

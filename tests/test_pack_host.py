@@ -1,0 +1,100 @@
+"""CPU: the C++ host packer (imp_pack_host through ctypes) bit-exact against oracle/ref_pack.py, and the
+C-ABI library exporting every symbol include/imp_b200.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_F64, ROOT, load_golden
+from ionic_mpnn_b200 import _lib, graph, synth
+from oracle import ref_inputs, ref_pack
+
+FIELDS = graph.GRAPH_FIELDS
+
+
+def assert_same(pk, ref):
+    assert (pk.n_pairs, pk.n_atoms, pk.n_cat_atoms, pk.n_unique, pk.n_edges) == (
+        ref["n_pairs"], ref["n_atoms"], ref["n_cat_atoms"], ref["n_unique"], ref["n_edges"])
+    for k in FIELDS:
+        assert pk.host[k].dtype == np.int32
+        assert np.array_equal(pk.host[k], ref[k]), k
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "imp_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(imp_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in imp_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().imp_version() == 100
+
+
+@pytest.mark.parametrize("seed,skewed", [(0, False), (1, True), (2, False)])
+def test_records_bit_exact(seed, skewed):
+    recs = synth.make_records(64, seed=seed, skewed=skewed)
+    assert_same(graph.pack_records(recs, 72), ref_pack.pack_records(recs, 72))
+
+
+def test_truncation_bit_exact():
+    recs = synth.make_records(16, seed=9, n_min=4, n_max=10)
+    assert_same(graph.pack_records(recs, 72, max_edges=6), ref_pack.pack_records(recs, 72, max_edges=6))
+
+
+@pytest.mark.parametrize("name", GOLDEN_F64)
+def test_padded_dict_gives_same_batch_as_records(name):
+    meta, x, _, _, _ = load_golden(name)
+    vb = meta["spec"]["bond_vocab_size"]
+    assert_same(graph.pack_padded(x, vb), ref_pack.pack_records(meta["records"], vb))
+
+
+def test_multithreaded_equals_single_thread():
+    recs = synth.make_records(3000, seed=4, n_min=3, n_max=8)
+    cat = graph.FlatIons.from_ion_dicts([r["cation"] for r in recs])
+    an = graph.FlatIons.from_ion_dicts([r["anion"] for r in recs])
+    a = graph.pack_flat(cat, an, 72, n_threads=1)
+    b = graph.pack_flat(cat, an, 72, n_threads=7)
+    for k in FIELDS:
+        assert np.array_equal(a.host[k], b.host[k]), k
+    assert a.n_edges == b.n_edges
+
+
+def test_edge_cases_and_errors():
+    empty = graph.pack_records([], 72)
+    assert empty.n_atoms == 0 and empty.host["row_ptr"].tolist() == [0]
+    recs = [{"cation": {"atom_ids": [3], "bond_ids": [], "edge_indices": []},
+             "anion": {"atom_ids": [1, 2], "bond_ids": [4, 4], "edge_indices": [(0, 1), (1, 0)]}, "T": 300.0}]
+    assert_same(graph.pack_records(recs, 72), ref_pack.pack_records(recs, 72))
+    bad = [{"cation": {"atom_ids": [0, 1], "bond_ids": [0, 0], "edge_indices": [(1, 2), (2, 1)]},
+            "anion": {"atom_ids": [0], "bond_ids": [], "edge_indices": []}}]
+    with pytest.raises(_lib.ImpError, match="out of range"):
+        graph.pack_records(bad, 72)
+    bad[0]["cation"]["edge_indices"] = [(1, 1), (1, 1)]
+    bad[0]["cation"]["bond_ids"] = [71, 71]  # shifted to 72 == vocabulary size
+    with pytest.raises(_lib.ImpError):
+        graph.pack_records(bad, 72)
+
+
+def test_synth_ions_follow_the_recipe():
+    ions = graph.synth_flat(2000, seed=11)
+    n = np.diff(ions.atom_ptr)
+    assert n.min() >= 10 and n.max() <= 40 and abs(n.mean() - 25) < 1.0
+    assert ions.atom_ids.min() >= 0 and ions.atom_ids.max() == 122
+    assert ions.bond_ids.min() == 0 and ions.bond_ids.max() == 70
+    # featurize convention: consecutive (a,b),(b,a) pairs sharing the bond id
+    assert np.array_equal(ions.edge_src[0::2], ions.edge_dst[1::2]) and np.array_equal(ions.edge_dst[0::2], ions.edge_src[1::2])
+    assert np.array_equal(ions.bond_ids[0::2], ions.bond_ids[1::2])
+    for i in range(50):  # tree + <=2 ring bonds, degree cap 4, local indices in range
+        e0, e1 = ions.edge_ptr[i], ions.edge_ptr[i + 1]
+        nb = (e1 - e0) // 2
+        assert n[i] - 1 <= nb <= n[i] + 1
+        deg = np.bincount(ions.edge_src[e0:e1], minlength=n[i])
+        assert deg.max() <= 4 and ions.edge_src[e0:e1].max() < n[i]
+    again = graph.synth_flat(2000, seed=11)
+    assert np.array_equal(again.edge_src, ions.edge_src) and np.array_equal(again.atom_ids, ions.atom_ids)
+    sk = graph.synth_flat(2000, seed=11, skewed=True)
+    assert np.bincount(sk.bond_ids, minlength=71)[0] > 5 * np.bincount(sk.bond_ids, minlength=71)[40]

@@ -256,8 +256,8 @@ def run_b200(args):
         finally:
             mm._lib.call = real_call
         torch.cuda.synchronize()
-        for name, e0, e1 in events:
-            per_kernel.setdefault(name.replace("imp_", ""), []).append(e0.elapsed_time(e1))
+        for kname, e0, e1 in events:
+            per_kernel.setdefault(kname.replace("imp_", ""), []).append(e0.elapsed_time(e1))
     barrier()
 
     # ---- end-to-end from pinned host buffers --------------------------------------------------

@@ -170,6 +170,14 @@ int imp_pool_head_mp(const imp_graph_t* g, const float* d_h, int32_t d, int32_t 
                      const float* d_b2, float* d_out /* [P] */, float* d_aux /* optional, as above w/o (A,B,C) */,
                      void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Diagnostics: one-CTA tcgen05 product D[128,N] = A[128,K] * B[N,K]^T (kind 0 = bf16, 1 = tf32 operands,
+ * fp32 accumulate) through the library's own shared-memory staging layout and UMMA descriptors.  Used by
+ * tests/test_gpu_tensor.py to validate the tensor-core plumbing in isolation.
+ * ------------------------------------------------------------------------------------------- */
+int imp_tc_selftest(const float* d_A, const float* d_B, float* d_D, int32_t N, int32_t K, int32_t kind,
+                    int32_t swap_lbo_sbo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,7 @@ SIGNATURES = {
                                      C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp]),
     "imp_pool_head_mp": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.POINTER(ReadoutWeights), C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp, vp]),
+    "imp_tc_selftest": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
 }
 
 _lib = None

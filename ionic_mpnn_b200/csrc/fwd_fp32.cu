@@ -614,7 +614,7 @@ extern "C" int imp_pool_head_visc(const imp_graph_t* g, const float* d_h, int32_
                                   const imp_readout_weights_t* w_cat, const imp_readout_weights_t* w_an,
                                   const float* d_W_head, const float* d_b_head, const float* d_T, float* d_out,
                                   float* d_aux, void* stream) {
-  IMP_REQUIRE(d_T, IMP_ERR_ARG, "imp_pool_head_visc: temperature is null");
+  IMP_REQUIRE(d_T || (g && g->n_pairs == 0), IMP_ERR_ARG, "imp_pool_head_visc: temperature is null");
   return launch_k6(g, d_h, d, fp, mix, 0, w_cat, w_an, d_W_head, d_b_head, nullptr, nullptr, d_T, d_out, d_aux, stream,
                    "imp_pool_head_visc");
 }

@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="visc_sweep", choices=["visc_sweep", "mp64k"])
     ap.add_argument("--pairs-per-gpu", type=int, default=None)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "bf16_precise"],
+                    help="fp32 = SIMT 1e-5 parity path; bf16 = tcgen05 tensor-core path (2e-2)")
     ap.add_argument("--skewed", action="store_true", help="Zipf(1.2) bond types instead of uniform")
     ap.add_argument("--cpu-sample-pairs", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -171,6 +173,7 @@ def stage_bytes(batch, d, S, s=4):
         "embed_atoms": 4 * N + N * d * s,
         "message_agg": 2 * N * d * s + 8 * Eu + 4 * N,   # h in, agg out, (src, bond|mult) per unique entry, row_ptr
         "gated_update": 3 * N * d * s,                    # h, agg in; h out
+        "gated_update_tc": 3 * N * d * s,
         "pool_head": N * d * s + 4 * N + 8 * P + 8 * P,   # h, atom_id, mol_ptr (2 towers), T + out
     }
 
@@ -193,7 +196,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     P, kind, name = workload_config(args)
     spec = make_spec(kind)
-    model = MPNNModel(spec, device=f"cuda:{local}", seed=0)
+    model = MPNNModel(spec, device=f"cuda:{local}", seed=0, precision=args.precision)
     d, S = spec["atom_dim"], spec["num_steps"]
 
     t_pack0 = time.perf_counter()
@@ -315,10 +318,10 @@ def run_b200(args):
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
+                "dtype": "f32" if args.precision == "fp32" else "bf16 operands, f32 accumulate/storage", "data": "synthetic",
                 "config": {"workload": name, "pairs_per_gpu": P, "atoms_per_gpu": batch.n_atoms,
                            "edges_per_gpu": batch.n_edges, "unique_edges_per_gpu": batch.n_unique,
-                           "bond_types": "zipf1.2" if args.skewed else "uniform",
+                           "bond_types": "zipf1.2" if args.skewed else "uniform", "precision": args.precision,
                            "l2_policy": "inputs larger than L2 (activations %.1f GB per GPU)" % (3 * batch.n_atoms * d * 4 / 1e9),
                            "parallelism": f"pairs sharded over {world} GPU(s), no collective",
                            "host_synth_and_pack_s": round(t_pack, 2)},

@@ -147,6 +147,15 @@ int imp_gated_update(const float* d_h, const float* d_agg, int32_t n_atoms, int3
  *                   log_eta = A + B / (T/100 + C + 1e-6)      (:204-214, models/layers.py:10-42)
  *       melting pt  Dense(fp2, relu) -> Dense(1)               (train_melting_point.py:191-198)
  * ------------------------------------------------------------------------------------------- */
+/* K5 on the tensor cores (tcgen05, bf16 operands, fp32 accumulation in TMEM; the "2e-2" path).  Weights are
+ * packed once per weight update into the UMMA operand layout: imp_gru_pack_bytes(d) bytes per (tower, step).
+ * precise_epilogue != 0 uses expf / tanhf / sqrtf in the gate epilogue instead of tanh.approx / rsqrt. */
+int64_t imp_gru_pack_bytes(int32_t d);
+int imp_gru_pack_bf16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
+int imp_gated_update_tc(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
+                        const void* d_packed_cat, const void* d_packed_an, float eps, int32_t precise_epilogue,
+                        float* d_h_out, void* stream);
+
 /* GlobalSumPool.call alone (models/layers.py:161-164): out[m,:] = sum of h rows of molecule m whose
  * atom_id > 0.  `n_mols` molecules delimited by d_mol_ptr[n_mols+1]. */
 int imp_global_sum_pool(const int32_t* d_mol_ptr, const int32_t* d_atom_id, int32_t n_mols, const float* d_h, int32_t d,

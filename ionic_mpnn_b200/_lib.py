@@ -60,6 +60,9 @@ SIGNATURES = {
     "imp_segment_sum": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, vp, vp]),
     "imp_gated_update": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(GruWeights), C.POINTER(GruWeights),
                                    C.c_float, vp, vp]),
+    "imp_gru_pack_bytes": (C.c_int64, [C.c_int32]),
+    "imp_gru_pack_bf16": (C.c_int, [C.POINTER(GruWeights), C.c_int32, vp, vp]),
+    "imp_gated_update_tc": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_float, C.c_int32, vp, vp]),
     "imp_global_sum_pool": (C.c_int, [vp, vp, C.c_int32, vp, C.c_int32, vp, vp]),
     "imp_pool_head_visc": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ReadoutWeights),
                                      C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp]),

@@ -1,0 +1,272 @@
+// K5 on the 5th-generation tensor cores: GatedUpdate.call (models/layers.py:142-156) as two tcgen05 GEMMs per
+// 128-atom tile with the gate / LayerNorm / residual epilogue fused (north_star kernel (c)).
+//
+//   GEMM 1   [h | agg] (128 x 2d, bf16)  x  [Wz | Wr] (2d x 2d)      -> TMEM columns [0, 2d)      fp32
+//   epi  1   z = sigmoid(. + bz) (kept in registers), r = sigmoid(. + br), r*h -> bf16 operand tile
+//   GEMM 2   [r*h | agg] (128 x 2d)      x  Wh (2d x d)               -> TMEM columns [2d, 3d)
+//   epi  2   h~ = tanh(. + bh); n = (1-z) h + z h~; LayerNorm(eps, biased var) * gamma + beta + h
+//
+// One thread owns one atom row in both epilogues (tcgen05.ld 32x32b: lane i of warp w <-> TMEM lane 32w+i), so the
+// LayerNorm reduction is thread-local.  Operands are staged by the threads themselves (fp32 -> bf16, chunk-major
+// canonical layout of tc_common.cuh); weights are pre-packed once per weight update by imp_gru_pack_bf16.
+// Storage of h / agg in HBM stays fp32; products are bf16 x bf16 with fp32 accumulation (the 2e-2 path).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace imp {
+
+template <int D>
+struct GruPackLayout {
+  static constexpr int N1 = 2 * D;            // z | r columns
+  static constexpr int C1 = 2 * D / 8;        // 16-byte chunks along K = 2d (bf16)
+  static constexpr int BZR_BYTES = N1 * C1 * 16;
+  static constexpr int BH_BYTES = D * C1 * 16;
+  static constexpr int BIAS_FLOATS = 5 * D;   // bz, br, bh, gamma, beta
+  static constexpr int BYTES = BZR_BYTES + BH_BYTES + BIAS_FLOATS * 4;
+};
+
+template <int D>
+__global__ void gru_pack_kernel(imp_gru_weights_t w, unsigned char* __restrict__ out) {
+  using L = GruPackLayout<D>;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < L::N1 * 2 * D) {  // Bzr[n][k] = (n < D ? Wz[k][n] : Wr[k][n - D])
+    const int n = i / (2 * D), k = i % (2 * D);
+    const float v = n < D ? w.Wz[k * D + n] : w.Wr[k * D + (n - D)];
+    *reinterpret_cast<__nv_bfloat16*>(out + tc::chunk_off(n, k / 8, L::N1) + (k % 8) * 2) = __float2bfloat16_rn(v);
+  }
+  if (i < D * 2 * D) {  // Bh[n][k] = Wh[k][n]
+    const int n = i / (2 * D), k = i % (2 * D);
+    *reinterpret_cast<__nv_bfloat16*>(out + L::BZR_BYTES + tc::chunk_off(n, k / 8, D) + (k % 8) * 2) =
+        __float2bfloat16_rn(w.Wh[k * D + n]);
+  }
+  if (i < D) {
+    float* b = reinterpret_cast<float*>(out + L::BZR_BYTES + L::BH_BYTES);
+    b[i] = w.bz[i], b[D + i] = w.br[i], b[2 * D + i] = w.bh[i], b[3 * D + i] = w.gamma[i], b[4 * D + i] = w.beta[i];
+  }
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool PRECISE>
+__device__ __forceinline__ float act_sigmoid(float x) {
+  if (PRECISE) return 1.0f / (1.0f + expf(-x));
+  return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f);
+}
+template <bool PRECISE>
+__device__ __forceinline__ float act_tanh(float x) {
+  return PRECISE ? tanhf(x) : tanh_fast(x);
+}
+
+constexpr int TC_TILE = 128;
+
+template <int D>
+struct GruTcSmem {
+  using L = GruPackLayout<D>;
+  alignas(128) unsigned char packed[L::BYTES];               // Bzr | Bh | biases (verbatim copy of the pack)
+  alignas(128) unsigned char A1[TC_TILE * L::C1 * 16];       // [h | agg] bf16, chunk-major
+  alignas(128) unsigned char RH[TC_TILE * (D / 8) * 16];     // r*h bf16, chunk-major
+  float H[TC_TILE][D + 1];                                   // fp32 h rows (epilogue + output staging)
+  alignas(8) uint64_t bar[2];
+  uint32_t tmem_base;
+};
+
+template <int D, bool PRECISE>
+__global__ void __launch_bounds__(TC_TILE) gated_update_tc_kernel(const float* __restrict__ h, const float* __restrict__ agg,
+                                                                  int n_atoms, int n_cat, int tiles_cat, int tiles_total,
+                                                                  int tiles_per_cta, const unsigned char* __restrict__ packed_cat,
+                                                                  const unsigned char* __restrict__ packed_an, float eps,
+                                                                  float* __restrict__ h_out) {
+  static_assert(D == 32, "tensor GRU kernel is instantiated for atom_dim 32");
+  using L = GruPackLayout<D>;
+  constexpr int CH = D / 8;  // chunks per half (h or agg)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  GruTcSmem<D>& s = *reinterpret_cast<GruTcSmem<D>*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (warp == 0) tc::tmem_alloc<128>(&s.tmem_base);
+  if (tid == 0) {
+    tc::mbar_init(&s.bar[0], 1);
+    tc::mbar_init(&s.bar[1], 1);
+    tc::mbar_fence_init();
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = s.tmem_base;
+  const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+  const float* bias = reinterpret_cast<const float*>(s.packed + L::BZR_BYTES + L::BH_BYTES);
+  const uint32_t idesc1 = tc::make_idesc(tc::FMT_BF16, TC_TILE, L::N1);
+  const uint32_t idesc2 = tc::make_idesc(tc::FMT_BF16, TC_TILE, D);
+  const uint32_t aA1 = tc::smem_u32(s.A1), aRH = tc::smem_u32(s.RH), aBzr = tc::smem_u32(s.packed),
+                 aBh = tc::smem_u32(s.packed + L::BZR_BYTES);
+  constexpr uint32_t LBO_A = TC_TILE * 16, LBO_BZR = L::N1 * 16, LBO_BH = D * 16, SBO = 128;
+
+  int cur_tower = -1;
+  uint32_t phase = 0;
+  const int t_begin = blockIdx.x * tiles_per_cta, t_end = min(tiles_total, t_begin + tiles_per_cta);
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    const int tower = tile >= tiles_cat;
+    if (tower != cur_tower) {  // (re)load this tower's packed weights
+      const uint4* src = reinterpret_cast<const uint4*>(tower ? packed_an : packed_cat);
+      uint4* dst = reinterpret_cast<uint4*>(s.packed);
+      for (int i = tid; i < L::BYTES / 16; i += TC_TILE) dst[i] = __ldg(src + i);
+      cur_tower = tower;
+    }
+    const int a0 = tower ? n_cat + (tile - tiles_cat) * TC_TILE : tile * TC_TILE;
+    const int rows = min(TC_TILE, (tower ? n_atoms : n_cat) - a0);
+    // ---- stage [h | agg] as bf16 operand + fp32 h rows
+    const float4* hg = reinterpret_cast<const float4*>(h + (size_t)a0 * D);
+    const float4* ag = reinterpret_cast<const float4*>(agg + (size_t)a0 * D);
+#pragma unroll
+    for (int it = 0; it < CH; ++it) {
+      const int i = tid + it * TC_TILE;
+      const int r = i / CH, c = i % CH;
+      float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0, g0 = h0, g1 = h0;
+      if (r < rows) {
+        h0 = __ldg(hg + 2 * i), h1 = __ldg(hg + 2 * i + 1);
+        g0 = __ldg(ag + 2 * i), g1 = __ldg(ag + 2 * i + 1);
+      }
+      float* hr = &s.H[r][c * 8];
+      hr[0] = h0.x, hr[1] = h0.y, hr[2] = h0.z, hr[3] = h0.w, hr[4] = h1.x, hr[5] = h1.y, hr[6] = h1.z, hr[7] = h1.w;
+      uint4 hv, gv;
+      hv.x = tc::pack_bf16x2(h0.x, h0.y), hv.y = tc::pack_bf16x2(h0.z, h0.w);
+      hv.z = tc::pack_bf16x2(h1.x, h1.y), hv.w = tc::pack_bf16x2(h1.z, h1.w);
+      gv.x = tc::pack_bf16x2(g0.x, g0.y), gv.y = tc::pack_bf16x2(g0.z, g0.w);
+      gv.z = tc::pack_bf16x2(g1.x, g1.y), gv.w = tc::pack_bf16x2(g1.z, g1.w);
+      *reinterpret_cast<uint4*>(s.A1 + tc::chunk_off(r, c, TC_TILE)) = hv;
+      *reinterpret_cast<uint4*>(s.A1 + tc::chunk_off(r, CH + c, TC_TILE)) = gv;
+    }
+    tc::fence_proxy_async_smem();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    // ---- GEMM 1: z | r pre-activations
+    if (tid == 0) {
+      tc::fence_after_thread_sync();
+#pragma unroll
+      for (int ks = 0; ks < L::C1 / 2; ++ks)
+        tc::mma_bf16(tmem, tc::make_smem_desc(aA1 + 2 * ks * LBO_A, LBO_A, SBO),
+                     tc::make_smem_desc(aBzr + 2 * ks * LBO_BZR, LBO_BZR, SBO), idesc1, ks > 0);
+      tc::mma_commit(&s.bar[0]);
+    }
+    tc::mbar_wait(&s.bar[0], phase);
+    tc::fence_after_thread_sync();
+    float z[D];
+    {
+      float v[32];
+      tc::tmem_ld32(tmem_row + 0, v);
+#pragma unroll
+      for (int j = 0; j < D; ++j) z[j] = act_sigmoid<PRECISE>(v[j] + bias[j]);
+      tc::tmem_ld32(tmem_row + D, v);
+      uint32_t pk[D / 2];
+#pragma unroll
+      for (int j = 0; j < D; j += 2) {
+        const float r0 = act_sigmoid<PRECISE>(v[j] + bias[D + j]) * s.H[tid][j];
+        const float r1 = act_sigmoid<PRECISE>(v[j + 1] + bias[D + j + 1]) * s.H[tid][j + 1];
+        pk[j / 2] = tc::pack_bf16x2(r0, r1);
+      }
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        *reinterpret_cast<uint4*>(s.RH + tc::chunk_off(tid, c, TC_TILE)) =
+            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    }
+    tc::fence_proxy_async_smem();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    // ---- GEMM 2: candidate pre-activation, [r*h | agg] x Wh
+    if (tid == 0) {
+      tc::fence_after_thread_sync();
+#pragma unroll
+      for (int ks = 0; ks < L::C1 / 2; ++ks) {
+        const uint32_t a = ks < CH / 2 ? aRH + 2 * ks * LBO_A : aA1 + 2 * ks * LBO_A;  // agg chunks live in A1
+        tc::mma_bf16(tmem + 2 * D, tc::make_smem_desc(a, LBO_A, SBO),
+                     tc::make_smem_desc(aBh + 2 * ks * LBO_BH, LBO_BH, SBO), idesc2, ks > 0);
+      }
+      tc::mma_commit(&s.bar[1]);
+    }
+    tc::mbar_wait(&s.bar[1], phase);
+    tc::fence_after_thread_sync();
+    {
+      float g[32];
+      tc::tmem_ld32(tmem_row + 2 * D, g);
+      float mean = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const float ht = act_tanh<PRECISE>(g[j] + bias[2 * D + j]);
+        const float hj = s.H[tid][j];
+        g[j] = fmaf(z[j], ht - hj, hj);  // (1 - z) h + z h~
+        mean += g[j];
+      }
+      mean *= (1.0f / D);
+      float var = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const float c = g[j] - mean;
+        var = fmaf(c, c, var);
+      }
+      const float inv = PRECISE ? 1.0f / sqrtf(var * (1.0f / D) + eps) : rsqrtf(var * (1.0f / D) + eps);
+#pragma unroll
+      for (int j = 0; j < D; ++j) s.H[tid][j] = fmaf((g[j] - mean) * inv, bias[3 * D + j], bias[4 * D + j]) + s.H[tid][j];
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    // ---- coalesced store of the new h rows
+    float4* og = reinterpret_cast<float4*>(h_out + (size_t)a0 * D);
+    for (int i = tid; i < rows * (D / 4); i += TC_TILE) {
+      const int r = i / (D / 4), c = (i % (D / 4)) * 4;
+      og[i] = make_float4(s.H[r][c], s.H[r][c + 1], s.H[r][c + 2], s.H[r][c + 3]);
+    }
+    __syncthreads();
+    phase ^= 1;
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<128>(tmem);
+}
+
+}  // namespace imp
+
+using namespace imp;
+
+extern "C" int64_t imp_gru_pack_bytes(int32_t d) { return d == 32 ? (int64_t)GruPackLayout<32>::BYTES : (int64_t)IMP_ERR_DIM; }
+
+extern "C" int imp_gru_pack_bf16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream) {
+  IMP_REQUIRE(w && d_packed && w->Wz && w->bz && w->Wr && w->br && w->Wh && w->bh && w->gamma && w->beta, IMP_ERR_ARG,
+              "imp_gru_pack_bf16: null pointer");
+  IMP_REQUIRE(d == 32, IMP_ERR_DIM, "imp_gru_pack_bf16: atom_dim %d not supported by the tensor path (32)", d);
+  const int n = GruPackLayout<32>::N1 * 2 * 32;
+  gru_pack_kernel<32><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<unsigned char*>(d_packed));
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int imp_gated_update_tc(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
+                                   const void* d_packed_cat, const void* d_packed_an, float eps, int32_t precise_epilogue,
+                                   float* d_h_out, void* stream) {
+  IMP_REQUIRE(n_atoms >= 0 && n_cat_atoms >= 0 && n_cat_atoms <= n_atoms, IMP_ERR_ARG, "imp_gated_update_tc: bad sizes");
+  IMP_REQUIRE(d == 32, IMP_ERR_DIM, "imp_gated_update_tc: atom_dim %d not supported by the tensor path (32)", d);
+  if (n_atoms == 0) return 0;
+  IMP_REQUIRE(d_h && d_agg && d_h_out && d_packed_cat && d_packed_an, IMP_ERR_ARG, "imp_gated_update_tc: null pointer");
+  IMP_REQUIRE(imp_device_is_sm100(), IMP_ERR_UNSUPPORTED, "imp_gated_update_tc: tcgen05 needs an sm_100 device");
+  const int tiles_cat = (int)ceil_div(n_cat_atoms, TC_TILE), tiles_an = (int)ceil_div(n_atoms - n_cat_atoms, TC_TILE);
+  const int tiles = tiles_cat + tiles_an;
+  const int max_ctas = 148 * 4;
+  const int per = (int)ceil_div(tiles, max_ctas);
+  const int grid = (int)ceil_div(tiles, per);
+  const size_t smem = sizeof(GruTcSmem<32>);
+  if (precise_epilogue) {
+    IMP_CUDA(cudaFuncSetAttribute(gated_update_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gated_update_tc_kernel<32, true><<<grid, TC_TILE, smem, (cudaStream_t)stream>>>(
+        d_h, d_agg, n_atoms, n_cat_atoms, tiles_cat, tiles, per, (const unsigned char*)d_packed_cat,
+        (const unsigned char*)d_packed_an, eps, d_h_out);
+  } else {
+    IMP_CUDA(cudaFuncSetAttribute(gated_update_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gated_update_tc_kernel<32, false><<<grid, TC_TILE, smem, (cudaStream_t)stream>>>(
+        d_h, d_agg, n_atoms, n_cat_atoms, tiles_cat, tiles, per, (const unsigned char*)d_packed_cat,
+        (const unsigned char*)d_packed_an, eps, d_h_out);
+  }
+  IMP_LAUNCH_CHECK();
+  return 0;
+}

@@ -82,8 +82,12 @@ class MPNNModel:
 
     LN_EPS = 1e-3  # Keras LayerNormalization default (models/layers.py:139)
 
-    def __init__(self, spec, device="cuda", seed=0):
+    def __init__(self, spec, device="cuda", seed=0, precision="fp32"):
         import torch
+
+        if precision not in ("fp32", "bf16", "bf16_precise"):
+            raise ValueError("precision must be 'fp32' (SIMT, 1e-5 path), 'bf16' (tcgen05, 2e-2 path) or 'bf16_precise'")
+        self.precision = precision
 
         _lib.load()
         if not torch.cuda.is_available():
@@ -151,6 +155,18 @@ class MPNNModel:
         T0 = (C.c_void_p * n)(*[tab.data_ptr() + 4 * per * j for j in range(n)])
         T1 = (C.c_void_p * n)(*[tab_il.data_ptr() + 4 * per * j for j in range(n)])
         _lib.call("imp_bond_table", self._ptr("bond_emb"), Vb, K, d, n, W, T0, T1, _stream())
+        if self.precision != "fp32":
+            import torch
+
+            nbytes = _lib.load().imp_gru_pack_bytes(d)
+            if nbytes < 0:
+                raise _lib.ImpError(f"tensor path does not support atom_dim {d}")
+            self._gru_pack_bytes = (nbytes + 255) // 256 * 256
+            pk = self._buf("gru_packed", self._gru_pack_bytes * n, torch.uint8)
+            for ti, t in enumerate(TOWERS):
+                for i in range(S):
+                    w = self._gru_struct(t, i)
+                    _lib.call("imp_gru_pack_bf16", C.byref(w), d, pk.data_ptr() + self._gru_pack_bytes * (ti * S + i), _stream())
         self._tables_valid = True
 
     def table_ptr(self, tower, step, interleaved):
@@ -197,9 +213,15 @@ class MPNNModel:
             else:
                 _lib.call("imp_message_agg", C.byref(g), h[i].data_ptr(), d, self.table_ptr(0, i, True),
                           self.table_ptr(1, i, True), aggs[i].data_ptr(), st)
-            wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
-            _lib.call("imp_gated_update", h[i].data_ptr(), aggs[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc),
-                      C.byref(wa), C.c_float(self.LN_EPS), h[i + 1].data_ptr(), st)
+            if self.precision == "fp32":
+                wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
+                _lib.call("imp_gated_update", h[i].data_ptr(), aggs[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc),
+                          C.byref(wa), C.c_float(self.LN_EPS), h[i + 1].data_ptr(), st)
+            else:
+                base = self._ws["gru_packed"].data_ptr()
+                _lib.call("imp_gated_update_tc", h[i].data_ptr(), aggs[i].data_ptr(), N, batch.n_cat_atoms, d,
+                          base + self._gru_pack_bytes * i, base + self._gru_pack_bytes * (S + i), C.c_float(self.LN_EPS),
+                          1 if self.precision == "bf16_precise" else 0, h[i + 1].data_ptr(), st)
         out = torch.empty(P, dtype=torch.float32, device=self.device)
         fp, mix = s["fp_size"], s["mixing_size"]
         visc = s["kind"] == "viscosity"

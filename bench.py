@@ -43,8 +43,11 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="visc_sweep", choices=["visc_sweep", "mp64k"])
     ap.add_argument("--pairs-per-gpu", type=int, default=None)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "bf16_precise"],
-                    help="fp32 = SIMT 1e-5 parity path; bf16 = tcgen05 tensor-core path (2e-2)")
+    ap.add_argument("--precision", default="fp16", choices=["fp32", "bf16", "bf16_precise", "fp16", "fp16_precise"],
+                    help="fp16 / bf16 = tcgen05 tensor-core path (16-bit operands, fp32 accumulate; the 2e-2 path, default); "
+                         "fp32 = SIMT 1e-5 parity path")
+    ap.add_argument("--staged", action="store_true", help="per-layer kernels instead of the fused whole-tower kernel")
+    ap.add_argument("--tc-flags", type=int, default=0, help="extra IMP_TC_* tuning flags (e.g. 4 = MP8)")
     ap.add_argument("--skewed", action="store_true", help="Zipf(1.2) bond types instead of uniform")
     ap.add_argument("--cpu-sample-pairs", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -166,10 +169,22 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def stage_flops(batch, d, S):
+    """Algorithmic FLOP per launch: messages 2*E*d^2 with E = live entries counted with multiplicity,
+    gated update 12*N*d^2, per step."""
+    N, E = batch.n_atoms, batch.n_edges
+    return {"mpnn_forward_fused": S * (2 * E + 12 * N) * d * d, "gated_update_tc": 12 * N * d * d}
+
+
 def stage_bytes(batch, d, S, s=4):
     """Algorithmic bytes per launch (each operand once, weights / tables amortised to 0, int32 indices)."""
     N, Eu, P = batch.n_atoms, batch.n_unique, batch.n_pairs
     return {
+        # fused forward: only the index stream is read (atom_id, row_ptr, mol_ptr, (src, bond|mult) per entry) and
+        # the molecule sums are written (SURVEY 8d "stretch": bytes -> indices only)
+        "mpnn_forward_fused": 8 * N + 8 * Eu + 8 * P + 2 * P * d * 4,
+        "readout_visc": 2 * P * d * 4 + 8 * P,
+        "readout_mp": 2 * P * d * 4 + 4 * P,
         "embed_atoms": 4 * N + N * d * s,
         "message_agg": 2 * N * d * s + 8 * Eu + 4 * N,   # h in, agg out, (src, bond|mult) per unique entry, row_ptr
         "gated_update": 3 * N * d * s,                    # h, agg in; h out
@@ -196,7 +211,9 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     P, kind, name = workload_config(args)
     spec = make_spec(kind)
-    model = MPNNModel(spec, device=f"cuda:{local}", seed=0, precision=args.precision)
+    model = MPNNModel(spec, device=f"cuda:{local}", seed=0, precision=args.precision,
+                      fused=False if args.staged else "auto")
+    model.extra_tc_flags = args.tc_flags
     d, S = spec["atom_dim"], spec["num_steps"]
 
     t_pack0 = time.perf_counter()
@@ -298,35 +315,53 @@ def run_b200(args):
     if rank == 0:
         hbm_peak, tf_peak, peak_src = measured_peaks()
         sb = stage_bytes(batch, d, S)
+        sf = stage_flops(batch, d, S)
         mean_ms = {k: sum(v) / len(v) for k, v in per_kernel.items()}
         tot_ms = {k: sum(v) / 2 for k, v in per_kernel.items()}  # two instrumented passes
         dom = max(tot_ms, key=tot_ms.get) if tot_ms else None
         roofline = None
         if dom:
-            ach = sb.get(dom, 0) / (mean_ms[dom] * 1e-3) / 1e9
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                        "algorithmic_bytes_per_launch": sb.get(dom), "avg_launch_ms": mean_ms[dom],
-                        "share_of_step": tot_ms[dom] / sum(tot_ms.values()),
-                        "per_kernel": {k: {"avg_ms": mean_ms[k], "launches_per_step": len(per_kernel[k]) // 2,
-                                           "share": tot_ms[k] / sum(tot_ms.values()),
-                                           "GBps": (sb[k] / (mean_ms[k] * 1e-3) / 1e9) if k in sb else None}
-                                       for k in mean_ms}}
+            pk = {k: {"avg_ms": mean_ms[k], "launches_per_step": len(per_kernel[k]) // 2,
+                      "share": tot_ms[k] / sum(tot_ms.values()),
+                      "GBps": (sb[k] / (mean_ms[k] * 1e-3) / 1e9) if k in sb else None,
+                      "TFLOPs": (sf[k] / (mean_ms[k] * 1e-3) / 1e12) if k in sf else None} for k in mean_ms}
+            if dom == "mpnn_forward_fused":
+                # the fused kernel keeps every activation on chip: 2.7 kFLOP per byte of index stream, far right of
+                # the ridge (211 FLOP/B) => the tensor roofline is the one that bounds it
+                ach = sf[dom] / (mean_ms[dom] * 1e-3) / 1e12
+                roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                            "frac": ach / tf_peak, "traffic": None, "peak_source": peak_src + ", sustained bf16",
+                            "algorithmic_flop_per_launch": sf[dom], "algorithmic_bytes_per_launch": sb[dom],
+                            "hbm_GBps_on_algorithmic_bytes": sb[dom] / (mean_ms[dom] * 1e-3) / 1e9,
+                            "hbm_frac": sb[dom] / (mean_ms[dom] * 1e-3) / 1e9 / hbm_peak}
+            else:
+                ach = sb.get(dom, 0) / (mean_ms[dom] * 1e-3) / 1e9
+                roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": sb.get(dom)}
+            roofline.update({"avg_launch_ms": mean_ms[dom], "share_of_step": tot_ms[dom] / sum(tot_ms.values()),
+                             "per_kernel": pk})
         cpu = None
         if not args.no_cpu_baseline:
             r = cpu_reference_run(kind, args.cpu_sample_pairs, 3, 1, args.skewed)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if args.precision == "fp32" else "bf16 operands, f32 accumulate/storage", "data": "synthetic",
+                "dtype": {"fp32": "f32", "bf16": "bf16", "bf16_precise": "bf16", "fp16": "f16",
+                          "fp16_precise": "f16"}[args.precision] + ("" if args.precision == "fp32" else
+                                                                    " operands, f32 accumulate, f32 atom states"),
+                "data": "synthetic",
                 "config": {"workload": name, "pairs_per_gpu": P, "atoms_per_gpu": batch.n_atoms,
                            "edges_per_gpu": batch.n_edges, "unique_edges_per_gpu": batch.n_unique,
                            "bond_types": "zipf1.2" if args.skewed else "uniform", "precision": args.precision,
-                           "l2_policy": "inputs larger than L2 (activations %.1f GB per GPU)" % (3 * batch.n_atoms * d * 4 / 1e9),
+                           "path": "fused whole-tower kernel" if model.use_fused(batch) else "staged per-layer kernels",
+                           "l2_policy": "inputs larger than L2 (%.1f GB of indices%s per GPU)" % (
+                               batch.nbytes() / 1e9, "" if model.use_fused(batch) else
+                               " + %.1f GB of activations" % (3 * batch.n_atoms * d * 4 / 1e9)),
                            "parallelism": f"pairs sharded over {world} GPU(s), no collective",
                            "host_synth_and_pack_s": round(t_pack, 2)},
                 "edges_per_s": batch.n_edges * world * args.steps / (ms_total * 1e-3),
-                "gpu_launches": model.launches_per_forward() * args.steps,
+                "gpu_launches": model.launches_per_forward(batch) * args.steps,
                 "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -147,13 +147,18 @@ int imp_gated_update(const float* d_h, const float* d_agg, int32_t n_atoms, int3
  *                   log_eta = A + B / (T/100 + C + 1e-6)      (:204-214, models/layers.py:10-42)
  *       melting pt  Dense(fp2, relu) -> Dense(1)               (train_melting_point.py:191-198)
  * ------------------------------------------------------------------------------------------- */
-/* K5 on the tensor cores (tcgen05, bf16 operands, fp32 accumulation in TMEM; the "2e-2" path).  Weights are
+/* K5 on the tensor cores (tcgen05, 16-bit operands, fp32 accumulation in TMEM; the "2e-2" path).  Weights are
  * packed once per weight update into the UMMA operand layout: imp_gru_pack_bytes(d) bytes per (tower, step).
- * precise_epilogue != 0 uses expf / tanhf / sqrtf in the gate epilogue instead of tanh.approx / rsqrt. */
+ * flags (IMP_TC_*, the same for pack and update): IMP_TC_FP16 = IEEE-half operands instead of bfloat16;
+ * IMP_TC_PRECISE_EPILOGUE = expf / tanhf / sqrtf in the gate epilogue instead of tanh.approx / rsqrt. */
+#define IMP_TC_FP16 1
+#define IMP_TC_PRECISE_EPILOGUE 2
+#define IMP_TC_MP8 4
 int64_t imp_gru_pack_bytes(int32_t d);
 int imp_gru_pack_bf16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
+int imp_gru_pack_f16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
 int imp_gated_update_tc(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
-                        const void* d_packed_cat, const void* d_packed_an, float eps, int32_t precise_epilogue,
+                        const void* d_packed_cat, const void* d_packed_an, float eps, int32_t flags,
                         float* d_h_out, void* stream);
 
 /* GlobalSumPool.call alone (models/layers.py:161-164): out[m,:] = sum of h rows of molecule m whose
@@ -180,8 +185,42 @@ int imp_pool_head_mp(const imp_graph_t* g, const float* d_h, int32_t d, int32_t 
                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Diagnostics: one-CTA tcgen05 product D[128,N] = A[128,K] * B[N,K]^T (kind 0 = bf16, 1 = tf32 operands,
- * fp32 accumulate) through the library's own shared-memory staging layout and UMMA descriptors.  Used by
+ * Fused forward (the throughput path): Embedding(atom) -> [BondMatrixMessage o Reduce -> GatedUpdate] x steps ->
+ * GlobalSumPool for BOTH towers in one persistent tcgen05 kernel; atom states never leave the SM between steps.
+ * Replaces train_viscosity.py:163,171-187 (the `encode` loop) + models/layers.py:57-164 for atom_dim 32,
+ * bond_dim 8, steps <= 4, molecules <= 128 atoms.  Other shapes: the staged kernels above (IMP_ERR_DIM here).
+ *
+ *   imp_fused_pack     once per weight update and per (tower, step): bond_transform (K,d,d) and the eight
+ *                      GatedUpdate variables -> one UMMA-ready block of imp_fused_pack_bytes() bytes.
+ *                      d_packed of imp_mpnn_forward_fused is [2 towers][steps] such blocks, cation first.
+ *   flags              IMP_TC_FP16: 16-bit operands are IEEE half (11-bit significand) instead of bfloat16;
+ *                      both accumulate in fp32.  Must match between pack and forward.
+ *                      IMP_TC_PRECISE_EPILOGUE: expf/tanhf/sqrtf instead of tanh.approx/rsqrt.
+ *                      IMP_TC_MP8: smaller register tile in the Z build (tuning switch, same results).
+ *   max_mol_atoms      largest molecule of the batch (the caller knows it from mol_ptr); > 128 is refused.
+ *   d_pooled           [2 * n_pairs, d] molecule sums in mol_ptr order -> imp_readout_visc / imp_readout_mp.
+ *   d_status           optional device int, set to 1 if the kernel met a molecule that does not fit a tile.
+ * ------------------------------------------------------------------------------------------- */
+int64_t imp_fused_pack_bytes(int32_t d, int32_t bond_dim);
+int imp_fused_pack(const float* d_bond_transform /* [K,d,d] */, const imp_gru_weights_t* w, int32_t d, int32_t bond_dim,
+                   int32_t flags, void* d_packed, void* stream);
+int imp_mpnn_forward_fused(const imp_graph_t* g, const float* d_atom_emb, int32_t atom_vocab, const float* d_bond_emb,
+                           int32_t d, int32_t bond_dim, int32_t steps, const void* d_packed, float eps, int32_t flags,
+                           int32_t max_mol_atoms, float* d_pooled, int32_t* d_status, void* stream);
+
+/* K6 without the pooling stage: Dense(fp, relu), Dense(mix, relu) per tower, AddTwoTensors, head
+ * (train_viscosity.py:189-214 / train_melting_point.py:173-198) on molecule sums [2P, d] (cations first). */
+int imp_readout_visc(const float* d_pooled, int32_t n_pairs, int32_t d, int32_t fp, int32_t mix,
+                     const imp_readout_weights_t* w_cat, const imp_readout_weights_t* w_an, const float* d_W_head,
+                     const float* d_b_head, const float* d_T, float* d_out, float* d_aux, void* stream);
+int imp_readout_mp(const float* d_pooled, int32_t n_pairs, int32_t d, int32_t fp, int32_t mix, int32_t fp2,
+                   const imp_readout_weights_t* w_cat, const imp_readout_weights_t* w_an, const float* d_W1,
+                   const float* d_b1, const float* d_W2, const float* d_b2, float* d_out, float* d_aux, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Diagnostics: one-CTA tcgen05 product D[128,N] = A[128,K] * B[N,K]^T (kind 0 = bf16, 1 = tf32 operands from
+ * shared memory; 2 = bf16, 3 = f16 with the A operand written to tensor memory by the threads, the form the fused
+ * forward uses; fp32 accumulate) through the library's own shared-memory staging layout and UMMA descriptors.  Used by
  * tests/test_gpu_tensor.py to validate the tensor-core plumbing in isolation.
  * ------------------------------------------------------------------------------------------- */
 int imp_tc_selftest(const float* d_A, const float* d_B, float* d_D, int32_t N, int32_t K, int32_t kind,

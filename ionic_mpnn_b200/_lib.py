@@ -39,6 +39,9 @@ class ReadoutWeights(C.Structure):
     _fields_ = [(n, vp) for n in ("W_fp", "b_fp", "W_mix", "b_mix")]
 
 
+TC_FP16 = 1
+TC_PRECISE_EPILOGUE = 2
+TC_MP8 = 4
 PACK_DOUBLE_EDGES = 1
 PACK_SHIFT_IDS = 2
 
@@ -62,12 +65,21 @@ SIGNATURES = {
                                    C.c_float, vp, vp]),
     "imp_gru_pack_bytes": (C.c_int64, [C.c_int32]),
     "imp_gru_pack_bf16": (C.c_int, [C.POINTER(GruWeights), C.c_int32, vp, vp]),
+    "imp_gru_pack_f16": (C.c_int, [C.POINTER(GruWeights), C.c_int32, vp, vp]),
     "imp_gated_update_tc": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_float, C.c_int32, vp, vp]),
     "imp_global_sum_pool": (C.c_int, [vp, vp, C.c_int32, vp, C.c_int32, vp, vp]),
     "imp_pool_head_visc": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ReadoutWeights),
                                      C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp]),
     "imp_pool_head_mp": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.POINTER(ReadoutWeights), C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp, vp]),
+    "imp_fused_pack_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "imp_fused_pack": (C.c_int, [vp, C.POINTER(GruWeights), C.c_int32, C.c_int32, C.c_int32, vp, vp]),
+    "imp_mpnn_forward_fused": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_float,
+                                         C.c_int32, C.c_int32, vp, vp, vp]),
+    "imp_readout_visc": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ReadoutWeights),
+                                   C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp]),
+    "imp_readout_mp": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ReadoutWeights),
+                                 C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp, vp]),
     "imp_tc_selftest": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
 }
 

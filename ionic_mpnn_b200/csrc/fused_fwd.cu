@@ -1,0 +1,466 @@
+// Whole-tower fused MPNN forward on sm_100a: Embedding -> [BondMatrixMessage o Reduce -> GatedUpdate] x S ->
+// GlobalSumPool in ONE persistent kernel, atom states resident on chip for all S steps.
+//
+// Replaces, for atom_dim 32 / bond_dim 8 / <= 4 steps (the viscosity model of train_viscosity.py:139-231):
+//   Embedding(atom)                     train_viscosity.py:163,171
+//   BondMatrixMessage.call + Reduce     models/layers.py:100-117, 57-83
+//   GatedUpdate.call                    models/layers.py:142-156
+//   GlobalSumPool.call                  models/layers.py:161-164
+//
+// Why it can be fused: no edge crosses a molecule, so a tile of whole molecules (<= 128 atoms) is closed under
+// message passing.  HBM traffic drops from ~5 activation round trips per step to the index stream only
+// (~23 B/atom + 8 B/entry); the kernel is bound by the SM's FP32 issue rate, not by memory.
+//
+// Re-association that turns the per-edge mat-vec into a dense GEMM.  With A_e = sum_k c_e[k] W_k
+// (models/layers.py:108, c_e = bond embedding row) the aggregated message of destination v is
+//     agg[v][l] = sum_e mult_e sum_m A_e[l][m] h[src_e][m]
+//               = sum_{m,k} W[k][l][m] * Z[v][m*8+k],      Z[v][m*8+k] = sum_e mult_e c_e[k] h[src_e][m]
+// so agg = Z (128 x 256) . Wc (256 x 32).  Z is built by the thread that owns row v (fp32 FMA, CSR order,
+// deterministic), rounded to 16 bits and written straight into TENSOR MEMORY (tcgen05.st); all GEMMs take their A
+// operand from TMEM (tcgen05.mma "TS" form) and their B operand (pre-packed weights, resident for all S steps) from
+// shared memory, accumulate in fp32 in TMEM, and are read back with tcgen05.ld so that one thread owns one atom row:
+// gates, blend, LayerNorm and residual need no cross-thread traffic.
+//
+// CTA = 256 threads = 2 independent warpgroups, each running its own 128-row tile pipeline on its own 256 TMEM
+// columns, sharing the tower's weights in shared memory.  One CTA per SM, persistent; CTAs [0, n_cta_cat) serve the
+// cation tower, the rest the anion tower (weights are per tower: train_viscosity.py:176-189).
+//
+// TMEM columns of a warpgroup (base = 256 * wg):
+//   [  0,128)  Z, 16-bit pairs (K = 256)        -- dead after GEMM1, then reused:
+//   [  0, 16)  h   operand (K = 32)   [ 16, 32)  agg operand    [ 32, 48)  r*h operand
+//   [128,160)  GEMM1 accumulator (agg, fp32)    [160,224)  z | r pre-activations    [224,256)  candidate pre-activation
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace imp {
+
+constexpr int FZ_ROWS = 128;      // rows per tile = TMEM lanes
+constexpr int FZ_D = 32;          // atom_dim
+constexpr int FZ_K = 8;           // bond_dim
+constexpr int FZ_GROUP = 64;      // molecules per scheduling unit
+constexpr int FZ_HS = 36;         // floats per h row in shared memory (144 B: conflict-free 16-byte row reads)
+constexpr int FZ_CS = 12;         // floats per bond-coefficient row (48 B)
+constexpr int FZ_MAX_STEPS = 4;
+constexpr int FZ_MAX_VB = 256;
+
+struct FusedPack {  // one (tower, step)
+  static constexpr int WC_BYTES = FZ_D * (FZ_D * FZ_K) * 2;  // Wc[n = l][kk = m*8+k], chunk-major, 16 KiB
+  static constexpr int BZR_BYTES = 2 * FZ_D * 2 * FZ_D * 2;  // [Wz | Wr]^T, 8 KiB
+  static constexpr int BH_BYTES = FZ_D * 2 * FZ_D * 2;       // Wh^T, 4 KiB
+  static constexpr int BIAS_FLOATS = 5 * FZ_D;               // bz, br, bh, gamma, beta
+  static constexpr int OFF_BZR = WC_BYTES;
+  static constexpr int OFF_BH = OFF_BZR + BZR_BYTES;
+  static constexpr int OFF_BIAS = OFF_BH + BH_BYTES;
+  static constexpr int BYTES = OFF_BIAS + BIAS_FLOATS * 4;   // 29 312
+};
+static_assert(FusedPack::BYTES % 128 == 0, "pack must keep 128-byte alignment of the next step");
+
+template <int FMT>
+__global__ void fused_pack_kernel(const float* __restrict__ W /* [K, d, d] */, imp_gru_weights_t w,
+                                  unsigned char* __restrict__ out) {
+  constexpr int D = FZ_D, KK = FZ_D * FZ_K;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < D * KK) {  // Wc[n = l][kk = m*8 + k] = W[k][l][m]
+    const int l = i / KK, kk = i % KK, m = kk / FZ_K, k = kk % FZ_K;
+    *reinterpret_cast<uint16_t*>(out + tc::chunk_off(l, kk / 8, D) + (kk % 8) * 2) = tc::cvt16<FMT>(W[(k * D + l) * D + m]);
+  }
+  if (i < 2 * D * 2 * D) {  // Bzr[n][k] = (n < D ? Wz[k][n] : Wr[k][n - D])
+    const int n = i / (2 * D), k = i % (2 * D);
+    const float v = n < D ? w.Wz[k * D + n] : w.Wr[k * D + (n - D)];
+    *reinterpret_cast<uint16_t*>(out + FusedPack::OFF_BZR + tc::chunk_off(n, k / 8, 2 * D) + (k % 8) * 2) = tc::cvt16<FMT>(v);
+  }
+  if (i < D * 2 * D) {  // Bh[n][k] = Wh[k][n]
+    const int n = i / (2 * D), k = i % (2 * D);
+    *reinterpret_cast<uint16_t*>(out + FusedPack::OFF_BH + tc::chunk_off(n, k / 8, D) + (k % 8) * 2) = tc::cvt16<FMT>(w.Wh[k * D + n]);
+  }
+  if (i < D) {
+    float* b = reinterpret_cast<float*>(out + FusedPack::OFF_BIAS);
+    b[i] = w.bz[i], b[D + i] = w.br[i], b[2 * D + i] = w.bh[i], b[3 * D + i] = w.gamma[i], b[4 * D + i] = w.beta[i];
+  }
+}
+
+struct FusedArgs {
+  const int* mol_ptr;
+  const int* atom_id;
+  const int* row_ptr;
+  const int* col_src;
+  const int* edge_bm;
+  const float* atom_emb;
+  const float* bond_emb;
+  const unsigned char* packed;  // [2][steps][FusedPack::BYTES]
+  float* pooled;                // [2P][32]
+  int* status;                  // optional: set to 1 if a molecule does not fit one tile
+  int n_pairs, atom_vocab, bond_vocab, steps, n_cta_cat;
+  float eps;
+};
+
+struct alignas(16) FusedWgSmem {
+  float h[FZ_ROWS * FZ_HS];
+  int molp[FZ_GROUP + 4];
+  unsigned char amask[FZ_ROWS];
+  uint64_t bar[4];
+};
+
+struct FusedCtl {
+  uint32_t tmem_base;
+  uint32_t pad[3];
+};
+
+__host__ __device__ inline int fused_smem_bytes(int steps, int bond_vocab) {
+  const int ctab = (bond_vocab * FZ_CS * 4 + 127) / 128 * 128;
+  return steps * FusedPack::BYTES + ctab + 2 * (int)sizeof(FusedWgSmem) + (int)sizeof(FusedCtl);
+}
+
+__device__ __forceinline__ float fz_tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool PRECISE>
+__device__ __forceinline__ float fz_sigmoid(float x) {
+  if (PRECISE) return 1.0f / (1.0f + expf(-x));
+  return fmaf(0.5f, fz_tanh_fast(0.5f * x), 0.5f);
+}
+template <bool PRECISE>
+__device__ __forceinline__ float fz_tanh(float x) {
+  return PRECISE ? tanhf(x) : fz_tanh_fast(x);
+}
+
+// MP = number of h columns (m) handled per pass over a row's entries: MP*8 fp32 accumulators live in registers.
+template <int FMT, bool PRECISE, int MP>
+__global__ void __launch_bounds__(256, 1) mpnn_fused_kernel(const FusedArgs a) {
+  static_assert(MP == 8 || MP == 16, "MP");
+  constexpr int D = FZ_D;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = tid >> 7, t = tid & 127;
+  const int wbytes = a.steps * FusedPack::BYTES;
+  const int ctab_bytes = (a.bond_vocab * FZ_CS * 4 + 127) / 128 * 128;
+  float* s_ctab = reinterpret_cast<float*>(smem + wbytes);
+  FusedWgSmem& ws = reinterpret_cast<FusedWgSmem*>(smem + wbytes + ctab_bytes)[wg];
+  FusedCtl& ctl = *reinterpret_cast<FusedCtl*>(smem + wbytes + ctab_bytes + 2 * sizeof(FusedWgSmem));
+
+  const int tower = blockIdx.x >= a.n_cta_cat;
+  {  // resident weights of this tower (all steps), bond coefficients
+    const uint4* src = reinterpret_cast<const uint4*>(a.packed + (size_t)tower * wbytes);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = tid; i < wbytes / 16; i += 256) dst[i] = __ldg(src + i);
+    for (int i = tid; i < a.bond_vocab * FZ_K; i += 256) s_ctab[(i / FZ_K) * FZ_CS + (i % FZ_K)] = __ldg(a.bond_emb + i);
+  }
+  if (warp == 0) tc::tmem_alloc<512>(&ctl.tmem_base);
+  if (t == 0) {
+    tc::mbar_init(&ws.bar[0], 1);
+    tc::mbar_init(&ws.bar[1], 1);
+    tc::mbar_init(&ws.bar[2], 1);
+    tc::mbar_fence_init();
+  }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+
+  const uint32_t tbase = ctl.tmem_base + (uint32_t)(wg * 256);
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t tZ = tbase, tAh = tbase, tAagg = tbase + 16, tArh = tbase + 32;
+  const uint32_t tCagg = tbase + 128, tCzr = tbase + 160, tCht = tbase + 224;
+  const uint32_t idesc32 = tc::make_idesc(FMT, FZ_ROWS, D), idesc64 = tc::make_idesc(FMT, FZ_ROWS, 2 * D);
+  const uint32_t sw0 = tc::smem_u32(smem);
+  const int bar_id = 1 + wg;
+
+  const int P = a.n_pairs;
+  const int n_groups = (P + FZ_GROUP - 1) / FZ_GROUP;
+  const int n_cta_tower = tower ? (int)gridDim.x - a.n_cta_cat : a.n_cta_cat;
+  const int cta_in_tower = tower ? (int)blockIdx.x - a.n_cta_cat : (int)blockIdx.x;
+  const float4* emb4 = reinterpret_cast<const float4*>(a.atom_emb);
+  float* hrow = &ws.h[t * FZ_HS];
+  uint32_t ph = 0;
+
+  for (int g = cta_in_tower * 2 + wg; g < n_groups; g += n_cta_tower * 2) {
+    const int m0 = g * FZ_GROUP, nm = min(FZ_GROUP, P - m0);
+    const int base_mol = tower * P + m0;
+    tc::named_bar_sync(bar_id, 128);
+    if (t <= nm) ws.molp[t] = __ldg(a.mol_ptr + base_mol + t);
+    tc::named_bar_sync(bar_id, 128);
+    int ms = 0;
+    while (ms < nm) {
+      const int a0 = ws.molp[ms];
+      int me = ms + 1;
+      while (me < nm && ws.molp[me + 1] - a0 <= FZ_ROWS) ++me;
+      int rows = ws.molp[me] - a0;
+      if (rows > FZ_ROWS) {  // a single molecule larger than a tile: flagged, never read out of bounds
+        if (t == 0 && a.status) *a.status = 1;
+        rows = FZ_ROWS;
+      }
+      // ---------------------------------------------------------------- Embedding(atom)
+      const bool valid = t < rows;
+      int aid = 0, e0 = 0, e1 = 0;
+      if (valid) {
+        aid = __ldg(a.atom_id + a0 + t);
+        e0 = __ldg(a.row_ptr + a0 + t);
+        e1 = __ldg(a.row_ptr + a0 + t + 1);
+      }
+      {
+        const int id = min(max(aid, 0), a.atom_vocab - 1);
+#pragma unroll
+        for (int c = 0; c < D / 4; ++c)
+          reinterpret_cast<float4*>(hrow)[c] = valid ? __ldg(emb4 + id * (D / 4) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ws.amask[t] = (valid && aid > 0) ? 1 : 0;  // models/layers.py:163
+      }
+      tc::named_bar_sync(bar_id, 128);
+
+      for (int s = 0; s < a.steps; ++s) {
+        const uint32_t sw = sw0 + (uint32_t)(s * FusedPack::BYTES);
+        const float* bias = reinterpret_cast<const float*>(smem + s * FusedPack::BYTES + FusedPack::OFF_BIAS);
+        // ------------------------------------------------------------ Z rows -> TMEM
+#pragma unroll 1
+        for (int pass = 0; pass < D / MP; ++pass) {
+          float acc[MP * FZ_K];
+#pragma unroll
+          for (int i = 0; i < MP * FZ_K; ++i) acc[i] = 0.f;
+#pragma unroll 1
+          for (int e = e0; e < e1; ++e) {
+            const int bm = __ldg(a.edge_bm + e);
+            int src = __ldg(a.col_src + e) - a0;
+            src = min(max(src, 0), FZ_ROWS - 1);
+            const float mult = (float)(bm >> 16);
+            const int bond = min(bm & 0xffff, a.bond_vocab - 1);
+            const float4 ca = *reinterpret_cast<const float4*>(s_ctab + bond * FZ_CS);
+            const float4 cb = *reinterpret_cast<const float4*>(s_ctab + bond * FZ_CS + 4);
+            const float c[FZ_K] = {ca.x * mult, ca.y * mult, ca.z * mult, ca.w * mult,
+                                   cb.x * mult, cb.y * mult, cb.z * mult, cb.w * mult};
+            const float4* hp = reinterpret_cast<const float4*>(&ws.h[src * FZ_HS + pass * MP]);
+#pragma unroll
+            for (int q = 0; q < MP / 4; ++q) {
+              const float4 hv = hp[q];
+              const float hs[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int k = 0; k < FZ_K; ++k) acc[(q * 4 + j) * FZ_K + k] = fmaf(hs[j], c[k], acc[(q * 4 + j) * FZ_K + k]);
+            }
+          }
+#pragma unroll
+          for (int ch = 0; ch < MP * FZ_K / 64; ++ch) {
+            uint32_t r[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = tc::pack2<FMT>(acc[ch * 64 + 2 * i], acc[ch * 64 + 2 * i + 1]);
+            tc::tmem_st32(tZ + lane_off + (uint32_t)(pass * (MP * FZ_K / 2) + ch * 32), r);
+          }
+        }
+        tc::tmem_wait_st();
+        tc::fence_before_thread_sync();
+        tc::named_bar_sync(bar_id, 128);
+        // ------------------------------------------------------------ GEMM1: agg = Z . Wc
+        if (t == 0) {
+          tc::fence_after_thread_sync();
+#pragma unroll
+          for (int ks = 0; ks < D * FZ_K / 16; ++ks)
+            tc::mma_f16_ts(tCagg, tZ + 8 * ks, tc::make_smem_desc(sw + ks * 1024, D * 16, 128), idesc32, ks > 0);
+          tc::mma_commit(&ws.bar[0]);
+        }
+        tc::mbar_wait(&ws.bar[0], ph);
+        tc::fence_after_thread_sync();
+        {  // agg and h rows as 16-bit A operands (the Z columns are dead now)
+          float v[32];
+          tc::tmem_ld32(tCagg + lane_off, v);
+          uint32_t r[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = tc::pack2<FMT>(v[2 * i], v[2 * i + 1]);
+          tc::tmem_st16(tAagg + lane_off, r);
+#pragma unroll
+          for (int c = 0; c < D / 4; ++c) {
+            const float4 x = reinterpret_cast<const float4*>(hrow)[c];
+            r[2 * c] = tc::pack2<FMT>(x.x, x.y), r[2 * c + 1] = tc::pack2<FMT>(x.z, x.w);
+          }
+          tc::tmem_st16(tAh + lane_off, r);
+        }
+        tc::tmem_wait_st();
+        tc::fence_before_thread_sync();
+        tc::named_bar_sync(bar_id, 128);
+        // ------------------------------------------------------------ GEMM2: [h | agg] . [Wz | Wr]; GEMM3a: agg . Wh[d:2d]
+        if (t == 0) {
+          tc::fence_after_thread_sync();
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            tc::mma_f16_ts(tCzr, tAh + 8 * ks, tc::make_smem_desc(sw + FusedPack::OFF_BZR + ks * 2048, 2 * D * 16, 128),
+                           idesc64, ks > 0);
+          tc::mma_commit(&ws.bar[1]);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            tc::mma_f16_ts(tCht, tAagg + 8 * ks, tc::make_smem_desc(sw + FusedPack::OFF_BH + (ks + 2) * 1024, D * 16, 128),
+                           idesc32, ks > 0);
+        }
+        tc::mbar_wait(&ws.bar[1], ph);
+        tc::fence_after_thread_sync();
+        float z[D];
+        {
+          float v[32];
+          tc::tmem_ld32(tCzr + lane_off, v);
+#pragma unroll
+          for (int j = 0; j < D; ++j) z[j] = fz_sigmoid<PRECISE>(v[j] + bias[j]);
+          tc::tmem_ld32(tCzr + D + lane_off, v);
+          uint32_t r[16];
+#pragma unroll
+          for (int c = 0; c < D / 4; ++c) {
+            const float4 x = reinterpret_cast<const float4*>(hrow)[c];
+            const float r0 = fz_sigmoid<PRECISE>(v[4 * c] + bias[D + 4 * c]) * x.x;
+            const float r1 = fz_sigmoid<PRECISE>(v[4 * c + 1] + bias[D + 4 * c + 1]) * x.y;
+            const float r2 = fz_sigmoid<PRECISE>(v[4 * c + 2] + bias[D + 4 * c + 2]) * x.z;
+            const float r3 = fz_sigmoid<PRECISE>(v[4 * c + 3] + bias[D + 4 * c + 3]) * x.w;
+            r[2 * c] = tc::pack2<FMT>(r0, r1), r[2 * c + 1] = tc::pack2<FMT>(r2, r3);
+          }
+          tc::tmem_st16(tArh + lane_off, r);
+        }
+        tc::tmem_wait_st();
+        tc::fence_before_thread_sync();
+        tc::named_bar_sync(bar_id, 128);
+        // ------------------------------------------------------------ GEMM3b: += (r*h) . Wh[0:d]
+        if (t == 0) {
+          tc::fence_after_thread_sync();
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            tc::mma_f16_ts(tCht, tArh + 8 * ks, tc::make_smem_desc(sw + FusedPack::OFF_BH + ks * 1024, D * 16, 128), idesc32,
+                           true);
+          tc::mma_commit(&ws.bar[2]);
+        }
+        tc::mbar_wait(&ws.bar[2], ph);
+        tc::fence_after_thread_sync();
+        {  // candidate, blend, LayerNorm (biased variance, eps), residual  (models/layers.py:151-156)
+          float gq[32], hq[32];
+          tc::tmem_ld32(tCht + lane_off, gq);
+#pragma unroll
+          for (int c = 0; c < D / 4; ++c) {
+            const float4 x = reinterpret_cast<const float4*>(hrow)[c];
+            hq[4 * c] = x.x, hq[4 * c + 1] = x.y, hq[4 * c + 2] = x.z, hq[4 * c + 3] = x.w;
+          }
+          float mean = 0.f;
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            const float ht = fz_tanh<PRECISE>(gq[j] + bias[2 * D + j]);
+            gq[j] = fmaf(z[j], ht - hq[j], hq[j]);
+            mean += gq[j];
+          }
+          mean *= (1.0f / D);
+          float var = 0.f;
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            const float cdev = gq[j] - mean;
+            var = fmaf(cdev, cdev, var);
+          }
+          const float inv = PRECISE ? 1.0f / sqrtf(var * (1.0f / D) + a.eps) : rsqrtf(var * (1.0f / D) + a.eps);
+#pragma unroll
+          for (int c = 0; c < D / 4; ++c) {
+            float4 o;
+            o.x = fmaf((gq[4 * c] - mean) * inv, bias[3 * D + 4 * c], bias[4 * D + 4 * c]) + hq[4 * c];
+            o.y = fmaf((gq[4 * c + 1] - mean) * inv, bias[3 * D + 4 * c + 1], bias[4 * D + 4 * c + 1]) + hq[4 * c + 1];
+            o.z = fmaf((gq[4 * c + 2] - mean) * inv, bias[3 * D + 4 * c + 2], bias[4 * D + 4 * c + 2]) + hq[4 * c + 2];
+            o.w = fmaf((gq[4 * c + 3] - mean) * inv, bias[3 * D + 4 * c + 3], bias[4 * D + 4 * c + 3]) + hq[4 * c + 3];
+            reinterpret_cast<float4*>(hrow)[c] = o;
+          }
+        }
+        tc::fence_before_thread_sync();
+        tc::named_bar_sync(bar_id, 128);
+        ph ^= 1;
+      }
+      // ---------------------------------------------------------------- GlobalSumPool: warp per molecule, lane = column
+      for (int mi = ms + (t >> 5); mi < me; mi += 4) {
+        const int lo = ws.molp[mi] - a0, hi = min(ws.molp[mi + 1] - a0, FZ_ROWS);
+        float sacc = 0.f;
+        for (int r = lo; r < hi; ++r)
+          if (ws.amask[r]) sacc += ws.h[r * FZ_HS + lane];
+        a.pooled[(size_t)(base_mol + mi) * D + lane] = sacc;
+      }
+      tc::named_bar_sync(bar_id, 128);
+      ms = me;
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(ctl.tmem_base);
+}
+
+}  // namespace imp
+
+using namespace imp;
+
+extern "C" int64_t imp_fused_pack_bytes(int32_t d, int32_t bond_dim) {
+  return (d == FZ_D && bond_dim == FZ_K) ? (int64_t)FusedPack::BYTES : (int64_t)IMP_ERR_DIM;
+}
+
+extern "C" int imp_fused_pack(const float* d_bond_transform, const imp_gru_weights_t* w, int32_t d, int32_t bond_dim,
+                              int32_t flags, void* d_packed, void* stream) {
+  IMP_REQUIRE(d_bond_transform && d_packed && w && w->Wz && w->bz && w->Wr && w->br && w->Wh && w->bh && w->gamma && w->beta,
+              IMP_ERR_ARG, "imp_fused_pack: null pointer");
+  IMP_REQUIRE(d == FZ_D && bond_dim == FZ_K, IMP_ERR_DIM, "imp_fused_pack: the fused path is built for atom_dim %d, bond_dim %d (got %d, %d)",
+              FZ_D, FZ_K, d, bond_dim);
+  const int n = FZ_D * FZ_D * FZ_K;
+  if (flags & IMP_TC_FP16)
+    fused_pack_kernel<tc::FMT_F16><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed);
+  else
+    fused_pack_kernel<tc::FMT_BF16><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+static int fused_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  }
+  return n;
+}
+
+template <int FMT, bool PRECISE, int MP>
+static int launch_fused(const FusedArgs& a, int grid, size_t smem, cudaStream_t stream) {
+  IMP_CUDA(cudaFuncSetAttribute(mpnn_fused_kernel<FMT, PRECISE, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mpnn_fused_kernel<FMT, PRECISE, MP><<<grid, 256, smem, stream>>>(a);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int imp_mpnn_forward_fused(const imp_graph_t* g, const float* d_atom_emb, int32_t atom_vocab,
+                                      const float* d_bond_emb, int32_t d, int32_t bond_dim, int32_t steps,
+                                      const void* d_packed, float eps, int32_t flags, int32_t max_mol_atoms,
+                                      float* d_pooled, int32_t* d_status, void* stream) {
+  IMP_REQUIRE(g, IMP_ERR_ARG, "imp_mpnn_forward_fused: graph is null");
+  IMP_REQUIRE(g->n_pairs >= 0 && g->n_atoms >= 0 && g->n_cat_atoms >= 0 && g->n_cat_atoms <= g->n_atoms, IMP_ERR_ARG,
+              "imp_mpnn_forward_fused: bad graph sizes");
+  IMP_REQUIRE(d == FZ_D && bond_dim == FZ_K, IMP_ERR_DIM,
+              "imp_mpnn_forward_fused: built for atom_dim %d, bond_dim %d (got %d, %d); use the staged kernels", FZ_D, FZ_K, d, bond_dim);
+  IMP_REQUIRE(steps >= 1 && steps <= FZ_MAX_STEPS, IMP_ERR_DIM, "imp_mpnn_forward_fused: 1..%d steps (got %d)", FZ_MAX_STEPS, steps);
+  IMP_REQUIRE(g->bond_vocab >= 1 && g->bond_vocab <= FZ_MAX_VB && atom_vocab >= 1, IMP_ERR_DIM,
+              "imp_mpnn_forward_fused: bond vocabulary must be in 1..%d", FZ_MAX_VB);
+  IMP_REQUIRE(max_mol_atoms <= FZ_ROWS, IMP_ERR_DIM,
+              "imp_mpnn_forward_fused: a molecule has %d atoms, a tile holds %d; use the staged kernels", max_mol_atoms, FZ_ROWS);
+  if (g->n_pairs == 0) return 0;
+  IMP_REQUIRE(d_atom_emb && d_bond_emb && d_packed && d_pooled && g->mol_ptr && g->atom_id && g->row_ptr, IMP_ERR_ARG,
+              "imp_mpnn_forward_fused: null pointer");
+  IMP_REQUIRE(g->n_unique == 0 || (g->col_src && g->edge_bm), IMP_ERR_ARG, "imp_mpnn_forward_fused: null edge arrays");
+  IMP_REQUIRE(imp_device_is_sm100(), IMP_ERR_UNSUPPORTED, "imp_mpnn_forward_fused: tcgen05 needs an sm_100 device");
+  FusedArgs a;
+  a.mol_ptr = g->mol_ptr, a.atom_id = g->atom_id, a.row_ptr = g->row_ptr, a.col_src = g->col_src, a.edge_bm = g->edge_bm;
+  a.atom_emb = d_atom_emb, a.bond_emb = d_bond_emb, a.packed = (const unsigned char*)d_packed, a.pooled = d_pooled;
+  a.status = d_status, a.n_pairs = g->n_pairs, a.atom_vocab = atom_vocab, a.bond_vocab = g->bond_vocab, a.steps = steps, a.eps = eps;
+  // one persistent CTA per SM; CTAs are split between the towers in proportion to their atoms
+  const int sms = fused_sm_count();
+  const int n_groups = (int)ceil_div(g->n_pairs, FZ_GROUP);
+  const int want = (int)ceil_div(n_groups, 2);  // two warpgroups per CTA
+  int n_cat = (int)((int64_t)sms * g->n_cat_atoms / (g->n_atoms > 0 ? g->n_atoms : 1));
+  n_cat = n_cat < 1 ? 1 : (n_cat > sms - 1 ? sms - 1 : n_cat);
+  int n_an = sms - n_cat;
+  if (n_cat > want) n_cat = want;
+  if (n_an > want) n_an = want;
+  a.n_cta_cat = n_cat;
+  const int grid = n_cat + n_an;
+  const size_t smem = (size_t)fused_smem_bytes(steps, g->bond_vocab);
+  IMP_REQUIRE(smem <= 227 * 1024, IMP_ERR_DIM, "imp_mpnn_forward_fused: needs %zu B of shared memory", smem);
+  const bool f16 = flags & IMP_TC_FP16, precise = flags & IMP_TC_PRECISE_EPILOGUE, mp8 = flags & IMP_TC_MP8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f16) {
+    if (precise) return mp8 ? launch_fused<tc::FMT_F16, true, 8>(a, grid, smem, st) : launch_fused<tc::FMT_F16, true, 16>(a, grid, smem, st);
+    return mp8 ? launch_fused<tc::FMT_F16, false, 8>(a, grid, smem, st) : launch_fused<tc::FMT_F16, false, 16>(a, grid, smem, st);
+  }
+  if (precise) return mp8 ? launch_fused<tc::FMT_BF16, true, 8>(a, grid, smem, st) : launch_fused<tc::FMT_BF16, true, 16>(a, grid, smem, st);
+  return mp8 ? launch_fused<tc::FMT_BF16, false, 8>(a, grid, smem, st) : launch_fused<tc::FMT_BF16, false, 16>(a, grid, smem, st);
+}

@@ -316,6 +316,7 @@ struct K6Args {
   const int* mol_ptr;
   const int* atom_id;
   const float* h;
+  const float* pooled;           // non-null: [2P, d] molecule sums already computed (fused forward); h / mol_ptr unused
   int n_pairs, d, fp, mix, fp2;  // fp2 = 0 -> viscosity head
   imp_readout_weights_t wc, wa;
   const float *W1, *b1, *W2, *b2;  // viscosity: W1 = [mix,3] head, b1 = [3]; mp: W1 [mix,fp2], W2 [fp2,1]
@@ -398,12 +399,16 @@ __global__ void __launch_bounds__(K6_WARPS * 32) pool_head_kernel(K6Args a) {
   for (int pair = warp_global; pair < a.n_pairs; pair += n_warps) {
     for (int t = 0; t < 2; ++t) {
       const int m = t * a.n_pairs + pair;
-      const int v0 = a.mol_ptr[m], v1e = a.mol_ptr[m + 1];
-      for (int j = lane; j < d; j += 32) {
-        float sacc = 0.f;
-        for (int v = v0; v < v1e; ++v)
-          if (a.atom_id[v] > 0) sacc += a.h[(int64_t)v * d + j];  // models/layers.py:163 mask
-        pool[j] = sacc;
+      if (a.pooled) {
+        for (int j = lane; j < d; j += 32) pool[j] = a.pooled[(int64_t)m * d + j];
+      } else {
+        const int v0 = a.mol_ptr[m], v1e = a.mol_ptr[m + 1];
+        for (int j = lane; j < d; j += 32) {
+          float sacc = 0.f;
+          for (int v = v0; v < v1e; ++v)
+            if (a.atom_id[v] > 0) sacc += a.h[(int64_t)v * d + j];  // models/layers.py:163 mask
+          pool[j] = sacc;
+        }
       }
       __syncwarp();
       k6_dense(Wfp[t], bfp[t], pool, v1, d, fp, true, lane);
@@ -572,7 +577,7 @@ extern "C" int imp_gated_update(const float* d_h, const float* d_agg, int32_t n_
   return rc;
 }
 
-static int launch_k6(const imp_graph_t* g, const float* d_h, int d, int fp, int mix, int fp2,
+static int launch_k6(const imp_graph_t* g, const float* d_h, const float* d_pooled, int d, int fp, int mix, int fp2,
                      const imp_readout_weights_t* wc, const imp_readout_weights_t* wa, const float* W1, const float* b1,
                      const float* W2, const float* b2, const float* T, float* out, float* aux, void* stream,
                      const char* who) {
@@ -580,11 +585,11 @@ static int launch_k6(const imp_graph_t* g, const float* d_h, int d, int fp, int 
   IMP_REQUIRE(d > 0 && fp > 0 && mix > 0 && d <= K6_MAXV && fp <= K6_MAXV && mix <= K6_MAXV && fp2 <= K6_MAXV, IMP_ERR_DIM,
               "%s: d/fp/mix/fp2 = %d/%d/%d/%d must be in 1..%d", who, d, fp, mix, fp2, K6_MAXV);
   if (g->n_pairs == 0) return 0;
-  IMP_REQUIRE(d_h && out && g->mol_ptr && g->atom_id && wc && wa && wc->W_fp && wc->b_fp && wc->W_mix && wc->b_mix &&
+  IMP_REQUIRE((d_pooled || (d_h && g->mol_ptr && g->atom_id)) && out && wc && wa && wc->W_fp && wc->b_fp && wc->W_mix && wc->b_mix &&
                   wa->W_fp && wa->b_fp && wa->W_mix && wa->b_mix && W1 && b1,
               IMP_ERR_ARG, "%s: null pointer", who);
   K6Args a;
-  a.mol_ptr = g->mol_ptr, a.atom_id = g->atom_id, a.h = d_h, a.n_pairs = g->n_pairs;
+  a.mol_ptr = g->mol_ptr, a.atom_id = g->atom_id, a.h = d_h, a.pooled = d_pooled, a.n_pairs = g->n_pairs;
   a.d = d, a.fp = fp, a.mix = mix, a.fp2 = fp2, a.wc = *wc, a.wa = *wa;
   a.W1 = W1, a.b1 = b1, a.W2 = W2, a.b2 = b2, a.T = T, a.out = out, a.aux = aux;
   const int n_head_out = fp2 > 0 ? fp2 : 3;
@@ -615,7 +620,7 @@ extern "C" int imp_pool_head_visc(const imp_graph_t* g, const float* d_h, int32_
                                   const float* d_W_head, const float* d_b_head, const float* d_T, float* d_out,
                                   float* d_aux, void* stream) {
   IMP_REQUIRE(d_T || (g && g->n_pairs == 0), IMP_ERR_ARG, "imp_pool_head_visc: temperature is null");
-  return launch_k6(g, d_h, d, fp, mix, 0, w_cat, w_an, d_W_head, d_b_head, nullptr, nullptr, d_T, d_out, d_aux, stream,
+  return launch_k6(g, d_h, nullptr, d, fp, mix, 0, w_cat, w_an, d_W_head, d_b_head, nullptr, nullptr, d_T, d_out, d_aux, stream,
                    "imp_pool_head_visc");
 }
 
@@ -624,6 +629,39 @@ extern "C" int imp_pool_head_mp(const imp_graph_t* g, const float* d_h, int32_t 
                                 const float* d_b1, const float* d_W2, const float* d_b2, float* d_out, float* d_aux,
                                 void* stream) {
   IMP_REQUIRE(fp2 > 0 && d_W2 && d_b2, IMP_ERR_ARG, "imp_pool_head_mp: head weights missing");
-  return launch_k6(g, d_h, d, fp, mix, fp2, w_cat, w_an, d_W1, d_b1, d_W2, d_b2, nullptr, d_out, d_aux, stream,
+  return launch_k6(g, d_h, nullptr, d, fp, mix, fp2, w_cat, w_an, d_W1, d_b1, d_W2, d_b2, nullptr, d_out, d_aux, stream,
                    "imp_pool_head_mp");
+}
+
+// Readout on molecule sums that are already pooled (output of imp_mpnn_forward_fused): Dense(fp) + Dense(mix) per
+// tower, AddTwoTensors, head.  Same kernel as imp_pool_head_*, with the pooling stage replaced by a row read.
+static int readout_graph(int32_t n_pairs, imp_graph_t* g) {
+  *g = imp_graph_t{};
+  g->n_pairs = n_pairs;
+  g->bond_vocab = 1;  // unused by the readout; keeps check_graph's size invariants
+  return 0;
+}
+
+extern "C" int imp_readout_visc(const float* d_pooled, int32_t n_pairs, int32_t d, int32_t fp, int32_t mix,
+                                const imp_readout_weights_t* w_cat, const imp_readout_weights_t* w_an,
+                                const float* d_W_head, const float* d_b_head, const float* d_T, float* d_out, float* d_aux,
+                                void* stream) {
+  IMP_REQUIRE(n_pairs >= 0, IMP_ERR_ARG, "imp_readout_visc: negative size");
+  IMP_REQUIRE((d_T && d_pooled) || n_pairs == 0, IMP_ERR_ARG, "imp_readout_visc: temperature / pooled is null");
+  imp_graph_t g;
+  readout_graph(n_pairs, &g);
+  return launch_k6(&g, nullptr, d_pooled, d, fp, mix, 0, w_cat, w_an, d_W_head, d_b_head, nullptr, nullptr, d_T, d_out, d_aux,
+                   stream, "imp_readout_visc");
+}
+
+extern "C" int imp_readout_mp(const float* d_pooled, int32_t n_pairs, int32_t d, int32_t fp, int32_t mix, int32_t fp2,
+                              const imp_readout_weights_t* w_cat, const imp_readout_weights_t* w_an, const float* d_W1,
+                              const float* d_b1, const float* d_W2, const float* d_b2, float* d_out, float* d_aux,
+                              void* stream) {
+  IMP_REQUIRE(n_pairs >= 0 && fp2 > 0 && d_W2 && d_b2, IMP_ERR_ARG, "imp_readout_mp: head weights missing");
+  IMP_REQUIRE(d_pooled || n_pairs == 0, IMP_ERR_ARG, "imp_readout_mp: pooled is null");
+  imp_graph_t g;
+  readout_graph(n_pairs, &g);
+  return launch_k6(&g, nullptr, d_pooled, d, fp, mix, fp2, w_cat, w_an, d_W1, d_b1, d_W2, d_b2, nullptr, d_out, d_aux, stream,
+                   "imp_readout_mp");
 }

@@ -25,19 +25,18 @@ struct GruPackLayout {
   static constexpr int BYTES = BZR_BYTES + BH_BYTES + BIAS_FLOATS * 4;
 };
 
-template <int D>
+template <int D, int FMT>
 __global__ void gru_pack_kernel(imp_gru_weights_t w, unsigned char* __restrict__ out) {
   using L = GruPackLayout<D>;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < L::N1 * 2 * D) {  // Bzr[n][k] = (n < D ? Wz[k][n] : Wr[k][n - D])
     const int n = i / (2 * D), k = i % (2 * D);
     const float v = n < D ? w.Wz[k * D + n] : w.Wr[k * D + (n - D)];
-    *reinterpret_cast<__nv_bfloat16*>(out + tc::chunk_off(n, k / 8, L::N1) + (k % 8) * 2) = __float2bfloat16_rn(v);
+    *reinterpret_cast<uint16_t*>(out + tc::chunk_off(n, k / 8, L::N1) + (k % 8) * 2) = tc::cvt16<FMT>(v);
   }
   if (i < D * 2 * D) {  // Bh[n][k] = Wh[k][n]
     const int n = i / (2 * D), k = i % (2 * D);
-    *reinterpret_cast<__nv_bfloat16*>(out + L::BZR_BYTES + tc::chunk_off(n, k / 8, D) + (k % 8) * 2) =
-        __float2bfloat16_rn(w.Wh[k * D + n]);
+    *reinterpret_cast<uint16_t*>(out + L::BZR_BYTES + tc::chunk_off(n, k / 8, D) + (k % 8) * 2) = tc::cvt16<FMT>(w.Wh[k * D + n]);
   }
   if (i < D) {
     float* b = reinterpret_cast<float*>(out + L::BZR_BYTES + L::BH_BYTES);
@@ -73,7 +72,7 @@ struct GruTcSmem {
   uint32_t tmem_base;
 };
 
-template <int D, bool PRECISE>
+template <int D, bool PRECISE, int FMT>
 __global__ void __launch_bounds__(TC_TILE) gated_update_tc_kernel(const float* __restrict__ h, const float* __restrict__ agg,
                                                                   int n_atoms, int n_cat, int tiles_cat, int tiles_total,
                                                                   int tiles_per_cta, const unsigned char* __restrict__ packed_cat,
@@ -98,8 +97,8 @@ __global__ void __launch_bounds__(TC_TILE) gated_update_tc_kernel(const float* _
   const uint32_t tmem = s.tmem_base;
   const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
   const float* bias = reinterpret_cast<const float*>(s.packed + L::BZR_BYTES + L::BH_BYTES);
-  const uint32_t idesc1 = tc::make_idesc(tc::FMT_BF16, TC_TILE, L::N1);
-  const uint32_t idesc2 = tc::make_idesc(tc::FMT_BF16, TC_TILE, D);
+  const uint32_t idesc1 = tc::make_idesc(FMT, TC_TILE, L::N1);
+  const uint32_t idesc2 = tc::make_idesc(FMT, TC_TILE, D);
   const uint32_t aA1 = tc::smem_u32(s.A1), aRH = tc::smem_u32(s.RH), aBzr = tc::smem_u32(s.packed),
                  aBh = tc::smem_u32(s.packed + L::BZR_BYTES);
   constexpr uint32_t LBO_A = TC_TILE * 16, LBO_BZR = L::N1 * 16, LBO_BH = D * 16, SBO = 128;
@@ -132,10 +131,10 @@ __global__ void __launch_bounds__(TC_TILE) gated_update_tc_kernel(const float* _
       float* hr = &s.H[r][c * 8];
       hr[0] = h0.x, hr[1] = h0.y, hr[2] = h0.z, hr[3] = h0.w, hr[4] = h1.x, hr[5] = h1.y, hr[6] = h1.z, hr[7] = h1.w;
       uint4 hv, gv;
-      hv.x = tc::pack_bf16x2(h0.x, h0.y), hv.y = tc::pack_bf16x2(h0.z, h0.w);
-      hv.z = tc::pack_bf16x2(h1.x, h1.y), hv.w = tc::pack_bf16x2(h1.z, h1.w);
-      gv.x = tc::pack_bf16x2(g0.x, g0.y), gv.y = tc::pack_bf16x2(g0.z, g0.w);
-      gv.z = tc::pack_bf16x2(g1.x, g1.y), gv.w = tc::pack_bf16x2(g1.z, g1.w);
+      hv.x = tc::pack2<FMT>(h0.x, h0.y), hv.y = tc::pack2<FMT>(h0.z, h0.w);
+      hv.z = tc::pack2<FMT>(h1.x, h1.y), hv.w = tc::pack2<FMT>(h1.z, h1.w);
+      gv.x = tc::pack2<FMT>(g0.x, g0.y), gv.y = tc::pack2<FMT>(g0.z, g0.w);
+      gv.z = tc::pack2<FMT>(g1.x, g1.y), gv.w = tc::pack2<FMT>(g1.z, g1.w);
       *reinterpret_cast<uint4*>(s.A1 + tc::chunk_off(r, c, TC_TILE)) = hv;
       *reinterpret_cast<uint4*>(s.A1 + tc::chunk_off(r, CH + c, TC_TILE)) = gv;
     }
@@ -165,7 +164,7 @@ __global__ void __launch_bounds__(TC_TILE) gated_update_tc_kernel(const float* _
       for (int j = 0; j < D; j += 2) {
         const float r0 = act_sigmoid<PRECISE>(v[j] + bias[D + j]) * s.H[tid][j];
         const float r1 = act_sigmoid<PRECISE>(v[j + 1] + bias[D + j + 1]) * s.H[tid][j + 1];
-        pk[j / 2] = tc::pack_bf16x2(r0, r1);
+        pk[j / 2] = tc::pack2<FMT>(r0, r1);
       }
 #pragma unroll
       for (int c = 0; c < CH; ++c)
@@ -232,18 +231,39 @@ using namespace imp;
 
 extern "C" int64_t imp_gru_pack_bytes(int32_t d) { return d == 32 ? (int64_t)GruPackLayout<32>::BYTES : (int64_t)IMP_ERR_DIM; }
 
-extern "C" int imp_gru_pack_bf16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream) {
+static int gru_pack_any(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream, bool f16) {
   IMP_REQUIRE(w && d_packed && w->Wz && w->bz && w->Wr && w->br && w->Wh && w->bh && w->gamma && w->beta, IMP_ERR_ARG,
-              "imp_gru_pack_bf16: null pointer");
-  IMP_REQUIRE(d == 32, IMP_ERR_DIM, "imp_gru_pack_bf16: atom_dim %d not supported by the tensor path (32)", d);
+              "imp_gru_pack: null pointer");
+  IMP_REQUIRE(d == 32, IMP_ERR_DIM, "imp_gru_pack: atom_dim %d not supported by the tensor path (32)", d);
   const int n = GruPackLayout<32>::N1 * 2 * 32;
-  gru_pack_kernel<32><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<unsigned char*>(d_packed));
+  if (f16)
+    gru_pack_kernel<32, tc::FMT_F16><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<unsigned char*>(d_packed));
+  else
+    gru_pack_kernel<32, tc::FMT_BF16><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<unsigned char*>(d_packed));
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int imp_gru_pack_bf16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream) {
+  return gru_pack_any(w, d, d_packed, stream, false);
+}
+extern "C" int imp_gru_pack_f16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream) {
+  return gru_pack_any(w, d, d_packed, stream, true);
+}
+
+template <bool PRECISE, int FMT>
+static int launch_gru_tc(const float* d_h, const float* d_agg, int n_atoms, int n_cat_atoms, int tiles_cat, int tiles, int per,
+                         int grid, const void* pc, const void* pa, float eps, float* d_h_out, cudaStream_t stream) {
+  const size_t smem = sizeof(GruTcSmem<32>);
+  IMP_CUDA(cudaFuncSetAttribute(gated_update_tc_kernel<32, PRECISE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gated_update_tc_kernel<32, PRECISE, FMT><<<grid, TC_TILE, smem, stream>>>(d_h, d_agg, n_atoms, n_cat_atoms, tiles_cat, tiles, per,
+                                                                            (const unsigned char*)pc, (const unsigned char*)pa,
+                                                                            eps, d_h_out);
   IMP_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int imp_gated_update_tc(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
-                                   const void* d_packed_cat, const void* d_packed_an, float eps, int32_t precise_epilogue,
+                                   const void* d_packed_cat, const void* d_packed_an, float eps, int32_t flags,
                                    float* d_h_out, void* stream) {
   IMP_REQUIRE(n_atoms >= 0 && n_cat_atoms >= 0 && n_cat_atoms <= n_atoms, IMP_ERR_ARG, "imp_gated_update_tc: bad sizes");
   IMP_REQUIRE(d == 32, IMP_ERR_DIM, "imp_gated_update_tc: atom_dim %d not supported by the tensor path (32)", d);
@@ -255,18 +275,11 @@ extern "C" int imp_gated_update_tc(const float* d_h, const float* d_agg, int32_t
   const int max_ctas = 148 * 4;
   const int per = (int)ceil_div(tiles, max_ctas);
   const int grid = (int)ceil_div(tiles, per);
-  const size_t smem = sizeof(GruTcSmem<32>);
-  if (precise_epilogue) {
-    IMP_CUDA(cudaFuncSetAttribute(gated_update_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gated_update_tc_kernel<32, true><<<grid, TC_TILE, smem, (cudaStream_t)stream>>>(
-        d_h, d_agg, n_atoms, n_cat_atoms, tiles_cat, tiles, per, (const unsigned char*)d_packed_cat,
-        (const unsigned char*)d_packed_an, eps, d_h_out);
-  } else {
-    IMP_CUDA(cudaFuncSetAttribute(gated_update_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gated_update_tc_kernel<32, false><<<grid, TC_TILE, smem, (cudaStream_t)stream>>>(
-        d_h, d_agg, n_atoms, n_cat_atoms, tiles_cat, tiles, per, (const unsigned char*)d_packed_cat,
-        (const unsigned char*)d_packed_an, eps, d_h_out);
-  }
-  IMP_LAUNCH_CHECK();
-  return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool precise = flags & IMP_TC_PRECISE_EPILOGUE, f16 = flags & IMP_TC_FP16;
+  if (precise)
+    return f16 ? launch_gru_tc<true, tc::FMT_F16>(d_h, d_agg, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st)
+               : launch_gru_tc<true, tc::FMT_BF16>(d_h, d_agg, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st);
+  return f16 ? launch_gru_tc<false, tc::FMT_F16>(d_h, d_agg, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st)
+             : launch_gru_tc<false, tc::FMT_BF16>(d_h, d_agg, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st);
 }

@@ -97,6 +97,8 @@ class PackedGraphBatch:
         self.n_pairs, self.n_atoms, self.n_cat_atoms, self.n_unique, self.n_edges, self.bond_vocab = counts
         self.temperature = None if temperature is None else np.ascontiguousarray(temperature, np.float32).reshape(-1)
         self.target = None if target is None else np.ascontiguousarray(target, np.float32).reshape(-1)
+        mp = self.host.get("mol_ptr")
+        self.max_mol_atoms = int(np.diff(mp).max()) if mp is not None and len(mp) > 1 else 0
         self.dev = None
         self.dev_T = None
         self.dev_y = None

@@ -82,12 +82,19 @@ class MPNNModel:
 
     LN_EPS = 1e-3  # Keras LayerNormalization default (models/layers.py:139)
 
-    def __init__(self, spec, device="cuda", seed=0, precision="fp32"):
+    PRECISIONS = ("fp32", "bf16", "bf16_precise", "fp16", "fp16_precise")
+
+    def __init__(self, spec, device="cuda", seed=0, precision="fp32", fused="auto"):
+        """``precision``: 'fp32' = SIMT kernels (the 1e-5 path); 'fp16' / 'bf16' = tcgen05 tensor-core path with
+        IEEE-half / bfloat16 operands and fp32 accumulation (the 2e-2 path; '*_precise' keeps expf/tanhf in the
+        epilogues).  ``fused``: run the whole-tower fused kernel (imp_mpnn_forward_fused) when the shape allows it
+        ('auto' = yes for the tensor precisions), else the staged per-layer kernels."""
         import torch
 
-        if precision not in ("fp32", "bf16", "bf16_precise"):
-            raise ValueError("precision must be 'fp32' (SIMT, 1e-5 path), 'bf16' (tcgen05, 2e-2 path) or 'bf16_precise'")
+        if precision not in self.PRECISIONS:
+            raise ValueError(f"precision must be one of {self.PRECISIONS}")
         self.precision = precision
+        self.fused = fused
 
         _lib.load()
         if not torch.cuda.is_available():
@@ -163,11 +170,44 @@ class MPNNModel:
                 raise _lib.ImpError(f"tensor path does not support atom_dim {d}")
             self._gru_pack_bytes = (nbytes + 255) // 256 * 256
             pk = self._buf("gru_packed", self._gru_pack_bytes * n, torch.uint8)
+            pack_fn = "imp_gru_pack_f16" if self.precision.startswith("fp16") else "imp_gru_pack_bf16"
             for ti, t in enumerate(TOWERS):
                 for i in range(S):
                     w = self._gru_struct(t, i)
-                    _lib.call("imp_gru_pack_bf16", C.byref(w), d, pk.data_ptr() + self._gru_pack_bytes * (ti * S + i), _stream())
+                    _lib.call(pack_fn, C.byref(w), d, pk.data_ptr() + self._gru_pack_bytes * (ti * S + i), _stream())
+            if self.fused_supported():
+                fb = _lib.load().imp_fused_pack_bytes(d, K)
+                fpk = self._buf("fused_packed", fb * n, torch.uint8)
+                for ti, t in enumerate(TOWERS):
+                    for i in range(S):
+                        w = self._gru_struct(t, i)
+                        _lib.call("imp_fused_pack", self._ptr(f"{t}_bmm_{i}.bond_transform"), C.byref(w), d, K,
+                                  self.tc_flags(), fpk.data_ptr() + fb * (ti * S + i), _stream())
         self._tables_valid = True
+
+    def tc_flags(self):
+        f = _lib.TC_FP16 if self.precision.startswith("fp16") else 0
+        if self.precision.endswith("_precise"):
+            f |= _lib.TC_PRECISE_EPILOGUE
+        return f | getattr(self, "extra_tc_flags", 0)
+
+    def fused_supported(self):
+        """Shape envelope of imp_mpnn_forward_fused (include/imp_b200.h)."""
+        s = self.spec
+        return (self.precision != "fp32" and s["atom_dim"] == 32 and s["bond_dim"] == 8 and 1 <= s["num_steps"] <= 4
+                and s["bond_vocab_size"] <= 256)
+
+    def use_fused(self, batch):
+        if self.fused is False or not self.fused_supported():
+            if self.fused is True:
+                raise _lib.ImpError("fused=True, but the model shape is outside the fused kernel's envelope "
+                                    "(tensor precision, atom_dim 32, bond_dim 8, <= 4 steps)")
+            return False
+        if batch.max_mol_atoms > 128:
+            if self.fused is True:
+                raise _lib.ImpError(f"fused=True, but a molecule has {batch.max_mol_atoms} atoms (tile = 128)")
+            return False
+        return True
 
     def table_ptr(self, tower, step, interleaved):
         s = self.spec
@@ -194,6 +234,8 @@ class MPNNModel:
         st = _stream()
         if not self._tables_valid:
             self.refresh_tables()
+        if not keep and not unfused_messages and self.use_fused(batch):
+            return self._forward_fused(batch, g, st)
         inter = {}
         if keep:
             h = [torch.empty(N * d, dtype=torch.float32, device=self.device) for _ in range(S + 1)]
@@ -221,7 +263,7 @@ class MPNNModel:
                 base = self._ws["gru_packed"].data_ptr()
                 _lib.call("imp_gated_update_tc", h[i].data_ptr(), aggs[i].data_ptr(), N, batch.n_cat_atoms, d,
                           base + self._gru_pack_bytes * i, base + self._gru_pack_bytes * (S + i), C.c_float(self.LN_EPS),
-                          1 if self.precision == "bf16_precise" else 0, h[i + 1].data_ptr(), st)
+                          self.tc_flags(), h[i + 1].data_ptr(), st)
         out = torch.empty(P, dtype=torch.float32, device=self.device)
         fp, mix = s["fp_size"], s["mixing_size"]
         visc = s["kind"] == "viscosity"
@@ -244,8 +286,37 @@ class MPNNModel:
                      "aux": aux.view(P, -1)}
         return (out, inter) if keep else out
 
-    def launches_per_forward(self):
-        """Kernels enqueued by forward_packed (fused message path, tables already valid)."""
+    def _forward_fused(self, batch, g, st):
+        """imp_mpnn_forward_fused (embed + all steps + pool, one kernel) then the readout kernel."""
+        import torch
+
+        s = self.spec
+        d, S, P = s["atom_dim"], s["num_steps"], batch.n_pairs
+        fp, mix = s["fp_size"], s["mixing_size"]
+        pooled = self._buf("pooled", 2 * P * d)
+        status = self._ws.get("status")
+        if status is None:
+            status = self._ws["status"] = torch.zeros(1, dtype=torch.int32, device=self.device)
+        _lib.call("imp_mpnn_forward_fused", C.byref(g), self._ptr("atom_emb"), s["atom_vocab_size"], self._ptr("bond_emb"),
+                  d, s["bond_dim"], S, self._ws["fused_packed"].data_ptr(), C.c_float(self.LN_EPS), self.tc_flags(),
+                  batch.max_mol_atoms, pooled.data_ptr(), status.data_ptr(), st)
+        out = torch.empty(P, dtype=torch.float32, device=self.device)
+        rc, ra = self._readout_struct("cat"), self._readout_struct("an")
+        if s["kind"] == "viscosity":
+            if batch.dev_T is None:
+                raise ValueError("viscosity model needs batch.temperature")
+            _lib.call("imp_readout_visc", pooled.data_ptr(), P, d, fp, mix, C.byref(rc), C.byref(ra),
+                      self._ptr("head.kernel"), self._ptr("head.bias"), batch.dev_T.data_ptr(), out.data_ptr(), None, st)
+        else:
+            _lib.call("imp_readout_mp", pooled.data_ptr(), P, d, fp, mix, fp, C.byref(rc), C.byref(ra),
+                      self._ptr("head1.kernel"), self._ptr("head1.bias"), self._ptr("head2.kernel"),
+                      self._ptr("head2.bias"), out.data_ptr(), None, st)
+        return out
+
+    def launches_per_forward(self, batch=None):
+        """Kernels enqueued by forward_packed (tables / packs already valid)."""
+        if batch is not None and self.use_fused(batch):
+            return 2
         return 1 + 2 * self.spec["num_steps"] + 1
 
     # -- Keras-like surface ---------------------------------------------------------------------

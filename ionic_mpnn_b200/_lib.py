@@ -42,6 +42,7 @@ class ReadoutWeights(C.Structure):
 TC_FP16 = 1
 TC_PRECISE_EPILOGUE = 2
 TC_MP8 = 4
+TC_F32_ZBUILD = 8
 PACK_DOUBLE_EDGES = 1
 PACK_SHIFT_IDS = 2
 

@@ -91,6 +91,7 @@ struct FusedArgs {
   float* pooled;                // [2P][32]
   int* status;                  // optional: set to 1 if a molecule does not fit one tile
   int n_pairs, atom_vocab, bond_vocab, steps, n_cta_cat;
+  int n_atoms, n_unique;
   float eps;
 };
 
@@ -379,6 +380,335 @@ __global__ void __launch_bounds__(256, 1) mpnn_fused_kernel(const FusedArgs a) {
   if (warp == 0) tc::tmem_dealloc<512>(ctl.tmem_base);
 }
 
+// =====================================================================================================================
+// v2 of the fused kernel for IEEE-half operands ("h2"): same GEMM pipeline, cheaper SIMT side.
+//   * Z rows are accumulated with packed HFMA2 (two products per lane-instruction) directly in the 16-bit pair layout
+//     the tensor core reads, in ONE pass over the row's entries (128 half2 accumulators), so there is no fp32->fp16
+//     pack and no second walk of the entry list.  Neighbour states are gathered from a shared-memory copy of h that is
+//     already half precision and lane-broadcast ((h_m, h_m) pairs); products are exact in the fma, one rounding per
+//     accumulation step (<= in-degree roundings on a value that is rounded to half for the MMA anyway).
+//   * the fp32 state of a row lives in its owner's REGISTERS for all steps (no shared-memory round trip);
+//   * rows are assigned to threads sorted by in-degree (counting sort with warp ballots), so that the 32 lanes of a
+//     warp run the same number of entry iterations; the two warpgroups sort in opposite directions so that every SM
+//     sub-partition gets one light and one heavy warp;
+//   * the index lines of the next tile are prefetched into L2 while the current tile computes.
+struct alignas(16) FusedWgSmem2 {
+  uint32_t hb[FZ_ROWS * FZ_HS];  // half2 (h_m, h_m) per column; after the last step: fp32 h rows for the pooling
+  int molp[FZ_GROUP + 4];
+  int se0[FZ_ROWS], se1[FZ_ROWS], said[FZ_ROWS];  // per natural row: entry range, atom id
+  int cnt[4][8];
+  unsigned char rowof[FZ_ROWS];
+  unsigned char amask[FZ_ROWS];
+  uint64_t bar[4];
+};
+
+__host__ __device__ inline int fused2_smem_bytes(int steps, int bond_vocab) {
+  const int ctab = (bond_vocab * 16 + 127) / 128 * 128;
+  return steps * FusedPack::BYTES + ctab + 2 * (int)sizeof(FusedWgSmem2) + (int)sizeof(FusedCtl);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <bool PRECISE>
+__global__ void __launch_bounds__(256, 1) mpnn_fused_h2_kernel(const FusedArgs a) {
+  constexpr int D = FZ_D;
+  constexpr int FMT = tc::FMT_F16;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = tid >> 7, t = tid & 127, wq = warp & 3;
+  const int wbytes = a.steps * FusedPack::BYTES;
+  const int ctab_bytes = (a.bond_vocab * 16 + 127) / 128 * 128;
+  uint4* s_ctab = reinterpret_cast<uint4*>(smem + wbytes);  // per bond: (c0,c1) (c2,c3) (c4,c5) (c6,c7) as half2
+  FusedWgSmem2& ws = reinterpret_cast<FusedWgSmem2*>(smem + wbytes + ctab_bytes)[wg];
+  FusedCtl& ctl = *reinterpret_cast<FusedCtl*>(smem + wbytes + ctab_bytes + 2 * sizeof(FusedWgSmem2));
+
+  const int tower = blockIdx.x >= a.n_cta_cat;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.packed + (size_t)tower * wbytes);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = tid; i < wbytes / 16; i += 256) dst[i] = __ldg(src + i);
+    for (int i = tid; i < a.bond_vocab; i += 256) {
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(a.bond_emb) + 2 * i);
+      const float4 c1 = __ldg(reinterpret_cast<const float4*>(a.bond_emb) + 2 * i + 1);
+      s_ctab[i] = make_uint4(tc::pack_f16x2(c0.x, c0.y), tc::pack_f16x2(c0.z, c0.w), tc::pack_f16x2(c1.x, c1.y),
+                             tc::pack_f16x2(c1.z, c1.w));
+    }
+  }
+  if (warp == 0) tc::tmem_alloc<512>(&ctl.tmem_base);
+  if (t == 0) {
+    tc::mbar_init(&ws.bar[0], 1);
+    tc::mbar_init(&ws.bar[1], 1);
+    tc::mbar_init(&ws.bar[2], 1);
+    tc::mbar_fence_init();
+  }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+
+  const uint32_t tbase = ctl.tmem_base + (uint32_t)(wg * 256);
+  const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+  const uint32_t tZ = tbase, tAh = tbase, tAagg = tbase + 16, tArh = tbase + 32;
+  const uint32_t tCagg = tbase + 128, tCzr = tbase + 160, tCht = tbase + 224;
+  const uint32_t idesc32 = tc::make_idesc(FMT, FZ_ROWS, D), idesc64 = tc::make_idesc(FMT, FZ_ROWS, 2 * D);
+  const uint32_t sw0 = tc::smem_u32(smem);
+  const int bar_id = 1 + wg;
+  const bool descending = wg & 1;
+
+  const int P = a.n_pairs;
+  const int n_groups = (P + FZ_GROUP - 1) / FZ_GROUP;
+  const int n_cta_tower = tower ? (int)gridDim.x - a.n_cta_cat : a.n_cta_cat;
+  const int cta_in_tower = tower ? (int)blockIdx.x - a.n_cta_cat : (int)blockIdx.x;
+  const float4* emb4 = reinterpret_cast<const float4*>(a.atom_emb);
+  uint32_t ph = 0;
+
+  for (int g = cta_in_tower * 2 + wg; g < n_groups; g += n_cta_tower * 2) {
+    const int m0 = g * FZ_GROUP, nm = min(FZ_GROUP, P - m0);
+    const int base_mol = tower * P + m0;
+    tc::named_bar_sync(bar_id, 128);
+    if (t <= nm) ws.molp[t] = __ldg(a.mol_ptr + base_mol + t);
+    tc::named_bar_sync(bar_id, 128);
+    int ms = 0;
+    while (ms < nm) {
+      const int a0 = ws.molp[ms];
+      int me = ms + 1;
+      while (me < nm && ws.molp[me + 1] - a0 <= FZ_ROWS) ++me;
+      int rows = ws.molp[me] - a0;
+      if (rows > FZ_ROWS) {
+        if (t == 0 && a.status) *a.status = 1;
+        rows = FZ_ROWS;
+      }
+      // ---------------------------------------------------------------- natural row t: indices, in-degree key
+      int key;
+      {
+        const bool valid = t < rows;
+        int aid = 0, e0 = 0, e1 = 0;
+        if (valid) {
+          aid = __ldg(a.atom_id + a0 + t);
+          e0 = __ldg(a.row_ptr + a0 + t);
+          e1 = __ldg(a.row_ptr + a0 + t + 1);
+        }
+        ws.se0[t] = e0, ws.se1[t] = e1, ws.said[t] = aid;
+        ws.amask[t] = (valid && aid > 0) ? 1 : 0;  // models/layers.py:163
+        key = min(e1 - e0, 7);
+      }
+      int rank = 0;
+      {
+        int mine = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const unsigned m = __ballot_sync(0xffffffffu, key == k);
+          if (lane == k) mine = __popc(m);
+          if (key == k) rank = __popc(m & ((1u << lane) - 1u));
+        }
+        if (lane < 8) ws.cnt[wq][lane] = mine;
+      }
+      tc::named_bar_sync(bar_id, 128);
+      {
+        int off = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c0 = ws.cnt[0][k], c1 = ws.cnt[1][k], c2 = ws.cnt[2][k], c3 = ws.cnt[3][k];
+          if (k < key) off += c0 + c1 + c2 + c3;
+          if (k == key) off += (wq > 0 ? c0 : 0) + (wq > 1 ? c1 : 0) + (wq > 2 ? c2 : 0);
+        }
+        const int slot = off + rank;
+        ws.rowof[descending ? FZ_ROWS - 1 - slot : slot] = (unsigned char)t;
+      }
+      tc::named_bar_sync(bar_id, 128);
+      // ---------------------------------------------------------------- thread t now owns row r
+      const int r = ws.rowof[t];
+      const int e0 = ws.se0[r], e1 = ws.se1[r];
+      uint32_t* hbrow = &ws.hb[r * FZ_HS];
+      float h[D];
+      {  // Embedding(atom)
+        const bool valid = r < rows;
+        const int id = min(max(ws.said[r], 0), a.atom_vocab - 1);
+#pragma unroll
+        for (int c = 0; c < D / 4; ++c) {
+          const float4 x = valid ? __ldg(emb4 + id * (D / 4) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          h[4 * c] = x.x, h[4 * c + 1] = x.y, h[4 * c + 2] = x.z, h[4 * c + 3] = x.w;
+          reinterpret_cast<uint4*>(hbrow)[c] =
+              make_uint4(tc::pack_f16x2(x.x, x.x), tc::pack_f16x2(x.y, x.y), tc::pack_f16x2(x.z, x.z), tc::pack_f16x2(x.w, x.w));
+        }
+      }
+      if (me < nm && lane < 8) {  // index lines of the next tile -> L2 (it follows this tile in all three arrays)
+        const int an = ws.molp[me], en = ws.se1[rows - 1];
+        if (wq == 0) prefetch_l2(a.atom_id + min(an + lane * 32, a.n_atoms - 1));
+        if (wq == 1) prefetch_l2(a.row_ptr + min(an + lane * 32, a.n_atoms));
+        if (wq == 2) prefetch_l2(a.col_src + min(en + lane * 32, a.n_unique - 1));
+        if (wq == 3) prefetch_l2(a.edge_bm + min(en + lane * 32, a.n_unique - 1));
+      }
+      tc::named_bar_sync(bar_id, 128);
+
+      for (int s = 0; s < a.steps; ++s) {
+        const uint32_t sw = sw0 + (uint32_t)(s * FusedPack::BYTES);
+        const float* bias = reinterpret_cast<const float*>(smem + s * FusedPack::BYTES + FusedPack::OFF_BIAS);
+        // ------------------------------------------------------------ Z row (half2 accumulators) -> TMEM
+        {
+          __half2 acc[D * FZ_K / 2];
+#pragma unroll
+          for (int i = 0; i < D * FZ_K / 2; ++i) acc[i] = __half2(__ushort_as_half(0), __ushort_as_half(0));
+#pragma unroll 1
+          for (int e = e0; e < e1; ++e) {
+            const int bm = __ldg(a.edge_bm + e);
+            int src = __ldg(a.col_src + e) - a0;
+            src = min(max(src, 0), FZ_ROWS - 1);
+            const __half2 mult = __float2half2_rn((float)(bm >> 16));
+            const int bond = min(bm & 0xffff, a.bond_vocab - 1);
+            const uint4 cu = s_ctab[bond];
+            __half2 c[4];
+            c[0] = __hmul2(*reinterpret_cast<const __half2*>(&cu.x), mult);
+            c[1] = __hmul2(*reinterpret_cast<const __half2*>(&cu.y), mult);
+            c[2] = __hmul2(*reinterpret_cast<const __half2*>(&cu.z), mult);
+            c[3] = __hmul2(*reinterpret_cast<const __half2*>(&cu.w), mult);
+            const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[src * FZ_HS]);
+#pragma unroll
+            for (int q = 0; q < D / 4; ++q) {
+              const uint4 hv = hp[q];
+              const __half2 hm[4] = {*reinterpret_cast<const __half2*>(&hv.x), *reinterpret_cast<const __half2*>(&hv.y),
+                                     *reinterpret_cast<const __half2*>(&hv.z), *reinterpret_cast<const __half2*>(&hv.w)};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[(4 * q + i) * 4 + j] = __hfma2(hm[i], c[j], acc[(4 * q + i) * 4 + j]);
+            }
+          }
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t rr[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) rr[i] = *reinterpret_cast<const uint32_t*>(&acc[ch * 32 + i]);
+            tc::tmem_st32(tZ + lane_off + (uint32_t)(ch * 32), rr);
+          }
+        }
+        tc::tmem_wait_st();
+        tc::fence_before_thread_sync();
+        tc::named_bar_sync(bar_id, 128);
+        // ------------------------------------------------------------ GEMM1: agg = Z . Wc
+        if (t == 0) {
+          tc::fence_after_thread_sync();
+#pragma unroll
+          for (int ks = 0; ks < D * FZ_K / 16; ++ks)
+            tc::mma_f16_ts(tCagg, tZ + 8 * ks, tc::make_smem_desc(sw + ks * 1024, D * 16, 128), idesc32, ks > 0);
+          tc::mma_commit(&ws.bar[0]);
+        }
+        tc::mbar_wait(&ws.bar[0], ph);
+        tc::fence_after_thread_sync();
+        {
+          float v[32];
+          tc::tmem_ld32(tCagg + lane_off, v);
+          uint32_t rr[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rr[i] = tc::pack_f16x2(v[2 * i], v[2 * i + 1]);
+          tc::tmem_st16(tAagg + lane_off, rr);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rr[i] = tc::pack_f16x2(h[2 * i], h[2 * i + 1]);
+          tc::tmem_st16(tAh + lane_off, rr);
+        }
+        tc::tmem_wait_st();
+        tc::fence_before_thread_sync();
+        tc::named_bar_sync(bar_id, 128);
+        // ------------------------------------------------------------ GEMM2 / GEMM3a
+        if (t == 0) {
+          tc::fence_after_thread_sync();
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            tc::mma_f16_ts(tCzr, tAh + 8 * ks, tc::make_smem_desc(sw + FusedPack::OFF_BZR + ks * 2048, 2 * D * 16, 128),
+                           idesc64, ks > 0);
+          tc::mma_commit(&ws.bar[1]);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            tc::mma_f16_ts(tCht, tAagg + 8 * ks, tc::make_smem_desc(sw + FusedPack::OFF_BH + (ks + 2) * 1024, D * 16, 128),
+                           idesc32, ks > 0);
+        }
+        tc::mbar_wait(&ws.bar[1], ph);
+        tc::fence_after_thread_sync();
+        float z[D];
+        {
+          float v[32];
+          tc::tmem_ld32(tCzr + lane_off, v);
+#pragma unroll
+          for (int j = 0; j < D; ++j) z[j] = fz_sigmoid<PRECISE>(v[j] + bias[j]);
+          tc::tmem_ld32(tCzr + D + lane_off, v);
+          uint32_t rr[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float r0 = fz_sigmoid<PRECISE>(v[2 * i] + bias[D + 2 * i]) * h[2 * i];
+            const float r1 = fz_sigmoid<PRECISE>(v[2 * i + 1] + bias[D + 2 * i + 1]) * h[2 * i + 1];
+            rr[i] = tc::pack_f16x2(r0, r1);
+          }
+          tc::tmem_st16(tArh + lane_off, rr);
+        }
+        tc::tmem_wait_st();
+        tc::fence_before_thread_sync();
+        tc::named_bar_sync(bar_id, 128);
+        // ------------------------------------------------------------ GEMM3b
+        if (t == 0) {
+          tc::fence_after_thread_sync();
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            tc::mma_f16_ts(tCht, tArh + 8 * ks, tc::make_smem_desc(sw + FusedPack::OFF_BH + ks * 1024, D * 16, 128), idesc32,
+                           true);
+          tc::mma_commit(&ws.bar[2]);
+        }
+        tc::mbar_wait(&ws.bar[2], ph);
+        tc::fence_after_thread_sync();
+        {  // candidate, blend, LayerNorm, residual  (models/layers.py:151-156)
+          float gq[32];
+          tc::tmem_ld32(tCht + lane_off, gq);
+          float mean = 0.f;
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            const float ht = fz_tanh<PRECISE>(gq[j] + bias[2 * D + j]);
+            gq[j] = fmaf(z[j], ht - h[j], h[j]);
+            mean += gq[j];
+          }
+          mean *= (1.0f / D);
+          float var = 0.f;
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            const float cdev = gq[j] - mean;
+            var = fmaf(cdev, cdev, var);
+          }
+          const float inv = PRECISE ? 1.0f / sqrtf(var * (1.0f / D) + a.eps) : rsqrtf(var * (1.0f / D) + a.eps);
+#pragma unroll
+          for (int j = 0; j < D; ++j) h[j] = fmaf((gq[j] - mean) * inv, bias[3 * D + j], bias[4 * D + j]) + h[j];
+          if (s + 1 < a.steps) {
+#pragma unroll
+            for (int c = 0; c < D / 4; ++c)
+              reinterpret_cast<uint4*>(hbrow)[c] = make_uint4(tc::pack_f16x2(h[4 * c], h[4 * c]), tc::pack_f16x2(h[4 * c + 1], h[4 * c + 1]),
+                                                              tc::pack_f16x2(h[4 * c + 2], h[4 * c + 2]), tc::pack_f16x2(h[4 * c + 3], h[4 * c + 3]));
+          } else {  // last step: fp32 rows for the pooling (every gather of this tile is done)
+#pragma unroll
+            for (int c = 0; c < D / 4; ++c)
+              reinterpret_cast<float4*>(hbrow)[c] = make_float4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+          }
+        }
+        tc::fence_before_thread_sync();
+        tc::named_bar_sync(bar_id, 128);
+        ph ^= 1;
+      }
+      // ---------------------------------------------------------------- GlobalSumPool
+      {
+        const float* hf = reinterpret_cast<const float*>(ws.hb);
+        for (int mi = ms + (t >> 5); mi < me; mi += 4) {
+          const int lo = ws.molp[mi] - a0, hi = min(ws.molp[mi + 1] - a0, FZ_ROWS);
+          float sacc = 0.f;
+          for (int rr = lo; rr < hi; ++rr)
+            if (ws.amask[rr]) sacc += hf[rr * FZ_HS + lane];
+          a.pooled[(size_t)(base_mol + mi) * D + lane] = sacc;
+        }
+      }
+      tc::named_bar_sync(bar_id, 128);
+      ms = me;
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(ctl.tmem_base);
+}
+
 }  // namespace imp
 
 using namespace imp;
@@ -441,6 +771,7 @@ extern "C" int imp_mpnn_forward_fused(const imp_graph_t* g, const float* d_atom_
   FusedArgs a;
   a.mol_ptr = g->mol_ptr, a.atom_id = g->atom_id, a.row_ptr = g->row_ptr, a.col_src = g->col_src, a.edge_bm = g->edge_bm;
   a.atom_emb = d_atom_emb, a.bond_emb = d_bond_emb, a.packed = (const unsigned char*)d_packed, a.pooled = d_pooled;
+  a.n_atoms = g->n_atoms, a.n_unique = g->n_unique;
   a.status = d_status, a.n_pairs = g->n_pairs, a.atom_vocab = atom_vocab, a.bond_vocab = g->bond_vocab, a.steps = steps, a.eps = eps;
   // one persistent CTA per SM; CTAs are split between the towers in proportion to their atoms
   const int sms = fused_sm_count();
@@ -457,6 +788,19 @@ extern "C" int imp_mpnn_forward_fused(const imp_graph_t* g, const float* d_atom_
   IMP_REQUIRE(smem <= 227 * 1024, IMP_ERR_DIM, "imp_mpnn_forward_fused: needs %zu B of shared memory", smem);
   const bool f16 = flags & IMP_TC_FP16, precise = flags & IMP_TC_PRECISE_EPILOGUE, mp8 = flags & IMP_TC_MP8;
   cudaStream_t st = (cudaStream_t)stream;
+  if (f16 && !(flags & IMP_TC_F32_ZBUILD)) {  // default for half operands: packed-half Z build, degree-sorted rows
+    const size_t smem2 = (size_t)fused2_smem_bytes(steps, g->bond_vocab);
+    IMP_REQUIRE(smem2 <= 227 * 1024, IMP_ERR_DIM, "imp_mpnn_forward_fused: needs %zu B of shared memory", smem2);
+    if (precise) {
+      IMP_CUDA(cudaFuncSetAttribute(mpnn_fused_h2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      mpnn_fused_h2_kernel<true><<<grid, 256, smem2, st>>>(a);
+    } else {
+      IMP_CUDA(cudaFuncSetAttribute(mpnn_fused_h2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      mpnn_fused_h2_kernel<false><<<grid, 256, smem2, st>>>(a);
+    }
+    IMP_LAUNCH_CHECK();
+    return 0;
+  }
   if (f16) {
     if (precise) return mp8 ? launch_fused<tc::FMT_F16, true, 8>(a, grid, smem, st) : launch_fused<tc::FMT_F16, true, 16>(a, grid, smem, st);
     return mp8 ? launch_fused<tc::FMT_F16, false, 8>(a, grid, smem, st) : launch_fused<tc::FMT_F16, false, 16>(a, grid, smem, st);

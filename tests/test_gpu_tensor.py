@@ -146,7 +146,7 @@ def test_ts_mma_matches_cpu(N, K, kind):
 
 
 # ---------------------------------------------------------------------------- fused whole-tower forward
-def _fused_vs_staged(n_pairs, seed, precision, skewed=False, n_min=10, n_max=40):
+def _fused_vs_staged(n_pairs, seed, precision, skewed=False, n_min=10, n_max=40, tc_flags=0):
     from ionic_mpnn_b200 import graph
     from ionic_mpnn_b200.viscosity import build_model
 
@@ -154,6 +154,7 @@ def _fused_vs_staged(n_pairs, seed, precision, skewed=False, n_min=10, n_max=40)
     batch.to("cuda")
     ref = build_model(124, 72, precision="fp32", seed=3)
     fz = build_model(124, 72, precision=precision, seed=3, fused=True)
+    fz.extra_tc_flags = tc_flags
     want = ref.forward_packed(batch).cpu().numpy()
     got = fz.forward_packed(batch).cpu().numpy()
     torch.cuda.synchronize()
@@ -169,6 +170,13 @@ def test_fused_forward_vs_fp32_kernels(n_pairs, precision):
     print(f"fused {precision}, {n_pairs} pairs: max rel err {err:.3e}")
     assert np.isfinite(got).all()
     assert err <= (BF16_RTOL if precision.startswith("fp16") else 1.5e-1), err
+
+
+@pytest.mark.parametrize("tc_flags", [8, 8 | 4])
+def test_fused_forward_fp32_zbuild_variants(tc_flags):
+    """First-generation kernel (fp32 Z accumulation; IMP_TC_F32_ZBUILD, optionally IMP_TC_MP8) stays covered."""
+    got, want = _fused_vs_staged(700, 4, "fp16", tc_flags=tc_flags)
+    assert _rel(got, want) <= BF16_RTOL
 
 
 def test_fused_forward_large_molecules_and_skew():

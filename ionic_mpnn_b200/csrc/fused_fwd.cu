@@ -93,6 +93,8 @@ struct FusedArgs {
   int n_pairs, atom_vocab, bond_vocab, steps, n_cta_cat;
   int n_atoms, n_unique;
   float eps;
+  long long* prof;  // FZ_PROFILE builds only
+  int debug;        // timing experiments only (results are wrong): 1 = skip the entry loop, 2 = skip MMAs and their waits
 };
 
 struct alignas(16) FusedWgSmem {
@@ -381,19 +383,27 @@ __global__ void __launch_bounds__(256, 1) mpnn_fused_kernel(const FusedArgs a) {
 }
 
 // =====================================================================================================================
-// v2 of the fused kernel for IEEE-half operands ("h2"): same GEMM pipeline, cheaper SIMT side.
+// Second generation of the fused kernel, for IEEE-half operands ("h2"): same GEMM pipeline, cheaper and wider SIMT side.
+//   * TWO threads per atom row (warps w and w+4 of a 256-thread "context" address the same TMEM lanes): each owns 16 of
+//     the 32 state columns -- half of the Z row, half of every epilogue.  512 threads per SM (4 warps per
+//     sub-partition) instead of 256 hide the tcgen05 round trips and the fixed-latency stalls that bounded the first
+//     generation (profiles/r01_fused_v1: 42 % issue-slot use at 2 warps per sub-partition).
 //   * Z rows are accumulated with packed HFMA2 (two products per lane-instruction) directly in the 16-bit pair layout
-//     the tensor core reads, in ONE pass over the row's entries (128 half2 accumulators), so there is no fp32->fp16
-//     pack and no second walk of the entry list.  Neighbour states are gathered from a shared-memory copy of h that is
-//     already half precision and lane-broadcast ((h_m, h_m) pairs); products are exact in the fma, one rounding per
-//     accumulation step (<= in-degree roundings on a value that is rounded to half for the MMA anyway).
-//   * the fp32 state of a row lives in its owner's REGISTERS for all steps (no shared-memory round trip);
+//     the tensor core reads, in ONE pass over the row's entries, so there is no fp32->fp16 pack and no second walk of
+//     the entry list.  Neighbour states are gathered from a shared-memory copy of h that is already half precision and
+//     lane-broadcast ((h_m, h_m) pairs); one rounding per accumulation step on a value that is rounded to half for the
+//     MMA anyway.
+//   * the fp32 state of a row lives in its owners' REGISTERS for all steps;
 //   * rows are assigned to threads sorted by in-degree (counting sort with warp ballots), so that the 32 lanes of a
-//     warp run the same number of entry iterations; the two warpgroups sort in opposite directions so that every SM
-//     sub-partition gets one light and one heavy warp;
+//     warp run the same number of entry iterations; the two contexts sort in opposite directions so that every SM
+//     sub-partition gets light and heavy warps;
+//   * LayerNorm statistics are exchanged between the two owners of a row through shared memory (sum, sum of squares);
 //   * the index lines of the next tile are prefetched into L2 while the current tile computes.
+constexpr int F2_CTX_THREADS = 256;
+
 struct alignas(16) FusedWgSmem2 {
   uint32_t hb[FZ_ROWS * FZ_HS];  // half2 (h_m, h_m) per column; after the last step: fp32 h rows for the pooling
+  float2 ln[2][FZ_ROWS];         // per half: (sum, sum of squares) of the blended row
   int molp[FZ_GROUP + 4];
   int se0[FZ_ROWS], se1[FZ_ROWS], said[FZ_ROWS];  // per natural row: entry range, atom id
   int cnt[4][8];
@@ -409,25 +419,52 @@ __host__ __device__ inline int fused2_smem_bytes(int steps, int bond_vocab) {
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Optional phase timing (compile with -DFZ_PROFILE): per-phase clock64 deltas of selected threads, summed into
+// a.prof[thread-class][18] (thread classes: u == 0, u == 96 (warp 3), u == 224 (warp 7)); read by tools/fused_phase_profile.py.
+#ifdef FZ_PROFILE
+#define FZ_PROF_DECL                                                                     \
+  long long prof_acc[18];                                                                \
+  for (int i_ = 0; i_ < 18; ++i_) prof_acc[i_] = 0;                                      \
+  long long prof_last = clock64();                                                       \
+  const int prof_cls = (u == 0) ? 0 : (u == 96) ? 1 : (u == 224) ? 2 : -1
+#define FZ_PROF_T(i)                         \
+  do {                                       \
+    const long long now_ = clock64();        \
+    prof_acc[i] += now_ - prof_last;         \
+    prof_last = now_;                        \
+  } while (0)
+#define FZ_PROF_FLUSH                                                                                       \
+  if (prof_cls >= 0 && a.prof)                                                                               \
+    for (int i_ = 0; i_ < 18; ++i_) atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + prof_cls * 18 + i_, (unsigned long long)prof_acc[i_])
+#else
+#define FZ_PROF_DECL
+#define FZ_PROF_T(i)
+#define FZ_PROF_FLUSH
+#endif
+
 template <bool PRECISE>
-__global__ void __launch_bounds__(256, 1) mpnn_fused_h2_kernel(const FusedArgs a) {
-  constexpr int D = FZ_D;
+__global__ void __launch_bounds__(2 * F2_CTX_THREADS, 1) mpnn_fused_h2_kernel(const FusedArgs a) {
+  constexpr int D = FZ_D, DH = FZ_D / 2;
   constexpr int FMT = tc::FMT_F16;
+  constexpr int NT = 2 * F2_CTX_THREADS;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wg = tid >> 7, t = tid & 127, wq = warp & 3;
+  const int ctx = tid >> 8, u = tid & 255;
+  const int p = u & 127;   // row slot = TMEM lane
+  const int hf = u >> 7;   // which 16 columns of the row this thread owns
+  const int wq = warp & 3; // TMEM lane quarter == (p >> 5)
   const int wbytes = a.steps * FusedPack::BYTES;
   const int ctab_bytes = (a.bond_vocab * 16 + 127) / 128 * 128;
   uint4* s_ctab = reinterpret_cast<uint4*>(smem + wbytes);  // per bond: (c0,c1) (c2,c3) (c4,c5) (c6,c7) as half2
-  FusedWgSmem2& ws = reinterpret_cast<FusedWgSmem2*>(smem + wbytes + ctab_bytes)[wg];
+  FusedWgSmem2& ws = reinterpret_cast<FusedWgSmem2*>(smem + wbytes + ctab_bytes)[ctx];
   FusedCtl& ctl = *reinterpret_cast<FusedCtl*>(smem + wbytes + ctab_bytes + 2 * sizeof(FusedWgSmem2));
 
   const int tower = blockIdx.x >= a.n_cta_cat;
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.packed + (size_t)tower * wbytes);
     uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < wbytes / 16; i += 256) dst[i] = __ldg(src + i);
-    for (int i = tid; i < a.bond_vocab; i += 256) {
+    for (int i = tid; i < wbytes / 16; i += NT) dst[i] = __ldg(src + i);
+    for (int i = tid; i < a.bond_vocab; i += NT) {
       const float4 c0 = __ldg(reinterpret_cast<const float4*>(a.bond_emb) + 2 * i);
       const float4 c1 = __ldg(reinterpret_cast<const float4*>(a.bond_emb) + 2 * i + 1);
       s_ctab[i] = make_uint4(tc::pack_f16x2(c0.x, c0.y), tc::pack_f16x2(c0.z, c0.w), tc::pack_f16x2(c1.x, c1.y),
@@ -435,7 +472,7 @@ __global__ void __launch_bounds__(256, 1) mpnn_fused_h2_kernel(const FusedArgs a
     }
   }
   if (warp == 0) tc::tmem_alloc<512>(&ctl.tmem_base);
-  if (t == 0) {
+  if (u == 0) {
     tc::mbar_init(&ws.bar[0], 1);
     tc::mbar_init(&ws.bar[1], 1);
     tc::mbar_init(&ws.bar[2], 1);
@@ -446,14 +483,21 @@ __global__ void __launch_bounds__(256, 1) mpnn_fused_h2_kernel(const FusedArgs a
   __syncthreads();
   tc::fence_after_thread_sync();
 
-  const uint32_t tbase = ctl.tmem_base + (uint32_t)(wg * 256);
+  const uint32_t sw0 = tc::smem_u32(smem);
+  const uint32_t tbase = ctl.tmem_base + (uint32_t)(ctx * 256);
   const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+  // TMEM columns of a context: [0,128) Z (K = 256), dead after GEMM1, then [0,16) h, [16,32) agg, [32,48) r*h operands;
+  // [128,160) GEMM1 accumulator (agg); [160,224) z | r pre-activations; [224,256) candidate pre-activation.
   const uint32_t tZ = tbase, tAh = tbase, tAagg = tbase + 16, tArh = tbase + 32;
   const uint32_t tCagg = tbase + 128, tCzr = tbase + 160, tCht = tbase + 224;
+  // B-operand descriptors of step 0; step s adds s * BYTES / 16 to the address field (no carry: smem < 256 KiB)
+  const uint64_t dWc = tc::make_smem_desc(sw0, D * 16, 128);
+  const uint64_t dBzr = tc::make_smem_desc(sw0 + FusedPack::OFF_BZR, 2 * D * 16, 128);
+  const uint64_t dBh = tc::make_smem_desc(sw0 + FusedPack::OFF_BH, D * 16, 128);
+  const bool mma_warp = (u >> 5) == 0;  // warp 0 of the context issues every MMA (one elected lane)
   const uint32_t idesc32 = tc::make_idesc(FMT, FZ_ROWS, D), idesc64 = tc::make_idesc(FMT, FZ_ROWS, 2 * D);
-  const uint32_t sw0 = tc::smem_u32(smem);
-  const int bar_id = 1 + wg;
-  const bool descending = wg & 1;
+  const int bar_id = 1 + ctx;
+  const bool descending = ctx & 1;
 
   const int P = a.n_pairs;
   const int n_groups = (P + FZ_GROUP - 1) / FZ_GROUP;
@@ -461,13 +505,14 @@ __global__ void __launch_bounds__(256, 1) mpnn_fused_h2_kernel(const FusedArgs a
   const int cta_in_tower = tower ? (int)blockIdx.x - a.n_cta_cat : (int)blockIdx.x;
   const float4* emb4 = reinterpret_cast<const float4*>(a.atom_emb);
   uint32_t ph = 0;
+  FZ_PROF_DECL;
 
-  for (int g = cta_in_tower * 2 + wg; g < n_groups; g += n_cta_tower * 2) {
+  for (int g = cta_in_tower * 2 + ctx; g < n_groups; g += n_cta_tower * 2) {
     const int m0 = g * FZ_GROUP, nm = min(FZ_GROUP, P - m0);
     const int base_mol = tower * P + m0;
-    tc::named_bar_sync(bar_id, 128);
-    if (t <= nm) ws.molp[t] = __ldg(a.mol_ptr + base_mol + t);
-    tc::named_bar_sync(bar_id, 128);
+    tc::named_bar_sync(bar_id, F2_CTX_THREADS);
+    if (u <= nm) ws.molp[u] = __ldg(a.mol_ptr + base_mol + u);
+    tc::named_bar_sync(bar_id, F2_CTX_THREADS);
     int ms = 0;
     while (ms < nm) {
       const int a0 = ws.molp[ms];
@@ -475,25 +520,23 @@ __global__ void __launch_bounds__(256, 1) mpnn_fused_h2_kernel(const FusedArgs a
       while (me < nm && ws.molp[me + 1] - a0 <= FZ_ROWS) ++me;
       int rows = ws.molp[me] - a0;
       if (rows > FZ_ROWS) {
-        if (t == 0 && a.status) *a.status = 1;
+        if (u == 0 && a.status) *a.status = 1;
         rows = FZ_ROWS;
       }
-      // ---------------------------------------------------------------- natural row t: indices, in-degree key
-      int key;
-      {
-        const bool valid = t < rows;
+      // ---------------------------------------------------------------- natural row p: indices, in-degree key (warps 0-3)
+      FZ_PROF_T(0);
+      int key = 0, rank = 0;
+      if (hf == 0) {
+        const bool valid = p < rows;
         int aid = 0, e0 = 0, e1 = 0;
         if (valid) {
-          aid = __ldg(a.atom_id + a0 + t);
-          e0 = __ldg(a.row_ptr + a0 + t);
-          e1 = __ldg(a.row_ptr + a0 + t + 1);
+          aid = __ldg(a.atom_id + a0 + p);
+          e0 = __ldg(a.row_ptr + a0 + p);
+          e1 = __ldg(a.row_ptr + a0 + p + 1);
         }
-        ws.se0[t] = e0, ws.se1[t] = e1, ws.said[t] = aid;
-        ws.amask[t] = (valid && aid > 0) ? 1 : 0;  // models/layers.py:163
+        ws.se0[p] = e0, ws.se1[p] = e1, ws.said[p] = aid;
+        ws.amask[p] = (valid && aid > 0) ? 1 : 0;  // models/layers.py:163
         key = min(e1 - e0, 7);
-      }
-      int rank = 0;
-      {
         int mine = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -503,8 +546,8 @@ __global__ void __launch_bounds__(256, 1) mpnn_fused_h2_kernel(const FusedArgs a
         }
         if (lane < 8) ws.cnt[wq][lane] = mine;
       }
-      tc::named_bar_sync(bar_id, 128);
-      {
+      tc::named_bar_sync(bar_id, F2_CTX_THREADS);
+      if (hf == 0) {
         int off = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -513,42 +556,44 @@ __global__ void __launch_bounds__(256, 1) mpnn_fused_h2_kernel(const FusedArgs a
           if (k == key) off += (wq > 0 ? c0 : 0) + (wq > 1 ? c1 : 0) + (wq > 2 ? c2 : 0);
         }
         const int slot = off + rank;
-        ws.rowof[descending ? FZ_ROWS - 1 - slot : slot] = (unsigned char)t;
+        ws.rowof[descending ? FZ_ROWS - 1 - slot : slot] = (unsigned char)p;
       }
-      tc::named_bar_sync(bar_id, 128);
-      // ---------------------------------------------------------------- thread t now owns row r
-      const int r = ws.rowof[t];
-      const int e0 = ws.se0[r], e1 = ws.se1[r];
-      uint32_t* hbrow = &ws.hb[r * FZ_HS];
-      float h[D];
+      tc::named_bar_sync(bar_id, F2_CTX_THREADS);
+      // ---------------------------------------------------------------- this thread owns columns [16 hf, 16 hf + 16) of row r
+      const int r = ws.rowof[p];
+      const int e0 = ws.se0[r], e1 = (a.debug & 1) ? e0 : ws.se1[r];
+      uint32_t* hbrow = &ws.hb[r * FZ_HS + hf * DH];
+      float h[DH];
       {  // Embedding(atom)
         const bool valid = r < rows;
         const int id = min(max(ws.said[r], 0), a.atom_vocab - 1);
 #pragma unroll
-        for (int c = 0; c < D / 4; ++c) {
-          const float4 x = valid ? __ldg(emb4 + id * (D / 4) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < DH / 4; ++c) {
+          const float4 x = valid ? __ldg(emb4 + id * (D / 4) + hf * (DH / 4) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
           h[4 * c] = x.x, h[4 * c + 1] = x.y, h[4 * c + 2] = x.z, h[4 * c + 3] = x.w;
           reinterpret_cast<uint4*>(hbrow)[c] =
               make_uint4(tc::pack_f16x2(x.x, x.x), tc::pack_f16x2(x.y, x.y), tc::pack_f16x2(x.z, x.z), tc::pack_f16x2(x.w, x.w));
         }
       }
-      if (me < nm && lane < 8) {  // index lines of the next tile -> L2 (it follows this tile in all three arrays)
+      if (me < nm && hf == 0 && lane < 8) {  // index lines of the next tile -> L2 (it follows this tile in all arrays)
         const int an = ws.molp[me], en = ws.se1[rows - 1];
         if (wq == 0) prefetch_l2(a.atom_id + min(an + lane * 32, a.n_atoms - 1));
         if (wq == 1) prefetch_l2(a.row_ptr + min(an + lane * 32, a.n_atoms));
         if (wq == 2) prefetch_l2(a.col_src + min(en + lane * 32, a.n_unique - 1));
         if (wq == 3) prefetch_l2(a.edge_bm + min(en + lane * 32, a.n_unique - 1));
       }
-      tc::named_bar_sync(bar_id, 128);
+      tc::named_bar_sync(bar_id, F2_CTX_THREADS);
 
+      FZ_PROF_T(1);
       for (int s = 0; s < a.steps; ++s) {
-        const uint32_t sw = sw0 + (uint32_t)(s * FusedPack::BYTES);
-        const float* bias = reinterpret_cast<const float*>(smem + s * FusedPack::BYTES + FusedPack::OFF_BIAS);
-        // ------------------------------------------------------------ Z row (half2 accumulators) -> TMEM
+        FZ_PROF_T(2);
+        const uint64_t dstep = (uint64_t)(s * (FusedPack::BYTES / 16));
+        const float* bias = reinterpret_cast<const float*>(smem + s * FusedPack::BYTES + FusedPack::OFF_BIAS) + hf * DH;
+        // ------------------------------------------------------------ half of the Z row (half2 accumulators) -> TMEM
         {
-          __half2 acc[D * FZ_K / 2];
+          __half2 acc[DH * FZ_K / 2];
 #pragma unroll
-          for (int i = 0; i < D * FZ_K / 2; ++i) acc[i] = __half2(__ushort_as_half(0), __ushort_as_half(0));
+          for (int i = 0; i < DH * FZ_K / 2; ++i) acc[i] = __half2(__ushort_as_half(0), __ushort_as_half(0));
 #pragma unroll 1
           for (int e = e0; e < e1; ++e) {
             const int bm = __ldg(a.edge_bm + e);
@@ -562,9 +607,9 @@ __global__ void __launch_bounds__(256, 1) mpnn_fused_h2_kernel(const FusedArgs a
             c[1] = __hmul2(*reinterpret_cast<const __half2*>(&cu.y), mult);
             c[2] = __hmul2(*reinterpret_cast<const __half2*>(&cu.z), mult);
             c[3] = __hmul2(*reinterpret_cast<const __half2*>(&cu.w), mult);
-            const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[src * FZ_HS]);
+            const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[src * FZ_HS + hf * DH]);
 #pragma unroll
-            for (int q = 0; q < D / 4; ++q) {
+            for (int q = 0; q < DH / 4; ++q) {
               const uint4 hv = hp[q];
               const __half2 hm[4] = {*reinterpret_cast<const __half2*>(&hv.x), *reinterpret_cast<const __half2*>(&hv.y),
                                      *reinterpret_cast<const __half2*>(&hv.z), *reinterpret_cast<const __half2*>(&hv.w)};
@@ -575,135 +620,154 @@ __global__ void __launch_bounds__(256, 1) mpnn_fused_h2_kernel(const FusedArgs a
             }
           }
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
+          for (int ch = 0; ch < 2; ++ch) {
             uint32_t rr[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) rr[i] = *reinterpret_cast<const uint32_t*>(&acc[ch * 32 + i]);
-            tc::tmem_st32(tZ + lane_off + (uint32_t)(ch * 32), rr);
+            tc::tmem_st32(tZ + lane_off + (uint32_t)(hf * 64 + ch * 32), rr);
           }
         }
         tc::tmem_wait_st();
+        FZ_PROF_T(3);
         tc::fence_before_thread_sync();
-        tc::named_bar_sync(bar_id, 128);
+        tc::named_bar_sync(bar_id, F2_CTX_THREADS);
+        FZ_PROF_T(4);
         // ------------------------------------------------------------ GEMM1: agg = Z . Wc
-        if (t == 0) {
+        if (mma_warp && !(a.debug & 2)) {
           tc::fence_after_thread_sync();
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < D * FZ_K / 16; ++ks)
-            tc::mma_f16_ts(tCagg, tZ + 8 * ks, tc::make_smem_desc(sw + ks * 1024, D * 16, 128), idesc32, ks > 0);
-          tc::mma_commit(&ws.bar[0]);
+            for (int ks = 0; ks < D * FZ_K / 16; ++ks)
+              tc::mma_f16_ts(tCagg, tZ + 8 * ks, dWc + dstep + (uint64_t)(ks * 64), idesc32, ks > 0);
+            tc::mma_commit(&ws.bar[0]);
+          }
+          __syncwarp();
         }
-        tc::mbar_wait(&ws.bar[0], ph);
+        if (!(a.debug & 2)) tc::mbar_wait(&ws.bar[0], ph);
         tc::fence_after_thread_sync();
+        FZ_PROF_T(5);
         {
-          float v[32];
-          tc::tmem_ld32(tCagg + lane_off, v);
-          uint32_t rr[16];
+          float v[16];
+          tc::tmem_ld16(tCagg + lane_off + hf * DH, v);
+          uint32_t rr[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) rr[i] = tc::pack_f16x2(v[2 * i], v[2 * i + 1]);
-          tc::tmem_st16(tAagg + lane_off, rr);
+          for (int i = 0; i < 8; ++i) rr[i] = tc::pack_f16x2(v[2 * i], v[2 * i + 1]);
+          tc::tmem_st8(tAagg + lane_off + hf * 8, rr);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) rr[i] = tc::pack_f16x2(h[2 * i], h[2 * i + 1]);
-          tc::tmem_st16(tAh + lane_off, rr);
+          for (int i = 0; i < 8; ++i) rr[i] = tc::pack_f16x2(h[2 * i], h[2 * i + 1]);
+          tc::tmem_st8(tAh + lane_off + hf * 8, rr);
         }
         tc::tmem_wait_st();
+        FZ_PROF_T(6);
         tc::fence_before_thread_sync();
-        tc::named_bar_sync(bar_id, 128);
+        tc::named_bar_sync(bar_id, F2_CTX_THREADS);
+        FZ_PROF_T(7);
         // ------------------------------------------------------------ GEMM2 / GEMM3a
-        if (t == 0) {
+        if (mma_warp && !(a.debug & 2)) {
           tc::fence_after_thread_sync();
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            tc::mma_f16_ts(tCzr, tAh + 8 * ks, tc::make_smem_desc(sw + FusedPack::OFF_BZR + ks * 2048, 2 * D * 16, 128),
-                           idesc64, ks > 0);
-          tc::mma_commit(&ws.bar[1]);
+            for (int ks = 0; ks < 4; ++ks) tc::mma_f16_ts(tCzr, tAh + 8 * ks, dBzr + dstep + (uint64_t)(ks * 128), idesc64, ks > 0);
+            tc::mma_commit(&ws.bar[1]);
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
-            tc::mma_f16_ts(tCht, tAagg + 8 * ks, tc::make_smem_desc(sw + FusedPack::OFF_BH + (ks + 2) * 1024, D * 16, 128),
-                           idesc32, ks > 0);
+            for (int ks = 0; ks < 2; ++ks)
+              tc::mma_f16_ts(tCht, tAagg + 8 * ks, dBh + dstep + (uint64_t)((ks + 2) * 64), idesc32, ks > 0);
+          }
+          __syncwarp();
         }
-        tc::mbar_wait(&ws.bar[1], ph);
+        if (!(a.debug & 2)) tc::mbar_wait(&ws.bar[1], ph);
         tc::fence_after_thread_sync();
-        float z[D];
+        FZ_PROF_T(8);
+        float z[DH];
         {
-          float v[32];
-          tc::tmem_ld32(tCzr + lane_off, v);
+          float v[16];
+          tc::tmem_ld16(tCzr + lane_off + hf * DH, v);
 #pragma unroll
-          for (int j = 0; j < D; ++j) z[j] = fz_sigmoid<PRECISE>(v[j] + bias[j]);
-          tc::tmem_ld32(tCzr + D + lane_off, v);
-          uint32_t rr[16];
+          for (int j = 0; j < DH; ++j) z[j] = fz_sigmoid<PRECISE>(v[j] + bias[j]);
+          tc::tmem_ld16(tCzr + D + lane_off + hf * DH, v);
+          uint32_t rr[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 8; ++i) {
             const float r0 = fz_sigmoid<PRECISE>(v[2 * i] + bias[D + 2 * i]) * h[2 * i];
             const float r1 = fz_sigmoid<PRECISE>(v[2 * i + 1] + bias[D + 2 * i + 1]) * h[2 * i + 1];
             rr[i] = tc::pack_f16x2(r0, r1);
           }
-          tc::tmem_st16(tArh + lane_off, rr);
+          tc::tmem_st8(tArh + lane_off + hf * 8, rr);
         }
         tc::tmem_wait_st();
+        FZ_PROF_T(9);
         tc::fence_before_thread_sync();
-        tc::named_bar_sync(bar_id, 128);
+        tc::named_bar_sync(bar_id, F2_CTX_THREADS);
+        FZ_PROF_T(10);
         // ------------------------------------------------------------ GEMM3b
-        if (t == 0) {
+        if (mma_warp && !(a.debug & 2)) {
           tc::fence_after_thread_sync();
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
-            tc::mma_f16_ts(tCht, tArh + 8 * ks, tc::make_smem_desc(sw + FusedPack::OFF_BH + ks * 1024, D * 16, 128), idesc32,
-                           true);
-          tc::mma_commit(&ws.bar[2]);
+            for (int ks = 0; ks < 2; ++ks) tc::mma_f16_ts(tCht, tArh + 8 * ks, dBh + dstep + (uint64_t)(ks * 64), idesc32, true);
+            tc::mma_commit(&ws.bar[2]);
+          }
+          __syncwarp();
         }
-        tc::mbar_wait(&ws.bar[2], ph);
+        if (!(a.debug & 2)) tc::mbar_wait(&ws.bar[2], ph);
         tc::fence_after_thread_sync();
+        FZ_PROF_T(11);
         {  // candidate, blend, LayerNorm, residual  (models/layers.py:151-156)
-          float gq[32];
-          tc::tmem_ld32(tCht + lane_off, gq);
-          float mean = 0.f;
+          float gq[16];
+          tc::tmem_ld16(tCht + lane_off + hf * DH, gq);
+          float sum = 0.f, sq = 0.f;
 #pragma unroll
-          for (int j = 0; j < D; ++j) {
+          for (int j = 0; j < DH; ++j) {
             const float ht = fz_tanh<PRECISE>(gq[j] + bias[2 * D + j]);
             gq[j] = fmaf(z[j], ht - h[j], h[j]);
-            mean += gq[j];
+            sum += gq[j];
+            sq = fmaf(gq[j], gq[j], sq);
           }
-          mean *= (1.0f / D);
-          float var = 0.f;
+          ws.ln[hf][p] = make_float2(sum, sq);
+          FZ_PROF_T(12);
+          tc::fence_before_thread_sync();
+          tc::named_bar_sync(bar_id, F2_CTX_THREADS);
+          FZ_PROF_T(13);
+          const float2 other = ws.ln[hf ^ 1][p];
+          const float mean = (sum + other.x) * (1.0f / D);
+          const float var = fmaxf((sq + other.y) * (1.0f / D) - mean * mean, 0.f);  // biased variance
+          const float inv = PRECISE ? 1.0f / sqrtf(var + a.eps) : rsqrtf(var + a.eps);
 #pragma unroll
-          for (int j = 0; j < D; ++j) {
-            const float cdev = gq[j] - mean;
-            var = fmaf(cdev, cdev, var);
-          }
-          const float inv = PRECISE ? 1.0f / sqrtf(var * (1.0f / D) + a.eps) : rsqrtf(var * (1.0f / D) + a.eps);
-#pragma unroll
-          for (int j = 0; j < D; ++j) h[j] = fmaf((gq[j] - mean) * inv, bias[3 * D + j], bias[4 * D + j]) + h[j];
+          for (int j = 0; j < DH; ++j) h[j] = fmaf((gq[j] - mean) * inv, bias[3 * D + j], bias[4 * D + j]) + h[j];
           if (s + 1 < a.steps) {
 #pragma unroll
-            for (int c = 0; c < D / 4; ++c)
+            for (int c = 0; c < DH / 4; ++c)
               reinterpret_cast<uint4*>(hbrow)[c] = make_uint4(tc::pack_f16x2(h[4 * c], h[4 * c]), tc::pack_f16x2(h[4 * c + 1], h[4 * c + 1]),
                                                               tc::pack_f16x2(h[4 * c + 2], h[4 * c + 2]), tc::pack_f16x2(h[4 * c + 3], h[4 * c + 3]));
           } else {  // last step: fp32 rows for the pooling (every gather of this tile is done)
 #pragma unroll
-            for (int c = 0; c < D / 4; ++c)
+            for (int c = 0; c < DH / 4; ++c)
               reinterpret_cast<float4*>(hbrow)[c] = make_float4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
           }
         }
-        tc::fence_before_thread_sync();
-        tc::named_bar_sync(bar_id, 128);
+        FZ_PROF_T(14);
+        tc::named_bar_sync(bar_id, F2_CTX_THREADS);
+        FZ_PROF_T(15);
         ph ^= 1;
       }
-      // ---------------------------------------------------------------- GlobalSumPool
+      // ---------------------------------------------------------------- GlobalSumPool: warp per molecule, lane = column
       {
-        const float* hf = reinterpret_cast<const float*>(ws.hb);
-        for (int mi = ms + (t >> 5); mi < me; mi += 4) {
+        const float* hfp = reinterpret_cast<const float*>(ws.hb);
+        for (int mi = ms + (u >> 5); mi < me; mi += F2_CTX_THREADS / 32) {
           const int lo = ws.molp[mi] - a0, hi = min(ws.molp[mi + 1] - a0, FZ_ROWS);
           float sacc = 0.f;
           for (int rr = lo; rr < hi; ++rr)
-            if (ws.amask[rr]) sacc += hf[rr * FZ_HS + lane];
+            if (ws.amask[rr]) sacc += hfp[rr * FZ_HS + lane];
           a.pooled[(size_t)(base_mol + mi) * D + lane] = sacc;
         }
       }
-      tc::named_bar_sync(bar_id, 128);
+      FZ_PROF_T(16);
+      tc::named_bar_sync(bar_id, F2_CTX_THREADS);
+      FZ_PROF_T(17);
       ms = me;
     }
   }
+  FZ_PROF_FLUSH;
   tc::fence_before_thread_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<512>(ctl.tmem_base);
@@ -772,7 +836,14 @@ extern "C" int imp_mpnn_forward_fused(const imp_graph_t* g, const float* d_atom_
   a.mol_ptr = g->mol_ptr, a.atom_id = g->atom_id, a.row_ptr = g->row_ptr, a.col_src = g->col_src, a.edge_bm = g->edge_bm;
   a.atom_emb = d_atom_emb, a.bond_emb = d_bond_emb, a.packed = (const unsigned char*)d_packed, a.pooled = d_pooled;
   a.n_atoms = g->n_atoms, a.n_unique = g->n_unique;
+
   a.status = d_status, a.n_pairs = g->n_pairs, a.atom_vocab = atom_vocab, a.bond_vocab = g->bond_vocab, a.steps = steps, a.eps = eps;
+  a.prof = nullptr;
+  a.debug = (flags >> 8) & 0xff;
+#ifdef FZ_PROFILE
+  a.prof = reinterpret_cast<long long*>(d_status);  // profiling build: d_status must hold 3 * 18 int64 (zeroed by the caller)
+  a.status = nullptr;
+#endif
   // one persistent CTA per SM; CTAs are split between the towers in proportion to their atoms
   const int sms = fused_sm_count();
   const int n_groups = (int)ceil_div(g->n_pairs, FZ_GROUP);
@@ -793,10 +864,10 @@ extern "C" int imp_mpnn_forward_fused(const imp_graph_t* g, const float* d_atom_
     IMP_REQUIRE(smem2 <= 227 * 1024, IMP_ERR_DIM, "imp_mpnn_forward_fused: needs %zu B of shared memory", smem2);
     if (precise) {
       IMP_CUDA(cudaFuncSetAttribute(mpnn_fused_h2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      mpnn_fused_h2_kernel<true><<<grid, 256, smem2, st>>>(a);
+      mpnn_fused_h2_kernel<true><<<grid, 2 * F2_CTX_THREADS, smem2, st>>>(a);
     } else {
       IMP_CUDA(cudaFuncSetAttribute(mpnn_fused_h2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      mpnn_fused_h2_kernel<false><<<grid, 256, smem2, st>>>(a);
+      mpnn_fused_h2_kernel<false><<<grid, 2 * F2_CTX_THREADS, smem2, st>>>(a);
     }
     IMP_LAUNCH_CHECK();
     return 0;

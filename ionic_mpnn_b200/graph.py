@@ -121,6 +121,15 @@ class PackedGraphBatch:
             self.dev_y = torch.from_numpy(self.target).to(self.device, non_blocking=non_blocking)
         return self
 
+    def pin(self):
+        """Page-locks the host arrays (once) so that H2D copies can run asynchronously on a copy stream."""
+        import torch
+
+        if getattr(self, "pinned", None) is None:
+            self.pinned = {k: torch.from_numpy(self.host[k]).pin_memory() for k in GRAPH_FIELDS}
+            self.pinned_T = None if self.temperature is None else torch.from_numpy(self.temperature).pin_memory()
+        return self
+
     def c_struct(self):
         if self.dev is None:
             raise _lib.ImpError("PackedGraphBatch is not on a device: call .to('cuda') first")
@@ -130,6 +139,56 @@ class PackedGraphBatch:
     def nbytes(self):
         n = sum(self.host[k].nbytes for k in GRAPH_FIELDS)
         return n + (0 if self.temperature is None else self.temperature.nbytes)
+
+
+FUSED_FIELDS = ("mol_ptr", "atom_id", "row_ptr", "col_src", "edge_bm")  # what imp_mpnn_forward_fused reads
+
+
+class DeviceSlot:
+    """Device staging buffers for one in-flight chunk of a streamed prediction (see MPNNModel.predict_stream).
+    Quacks like a PackedGraphBatch on the device side."""
+
+    def __init__(self, device, fields):
+        self.device, self.fields = device, fields
+        self.dev = {}
+        self.dev_T = None
+        self.dev_y = None
+        self.cap = {}
+
+    def load(self, chunk, stream):
+        """Enqueues the H2D copies of ``chunk`` (pinned) on ``stream``; returns the bytes copied."""
+        import torch
+
+        n = 0
+        with torch.cuda.stream(stream):
+            for k in self.fields:
+                src = chunk.pinned[k]
+                if self.cap.get(k, 0) < src.numel():
+                    self.cap[k] = int(src.numel() * 1.05) + 16
+                    self.dev[k + "_buf"] = torch.empty(self.cap[k], dtype=torch.int32, device=self.device)
+                self.dev[k] = self.dev[k + "_buf"][: src.numel()]
+                self.dev[k].copy_(src, non_blocking=True)
+                n += src.numel() * 4
+            for k in GRAPH_FIELDS:  # fields the fused path never reads
+                if k not in self.fields:
+                    self.dev[k] = self.dev[self.fields[0]]
+            if chunk.pinned_T is not None:
+                if self.cap.get("T", 0) < chunk.pinned_T.numel():
+                    self.cap["T"] = int(chunk.pinned_T.numel() * 1.05) + 16
+                    self._T_buf = torch.empty(self.cap["T"], dtype=torch.float32, device=self.device)
+                self.dev_T = self._T_buf[: chunk.pinned_T.numel()]
+                self.dev_T.copy_(chunk.pinned_T, non_blocking=True)
+                n += chunk.pinned_T.numel() * 4
+        for a in ("n_pairs", "n_atoms", "n_cat_atoms", "n_unique", "n_edges", "bond_vocab", "max_mol_atoms"):
+            setattr(self, a, getattr(chunk, a))
+        return n
+
+    def c_struct(self):
+        return _lib.Graph(self.n_pairs, self.n_atoms, self.n_cat_atoms, self.n_unique, self.n_edges, self.bond_vocab,
+                          *(self.dev[k].data_ptr() for k in GRAPH_FIELDS))
+
+    def to(self, device):
+        return self
 
 
 def pack_flat(cation: FlatIons, anion: FlatIons, bond_vocab_size, max_edges=None, double_edges=True, shift_ids=True,

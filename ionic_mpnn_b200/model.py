@@ -340,6 +340,51 @@ class MPNNModel:
 
     __call__ = predict
 
+    def predict_stream(self, chunks, out=None):
+        """Pipelined prediction over a list of host-resident packed chunks (the cfg-3 "inference sweep" shape): the
+        H2D copy of chunk i+1 runs on a copy stream while chunk i computes; predictions are copied back into ``out``
+        (a pinned float32 tensor of the total pair count, allocated if None).  Two device staging slots.
+        Returns (out, bytes_h2d).  Nothing is synchronised on return: the caller syncs the current stream."""
+        import torch
+
+        from .graph import FUSED_FIELDS, GRAPH_FIELDS, DeviceSlot
+
+        total = sum(c.n_pairs for c in chunks)
+        if out is None:
+            out = torch.empty(total, dtype=torch.float32).pin_memory()
+        if not self._tables_valid:
+            self.refresh_tables()
+        st = getattr(self, "_stream_state", None)
+        if st is None:
+            st = self._stream_state = {"copy": torch.cuda.Stream(device=self.device), "slots": None, "fields": None}
+        compute = torch.cuda.current_stream()
+        copy = st["copy"]
+        nbytes = 0
+        off = 0
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [None, None]
+        for i, ch in enumerate(chunks):
+            ch.pin()
+            fields = FUSED_FIELDS if self.use_fused(ch) else GRAPH_FIELDS
+            if st["slots"] is None or st["fields"] != fields:
+                st["slots"] = [DeviceSlot(self.device, fields), DeviceSlot(self.device, fields)]
+                st["fields"] = fields
+            slot = st["slots"][i % 2]
+            if done[i % 2] is not None:
+                copy.wait_event(done[i % 2])  # the kernels that read this slot two chunks ago have finished
+            else:
+                copy.wait_stream(compute)
+            nbytes += slot.load(ch, copy)
+            ready[i % 2] = torch.cuda.Event()
+            ready[i % 2].record(copy)
+            compute.wait_event(ready[i % 2])
+            o = self.forward_packed(slot)
+            out[off:off + ch.n_pairs].copy_(o, non_blocking=True)
+            off += ch.n_pairs
+            done[i % 2] = torch.cuda.Event()
+            done[i % 2].record(compute)
+        return out, nbytes
+
 
 def make_spec(kind="viscosity", atom_vocab_size=124, bond_vocab_size=72, atom_dim=32, bond_dim=8, fp_size=32,
               mixing_size=20, num_steps=4):

@@ -227,3 +227,22 @@ def test_fused_refuses_shapes_outside_its_envelope():
     # 'auto' falls back to the staged tensor kernels for the same batch
     m2 = build_model(124, 72, precision="fp16")
     assert np.isfinite(m2.forward_packed(big).cpu().numpy()).all()
+
+
+def test_predict_stream_matches_per_chunk_predict():
+    """Double-buffered streamed prediction == chunk-by-chunk forward (bit-identical: same kernels, same order)."""
+    from ionic_mpnn_b200 import graph
+    from ionic_mpnn_b200.viscosity import build_model
+
+    m = build_model(124, 72, precision="fp16", seed=4)
+    chunks = [graph.synth_batch(n, seed=40 + i)[0] for i, n in enumerate([700, 64, 1500, 1, 333])]
+    out, nbytes = m.predict_stream(chunks)
+    torch.cuda.synchronize()
+    want = np.concatenate([m.forward_packed(c.to("cuda")).cpu().numpy() for c in chunks])
+    assert nbytes > 0 and np.array_equal(out.numpy(), want)
+    # staged kernels stream too (all CSR fields are copied)
+    m2 = build_model(124, 72, precision="fp32", seed=4)
+    out2, _ = m2.predict_stream(chunks)
+    torch.cuda.synchronize()
+    want2 = np.concatenate([m2.forward_packed(c.to("cuda")).cpu().numpy() for c in chunks])
+    assert np.array_equal(out2.numpy(), want2)

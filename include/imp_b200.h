@@ -221,6 +221,54 @@ int imp_readout_mp(const float* d_pooled, int32_t n_pairs, int32_t d, int32_t fp
                    const float* d_b1, const float* d_W2, const float* d_b2, float* d_out, float* d_aux, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Training step (train_viscosity.py:227-230,328-338: mse + l2 kernel regularisers, Adam(1e-3, clipnorm=1.0)).
+ * fp32 backward kernels for atom_dim 32; every reduction is two-stage in a fixed order (bit-reproducible).
+ * The forward that precedes them is the staged fp32 path with h_0..h_S and agg_0..agg_{S-1} kept.
+ * "workspace" sizes come from the imp_*_workspace_floats queries; gradients of one GatedUpdate layer are laid out
+ * [dWz (2d,d) | dbz | dWr | dbr | dWh | dbh | dgamma | dbeta] (the Keras variable order of the layer); gradients of the readout
+ * [per tower: dW_fp, db_fp, dW_mix, db_mix | dW_head (mix,3 or mix,fp2), db_head | (mp) dW2, db2].
+ * ------------------------------------------------------------------------------------------- */
+/* K2 for training: lane-interleaved tables and their transposes (for imp_message_agg_bwd). */
+int imp_bond_table_train(const float* d_bond_emb, int32_t bond_vocab, int32_t bond_dim, int32_t d, int32_t n_tables,
+                         const float* const* h_W, float* const* h_table_il, float* const* h_table_ilT, void* stream);
+/* B6: loss and readout backward.  scale = 2 / global batch (d mse / d out); *d_sse = sum of squared errors of this
+ * batch; d_dpooled [2P,d]; d_out optional predictions. */
+int64_t imp_readout_bwd_workspace_floats(int32_t d, int32_t fp, int32_t mix, int32_t fp2);
+int imp_readout_bwd(const float* d_pooled, int32_t n_pairs, int32_t d, int32_t fp, int32_t mix, int32_t fp2,
+                    const imp_readout_weights_t* w_cat, const imp_readout_weights_t* w_an, const float* d_W1,
+                    const float* d_b1, const float* d_W2, const float* d_b2, const float* d_T, const float* d_y, float scale,
+                    float* d_dpooled, float* d_out, float* d_grads, float* d_sse, float* d_workspace, void* stream);
+/* B5: GlobalSumPool backward (models/layers.py:161-164): dh[v] = [atom_id[v] > 0] * d_pooled[molecule of v]. */
+int imp_pool_bwd(const int32_t* d_mol_ptr, const int32_t* d_atom_id, int32_t n_mols, const float* d_dpooled, int32_t d,
+                 float* d_dh, void* stream);
+/* B4: GatedUpdate backward (models/layers.py:142-156); recomputes the gates from (h, agg). */
+int64_t imp_gated_update_bwd_workspace_floats(int32_t d);
+int imp_gated_update_bwd(const float* d_h, const float* d_agg, const float* d_gout, int32_t n_atoms, int32_t n_cat_atoms,
+                         int32_t d, const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_dh,
+                         float* d_dagg, float* d_grads_cat, float* d_grads_an, float* d_workspace, void* stream);
+/* B3a: dh += sum_e mult_e T[b_e]^T dagg[src_e] over the rows of the SAME CSR (the live edge set is symmetric:
+ * train_viscosity.py:87-91 appends the reverse of every entry).  Tables from imp_bond_table_train. */
+int imp_message_agg_bwd(const imp_graph_t* g, const float* d_dagg, int32_t d, const float* d_table_ilT_cat,
+                        const float* d_table_ilT_an, float* d_dh /* accumulated */, void* stream);
+/* B3b: gradients of bond_transform (both towers of one step) and of the shared bond embedding (accumulated).
+ * d_entry_dst[e] = destination atom of CSR entry e; chunks = host-built split of the (tower, bond) buckets:
+ * chunk c covers bucket_perm[chunk_begin[c] .. chunk_end[c]); bucket_chunk_ptr[2*V_b+1] delimits each bucket's chunks. */
+int imp_bond_transform_bwd(const imp_graph_t* g, const int32_t* d_entry_dst, const int32_t* d_chunk_begin,
+                           const int32_t* d_chunk_end, int32_t n_chunks, const int32_t* d_bucket_chunk_ptr,
+                           const float* d_dagg, const float* d_h, int32_t d, int32_t bond_dim, const float* d_bond_emb,
+                           const float* d_W_cat, const float* d_W_an, float* d_dW_cat, float* d_dW_an, float* d_dbond_emb,
+                           float* d_dtable, float* d_workspace, void* stream);
+/* B1: Embedding(atom) backward. */
+int64_t imp_embed_bwd_workspace_floats(int32_t atom_vocab, int32_t d);
+int imp_embed_bwd(const int32_t* d_atom_id, const float* d_dh0, int32_t n_atoms, int32_t atom_vocab, int32_t d,
+                  float* d_datom_emb, float* d_workspace, void* stream);
+/* Per-variable clip_by_norm + Adam over a flat parameter buffer [Keras semantics].  var_off[n_vars+1] delimits the
+ * variables; var_l2[v] = l2 regulariser coefficient of variable v (its gradient 2*l2*w is added before clipping). */
+int imp_clip_adam(float* d_param, const float* d_grad, float* d_m, float* d_v, const int64_t* d_var_off,
+                  const float* d_var_l2, int32_t n_vars, float* d_norms2, float clipnorm, float lr, float beta1, float beta2,
+                  float eps, int32_t step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Diagnostics: one-CTA tcgen05 product D[128,N] = A[128,K] * B[N,K]^T (kind 0 = bf16, 1 = tf32 operands from
  * shared memory; 2 = bf16, 3 = f16 with the A operand written to tensor memory by the threads, the form the fused
  * forward uses; fp32 accumulate) through the library's own shared-memory staging layout and UMMA descriptors.  Used by

@@ -81,6 +81,22 @@ SIGNATURES = {
                                    C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp]),
     "imp_readout_mp": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ReadoutWeights),
                                  C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp, vp]),
+    "imp_bond_table_train": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(vp),
+                                       C.POINTER(vp), vp]),
+    "imp_readout_bwd_workspace_floats": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "imp_readout_bwd": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ReadoutWeights),
+                                  C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp, vp, vp, vp]),
+    "imp_pool_bwd": (C.c_int, [vp, vp, C.c_int32, vp, C.c_int32, vp, vp]),
+    "imp_gated_update_bwd_workspace_floats": (C.c_int64, [C.c_int32]),
+    "imp_gated_update_bwd": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(GruWeights),
+                                       C.POINTER(GruWeights), C.c_float, vp, vp, vp, vp, vp, vp]),
+    "imp_message_agg_bwd": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, vp, vp, vp, vp]),
+    "imp_bond_transform_bwd": (C.c_int, [C.POINTER(Graph), vp, vp, vp, C.c_int32, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp,
+                                         vp, vp, vp, vp, vp, vp]),
+    "imp_embed_bwd_workspace_floats": (C.c_int64, [C.c_int32, C.c_int32]),
+    "imp_embed_bwd": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]),
+    "imp_clip_adam": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int32, vp, C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_float, C.c_int32, vp]),
     "imp_tc_selftest": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
 }
 

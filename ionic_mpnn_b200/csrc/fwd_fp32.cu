@@ -37,6 +37,7 @@ struct TablePtrs {
   const float* W[IMP_MAX_TABLES];
   float* table[IMP_MAX_TABLES];
   float* table_il[IMP_MAX_TABLES];
+  float* table_ilT[IMP_MAX_TABLES];  // lane-interleaved layout of the TRANSPOSED matrices (backward: dh = T^T g)
 };
 
 constexpr int K2_COLS = 64;
@@ -86,6 +87,8 @@ __global__ void __launch_bounds__(256) bond_table_kernel(const float* __restrict
           if (ptrs.table[t]) ptrs.table[t][(int64_t)v * dd + j] = acc[i];
           if (ptrs.table_il[t])  // [v][m/4][l][m%4]
             ptrs.table_il[t][(((int64_t)v * (d / 4) + m / 4) * d + l) * 4 + (m & 3)] = acc[i];
+          if (ptrs.table_ilT[t])  // [v][l/4][m][l%4]
+            ptrs.table_ilT[t][(((int64_t)v * (d / 4) + l / 4) * d + m) * 4 + (l & 3)] = acc[i];
         }
       }
     }
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(256) message_agg_kernel(const int* __restrict_
                                                            const int* __restrict__ edge_bm, const float* __restrict__ h,
                                                            const float* __restrict__ tab_cat,
                                                            const float* __restrict__ tab_an, int n_atoms, int n_cat,
-                                                           float* __restrict__ agg) {
+                                                           float* __restrict__ agg, int accumulate) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int v = (int)(t / D), l = (int)(t % D);
   if (v >= n_atoms) return;
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(256) message_agg_kernel(const int* __restrict_
     const float4* hrow = reinterpret_cast<const float4*>(h + (int64_t)src * D);
     acc = fmaf((float)(bm >> 16), bond_matvec_row<D>(trow, hrow), acc);
   }
-  agg[(int64_t)v * D + l] = acc;
+  agg[(int64_t)v * D + l] = accumulate ? agg[(int64_t)v * D + l] + acc : acc;
 }
 
 // K3 alone: messages bucket by bucket, written at the entry's CSR position.  Uses the row-major table.
@@ -469,9 +472,10 @@ extern "C" int imp_embed_atoms(const float* d_atom_emb, int32_t atom_vocab, cons
   return 0;
 }
 
-extern "C" int imp_bond_table(const float* d_bond_emb, int32_t bond_vocab, int32_t bond_dim, int32_t d, int32_t n_tables,
-                              const float* const* h_W, float* const* h_table, float* const* h_table_il, void* stream) {
-  IMP_REQUIRE(d_bond_emb && h_W && (h_table || h_table_il), IMP_ERR_ARG, "imp_bond_table: null pointer");
+static int bond_table_any(const float* d_bond_emb, int32_t bond_vocab, int32_t bond_dim, int32_t d, int32_t n_tables,
+                          const float* const* h_W, float* const* h_table, float* const* h_table_il, float* const* h_table_ilT,
+                          void* stream) {
+  IMP_REQUIRE(d_bond_emb && h_W && (h_table || h_table_il || h_table_ilT), IMP_ERR_ARG, "imp_bond_table: null pointer");
   IMP_REQUIRE(n_tables > 0 && n_tables <= IMP_MAX_TABLES, IMP_ERR_ARG, "imp_bond_table: n_tables %d not in 1..%d",
               n_tables, IMP_MAX_TABLES);
   IMP_REQUIRE(bond_vocab > 0 && bond_dim > 0, IMP_ERR_ARG, "imp_bond_table: bad sizes");
@@ -481,12 +485,23 @@ extern "C" int imp_bond_table(const float* d_bond_emb, int32_t bond_vocab, int32
     p.W[i] = i < n_tables ? h_W[i] : nullptr;
     p.table[i] = (i < n_tables && h_table) ? h_table[i] : nullptr;
     p.table_il[i] = (i < n_tables && h_table_il) ? h_table_il[i] : nullptr;
+    p.table_ilT[i] = (i < n_tables && h_table_ilT) ? h_table_ilT[i] : nullptr;
     IMP_REQUIRE(i >= n_tables || p.W[i], IMP_ERR_ARG, "imp_bond_table: W[%d] is null", i);
   }
   dim3 grid((unsigned)ceil_div((int64_t)d * d, K2_COLS), (unsigned)n_tables);
   bond_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_bond_emb, bond_vocab, bond_dim, d, p);
   IMP_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int imp_bond_table(const float* d_bond_emb, int32_t bond_vocab, int32_t bond_dim, int32_t d, int32_t n_tables,
+                              const float* const* h_W, float* const* h_table, float* const* h_table_il, void* stream) {
+  return bond_table_any(d_bond_emb, bond_vocab, bond_dim, d, n_tables, h_W, h_table, h_table_il, nullptr, stream);
+}
+
+extern "C" int imp_bond_table_train(const float* d_bond_emb, int32_t bond_vocab, int32_t bond_dim, int32_t d, int32_t n_tables,
+                                    const float* const* h_W, float* const* h_table_il, float* const* h_table_ilT, void* stream) {
+  return bond_table_any(d_bond_emb, bond_vocab, bond_dim, d, n_tables, h_W, nullptr, h_table_il, h_table_ilT, stream);
 }
 
 static int check_graph(const imp_graph_t* g, const char* who) {
@@ -506,8 +521,21 @@ static int check_graph(const imp_graph_t* g, const char* who) {
     default: break;                        \
   }
 
+static int message_agg_any(const imp_graph_t* g, const float* d_h, int32_t d, const float* d_table_il_cat,
+                           const float* d_table_il_an, float* d_agg, int accumulate, void* stream);
+
 extern "C" int imp_message_agg(const imp_graph_t* g, const float* d_h, int32_t d, const float* d_table_il_cat,
                                const float* d_table_il_an, float* d_agg, void* stream) {
+  return message_agg_any(g, d_h, d, d_table_il_cat, d_table_il_an, d_agg, 0, stream);
+}
+
+extern "C" int imp_message_agg_bwd(const imp_graph_t* g, const float* d_dagg, int32_t d, const float* d_table_ilT_cat,
+                                   const float* d_table_ilT_an, float* d_dh, void* stream) {
+  return message_agg_any(g, d_dagg, d, d_table_ilT_cat, d_table_ilT_an, d_dh, 1, stream);
+}
+
+static int message_agg_any(const imp_graph_t* g, const float* d_h, int32_t d, const float* d_table_il_cat,
+                           const float* d_table_il_an, float* d_agg, int accumulate, void* stream) {
   if (int rc = check_graph(g, "imp_message_agg")) return rc;
   IMP_REQUIRE(dim_ok(d), IMP_ERR_DIM, "imp_message_agg: atom_dim %d not in {8,16,32,64} (fp32 path)", d);
   if (g->n_atoms == 0) return 0;
@@ -517,7 +545,7 @@ extern "C" int imp_message_agg(const imp_graph_t* g, const float* d_h, int32_t d
   const unsigned blocks = (unsigned)ceil_div(threads, 256);
   IMP_DISPATCH_D(d, (message_agg_kernel<D><<<blocks, 256, 0, (cudaStream_t)stream>>>(
                         g->row_ptr, g->col_src, g->edge_bm, d_h, d_table_il_cat, d_table_il_an, g->n_atoms,
-                        g->n_cat_atoms, d_agg)));
+                        g->n_cat_atoms, d_agg, accumulate)));
   IMP_LAUNCH_CHECK();
   return 0;
 }

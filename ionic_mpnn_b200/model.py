@@ -18,6 +18,7 @@ import numpy as np
 
 from . import _lib
 from .graph import PackedGraphBatch, pack_padded, pack_records
+from .train import TrainMixin
 
 TOWERS = ("cat", "an")
 
@@ -77,7 +78,7 @@ def keras_default_init(spec, seed=0):
     return out
 
 
-class MPNNModel:
+class MPNNModel(TrainMixin):
     """Object returned by ``build_model``: ``predict(x)`` like the Keras model, on the B200 kernels."""
 
     LN_EPS = 1e-3  # Keras LayerNormalization default (models/layers.py:139)
@@ -102,6 +103,7 @@ class MPNNModel:
         self.spec = dict(spec)
         self.device = torch.device(device)
         self.params = {}
+        self.flat = None
         self.set_weights(keras_default_init(spec, seed))
         self._ws = {}
         self._tables_valid = False
@@ -111,13 +113,22 @@ class MPNNModel:
         import torch
 
         shapes = param_shapes(self.spec)
+        if getattr(self, "flat", None) is None:
+            # one flat fp32 buffer (the gradient bucket mirrors it); every variable is a view, 16-byte aligned
+            self.var_names, self.var_off, off = list(shapes), {}, 0
+            for k, shp in shapes.items():
+                self.var_off[k] = off
+                off += (int(np.prod(shp)) + 3) // 4 * 4
+            self.flat = torch.zeros(off, dtype=torch.float32, device=self.device)
+            for k, shp in shapes.items():
+                self.params[k] = self.flat[self.var_off[k]: self.var_off[k] + int(np.prod(shp))].view(*shp)
         for k, shp in shapes.items():
             if k not in weights:
                 raise KeyError(f"missing weight {k}")
             w = np.ascontiguousarray(np.asarray(weights[k], dtype=np.float32))
             if tuple(w.shape) != tuple(shp):
                 raise ValueError(f"{k}: shape {w.shape} != {shp}")
-            self.params[k] = torch.from_numpy(w).to(self.device)
+            self.params[k].copy_(torch.from_numpy(w))
         self._tables_valid = False
 
     def get_weights(self):

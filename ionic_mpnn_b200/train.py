@@ -1,0 +1,218 @@
+"""Training step of the reference (train_viscosity.py:227-230,328-338; train_melting_point.py:210-214) on the B200
+kernels: loss = mean((y - yhat)^2) + l2 kernel regularisers, per-variable clip_by_norm(1.0), Adam(1e-3).
+
+Forward = the staged fp32 kernels with every h_i / agg_i kept; backward = csrc/bwd_fp32.cu (B1..B6); the flat gradient
+bucket is summed over ranks with ONE all-reduce (torch.distributed, NCCL) when a process group is initialised --
+SURVEY 8e; the only collective of the whole framework.  Mixed into MPNNModel (model.py)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+TOWERS = ("cat", "an")
+DT_CHUNK = 2048  # entries per CTA of the dTable partial kernel
+
+
+def l2_terms(spec):
+    """(variable, coefficient) of the kernel regularisers: train_viscosity.py:189; train_melting_point.py:172,196."""
+    if spec["kind"] == "viscosity":
+        return {"cat_fp.kernel": 1e-4, "an_fp.kernel": 1e-4}
+    return {"cat_fp.kernel": 1e-5, "an_fp.kernel": 1e-5, "head1.kernel": 1e-5}
+
+
+def _stream():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def prepare_training(batch, device):
+    """Per-batch index structures of the backward pass, built once on the host and uploaded:
+    entry_dst[e] (destination atom of CSR entry e) and the split of the (tower, bond) buckets into chunks."""
+    import torch
+
+    if getattr(batch, "train_dev", None) is not None:
+        return batch.train_dev
+    rp = batch.host["row_ptr"].astype(np.int64)
+    entry_dst = np.repeat(np.arange(batch.n_atoms, dtype=np.int32), np.diff(rp)).astype(np.int32)
+    bp = batch.host["bucket_ptr"].astype(np.int64)
+    nb = len(bp) - 1
+    sizes = np.diff(bp)
+    n_chunks_per = (sizes + DT_CHUNK - 1) // DT_CHUNK
+    bcp = np.zeros(nb + 1, np.int32)
+    bcp[1:] = np.cumsum(n_chunks_per)
+    total = int(bcp[-1])
+    which = np.repeat(np.arange(nb), n_chunks_per)
+    idx_in = np.arange(total) - bcp[which]
+    begin = (bp[which] + idx_in * DT_CHUNK).astype(np.int32)
+    end = np.minimum(bp[which + 1], begin.astype(np.int64) + DT_CHUNK).astype(np.int32)
+    dev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in
+           dict(entry_dst=entry_dst if len(entry_dst) else np.zeros(1, np.int32), chunk_begin=begin if total else np.zeros(1, np.int32),
+                chunk_end=end if total else np.zeros(1, np.int32), bucket_chunk_ptr=bcp).items()}
+    dev["n_chunks"] = total
+    batch.train_dev = dev
+    return dev
+
+
+class TrainMixin:
+    """loss_and_grads / train_step for MPNNModel."""
+
+    def _train_state(self):
+        import torch
+
+        st = getattr(self, "_train", None)
+        if st is not None:
+            return st
+        s = self.spec
+        if s["atom_dim"] != 32:
+            raise _lib.ImpError("the backward kernels are built for atom_dim 32")
+        n = self.flat.numel()
+        st = {"grad": torch.zeros(n, dtype=torch.float32, device=self.device),
+              "m": torch.zeros(n, dtype=torch.float32, device=self.device),
+              "v": torch.zeros(n, dtype=torch.float32, device=self.device), "step": 0}
+        shapes = {k: tuple(self.params[k].shape) for k in self.var_names}
+        st["g"] = {k: st["grad"][self.var_off[k]: self.var_off[k] + int(np.prod(shapes[k]))].view(*shapes[k])
+                   for k in self.var_names}
+        offs = [self.var_off[k] for k in self.var_names] + [n]
+        st["var_off"] = torch.tensor(offs, dtype=torch.int64, device=self.device)
+        l2 = l2_terms(s)
+        st["var_l2"] = torch.tensor([l2.get(k, 0.0) for k in self.var_names], dtype=torch.float32, device=self.device)
+        st["norms2"] = torch.zeros(len(self.var_names), dtype=torch.float32, device=self.device)
+        st["sse"] = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._train = st
+        return st
+
+    def loss_and_grads(self, batch, global_batch=None):
+        """Forward + backward on a packed batch with ``batch.target``.  Returns (sse, out): device tensors holding this
+        rank's sum of squared errors and predictions; gradients of mean-squared-error over ``global_batch`` pairs
+        (default: this batch) are left in the flat bucket ``self._train['grad']`` (WITHOUT the l2 terms, which
+        imp_clip_adam adds after the all-reduce so that they are counted once)."""
+        import torch
+
+        s = self.spec
+        d, S, K, Vb = s["atom_dim"], s["num_steps"], s["bond_dim"], s["bond_vocab_size"]
+        fp, mix = s["fp_size"], s["mixing_size"]
+        visc = s["kind"] == "viscosity"
+        fp2 = 0 if visc else fp
+        st = self._train_state()
+        if batch.dev is None:
+            batch.to(self.device)
+        if batch.dev_y is None:
+            raise ValueError("training needs batch.target")
+        tr = prepare_training(batch, self.device)
+        g = batch.c_struct()
+        N, P = batch.n_atoms, batch.n_pairs
+        sm = _stream()
+        G = st["g"]
+        lib = _lib.load()
+        # ---- tables (lane-interleaved + transposed) for this weight set
+        n = 2 * S
+        per = Vb * d * d
+        til, tilT = self._buf("tr_table_il", n * per), self._buf("tr_table_ilT", n * per)
+        W = (C.c_void_p * n)(*[self.params[f"{t}_bmm_{i}.bond_transform"].data_ptr() for t in TOWERS for i in range(S)])
+        T1 = (C.c_void_p * n)(*[til.data_ptr() + 4 * per * j for j in range(n)])
+        T2 = (C.c_void_p * n)(*[tilT.data_ptr() + 4 * per * j for j in range(n)])
+        _lib.call("imp_bond_table_train", self._ptr("bond_emb"), Vb, K, d, n, W, T1, T2, sm)
+        # ---- forward, everything kept
+        h = [self._buf(f"tr_h{i}", N * d) for i in range(S + 1)]
+        agg = [self._buf(f"tr_agg{i}", N * d) for i in range(S)]
+        _lib.call("imp_embed_atoms", self._ptr("atom_emb"), s["atom_vocab_size"], batch.dev["atom_id"].data_ptr(), N, d,
+                  h[0].data_ptr(), sm)
+        for i in range(S):
+            _lib.call("imp_message_agg", C.byref(g), h[i].data_ptr(), d, til.data_ptr() + 4 * per * i,
+                      til.data_ptr() + 4 * per * (S + i), agg[i].data_ptr(), sm)
+            wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
+            _lib.call("imp_gated_update", h[i].data_ptr(), agg[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc), C.byref(wa),
+                      C.c_float(self.LN_EPS), h[i + 1].data_ptr(), sm)
+        pooled, dpooled = self._buf("tr_pooled", 2 * P * d), self._buf("tr_dpooled", 2 * P * d)
+        _lib.call("imp_global_sum_pool", batch.dev["mol_ptr"].data_ptr(), batch.dev["atom_id"].data_ptr(), 2 * P,
+                  h[S].data_ptr(), d, pooled.data_ptr(), sm)
+        # ---- loss + readout backward
+        out = torch.empty(P, dtype=torch.float32, device=self.device)
+        rc, ra = self._readout_struct("cat"), self._readout_struct("an")
+        nh = fp2 if fp2 else 3
+        n_ro = 2 * (d * fp + fp + fp * mix + mix) + mix * nh + nh + ((fp2 + 1) if fp2 else 0)
+        ro = self._buf("tr_ro_grads", n_ro)
+        ws_ro = self._buf("tr_ws_ro", lib.imp_readout_bwd_workspace_floats(d, fp, mix, fp2))
+        scale = 2.0 / float(global_batch if global_batch else P)
+        if visc:
+            if batch.dev_T is None:
+                raise ValueError("viscosity model needs batch.temperature")
+            W1, b1, W2, b2, Tp = self._ptr("head.kernel"), self._ptr("head.bias"), None, None, batch.dev_T.data_ptr()
+        else:
+            W1, b1, W2, b2, Tp = (self._ptr("head1.kernel"), self._ptr("head1.bias"), self._ptr("head2.kernel"),
+                                  self._ptr("head2.bias"), None)
+        _lib.call("imp_readout_bwd", pooled.data_ptr(), P, d, fp, mix, fp2, C.byref(rc), C.byref(ra), W1, b1, W2, b2, Tp,
+                  batch.dev_y.data_ptr(), C.c_float(scale), dpooled.data_ptr(), out.data_ptr(), ro.data_ptr(),
+                  st["sse"].data_ptr(), ws_ro.data_ptr(), sm)
+        o = 0
+        for t in TOWERS:
+            for name, cnt in ((f"{t}_fp.kernel", d * fp), (f"{t}_fp.bias", fp), (f"{t}_mix.kernel", fp * mix),
+                              (f"{t}_mix.bias", mix)):
+                G[name].view(-1).copy_(ro[o:o + cnt])
+                o += cnt
+        heads = (("head.kernel", mix * 3), ("head.bias", 3)) if visc else (
+            ("head1.kernel", mix * fp2), ("head1.bias", fp2), ("head2.kernel", fp2), ("head2.bias", 1))
+        for name, cnt in heads:
+            G[name].view(-1).copy_(ro[o:o + cnt])
+            o += cnt
+        # ---- back through the pooling and the S steps
+        ga, gb = self._buf("tr_ga", N * d), self._buf("tr_gb", N * d)
+        dagg = self._buf("tr_dagg", N * d)
+        _lib.call("imp_pool_bwd", batch.dev["mol_ptr"].data_ptr(), batch.dev["atom_id"].data_ptr(), 2 * P, dpooled.data_ptr(), d,
+                  ga.data_ptr(), sm)
+        ws_gru = self._buf("tr_ws_gru", lib.imp_gated_update_bwd_workspace_floats(d))
+        dtable = self._buf("tr_dtable", 2 * per)
+        ws_dt = self._buf("tr_ws_dt", max(1, tr["n_chunks"]) * d * d)
+        G["bond_emb"].zero_()
+        cur, nxt = ga, gb
+        for i in reversed(range(S)):
+            wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
+            gc = G[f"cat_gu_{i}.dense_z.kernel"].data_ptr()  # the layer's 8 variables are contiguous from here
+            gn = G[f"an_gu_{i}.dense_z.kernel"].data_ptr()
+            _lib.call("imp_gated_update_bwd", h[i].data_ptr(), agg[i].data_ptr(), cur.data_ptr(), N, batch.n_cat_atoms, d,
+                      C.byref(wc), C.byref(wa), C.c_float(self.LN_EPS), nxt.data_ptr(), dagg.data_ptr(), gc, gn,
+                      ws_gru.data_ptr(), sm)
+            _lib.call("imp_message_agg_bwd", C.byref(g), dagg.data_ptr(), d, tilT.data_ptr() + 4 * per * i,
+                      tilT.data_ptr() + 4 * per * (S + i), nxt.data_ptr(), sm)
+            _lib.call("imp_bond_transform_bwd", C.byref(g), tr["entry_dst"].data_ptr(), tr["chunk_begin"].data_ptr(),
+                      tr["chunk_end"].data_ptr(), tr["n_chunks"], tr["bucket_chunk_ptr"].data_ptr(), dagg.data_ptr(),
+                      h[i].data_ptr(), d, K, self._ptr("bond_emb"), self._ptr(f"cat_bmm_{i}.bond_transform"),
+                      self._ptr(f"an_bmm_{i}.bond_transform"), G[f"cat_bmm_{i}.bond_transform"].data_ptr(),
+                      G[f"an_bmm_{i}.bond_transform"].data_ptr(), G["bond_emb"].data_ptr(), dtable.data_ptr(), ws_dt.data_ptr(), sm)
+            cur, nxt = nxt, cur
+        ws_e = self._buf("tr_ws_emb", lib.imp_embed_bwd_workspace_floats(s["atom_vocab_size"], d))
+        _lib.call("imp_embed_bwd", batch.dev["atom_id"].data_ptr(), cur.data_ptr(), N, s["atom_vocab_size"], d,
+                  G["atom_emb"].data_ptr(), ws_e.data_ptr(), sm)
+        return st["sse"], out
+
+    def gradients(self):
+        """Host copy of the gradient bucket as {variable: array} (after loss_and_grads)."""
+        return {k: v.detach().cpu().numpy().copy() for k, v in self._train_state()["g"].items()}
+
+    def train_step(self, batch, lr=1e-3, clipnorm=1.0, beta1=0.9, beta2=0.999, eps=1e-7, global_batch=None, group=None):
+        """One optimiser step.  With an initialised process group the gradient bucket (and the squared-error sum) is
+        all-reduced once; ``global_batch`` defaults to world_size * local pairs.  Returns the loss (mse + l2) as a
+        device scalar tensor -- no host synchronisation."""
+        import torch
+        import torch.distributed as dist
+
+        st = self._train_state()
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        gbatch = global_batch or batch.n_pairs * world
+        sse, _ = self.loss_and_grads(batch, global_batch=gbatch)
+        if world > 1:
+            dist.all_reduce(st["grad"], op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(sse, op=dist.ReduceOp.SUM, group=group)
+        reg = sum(c * (self.params[k] ** 2).sum() for k, c in l2_terms(self.spec).items())
+        loss = sse[0] / gbatch + reg
+        st["step"] += 1
+        _lib.call("imp_clip_adam", self.flat.data_ptr(), st["grad"].data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(),
+                  st["var_off"].data_ptr(), st["var_l2"].data_ptr(), len(self.var_names), st["norms2"].data_ptr(),
+                  C.c_float(clipnorm if clipnorm else 0.0), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
+                  st["step"], _stream())
+        self._tables_valid = False
+        return loss

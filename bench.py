@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="visc_sweep", choices=["visc_sweep", "mp64k"])
+    ap.add_argument("--workload", default="visc_sweep", choices=["visc_sweep", "mp64k", "visc_train"],
+                    help="visc_sweep = BASELINE configs[2] (headline); mp64k = configs[1]; visc_train = configs[3] "
+                         "(forward + backward + all-reduce + Adam, 65,536 pairs per GPU)")
     ap.add_argument("--pairs-per-gpu", type=int, default=None)
     ap.add_argument("--precision", default="fp16", choices=["fp32", "bf16", "bf16_precise", "fp16", "fp16_precise"],
                     help="fp16 / bf16 = tcgen05 tensor-core path (16-bit operands, fp32 accumulate; the 2e-2 path, default); "
@@ -52,6 +54,7 @@ def parse():
     ap.add_argument("--cpu-sample-pairs", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sync-every-step", action="store_true", help="visc_train: read the loss back after every step")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="host-resident chunks the e2e leg streams per step")
     return ap.parse_args()
 
@@ -62,6 +65,11 @@ def workload_config(args):
         kind = "viscosity"
         name = ("BASELINE configs[2]: viscosity MPNN inference sweep (atom_dim 32, bond_dim 8, 4 steps, vocab 123/71, "
                 "10-40 atoms/ion), weak scaling")
+    elif args.workload == "visc_train":
+        P = args.pairs_per_gpu or 65_536
+        kind = "viscosity"
+        name = ("BASELINE configs[3]: viscosity MPNN training step (forward + backward, NCCL gradient all-reduce, "
+                "per-variable clipnorm + Adam), 65,536 pairs per GPU")
     else:
         P = args.pairs_per_gpu or 65_536
         kind = "melting_point"
@@ -192,6 +200,102 @@ def stage_bytes(batch, d, S, s=4):
         "gated_update_tc": 3 * N * d * s,
         "pool_head": N * d * s + 4 * N + 8 * P + 8 * P,   # h, atom_id, mol_ptr (2 towers), T + out
     }
+
+
+def run_train(args):
+    """configs[3]: one step = loss_and_grads + one flat all-reduce + clip/Adam on a resident batch (weak scaling)."""
+    import torch
+    import torch.distributed as dist
+
+    from ionic_mpnn_b200 import graph
+    from ionic_mpnn_b200.model import MPNNModel, make_spec
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P, kind, name = workload_config(args)
+    spec = make_spec(kind)
+    model = MPNNModel(spec, device=f"cuda:{local}", seed=0, precision="fp32")
+    batch, _, _ = graph.synth_batch(P, seed=2003 + rank, skewed=args.skewed)
+    batch.target = __import__("numpy").random.default_rng(7 + rank).normal(2.0, 1.0, size=P).astype("float32")
+    batch.to(f"cuda:{local}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    losses = []
+    for _ in range(args.warmup):
+        losses.append(model.train_step(batch))
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()  # the step contains a collective: every rank must enter the timed region together
+    t0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        losses.append(model.train_step(batch))
+        if args.sync_every_step:
+            losses[-1].item()  # what a training loop that logs its loss does
+    ev1.record()
+    t_enq = time.time() - t0
+    torch.cuda.synchronize()
+    t1 = time.time()
+    barrier()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    # per-kernel share: one more instrumented step.  EVERY rank runs it (the step contains the all-reduce);
+    # rank 0 reports its own events.
+    per_kernel = {}
+    from ionic_mpnn_b200 import _lib
+    import ionic_mpnn_b200.train as tt
+    real_call = _lib.call
+    events = []
+
+    def timed_call(n, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        real_call(n, *a)
+        e1.record()
+        events.append((n, e0, e1))
+
+    tt._lib.call = timed_call
+    try:
+        model.train_step(batch)
+    finally:
+        tt._lib.call = real_call
+    torch.cuda.synchronize()
+    for n, e0, e1 in events:
+        per_kernel[n.replace("imp_", "")] = per_kernel.get(n.replace("imp_", ""), 0.0) + e0.elapsed_time(e1)
+    barrier()
+    if rank == 0:
+        lv = [float(l.item()) for l in losses]
+        tot = sum(per_kernel.values()) or 1.0
+        line = {"metric": "train_ion_pair_graphs_per_s", "value": P * world * args.steps / (ms_total * 1e-3), "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": name, "pairs_per_gpu": P, "global_batch": P * world, "atoms_per_gpu": batch.n_atoms,
+                           "params": model.count_params(), "collective": "one NCCL all-reduce of the flat gradient bucket "
+                           f"({model.flat.numel()} fp32) per step" if world > 1 else "none (1 GPU)",
+                           "l2_policy": "inputs larger than L2 (%.1f GB of saved activations per GPU)" % (
+                               9 * batch.n_atoms * 32 * 4 / 1e9)},
+                "gpu_launches": len(events) * args.steps, "clocks": clocks,
+                "host_enqueue_ms_per_step": round(t_enq * 1e3 / args.steps, 2), "loss_first_last": [lv[0], lv[-1]], "loss_decreased": lv[-1] < lv[0],
+                "kernel_ms": {k: round(v, 3) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
+                "kernel_share": {k: round(v / tot, 3) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_b200(args):
@@ -378,6 +482,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "visc_train":
+        run_train(args)
     else:
         run_b200(args)
 

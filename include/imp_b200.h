@@ -155,6 +155,8 @@ int imp_gated_update(const float* d_h, const float* d_agg, int32_t n_atoms, int3
 #define IMP_TC_PRECISE_EPILOGUE 2
 #define IMP_TC_MP8 4
 #define IMP_TC_F32_ZBUILD 8
+#define IMP_TC_TWO_THREADS_PER_ROW 16
+#define IMP_TC_THREE_CONTEXTS 32
 int64_t imp_gru_pack_bytes(int32_t d);
 int imp_gru_pack_bf16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
 int imp_gru_pack_f16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
@@ -200,6 +202,9 @@ int imp_pool_head_mp(const imp_graph_t* g, const float* d_h, int32_t d, int32_t 
  *                      IMP_TC_F32_ZBUILD: with IMP_TC_FP16, accumulate the Z rows in fp32 (first-generation kernel)
  *                      instead of packed half2 (default; 2 products per lane-instruction, rows sorted by degree).
  *                      IMP_TC_MP8: smaller register tile in the fp32 Z build (tuning switch, same results).
+ *                      IMP_TC_TWO_THREADS_PER_ROW: second-generation half kernel (2 contexts x 256 threads per SM) instead
+ *                      of the default third generation (4 contexts x 128 threads); IMP_TC_THREE_CONTEXTS: 3 contexts.
+ *                      Pack and forward must be called with the same flags (the Wc block layout differs).
  *   max_mol_atoms      largest molecule of the batch (the caller knows it from mol_ptr); > 128 is refused.
  *   d_pooled           [2 * n_pairs, d] molecule sums in mol_ptr order -> imp_readout_visc / imp_readout_mp.
  *   d_status           optional device int, set to 1 if the kernel met a molecule that does not fit a tile.

@@ -43,6 +43,8 @@ TC_FP16 = 1
 TC_PRECISE_EPILOGUE = 2
 TC_MP8 = 4
 TC_F32_ZBUILD = 8
+TC_TWO_THREADS_PER_ROW = 16
+TC_THREE_CONTEXTS = 32
 PACK_DOUBLE_EDGES = 1
 PACK_SHIFT_IDS = 2
 

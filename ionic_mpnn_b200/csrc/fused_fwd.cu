@@ -55,14 +55,23 @@ struct FusedPack {  // one (tower, step)
 };
 static_assert(FusedPack::BYTES % 128 == 0, "pack must keep 128-byte alignment of the next step");
 
-template <int FMT>
+// KHALF = false: Wc[n = l][kk = m*8 + k] = W[k][l][m] as one [32 x 256] K-major block (first-generation kernels).
+// KHALF = true : two [32 x 128] blocks, block hz holds k in [4 hz, 4 hz + 4): Wc_hz[l][m*4 + (k - 4 hz)] = W[k][l][m]
+//                (the four-context kernel builds and multiplies Z in two K halves).
+template <int FMT, bool KHALF>
 __global__ void fused_pack_kernel(const float* __restrict__ W /* [K, d, d] */, imp_gru_weights_t w,
                                   unsigned char* __restrict__ out) {
   constexpr int D = FZ_D, KK = FZ_D * FZ_K;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < D * KK) {  // Wc[n = l][kk = m*8 + k] = W[k][l][m]
+  if (i < D * KK) {
     const int l = i / KK, kk = i % KK, m = kk / FZ_K, k = kk % FZ_K;
-    *reinterpret_cast<uint16_t*>(out + tc::chunk_off(l, kk / 8, D) + (kk % 8) * 2) = tc::cvt16<FMT>(W[(k * D + l) * D + m]);
+    if (KHALF) {
+      const int hz = k / 4, kq = m * 4 + (k % 4);
+      *reinterpret_cast<uint16_t*>(out + hz * (FusedPack::WC_BYTES / 2) + tc::chunk_off(l, kq / 8, D) + (kq % 8) * 2) =
+          tc::cvt16<FMT>(W[(k * D + l) * D + m]);
+    } else {
+      *reinterpret_cast<uint16_t*>(out + tc::chunk_off(l, kk / 8, D) + (kk % 8) * 2) = tc::cvt16<FMT>(W[(k * D + l) * D + m]);
+    }
   }
   if (i < 2 * D * 2 * D) {  // Bzr[n][k] = (n < D ? Wz[k][n] : Wr[k][n - D])
     const int n = i / (2 * D), k = i % (2 * D);
@@ -773,6 +782,339 @@ __global__ void __launch_bounds__(2 * F2_CTX_THREADS, 1) mpnn_fused_h2_kernel(co
   if (warp == 0) tc::tmem_dealloc<512>(ctl.tmem_base);
 }
 
+// =====================================================================================================================
+// Third generation ("h2x", the default for half operands): NCTX independent 128-thread contexts per CTA, one thread per
+// atom row, 128 TMEM columns per context.  The second generation is bounded by latency: a context is a serial chain of
+// barriers and tcgen05 round trips, and TMEM (2 x 256 columns) allowed only two of them per SM.  Here
+//   * Z is built and multiplied in two K halves (bond-embedding components k < 4, then k >= 4) through the SAME 64
+//     columns -- 64 half2 accumulators per thread -- and GEMM1 of the first half runs under the build of the second;
+//   * accumulators are recycled: [64,96) agg, then [64,128) z|r, then [64,96) candidate; operands h / agg / r*h reuse
+//     the Z columns; the candidate GEMM is one K = 64 chain [agg | r*h] . Wh issued after the gate epilogue;
+// so a context needs 128 columns and four of them fit (512 threads, <= 128 registers each; three at <= 168 registers).
+// Row ownership, degree sort, packed-HFMA2 Z build, register-resident fp32 state, warp-uniform MMA issue: as above.
+constexpr int F3_CTX_THREADS = 128;
+
+struct alignas(16) FusedWgSmem3 {
+  uint32_t hb[FZ_ROWS * FZ_HS];  // half2 (h_m, h_m) per column; after the last step: fp32 h rows for the pooling
+  int molp[FZ_GROUP + 4];
+  int se0[FZ_ROWS], se1[FZ_ROWS], said[FZ_ROWS];
+  int cnt[4][8];
+  unsigned char rowof[FZ_ROWS];
+  unsigned char amask[FZ_ROWS];
+  uint64_t bar[4];
+};
+
+__host__ __device__ inline int fused3_smem_bytes(int steps, int bond_vocab, int nctx) {
+  const int ctab = (bond_vocab * 16 + 127) / 128 * 128;
+  return steps * FusedPack::BYTES + ctab + nctx * (int)sizeof(FusedWgSmem3) + (int)sizeof(FusedCtl);
+}
+
+template <bool PRECISE, int NCTX>
+__global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kernel(const FusedArgs a) {
+  constexpr int D = FZ_D;
+  constexpr int FMT = tc::FMT_F16;
+  constexpr int NT = NCTX * F3_CTX_THREADS;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ctx = tid >> 7, t = tid & 127, wq = warp & 3;
+  const int wbytes = a.steps * FusedPack::BYTES;
+  const int ctab_bytes = (a.bond_vocab * 16 + 127) / 128 * 128;
+  uint4* s_ctab = reinterpret_cast<uint4*>(smem + wbytes);
+  FusedWgSmem3& ws = reinterpret_cast<FusedWgSmem3*>(smem + wbytes + ctab_bytes)[ctx];
+  FusedCtl& ctl = *reinterpret_cast<FusedCtl*>(smem + wbytes + ctab_bytes + NCTX * sizeof(FusedWgSmem3));
+
+  const int tower = blockIdx.x >= a.n_cta_cat;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.packed + (size_t)tower * wbytes);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = tid; i < wbytes / 16; i += NT) dst[i] = __ldg(src + i);
+    for (int i = tid; i < a.bond_vocab; i += NT) {
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(a.bond_emb) + 2 * i);
+      const float4 c1 = __ldg(reinterpret_cast<const float4*>(a.bond_emb) + 2 * i + 1);
+      s_ctab[i] = make_uint4(tc::pack_f16x2(c0.x, c0.y), tc::pack_f16x2(c0.z, c0.w), tc::pack_f16x2(c1.x, c1.y),
+                             tc::pack_f16x2(c1.z, c1.w));
+    }
+  }
+  if (warp == 0) tc::tmem_alloc<512>(&ctl.tmem_base);
+  if (t == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&ws.bar[i], 1);
+    tc::mbar_fence_init();
+  }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+
+  const uint32_t sw0 = tc::smem_u32(smem);
+  const uint32_t tbase = ctl.tmem_base + (uint32_t)(ctx * 128);
+  const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+  const uint32_t tZ = tbase, tAh = tbase, tAagg = tbase + 16, tArh = tbase + 32;
+  const uint32_t tCagg = tbase + 64, tCzr = tbase + 64, tCht = tbase + 64;
+  const uint32_t idesc32 = tc::make_idesc(FMT, FZ_ROWS, D), idesc64 = tc::make_idesc(FMT, FZ_ROWS, 2 * D);
+  const uint64_t dWc = tc::make_smem_desc(sw0, D * 16, 128);
+  const uint64_t dBzr = tc::make_smem_desc(sw0 + FusedPack::OFF_BZR, 2 * D * 16, 128);
+  const uint64_t dBh = tc::make_smem_desc(sw0 + FusedPack::OFF_BH, D * 16, 128);
+  const bool mma_warp = (t >> 5) == 0;
+  const int bar_id = 1 + ctx;
+  const bool descending = ctx & 1;
+
+  const int P = a.n_pairs;
+  const int n_groups = (P + FZ_GROUP - 1) / FZ_GROUP;
+  const int n_cta_tower = tower ? (int)gridDim.x - a.n_cta_cat : a.n_cta_cat;
+  const int cta_in_tower = tower ? (int)blockIdx.x - a.n_cta_cat : (int)blockIdx.x;
+  const float4* emb4 = reinterpret_cast<const float4*>(a.atom_emb);
+  uint32_t ph = 0;
+
+  for (int g = cta_in_tower * NCTX + ctx; g < n_groups; g += n_cta_tower * NCTX) {
+    const int m0 = g * FZ_GROUP, nm = min(FZ_GROUP, P - m0);
+    const int base_mol = tower * P + m0;
+    tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+    if (t <= nm) ws.molp[t] = __ldg(a.mol_ptr + base_mol + t);
+    tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+    int ms = 0;
+    while (ms < nm) {
+      const int a0 = ws.molp[ms];
+      int me = ms + 1;
+      while (me < nm && ws.molp[me + 1] - a0 <= FZ_ROWS) ++me;
+      int rows = ws.molp[me] - a0;
+      if (rows > FZ_ROWS) {
+        if (t == 0 && a.status) *a.status = 1;
+        rows = FZ_ROWS;
+      }
+      // ---------------------------------------------------------------- natural row t: indices, in-degree key
+      int key, rank = 0;
+      {
+        const bool valid = t < rows;
+        int aid = 0, e0 = 0, e1 = 0;
+        if (valid) {
+          aid = __ldg(a.atom_id + a0 + t);
+          e0 = __ldg(a.row_ptr + a0 + t);
+          e1 = __ldg(a.row_ptr + a0 + t + 1);
+        }
+        ws.se0[t] = e0, ws.se1[t] = e1, ws.said[t] = aid;
+        ws.amask[t] = (valid && aid > 0) ? 1 : 0;  // models/layers.py:163
+        key = min(e1 - e0, 7);
+        int mine = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const unsigned m = __ballot_sync(0xffffffffu, key == k);
+          if (lane == k) mine = __popc(m);
+          if (key == k) rank = __popc(m & ((1u << lane) - 1u));
+        }
+        if (lane < 8) ws.cnt[wq][lane] = mine;
+      }
+      tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+      {
+        int off = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c0 = ws.cnt[0][k], c1 = ws.cnt[1][k], c2 = ws.cnt[2][k], c3 = ws.cnt[3][k];
+          if (k < key) off += c0 + c1 + c2 + c3;
+          if (k == key) off += (wq > 0 ? c0 : 0) + (wq > 1 ? c1 : 0) + (wq > 2 ? c2 : 0);
+        }
+        const int slot = off + rank;
+        ws.rowof[descending ? FZ_ROWS - 1 - slot : slot] = (unsigned char)t;
+      }
+      tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+      // ---------------------------------------------------------------- thread t owns row r
+      const int r = ws.rowof[t];
+      const int e0 = ws.se0[r], e1 = (a.debug & 1) ? e0 : ws.se1[r];
+      uint32_t* hbrow = &ws.hb[r * FZ_HS];
+      float h[D];
+      {  // Embedding(atom)
+        const bool valid = r < rows;
+        const int id = min(max(ws.said[r], 0), a.atom_vocab - 1);
+#pragma unroll
+        for (int c = 0; c < D / 4; ++c) {
+          const float4 x = valid ? __ldg(emb4 + id * (D / 4) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          h[4 * c] = x.x, h[4 * c + 1] = x.y, h[4 * c + 2] = x.z, h[4 * c + 3] = x.w;
+          reinterpret_cast<uint4*>(hbrow)[c] =
+              make_uint4(tc::pack_f16x2(x.x, x.x), tc::pack_f16x2(x.y, x.y), tc::pack_f16x2(x.z, x.z), tc::pack_f16x2(x.w, x.w));
+        }
+      }
+      if (me < nm && lane < 8) {  // index lines of the next tile -> L2
+        const int an = ws.molp[me], en = ws.se1[rows - 1];
+        if (wq == 0) prefetch_l2(a.atom_id + min(an + lane * 32, a.n_atoms - 1));
+        if (wq == 1) prefetch_l2(a.row_ptr + min(an + lane * 32, a.n_atoms));
+        if (wq == 2) prefetch_l2(a.col_src + min(en + lane * 32, a.n_unique - 1));
+        if (wq == 3) prefetch_l2(a.edge_bm + min(en + lane * 32, a.n_unique - 1));
+      }
+      tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+
+      for (int s = 0; s < a.steps; ++s) {
+        const uint64_t dstep = (uint64_t)(s * (FusedPack::BYTES / 16));
+        const float* bias = reinterpret_cast<const float*>(smem + s * FusedPack::BYTES + FusedPack::OFF_BIAS);
+        // ------------------------------------------------------------ Z in two K halves -> TMEM -> GEMM1
+#pragma unroll 1
+        for (int hz = 0; hz < 2; ++hz) {
+          __half2 acc[D * 2];
+#pragma unroll
+          for (int i = 0; i < D * 2; ++i) acc[i] = __half2(__ushort_as_half(0), __ushort_as_half(0));
+#pragma unroll 1
+          for (int e = e0; e < e1; ++e) {
+            const int bm = __ldg(a.edge_bm + e);
+            int src = __ldg(a.col_src + e) - a0;
+            src = min(max(src, 0), FZ_ROWS - 1);
+            const __half2 mult = __float2half2_rn((float)(bm >> 16));
+            const int bond = min(bm & 0xffff, a.bond_vocab - 1);
+            const uint2 cu = reinterpret_cast<const uint2*>(s_ctab + bond)[hz];
+            const __half2 c0 = __hmul2(*reinterpret_cast<const __half2*>(&cu.x), mult);
+            const __half2 c1 = __hmul2(*reinterpret_cast<const __half2*>(&cu.y), mult);
+            const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[src * FZ_HS]);
+#pragma unroll
+            for (int q = 0; q < D / 4; ++q) {
+              const uint4 hv = hp[q];
+              const __half2 hm[4] = {*reinterpret_cast<const __half2*>(&hv.x), *reinterpret_cast<const __half2*>(&hv.y),
+                                     *reinterpret_cast<const __half2*>(&hv.z), *reinterpret_cast<const __half2*>(&hv.w)};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                acc[(4 * q + i) * 2] = __hfma2(hm[i], c0, acc[(4 * q + i) * 2]);
+                acc[(4 * q + i) * 2 + 1] = __hfma2(hm[i], c1, acc[(4 * q + i) * 2 + 1]);
+              }
+            }
+          }
+          if (hz == 1 && !(a.debug & 2)) {  // GEMM1a must have consumed the first half before its columns are rewritten
+            tc::mbar_wait(&ws.bar[3], ph);
+            tc::fence_after_thread_sync();
+          }
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            uint32_t rr[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) rr[i] = *reinterpret_cast<const uint32_t*>(&acc[ch * 32 + i]);
+            tc::tmem_st32(tZ + lane_off + (uint32_t)(ch * 32), rr);
+          }
+          tc::tmem_wait_st();
+          tc::fence_before_thread_sync();
+          tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+          if (mma_warp && !(a.debug & 2)) {
+            tc::fence_after_thread_sync();
+            if (tc::elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                tc::mma_f16_ts(tCagg, tZ + 8 * ks, dWc + dstep + (uint64_t)(hz * (FusedPack::WC_BYTES / 32) + ks * 64), idesc32,
+                               hz > 0 || ks > 0);
+              tc::mma_commit(hz == 0 ? &ws.bar[3] : &ws.bar[0]);
+            }
+            __syncwarp();
+          }
+        }
+        if (!(a.debug & 2)) tc::mbar_wait(&ws.bar[0], ph);
+        tc::fence_after_thread_sync();
+        {  // agg and h as 16-bit A operands
+          float v[32];
+          tc::tmem_ld32(tCagg + lane_off, v);
+          uint32_t rr[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rr[i] = tc::pack_f16x2(v[2 * i], v[2 * i + 1]);
+          tc::tmem_st16(tAagg + lane_off, rr);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rr[i] = tc::pack_f16x2(h[2 * i], h[2 * i + 1]);
+          tc::tmem_st16(tAh + lane_off, rr);
+        }
+        tc::tmem_wait_st();
+        tc::fence_before_thread_sync();
+        tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+        // ------------------------------------------------------------ GEMM2: [h | agg] . [Wz | Wr]
+        if (mma_warp && !(a.debug & 2)) {
+          tc::fence_after_thread_sync();
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) tc::mma_f16_ts(tCzr, tAh + 8 * ks, dBzr + dstep + (uint64_t)(ks * 128), idesc64, ks > 0);
+            tc::mma_commit(&ws.bar[1]);
+          }
+          __syncwarp();
+        }
+        if (!(a.debug & 2)) tc::mbar_wait(&ws.bar[1], ph);
+        tc::fence_after_thread_sync();
+        float z[D];
+        {
+          float v[32];
+          tc::tmem_ld32(tCzr + lane_off, v);
+#pragma unroll
+          for (int j = 0; j < D; ++j) z[j] = fz_sigmoid<PRECISE>(v[j] + bias[j]);
+          tc::tmem_ld32(tCzr + D + lane_off, v);
+          uint32_t rr[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float r0 = fz_sigmoid<PRECISE>(v[2 * i] + bias[D + 2 * i]) * h[2 * i];
+            const float r1 = fz_sigmoid<PRECISE>(v[2 * i + 1] + bias[D + 2 * i + 1]) * h[2 * i + 1];
+            rr[i] = tc::pack_f16x2(r0, r1);
+          }
+          tc::tmem_st16(tArh + lane_off, rr);
+        }
+        tc::tmem_wait_st();
+        tc::fence_before_thread_sync();
+        tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+        // ------------------------------------------------------------ GEMM3: [agg | r*h] . [Wh[d:2d] ; Wh[0:d]]
+        if (mma_warp && !(a.debug & 2)) {
+          tc::fence_after_thread_sync();
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              tc::mma_f16_ts(tCht, tAagg + 8 * ks, dBh + dstep + (uint64_t)((ks < 2 ? ks + 2 : ks - 2) * 64), idesc32, ks > 0);
+            tc::mma_commit(&ws.bar[2]);
+          }
+          __syncwarp();
+        }
+        if (!(a.debug & 2)) tc::mbar_wait(&ws.bar[2], ph);
+        tc::fence_after_thread_sync();
+        {  // candidate, blend, LayerNorm (biased variance, eps), residual  (models/layers.py:151-156)
+          float gq[32];
+          tc::tmem_ld32(tCht + lane_off, gq);
+          float mean = 0.f;
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            const float ht = fz_tanh<PRECISE>(gq[j] + bias[2 * D + j]);
+            gq[j] = fmaf(z[j], ht - h[j], h[j]);
+            mean += gq[j];
+          }
+          mean *= (1.0f / D);
+          float var = 0.f;
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            const float cdev = gq[j] - mean;
+            var = fmaf(cdev, cdev, var);
+          }
+          const float inv = PRECISE ? 1.0f / sqrtf(var * (1.0f / D) + a.eps) : rsqrtf(var * (1.0f / D) + a.eps);
+#pragma unroll
+          for (int j = 0; j < D; ++j) h[j] = fmaf((gq[j] - mean) * inv, bias[3 * D + j], bias[4 * D + j]) + h[j];
+          if (s + 1 < a.steps) {
+#pragma unroll
+            for (int c = 0; c < D / 4; ++c)
+              reinterpret_cast<uint4*>(hbrow)[c] = make_uint4(tc::pack_f16x2(h[4 * c], h[4 * c]), tc::pack_f16x2(h[4 * c + 1], h[4 * c + 1]),
+                                                              tc::pack_f16x2(h[4 * c + 2], h[4 * c + 2]), tc::pack_f16x2(h[4 * c + 3], h[4 * c + 3]));
+          } else {
+#pragma unroll
+            for (int c = 0; c < D / 4; ++c)
+              reinterpret_cast<float4*>(hbrow)[c] = make_float4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+          }
+        }
+        tc::fence_before_thread_sync();
+        tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+        ph ^= 1;
+      }
+      // ---------------------------------------------------------------- GlobalSumPool
+      {
+        const float* hfp = reinterpret_cast<const float*>(ws.hb);
+        for (int mi = ms + (t >> 5); mi < me; mi += 4) {
+          const int lo = ws.molp[mi] - a0, hi = min(ws.molp[mi + 1] - a0, FZ_ROWS);
+          float sacc = 0.f;
+          for (int rr = lo; rr < hi; ++rr)
+            if (ws.amask[rr]) sacc += hfp[rr * FZ_HS + lane];
+          a.pooled[(size_t)(base_mol + mi) * D + lane] = sacc;
+        }
+      }
+      tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+      ms = me;
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(ctl.tmem_base);
+}
+
 }  // namespace imp
 
 using namespace imp;
@@ -788,10 +1130,13 @@ extern "C" int imp_fused_pack(const float* d_bond_transform, const imp_gru_weigh
   IMP_REQUIRE(d == FZ_D && bond_dim == FZ_K, IMP_ERR_DIM, "imp_fused_pack: the fused path is built for atom_dim %d, bond_dim %d (got %d, %d)",
               FZ_D, FZ_K, d, bond_dim);
   const int n = FZ_D * FZ_D * FZ_K;
-  if (flags & IMP_TC_FP16)
-    fused_pack_kernel<tc::FMT_F16><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed);
+  const bool khalf = (flags & IMP_TC_FP16) && !(flags & (IMP_TC_F32_ZBUILD | IMP_TC_TWO_THREADS_PER_ROW));
+  if (khalf)
+    fused_pack_kernel<tc::FMT_F16, true><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed);
+  else if (flags & IMP_TC_FP16)
+    fused_pack_kernel<tc::FMT_F16, false><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed);
   else
-    fused_pack_kernel<tc::FMT_BF16><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed);
+    fused_pack_kernel<tc::FMT_BF16, false><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed);
   IMP_LAUNCH_CHECK();
   return 0;
 }
@@ -859,16 +1204,44 @@ extern "C" int imp_mpnn_forward_fused(const imp_graph_t* g, const float* d_atom_
   IMP_REQUIRE(smem <= 227 * 1024, IMP_ERR_DIM, "imp_mpnn_forward_fused: needs %zu B of shared memory", smem);
   const bool f16 = flags & IMP_TC_FP16, precise = flags & IMP_TC_PRECISE_EPILOGUE, mp8 = flags & IMP_TC_MP8;
   cudaStream_t st = (cudaStream_t)stream;
-  if (f16 && !(flags & IMP_TC_F32_ZBUILD)) {  // default for half operands: packed-half Z build, degree-sorted rows
-    const size_t smem2 = (size_t)fused2_smem_bytes(steps, g->bond_vocab);
-    IMP_REQUIRE(smem2 <= 227 * 1024, IMP_ERR_DIM, "imp_mpnn_forward_fused: needs %zu B of shared memory", smem2);
-    if (precise) {
-      IMP_CUDA(cudaFuncSetAttribute(mpnn_fused_h2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      mpnn_fused_h2_kernel<true><<<grid, 2 * F2_CTX_THREADS, smem2, st>>>(a);
-    } else {
-      IMP_CUDA(cudaFuncSetAttribute(mpnn_fused_h2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      mpnn_fused_h2_kernel<false><<<grid, 2 * F2_CTX_THREADS, smem2, st>>>(a);
+  if (f16 && !(flags & IMP_TC_F32_ZBUILD)) {
+    if (flags & IMP_TC_TWO_THREADS_PER_ROW) {  // second generation: 2 contexts x 256 threads
+      const size_t smem2 = (size_t)fused2_smem_bytes(steps, g->bond_vocab);
+      IMP_REQUIRE(smem2 <= 227 * 1024, IMP_ERR_DIM, "imp_mpnn_forward_fused: needs %zu B of shared memory", smem2);
+      // work units are distributed over 2 contexts per CTA
+      if (precise) {
+        IMP_CUDA(cudaFuncSetAttribute(mpnn_fused_h2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        mpnn_fused_h2_kernel<true><<<grid, 2 * F2_CTX_THREADS, smem2, st>>>(a);
+      } else {
+        IMP_CUDA(cudaFuncSetAttribute(mpnn_fused_h2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        mpnn_fused_h2_kernel<false><<<grid, 2 * F2_CTX_THREADS, smem2, st>>>(a);
+      }
+      IMP_LAUNCH_CHECK();
+      return 0;
     }
+    // default for half operands: third generation, 4 (or 3) contexts x 128 threads
+    const int nctx = (flags & IMP_TC_THREE_CONTEXTS) ? 3 : 4;
+    int nc = (int)((int64_t)sms * g->n_cat_atoms / (g->n_atoms > 0 ? g->n_atoms : 1));
+    nc = nc < 1 ? 1 : (nc > sms - 1 ? sms - 1 : nc);
+    int na = sms - nc;
+    const int want3 = (int)ceil_div(n_groups, nctx);
+    if (nc > want3) nc = want3;
+    if (na > want3) na = want3;
+    a.n_cta_cat = nc;
+    const int grid3 = nc + na;
+    const size_t smem3 = (size_t)fused3_smem_bytes(steps, g->bond_vocab, nctx);
+    IMP_REQUIRE(smem3 <= 227 * 1024, IMP_ERR_DIM, "imp_mpnn_forward_fused: needs %zu B of shared memory", smem3);
+#define IMP_LAUNCH_H2X(PREC, NC)                                                                                           \
+  do {                                                                                                                     \
+    IMP_CUDA(cudaFuncSetAttribute(mpnn_fused_h2x_kernel<PREC, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
+    mpnn_fused_h2x_kernel<PREC, NC><<<grid3, NC * F3_CTX_THREADS, smem3, st>>>(a);                                        \
+  } while (0)
+    if (nctx == 4) {
+      if (precise) IMP_LAUNCH_H2X(true, 4); else IMP_LAUNCH_H2X(false, 4);
+    } else {
+      if (precise) IMP_LAUNCH_H2X(true, 3); else IMP_LAUNCH_H2X(false, 3);
+    }
+#undef IMP_LAUNCH_H2X
     IMP_LAUNCH_CHECK();
     return 0;
   }

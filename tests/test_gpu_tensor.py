@@ -172,9 +172,10 @@ def test_fused_forward_vs_fp32_kernels(n_pairs, precision):
     assert err <= (BF16_RTOL if precision.startswith("fp16") else 1.5e-1), err
 
 
-@pytest.mark.parametrize("tc_flags", [8, 8 | 4])
-def test_fused_forward_fp32_zbuild_variants(tc_flags):
-    """First-generation kernel (fp32 Z accumulation; IMP_TC_F32_ZBUILD, optionally IMP_TC_MP8) stays covered."""
+@pytest.mark.parametrize("tc_flags", [8, 8 | 4, 16, 32])
+def test_fused_forward_kernel_generations(tc_flags):
+    """Earlier generations stay covered: fp32 Z accumulation (IMP_TC_F32_ZBUILD, optionally IMP_TC_MP8), two threads
+    per row (IMP_TC_TWO_THREADS_PER_ROW), and the three-context variant of the default kernel."""
     got, want = _fused_vs_staged(700, 4, "fp16", tc_flags=tc_flags)
     assert _rel(got, want) <= BF16_RTOL
 

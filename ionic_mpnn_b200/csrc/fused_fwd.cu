@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(2 * F2_CTX_THREADS, 1) mpnn_fused_h2_kernel(co
         }
       }
       if (me < nm && hf == 0 && lane < 8) {  // index lines of the next tile -> L2 (it follows this tile in all arrays)
-        const int an = ws.molp[me], en = ws.se1[rows - 1];
+        const int an = ws.molp[me], en = ws.se1[max(rows, 1) - 1];
         if (wq == 0) prefetch_l2(a.atom_id + min(an + lane * 32, a.n_atoms - 1));
         if (wq == 1) prefetch_l2(a.row_ptr + min(an + lane * 32, a.n_atoms));
         if (wq == 2) prefetch_l2(a.col_src + min(en + lane * 32, a.n_unique - 1));
@@ -793,12 +793,14 @@ __global__ void __launch_bounds__(2 * F2_CTX_THREADS, 1) mpnn_fused_h2_kernel(co
 // so a context needs 128 columns and four of them fit (512 threads, <= 128 registers each; three at <= 168 registers).
 // Row ownership, degree sort, packed-HFMA2 Z build, register-resident fp32 state, warp-uniform MMA issue: as above.
 constexpr int F3_CTX_THREADS = 128;
+constexpr int F3_ECAP = 768;  // decoded entries staged per tile (tiles with more entries read the global arrays)
 
 struct alignas(16) FusedWgSmem3 {
   uint32_t hb[FZ_ROWS * FZ_HS];  // half2 (h_m, h_m) per column; after the last step: fp32 h rows for the pooling
   int molp[FZ_GROUP + 4];
   int se0[FZ_ROWS], se1[FZ_ROWS], said[FZ_ROWS];
   int cnt[4][8];
+  uint32_t ent[F3_ECAP];  // decoded entries of the tile: src row | bond << 8 | mult (half bits) << 16
   unsigned char rowof[FZ_ROWS];
   unsigned char amask[FZ_ROWS];
   uint64_t bar[4];
@@ -917,6 +919,16 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
         ws.rowof[descending ? FZ_ROWS - 1 - slot : slot] = (unsigned char)t;
       }
       tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+      // ---------------------------------------------------------------- decoded entries of the tile -> shared memory
+      const int E0 = ws.se0[0], n_ent = ws.se1[max(rows, 1) - 1] - E0;
+      const bool staged = n_ent <= F3_ECAP && a.bond_vocab <= 256;
+      if (staged)
+        for (int i = t; i < n_ent; i += F3_CTX_THREADS) {
+          const int bm = __ldg(a.edge_bm + E0 + i);
+          const int src = min(max(__ldg(a.col_src + E0 + i) - a0, 0), FZ_ROWS - 1);
+          const int bond = min(bm & 0xffff, a.bond_vocab - 1);
+          ws.ent[i] = (uint32_t)src | ((uint32_t)bond << 8) | ((uint32_t)__half_as_ushort(__float2half_rn((float)(bm >> 16))) << 16);
+        }
       // ---------------------------------------------------------------- thread t owns row r
       const int r = ws.rowof[t];
       const int e0 = ws.se0[r], e1 = (a.debug & 1) ? e0 : ws.se1[r];
@@ -934,7 +946,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
         }
       }
       if (me < nm && lane < 8) {  // index lines of the next tile -> L2
-        const int an = ws.molp[me], en = ws.se1[rows - 1];
+        const int an = ws.molp[me], en = ws.se1[max(rows, 1) - 1];
         if (wq == 0) prefetch_l2(a.atom_id + min(an + lane * 32, a.n_atoms - 1));
         if (wq == 1) prefetch_l2(a.row_ptr + min(an + lane * 32, a.n_atoms));
         if (wq == 2) prefetch_l2(a.col_src + min(en + lane * 32, a.n_unique - 1));
@@ -951,26 +963,52 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
           __half2 acc[D * 2];
 #pragma unroll
           for (int i = 0; i < D * 2; ++i) acc[i] = __half2(__ushort_as_half(0), __ushort_as_half(0));
+          if (staged) {
+            uint32_t en = e0 < e1 ? ws.ent[e0 - E0] : 0u;
 #pragma unroll 1
-          for (int e = e0; e < e1; ++e) {
-            const int bm = __ldg(a.edge_bm + e);
-            int src = __ldg(a.col_src + e) - a0;
-            src = min(max(src, 0), FZ_ROWS - 1);
-            const __half2 mult = __float2half2_rn((float)(bm >> 16));
-            const int bond = min(bm & 0xffff, a.bond_vocab - 1);
-            const uint2 cu = reinterpret_cast<const uint2*>(s_ctab + bond)[hz];
-            const __half2 c0 = __hmul2(*reinterpret_cast<const __half2*>(&cu.x), mult);
-            const __half2 c1 = __hmul2(*reinterpret_cast<const __half2*>(&cu.y), mult);
-            const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[src * FZ_HS]);
+            for (int e = e0; e < e1; ++e) {
+              const uint32_t ec = en;
+              if (e + 1 < e1) en = ws.ent[e + 1 - E0];  // next entry's descriptor is in flight during this one's FMAs
+              const uint2 cu = reinterpret_cast<const uint2*>(s_ctab + ((ec >> 8) & 0xff))[hz];
+              const uint32_t mbits = (ec >> 16) | (ec & 0xffff0000u);
+              const __half2 mult = *reinterpret_cast<const __half2*>(&mbits);
+              const __half2 c0 = __hmul2(*reinterpret_cast<const __half2*>(&cu.x), mult);
+              const __half2 c1 = __hmul2(*reinterpret_cast<const __half2*>(&cu.y), mult);
+              const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[(ec & 0xff) * FZ_HS]);
 #pragma unroll
-            for (int q = 0; q < D / 4; ++q) {
-              const uint4 hv = hp[q];
-              const __half2 hm[4] = {*reinterpret_cast<const __half2*>(&hv.x), *reinterpret_cast<const __half2*>(&hv.y),
-                                     *reinterpret_cast<const __half2*>(&hv.z), *reinterpret_cast<const __half2*>(&hv.w)};
+              for (int q = 0; q < D / 4; ++q) {
+                const uint4 hv = hp[q];
+                const __half2 hm[4] = {*reinterpret_cast<const __half2*>(&hv.x), *reinterpret_cast<const __half2*>(&hv.y),
+                                       *reinterpret_cast<const __half2*>(&hv.z), *reinterpret_cast<const __half2*>(&hv.w)};
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                acc[(4 * q + i) * 2] = __hfma2(hm[i], c0, acc[(4 * q + i) * 2]);
-                acc[(4 * q + i) * 2 + 1] = __hfma2(hm[i], c1, acc[(4 * q + i) * 2 + 1]);
+                for (int i = 0; i < 4; ++i) {
+                  acc[(4 * q + i) * 2] = __hfma2(hm[i], c0, acc[(4 * q + i) * 2]);
+                  acc[(4 * q + i) * 2 + 1] = __hfma2(hm[i], c1, acc[(4 * q + i) * 2 + 1]);
+                }
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int e = e0; e < e1; ++e) {
+              const int bm = __ldg(a.edge_bm + e);
+              int src = __ldg(a.col_src + e) - a0;
+              src = min(max(src, 0), FZ_ROWS - 1);
+              const __half2 mult = __float2half2_rn((float)(bm >> 16));
+              const int bond = min(bm & 0xffff, a.bond_vocab - 1);
+              const uint2 cu = reinterpret_cast<const uint2*>(s_ctab + bond)[hz];
+              const __half2 c0 = __hmul2(*reinterpret_cast<const __half2*>(&cu.x), mult);
+              const __half2 c1 = __hmul2(*reinterpret_cast<const __half2*>(&cu.y), mult);
+              const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[src * FZ_HS]);
+#pragma unroll
+              for (int q = 0; q < D / 4; ++q) {
+                const uint4 hv = hp[q];
+                const __half2 hm[4] = {*reinterpret_cast<const __half2*>(&hv.x), *reinterpret_cast<const __half2*>(&hv.y),
+                                       *reinterpret_cast<const __half2*>(&hv.z), *reinterpret_cast<const __half2*>(&hv.w)};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  acc[(4 * q + i) * 2] = __hfma2(hm[i], c0, acc[(4 * q + i) * 2]);
+                  acc[(4 * q + i) * 2 + 1] = __hfma2(hm[i], c1, acc[(4 * q + i) * 2 + 1]);
+                }
               }
             }
           }

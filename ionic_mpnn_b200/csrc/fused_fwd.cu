@@ -51,7 +51,11 @@ struct FusedPack {  // one (tower, step)
   static constexpr int OFF_BZR = WC_BYTES;
   static constexpr int OFF_BH = OFF_BZR + BZR_BYTES;
   static constexpr int OFF_BIAS = OFF_BH + BH_BYTES;
-  static constexpr int BYTES = OFF_BIAS + BIAS_FLOATS * 4;   // 29 312
+  static constexpr int OFF_BBZR = OFF_BIAS + BIAS_FLOATS * 4;  // [64 x 16] K-major block, column 0 = 0.5 * (bz | br)
+  static constexpr int BBZR_BYTES = 2 * FZ_D * 16 * 2;         //   (third-generation kernel: biases ride in the GEMM)
+  static constexpr int OFF_BBH = OFF_BBZR + BBZR_BYTES;        // [32 x 16] block, column 0 = bh
+  static constexpr int BBH_BYTES = FZ_D * 16 * 2;
+  static constexpr int BYTES = OFF_BBH + BBH_BYTES;            // 32 384
 };
 static_assert(FusedPack::BYTES % 128 == 0, "pack must keep 128-byte alignment of the next step");
 
@@ -73,10 +77,22 @@ __global__ void fused_pack_kernel(const float* __restrict__ W /* [K, d, d] */, i
       *reinterpret_cast<uint16_t*>(out + tc::chunk_off(l, kk / 8, D) + (kk % 8) * 2) = tc::cvt16<FMT>(W[(k * D + l) * D + m]);
     }
   }
+  // third generation: sigmoid(x) = 0.5 tanh(0.5 x) + 0.5 with the 0.5 folded into [Wz | Wr] and their biases
+  const float gate_scale = KHALF ? 0.5f : 1.0f;
   if (i < 2 * D * 2 * D) {  // Bzr[n][k] = (n < D ? Wz[k][n] : Wr[k][n - D])
     const int n = i / (2 * D), k = i % (2 * D);
-    const float v = n < D ? w.Wz[k * D + n] : w.Wr[k * D + (n - D)];
+    const float v = gate_scale * (n < D ? w.Wz[k * D + n] : w.Wr[k * D + (n - D)]);
     *reinterpret_cast<uint16_t*>(out + FusedPack::OFF_BZR + tc::chunk_off(n, k / 8, 2 * D) + (k % 8) * 2) = tc::cvt16<FMT>(v);
+  }
+  if (i < 2 * D * 16) {  // bias block of the gates: element (n, k) of a [64 x 16] K-major tile, only k = 0 is non-zero
+    const int n = i / 16, k = i % 16;
+    const float v = k == 0 ? gate_scale * (n < D ? w.bz[n] : w.br[n - D]) : 0.f;
+    *reinterpret_cast<uint16_t*>(out + FusedPack::OFF_BBZR + tc::chunk_off(n, k / 8, 2 * D) + (k % 8) * 2) = tc::cvt16<FMT>(v);
+  }
+  if (i < D * 16) {  // bias block of the candidate
+    const int n = i / 16, k = i % 16;
+    *reinterpret_cast<uint16_t*>(out + FusedPack::OFF_BBH + tc::chunk_off(n, k / 8, D) + (k % 8) * 2) =
+        tc::cvt16<FMT>(k == 0 ? w.bh[n] : 0.f);
   }
   if (i < D * 2 * D) {  // Bh[n][k] = Wh[k][n]
     const int n = i / (2 * D), k = i % (2 * D);
@@ -132,6 +148,12 @@ template <bool PRECISE>
 __device__ __forceinline__ float fz_sigmoid(float x) {
   if (PRECISE) return 1.0f / (1.0f + expf(-x));
   return fmaf(0.5f, fz_tanh_fast(0.5f * x), 0.5f);
+}
+// sigmoid(2 y) for a pre-activation y that was already halved by the packed weights
+template <bool PRECISE>
+__device__ __forceinline__ float fz_sigmoid_half(float y) {
+  if (PRECISE) return 1.0f / (1.0f + expf(-2.0f * y));
+  return fmaf(0.5f, fz_tanh_fast(y), 0.5f);
 }
 template <bool PRECISE>
 __device__ __forceinline__ float fz_tanh(float x) {
@@ -851,12 +873,14 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
   const uint32_t sw0 = tc::smem_u32(smem);
   const uint32_t tbase = ctl.tmem_base + (uint32_t)(ctx * 128);
   const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
-  const uint32_t tZ = tbase, tAh = tbase, tAagg = tbase + 16, tArh = tbase + 32;
+  const uint32_t tZ = tbase, tAh = tbase, tAagg = tbase + 16, tArh = tbase + 32, tOnes = tbase + 48;
   const uint32_t tCagg = tbase + 64, tCzr = tbase + 64, tCht = tbase + 64;
   const uint32_t idesc32 = tc::make_idesc(FMT, FZ_ROWS, D), idesc64 = tc::make_idesc(FMT, FZ_ROWS, 2 * D);
   const uint64_t dWc = tc::make_smem_desc(sw0, D * 16, 128);
   const uint64_t dBzr = tc::make_smem_desc(sw0 + FusedPack::OFF_BZR, 2 * D * 16, 128);
   const uint64_t dBh = tc::make_smem_desc(sw0 + FusedPack::OFF_BH, D * 16, 128);
+  const uint64_t dBBzr = tc::make_smem_desc(sw0 + FusedPack::OFF_BBZR, 2 * D * 16, 128);
+  const uint64_t dBBh = tc::make_smem_desc(sw0 + FusedPack::OFF_BBH, D * 16, 128);
   const bool mma_warp = (t >> 5) == 0;
   const int bar_id = 1 + ctx;
   const bool descending = ctx & 1;
@@ -1050,16 +1074,19 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
 #pragma unroll
           for (int i = 0; i < 16; ++i) rr[i] = tc::pack_f16x2(h[2 * i], h[2 * i + 1]);
           tc::tmem_st16(tAh + lane_off, rr);
+          const uint32_t ones[8] = {0x00003c00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};  // (1, 0, ..., 0): the bias K-step
+          tc::tmem_st8(tOnes + lane_off, ones);
         }
         tc::tmem_wait_st();
         tc::fence_before_thread_sync();
         tc::named_bar_sync(bar_id, F3_CTX_THREADS);
-        // ------------------------------------------------------------ GEMM2: [h | agg] . [Wz | Wr]
+        // ------------------------------------------------------------ GEMM2: 0.5 ([h | agg | 1] . [Wz | Wr ; bz | br])
         if (mma_warp && !(a.debug & 2)) {
           tc::fence_after_thread_sync();
           if (tc::elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) tc::mma_f16_ts(tCzr, tAh + 8 * ks, dBzr + dstep + (uint64_t)(ks * 128), idesc64, ks > 0);
+            tc::mma_f16_ts(tCzr, tOnes, dBBzr + dstep, idesc64, true);
             tc::mma_commit(&ws.bar[1]);
           }
           __syncwarp();
@@ -1071,13 +1098,13 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
           float v[32];
           tc::tmem_ld32(tCzr + lane_off, v);
 #pragma unroll
-          for (int j = 0; j < D; ++j) z[j] = fz_sigmoid<PRECISE>(v[j] + bias[j]);
+          for (int j = 0; j < D; ++j) z[j] = fz_sigmoid_half<PRECISE>(v[j]);
           tc::tmem_ld32(tCzr + D + lane_off, v);
           uint32_t rr[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float r0 = fz_sigmoid<PRECISE>(v[2 * i] + bias[D + 2 * i]) * h[2 * i];
-            const float r1 = fz_sigmoid<PRECISE>(v[2 * i + 1] + bias[D + 2 * i + 1]) * h[2 * i + 1];
+            const float r0 = fz_sigmoid_half<PRECISE>(v[2 * i]) * h[2 * i];
+            const float r1 = fz_sigmoid_half<PRECISE>(v[2 * i + 1]) * h[2 * i + 1];
             rr[i] = tc::pack_f16x2(r0, r1);
           }
           tc::tmem_st16(tArh + lane_off, rr);
@@ -1092,6 +1119,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               tc::mma_f16_ts(tCht, tAagg + 8 * ks, dBh + dstep + (uint64_t)((ks < 2 ? ks + 2 : ks - 2) * 64), idesc32, ks > 0);
+            tc::mma_f16_ts(tCht, tOnes, dBBh + dstep, idesc32, true);
             tc::mma_commit(&ws.bar[2]);
           }
           __syncwarp();
@@ -1101,21 +1129,17 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
         {  // candidate, blend, LayerNorm (biased variance, eps), residual  (models/layers.py:151-156)
           float gq[32];
           tc::tmem_ld32(tCht + lane_off, gq);
-          float mean = 0.f;
+          float mean = 0.f, sq = 0.f;
 #pragma unroll
           for (int j = 0; j < D; ++j) {
-            const float ht = fz_tanh<PRECISE>(gq[j] + bias[2 * D + j]);
+            const float ht = fz_tanh<PRECISE>(gq[j]);
             gq[j] = fmaf(z[j], ht - h[j], h[j]);
             mean += gq[j];
+            sq = fmaf(gq[j], gq[j], sq);
           }
           mean *= (1.0f / D);
-          float var = 0.f;
-#pragma unroll
-          for (int j = 0; j < D; ++j) {
-            const float cdev = gq[j] - mean;
-            var = fmaf(cdev, cdev, var);
-          }
-          const float inv = PRECISE ? 1.0f / sqrtf(var * (1.0f / D) + a.eps) : rsqrtf(var * (1.0f / D) + a.eps);
+          const float var = fmaxf(fmaf(sq, 1.0f / D, -mean * mean), 0.f);  // biased variance
+          const float inv = PRECISE ? 1.0f / sqrtf(var + a.eps) : rsqrtf(var + a.eps);
 #pragma unroll
           for (int j = 0; j < D; ++j) h[j] = fmaf((gq[j] - mean) * inv, bias[3 * D + j], bias[4 * D + j]) + h[j];
           if (s + 1 < a.steps) {

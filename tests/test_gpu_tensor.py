@@ -247,3 +247,52 @@ def test_predict_stream_matches_per_chunk_predict():
     torch.cuda.synchronize()
     want2 = np.concatenate([m2.forward_packed(c.to("cuda")).cpu().numpy() for c in chunks])
     assert np.array_equal(out2.numpy(), want2)
+
+
+def _dense_records(n_pairs, seed, n_atoms=(20, 36), p_edge=0.35):
+    """Ions that are far denser than molecules (in-degree up to ~15, > 768 unique entries per 128-atom tile): drives
+    the fused kernel through its unstaged-entry path and through rows whose degree exceeds the sort key range."""
+    rng = np.random.default_rng(seed)
+
+    def ion():
+        n = int(rng.integers(n_atoms[0], n_atoms[1] + 1))
+        ei, bi = [], []
+        for a in range(n):
+            for b in range(a + 1, n):
+                if rng.random() < p_edge:
+                    bond = int(rng.integers(0, 71))
+                    ei += [(a, b), (b, a)]
+                    bi += [bond, bond]
+        return {"atom_ids": [int(x) for x in rng.integers(0, 123, n)], "bond_ids": bi, "edge_indices": ei, "num_atoms": n}
+
+    return [{"cation": ion(), "anion": ion(), "T": float(rng.uniform(273.15, 373.15))} for _ in range(n_pairs)]
+
+
+def test_fused_forward_dense_graphs_and_degenerate_ions():
+    from ionic_mpnn_b200 import graph
+    from ionic_mpnn_b200.viscosity import build_model
+
+    recs = _dense_records(40, 1)
+    # degenerate ions: a single atom, and an ion without any bond
+    recs[3]["cation"] = {"atom_ids": [5], "bond_ids": [], "edge_indices": [], "num_atoms": 1}
+    recs[7]["anion"] = {"atom_ids": [1, 2, 3, 4], "bond_ids": [], "edge_indices": [], "num_atoms": 4}
+    batch = graph.pack_records(recs, 72).to("cuda")
+    assert np.diff(batch.host["row_ptr"]).max() > 7
+    ref = build_model(124, 72, precision="fp32", seed=3)
+    want = ref.forward_packed(batch).cpu().numpy()
+    for flags in (0, 32, 16, 8):
+        fz = build_model(124, 72, precision="fp16", seed=3, fused=True)
+        fz.extra_tc_flags = flags
+        got = fz.forward_packed(batch).cpu().numpy()
+        assert np.isfinite(got).all()
+        assert _rel(got, want) <= BF16_RTOL, (flags, _rel(got, want))
+
+
+def test_fused_forward_empty_batch():
+    from ionic_mpnn_b200 import graph
+    from ionic_mpnn_b200.viscosity import build_model
+
+    empty = graph.pack_records([], 72)
+    empty.temperature = np.zeros(0, np.float32)
+    m = build_model(124, 72, precision="fp16", fused=True)
+    assert m.predict(empty).shape == (0, 1)

@@ -818,7 +818,7 @@ constexpr int F3_CTX_THREADS = 128;
 constexpr int F3_ECAP = 768;  // decoded entries staged per tile (tiles with more entries read the global arrays)
 
 struct alignas(16) FusedWgSmem3 {
-  uint32_t hb[FZ_ROWS * FZ_HS];  // half2 (h_m, h_m) per column; after the last step: fp32 h rows for the pooling
+  uint32_t hb[FZ_ROWS * FZ_HS];  // words 0..15 of a row: h as packed halves; after the last step: fp32 h rows for the pooling
   int molp[FZ_GROUP + 4];
   int se0[FZ_ROWS], se1[FZ_ROWS], said[FZ_ROWS];
   int cnt[4][8];
@@ -965,8 +965,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
         for (int c = 0; c < D / 4; ++c) {
           const float4 x = valid ? __ldg(emb4 + id * (D / 4) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
           h[4 * c] = x.x, h[4 * c + 1] = x.y, h[4 * c + 2] = x.z, h[4 * c + 3] = x.w;
-          reinterpret_cast<uint4*>(hbrow)[c] =
-              make_uint4(tc::pack_f16x2(x.x, x.x), tc::pack_f16x2(x.y, x.y), tc::pack_f16x2(x.z, x.z), tc::pack_f16x2(x.w, x.w));
+          reinterpret_cast<uint2*>(hbrow)[c] = make_uint2(tc::pack_f16x2(x.x, x.y), tc::pack_f16x2(x.z, x.w));
         }
       }
       if (me < nm && lane < 8) {  // index lines of the next tile -> L2
@@ -1000,14 +999,18 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
               const __half2 c1 = __hmul2(*reinterpret_cast<const __half2*>(&cu.y), mult);
               const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[(ec & 0xff) * FZ_HS]);
 #pragma unroll
-              for (int q = 0; q < D / 4; ++q) {
+              for (int q = 0; q < D / 8; ++q) {  // 8 columns per 16-byte read; HFMA2 broadcasts the low / high half
                 const uint4 hv = hp[q];
-                const __half2 hm[4] = {*reinterpret_cast<const __half2*>(&hv.x), *reinterpret_cast<const __half2*>(&hv.y),
+                const __half2 hw[4] = {*reinterpret_cast<const __half2*>(&hv.x), *reinterpret_cast<const __half2*>(&hv.y),
                                        *reinterpret_cast<const __half2*>(&hv.z), *reinterpret_cast<const __half2*>(&hv.w)};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  acc[(4 * q + i) * 2] = __hfma2(hm[i], c0, acc[(4 * q + i) * 2]);
-                  acc[(4 * q + i) * 2 + 1] = __hfma2(hm[i], c1, acc[(4 * q + i) * 2 + 1]);
+                  const __half2 lo = __low2half2(hw[i]), hi = __high2half2(hw[i]);
+                  const int m = 8 * q + 2 * i;
+                  acc[m * 2] = __hfma2(lo, c0, acc[m * 2]);
+                  acc[m * 2 + 1] = __hfma2(lo, c1, acc[m * 2 + 1]);
+                  acc[m * 2 + 2] = __hfma2(hi, c0, acc[m * 2 + 2]);
+                  acc[m * 2 + 3] = __hfma2(hi, c1, acc[m * 2 + 3]);
                 }
               }
             }
@@ -1024,14 +1027,18 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
               const __half2 c1 = __hmul2(*reinterpret_cast<const __half2*>(&cu.y), mult);
               const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[src * FZ_HS]);
 #pragma unroll
-              for (int q = 0; q < D / 4; ++q) {
+              for (int q = 0; q < D / 8; ++q) {  // 8 columns per 16-byte read; HFMA2 broadcasts the low / high half
                 const uint4 hv = hp[q];
-                const __half2 hm[4] = {*reinterpret_cast<const __half2*>(&hv.x), *reinterpret_cast<const __half2*>(&hv.y),
+                const __half2 hw[4] = {*reinterpret_cast<const __half2*>(&hv.x), *reinterpret_cast<const __half2*>(&hv.y),
                                        *reinterpret_cast<const __half2*>(&hv.z), *reinterpret_cast<const __half2*>(&hv.w)};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  acc[(4 * q + i) * 2] = __hfma2(hm[i], c0, acc[(4 * q + i) * 2]);
-                  acc[(4 * q + i) * 2 + 1] = __hfma2(hm[i], c1, acc[(4 * q + i) * 2 + 1]);
+                  const __half2 lo = __low2half2(hw[i]), hi = __high2half2(hw[i]);
+                  const int m = 8 * q + 2 * i;
+                  acc[m * 2] = __hfma2(lo, c0, acc[m * 2]);
+                  acc[m * 2 + 1] = __hfma2(lo, c1, acc[m * 2 + 1]);
+                  acc[m * 2 + 2] = __hfma2(hi, c0, acc[m * 2 + 2]);
+                  acc[m * 2 + 3] = __hfma2(hi, c1, acc[m * 2 + 3]);
                 }
               }
             }
@@ -1144,9 +1151,9 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
           for (int j = 0; j < D; ++j) h[j] = fmaf((gq[j] - mean) * inv, bias[3 * D + j], bias[4 * D + j]) + h[j];
           if (s + 1 < a.steps) {
 #pragma unroll
-            for (int c = 0; c < D / 4; ++c)
-              reinterpret_cast<uint4*>(hbrow)[c] = make_uint4(tc::pack_f16x2(h[4 * c], h[4 * c]), tc::pack_f16x2(h[4 * c + 1], h[4 * c + 1]),
-                                                              tc::pack_f16x2(h[4 * c + 2], h[4 * c + 2]), tc::pack_f16x2(h[4 * c + 3], h[4 * c + 3]));
+            for (int c = 0; c < D / 8; ++c)
+              reinterpret_cast<uint4*>(hbrow)[c] = make_uint4(tc::pack_f16x2(h[8 * c], h[8 * c + 1]), tc::pack_f16x2(h[8 * c + 2], h[8 * c + 3]),
+                                                              tc::pack_f16x2(h[8 * c + 4], h[8 * c + 5]), tc::pack_f16x2(h[8 * c + 6], h[8 * c + 7]));
           } else {
 #pragma unroll
             for (int c = 0; c < D / 4; ++c)

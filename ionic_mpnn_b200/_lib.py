@@ -31,6 +31,12 @@ class Graph(C.Structure):
                 ("col_src", vp), ("edge_bm", vp), ("bucket_ptr", vp), ("bucket_perm", vp)]
 
 
+class CompactGraph(C.Structure):
+    _fields_ = [("n_pairs", C.c_int32), ("n_atoms", C.c_int32), ("n_cat_atoms", C.c_int32), ("n_unique", C.c_int32),
+                ("n_edges", C.c_int32), ("bond_vocab", C.c_int32), ("mol_ptr", vp), ("mol_eptr", vp), ("atom_w", vp),
+                ("edge_w", vp)]
+
+
 class GruWeights(C.Structure):
     _fields_ = [(n, vp) for n in ("Wz", "bz", "Wr", "br", "Wh", "bh", "gamma", "beta")]
 
@@ -79,6 +85,8 @@ SIGNATURES = {
     "imp_fused_pack": (C.c_int, [vp, C.POINTER(GruWeights), C.c_int32, C.c_int32, C.c_int32, vp, vp]),
     "imp_mpnn_forward_fused": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_float,
                                          C.c_int32, C.c_int32, vp, vp, vp]),
+    "imp_mpnn_forward_fused_compact": (C.c_int, [C.POINTER(CompactGraph), vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, vp,
+                                                 C.c_float, C.c_int32, C.c_int32, vp, vp, vp]),
     "imp_readout_visc": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ReadoutWeights),
                                    C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp]),
     "imp_readout_mp": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ReadoutWeights),

@@ -118,6 +118,10 @@ struct FusedArgs {
   int n_pairs, atom_vocab, bond_vocab, steps, n_cta_cat;
   int n_atoms, n_unique;
   float eps;
+  // compact input feed (imp_mpnn_forward_fused_compact): 16-bit atom words, 32-bit entry words, per-molecule entry offsets
+  const int* mol_eptr;             // [2P+1] first CSR entry of every molecule
+  const unsigned short* atom_w;    // [N] atom id | in-degree << 8
+  const unsigned int* edge_w;      // [Eu] src (molecule-local) | bond << 8 | multiplicity << 16
   long long* prof;  // FZ_PROFILE builds only
   int debug;        // timing experiments only (results are wrong): 1 = skip the entry loop, 2 = skip MMAs and their waits
 };
@@ -815,13 +819,15 @@ __global__ void __launch_bounds__(2 * F2_CTX_THREADS, 1) mpnn_fused_h2_kernel(co
 // so a context needs 128 columns and four of them fit (512 threads, <= 128 registers each; three at <= 168 registers).
 // Row ownership, degree sort, packed-HFMA2 Z build, register-resident fp32 state, warp-uniform MMA issue: as above.
 constexpr int F3_CTX_THREADS = 128;
-constexpr int F3_ECAP = 768;  // decoded entries staged per tile (tiles with more entries read the global arrays)
+constexpr int F3_ECAP = 688;  // decoded entries staged per tile (tiles with more entries read the global arrays)
 
 struct alignas(16) FusedWgSmem3 {
   uint32_t hb[FZ_ROWS * FZ_HS];  // words 0..15 of a row: h as packed halves; after the last step: fp32 h rows for the pooling
   int molp[FZ_GROUP + 4];
   int se0[FZ_ROWS], se1[FZ_ROWS], said[FZ_ROWS];
   int cnt[4][8];
+  int mole[FZ_GROUP + 4];  // compact feed: first entry of every molecule of the group
+  int wsum[4];
   uint32_t ent[F3_ECAP];  // decoded entries of the tile: src row | bond << 8 | mult (half bits) << 16
   unsigned char rowof[FZ_ROWS];
   unsigned char amask[FZ_ROWS];
@@ -833,7 +839,7 @@ __host__ __device__ inline int fused3_smem_bytes(int steps, int bond_vocab, int 
   return steps * FusedPack::BYTES + ctab + nctx * (int)sizeof(FusedWgSmem3) + (int)sizeof(FusedCtl);
 }
 
-template <bool PRECISE, int NCTX>
+template <bool PRECISE, int NCTX, bool COMPACT>
 __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kernel(const FusedArgs a) {
   constexpr int D = FZ_D;
   constexpr int FMT = tc::FMT_F16;
@@ -896,7 +902,10 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
     const int m0 = g * FZ_GROUP, nm = min(FZ_GROUP, P - m0);
     const int base_mol = tower * P + m0;
     tc::named_bar_sync(bar_id, F3_CTX_THREADS);
-    if (t <= nm) ws.molp[t] = __ldg(a.mol_ptr + base_mol + t);
+    if (t <= nm) {
+      ws.molp[t] = __ldg(a.mol_ptr + base_mol + t);
+      if (COMPACT) ws.mole[t] = __ldg(a.mol_eptr + base_mol + t);
+    }
     tc::named_bar_sync(bar_id, F3_CTX_THREADS);
     int ms = 0;
     while (ms < nm) {
@@ -913,10 +922,28 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
       {
         const bool valid = t < rows;
         int aid = 0, e0 = 0, e1 = 0;
-        if (valid) {
-          aid = __ldg(a.atom_id + a0 + t);
-          e0 = __ldg(a.row_ptr + a0 + t);
-          e1 = __ldg(a.row_ptr + a0 + t + 1);
+        if (!COMPACT) {
+          if (valid) {
+            aid = __ldg(a.atom_id + a0 + t);
+            e0 = __ldg(a.row_ptr + a0 + t);
+            e1 = __ldg(a.row_ptr + a0 + t + 1);
+          }
+        } else {  // row_ptr of the tile = first entry of its first molecule + exclusive scan of the in-degrees
+          const int aw = valid ? (int)__ldg(a.atom_w + a0 + t) : 0;
+          aid = aw & 0xff;
+          const int deg = aw >> 8;
+          int incl = deg;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+          }
+          if (lane == 31) ws.wsum[wq] = incl;
+          tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+          int base = ws.mole[ms];
+          for (int w = 0; w < wq; ++w) base += ws.wsum[w];
+          e1 = base + incl;
+          e0 = e1 - deg;
         }
         ws.se0[t] = e0, ws.se1[t] = e1, ws.said[t] = aid;
         ws.amask[t] = (valid && aid > 0) ? 1 : 0;  // models/layers.py:163
@@ -948,15 +975,25 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
       const bool staged = n_ent <= F3_ECAP && a.bond_vocab <= 256;
       if (staged)
         for (int i = t; i < n_ent; i += F3_CTX_THREADS) {
-          const int bm = __ldg(a.edge_bm + E0 + i);
-          const int src = min(max(__ldg(a.col_src + E0 + i) - a0, 0), FZ_ROWS - 1);
-          const int bond = min(bm & 0xffff, a.bond_vocab - 1);
-          ws.ent[i] = (uint32_t)src | ((uint32_t)bond << 8) | ((uint32_t)__half_as_ushort(__float2half_rn((float)(bm >> 16))) << 16);
+          if (!COMPACT) {
+            const int bm = __ldg(a.edge_bm + E0 + i);
+            const int src = min(max(__ldg(a.col_src + E0 + i) - a0, 0), FZ_ROWS - 1);
+            const int bond = min(bm & 0xffff, a.bond_vocab - 1);
+            ws.ent[i] = (uint32_t)src | ((uint32_t)bond << 8) | ((uint32_t)__half_as_ushort(__float2half_rn((float)(bm >> 16))) << 16);
+          } else {  // src stays molecule-local here; the row owner adds its molecule's first row
+            const uint32_t w = __ldg(a.edge_w + E0 + i);
+            const uint32_t bond = min((w >> 8) & 0xffu, (uint32_t)(a.bond_vocab - 1));
+            ws.ent[i] = (w & 0xffu) | (bond << 8) | ((uint32_t)__half_as_ushort(__float2half_rn((float)((w >> 16) & 0xffu))) << 16);
+          }
         }
       // ---------------------------------------------------------------- thread t owns row r
       const int r = ws.rowof[t];
       const int e0 = ws.se0[r], e1 = (a.debug & 1) ? e0 : ws.se1[r];
       uint32_t* hbrow = &ws.hb[r * FZ_HS];
+      int mbase = 0;  // COMPACT: first row of the molecule that owns row r (entries carry molecule-local sources)
+      if (COMPACT)
+        for (int mi = ms; mi < me; ++mi)
+          if (ws.molp[mi] - a0 <= r) mbase = ws.molp[mi] - a0;
       float h[D];
       {  // Embedding(atom)
         const bool valid = r < rows;
@@ -970,10 +1007,15 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
       }
       if (me < nm && lane < 8) {  // index lines of the next tile -> L2
         const int an = ws.molp[me], en = ws.se1[max(rows, 1) - 1];
-        if (wq == 0) prefetch_l2(a.atom_id + min(an + lane * 32, a.n_atoms - 1));
-        if (wq == 1) prefetch_l2(a.row_ptr + min(an + lane * 32, a.n_atoms));
-        if (wq == 2) prefetch_l2(a.col_src + min(en + lane * 32, a.n_unique - 1));
-        if (wq == 3) prefetch_l2(a.edge_bm + min(en + lane * 32, a.n_unique - 1));
+        if (!COMPACT) {
+          if (wq == 0) prefetch_l2(a.atom_id + min(an + lane * 32, a.n_atoms - 1));
+          if (wq == 1) prefetch_l2(a.row_ptr + min(an + lane * 32, a.n_atoms));
+          if (wq == 2) prefetch_l2(a.col_src + min(en + lane * 32, a.n_unique - 1));
+          if (wq == 3) prefetch_l2(a.edge_bm + min(en + lane * 32, a.n_unique - 1));
+        } else {
+          if (wq == 0 && lane < 2) prefetch_l2(a.atom_w + min(an + lane * 64, a.n_atoms - 1));
+          if (wq == 2) prefetch_l2(a.edge_w + min(en + lane * 32, a.n_unique - 1));
+        }
       }
       tc::named_bar_sync(bar_id, F3_CTX_THREADS);
 
@@ -997,7 +1039,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
               const __half2 mult = *reinterpret_cast<const __half2*>(&mbits);
               const __half2 c0 = __hmul2(*reinterpret_cast<const __half2*>(&cu.x), mult);
               const __half2 c1 = __hmul2(*reinterpret_cast<const __half2*>(&cu.y), mult);
-              const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[(ec & 0xff) * FZ_HS]);
+              const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[(COMPACT ? min((int)(ec & 0xff) + mbase, FZ_ROWS - 1) : (int)(ec & 0xff)) * FZ_HS]);
 #pragma unroll
               for (int q = 0; q < D / 8; ++q) {  // 8 columns per 16-byte read; HFMA2 broadcasts the low / high half
                 const uint4 hv = hp[q];
@@ -1017,8 +1059,15 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
           } else {
 #pragma unroll 1
             for (int e = e0; e < e1; ++e) {
-              const int bm = __ldg(a.edge_bm + e);
-              int src = __ldg(a.col_src + e) - a0;
+              int bm, src;
+              if (!COMPACT) {
+                bm = __ldg(a.edge_bm + e);
+                src = __ldg(a.col_src + e) - a0;
+              } else {
+                const uint32_t w = __ldg(a.edge_w + e);
+                bm = (int)(((w >> 8) & 0xffu) | ((w >> 16) & 0xffu) << 16);
+                src = (int)(w & 0xffu) + mbase;
+              }
               src = min(max(src, 0), FZ_ROWS - 1);
               const __half2 mult = __float2half2_rn((float)(bm >> 16));
               const int bond = min(bm & 0xffff, a.bond_vocab - 1);
@@ -1227,10 +1276,37 @@ static int launch_fused(const FusedArgs& a, int grid, size_t smem, cudaStream_t 
   return 0;
 }
 
+static int fused_forward_impl(const imp_graph_t* g, const imp_compact_graph_t* cg, const float* d_atom_emb, int32_t atom_vocab,
+                              const float* d_bond_emb, int32_t d, int32_t bond_dim, int32_t steps, const void* d_packed,
+                              float eps, int32_t flags, int32_t max_mol_atoms, float* d_pooled, int32_t* d_status, void* stream);
+
 extern "C" int imp_mpnn_forward_fused(const imp_graph_t* g, const float* d_atom_emb, int32_t atom_vocab,
                                       const float* d_bond_emb, int32_t d, int32_t bond_dim, int32_t steps,
                                       const void* d_packed, float eps, int32_t flags, int32_t max_mol_atoms,
                                       float* d_pooled, int32_t* d_status, void* stream) {
+  return fused_forward_impl(g, nullptr, d_atom_emb, atom_vocab, d_bond_emb, d, bond_dim, steps, d_packed, eps, flags,
+                            max_mol_atoms, d_pooled, d_status, stream);
+}
+
+extern "C" int imp_mpnn_forward_fused_compact(const imp_compact_graph_t* cg, const float* d_atom_emb, int32_t atom_vocab,
+                                              const float* d_bond_emb, int32_t d, int32_t bond_dim, int32_t steps,
+                                              const void* d_packed, float eps, int32_t flags, int32_t max_mol_atoms,
+                                              float* d_pooled, int32_t* d_status, void* stream) {
+  IMP_REQUIRE(cg, IMP_ERR_ARG, "imp_mpnn_forward_fused_compact: graph is null");
+  IMP_REQUIRE((flags & IMP_TC_FP16) && !(flags & (IMP_TC_F32_ZBUILD | IMP_TC_TWO_THREADS_PER_ROW)), IMP_ERR_UNSUPPORTED,
+              "imp_mpnn_forward_fused_compact: the compact feed is read by the default half-operand kernel only");
+  IMP_REQUIRE(atom_vocab <= 256 && cg->bond_vocab <= 256, IMP_ERR_DIM, "imp_mpnn_forward_fused_compact: vocabularies must fit 8 bits");
+  imp_graph_t g{};
+  g.n_pairs = cg->n_pairs, g.n_atoms = cg->n_atoms, g.n_cat_atoms = cg->n_cat_atoms, g.n_unique = cg->n_unique;
+  g.n_edges = cg->n_edges, g.bond_vocab = cg->bond_vocab, g.mol_ptr = const_cast<int32_t*>(cg->mol_ptr);
+  return fused_forward_impl(&g, cg, d_atom_emb, atom_vocab, d_bond_emb, d, bond_dim, steps, d_packed, eps, flags, max_mol_atoms,
+                            d_pooled, d_status, stream);
+}
+
+static int fused_forward_impl(const imp_graph_t* g, const imp_compact_graph_t* cg, const float* d_atom_emb, int32_t atom_vocab,
+                              const float* d_bond_emb, int32_t d, int32_t bond_dim, int32_t steps, const void* d_packed,
+                              float eps, int32_t flags, int32_t max_mol_atoms, float* d_pooled, int32_t* d_status, void* stream) {
+  const bool compact = cg != nullptr;
   IMP_REQUIRE(g, IMP_ERR_ARG, "imp_mpnn_forward_fused: graph is null");
   IMP_REQUIRE(g->n_pairs >= 0 && g->n_atoms >= 0 && g->n_cat_atoms >= 0 && g->n_cat_atoms <= g->n_atoms, IMP_ERR_ARG,
               "imp_mpnn_forward_fused: bad graph sizes");
@@ -1242,9 +1318,14 @@ extern "C" int imp_mpnn_forward_fused(const imp_graph_t* g, const float* d_atom_
   IMP_REQUIRE(max_mol_atoms <= FZ_ROWS, IMP_ERR_DIM,
               "imp_mpnn_forward_fused: a molecule has %d atoms, a tile holds %d; use the staged kernels", max_mol_atoms, FZ_ROWS);
   if (g->n_pairs == 0) return 0;
-  IMP_REQUIRE(d_atom_emb && d_bond_emb && d_packed && d_pooled && g->mol_ptr && g->atom_id && g->row_ptr, IMP_ERR_ARG,
-              "imp_mpnn_forward_fused: null pointer");
-  IMP_REQUIRE(g->n_unique == 0 || (g->col_src && g->edge_bm), IMP_ERR_ARG, "imp_mpnn_forward_fused: null edge arrays");
+  IMP_REQUIRE(d_atom_emb && d_bond_emb && d_packed && d_pooled && g->mol_ptr, IMP_ERR_ARG, "imp_mpnn_forward_fused: null pointer");
+  if (compact) {
+    IMP_REQUIRE(cg->mol_eptr && cg->atom_w && (g->n_unique == 0 || cg->edge_w), IMP_ERR_ARG,
+                "imp_mpnn_forward_fused_compact: null index arrays");
+  } else {
+    IMP_REQUIRE(g->atom_id && g->row_ptr, IMP_ERR_ARG, "imp_mpnn_forward_fused: null pointer");
+    IMP_REQUIRE(g->n_unique == 0 || (g->col_src && g->edge_bm), IMP_ERR_ARG, "imp_mpnn_forward_fused: null edge arrays");
+  }
   IMP_REQUIRE(imp_device_is_sm100(), IMP_ERR_UNSUPPORTED, "imp_mpnn_forward_fused: tcgen05 needs an sm_100 device");
   FusedArgs a;
   a.mol_ptr = g->mol_ptr, a.atom_id = g->atom_id, a.row_ptr = g->row_ptr, a.col_src = g->col_src, a.edge_bm = g->edge_bm;
@@ -1253,6 +1334,8 @@ extern "C" int imp_mpnn_forward_fused(const imp_graph_t* g, const float* d_atom_
 
   a.status = d_status, a.n_pairs = g->n_pairs, a.atom_vocab = atom_vocab, a.bond_vocab = g->bond_vocab, a.steps = steps, a.eps = eps;
   a.prof = nullptr;
+  a.mol_eptr = nullptr, a.atom_w = nullptr, a.edge_w = nullptr;
+  if (compact) a.mol_eptr = cg->mol_eptr, a.atom_w = cg->atom_w, a.edge_w = cg->edge_w;
   a.debug = (flags >> 8) & 0xff;
 #ifdef FZ_PROFILE
   a.prof = reinterpret_cast<long long*>(d_status);  // profiling build: d_status must hold 3 * 18 int64 (zeroed by the caller)
@@ -1302,8 +1385,13 @@ extern "C" int imp_mpnn_forward_fused(const imp_graph_t* g, const float* d_atom_
     IMP_REQUIRE(smem3 <= 227 * 1024, IMP_ERR_DIM, "imp_mpnn_forward_fused: needs %zu B of shared memory", smem3);
 #define IMP_LAUNCH_H2X(PREC, NC)                                                                                           \
   do {                                                                                                                     \
-    IMP_CUDA(cudaFuncSetAttribute(mpnn_fused_h2x_kernel<PREC, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
-    mpnn_fused_h2x_kernel<PREC, NC><<<grid3, NC * F3_CTX_THREADS, smem3, st>>>(a);                                        \
+    if (compact) {                                                                                                         \
+      IMP_CUDA(cudaFuncSetAttribute(mpnn_fused_h2x_kernel<PREC, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
+      mpnn_fused_h2x_kernel<PREC, NC, true><<<grid3, NC * F3_CTX_THREADS, smem3, st>>>(a);                                \
+    } else {                                                                                                               \
+      IMP_CUDA(cudaFuncSetAttribute(mpnn_fused_h2x_kernel<PREC, NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
+      mpnn_fused_h2x_kernel<PREC, NC, false><<<grid3, NC * F3_CTX_THREADS, smem3, st>>>(a);                               \
+    }                                                                                                                      \
   } while (0)
     if (nctx == 4) {
       if (precise) IMP_LAUNCH_H2X(true, 4); else IMP_LAUNCH_H2X(false, 4);

@@ -130,6 +130,57 @@ class PackedGraphBatch:
             self.pinned_T = None if self.temperature is None else torch.from_numpy(self.temperature).pin_memory()
         return self
 
+    def compact(self):
+        """Builds (once) the compact input feed of the fused forward (include/imp_b200.h, imp_compact_graph_t): 16-bit atom
+        words, 32-bit entry words with molecule-local sources, per-molecule entry offsets.  Raises if the batch does
+        not fit the format (ids >= 256, in-degree > 255, molecule > 256 atoms, multiplicity > 255)."""
+        if getattr(self, "chost", None) is not None:
+            return self
+        h = self.host
+        mol_ptr, row_ptr = h["mol_ptr"].astype(np.int64), h["row_ptr"].astype(np.int64)
+        deg = np.diff(row_ptr)
+        n_mols = len(mol_ptr) - 1
+        atom_mol_base = np.repeat(mol_ptr[:-1], np.diff(mol_ptr))
+        entry_dst = np.repeat(np.arange(self.n_atoms, dtype=np.int64), deg)
+        src_local = h["col_src"].astype(np.int64) - atom_mol_base[entry_dst] if self.n_unique else np.zeros(0, np.int64)
+        bond = h["edge_bm"].astype(np.int64) & 0xFFFF
+        mult = h["edge_bm"].astype(np.int64) >> 16
+        ok = (self.n_atoms == 0 or (h["atom_id"].min() >= 0 and h["atom_id"].max() < 256 and deg.max() <= 255)) and \
+             (self.n_unique == 0 or (src_local.min() >= 0 and src_local.max() < 256 and bond.max() < 256 and mult.max() < 256))
+        if not ok:
+            raise _lib.ImpError("batch does not fit the compact feed (8-bit ids / degrees / local sources)")
+        self.chost = {
+            "mol_ptr": h["mol_ptr"],
+            "mol_eptr": np.ascontiguousarray(row_ptr[mol_ptr].astype(I32)) if n_mols >= 0 else np.zeros(1, I32),
+            "atom_w": np.ascontiguousarray((h["atom_id"].astype(np.int64) | (deg << 8)).astype(np.uint16)),
+            "edge_w": np.ascontiguousarray((src_local | (bond << 8) | (mult << 16)).astype(np.uint32)),
+        }
+        return self
+
+    def nbytes_compact(self):
+        self.compact()
+        return sum(v.nbytes for v in self.chost.values()) + (0 if self.temperature is None else self.temperature.nbytes)
+
+    def pin_compact(self):
+        import torch
+
+        self.compact()
+        if getattr(self, "cpinned", None) is None:
+            views = {"mol_ptr": self.chost["mol_ptr"], "mol_eptr": self.chost["mol_eptr"],
+                     "atom_w": self.chost["atom_w"].view(np.int16), "edge_w": self.chost["edge_w"].view(np.int32)}
+            self.cpinned = {k: torch.from_numpy(v).pin_memory() for k, v in views.items()}
+            self.pinned_T = None if self.temperature is None else torch.from_numpy(self.temperature).pin_memory()
+        return self
+
+    def to_compact(self, device):
+        """Device copy of the compact feed only (what imp_mpnn_forward_fused_compact reads)."""
+        import torch
+
+        self.pin_compact()
+        slot = DeviceSlot(torch.device(device), COMPACT_FIELDS)
+        slot.load(self, torch.cuda.current_stream())
+        return slot
+
     def c_struct(self):
         if self.dev is None:
             raise _lib.ImpError("PackedGraphBatch is not on a device: call .to('cuda') first")
@@ -142,6 +193,7 @@ class PackedGraphBatch:
 
 
 FUSED_FIELDS = ("mol_ptr", "atom_id", "row_ptr", "col_src", "edge_bm")  # what imp_mpnn_forward_fused reads
+COMPACT_FIELDS = ("mol_ptr", "mol_eptr", "atom_w", "edge_w")              # what imp_mpnn_forward_fused_compact reads
 
 
 class DeviceSlot:
@@ -155,23 +207,29 @@ class DeviceSlot:
         self.dev_y = None
         self.cap = {}
 
+    @property
+    def is_compact(self):
+        return self.fields == COMPACT_FIELDS
+
     def load(self, chunk, stream):
         """Enqueues the H2D copies of ``chunk`` (pinned) on ``stream``; returns the bytes copied."""
         import torch
 
         n = 0
+        pinned = chunk.cpinned if self.is_compact else chunk.pinned
         with torch.cuda.stream(stream):
             for k in self.fields:
-                src = chunk.pinned[k]
+                src = pinned[k]
                 if self.cap.get(k, 0) < src.numel():
                     self.cap[k] = int(src.numel() * 1.05) + 16
-                    self.dev[k + "_buf"] = torch.empty(self.cap[k], dtype=torch.int32, device=self.device)
+                    self.dev[k + "_buf"] = torch.empty(self.cap[k], dtype=src.dtype, device=self.device)
                 self.dev[k] = self.dev[k + "_buf"][: src.numel()]
                 self.dev[k].copy_(src, non_blocking=True)
-                n += src.numel() * 4
-            for k in GRAPH_FIELDS:  # fields the fused path never reads
-                if k not in self.fields:
-                    self.dev[k] = self.dev[self.fields[0]]
+                n += src.numel() * src.element_size()
+            if not self.is_compact:
+                for k in GRAPH_FIELDS:  # fields the fused path never reads
+                    if k not in self.fields:
+                        self.dev[k] = self.dev[self.fields[0]]
             if chunk.pinned_T is not None:
                 if self.cap.get("T", 0) < chunk.pinned_T.numel():
                     self.cap["T"] = int(chunk.pinned_T.numel() * 1.05) + 16
@@ -182,6 +240,10 @@ class DeviceSlot:
         for a in ("n_pairs", "n_atoms", "n_cat_atoms", "n_unique", "n_edges", "bond_vocab", "max_mol_atoms"):
             setattr(self, a, getattr(chunk, a))
         return n
+
+    def compact_struct(self):
+        return _lib.CompactGraph(self.n_pairs, self.n_atoms, self.n_cat_atoms, self.n_unique, self.n_edges, self.bond_vocab,
+                                 *(self.dev[k].data_ptr() for k in COMPACT_FIELDS))
 
     def c_struct(self):
         return _lib.Graph(self.n_pairs, self.n_atoms, self.n_cat_atoms, self.n_unique, self.n_edges, self.bond_vocab,

@@ -296,3 +296,26 @@ def test_fused_forward_empty_batch():
     empty.temperature = np.zeros(0, np.float32)
     m = build_model(124, 72, precision="fp16", fused=True)
     assert m.predict(empty).shape == (0, 1)
+
+
+def test_compact_feed_is_bit_identical():
+    """imp_mpnn_forward_fused_compact (16-bit atom words, 32-bit entry words) == imp_mpnn_forward_fused, bit for bit,
+    on molecule-like, large and dense graphs; predict_stream picks it up automatically."""
+    from ionic_mpnn_b200 import graph
+    from ionic_mpnn_b200.viscosity import build_model
+
+    m = build_model(124, 72, precision="fp16", seed=4)
+    cases = [graph.synth_batch(777, seed=21)[0], graph.synth_batch(90, seed=22, n_min=40, n_max=120, skewed=True)[0],
+             graph.pack_records(_dense_records(30, 2), 72)]
+    for b in cases:
+        want = m.forward_packed(b.to("cuda")).cpu().numpy()
+        got = m.forward_packed(b.to_compact("cuda")).cpu().numpy()
+        assert np.array_equal(got, want)
+        assert b.nbytes_compact() < 0.5 * b.nbytes()
+    chunks = [graph.synth_batch(n, seed=60 + i)[0] for i, n in enumerate([500, 65, 900])]
+    out_c, bytes_c = m.predict_stream(chunks, compact=True)
+    torch.cuda.synchronize()
+    out_c = out_c.numpy().copy()
+    out_f, bytes_f = m.predict_stream(chunks, compact=False)
+    torch.cuda.synchronize()
+    assert np.array_equal(out_c, out_f.numpy()) and bytes_c < 0.5 * bytes_f

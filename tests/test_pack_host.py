@@ -98,3 +98,22 @@ def test_synth_ions_follow_the_recipe():
     assert np.array_equal(again.edge_src, ions.edge_src) and np.array_equal(again.atom_ids, ions.atom_ids)
     sk = graph.synth_flat(2000, seed=11, skewed=True)
     assert np.bincount(sk.bond_ids, minlength=71)[0] > 5 * np.bincount(sk.bond_ids, minlength=71)[40]
+
+
+def test_compact_feed_round_trips_the_csr():
+    """PackedGraphBatch.compact(): the 16/32-bit words decode back to atom_id / row_ptr / col_src / edge_bm exactly."""
+    from ionic_mpnn_b200 import graph
+
+    b, _, _ = graph.synth_batch(300, seed=9)
+    b.compact()
+    h, c = b.host, b.chost
+    mp = h["mol_ptr"].astype(np.int64)
+    deg = (c["atom_w"] >> 8).astype(np.int64)
+    assert np.array_equal(c["atom_w"] & 0xFF, h["atom_id"])
+    row_ptr = np.concatenate([[0], np.cumsum(deg)])
+    assert np.array_equal(row_ptr, h["row_ptr"])
+    assert np.array_equal(c["mol_eptr"], h["row_ptr"][mp])
+    base = np.repeat(mp[:-1], np.diff(mp))[np.repeat(np.arange(b.n_atoms), deg)]
+    assert np.array_equal((c["edge_w"] & 0xFF).astype(np.int64) + base, h["col_src"])
+    assert np.array_equal(((c["edge_w"] >> 8) & 0xFF) | ((c["edge_w"] >> 16) << 16), h["edge_bm"])
+    assert b.nbytes_compact() < 0.5 * b.nbytes()

@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="visc_sweep", choices=["visc_sweep", "mp64k", "visc_train"],
+    ap.add_argument("--workload", default="visc_sweep", choices=["visc_sweep", "mp64k", "visc_train", "wide"],
                     help="visc_sweep = BASELINE configs[2] (headline); mp64k = configs[1]; visc_train = configs[3] "
                          "(forward + backward + all-reduce + Adam, 65,536 pairs per GPU)")
     ap.add_argument("--pairs-per-gpu", type=int, default=None)
@@ -65,6 +65,11 @@ def workload_config(args):
         kind = "viscosity"
         name = ("BASELINE configs[2]: viscosity MPNN inference sweep (atom_dim 32, bond_dim 8, 4 steps, vocab 123/71, "
                 "10-40 atoms/ion), weak scaling")
+    elif args.workload == "wide":
+        P = args.pairs_per_gpu or 16_384
+        kind = "viscosity"
+        name = ("BASELINE configs[4]: wide/deep viscosity MPNN forward (atom_dim 256, bond_dim 8, 6 steps, 40-120 atoms/ion), "
+                "fp32 general-shape kernels")
     elif args.workload == "visc_train":
         P = args.pairs_per_gpu or 65_536
         kind = "viscosity"
@@ -182,7 +187,8 @@ def stage_flops(batch, d, S):
     """Algorithmic FLOP per launch: messages 2*E*d^2 with E = live entries counted with multiplicity,
     gated update 12*N*d^2, per step."""
     N, E = batch.n_atoms, batch.n_edges
-    return {"mpnn_forward_fused": S * (2 * E + 12 * N) * d * d, "gated_update_tc": 12 * N * d * d}
+    return {"mpnn_forward_fused": S * (2 * E + 12 * N) * d * d, "gated_update_tc": 12 * N * d * d,
+            "gated_update_wide": 12 * N * d * d, "message_agg": 2 * batch.n_unique * d * d}
 
 
 def stage_bytes(batch, d, S, s=4):
@@ -198,6 +204,7 @@ def stage_bytes(batch, d, S, s=4):
         "message_agg": 2 * N * d * s + 8 * Eu + 4 * N,   # h in, agg out, (src, bond|mult) per unique entry, row_ptr
         "gated_update": 3 * N * d * s,                    # h, agg in; h out
         "gated_update_tc": 3 * N * d * s,
+        "gated_update_wide": 3 * N * d * s,
         "pool_head": N * d * s + 4 * N + 8 * P + 8 * P,   # h, atom_id, mol_ptr (2 towers), T + out
     }
 
@@ -315,14 +322,19 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     P, kind, name = workload_config(args)
-    spec = make_spec(kind)
+    wide = args.workload == "wide"
+    spec = make_spec(kind, atom_dim=256, num_steps=6) if wide else make_spec(kind)
+    if wide:
+        args.precision = "fp32"
     model = MPNNModel(spec, device=f"cuda:{local}", seed=0, precision=args.precision,
                       fused=False if args.staged else "auto")
     model.extra_tc_flags = args.tc_flags
     d, S = spec["atom_dim"], spec["num_steps"]
 
     t_pack0 = time.perf_counter()
-    batch, _, _ = graph.synth_batch(P, seed=1003 + rank, skewed=args.skewed, with_temperature=(kind == "viscosity"))
+    nmin, nmax = (40, 120) if wide else (10, 40)
+    batch, _, _ = graph.synth_batch(P, seed=1003 + rank, n_min=nmin, n_max=nmax, skewed=args.skewed,
+                                    with_temperature=(kind == "viscosity"))
     t_pack = time.perf_counter() - t_pack0
     batch.to(f"cuda:{local}")
     model.refresh_tables()
@@ -399,7 +411,7 @@ def run_b200(args):
         chunks = []
         for c in range(n_chunks):
             pc = per if c + 1 < n_chunks else P - per * (n_chunks - 1)
-            ch, _, _ = graph.synth_batch(pc, seed=5003 + 97 * rank + c, skewed=args.skewed,
+            ch, _, _ = graph.synth_batch(pc, seed=5003 + 97 * rank + c, n_min=nmin, n_max=nmax, skewed=args.skewed,
                                          with_temperature=(kind == "viscosity"))
             chunks.append(ch.pin())
         out_host = torch.empty(P, dtype=torch.float32).pin_memory()

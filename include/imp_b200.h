@@ -140,6 +140,13 @@ int imp_gated_update(const float* d_h, const float* d_agg, int32_t n_atoms, int3
                      const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_h_out,
                      void* stream);
 
+/* K5 for wide atom states (atom_dim a multiple of 16, e.g. 128 / 256 -- the "wide/deep" variant): three tiled fp32
+ * GEMMs with fused gate epilogues + one LayerNorm/residual kernel.  d_workspace: imp_gated_update_wide_workspace_floats. */
+int64_t imp_gated_update_wide_workspace_floats(int32_t n_atoms, int32_t d);
+int imp_gated_update_wide(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
+                          const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_h_out,
+                          float* d_workspace, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K6  GlobalSumPool (models/layers.py:161-164) + Dense(fp, relu) (train_viscosity.py:189) +
  *     Dense(mix, relu) x2 + AddTwoTensors (:197-201) + head:

@@ -72,6 +72,9 @@ SIGNATURES = {
     "imp_segment_sum": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, vp, vp]),
     "imp_gated_update": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(GruWeights), C.POINTER(GruWeights),
                                    C.c_float, vp, vp]),
+    "imp_gated_update_wide_workspace_floats": (C.c_int64, [C.c_int32, C.c_int32]),
+    "imp_gated_update_wide": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(GruWeights), C.POINTER(GruWeights),
+                                        C.c_float, vp, vp, vp]),
     "imp_gru_pack_bytes": (C.c_int64, [C.c_int32]),
     "imp_gru_pack_bf16": (C.c_int, [C.POINTER(GruWeights), C.c_int32, vp, vp]),
     "imp_gru_pack_f16": (C.c_int, [C.POINTER(GruWeights), C.c_int32, vp, vp]),

@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(K5_TILE) gated_update_kernel(const float* __re
 // One warp per ion pair.  Pool: lanes stride over feature columns (coalesced row reads).  The tiny dense
 // layers run out of per-warp shared scratch.  Readout weights are staged in shared memory per CTA.
 constexpr int K6_WARPS = 8;
-constexpr int K6_MAXV = 64;  // max of d, fp, mix, fp2
+constexpr int K6_MAXV = 256;  // max of d, fp, mix, fp2
 
 struct K6Args {
   const int* mol_ptr;
@@ -457,7 +457,8 @@ __global__ void __launch_bounds__(K6_WARPS * 32) pool_head_kernel(K6Args a) {
 // =========================================================================================== ABI
 using namespace imp;
 
-static bool dim_ok(int d) { return d == 8 || d == 16 || d == 32 || d == 64; }
+static bool dim_ok(int d) { return d == 8 || d == 16 || d == 32 || d == 64; }                      // thread-per-atom GRU
+static bool dim_ok_msg(int d) { return dim_ok(d) || d == 128 || d == 256; }                          // message kernels
 
 extern "C" int imp_embed_atoms(const float* d_atom_emb, int32_t atom_vocab, const int32_t* d_atom_id, int32_t n_atoms,
                                int32_t d, float* d_h0, void* stream) {
@@ -521,6 +522,17 @@ static int check_graph(const imp_graph_t* g, const char* who) {
     default: break;                        \
   }
 
+#define IMP_DISPATCH_D_MSG(d, CALL)        \
+  switch (d) {                             \
+    case 8: { constexpr int D = 8; CALL; } break;   \
+    case 16: { constexpr int D = 16; CALL; } break; \
+    case 32: { constexpr int D = 32; CALL; } break; \
+    case 64: { constexpr int D = 64; CALL; } break; \
+    case 128: { constexpr int D = 128; CALL; } break; \
+    case 256: { constexpr int D = 256; CALL; } break; \
+    default: break;                        \
+  }
+
 static int message_agg_any(const imp_graph_t* g, const float* d_h, int32_t d, const float* d_table_il_cat,
                            const float* d_table_il_an, float* d_agg, int accumulate, void* stream);
 
@@ -537,13 +549,13 @@ extern "C" int imp_message_agg_bwd(const imp_graph_t* g, const float* d_dagg, in
 static int message_agg_any(const imp_graph_t* g, const float* d_h, int32_t d, const float* d_table_il_cat,
                            const float* d_table_il_an, float* d_agg, int accumulate, void* stream) {
   if (int rc = check_graph(g, "imp_message_agg")) return rc;
-  IMP_REQUIRE(dim_ok(d), IMP_ERR_DIM, "imp_message_agg: atom_dim %d not in {8,16,32,64} (fp32 path)", d);
+  IMP_REQUIRE(dim_ok_msg(d), IMP_ERR_DIM, "imp_message_agg: atom_dim %d not in {8,16,32,64,128,256} (fp32 path)", d);
   if (g->n_atoms == 0) return 0;
   IMP_REQUIRE(d_h && d_table_il_cat && d_table_il_an && d_agg && g->row_ptr && (g->n_unique == 0 || (g->col_src && g->edge_bm)),
               IMP_ERR_ARG, "imp_message_agg: null pointer");
   const int64_t threads = (int64_t)g->n_atoms * d;
   const unsigned blocks = (unsigned)ceil_div(threads, 256);
-  IMP_DISPATCH_D(d, (message_agg_kernel<D><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+  IMP_DISPATCH_D_MSG(d, (message_agg_kernel<D><<<blocks, 256, 0, (cudaStream_t)stream>>>(
                         g->row_ptr, g->col_src, g->edge_bm, d_h, d_table_il_cat, d_table_il_an, g->n_atoms,
                         g->n_cat_atoms, d_agg, accumulate)));
   IMP_LAUNCH_CHECK();
@@ -553,13 +565,13 @@ static int message_agg_any(const imp_graph_t* g, const float* d_h, int32_t d, co
 extern "C" int imp_edge_messages(const imp_graph_t* g, const float* d_h, int32_t d, const float* d_table_cat,
                                  const float* d_table_an, float* d_msg, void* stream) {
   if (int rc = check_graph(g, "imp_edge_messages")) return rc;
-  IMP_REQUIRE(dim_ok(d), IMP_ERR_DIM, "imp_edge_messages: atom_dim %d not in {8,16,32,64} (fp32 path)", d);
+  IMP_REQUIRE(dim_ok_msg(d), IMP_ERR_DIM, "imp_edge_messages: atom_dim %d not in {8,16,32,64,128,256} (fp32 path)", d);
   if (g->n_unique == 0) return 0;
   IMP_REQUIRE(d_h && d_table_cat && d_table_an && d_msg && g->col_src && g->edge_bm && g->bucket_perm && g->bucket_ptr, IMP_ERR_ARG,
               "imp_edge_messages: null pointer");
   const int64_t threads = (int64_t)g->n_unique * d;
   const unsigned blocks = (unsigned)ceil_div(threads, 256);
-  IMP_DISPATCH_D(d, (edge_messages_kernel<D><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+  IMP_DISPATCH_D_MSG(d, (edge_messages_kernel<D><<<blocks, 256, 0, (cudaStream_t)stream>>>(
                         g->bucket_perm, g->col_src, g->edge_bm, d_h, d_table_cat, d_table_an, g->n_unique,
                         g->bucket_ptr + g->bond_vocab, d_msg)));
   IMP_LAUNCH_CHECK();
@@ -623,8 +635,8 @@ static int launch_k6(const imp_graph_t* g, const float* d_h, const float* d_pool
   const int n_head_out = fp2 > 0 ? fp2 : 3;
   const size_t smem = sizeof(float) * (2 * d * fp + 2 * fp + 2 * fp * mix + 2 * mix + mix * n_head_out + n_head_out +
                                        (fp2 > 0 ? fp2 : 0) + K6_WARPS * 4 * K6_MAXV);
-  IMP_CUDA(cudaFuncSetAttribute(pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-  IMP_REQUIRE(smem <= 96 * 1024, IMP_ERR_DIM, "%s: readout weights need %zu B of shared memory", who, smem);
+  IMP_CUDA(cudaFuncSetAttribute(pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  IMP_REQUIRE(smem <= 200 * 1024, IMP_ERR_DIM, "%s: readout weights need %zu B of shared memory", who, smem);
   int blocks = (int)ceil_div(g->n_pairs, K6_WARPS);
   if (blocks > 148 * 8) blocks = 148 * 8;
   pool_head_kernel<<<blocks, K6_WARPS * 32, smem, (cudaStream_t)stream>>>(a);

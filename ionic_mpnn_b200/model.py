@@ -276,7 +276,12 @@ class MPNNModel(TrainMixin):
             else:
                 _lib.call("imp_message_agg", C.byref(g), h[i].data_ptr(), d, self.table_ptr(0, i, True),
                           self.table_ptr(1, i, True), aggs[i].data_ptr(), st)
-            if self.precision == "fp32":
+            if self.precision == "fp32" and d > 64:  # wide atom states: tiled-GEMM GatedUpdate
+                wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
+                ws = self._buf("gru_wide_ws", 3 * N * d)
+                _lib.call("imp_gated_update_wide", h[i].data_ptr(), aggs[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc),
+                          C.byref(wa), C.c_float(self.LN_EPS), h[i + 1].data_ptr(), ws.data_ptr(), st)
+            elif self.precision == "fp32":
                 wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
                 _lib.call("imp_gated_update", h[i].data_ptr(), aggs[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc),
                           C.byref(wa), C.c_float(self.LN_EPS), h[i + 1].data_ptr(), st)

@@ -201,3 +201,23 @@ def test_argument_errors_are_loud():
     empty = graph.pack_records([], 72)
     empty.temperature = np.zeros(0, np.float32)
     assert mp.predict(empty).shape == (0, 1)
+
+
+@pytest.mark.parametrize("atom_dim,num_steps,n_min,n_max", [(256, 6, 20, 40), (128, 3, 40, 120)])
+def test_wide_variant_matches_fp64_oracle(atom_dim, num_steps, n_min, n_max):
+    """BASELINE configs[4] shape (atom_dim 256, 6 steps; larger ions at atom_dim 128): the wide fp32 path
+    (message kernels at D = 128 / 256, imp_gated_update_wide) against the oracle."""
+    from ionic_mpnn_b200 import synth
+    from ionic_mpnn_b200.viscosity import build_model
+    from oracle import ref_inputs, ref_model
+
+    recs = synth.make_records(6, seed=4, n_min=n_min, n_max=n_max)
+    spec = ref_model.make_spec("viscosity", atom_dim=atom_dim, num_steps=num_steps)
+    params = ref_model.init_params(spec, seed=2, trained_like=True)
+    want = ref_model.predict(spec, params, ref_inputs.build_inputs(recs), batch_size=2)
+    model = build_model(124, 72, atom_dim=atom_dim, num_steps=num_steps)
+    model.set_weights(params)
+    got = model.predict(recs)
+    err = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0)))
+    print(f"wide d={atom_dim} S={num_steps}: max rel err {err:.3e}")
+    assert err <= 2e-5, err

@@ -452,6 +452,104 @@ __global__ void __launch_bounds__(K6_WARPS * 32) pool_head_kernel(K6Args a) {
   }
 }
 
+
+// ----------------------------------------------------------------------------------------- K6, fast form
+// Readout on pooled sums for d, fp, mix, fp2 <= 32 (both reference models): lane o keeps column o of every Dense kernel
+// in REGISTERS for the whole kernel, so a multiply-accumulate costs one broadcast shared-memory read per four FMAs
+// instead of two reads per FMA.  Same arithmetic and summation order as pool_head_kernel.
+constexpr int R32_WARPS = 8;
+__global__ void __launch_bounds__(R32_WARPS * 32) readout32_kernel(K6Args a) {
+  __shared__ __align__(16) float sx[R32_WARPS][4][32];  // per warp: pool, v1, v2 (one tower at a time), mixed
+  const int d = a.d, fp = a.fp, mix = a.mix, fp2 = a.fp2, nh = fp2 > 0 ? fp2 : 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float wfp[2][32], wmx[2][32], w1[32];
+  float bfp[2], bmx[2], b1v, w2v = 0.f;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const imp_readout_weights_t& w = t == 0 ? a.wc : a.wa;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      wfp[t][k] = (k < d && lane < fp) ? w.W_fp[k * fp + lane] : 0.f;
+      wmx[t][k] = (k < fp && lane < mix) ? w.W_mix[k * mix + lane] : 0.f;
+    }
+    bfp[t] = lane < fp ? w.b_fp[lane] : 0.f;
+    bmx[t] = lane < mix ? w.b_mix[lane] : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 32; ++k) w1[k] = (k < mix && lane < nh) ? a.W1[k * nh + lane] : 0.f;
+  b1v = lane < nh ? a.b1[lane] : 0.f;
+  if (fp2 > 0 && lane < fp2) w2v = a.W2[lane];
+  float* pool = sx[warp][0];
+  float* v1 = sx[warp][1];
+  float* mixed = sx[warp][3];
+  const int warp_global = blockIdx.x * R32_WARPS + warp, n_warps = gridDim.x * R32_WARPS;
+  // the pooled rows (and temperature) of the NEXT pair are in flight while the current pair computes
+  float nx[2] = {0.f, 0.f}, nT = 0.f;
+  if (warp_global < a.n_pairs) {
+    nx[0] = lane < d ? __ldg(a.pooled + (int64_t)warp_global * d + lane) : 0.f;
+    nx[1] = lane < d ? __ldg(a.pooled + (int64_t)(a.n_pairs + warp_global) * d + lane) : 0.f;
+    if (fp2 == 0) nT = __ldg(a.T + warp_global);
+  }
+  for (int pair = warp_global; pair < a.n_pairs; pair += n_warps) {
+    const float cx[2] = {nx[0], nx[1]};
+    const float cT = nT;
+    const int np = pair + n_warps;
+    if (np < a.n_pairs) {
+      nx[0] = lane < d ? __ldg(a.pooled + (int64_t)np * d + lane) : 0.f;
+      nx[1] = lane < d ? __ldg(a.pooled + (int64_t)(a.n_pairs + np) * d + lane) : 0.f;
+      if (fp2 == 0) nT = __ldg(a.T + np);
+    }
+    float mixv = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      pool[lane] = cx[t];
+      __syncwarp();
+      float acc = bfp[t];
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        const float4 x = *reinterpret_cast<const float4*>(pool + 4 * k4);
+        acc = fmaf(x.x, wfp[t][4 * k4], acc), acc = fmaf(x.y, wfp[t][4 * k4 + 1], acc);
+        acc = fmaf(x.z, wfp[t][4 * k4 + 2], acc), acc = fmaf(x.w, wfp[t][4 * k4 + 3], acc);
+      }
+      v1[lane] = lane < fp ? fmaxf(acc, 0.f) : 0.f;
+      __syncwarp();
+      acc = bmx[t];
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        const float4 x = *reinterpret_cast<const float4*>(v1 + 4 * k4);
+        acc = fmaf(x.x, wmx[t][4 * k4], acc), acc = fmaf(x.y, wmx[t][4 * k4 + 1], acc);
+        acc = fmaf(x.z, wmx[t][4 * k4 + 2], acc), acc = fmaf(x.w, wmx[t][4 * k4 + 3], acc);
+      }
+      const float v2 = lane < mix ? fmaxf(acc, 0.f) : 0.f;
+      mixv = t == 0 ? v2 : mixv + v2;
+      __syncwarp();
+    }
+    mixed[lane] = mixv;
+    __syncwarp();
+    float hp = b1v;
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+      const float4 x = *reinterpret_cast<const float4*>(mixed + 4 * k4);
+      hp = fmaf(x.x, w1[4 * k4], hp), hp = fmaf(x.y, w1[4 * k4 + 1], hp);
+      hp = fmaf(x.z, w1[4 * k4 + 2], hp), hp = fmaf(x.w, w1[4 * k4 + 3], hp);
+    }
+    if (fp2 == 0) {
+      const float p0 = __shfl_sync(0xffffffffu, hp, 0), p1 = __shfl_sync(0xffffffffu, hp, 1), p2 = __shfl_sync(0xffffffffu, hp, 2);
+      if (lane == 0) {
+        const float B = fminf(fmaxf(softplusf_precise(p1), 0.0f), 20.0f);
+        const float Cc = fminf(fmaxf(softplusf_precise(p2), 0.1f), 50.0f);
+        a.out[pair] = p0 + B / (cT / 100.0f + Cc + 1e-6f);
+      }
+    } else {
+      const float part = lane < fp2 ? fmaxf(hp, 0.f) * w2v : 0.f;
+      float tot = 0.f;
+      for (int l = 0; l < 32; ++l) tot += __shfl_sync(0xffffffffu, part, l);  // fixed order
+      if (lane == 0) a.out[pair] = tot + a.b2[0];
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace imp
 
 // =========================================================================================== ABI
@@ -637,6 +735,13 @@ static int launch_k6(const imp_graph_t* g, const float* d_h, const float* d_pool
                                        (fp2 > 0 ? fp2 : 0) + K6_WARPS * 4 * K6_MAXV);
   IMP_CUDA(cudaFuncSetAttribute(pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   IMP_REQUIRE(smem <= 200 * 1024, IMP_ERR_DIM, "%s: readout weights need %zu B of shared memory", who, smem);
+  if (d_pooled && !aux && d <= 32 && fp <= 32 && mix <= 32 && fp2 <= 32) {  // both reference models: register-resident weights
+    int nb = (int)ceil_div(g->n_pairs, R32_WARPS);
+    if (nb > 148 * 6) nb = 148 * 6;
+    readout32_kernel<<<nb, R32_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    IMP_LAUNCH_CHECK();
+    return 0;
+  }
   int blocks = (int)ceil_div(g->n_pairs, K6_WARPS);
   if (blocks > 148 * 8) blocks = 148 * 8;
   pool_head_kernel<<<blocks, K6_WARPS * 32, smem, (cudaStream_t)stream>>>(a);

@@ -85,6 +85,19 @@ typedef struct {
 int imp_pack_host(const imp_ions_t* cation, const imp_ions_t* anion, int32_t bond_vocab, int32_t max_edges,
                   int32_t flags, int32_t edge_capacity, imp_graph_t* out, int32_t n_threads);
 
+/* Device packer (same contract and bit-identical mol_ptr / atom_id / row_ptr / col_src / edge_bm as imp_pack_host; the
+ * bond-bucket permutation of the staged message / training kernels is NOT produced).  `cation` / `anion` hold DEVICE
+ * pointers; n_cat_atoms / n_atoms are the host-known totals (atom_ptr[P] of each tower).  Optional compact-feed outputs
+ * (d_mol_eptr[2P+1], d_atom_w[N], d_edge_w[capacity]; see imp_compact_graph_t) may be NULL.  Enqueue-only: the four
+ * int32 of d_counts receive n_unique, a status (0 or an IMP_ERR_* code: index out of range, a molecule with more than
+ * 512 doubled entries or 1024 atoms, capacity exceeded) and the 64-bit sum of multiplicities; the caller reads them
+ * back after synchronising.  d_workspace: imp_pack_device_workspace_bytes(n_pairs). */
+int64_t imp_pack_device_workspace_bytes(int32_t n_pairs);
+int imp_pack_device(const imp_ions_t* cation, const imp_ions_t* anion, int32_t n_cat_atoms, int32_t n_atoms,
+                    int32_t bond_vocab, int32_t max_edges, int32_t flags, int32_t edge_capacity, imp_graph_t* out,
+                    int32_t* d_mol_eptr, uint16_t* d_atom_w, uint32_t* d_edge_w, int32_t* d_counts, void* d_workspace,
+                    void* stream);
+
 /* Benchmark-sized synthetic ions (recipe of SURVEY 8d; splitmix64 stream, see synth.py).  Two-phase:
  * call with all output pointers NULL to get *n_atoms / *n_entries, then again with buffers. */
 int imp_synth_ions(uint64_t seed, int32_t n_ions, int32_t n_min, int32_t n_max, int32_t atom_types,

@@ -62,6 +62,9 @@ SIGNATURES = {
     "imp_device_is_sm100": (C.c_int, []),
     "imp_pack_host": (C.c_int, [C.POINTER(Ions), C.POINTER(Ions), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.POINTER(Graph), C.c_int32]),
+    "imp_pack_device_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "imp_pack_device": (C.c_int, [C.POINTER(Ions), C.POINTER(Ions), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int32, C.POINTER(Graph), vp, vp, vp, vp, vp, vp]),
     "imp_synth_ions": (C.c_int, [C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp,
                                  vp, vp, vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "imp_embed_atoms": (C.c_int, [vp, C.c_int32, vp, C.c_int32, C.c_int32, vp, vp]),

@@ -311,3 +311,100 @@ def synth_batch(n_pairs, seed, n_min=10, n_max=40, skewed=False, bond_vocab_size
     if with_temperature:
         T = np.random.default_rng(seed).uniform(273.15, 373.15, size=n_pairs).astype(np.float32)
     return pack_flat(cat, an, bond_vocab_size, temperature=T), cat, an
+
+
+ION_FIELDS = ("atom_ptr", "atom_ids", "edge_ptr", "edge_src", "edge_dst", "bond_ids")
+
+
+class DevicePackedBatch:
+    """A batch packed ON the device by imp_pack_device: int32 CSR arrays + the compact feed, no host copy and no
+    bond buckets (forward only: fused kernel, fp32 staged kernels with fused messages).  Quacks like a PackedGraphBatch
+    on the device side; ``as_compact()`` returns the view that routes through imp_mpnn_forward_fused_compact."""
+
+    is_compact = False
+
+    def __init__(self, dev, counts, max_mol_atoms, dev_T=None):
+        self.dev, self.dev_T, self.dev_y = dev, dev_T, None
+        self.n_pairs, self.n_atoms, self.n_cat_atoms, self.n_unique, self.n_edges, self.bond_vocab = counts
+        self.max_mol_atoms = max_mol_atoms
+
+    def c_struct(self):
+        ptr = lambda k: self.dev[k].data_ptr() if k in self.dev else 0  # noqa: E731
+        return _lib.Graph(self.n_pairs, self.n_atoms, self.n_cat_atoms, self.n_unique, self.n_edges, self.bond_vocab,
+                          *(ptr(k) for k in GRAPH_FIELDS))
+
+    def compact_struct(self):
+        return _lib.CompactGraph(self.n_pairs, self.n_atoms, self.n_cat_atoms, self.n_unique, self.n_edges, self.bond_vocab,
+                                 *(self.dev[k].data_ptr() for k in COMPACT_FIELDS))
+
+    def as_compact(self):
+        import copy
+
+        c = copy.copy(self)
+        c.is_compact = True
+        return c
+
+    def to(self, device):
+        return self
+
+
+def upload_ions(cation: FlatIons, anion: FlatIons, device="cuda", pin=False):
+    """H2D copy of the flat ragged ion arrays of both towers (optionally through pinned staging buffers)."""
+    import torch
+
+    dev = torch.device(device)
+    out = {}
+    for t, ions in (("cat", cation), ("an", anion)):
+        out[t] = {}
+        for f in ION_FIELDS:
+            src = torch.from_numpy(getattr(ions, f))
+            if pin:
+                src = src.pin_memory()
+            out[t][f] = src.to(dev, non_blocking=True)
+    return out
+
+
+def pack_flat_device(cation: FlatIons, anion: FlatIons, bond_vocab_size, device="cuda", max_edges=None, double_edges=True,
+                     shift_ids=True, temperature=None, compact=True, stream=None, uploaded=None):
+    """Uploads the flat ragged ion arrays (unless ``uploaded`` = upload_ions(...) is given) and builds the packed batch
+    on the GPU (imp_pack_device).  One host synchronisation at the end to read the counts / status back."""
+    import torch
+
+    assert cation.n_ions == anion.n_ions
+    dev = torch.device(device)
+    P = cation.n_ions
+    n_cat, n_an = int(cation.atom_ptr[-1]), int(anion.atom_ptr[-1])
+    N = n_cat + n_an
+    cap = (int(cation.edge_ptr[-1]) + int(anion.edge_ptr[-1])) * (2 if double_edges else 1)
+    up = uploaded if uploaded is not None else upload_ions(cation, anion, dev)
+    cs = _lib.Ions(P, *(up["cat"][f].data_ptr() for f in ION_FIELDS))
+    an = _lib.Ions(P, *(up["an"][f].data_ptr() for f in ION_FIELDS))
+    i32 = dict(dtype=torch.int32, device=dev)
+    out = {"mol_ptr": torch.empty(2 * P + 1, **i32), "atom_id": torch.empty(max(N, 1), **i32),
+           "row_ptr": torch.empty(N + 1, **i32), "col_src": torch.empty(max(cap, 1), **i32),
+           "edge_bm": torch.empty(max(cap, 1), **i32)}
+    if compact:
+        out["mol_eptr"] = torch.empty(2 * P + 1, **i32)
+        out["atom_w"] = torch.empty(max(N, 1), dtype=torch.int16, device=dev)
+        out["edge_w"] = torch.empty(max(cap, 1), **i32)
+    counts = torch.zeros(4, **i32)
+    ws = torch.empty(int(_lib.load().imp_pack_device_workspace_bytes(P)), dtype=torch.uint8, device=dev)
+    g = _lib.Graph(0, 0, 0, 0, 0, 0, out["mol_ptr"].data_ptr(), out["atom_id"].data_ptr(), out["row_ptr"].data_ptr(),
+                   out["col_src"].data_ptr(), out["edge_bm"].data_ptr(), 0, 0)
+    flags = (_lib.PACK_DOUBLE_EDGES if double_edges else 0) | (_lib.PACK_SHIFT_IDS if shift_ids else 0)
+    st = C.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+    opt = lambda k: out[k].data_ptr() if compact else None  # noqa: E731
+    _lib.call("imp_pack_device", C.byref(cs), C.byref(an), n_cat, N, bond_vocab_size, -1 if max_edges is None else int(max_edges),
+              flags, cap, C.byref(g), opt("mol_eptr"), opt("atom_w"), opt("edge_w"), counts.data_ptr(), ws.data_ptr(), st)
+    c = counts.cpu().numpy()  # synchronises
+    if c[1] != 0:
+        raise _lib.ImpError(f"imp_pack_device: device packer reported error {int(c[1])} "
+                            "(-3 index out of range, -4 molecule too large for the device packer / capacity, -2 compact range)")
+    n_unique = int(c[0])
+    n_edges = int(np.uint32(c[2])) | (int(np.uint32(c[3])) << 32)
+    for k in ("col_src", "edge_bm", "edge_w"):
+        if k in out:
+            out[k] = out[k][: max(n_unique, 1)]
+    sizes = np.concatenate([np.diff(cation.atom_ptr), np.diff(anion.atom_ptr)]) if P else np.zeros(0, I32)
+    dev_T = None if temperature is None else torch.from_numpy(np.ascontiguousarray(temperature, np.float32)).to(dev)
+    return DevicePackedBatch(out, (P, N, n_cat, n_unique, n_edges, bond_vocab_size), int(sizes.max()) if P else 0, dev_T)

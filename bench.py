@@ -127,6 +127,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic(kernel, pairs):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of the SAME launch size
+    (profiles/r01_fused_traffic.json); None when there is no capture for this size."""
+    p = os.path.join(ROOT, "profiles", "r01_fused_traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if d.get("kernel") == kernel and d.get("pairs_per_launch") == pairs:
+            return d["dram_bytes_read"] + d["dram_bytes_write"], d["source"]
+    return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -491,8 +502,10 @@ def run_b200(args):
                 # the fused kernel keeps every activation on chip: 2.7 kFLOP per byte of index stream, far right of
                 # the ridge (211 FLOP/B) => the tensor roofline is the one that bounds it
                 ach = sf[dom] / (mean_ms[dom] * 1e-3) / 1e12
+                traffic, traffic_src = ncu_traffic(dom, P)
                 roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                            "frac": ach / tf_peak, "traffic": None, "peak_source": peak_src + ", sustained bf16",
+                            "frac": ach / tf_peak, "traffic": traffic, "traffic_source": traffic_src,
+                            "peak_source": peak_src + ", sustained bf16",
                             "algorithmic_flop_per_launch": sf[dom], "algorithmic_bytes_per_launch": sb[dom],
                             "hbm_GBps_on_algorithmic_bytes": sb[dom] / (mean_ms[dom] * 1e-3) / 1e9,
                             "hbm_frac": sb[dom] / (mean_ms[dom] * 1e-3) / 1e9 / hbm_peak}

@@ -512,7 +512,33 @@ __global__ void __launch_bounds__(DT_CHUNK_THREADS) dtable_partial_kernel(const 
   const int l = threadIdx.x / (D / 4), mq = threadIdx.x % (D / 4);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const int e1 = chunk_end[blockIdx.x];
-  for (int i = chunk_begin[blockIdx.x]; i < e1; ++i) {
+  int i = chunk_begin[blockIdx.x];
+  // four entries per iteration: the index chain (perm -> dst / src -> rows) of all four is in flight together;
+  // the accumulation order stays the chunk order (bit-reproducible)
+  for (; i + 4 <= e1; i += 4) {
+    int e[4], dst[4], src[4];
+    float mult[4], gv[4];
+    float4 hv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) e[u] = __ldg(bucket_perm + i + u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      dst[u] = __ldg(entry_dst + e[u]);
+      src[u] = __ldg(col_src + e[u]);
+      mult[u] = (float)(__ldg(edge_bm + e[u]) >> 16);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      gv[u] = mult[u] * __ldg(g + (int64_t)dst[u] * D + l);
+      hv[u] = __ldg(reinterpret_cast<const float4*>(h + (int64_t)src[u] * D) + mq);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc.x = fmaf(gv[u], hv[u].x, acc.x), acc.y = fmaf(gv[u], hv[u].y, acc.y);
+      acc.z = fmaf(gv[u], hv[u].z, acc.z), acc.w = fmaf(gv[u], hv[u].w, acc.w);
+    }
+  }
+  for (; i < e1; ++i) {
     const int e = __ldg(bucket_perm + i);
     const int dst = __ldg(entry_dst + e), src = __ldg(col_src + e);
     const float mult = (float)(__ldg(edge_bm + e) >> 16);

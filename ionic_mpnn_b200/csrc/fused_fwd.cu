@@ -123,7 +123,7 @@ struct FusedArgs {
   const unsigned short* atom_w;    // [N] atom id | in-degree << 8
   const unsigned int* edge_w;      // [Eu] src (molecule-local) | bond << 8 | multiplicity << 16
   long long* prof;  // FZ_PROFILE builds only
-  int debug;        // timing experiments only (results are wrong): 1 = skip the entry loop, 2 = skip MMAs and their waits
+  int debug;        // FZ_PROFILE builds only (timing ablations, results are wrong): 1 = skip the entry loop, 2 = skip MMAs
 };
 
 struct alignas(16) FusedWgSmem {
@@ -457,6 +457,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // Optional phase timing (compile with -DFZ_PROFILE): per-phase clock64 deltas of selected threads, summed into
 // a.prof[thread-class][18] (thread classes: u == 0, u == 96 (warp 3), u == 224 (warp 7)); read by tools/fused_phase_profile.py.
 #ifdef FZ_PROFILE
+#define FZ_DEBUG(a) ((a).debug)
 #define FZ_PROF_DECL                                                                     \
   long long prof_acc[18];                                                                \
   for (int i_ = 0; i_ < 18; ++i_) prof_acc[i_] = 0;                                      \
@@ -472,6 +473,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
   if (prof_cls >= 0 && a.prof)                                                                               \
     for (int i_ = 0; i_ < 18; ++i_) atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + prof_cls * 18 + i_, (unsigned long long)prof_acc[i_])
 #else
+#define FZ_DEBUG(a) 0
 #define FZ_PROF_DECL
 #define FZ_PROF_T(i)
 #define FZ_PROF_FLUSH
@@ -596,7 +598,7 @@ __global__ void __launch_bounds__(2 * F2_CTX_THREADS, 1) mpnn_fused_h2_kernel(co
       tc::named_bar_sync(bar_id, F2_CTX_THREADS);
       // ---------------------------------------------------------------- this thread owns columns [16 hf, 16 hf + 16) of row r
       const int r = ws.rowof[p];
-      const int e0 = ws.se0[r], e1 = (a.debug & 1) ? e0 : ws.se1[r];
+      const int e0 = ws.se0[r], e1 = (FZ_DEBUG(a) & 1) ? e0 : ws.se1[r];
       uint32_t* hbrow = &ws.hb[r * FZ_HS + hf * DH];
       float h[DH];
       {  // Embedding(atom)
@@ -668,7 +670,7 @@ __global__ void __launch_bounds__(2 * F2_CTX_THREADS, 1) mpnn_fused_h2_kernel(co
         tc::named_bar_sync(bar_id, F2_CTX_THREADS);
         FZ_PROF_T(4);
         // ------------------------------------------------------------ GEMM1: agg = Z . Wc
-        if (mma_warp && !(a.debug & 2)) {
+        if (mma_warp && !(FZ_DEBUG(a) & 2)) {
           tc::fence_after_thread_sync();
           if (tc::elect_one()) {
 #pragma unroll
@@ -678,7 +680,7 @@ __global__ void __launch_bounds__(2 * F2_CTX_THREADS, 1) mpnn_fused_h2_kernel(co
           }
           __syncwarp();
         }
-        if (!(a.debug & 2)) tc::mbar_wait(&ws.bar[0], ph);
+        if (!(FZ_DEBUG(a) & 2)) tc::mbar_wait(&ws.bar[0], ph);
         tc::fence_after_thread_sync();
         FZ_PROF_T(5);
         {
@@ -698,7 +700,7 @@ __global__ void __launch_bounds__(2 * F2_CTX_THREADS, 1) mpnn_fused_h2_kernel(co
         tc::named_bar_sync(bar_id, F2_CTX_THREADS);
         FZ_PROF_T(7);
         // ------------------------------------------------------------ GEMM2 / GEMM3a
-        if (mma_warp && !(a.debug & 2)) {
+        if (mma_warp && !(FZ_DEBUG(a) & 2)) {
           tc::fence_after_thread_sync();
           if (tc::elect_one()) {
 #pragma unroll
@@ -710,7 +712,7 @@ __global__ void __launch_bounds__(2 * F2_CTX_THREADS, 1) mpnn_fused_h2_kernel(co
           }
           __syncwarp();
         }
-        if (!(a.debug & 2)) tc::mbar_wait(&ws.bar[1], ph);
+        if (!(FZ_DEBUG(a) & 2)) tc::mbar_wait(&ws.bar[1], ph);
         tc::fence_after_thread_sync();
         FZ_PROF_T(8);
         float z[DH];
@@ -735,7 +737,7 @@ __global__ void __launch_bounds__(2 * F2_CTX_THREADS, 1) mpnn_fused_h2_kernel(co
         tc::named_bar_sync(bar_id, F2_CTX_THREADS);
         FZ_PROF_T(10);
         // ------------------------------------------------------------ GEMM3b
-        if (mma_warp && !(a.debug & 2)) {
+        if (mma_warp && !(FZ_DEBUG(a) & 2)) {
           tc::fence_after_thread_sync();
           if (tc::elect_one()) {
 #pragma unroll
@@ -744,7 +746,7 @@ __global__ void __launch_bounds__(2 * F2_CTX_THREADS, 1) mpnn_fused_h2_kernel(co
           }
           __syncwarp();
         }
-        if (!(a.debug & 2)) tc::mbar_wait(&ws.bar[2], ph);
+        if (!(FZ_DEBUG(a) & 2)) tc::mbar_wait(&ws.bar[2], ph);
         tc::fence_after_thread_sync();
         FZ_PROF_T(11);
         {  // candidate, blend, LayerNorm, residual  (models/layers.py:151-156)
@@ -988,7 +990,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
         }
       // ---------------------------------------------------------------- thread t owns row r
       const int r = ws.rowof[t];
-      const int e0 = ws.se0[r], e1 = (a.debug & 1) ? e0 : ws.se1[r];
+      const int e0 = ws.se0[r], e1 = (FZ_DEBUG(a) & 1) ? e0 : ws.se1[r];
       uint32_t* hbrow = &ws.hb[r * FZ_HS];
       int mbase = 0;  // COMPACT: first row of the molecule that owns row r (entries carry molecule-local sources)
       if (COMPACT)
@@ -1092,7 +1094,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
               }
             }
           }
-          if (hz == 1 && !(a.debug & 2)) {  // GEMM1a must have consumed the first half before its columns are rewritten
+          if (hz == 1 && !(FZ_DEBUG(a) & 2)) {  // GEMM1a must have consumed the first half before its columns are rewritten
             tc::mbar_wait(&ws.bar[3], ph);
             tc::fence_after_thread_sync();
           }
@@ -1106,7 +1108,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
           tc::tmem_wait_st();
           tc::fence_before_thread_sync();
           tc::named_bar_sync(bar_id, F3_CTX_THREADS);
-          if (mma_warp && !(a.debug & 2)) {
+          if (mma_warp && !(FZ_DEBUG(a) & 2)) {
             tc::fence_after_thread_sync();
             if (tc::elect_one()) {
 #pragma unroll
@@ -1118,7 +1120,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
             __syncwarp();
           }
         }
-        if (!(a.debug & 2)) tc::mbar_wait(&ws.bar[0], ph);
+        if (!(FZ_DEBUG(a) & 2)) tc::mbar_wait(&ws.bar[0], ph);
         tc::fence_after_thread_sync();
         {  // agg and h as 16-bit A operands
           float v[32];
@@ -1137,7 +1139,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
         tc::fence_before_thread_sync();
         tc::named_bar_sync(bar_id, F3_CTX_THREADS);
         // ------------------------------------------------------------ GEMM2: 0.5 ([h | agg | 1] . [Wz | Wr ; bz | br])
-        if (mma_warp && !(a.debug & 2)) {
+        if (mma_warp && !(FZ_DEBUG(a) & 2)) {
           tc::fence_after_thread_sync();
           if (tc::elect_one()) {
 #pragma unroll
@@ -1147,7 +1149,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
           }
           __syncwarp();
         }
-        if (!(a.debug & 2)) tc::mbar_wait(&ws.bar[1], ph);
+        if (!(FZ_DEBUG(a) & 2)) tc::mbar_wait(&ws.bar[1], ph);
         tc::fence_after_thread_sync();
         float z[D];
         {
@@ -1169,7 +1171,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
         tc::fence_before_thread_sync();
         tc::named_bar_sync(bar_id, F3_CTX_THREADS);
         // ------------------------------------------------------------ GEMM3: [agg | r*h] . [Wh[d:2d] ; Wh[0:d]]
-        if (mma_warp && !(a.debug & 2)) {
+        if (mma_warp && !(FZ_DEBUG(a) & 2)) {
           tc::fence_after_thread_sync();
           if (tc::elect_one()) {
 #pragma unroll
@@ -1180,7 +1182,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
           }
           __syncwarp();
         }
-        if (!(a.debug & 2)) tc::mbar_wait(&ws.bar[2], ph);
+        if (!(FZ_DEBUG(a) & 2)) tc::mbar_wait(&ws.bar[2], ph);
         tc::fence_after_thread_sync();
         {  // candidate, blend, LayerNorm (biased variance, eps), residual  (models/layers.py:151-156)
           float gq[32];
@@ -1336,7 +1338,12 @@ static int fused_forward_impl(const imp_graph_t* g, const imp_compact_graph_t* c
   a.prof = nullptr;
   a.mol_eptr = nullptr, a.atom_w = nullptr, a.edge_w = nullptr;
   if (compact) a.mol_eptr = cg->mol_eptr, a.atom_w = cg->atom_w, a.edge_w = cg->edge_w;
-  a.debug = (flags >> 8) & 0xff;
+#ifdef FZ_PROFILE
+  a.debug = (flags >> 8) & 0xff;  // timing ablations, profiling builds only
+#else
+  a.debug = 0;
+  IMP_REQUIRE((flags >> 8) == 0, IMP_ERR_ARG, "imp_mpnn_forward_fused: unknown flag bits 0x%x", flags & ~0xff);
+#endif
 #ifdef FZ_PROFILE
   a.prof = reinterpret_cast<long long*>(d_status);  // profiling build: d_status must hold 3 * 18 int64 (zeroed by the caller)
   a.status = nullptr;

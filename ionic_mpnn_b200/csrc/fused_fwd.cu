@@ -899,6 +899,8 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
   const int cta_in_tower = tower ? (int)blockIdx.x - a.n_cta_cat : (int)blockIdx.x;
   const float4* emb4 = reinterpret_cast<const float4*>(a.atom_emb);
   uint32_t ph = 0;
+  const int u = t;
+  FZ_PROF_DECL;
 
   for (int g = cta_in_tower * NCTX + ctx; g < n_groups; g += n_cta_tower * NCTX) {
     const int m0 = g * FZ_GROUP, nm = min(FZ_GROUP, P - m0);
@@ -919,6 +921,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
         if (t == 0 && a.status) *a.status = 1;
         rows = FZ_ROWS;
       }
+      FZ_PROF_T(0);
       // ---------------------------------------------------------------- natural row t: indices, in-degree key
       int key, rank = 0;
       {
@@ -959,7 +962,9 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
         }
         if (lane < 8) ws.cnt[wq][lane] = mine;
       }
+      FZ_PROF_T(1);
       tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+      FZ_PROF_T(2);
       {
         int off = 0;
 #pragma unroll
@@ -971,31 +976,36 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
         const int slot = off + rank;
         ws.rowof[descending ? FZ_ROWS - 1 - slot : slot] = (unsigned char)t;
       }
+      FZ_PROF_T(3);
       tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+      FZ_PROF_T(4);
       // ---------------------------------------------------------------- decoded entries of the tile -> shared memory
       const int E0 = ws.se0[0], n_ent = ws.se1[max(rows, 1) - 1] - E0;
       const bool staged = n_ent <= F3_ECAP && a.bond_vocab <= 256;
       if (staged)
         for (int i = t; i < n_ent; i += F3_CTX_THREADS) {
-          if (!COMPACT) {
+          if (COMPACT) {  // molecule-local source -> tile row: the entry's molecule is found from the entry offsets
+            const uint32_t w = __ldg(a.edge_w + E0 + i);
+            int mrow = 0;
+            for (int mi = ms; mi < me; ++mi)
+              if (ws.mole[mi] <= E0 + i) mrow = ws.molp[mi] - a0;
+            const uint32_t src = (uint32_t)min((int)(w & 0xffu) + mrow, FZ_ROWS - 1);
+            const uint32_t bond = min((w >> 8) & 0xffu, (uint32_t)(a.bond_vocab - 1));
+            ws.ent[i] = src | (bond << 8) | ((uint32_t)__half_as_ushort(__float2half_rn((float)((w >> 16) & 0xffu))) << 16);
+            continue;
+          }
+          {
             const int bm = __ldg(a.edge_bm + E0 + i);
             const int src = min(max(__ldg(a.col_src + E0 + i) - a0, 0), FZ_ROWS - 1);
             const int bond = min(bm & 0xffff, a.bond_vocab - 1);
             ws.ent[i] = (uint32_t)src | ((uint32_t)bond << 8) | ((uint32_t)__half_as_ushort(__float2half_rn((float)(bm >> 16))) << 16);
-          } else {  // src stays molecule-local here; the row owner adds its molecule's first row
-            const uint32_t w = __ldg(a.edge_w + E0 + i);
-            const uint32_t bond = min((w >> 8) & 0xffu, (uint32_t)(a.bond_vocab - 1));
-            ws.ent[i] = (w & 0xffu) | (bond << 8) | ((uint32_t)__half_as_ushort(__float2half_rn((float)((w >> 16) & 0xffu))) << 16);
           }
         }
+      FZ_PROF_T(5);
       // ---------------------------------------------------------------- thread t owns row r
       const int r = ws.rowof[t];
       const int e0 = ws.se0[r], e1 = (FZ_DEBUG(a) & 1) ? e0 : ws.se1[r];
       uint32_t* hbrow = &ws.hb[r * FZ_HS];
-      int mbase = 0;  // COMPACT: first row of the molecule that owns row r (entries carry molecule-local sources)
-      if (COMPACT)
-        for (int mi = ms; mi < me; ++mi)
-          if (ws.molp[mi] - a0 <= r) mbase = ws.molp[mi] - a0;
       float h[D];
       {  // Embedding(atom)
         const bool valid = r < rows;
@@ -1019,7 +1029,9 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
           if (wq == 2) prefetch_l2(a.edge_w + min(en + lane * 32, a.n_unique - 1));
         }
       }
+      FZ_PROF_T(6);
       tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+      FZ_PROF_T(7);
 
       for (int s = 0; s < a.steps; ++s) {
         const uint64_t dstep = (uint64_t)(s * (FusedPack::BYTES / 16));
@@ -1041,7 +1053,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
               const __half2 mult = *reinterpret_cast<const __half2*>(&mbits);
               const __half2 c0 = __hmul2(*reinterpret_cast<const __half2*>(&cu.x), mult);
               const __half2 c1 = __hmul2(*reinterpret_cast<const __half2*>(&cu.y), mult);
-              const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[(COMPACT ? min((int)(ec & 0xff) + mbase, FZ_ROWS - 1) : (int)(ec & 0xff)) * FZ_HS]);
+              const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[(ec & 0xff) * FZ_HS]);
 #pragma unroll
               for (int q = 0; q < D / 8; ++q) {  // 8 columns per 16-byte read; HFMA2 broadcasts the low / high half
                 const uint4 hv = hp[q];
@@ -1059,6 +1071,10 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
               }
             }
           } else {
+            int mbase = 0;  // COMPACT: first row of the molecule that owns row r (recomputed here: rare path, no live register)
+            if (COMPACT)
+              for (int mi = ms; mi < me; ++mi)
+                if (ws.molp[mi] - a0 <= r) mbase = ws.molp[mi] - a0;
 #pragma unroll 1
             for (int e = e0; e < e1; ++e) {
               int bm, src;
@@ -1215,21 +1231,33 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
         tc::named_bar_sync(bar_id, F3_CTX_THREADS);
         ph ^= 1;
       }
+      FZ_PROF_T(8);
       // ---------------------------------------------------------------- GlobalSumPool
       {
         const float* hfp = reinterpret_cast<const float*>(ws.hb);
         for (int mi = ms + (t >> 5); mi < me; mi += 4) {
           const int lo = ws.molp[mi] - a0, hi = min(ws.molp[mi + 1] - a0, FZ_ROWS);
-          float sacc = 0.f;
-          for (int rr = lo; rr < hi; ++rr)
-            if (ws.amask[rr]) sacc += hfp[rr * FZ_HS + lane];
-          a.pooled[(size_t)(base_mol + mi) * D + lane] = sacc;
+          // four interleaved partial sums (rows lo+0, lo+4, ... etc.), combined in a fixed order: the row loop is a
+          // chain of dependent shared-memory loads and adds, and it sits on every tile's critical path
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          int rr = lo;
+          for (; rr + 4 <= hi; rr += 4) {
+            const float v0 = hfp[rr * FZ_HS + lane], v1 = hfp[(rr + 1) * FZ_HS + lane];
+            const float v2 = hfp[(rr + 2) * FZ_HS + lane], v3 = hfp[(rr + 3) * FZ_HS + lane];
+            const uchar4 mk = make_uchar4(ws.amask[rr], ws.amask[rr + 1], ws.amask[rr + 2], ws.amask[rr + 3]);
+            s0 += mk.x ? v0 : 0.f, s1 += mk.y ? v1 : 0.f, s2 += mk.z ? v2 : 0.f, s3 += mk.w ? v3 : 0.f;
+          }
+          for (; rr < hi; ++rr) s0 += ws.amask[rr] ? hfp[rr * FZ_HS + lane] : 0.f;
+          a.pooled[(size_t)(base_mol + mi) * D + lane] = (s0 + s1) + (s2 + s3);
         }
       }
+      FZ_PROF_T(9);
       tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+      FZ_PROF_T(10);
       ms = me;
     }
   }
+  FZ_PROF_FLUSH;
   tc::fence_before_thread_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<512>(ctl.tmem_base);

@@ -14,6 +14,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "tools", "_prof")
+PHASES_H2X = ["between tiles / group load", "index loads + ballots", "bar (sort 1)", "offsets + rowof", "bar (sort 2)",
+              "entry staging", "embedding + prefetch", "bar (tile ready)", "all steps", "pool", "bar (after pool)"] + ["-"] * 7
 PHASES = ["tile:idle/next", "sort+embed", "step:loop-top", "Z build", "bar after Z", "GEMM1 wait", "epi0 (agg,h->A)",
           "bar after epi0", "GEMM2 wait", "epi1 (z, r*h)", "bar after epi1", "GEMM3 wait", "epi2a (blend,sums)",
           "bar LN exchange", "epi2b (LN, h)", "bar end of step", "pool", "bar after pool"]
@@ -37,10 +39,12 @@ def main():
     _lib.LIB_PATH = lib
     from ionic_mpnn_b200.viscosity import build_model
 
-    pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+    pairs = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 262144
     batch, _, _ = graph.synth_batch(pairs, seed=1003)
     batch.to("cuda")
-    m = build_model(124, 72, precision="fp16", fused=True)
+    m = build_model(124, 72, precision="fp16", fused=True, num_steps=int(os.environ.get("FZ_STEPS", "4")))
+    if "--gen2" in sys.argv:
+        m.extra_tc_flags = _lib.TC_TWO_THREADS_PER_ROW
     m._ws["status"] = torch.zeros(3 * 18 * 2, dtype=torch.int32, device="cuda")
     for _ in range(2):
         m.forward_packed(batch)
@@ -49,11 +53,15 @@ def main():
     m.forward_packed(batch)
     torch.cuda.synchronize()
     prof = m._ws["status"].view(torch.int64).cpu().numpy().reshape(3, 18)
+    labels = PHASES if "--gen2" in sys.argv else PHASES_H2X
     for cls, name in enumerate(["u=0 (warp 0, issues MMAs)", "u=96 (warp 3)", "u=224 (warp 7)"]):
         tot = prof[cls].sum()
+        if tot == 0:
+            continue
         print(f"--- {name}: total {tot / 1e6:.1f} Mcycles over all CTAs/contexts")
-        for i, ph in enumerate(PHASES):
-            print(f"   {ph:22s} {100.0 * prof[cls][i] / tot:6.2f} %")
+        for i, ph in enumerate(labels):
+            if prof[cls][i]:
+                print(f"   {ph:28s} {100.0 * prof[cls][i] / tot:6.2f} %")
 
 
 if __name__ == "__main__":

@@ -117,3 +117,30 @@ def test_compact_feed_round_trips_the_csr():
     assert np.array_equal((c["edge_w"] & 0xFF).astype(np.int64) + base, h["col_src"])
     assert np.array_equal(((c["edge_w"] >> 8) & 0xFF) | ((c["edge_w"] >> 16) << 16), h["edge_bm"])
     assert b.nbytes_compact() < 0.5 * b.nbytes()
+
+
+def test_training_chunk_lists_partition_the_buckets():
+    """train.prepare_training's host-built structures (entry_dst, chunk list of the (tower, bond) buckets) without a GPU:
+    every bucket position is covered exactly once, in order, by chunks of at most DT_CHUNK entries."""
+    from ionic_mpnn_b200 import graph, train
+
+    b, _, _ = graph.synth_batch(400, seed=5)
+    rp = b.host["row_ptr"].astype(np.int64)
+    entry_dst = np.repeat(np.arange(b.n_atoms), np.diff(rp))
+    assert len(entry_dst) == b.n_unique and (np.diff(entry_dst) >= 0).all()
+    bp = b.host["bucket_ptr"].astype(np.int64)
+    sizes = np.diff(bp)
+    n_per = (sizes + train.DT_CHUNK - 1) // train.DT_CHUNK
+    bcp = np.concatenate([[0], np.cumsum(n_per)])
+    which = np.repeat(np.arange(len(sizes)), n_per)
+    idx = np.arange(bcp[-1]) - bcp[which]
+    begin = bp[which] + idx * train.DT_CHUNK
+    end = np.minimum(bp[which + 1], begin + train.DT_CHUNK)
+    covered = np.concatenate([np.arange(s, e) for s, e in zip(begin, end)]) if len(begin) else np.zeros(0, np.int64)
+    assert np.array_equal(covered, np.arange(bp[-1]))
+    assert (end - begin).max() <= train.DT_CHUNK and (end > begin).all()
+    # the bucket key of every chunk is the bucket it was cut from
+    key = (entry_dst[b.host["bucket_perm"]] >= b.n_cat_atoms) * b.bond_vocab + (b.host["edge_bm"][b.host["bucket_perm"]] & 0xFFFF)
+    for c in range(0, len(begin), max(1, len(begin) // 50)):
+        assert (key[begin[c]:end[c]] == which[c]).all()
+    assert train.l2_terms({"kind": "viscosity"}) == {"cat_fp.kernel": 1e-4, "an_fp.kernel": 1e-4}

@@ -216,3 +216,62 @@ class TrainMixin:
                   st["step"], _stream())
         self._tables_valid = False
         return loss
+
+    # ------------------------------------------------------------------------------------------ fit / evaluate
+    def evaluate(self, records, label=None):
+        """Keras ``model.evaluate``: mean squared error over ``records`` (src/dataset.py schema, labels under
+        ``label``) plus the l2 regularisation terms, with the current weights (fp32 kernels)."""
+        from .graph import pack_records
+
+        label = label or ("log_eta" if self.spec["kind"] == "viscosity" else "mp")
+        batch = pack_records(records, self.spec["bond_vocab_size"], label=label)
+        pred = self.forward_packed(batch.to(self.device))
+        y = batch.dev_y
+        mse = ((pred - y) ** 2).mean()
+        reg = sum(c * (self.params[k] ** 2).sum() for k, c in l2_terms(self.spec).items())
+        return float((mse + reg).item())
+
+    def fit(self, records, validation_data=None, epochs=1, batch_size=32, shuffle=True, patience=None,
+            restore_best_weights=True, label=None, seed=0, verbose=0, lr=1e-3, clipnorm=1.0):
+        """The reference's training loop (train_viscosity.py:328-338: ``model.fit(x, y, validation_data, epochs,
+        batch_size=32, callbacks=[EarlyStopping(monitor="val_loss", patience=50, restore_best_weights=True)])``) on
+        record lists: per epoch a fresh shuffle, mini-batches of ``batch_size`` (the last one may be smaller), one
+        ``train_step`` each; epoch loss = sample-weighted mean of the batch losses [Keras semantics]; ``val_loss`` =
+        ``evaluate(validation_data)`` at the end of the epoch; early stopping on ``val_loss`` with ``patience`` (None =
+        off), strict improvement, optional restore of the best epoch's weights.  Returns ``{"loss": [...],
+        "val_loss": [...]}`` like ``History.history``.  Mini-batches are packed on the host (imp_pack_host)."""
+        from .graph import pack_records
+
+        label = label or ("log_eta" if self.spec["kind"] == "viscosity" else "mp")
+        rng = np.random.default_rng(seed)
+        n = len(records)
+        hist = {"loss": [], "val_loss": []} if validation_data is not None else {"loss": []}
+        best, best_w, wait = float("inf"), None, 0
+        for epoch in range(epochs):
+            order = rng.permutation(n) if shuffle else np.arange(n)
+            tot, losses = 0, []
+            for lo in range(0, n, batch_size):
+                idx = order[lo:lo + batch_size]
+                batch = pack_records([records[i] for i in idx], self.spec["bond_vocab_size"], label=label)
+                losses.append((len(idx), self.train_step(batch.to(self.device), lr=lr, clipnorm=clipnorm)))
+                tot += len(idx)
+            hist["loss"].append(float(sum(k * float(l.item()) for k, l in losses) / max(tot, 1)))
+            if validation_data is not None:
+                v = self.evaluate(validation_data, label)
+                hist["val_loss"].append(v)
+                if v < best:
+                    best, wait = v, 0
+                    if restore_best_weights:
+                        best_w = self.flat.clone()
+                else:
+                    wait += 1
+                if verbose:
+                    print(f"Epoch {epoch + 1}/{epochs} - loss: {hist['loss'][-1]:.6f} - val_loss: {v:.6f}")
+                if patience is not None and wait >= patience:
+                    break
+            elif verbose:
+                print(f"Epoch {epoch + 1}/{epochs} - loss: {hist['loss'][-1]:.6f}")
+        if best_w is not None and restore_best_weights and validation_data is not None and hist["val_loss"][-1] > best:
+            self.flat.copy_(best_w)
+            self._tables_valid = False
+        return hist

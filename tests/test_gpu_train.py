@@ -102,3 +102,30 @@ def test_training_then_fused_inference_uses_new_weights():
     ref_after = model.forward_packed(batch).cpu().numpy()
     assert np.abs(after - before).max() > 1e-3
     assert np.abs(after - ref_after).max() <= 2e-2 * (np.abs(ref_after).max() + 1.0)
+
+
+def test_fit_loop_early_stopping_and_best_weight_restore():
+    """fit(): shuffled mini-batches of 32, sample-weighted epoch loss, val_loss per epoch, EarlyStopping(patience)
+    with restore_best_weights (train_viscosity.py:328-338)."""
+    from ionic_mpnn_b200 import synth
+    from ionic_mpnn_b200.model import MPNNModel
+    from oracle import ref_model
+
+    spec = ref_model.make_spec("viscosity")
+    train = synth.make_records(100, seed=11, label="log_eta")   # 3 batches of 32 + one of 4
+    val = synth.make_records(40, seed=12, label="log_eta")      # labels are noise: val_loss stops improving early
+    model = MPNNModel(spec, precision="fp32", seed=3)
+    v0 = model.evaluate(val)
+    hist = model.fit(train, validation_data=val, epochs=12, batch_size=32, patience=3, seed=1)
+    assert len(hist["loss"]) == len(hist["val_loss"]) <= 12
+    assert hist["loss"][-1] < hist["loss"][0]                    # the training loss goes down
+    assert min(hist["val_loss"]) < v0
+    stopped_early = len(hist["val_loss"]) < 12
+    if stopped_early:                                            # stopped `patience` epochs after the best one
+        assert len(hist["val_loss"]) - 1 - int(np.argmin(hist["val_loss"])) == 3
+    # restore_best_weights: the model now holds the weights of the best epoch
+    assert abs(model.evaluate(val) - min(hist["val_loss"])) <= 1e-5 * max(1.0, min(hist["val_loss"]))
+    # determinism: same seed, same history
+    again = MPNNModel(spec, precision="fp32", seed=3)
+    h2 = again.fit(train, validation_data=val, epochs=len(hist["loss"]), batch_size=32, patience=3, seed=1)
+    assert h2["loss"] == hist["loss"] and h2["val_loss"] == hist["val_loss"]

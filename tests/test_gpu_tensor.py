@@ -319,3 +319,40 @@ def test_compact_feed_is_bit_identical():
     out_f, bytes_f = m.predict_stream(chunks, compact=False)
     torch.cuda.synchronize()
     assert np.array_equal(out_c, out_f.numpy()) and bytes_c < 0.5 * bytes_f
+
+
+@pytest.mark.parametrize("num_steps,fp_size,mixing_size", [(1, 32, 20), (2, 16, 8), (3, 24, 32)])
+def test_fused_forward_other_step_counts_and_readout_sizes(num_steps, fp_size, mixing_size):
+    """The fused kernel takes 1..4 steps and the fast readout any fp / mix <= 32: parity against the fp64 oracle."""
+    from ionic_mpnn_b200 import synth
+    from ionic_mpnn_b200.viscosity import build_model
+    from oracle import ref_inputs, ref_model
+
+    recs = synth.make_records(200, seed=8)
+    spec = ref_model.make_spec("viscosity", num_steps=num_steps, fp_size=fp_size, mixing_size=mixing_size)
+    params = ref_model.init_params(spec, seed=5, trained_like=True)
+    want = ref_model.predict(spec, params, ref_inputs.build_inputs(recs), batch_size=64)
+    model = build_model(124, 72, num_steps=num_steps, fp_size=fp_size, mixing_size=mixing_size, precision="fp16", fused=True)
+    model.set_weights(params)
+    got = model.predict(recs)
+    assert _rel(got, want) <= BF16_RTOL, _rel(got, want)
+    ref32 = build_model(124, 72, num_steps=num_steps, fp_size=fp_size, mixing_size=mixing_size, precision="fp32")
+    ref32.set_weights(params)
+    assert _rel(ref32.predict(recs), want) <= 1e-5
+
+
+def test_fused_forward_unbalanced_towers_and_small_vocabularies():
+    """Tiny cations / large anions (the CTA split between towers follows the atom counts) and non-default vocabularies."""
+    from ionic_mpnn_b200 import graph
+    from ionic_mpnn_b200.viscosity import build_model
+
+    cat = graph.synth_flat(500, 71, 2, 4, atom_types=9, bond_types=5)
+    an = graph.synth_flat(500, 72, 60, 120, atom_types=9, bond_types=5)
+    T = np.random.default_rng(3).uniform(273.15, 373.15, 500).astype(np.float32)
+    b = graph.pack_flat(cat, an, 6, temperature=T).to("cuda")
+    ref = build_model(10, 6, precision="fp32", seed=9)
+    fz = build_model(10, 6, precision="fp16", seed=9, fused=True)
+    want = ref.forward_packed(b).cpu().numpy()
+    got = fz.forward_packed(b).cpu().numpy()
+    assert _rel(got, want) <= BF16_RTOL
+    assert np.array_equal(fz.forward_packed(b.to_compact("cuda")).cpu().numpy(), got)

@@ -899,7 +899,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
   const int cta_in_tower = tower ? (int)blockIdx.x - a.n_cta_cat : (int)blockIdx.x;
   const float4* emb4 = reinterpret_cast<const float4*>(a.atom_emb);
   uint32_t ph = 0;
-  const int u = t;
+  [[maybe_unused]] const int u = t;
   FZ_PROF_DECL;
 
   for (int g = cta_in_tower * NCTX + ctx; g < n_groups; g += n_cta_tower * NCTX) {

@@ -321,6 +321,7 @@ struct K6Args {
   const float* h;
   const float* pooled;           // non-null: [2P, d] molecule sums already computed (fused forward); h / mol_ptr unused
   int n_pairs, d, fp, mix, fp2;  // fp2 = 0 -> viscosity head
+  int scratch_stride;
   imp_readout_weights_t wc, wa;
   const float *W1, *b1, *W2, *b2;  // viscosity: W1 = [mix,3] head, b1 = [3]; mp: W1 [mix,fp2], W2 [fp2,1]
   const float* T;
@@ -377,7 +378,8 @@ __global__ void __launch_bounds__(K6_WARPS * 32) pool_head_kernel(K6Args a) {
   p += n_head_out;
   float* W2 = p;
   p += (fp2 > 0 ? fp2 : 0);
-  float* scratch = p + (threadIdx.x / 32) * (4 * K6_MAXV);
+  const int sv = a.scratch_stride;  // max(d, fp, mix, fp2) rounded up to 32 floats
+  float* scratch = p + (threadIdx.x / 32) * (4 * sv);
   for (int t = 0; t < 2; ++t) {
     const imp_readout_weights_t& w = t == 0 ? a.wc : a.wa;
     for (int i = threadIdx.x; i < d * fp; i += blockDim.x) Wfp[t][i] = w.W_fp[i];
@@ -395,9 +397,9 @@ __global__ void __launch_bounds__(K6_WARPS * 32) pool_head_kernel(K6Args a) {
   const int warp_global = blockIdx.x * K6_WARPS + (threadIdx.x >> 5);
   const int n_warps = gridDim.x * K6_WARPS;
   float* pool = scratch;             // [d]
-  float* v1 = scratch + K6_MAXV;     // [fp]
-  float* v2 = scratch + 2 * K6_MAXV; // [mix]
-  float* mixed = scratch + 3 * K6_MAXV;
+  float* v1 = scratch + sv;     // [fp]
+  float* v2 = scratch + 2 * sv; // [mix]
+  float* mixed = scratch + 3 * sv;
   const int aux_stride = 2 * d + 2 * fp + mix + (fp2 > 0 ? 0 : 3);
   for (int pair = warp_global; pair < a.n_pairs; pair += n_warps) {
     for (int t = 0; t < 2; ++t) {
@@ -731,8 +733,14 @@ static int launch_k6(const imp_graph_t* g, const float* d_h, const float* d_pool
   a.d = d, a.fp = fp, a.mix = mix, a.fp2 = fp2, a.wc = *wc, a.wa = *wa;
   a.W1 = W1, a.b1 = b1, a.W2 = W2, a.b2 = b2, a.T = T, a.out = out, a.aux = aux;
   const int n_head_out = fp2 > 0 ? fp2 : 3;
+  {
+    int mv = d > fp ? d : fp;
+    mv = mv > mix ? mv : mix;
+    mv = mv > fp2 ? mv : fp2;
+    a.scratch_stride = (mv + 31) / 32 * 32;
+  }
   const size_t smem = sizeof(float) * (2 * d * fp + 2 * fp + 2 * fp * mix + 2 * mix + mix * n_head_out + n_head_out +
-                                       (fp2 > 0 ? fp2 : 0) + K6_WARPS * 4 * K6_MAXV);
+                                       (fp2 > 0 ? fp2 : 0) + K6_WARPS * 4 * a.scratch_stride);
   IMP_CUDA(cudaFuncSetAttribute(pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   IMP_REQUIRE(smem <= 200 * 1024, IMP_ERR_DIM, "%s: readout weights need %zu B of shared memory", who, smem);
   if (d_pooled && !aux && d <= 32 && fp <= 32 && mix <= 32 && fp2 <= 32) {  // both reference models: register-resident weights

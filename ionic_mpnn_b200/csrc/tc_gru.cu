@@ -142,13 +142,16 @@ __global__ void __launch_bounds__(TC_TILE) gated_update_tc_kernel(const float* _
     tc::fence_before_thread_sync();
     __syncthreads();
     // ---- GEMM 1: z | r pre-activations
-    if (tid == 0) {
+    if (warp == 0) {  // warp-uniform issue + elect.sync: operands stay in uniform registers (tc_common.cuh, elect_one)
       tc::fence_after_thread_sync();
+      if (tc::elect_one()) {
 #pragma unroll
-      for (int ks = 0; ks < L::C1 / 2; ++ks)
-        tc::mma_bf16(tmem, tc::make_smem_desc(aA1 + 2 * ks * LBO_A, LBO_A, SBO),
-                     tc::make_smem_desc(aBzr + 2 * ks * LBO_BZR, LBO_BZR, SBO), idesc1, ks > 0);
-      tc::mma_commit(&s.bar[0]);
+        for (int ks = 0; ks < L::C1 / 2; ++ks)
+          tc::mma_bf16(tmem, tc::make_smem_desc(aA1 + 2 * ks * LBO_A, LBO_A, SBO),
+                       tc::make_smem_desc(aBzr + 2 * ks * LBO_BZR, LBO_BZR, SBO), idesc1, ks > 0);
+        tc::mma_commit(&s.bar[0]);
+      }
+      __syncwarp();
     }
     tc::mbar_wait(&s.bar[0], phase);
     tc::fence_after_thread_sync();
@@ -175,15 +178,18 @@ __global__ void __launch_bounds__(TC_TILE) gated_update_tc_kernel(const float* _
     tc::fence_before_thread_sync();
     __syncthreads();
     // ---- GEMM 2: candidate pre-activation, [r*h | agg] x Wh
-    if (tid == 0) {
+    if (warp == 0) {
       tc::fence_after_thread_sync();
+      if (tc::elect_one()) {
 #pragma unroll
-      for (int ks = 0; ks < L::C1 / 2; ++ks) {
-        const uint32_t a = ks < CH / 2 ? aRH + 2 * ks * LBO_A : aA1 + 2 * ks * LBO_A;  // agg chunks live in A1
-        tc::mma_bf16(tmem + 2 * D, tc::make_smem_desc(a, LBO_A, SBO),
-                     tc::make_smem_desc(aBh + 2 * ks * LBO_BH, LBO_BH, SBO), idesc2, ks > 0);
+        for (int ks = 0; ks < L::C1 / 2; ++ks) {
+          const uint32_t a = ks < CH / 2 ? aRH + 2 * ks * LBO_A : aA1 + 2 * ks * LBO_A;  // agg chunks live in A1
+          tc::mma_bf16(tmem + 2 * D, tc::make_smem_desc(a, LBO_A, SBO),
+                       tc::make_smem_desc(aBh + 2 * ks * LBO_BH, LBO_BH, SBO), idesc2, ks > 0);
+        }
+        tc::mma_commit(&s.bar[1]);
       }
-      tc::mma_commit(&s.bar[1]);
+      __syncwarp();
     }
     tc::mbar_wait(&s.bar[1], phase);
     tc::fence_after_thread_sync();

@@ -15,6 +15,7 @@ batch.to("cuda")
 cbatch = batch.to_compact("cuda")
 for S in (1, 4):
     m = build_model(124, 72, num_steps=S, precision="fp16", fused=True)
+    m.extra_tc_flags = int(os.environ.get("FZ_FLAGS", "0"))
     for _ in range(3):
         m.forward_packed(batch)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

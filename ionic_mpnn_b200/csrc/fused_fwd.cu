@@ -135,7 +135,8 @@ struct alignas(16) FusedWgSmem {
 
 struct FusedCtl {
   uint32_t tmem_base;
-  uint32_t pad[3];
+  uint32_t pad;
+  uint64_t wbar;  // mbarrier of the TMA weight load (third-generation kernel)
 };
 
 __host__ __device__ inline int fused_smem_bytes(int steps, int bond_vocab) {
@@ -856,16 +857,19 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
   FusedCtl& ctl = *reinterpret_cast<FusedCtl*>(smem + wbytes + ctab_bytes + NCTX * sizeof(FusedWgSmem3));
 
   const int tower = blockIdx.x >= a.n_cta_cat;
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(a.packed + (size_t)tower * wbytes);
-    uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < wbytes / 16; i += NT) dst[i] = __ldg(src + i);
-    for (int i = tid; i < a.bond_vocab; i += NT) {
-      const float4 c0 = __ldg(reinterpret_cast<const float4*>(a.bond_emb) + 2 * i);
-      const float4 c1 = __ldg(reinterpret_cast<const float4*>(a.bond_emb) + 2 * i + 1);
-      s_ctab[i] = make_uint4(tc::pack_f16x2(c0.x, c0.y), tc::pack_f16x2(c0.z, c0.w), tc::pack_f16x2(c1.x, c1.y),
-                             tc::pack_f16x2(c1.z, c1.w));
-    }
+  // Resident weights of this tower (all steps, 127 KB): ONE TMA bulk copy, issued by one thread and
+  // counted in bytes on an mbarrier; the bond-coefficient table is converted by the threads meanwhile.
+  if (tid == 0) {
+    tc::mbar_init(&ctl.wbar, 1);
+    tc::mbar_fence_init();
+    tc::mbar_arrive_expect_tx(&ctl.wbar, (uint32_t)wbytes);
+    tc::bulk_copy_g2s(smem, a.packed + (size_t)tower * wbytes, (uint32_t)wbytes, &ctl.wbar);
+  }
+  for (int i = tid; i < a.bond_vocab; i += NT) {
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(a.bond_emb) + 2 * i);
+    const float4 c1 = __ldg(reinterpret_cast<const float4*>(a.bond_emb) + 2 * i + 1);
+    s_ctab[i] = make_uint4(tc::pack_f16x2(c0.x, c0.y), tc::pack_f16x2(c0.z, c0.w), tc::pack_f16x2(c1.x, c1.y),
+                           tc::pack_f16x2(c1.z, c1.w));
   }
   if (warp == 0) tc::tmem_alloc<512>(&ctl.tmem_base);
   if (t == 0) {
@@ -877,6 +881,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
+  tc::mbar_wait(&ctl.wbar, 0);  // weights have landed (async proxy writes: visible to tcgen05.mma without a proxy fence)
 
   const uint32_t sw0 = tc::smem_u32(smem);
   const uint32_t tbase = ctl.tmem_base + (uint32_t)(ctx * 128);

@@ -6,7 +6,10 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from ionic_mpnn_b200 import graph  # noqa: E402
+from ionic_mpnn_b200 import _lib, graph  # noqa: E402
+
+if os.environ.get("IMP_LIB"):
+    _lib.LIB_PATH = os.environ["IMP_LIB"]  # A/B runs against another build of the library
 from ionic_mpnn_b200.viscosity import build_model  # noqa: E402
 
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 524288

@@ -254,6 +254,40 @@ int imp_mpnn_forward_fused_compact(const imp_compact_graph_t* cg, const float* d
                                    float eps, int32_t flags, int32_t max_mol_atoms, float* d_pooled, int32_t* d_status,
                                    void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Wide atom states on the tensor cores (atom_dim 256, bond_dim 8: BASELINE configs[4], the "wide/deep" variant).
+ * Replaces the same reference code as the fused forward (train_viscosity.py:163,171-187 + models/layers.py:57-164)
+ * at a width where the layers are tensor-bound: per step three pipelined tcgen05 GEMM kernels (TMA bulk-copy
+ * operand stages, fp32 accumulators in TMEM, IEEE-half operands) --
+ *   messages      agg = Z . Wc with Z (K = 2048) built on the fly from the CSR by the producer warps,
+ *   gates         z, r*h = sigma([h|agg] [Wz|Wr] + b) written as 16-bit operands,
+ *   candidate     tanh([r*h|agg] Wh + bh), blend, LayerNorm, residual in the epilogue (the row lives in TMEM) --
+ * between an Embedding kernel and a GlobalSumPool kernel.  Any molecule size, any number of steps.
+ *   imp_wide_pack        once per weight update and per (tower, step) -> imp_wide_pack_bytes() bytes;
+ *                        d_packed of the forward is [2 towers][steps] such blocks, cation first.
+ *   d_workspace          imp_wide_workspace_bytes(n_atoms, d) bytes (fp32 state + four 16-bit operand matrices,
+ *                        tile-packed layouts, csrc/wide_tc.cu).
+ *   flags                IMP_TC_FP16 is required; IMP_TC_PRECISE_EPILOGUE as above.
+ *   d_pooled             [2 * n_pairs, d] molecule sums -> imp_readout_visc / imp_readout_mp.
+ * ------------------------------------------------------------------------------------------- */
+int64_t imp_wide_pack_bytes(int32_t d, int32_t bond_dim);
+int imp_wide_pack(const float* d_bond_transform /* [K,d,d] */, const imp_gru_weights_t* w, int32_t d, int32_t bond_dim,
+                  void* d_packed, void* stream);
+int64_t imp_wide_workspace_bytes(int32_t n_atoms, int32_t d);
+int imp_mpnn_forward_wide(const imp_graph_t* g, const float* d_atom_emb, int32_t atom_vocab, const float* d_bond_emb,
+                          int32_t d, int32_t bond_dim, int32_t steps, const void* d_packed, float eps, int32_t flags,
+                          void* d_workspace, float* d_pooled, void* stream);
+/* The stages of imp_mpnn_forward_wide as separate calls on the same workspace (layer granularity: Embedding;
+ * BondMatrixMessage o Reduce; GatedUpdate gates; GatedUpdate candidate + LayerNorm + residual; GlobalSumPool). */
+int imp_wide_embed(const imp_graph_t* g, const float* d_atom_emb, int32_t atom_vocab, int32_t d, void* d_workspace, void* stream);
+int imp_wide_message(const imp_graph_t* g, const float* d_bond_emb, int32_t d, int32_t bond_dim, const void* d_packed_cat,
+                     const void* d_packed_an, int32_t flags, void* d_workspace, void* stream);
+int imp_wide_gates(const imp_graph_t* g, int32_t d, const void* d_packed_cat, const void* d_packed_an, int32_t flags,
+                   void* d_workspace, void* stream);
+int imp_wide_candidate(const imp_graph_t* g, int32_t d, const void* d_packed_cat, const void* d_packed_an, float eps,
+                       int32_t flags, void* d_workspace, void* stream);
+int imp_wide_pool(const imp_graph_t* g, int32_t d, const void* d_workspace, float* d_pooled, void* stream);
+
 /* K6 without the pooling stage: Dense(fp, relu), Dense(mix, relu) per tower, AddTwoTensors, head
  * (train_viscosity.py:189-214 / train_melting_point.py:173-198) on molecule sums [2P, d] (cations first). */
 int imp_readout_visc(const float* d_pooled, int32_t n_pairs, int32_t d, int32_t fp, int32_t mix,

@@ -93,6 +93,16 @@ SIGNATURES = {
                                          C.c_int32, C.c_int32, vp, vp, vp]),
     "imp_mpnn_forward_fused_compact": (C.c_int, [C.POINTER(CompactGraph), vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, vp,
                                                  C.c_float, C.c_int32, C.c_int32, vp, vp, vp]),
+    "imp_wide_pack_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "imp_wide_pack": (C.c_int, [vp, C.POINTER(GruWeights), C.c_int32, C.c_int32, vp, vp]),
+    "imp_wide_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "imp_mpnn_forward_wide": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_float,
+                                        C.c_int32, vp, vp, vp]),
+    "imp_wide_embed": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, C.c_int32, vp, vp]),
+    "imp_wide_message": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, vp]),
+    "imp_wide_gates": (C.c_int, [C.POINTER(Graph), C.c_int32, vp, vp, C.c_int32, vp, vp]),
+    "imp_wide_candidate": (C.c_int, [C.POINTER(Graph), C.c_int32, vp, vp, C.c_float, C.c_int32, vp, vp]),
+    "imp_wide_pool": (C.c_int, [C.POINTER(Graph), C.c_int32, vp, vp, vp]),
     "imp_readout_visc": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ReadoutWeights),
                                    C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp]),
     "imp_readout_mp": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ReadoutWeights),

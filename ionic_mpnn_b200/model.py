@@ -166,6 +166,20 @@ class MPNNModel(TrainMixin):
         s = self.spec
         S, d, Vb, K = s["num_steps"], s["atom_dim"], s["bond_vocab_size"], s["bond_dim"]
         n = 2 * S
+        if self.wide_supported():
+            # wide tensor path (csrc/wide_tc.cu): bond tables are never formed (messages are Z . Wc), one packed block
+            # per (tower, step)
+            import torch
+
+            wb = _lib.load().imp_wide_pack_bytes(d, K)
+            wpk = self._buf("wide_packed", wb * n, torch.uint8)
+            for ti, t in enumerate(TOWERS):
+                for i in range(S):
+                    w = self._gru_struct(t, i)
+                    _lib.call("imp_wide_pack", self._ptr(f"{t}_bmm_{i}.bond_transform"), C.byref(w), d, K,
+                              wpk.data_ptr() + wb * (ti * S + i), _stream())
+            self._tables_valid = True
+            return
         per = Vb * d * d
         tab = self._buf("table", n * per)
         tab_il = self._buf("table_il", n * per)
@@ -201,6 +215,12 @@ class MPNNModel(TrainMixin):
         if self.precision.endswith("_precise"):
             f |= _lib.TC_PRECISE_EPILOGUE
         return f | getattr(self, "extra_tc_flags", 0)
+
+    def wide_supported(self):
+        """Shape envelope of imp_mpnn_forward_wide (include/imp_b200.h): IEEE-half operands, atom_dim 256, bond_dim 8."""
+        s = self.spec
+        return (self.precision.startswith("fp16") and s["atom_dim"] == 256 and s["bond_dim"] == 8
+                and s["bond_vocab_size"] <= 256)
 
     def fused_supported(self):
         """Shape envelope of imp_mpnn_forward_fused (include/imp_b200.h)."""
@@ -255,6 +275,10 @@ class MPNNModel(TrainMixin):
             return self._forward_fused(batch, None, st)
         g = batch.c_struct()
         N, P = batch.n_atoms, batch.n_pairs
+        if self.wide_supported():
+            if keep or unfused_messages:
+                raise _lib.ImpError("the wide tensor path keeps no per-layer intermediates (use precision='fp32')")
+            return self._forward_wide(batch, g, st)
         if not keep and not unfused_messages and self.use_fused(batch):
             return self._forward_fused(batch, g, st)
         inter = {}
@@ -345,8 +369,53 @@ class MPNNModel(TrainMixin):
                       self._ptr("head2.bias"), out.data_ptr(), None, st)
         return out
 
+    def _forward_wide(self, batch, g, st):
+        """imp_mpnn_forward_wide (embed, 3 tcgen05 GEMM kernels per step, pool) then the readout kernel."""
+        import torch
+
+        s = self.spec
+        d, S, P = s["atom_dim"], s["num_steps"], batch.n_pairs
+        pooled = self._buf("pooled", 2 * P * d)
+        wsb = _lib.load().imp_wide_workspace_bytes(batch.n_atoms, d)
+        ws = self._buf("wide_ws", wsb, torch.uint8)
+        if getattr(self, "wide_per_stage_calls", False):  # the same launches as separate ABI calls (bench: per-kernel timing)
+            wb = _lib.load().imp_wide_pack_bytes(d, s["bond_dim"])
+            pk, f, w = self._ws["wide_packed"].data_ptr(), self.tc_flags(), ws.data_ptr()
+            _lib.call("imp_wide_embed", C.byref(g), self._ptr("atom_emb"), s["atom_vocab_size"], d, w, st)
+            for i in range(S):
+                pc, pa = pk + wb * i, pk + wb * (S + i)
+                _lib.call("imp_wide_message", C.byref(g), self._ptr("bond_emb"), d, s["bond_dim"], pc, pa, f, w, st)
+                _lib.call("imp_wide_gates", C.byref(g), d, pc, pa, f, w, st)
+                _lib.call("imp_wide_candidate", C.byref(g), d, pc, pa, C.c_float(self.LN_EPS), f, w, st)
+            _lib.call("imp_wide_pool", C.byref(g), d, w, pooled.data_ptr(), st)
+        else:
+            _lib.call("imp_mpnn_forward_wide", C.byref(g), self._ptr("atom_emb"), s["atom_vocab_size"], self._ptr("bond_emb"),
+                      d, s["bond_dim"], S, self._ws["wide_packed"].data_ptr(), C.c_float(self.LN_EPS), self.tc_flags(),
+                      ws.data_ptr(), pooled.data_ptr(), st)
+        return self._readout(batch, pooled, st)
+
+    def _readout(self, batch, pooled, st):
+        import torch
+
+        s = self.spec
+        d, P, fp, mix = s["atom_dim"], batch.n_pairs, s["fp_size"], s["mixing_size"]
+        out = torch.empty(P, dtype=torch.float32, device=self.device)
+        rc, ra = self._readout_struct("cat"), self._readout_struct("an")
+        if s["kind"] == "viscosity":
+            if batch.dev_T is None:
+                raise ValueError("viscosity model needs batch.temperature")
+            _lib.call("imp_readout_visc", pooled.data_ptr(), P, d, fp, mix, C.byref(rc), C.byref(ra),
+                      self._ptr("head.kernel"), self._ptr("head.bias"), batch.dev_T.data_ptr(), out.data_ptr(), None, st)
+        else:
+            _lib.call("imp_readout_mp", pooled.data_ptr(), P, d, fp, mix, fp, C.byref(rc), C.byref(ra),
+                      self._ptr("head1.kernel"), self._ptr("head1.bias"), self._ptr("head2.kernel"),
+                      self._ptr("head2.bias"), out.data_ptr(), None, st)
+        return out
+
     def launches_per_forward(self, batch=None):
         """Kernels enqueued by forward_packed (tables / packs already valid)."""
+        if self.wide_supported():
+            return 2 + 3 * self.spec["num_steps"] + 1
         if batch is not None and self.use_fused(batch):
             return 2
         return 1 + 2 * self.spec["num_steps"] + 1

@@ -177,6 +177,7 @@ int imp_gated_update_wide(const float* d_h, const float* d_agg, int32_t n_atoms,
 #define IMP_TC_F32_ZBUILD 8
 #define IMP_TC_TWO_THREADS_PER_ROW 16
 #define IMP_TC_THREE_CONTEXTS 32
+#define IMP_TC_WIDE_SPLIT_GRU 64
 int64_t imp_gru_pack_bytes(int32_t d);
 int imp_gru_pack_bf16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
 int imp_gru_pack_f16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
@@ -286,6 +287,10 @@ int imp_wide_gates(const imp_graph_t* g, int32_t d, const void* d_packed_cat, co
                    void* d_workspace, void* stream);
 int imp_wide_candidate(const imp_graph_t* g, int32_t d, const void* d_packed_cat, const void* d_packed_an, float eps,
                        int32_t flags, void* d_workspace, void* stream);
+/* GatedUpdate as one kernel (gates stay in TMEM / shared memory); imp_wide_gates + imp_wide_candidate are the two-kernel
+ * form of the same layer (flag IMP_TC_WIDE_SPLIT_GRU of imp_mpnn_forward_wide), kept for comparison. */
+int imp_wide_gated_update(const imp_graph_t* g, int32_t d, const void* d_packed_cat, const void* d_packed_an, float eps,
+                          int32_t flags, void* d_workspace, void* stream);
 int imp_wide_pool(const imp_graph_t* g, int32_t d, const void* d_workspace, float* d_pooled, void* stream);
 
 /* K6 without the pooling stage: Dense(fp, relu), Dense(mix, relu) per tower, AddTwoTensors, head

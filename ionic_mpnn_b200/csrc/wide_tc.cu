@@ -406,6 +406,304 @@ __global__ void __launch_bounds__(THREADS, 1) wide_gemm_kernel(const Args a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// GatedUpdate.call (models/layers.py:142-156) as ONE kernel per step: a CTA owns a 128-row tile whose gates never leave the
+// SM.  TMEM: z pre-activations in columns [0,256) (later the row's fp32 state), r in [256,512) (later the candidate,
+// later the blended row n).  Shared memory: a resident 64 KB operand tile X (TP16 layout = UMMA layout) + 3 stages.
+//   tile start  X <- the tile's h16 (one 64 KB bulk copy); the tile's fp32 state (128 contiguous KB) is prefetched into L2
+//   phase A     [h|agg] . [Wz|Wr]: 16 K-slices of 32; A from X (K < 256) or a streamed agg slice, both weight slices streamed
+//   EA          r = sigma(. + br); X <- r * h in place (X is now the A operand of phase B)
+//   phase B     [r*h|agg] . Wh -> the r columns
+//   E2 pass 1   z = sigma(. + bz), ht = tanh(. + bh), n = h + z (ht - h); n parked over the candidate and h (fp32, read once
+//               from L2) over the z columns; LayerNorm partial sums (two workers per row meet through shared memory)
+//   E2 pass 2   out = (n - mean) rstd gamma + beta + h from TMEM only; fp32 state and its 16-bit copy written in place.
+// Every epilogue loop is rolled (32 / 16 columns per trip): an unrolled 128-column body per thread is ~6,000 SASS
+// instructions and ran instruction-fetch bound (ncu: 15 no_instruction stalls per issue, profiles/README.md).
+constexpr int G_KC = 32, G_STAGES = 3, G_CHUNKS = 2 * D / G_KC;  // 16 slices per phase
+constexpr int G_A_BYTES = TILE * G_KC * 2;                        // 8 KB
+constexpr int G_B_BYTES = D * G_KC * 2;                           // 16 KB per gate
+constexpr int G_STAGE_BYTES = G_A_BYTES + 2 * G_B_BYTES;          // 40 KB
+constexpr int G_X_BYTES = TILE * D * 2;                           // 64 KB
+
+struct GCtl {
+  uint64_t full[G_STAGES], empty[G_STAGES], x_full, accA, rh_ready, accB, acc_empty;
+  uint32_t tmem;
+};
+constexpr int G_OFF_X = G_STAGES * G_STAGE_BYTES, G_OFF_VEC = G_OFF_X + G_X_BYTES, G_OFF_RED = G_OFF_VEC + 5 * D * 4,
+              G_OFF_CTL = G_OFF_RED + 2 * TILE * 8;
+constexpr int G_SMEM_BYTES = G_OFF_CTL + (int)sizeof(GCtl) + 64;
+
+struct GItem {
+  int tower, t, lo, hi;
+};
+__device__ __forceinline__ GItem decode_gitem(int i, int n_atoms, int n_cat) {
+  GItem it;
+  const int nc = (n_cat + TILE - 1) / TILE;
+  if (i < nc) {
+    it.tower = 0, it.t = i, it.lo = 0, it.hi = n_cat;
+  } else {
+    it.tower = 1, it.t = n_cat / TILE + (i - nc), it.lo = n_cat, it.hi = n_atoms;
+  }
+  return it;
+}
+static inline int n_gitems(int n_atoms, int n_cat) {
+  const int nc = (n_cat + TILE - 1) / TILE;
+  return nc + (n_atoms > n_cat ? (n_atoms + TILE - 1) / TILE - n_cat / TILE : 0);
+}
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
+
+template <bool PRECISE>
+__device__ __forceinline__ float sigmoid_f(float x) {
+  return PRECISE ? 1.0f / (1.0f + expf(-x)) : fast_sigmoid(x);
+}
+template <bool PRECISE>
+__device__ __forceinline__ float tanh_f(float x) {
+  return PRECISE ? tanhf(x) : fast_tanh(x);
+}
+
+template <bool PRECISE>
+__global__ void __launch_bounds__(THREADS, 1) wide_gru_kernel(const Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* xs = smem + G_OFF_X;
+  float* vec_s = reinterpret_cast<float*>(smem + G_OFF_VEC);
+  float2* red_s = reinterpret_cast<float2*>(smem + G_OFF_RED);
+  GCtl& ctl = *reinterpret_cast<GCtl*>(smem + G_OFF_CTL);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nc = (a.n_cat + TILE - 1) / TILE;
+  const int items = nc + (a.n_atoms > a.n_cat ? (a.n_atoms + TILE - 1) / TILE - a.n_cat / TILE : 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < G_STAGES; ++s) {
+      tc::mbar_init(&ctl.full[s], 1);
+      tc::mbar_init(&ctl.empty[s], 1);
+    }
+    tc::mbar_init(&ctl.x_full, 1);
+    tc::mbar_init(&ctl.accA, 1);
+    tc::mbar_init(&ctl.rh_ready, 8);
+    tc::mbar_init(&ctl.accB, 1);
+    tc::mbar_init(&ctl.acc_empty, 8);
+    tc::mbar_fence_init();
+  }
+  if (warp == 9) tc::tmem_alloc<512>(&ctl.tmem);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = ctl.tmem;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA loader
+    if (lane == 0) {
+      uint32_t it = 0, k = 0;
+      for (int i = blockIdx.x; i < items; i += gridDim.x, ++k) {
+        const GItem w = decode_gitem(i, a.n_atoms, a.n_cat);
+        const uint8_t* pk = w.tower ? a.packed[1] : a.packed[0];
+        const uint8_t* aggt = a.agg16 + (int64_t)w.t * 65536;
+        if (k > 0) tc::mbar_wait(&ctl.accB, (k - 1) & 1);  // phase B of the previous tile has finished reading X
+        tc::mbar_arrive_expect_tx(&ctl.x_full, G_X_BYTES);
+        tc::bulk_copy_g2s(xs, a.h16 + (int64_t)w.t * 65536, G_X_BYTES, &ctl.x_full);
+        bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.h32) + (int64_t)w.t * 131072, 131072);
+        for (int j = 0; j < 2 * G_CHUNKS; ++j, ++it) {  // phase A: slices 0..15, phase B: 16..31
+          const int s = it % G_STAGES;
+          tc::mbar_wait(&ctl.empty[s], ((it / G_STAGES) & 1) ^ 1);
+          uint8_t* sb = smem + s * G_STAGE_BYTES;
+          const bool phase_b = j >= G_CHUNKS;
+          const int jj = phase_b ? j - G_CHUNKS : j;
+          const bool stream_a = jj >= G_CHUNKS / 2;
+          tc::mbar_arrive_expect_tx(&ctl.full[s], (phase_b ? G_B_BYTES : 2 * G_B_BYTES) + (stream_a ? G_A_BYTES : 0));
+          if (stream_a) tc::bulk_copy_g2s(sb, aggt + (jj - G_CHUNKS / 2) * G_A_BYTES, G_A_BYTES, &ctl.full[s]);
+          if (phase_b) {
+            tc::bulk_copy_g2s(sb + G_A_BYTES, pk + OFF_WH + (int64_t)jj * G_B_BYTES, G_B_BYTES, &ctl.full[s]);
+          } else {
+            tc::bulk_copy_g2s(sb + G_A_BYTES, pk + OFF_WZ + (int64_t)jj * G_B_BYTES, G_B_BYTES, &ctl.full[s]);
+            tc::bulk_copy_g2s(sb + G_A_BYTES + G_B_BYTES, pk + OFF_WR + (int64_t)jj * G_B_BYTES, G_B_BYTES, &ctl.full[s]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = tc::make_idesc(tc::FMT_F16, TILE, D);
+    const uint32_t x_addr = tc::smem_u32(xs);
+    uint32_t it = 0, k = 0;
+    for (int i = blockIdx.x; i < items; i += gridDim.x, ++k) {
+      tc::mbar_wait(&ctl.acc_empty, (k & 1) ^ 1);
+      tc::mbar_wait(&ctl.x_full, k & 1);
+      tc::fence_after_thread_sync();
+      for (int j = 0; j < G_CHUNKS; ++j, ++it) {
+        const int s = it % G_STAGES;
+        tc::mbar_wait(&ctl.full[s], (it / G_STAGES) & 1);
+        tc::fence_after_thread_sync();
+        const uint32_t sa = tc::smem_u32(smem + s * G_STAGE_BYTES);
+        const uint64_t da = tc::make_smem_desc(j < G_CHUNKS / 2 ? x_addr + j * G_A_BYTES : sa, 2048, 128),
+                       dz = tc::make_smem_desc(sa + G_A_BYTES, 4096, 128), dr = tc::make_smem_desc(sa + G_A_BYTES + G_B_BYTES, 4096, 128);
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < G_KC / 16; ++ks) {
+            tc::mma_bf16(tmem, da + (uint64_t)((ks * 4096) >> 4), dz + (uint64_t)((ks * 8192) >> 4), idesc, j > 0 || ks > 0);
+            tc::mma_bf16(tmem + D, da + (uint64_t)((ks * 4096) >> 4), dr + (uint64_t)((ks * 8192) >> 4), idesc, j > 0 || ks > 0);
+          }
+          tc::mma_commit(&ctl.empty[s]);
+          if (j == G_CHUNKS - 1) tc::mma_commit(&ctl.accA);
+        }
+        __syncwarp();
+      }
+      tc::mbar_wait(&ctl.rh_ready, k & 1);
+      tc::fence_after_thread_sync();
+      for (int j = 0; j < G_CHUNKS; ++j, ++it) {
+        const int s = it % G_STAGES;
+        tc::mbar_wait(&ctl.full[s], (it / G_STAGES) & 1);
+        tc::fence_after_thread_sync();
+        const uint32_t sa = tc::smem_u32(smem + s * G_STAGE_BYTES);
+        const uint64_t da = tc::make_smem_desc(j < G_CHUNKS / 2 ? x_addr + j * G_A_BYTES : sa, 2048, 128),
+                       db = tc::make_smem_desc(sa + G_A_BYTES, 4096, 128);
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < G_KC / 16; ++ks)
+            tc::mma_bf16(tmem + D, da + (uint64_t)((ks * 4096) >> 4), db + (uint64_t)((ks * 8192) >> 4), idesc, j > 0 || ks > 0);
+          tc::mma_commit(&ctl.empty[s]);
+          if (j == G_CHUNKS - 1) tc::mma_commit(&ctl.accB);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ workers: 4 lane quarters x 2 column halves
+    const int q = warp & 3, ch = warp >> 2;
+    const int rowt = q * 32 + lane;
+    const uint32_t tz = tmem + (uint32_t)(ch * 128) + ((uint32_t)(q * 32) << 16), tr = tz + D;
+    const float *bz = vec_s + ch * 128, *br = vec_s + D + ch * 128, *bh = vec_s + 2 * D + ch * 128,
+                *gamma = vec_s + 3 * D + ch * 128, *beta = vec_s + 4 * D + ch * 128;
+    uint8_t* h32b = reinterpret_cast<uint8_t*>(a.h32);
+    uint8_t* xrow = xs + (16 * ch) * 2048 + rowt * 16;  // this thread's pieces of X: + p * 2048
+    int cur_tower = -1;
+    uint32_t k = 0;
+    for (int i = blockIdx.x; i < items; i += gridDim.x, ++k) {
+      const GItem w = decode_gitem(i, a.n_atoms, a.n_cat);
+      const int row = w.t * TILE + rowt;
+      const bool mine = row >= w.lo && row < w.hi;
+      if (w.tower != cur_tower) {  // bz, br, bh, gamma, beta of this tower -> shared memory
+        tc::named_bar_sync(1, 256);
+        const float* v = reinterpret_cast<const float*>((w.tower ? a.packed[1] : a.packed[0]) + OFF_VEC);
+        for (int x = threadIdx.x; x < 5 * D; x += 256) vec_s[x] = __ldg(v + x);
+        tc::named_bar_sync(1, 256);
+        cur_tower = w.tower;
+      }
+      const uint8_t* hrow = h32b + tp32_off(row, 32 * ch);  // this thread's quads of the fp32 state: + x * 2048
+      // ---- EA: r -> r*h operand, in place over the h16 tile
+      tc::mbar_wait(&ctl.x_full, k & 1);
+      tc::mbar_wait(&ctl.accA, k & 1);
+      tc::fence_after_thread_sync();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tc::tmem_ld32(tr + c * 32, v);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          uint4* xp = reinterpret_cast<uint4*>(xrow + (4 * c + p) * 2048);
+          const uint4 hw = *xp;
+          const __half2* h2 = reinterpret_cast<const __half2*>(&hw);
+          const float4 b0 = *reinterpret_cast<const float4*>(br + c * 32 + 8 * p), b1 = *reinterpret_cast<const float4*>(br + c * 32 + 8 * p + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float o[8];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const float2 hf = __half22float2(h2[x]);
+            o[2 * x] = sigmoid_f<PRECISE>(v[8 * p + 2 * x] + bb[2 * x]) * hf.x;
+            o[2 * x + 1] = sigmoid_f<PRECISE>(v[8 * p + 2 * x + 1] + bb[2 * x + 1]) * hf.y;
+          }
+          *xp = make_uint4(tc::pack_f16x2(o[0], o[1]), tc::pack_f16x2(o[2], o[3]), tc::pack_f16x2(o[4], o[5]), tc::pack_f16x2(o[6], o[7]));
+        }
+      }
+      tc::fence_proxy_async_smem();
+      tc::fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl.rh_ready);
+      // ---- E2 pass 1: blend, statistics; n -> candidate columns, h -> z columns
+      float4 hq[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) hq[x] = mine ? *reinterpret_cast<const float4*>(hrow + x * 2048) : make_float4(0.f, 0.f, 0.f, 0.f);
+      tc::mbar_wait(&ctl.accB, k & 1);
+      tc::fence_after_thread_sync();
+      float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        float zp[16], hp[16];
+        tc::tmem_ld16(tz + c * 16, zp);
+        tc::tmem_ld16(tr + c * 16, hp);
+        float4 hn[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+          hn[x] = (mine && c < 7) ? *reinterpret_cast<const float4*>(hrow + (4 * (c + 1) + x) * 2048) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t nn[16], hh[16];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bz + c * 16 + 4 * x), b1 = *reinterpret_cast<const float4*>(bh + c * 16 + 4 * x);
+          const float bzv[4] = {b0.x, b0.y, b0.z, b0.w}, bhv[4] = {b1.x, b1.y, b1.z, b1.w}, hv[4] = {hq[x].x, hq[x].y, hq[x].z, hq[x].w};
+#pragma unroll
+          for (int y = 0; y < 4; ++y) {
+            const float z = sigmoid_f<PRECISE>(zp[4 * x + y] + bzv[y]), ht = tanh_f<PRECISE>(hp[4 * x + y] + bhv[y]);
+            const float n = fmaf(z, ht - hv[y], hv[y]);
+            sum += n, sq = fmaf(n, n, sq);
+            nn[4 * x + y] = __float_as_uint(n), hh[4 * x + y] = __float_as_uint(hv[y]);
+          }
+        }
+        tc::tmem_st16(tr + c * 16, nn);
+        tc::tmem_st16(tz + c * 16, hh);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) hq[x] = hn[x];
+      }
+      red_s[ch * TILE + rowt] = make_float2(sum, sq);
+      tc::tmem_wait_st();
+      tc::named_bar_sync(1, 256);
+      {
+        const float2 o = red_s[(ch ^ 1) * TILE + rowt];
+        sum += o.x, sq += o.y;
+      }
+      const float mean = sum * (1.0f / D);
+      const float var = fmaxf(sq * (1.0f / D) - mean * mean, 0.f);
+      const float rstd = PRECISE ? 1.0f / sqrtf(var + a.eps) : rsqrtf(var + a.eps);
+      // ---- E2 pass 2: normalise + residual from TMEM, write the state
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        float v[16], hv[16];
+        tc::tmem_ld16(tr + c * 16, v);
+        tc::tmem_ld16(tz + c * 16, hv);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const float4 g = *reinterpret_cast<const float4*>(gamma + c * 16 + 4 * x), b = *reinterpret_cast<const float4*>(beta + c * 16 + 4 * x);
+          v[4 * x] = fmaf((v[4 * x] - mean) * rstd, g.x, b.x) + hv[4 * x];
+          v[4 * x + 1] = fmaf((v[4 * x + 1] - mean) * rstd, g.y, b.y) + hv[4 * x + 1];
+          v[4 * x + 2] = fmaf((v[4 * x + 2] - mean) * rstd, g.z, b.z) + hv[4 * x + 2];
+          v[4 * x + 3] = fmaf((v[4 * x + 3] - mean) * rstd, g.w, b.w) + hv[4 * x + 3];
+        }
+        if (mine) {
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+            *reinterpret_cast<float4*>(h32b + tp32_off(row, 32 * ch + 4 * c + x)) = make_float4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+#pragma unroll
+          for (int p = 0; p < 2; ++p)
+            *reinterpret_cast<uint4*>(a.h16 + tp16_off(row, 16 * ch + 2 * c + p)) =
+                make_uint4(tc::pack_f16x2(v[8 * p], v[8 * p + 1]), tc::pack_f16x2(v[8 * p + 2], v[8 * p + 3]),
+                           tc::pack_f16x2(v[8 * p + 4], v[8 * p + 5]), tc::pack_f16x2(v[8 * p + 6], v[8 * p + 7]));
+        }
+      }
+      tc::fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl.acc_empty);
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 9) {
+    tc::fence_after_thread_sync();
+    tc::tmem_dealloc<512>(tmem);
+  }
+}
+
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + MAX_BOND_VOCAB * 16 + (int)sizeof(Ctl) + 64;
 
 // Embedding(atom) (train_viscosity.py:163,171) into the tile-packed fp32 state and its 16-bit operand copy.
@@ -587,6 +885,33 @@ extern "C" int imp_wide_candidate(const imp_graph_t* g, int32_t d, const void* d
   return wide_part(2, g, nullptr, d, wide::KB, d_packed_cat, d_packed_an, eps, flags, d_workspace, stream, "imp_wide_candidate");
 }
 
+extern "C" int imp_wide_gated_update(const imp_graph_t* g, int32_t d, const void* d_packed_cat, const void* d_packed_an, float eps,
+                                     int32_t flags, void* d_workspace, void* stream) {
+  if (int rc = wide_check(g, d, wide::KB, flags, d_workspace, "imp_wide_gated_update")) return rc;
+  if (g->n_atoms == 0) return 0;
+  IMP_REQUIRE(d_packed_cat && d_packed_an, IMP_ERR_ARG, "imp_wide_gated_update: null pointer");
+  wide::Args a;
+  wide_args(g, d_workspace, &a);
+  a.packed[0] = reinterpret_cast<const uint8_t*>(d_packed_cat), a.packed[1] = reinterpret_cast<const uint8_t*>(d_packed_an);
+  a.eps = eps, a.precise = (flags & IMP_TC_PRECISE_EPILOGUE) ? 1 : 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    IMP_CUDA(cudaFuncSetAttribute(wide::wide_gru_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide::G_SMEM_BYTES));
+    IMP_CUDA(cudaFuncSetAttribute(wide::wide_gru_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide::G_SMEM_BYTES));
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  IMP_CUDA(cudaGetDevice(&dev));
+  IMP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int items = wide::n_gitems(a.n_atoms, a.n_cat);
+  if (a.precise)
+    wide::wide_gru_kernel<true><<<items < sms ? items : sms, wide::THREADS, wide::G_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  else
+    wide::wide_gru_kernel<false><<<items < sms ? items : sms, wide::THREADS, wide::G_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int imp_wide_pool(const imp_graph_t* g, int32_t d, const void* d_workspace, float* d_pooled, void* stream) {
   if (int rc = wide_check(g, d, wide::KB, IMP_TC_FP16, d_workspace, "imp_wide_pool")) return rc;
   if (g->n_pairs == 0) return 0;
@@ -608,8 +933,12 @@ extern "C" int imp_mpnn_forward_wide(const imp_graph_t* g, const float* d_atom_e
   for (int s = 0; s < num_steps; ++s) {
     const void *pc = pk + (int64_t)s * wide::PACK_BYTES, *pa = pk + (int64_t)(num_steps + s) * wide::PACK_BYTES;
     if (int rc = imp_wide_message(g, d_bond_emb, d, bond_dim, pc, pa, flags, d_workspace, stream)) return rc;
-    if (int rc = imp_wide_gates(g, d, pc, pa, flags, d_workspace, stream)) return rc;
-    if (int rc = imp_wide_candidate(g, d, pc, pa, eps, flags, d_workspace, stream)) return rc;
+    if (flags & IMP_TC_WIDE_SPLIT_GRU) {
+      if (int rc = imp_wide_gates(g, d, pc, pa, flags, d_workspace, stream)) return rc;
+      if (int rc = imp_wide_candidate(g, d, pc, pa, eps, flags, d_workspace, stream)) return rc;
+    } else if (int rc = imp_wide_gated_update(g, d, pc, pa, eps, flags, d_workspace, stream)) {
+      return rc;
+    }
   }
   return imp_wide_pool(g, d, d_workspace, d_pooled, stream);
 }

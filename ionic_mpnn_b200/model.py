@@ -385,8 +385,11 @@ class MPNNModel(TrainMixin):
             for i in range(S):
                 pc, pa = pk + wb * i, pk + wb * (S + i)
                 _lib.call("imp_wide_message", C.byref(g), self._ptr("bond_emb"), d, s["bond_dim"], pc, pa, f, w, st)
-                _lib.call("imp_wide_gates", C.byref(g), d, pc, pa, f, w, st)
-                _lib.call("imp_wide_candidate", C.byref(g), d, pc, pa, C.c_float(self.LN_EPS), f, w, st)
+                if f & _lib.TC_WIDE_SPLIT_GRU:
+                    _lib.call("imp_wide_gates", C.byref(g), d, pc, pa, f, w, st)
+                    _lib.call("imp_wide_candidate", C.byref(g), d, pc, pa, C.c_float(self.LN_EPS), f, w, st)
+                else:
+                    _lib.call("imp_wide_gated_update", C.byref(g), d, pc, pa, C.c_float(self.LN_EPS), f, w, st)
             _lib.call("imp_wide_pool", C.byref(g), d, w, pooled.data_ptr(), st)
         else:
             _lib.call("imp_mpnn_forward_wide", C.byref(g), self._ptr("atom_emb"), s["atom_vocab_size"], self._ptr("bond_emb"),

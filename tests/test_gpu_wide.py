@@ -32,8 +32,9 @@ def test_wide_tensor_path_matches_fp64_oracle(n_pairs, num_steps, n_min, n_max, 
     assert err <= HALF_RTOL, err
 
 
-@pytest.mark.parametrize("kind,n_pairs,seed", [("viscosity", 700, 11), ("melting_point", 130, 12)])
-def test_wide_tensor_path_vs_fp32_kernels_many_tiles(kind, n_pairs, seed):
+@pytest.mark.parametrize("kind,n_pairs,seed,tc_flags", [("viscosity", 700, 11, 0), ("melting_point", 130, 12, 0),
+                                                       ("viscosity", 300, 13, 64)])
+def test_wide_tensor_path_vs_fp32_kernels_many_tiles(kind, n_pairs, seed, tc_flags):
     """More super-tiles than SMs (persistent loop, both towers, the straddling tile), compared with the fp32 staged
     kernels (themselves held to the oracle at 2e-5 in test_gpu_parity): every atom state after the last step and every
     molecule sum at half-precision accuracy, predictions within the north-star tolerance."""
@@ -51,6 +52,7 @@ def test_wide_tensor_path_vs_fp32_kernels_many_tiles(kind, n_pairs, seed):
     want, inter = ref.forward_packed(batch, keep=True)
     model = MPNNModel(spec, seed=5, precision="fp16")
     model.set_weights(ref.get_weights())
+    model.extra_tc_flags = tc_flags  # 64 = IMP_TC_WIDE_SPLIT_GRU: GatedUpdate as two kernels
     got = model.forward_packed(batch)
     again = model.forward_packed(batch).clone()
     torch.cuda.synchronize()

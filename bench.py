@@ -68,8 +68,8 @@ def workload_config(args):
     elif args.workload == "wide":
         P = args.pairs_per_gpu or 16_384
         kind = "viscosity"
-        name = ("BASELINE configs[4]: wide/deep viscosity MPNN forward (atom_dim 256, bond_dim 8, 6 steps, 40-120 atoms/ion), "
-                "fp32 general-shape kernels")
+        name = ("BASELINE configs[4]: wide/deep viscosity MPNN forward (atom_dim 256, bond_dim 8, 6 steps, 40-120 atoms/ion); "
+                "fp16 = tcgen05 GEMM kernels (csrc/wide_tc.cu), fp32 = general-shape SIMT kernels")
     elif args.workload == "visc_train":
         P = args.pairs_per_gpu or 65_536
         kind = "viscosity"
@@ -147,7 +147,7 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------ reference arm / cpu baseline
-def cpu_reference_run(kind, n_pairs, steps, warmup, skewed):
+def cpu_reference_run(kind, n_pairs, steps, warmup, skewed, wide=False):
     """Times oracle/ref_model.py (fp32, all host threads) the way the reference predicts: padded inputs,
     ``model.predict(x)`` with Keras' default batch size 32 (train_viscosity.py:366)."""
     import torch
@@ -157,8 +157,11 @@ def cpu_reference_run(kind, n_pairs, steps, warmup, skewed):
 
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    recs = synth.make_records(n_pairs, seed=1002, skewed=skewed, label="log_eta" if kind == "viscosity" else "mp")
-    spec = ref_model.make_spec(kind)
+    if wide:  # configs[4]: ~240x the arithmetic per pair, and a (B, E, d, d) temporary of 68 MB per pair
+        n_pairs = min(n_pairs, 64)
+    recs = synth.make_records(n_pairs, seed=1002, skewed=skewed, label="log_eta" if kind == "viscosity" else "mp",
+                              **({"n_min": 40, "n_max": 120} if wide else {}))
+    spec = ref_model.make_spec(kind, atom_dim=256, num_steps=6) if wide else ref_model.make_spec(kind)
     params = ref_model.init_params(spec, seed=1)
     x = ref_inputs.build_inputs(recs, with_temperature=kind == "viscosity")
     best = None
@@ -171,9 +174,11 @@ def cpu_reference_run(kind, n_pairs, steps, warmup, skewed):
             times.append(dt)
     mean = sum(times) / len(times)
     # the same port with a large batch ("also batch_size=1024 for a fairer number"), one run after the warm-up
-    t0 = time.perf_counter()
-    ref_model.predict(spec, params, x, dtype=torch.float32, batch_size=1024)
-    big = n_pairs / (time.perf_counter() - t0)
+    big = None
+    if not wide:
+        t0 = time.perf_counter()
+        ref_model.predict(spec, params, x, dtype=torch.float32, batch_size=1024)
+        big = n_pairs / (time.perf_counter() - t0)
     return {"value": n_pairs / mean, "value_batch1024": big, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n_pairs} synthetic pairs (seed 1002), padded as the reference pads, predict(batch_size=32), "
                       f"torch fp32 CPU port of models/layers.py, mean of {len(times)} runs after {warmup} warm-up",
@@ -187,7 +192,7 @@ def run_reference(args):
     P, kind, name = workload_config(args)
     warm = max(1, min(args.warmup, 2))
     steps = max(1, min(args.steps, 5))
-    r = cpu_reference_run(kind, args.cpu_sample_pairs, steps, warm, args.skewed)
+    r = cpu_reference_run(kind, args.cpu_sample_pairs, steps, warm, args.skewed, wide=args.workload == "wide")
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -203,7 +208,10 @@ def stage_flops(batch, d, S):
     gated update 12*N*d^2, per step."""
     N, E = batch.n_atoms, batch.n_edges
     return {"mpnn_forward_fused": S * (2 * E + 12 * N) * d * d, "gated_update_tc": 12 * N * d * d,
-            "gated_update_wide": 12 * N * d * d, "message_agg": 2 * batch.n_unique * d * d}
+            "gated_update_wide": 12 * N * d * d, "message_agg": 2 * batch.n_unique * d * d,
+            # wide tensor path: algorithmic message work is 2*E*d^2 (the kernel executes 16*N*d^2 as Z.Wc, K = 8d)
+            "wide_message": 2 * E * d * d, "wide_gated_update": 12 * N * d * d,
+            "edge_messages_tc": 2 * batch.n_unique * d * d}
 
 
 def stage_bytes(batch, d, S, s=4):
@@ -217,9 +225,18 @@ def stage_bytes(batch, d, S, s=4):
         "readout_mp": 2 * P * d * 4 + 4 * P,
         "embed_atoms": 4 * N + N * d * s,
         "message_agg": 2 * N * d * s + 8 * Eu + 4 * N,   # h in, agg out, (src, bond|mult) per unique entry, row_ptr
+        # grouped tcgen05 message GEMM (csrc/msg_tc.cu): one gathered source row in, one message row out per unique
+        # entry, bucket_perm + src + bond|mult; then the CSR segment sum
+        "edge_messages_tc": Eu * (2 * d * 4 + 12),
+        "segment_sum": Eu * d * 4 + N * d * 4 + 4 * N,
         "gated_update": 3 * N * d * s,                    # h, agg in; h out
         "gated_update_tc": 3 * N * d * s,
         "gated_update_wide": 3 * N * d * s,
+        # wide tensor path (16-bit operand copies next to the fp32 state, csrc/wide_tc.cu)
+        "wide_embed": 4 * N + N * d * 6,
+        "wide_message": N * d * 2 + N * d * 2 + 8 * Eu + 4 * N,          # h16 in, agg16 out, entries, row_ptr
+        "wide_gated_update": N * d * (2 + 2 + 4) + N * d * (4 + 2),      # h16, agg16, h32 in; h32, h16 out
+        "wide_pool": N * d * 4 + 4 * N + 8 * P + 2 * P * d * 4,
         "pool_head": N * d * s + 4 * N + 8 * P + 8 * P,   # h, atom_id, mol_ptr (2 towers), T + out
     }
 
@@ -339,7 +356,7 @@ def run_b200(args):
     P, kind, name = workload_config(args)
     wide = args.workload == "wide"
     spec = make_spec(kind, atom_dim=256, num_steps=6) if wide else make_spec(kind)
-    if wide:
+    if wide and args.precision not in ("fp16", "fp16_precise"):
         args.precision = "fp32"
     model = MPNNModel(spec, device=f"cuda:{local}", seed=0, precision=args.precision,
                       fused=False if args.staged else "auto")
@@ -402,11 +419,13 @@ def run_b200(args):
 
         import ionic_mpnn_b200.model as mm
         mm._lib.call = timed_call
+        model.wide_per_stage_calls = True  # wide path: one ABI call per kernel, so that each one is timed
         try:
             for _ in range(2):
                 model.forward_packed(batch)
         finally:
             mm._lib.call = real_call
+            model.wide_per_stage_calls = False
         torch.cuda.synchronize()
         for kname, e0, e1 in events:
             per_kernel.setdefault(kname.replace("imp_", ""), []).append(e0.elapsed_time(e1))
@@ -502,7 +521,23 @@ def run_b200(args):
                       "share": tot_ms[k] / sum(tot_ms.values()),
                       "GBps": (sb[k] / (mean_ms[k] * 1e-3) / 1e9) if k in sb else None,
                       "TFLOPs": (sf[k] / (mean_ms[k] * 1e-3) / 1e12) if k in sf else None} for k in mean_ms}
-            if dom == "mpnn_forward_fused":
+            if dom in ("wide_message", "wide_gated_update"):
+                # d = 256: 238+ FLOP per activation byte => tensor-bound; achieved = algorithmic FLOP of the
+                # kernel / its launch time.  The message kernel executes 16*N*d^2 (Z.Wc with K = 8d) for 2*E*d^2
+                # algorithmic; "executed_TFLOPs" reports what the tensor pipe actually ran.
+                ach = sf[dom] / (mean_ms[dom] * 1e-3) / 1e12
+                executed = {"wide_message": 16 * batch.n_atoms * d * d, "wide_gated_update": 12 * batch.n_atoms * d * d}
+                for kk in executed:
+                    if kk in pk:
+                        pk[kk]["executed_TFLOPs"] = executed[kk] / (mean_ms[kk] * 1e-3) / 1e12
+                step_flop = S * (2 * batch.n_edges + 12 * batch.n_atoms) * d * d
+                roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                            "frac": ach / tf_peak, "traffic": None, "peak_source": peak_src + ", sustained bf16",
+                            "algorithmic_flop_per_launch": sf[dom], "algorithmic_bytes_per_launch": sb.get(dom),
+                            "executed_TFLOPs": executed[dom] / (mean_ms[dom] * 1e-3) / 1e12,
+                            "whole_forward_algorithmic_TFLOPs": step_flop / (ms_total / args.steps * 1e-3) / 1e12,
+                            "whole_forward_frac": step_flop / (ms_total / args.steps * 1e-3) / 1e12 / tf_peak}
+            elif dom == "mpnn_forward_fused":
                 # the fused kernel keeps every activation on chip: 2.7 kFLOP per byte of index stream, far right of
                 # the ridge (211 FLOP/B) => the tensor roofline is the one that bounds it
                 ach = sf[dom] / (mean_ms[dom] * 1e-3) / 1e12
@@ -522,7 +557,7 @@ def run_b200(args):
                              "per_kernel": pk})
         cpu = None
         if not args.no_cpu_baseline:
-            r = cpu_reference_run(kind, args.cpu_sample_pairs, 3, 1, args.skewed)
+            r = cpu_reference_run(kind, args.cpu_sample_pairs, 3, 1, args.skewed, wide=wide)
             cpu = {k: r[k] for k in ("value", "value_batch1024", "unit", "cores", "kind", "sample")}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -533,7 +568,8 @@ def run_b200(args):
                 "config": {"workload": name, "pairs_per_gpu": P, "atoms_per_gpu": batch.n_atoms,
                            "edges_per_gpu": batch.n_edges, "unique_edges_per_gpu": batch.n_unique,
                            "bond_types": "zipf1.2" if args.skewed else "uniform", "precision": args.precision,
-                           "path": "fused whole-tower kernel" if model.use_fused(batch) else "staged per-layer kernels",
+                           "path": "wide tcgen05 GEMM kernels" if model.wide_supported() else
+                           "fused whole-tower kernel" if model.use_fused(batch) else "staged per-layer kernels",
                            "l2_policy": "inputs larger than L2 (%.1f GB of indices%s per GPU)" % (
                                batch.nbytes() / 1e9, "" if model.use_fused(batch) else
                                " + %.1f GB of activations" % (3 * batch.n_atoms * d * 4 / 1e9)),

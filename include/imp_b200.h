@@ -185,6 +185,20 @@ int imp_gated_update_tc(const float* d_h, const float* d_agg, int32_t n_atoms, i
                         const void* d_packed_cat, const void* d_packed_an, float eps, int32_t flags,
                         float* d_h_out, void* stream);
 
+/* K3 on the tensor cores for atom_dim 32, any bond_dim (the message kernel of the melting-point model, bond_dim 1024):
+ * the bond-type-grouped GEMM  M_b = H_src,b . T[b]^T  per (tower, bond) bucket -- chunks of 128 gathered source rows as
+ * the shared-memory A operand, T[b] as B, tcgen05.mma with fp32 accumulators in TMEM, rows scaled by the multiplicity
+ * and written at the entry's CSR position (csrc/msg_tc.cu).  Same output contract as imp_edge_messages at 16-bit
+ * operand precision (the "2e-2" path); follow with imp_segment_sum (Reduce).  Needs the graph's bucket arrays.
+ *   imp_message_pack   table [V_b, d, d] (imp_bond_table's d_table) -> imp_message_pack_bytes() bytes, once per weight
+ *                      update and per (tower, step);  flags: IMP_TC_FP16 (must match the forward call).
+ *   d_workspace        imp_edge_messages_tc_workspace_bytes(bond_vocab) bytes (per-bucket chunk offsets). */
+int64_t imp_message_pack_bytes(int32_t bond_vocab, int32_t d);
+int imp_message_pack(const float* d_table, int32_t bond_vocab, int32_t d, int32_t flags, void* d_packed, void* stream);
+int64_t imp_edge_messages_tc_workspace_bytes(int32_t bond_vocab);
+int imp_edge_messages_tc(const imp_graph_t* g, const float* d_h, int32_t d, const void* d_packed_cat, const void* d_packed_an,
+                         int32_t flags, float* d_msg /* [Eu, d] */, void* d_workspace, void* stream);
+
 /* GlobalSumPool.call alone (models/layers.py:161-164): out[m,:] = sum of h rows of molecule m whose
  * atom_id > 0.  `n_mols` molecules delimited by d_mol_ptr[n_mols+1]. */
 int imp_global_sum_pool(const int32_t* d_mol_ptr, const int32_t* d_atom_id, int32_t n_mols, const float* d_h, int32_t d,

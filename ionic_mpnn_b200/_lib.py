@@ -83,6 +83,10 @@ SIGNATURES = {
     "imp_gru_pack_bf16": (C.c_int, [C.POINTER(GruWeights), C.c_int32, vp, vp]),
     "imp_gru_pack_f16": (C.c_int, [C.POINTER(GruWeights), C.c_int32, vp, vp]),
     "imp_gated_update_tc": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_float, C.c_int32, vp, vp]),
+    "imp_message_pack_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "imp_message_pack": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
+    "imp_edge_messages_tc_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "imp_edge_messages_tc": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp]),
     "imp_global_sum_pool": (C.c_int, [vp, vp, C.c_int32, vp, C.c_int32, vp, vp]),
     "imp_pool_head_visc": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ReadoutWeights),
                                      C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp]),

@@ -1,0 +1,202 @@
+// BondMatrixMessage (models/layers.py:100-117) for atom_dim 32 on the tensor cores, from the bond-matrix TABLE (any
+// bond_dim: this is the message kernel of the melting-point model, bond_dim = 1024, BASELINE configs[1]) -- the
+// north-star's "bond-type-grouped tcgen05 GEMM over gathered h_src rows":
+//
+//     for every (tower, bond type) bucket b:   M_b = H_src,b . T[b]^T     (E_b x 32) = (E_b x 32) . (32 x 32)
+//
+// The CSR entries are already grouped by (tower, bond) through bucket_perm (oracle/ref_pack.py, pack_host.cpp).  A CTA
+// takes one chunk of <= 128 consecutive slots of ONE bucket: the source rows of its slots are gathered (128 B each, fp32 ->
+// 16-bit) into the shared-memory A operand (canonical K-major UMMA layout), the 2 KB operand image of T[b] is copied
+// next to it, one elected lane issues two tcgen05.mma (M = 128, N = 32, K = 16) into 32 TMEM columns, and the epilogue
+// scales row t by the entry's multiplicity and writes it at the entry's CSR position -- where Reduce
+// (models/layers.py:57-83) is the contiguous, deterministic segment sum of imp_segment_sum.
+// The kernel is a pure gather/scatter stream (~270 B per entry); the 1,024 FMA per entry that made the SIMT kernels
+// L1/FMA-bound (fwd_fp32.cu, profiles/README.md) cost two tensor instructions per 128 entries.  CTAs are small
+// (128 threads, 17 KB of shared memory, 32 TMEM columns) so that ~9 of them overlap their gather latencies per SM.
+//
+// (A first version built agg = Z . Tcat with a block-sparse Z of K = 32 * bond_vocab in shared memory: correct, but the
+// A operand traffic of 72 mostly-zero K blocks made it shared-memory-bandwidth-bound at 1.7 ms per step on configs[1].)
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+extern "C" int imp_device_is_sm100(void);
+
+namespace imp {
+namespace msgtc {
+
+constexpr int D = 32;
+constexpr int CHUNK = 128;                   // slots per CTA = MMA M
+constexpr int A_BYTES = CHUNK * D * 2;       // 8 KB
+constexpr int B_BYTES = D * D * 2;           // 2 KB per bond type
+
+// chunk_ptr[b] = first chunk of bucket b (b over 2 * V_b (tower, bond) buckets); chunk_ptr[2 V_b] = number of chunks
+__global__ void chunk_scan_kernel(const int32_t* __restrict__ bucket_ptr, int n_buckets, int32_t* __restrict__ chunk_ptr) {
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int b = 0; b < n_buckets; ++b) {
+      chunk_ptr[b] = c;
+      c += (bucket_ptr[b + 1] - bucket_ptr[b] + CHUNK - 1) / CHUNK;
+    }
+    chunk_ptr[n_buckets] = c;
+  }
+}
+
+// Memory access shape: 8 lanes share one 128-byte row (gather of h[src], store of msg[e]), i.e. a warp instruction touches 4
+// whole lines instead of 32 partial ones (the one-thread-per-row form spent 8x the L1 wavefronts and ran at 2.1 TB/s).
+// The accumulator rows (thread = TMEM lane = slot) are transposed to that shape through a padded shared-memory tile that
+// aliases the operand buffers once the MMAs have completed.
+constexpr int STG_LD = D + 1;                                   // padded fp32 row
+constexpr int SMEM_UNION = CHUNK * STG_LD * 4 > A_BYTES + B_BYTES ? CHUNK * STG_LD * 4 : A_BYTES + B_BYTES;
+
+template <int FMT>
+__global__ void __launch_bounds__(CHUNK) grouped_msg_kernel(const int32_t* __restrict__ bucket_ptr, const int32_t* __restrict__ chunk_ptr,
+                                                            int n_buckets, int bond_vocab, const int32_t* __restrict__ bucket_perm,
+                                                            const int32_t* __restrict__ col_src, const int32_t* __restrict__ edge_bm,
+                                                            const float* __restrict__ h, const uint8_t* __restrict__ packed_cat,
+                                                            const uint8_t* __restrict__ packed_an, float* __restrict__ msg) {
+  __shared__ __align__(128) uint8_t su[SMEM_UNION];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t *sA = su, *sB = su + A_BYTES;
+  float* stg = reinterpret_cast<float*>(su);
+  const int chunk = blockIdx.x;
+  if (chunk >= __ldg(chunk_ptr + n_buckets)) return;
+  // bucket of this chunk: last b with chunk_ptr[b] <= chunk
+  int lo = 0, hi = n_buckets - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(chunk_ptr + mid) <= chunk) lo = mid; else hi = mid - 1;
+  }
+  const int b = lo;
+  const int slot0 = __ldg(bucket_ptr + b) + (chunk - __ldg(chunk_ptr + b)) * CHUNK;
+  const int n = min(CHUNK, __ldg(bucket_ptr + b + 1) - slot0);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const uint8_t* tb = (b < bond_vocab ? packed_cat + (int64_t)b * B_BYTES : packed_an + (int64_t)(b - bond_vocab) * B_BYTES);
+
+  if (t == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 0) tc::tmem_alloc<32>(&tmem_slot);
+  // operand image of T[b]: 128 threads x 16 B
+  *reinterpret_cast<uint4*>(sB + t * 16) = __ldg(reinterpret_cast<const uint4*>(tb) + t);
+  int e = -1, src = 0;
+  float mult = 0.f;
+  if (t < n) {
+    e = __ldg(bucket_perm + slot0 + t);
+    mult = (float)((uint32_t)__ldg(edge_bm + e) >> 16);
+    src = __ldg(col_src + e);
+  }
+  // gather: lane group g = lane / 8 takes slot 4 * it + g of this warp, lane % 8 = float4 of the row
+  const int g = lane >> 3, q = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = 4 * it + g;  // slot within the warp
+    const int rs = __shfl_sync(0xffffffffu, src, r), re = __shfl_sync(0xffffffffu, e, r);
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (re >= 0) x = __ldg(reinterpret_cast<const float4*>(h + (int64_t)rs * D) + q);
+    // piece p = q / 2 (k in [8p, 8p+8)), half (q % 2) of its 16 bytes
+    *reinterpret_cast<uint2*>(sA + (q >> 1) * 2048 + (warp * 32 + r) * 16 + (q & 1) * 8) =
+        make_uint2(tc::pack2<FMT>(x.x, x.y), tc::pack2<FMT>(x.z, x.w));
+  }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = tc::make_idesc(FMT, CHUNK, D);
+    const uint64_t da = tc::make_smem_desc(tc::smem_u32(sA), 2048, 128), db = tc::make_smem_desc(tc::smem_u32(sB), D * 16, 128);
+    if (tc::elect_one()) {
+      tc::mma_bf16(tmem, da, db, idesc, false);
+      tc::mma_bf16(tmem, da + (uint64_t)(4096 >> 4), db + (uint64_t)((2 * D * 16) >> 4), idesc, true);
+      tc::mma_commit(&bar);
+    }
+    __syncwarp();
+  }
+  tc::mbar_wait(&bar, 0);  // the MMAs have read the operands: the buffers may be reused as the staging tile
+  tc::fence_after_thread_sync();
+  float v[32];
+  tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+  // (the mbarrier completes only after both MMAs have read the operands, so no further CTA-wide sync is needed here)
+#pragma unroll
+  for (int c = 0; c < 32; ++c) stg[t * STG_LD + c] = mult * v[c];
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = 4 * it + g;
+    const int re = __shfl_sync(0xffffffffu, e, r);
+    const float* sr = stg + (warp * 32 + r) * STG_LD + 4 * q;
+    const float4 o = make_float4(sr[0], sr[1], sr[2], sr[3]);
+    if (re >= 0) reinterpret_cast<float4*>(msg + (int64_t)re * D)[q] = o;
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc::fence_after_thread_sync();
+    tc::tmem_dealloc<32>(tmem);
+  }
+}
+
+// table [V_b, d, d] fp32 (T[b][l][m], models/layers.py:108-112) -> per bond type one 2 KB image of the canonical K-major
+// B operand [piece c of 4][n = l of 32][8 halfs]: B[n][kk] = T[b][n][kk], kk = c*8 + i = m.
+template <int FMT>
+__global__ void msg_pack_kernel(const float* __restrict__ table, int bond_vocab, uint16_t* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= bond_vocab * D * D) return;
+  const int i = idx & 7, n = (idx >> 3) & 31, c = (idx >> 8) & 3, b = idx >> 10;
+  out[idx] = tc::cvt16<FMT>(table[((int64_t)b * D + n) * D + c * 8 + i]);
+}
+
+}  // namespace msgtc
+}  // namespace imp
+
+using namespace imp;
+
+extern "C" int64_t imp_message_pack_bytes(int32_t bond_vocab, int32_t d) {
+  if (d != msgtc::D || bond_vocab <= 0) return IMP_ERR_DIM;
+  return (int64_t)bond_vocab * msgtc::B_BYTES;
+}
+
+extern "C" int imp_message_pack(const float* d_table, int32_t bond_vocab, int32_t d, int32_t flags, void* d_packed, void* stream) {
+  IMP_REQUIRE(d == msgtc::D, IMP_ERR_DIM, "imp_message_pack: atom_dim %d not supported by the tensor path (32)", d);
+  IMP_REQUIRE(d_table && d_packed && bond_vocab > 0 && bond_vocab <= 65535, IMP_ERR_ARG, "imp_message_pack: bad arguments");
+  const int n = bond_vocab * msgtc::D * msgtc::D;
+  if (flags & IMP_TC_FP16)
+    msgtc::msg_pack_kernel<tc::FMT_F16><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_table, bond_vocab, (uint16_t*)d_packed);
+  else
+    msgtc::msg_pack_kernel<tc::FMT_BF16><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_table, bond_vocab, (uint16_t*)d_packed);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int64_t imp_edge_messages_tc_workspace_bytes(int32_t bond_vocab) { return (int64_t)(2 * bond_vocab + 1) * 4; }
+
+extern "C" int imp_edge_messages_tc(const imp_graph_t* g, const float* d_h, int32_t d, const void* d_packed_cat,
+                                    const void* d_packed_an, int32_t flags, float* d_msg, void* d_workspace, void* stream) {
+  IMP_REQUIRE(g, IMP_ERR_ARG, "imp_edge_messages_tc: graph is null");
+  IMP_REQUIRE(d == msgtc::D, IMP_ERR_DIM, "imp_edge_messages_tc: atom_dim %d not supported by the tensor path (32)", d);
+  if (g->n_unique == 0) return 0;
+  IMP_REQUIRE(d_h && d_msg && d_packed_cat && d_packed_an && d_workspace && g->bucket_ptr && g->bucket_perm && g->col_src && g->edge_bm,
+              IMP_ERR_ARG, "imp_edge_messages_tc: null pointer (the bond-bucket permutation is required)");
+  IMP_REQUIRE(g->bond_vocab > 0 && g->bond_vocab <= 65535, IMP_ERR_ARG, "imp_edge_messages_tc: bond vocabulary out of range");
+  IMP_REQUIRE(imp_device_is_sm100(), IMP_ERR_UNSUPPORTED, "imp_edge_messages_tc: tcgen05 needs an sm_100 device");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = 2 * g->bond_vocab;
+  int32_t* chunk_ptr = reinterpret_cast<int32_t*>(d_workspace);
+  msgtc::chunk_scan_kernel<<<1, 32, 0, st>>>(g->bucket_ptr, nb, chunk_ptr);
+  IMP_LAUNCH_CHECK();
+  const unsigned grid = (unsigned)(ceil_div(g->n_unique, msgtc::CHUNK) + nb);  // upper bound; surplus CTAs exit at once
+  const uint8_t *pc = reinterpret_cast<const uint8_t*>(d_packed_cat), *pa = reinterpret_cast<const uint8_t*>(d_packed_an);
+  if (flags & IMP_TC_FP16)
+    msgtc::grouped_msg_kernel<tc::FMT_F16><<<grid, msgtc::CHUNK, 0, st>>>(g->bucket_ptr, chunk_ptr, nb, g->bond_vocab, g->bucket_perm,
+                                                                         g->col_src, g->edge_bm, d_h, pc, pa, d_msg);
+  else
+    msgtc::grouped_msg_kernel<tc::FMT_BF16><<<grid, msgtc::CHUNK, 0, st>>>(g->bucket_ptr, chunk_ptr, nb, g->bond_vocab, g->bucket_perm,
+                                                                          g->col_src, g->edge_bm, d_h, pc, pa, d_msg);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}

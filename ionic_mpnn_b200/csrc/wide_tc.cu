@@ -230,6 +230,13 @@ __global__ void __launch_bounds__(THREADS, 1) wide_gemm_kernel(const Args a) {
             for (int q = 0; q < 4; ++q) cm[e][q] = __hmul2(c2[q], mult);
           }
         }
+        // the gathers of slice j + 1 are in flight while slice j is accumulated (they do not depend on a stage being free)
+        uint4 hw[REG_ENTRIES], hnext[REG_ENTRIES];
+#pragma unroll
+        for (int e = 0; e < REG_ENTRIES; ++e) {
+          hnext[e] = make_uint4(0, 0, 0, 0);
+          if (e < deg) hnext[e] = __ldg(reinterpret_cast<const uint4*>(a.h16 + soff[e]));
+        }
         for (int j = 0; j < MSG_CHUNKS; ++j, ++it) {
           const int s = it % STAGES;
           __half2 acc[8][4];
@@ -237,11 +244,11 @@ __global__ void __launch_bounds__(THREADS, 1) wide_gemm_kernel(const Args a) {
           for (int p = 0; p < 8; ++p)
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[p][q] = __float2half2_rn(0.f);
-          // gathers first (they do not depend on the stage being free)
-          uint4 hw[REG_ENTRIES];
 #pragma unroll
-          for (int e = 0; e < REG_ENTRIES; ++e)
-            if (e < deg) hw[e] = __ldg(reinterpret_cast<const uint4*>(a.h16 + soff[e] + j * 2048));
+          for (int e = 0; e < REG_ENTRIES; ++e) {
+            hw[e] = hnext[e];
+            if (e < deg && j + 1 < MSG_CHUNKS) hnext[e] = __ldg(reinterpret_cast<const uint4*>(a.h16 + soff[e] + (j + 1) * 2048));
+          }
 #pragma unroll
           for (int e = 0; e < REG_ENTRIES; ++e) {
             if (e < deg) {

@@ -193,6 +193,13 @@ class MPNNModel(TrainMixin):
             nbytes = _lib.load().imp_gru_pack_bytes(d)
             if nbytes < 0:
                 raise _lib.ImpError(f"tensor path does not support atom_dim {d}")
+            # tensor-core message kernel (csrc/msg_tc.cu): the tables as UMMA operand slices
+            mb = _lib.load().imp_message_pack_bytes(Vb, d)
+            self._msg_pack_bytes = (mb + 255) // 256 * 256
+            mpk = self._buf("msg_packed", self._msg_pack_bytes * n, torch.uint8)
+            for j in range(n):
+                _lib.call("imp_message_pack", tab.data_ptr() + 4 * per * j, Vb, d, self.tc_flags(),
+                          mpk.data_ptr() + self._msg_pack_bytes * j, _stream())
             self._gru_pack_bytes = (nbytes + 255) // 256 * 256
             pk = self._buf("gru_packed", self._gru_pack_bytes * n, torch.uint8)
             pack_fn = "imp_gru_pack_f16" if self.precision.startswith("fp16") else "imp_gru_pack_bf16"
@@ -296,6 +303,14 @@ class MPNNModel(TrainMixin):
                 msg = self._buf("msg", batch.n_unique * d)
                 _lib.call("imp_edge_messages", C.byref(g), h[i].data_ptr(), d, self.table_ptr(0, i, False),
                           self.table_ptr(1, i, False), msg.data_ptr(), st)
+                _lib.call("imp_segment_sum", C.byref(g), msg.data_ptr(), d, aggs[i].data_ptr(), st)
+            elif self.precision != "fp32" and d == 32 and not getattr(self, "simt_messages", False):
+                # bond-type-grouped tcgen05 GEMM over gathered source rows, then the CSR segment sum (csrc/msg_tc.cu)
+                mbase = self._ws["msg_packed"].data_ptr()
+                msg = self._buf("msg", batch.n_unique * d)
+                cws = self._buf("msg_chunks", 2 * s["bond_vocab_size"] + 1, torch.int32)
+                _lib.call("imp_edge_messages_tc", C.byref(g), h[i].data_ptr(), d, mbase + self._msg_pack_bytes * i,
+                          mbase + self._msg_pack_bytes * (S + i), self.tc_flags(), msg.data_ptr(), cws.data_ptr(), st)
                 _lib.call("imp_segment_sum", C.byref(g), msg.data_ptr(), d, aggs[i].data_ptr(), st)
             else:
                 _lib.call("imp_message_agg", C.byref(g), h[i].data_ptr(), d, self.table_ptr(0, i, True),
@@ -418,7 +433,9 @@ class MPNNModel(TrainMixin):
     def launches_per_forward(self, batch=None):
         """Kernels enqueued by forward_packed (tables / packs already valid)."""
         if self.wide_supported():
-            return 2 + 3 * self.spec["num_steps"] + 1
+            return 2 + 2 * self.spec["num_steps"] + 1
+        if self.precision != "fp32" and self.spec["atom_dim"] == 32:
+            return 1 + 4 * self.spec["num_steps"] + 1  # chunk scan, grouped GEMM, segment sum, GatedUpdate per step
         if batch is not None and self.use_fused(batch):
             return 2
         return 1 + 2 * self.spec["num_steps"] + 1

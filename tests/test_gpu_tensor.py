@@ -113,6 +113,47 @@ def test_bf16_gated_update_vs_fp32_kernel_per_step():
     assert batch.n_cat_atoms % 128 != 0 or (batch.n_atoms - batch.n_cat_atoms) % 128 != 0
 
 
+@pytest.mark.parametrize("kind,precision", [("viscosity", "fp16"), ("viscosity", "bf16"), ("melting_point", "fp16")])
+def test_tensor_message_kernel_vs_fp32_kernel(kind, precision):
+    """imp_edge_messages_tc (csrc/msg_tc.cu: bond-type-grouped tcgen05 GEMM over gathered source rows) + imp_segment_sum
+    against imp_message_agg (fp32 SIMT) on the SAME atom states, for every step's table of both towers."""
+    import ctypes as C
+
+    from ionic_mpnn_b200 import _lib, graph
+    from ionic_mpnn_b200.model import MPNNModel, make_spec
+
+    spec = make_spec(kind)
+    batch, _, _ = graph.synth_batch(1800, seed=21, with_temperature=(kind == "viscosity"))
+    batch.to("cuda")
+    ref = MPNNModel(spec, seed=3, precision="fp32")
+    _, ia = ref.forward_packed(batch, keep=True)
+    m = MPNNModel(spec, seed=3, precision=precision, fused=False)
+    m.refresh_tables()
+    g = batch.c_struct()
+    S, d = spec["num_steps"], 32
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert batch.n_atoms > 148 * 256 and batch.n_cat_atoms % 256 != 0
+    for i in range(S):
+        h = ia["h"][i].contiguous()
+        agg = torch.full_like(h, float("nan"))
+        msg = torch.full((batch.n_unique, d), float("nan"), device="cuda")
+        cws = torch.empty(2 * 72 + 1, dtype=torch.int32, device="cuda")
+        base = m._ws["msg_packed"].data_ptr()
+        _lib.call("imp_edge_messages_tc", C.byref(g), h.data_ptr(), d, base + m._msg_pack_bytes * i,
+                  base + m._msg_pack_bytes * (S + i), m.tc_flags(), msg.data_ptr(), cws.data_ptr(), st)
+        _lib.call("imp_segment_sum", C.byref(g), msg.data_ptr(), d, agg.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert torch.isfinite(msg).all(), "every CSR entry must have been written exactly once"
+        want = ia["agg"][i]
+        err = float((agg - want).abs().max() / want.abs().max())
+        print(f"{kind} {precision} step {i}: |agg| max {float(want.abs().max()):.3f}, tensor message kernel err {err:.3e}")
+        assert torch.isfinite(agg).all()
+        assert err <= (2e-3 if precision == "fp16" else 1.6e-2), err
+        # rows without live entries (the first atom of every ion) are exactly zero
+        deg = torch.from_numpy(np.diff(batch.host["row_ptr"])).cuda()
+        assert float(agg[deg == 0].abs().max()) == 0.0
+
+
 def test_bf16_cfg1_thousand_pairs_vs_fp64_oracle():
     from ionic_mpnn_b200 import synth
     from ionic_mpnn_b200.viscosity import build_model

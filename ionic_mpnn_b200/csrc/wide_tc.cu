@@ -431,13 +431,15 @@ constexpr int G_A_BYTES = TILE * G_KC * 2;                        // 8 KB
 constexpr int G_B_BYTES = D * G_KC * 2;                           // 16 KB per gate
 constexpr int G_STAGE_BYTES = G_A_BYTES + 2 * G_B_BYTES;          // 40 KB
 constexpr int G_X_BYTES = TILE * D * 2;                           // 64 KB
+constexpr int G_CH = 4, G_WORKERS = 4 * G_CH, G_COLS = D / G_CH;  // worker warps: 4 lane quarters x G_CH column slices
+constexpr int G_THREADS = (G_WORKERS + 2) * 32;
 
 struct GCtl {
   uint64_t full[G_STAGES], empty[G_STAGES], x_full, accA, rh_ready, accB, acc_empty;
   uint32_t tmem;
 };
 constexpr int G_OFF_X = G_STAGES * G_STAGE_BYTES, G_OFF_VEC = G_OFF_X + G_X_BYTES, G_OFF_RED = G_OFF_VEC + 5 * D * 4,
-              G_OFF_CTL = G_OFF_RED + 2 * TILE * 8;
+              G_OFF_CTL = G_OFF_RED + G_CH * TILE * 8;
 constexpr int G_SMEM_BYTES = G_OFF_CTL + (int)sizeof(GCtl) + 64;
 
 struct GItem {
@@ -472,7 +474,7 @@ __device__ __forceinline__ float tanh_f(float x) {
 }
 
 template <bool PRECISE>
-__global__ void __launch_bounds__(THREADS, 1) wide_gru_kernel(const Args a) {
+__global__ void __launch_bounds__(G_THREADS, 1) wide_gru_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* xs = smem + G_OFF_X;
   float* vec_s = reinterpret_cast<float*>(smem + G_OFF_VEC);
@@ -489,18 +491,18 @@ __global__ void __launch_bounds__(THREADS, 1) wide_gru_kernel(const Args a) {
     }
     tc::mbar_init(&ctl.x_full, 1);
     tc::mbar_init(&ctl.accA, 1);
-    tc::mbar_init(&ctl.rh_ready, 8);
+    tc::mbar_init(&ctl.rh_ready, G_WORKERS);
     tc::mbar_init(&ctl.accB, 1);
-    tc::mbar_init(&ctl.acc_empty, 8);
+    tc::mbar_init(&ctl.acc_empty, G_WORKERS);
     tc::mbar_fence_init();
   }
-  if (warp == 9) tc::tmem_alloc<512>(&ctl.tmem);
+  if (warp == G_WORKERS + 1) tc::tmem_alloc<512>(&ctl.tmem);
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
   const uint32_t tmem = ctl.tmem;
 
-  if (warp == 8) {
+  if (warp == G_WORKERS) {
     // ------------------------------------------------------------------ TMA loader
     if (lane == 0) {
       uint32_t it = 0, k = 0;
@@ -531,7 +533,7 @@ __global__ void __launch_bounds__(THREADS, 1) wide_gru_kernel(const Args a) {
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == G_WORKERS + 1) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = tc::make_idesc(tc::FMT_F16, TILE, D);
     const uint32_t x_addr = tc::smem_u32(xs);
@@ -578,14 +580,14 @@ __global__ void __launch_bounds__(THREADS, 1) wide_gru_kernel(const Args a) {
       }
     }
   } else {
-    // ------------------------------------------------------------------ workers: 4 lane quarters x 2 column halves
+    // ------------------------------------------------------------------ workers: 4 lane quarters x G_CH column slices
     const int q = warp & 3, ch = warp >> 2;
     const int rowt = q * 32 + lane;
-    const uint32_t tz = tmem + (uint32_t)(ch * 128) + ((uint32_t)(q * 32) << 16), tr = tz + D;
-    const float *bz = vec_s + ch * 128, *br = vec_s + D + ch * 128, *bh = vec_s + 2 * D + ch * 128,
-                *gamma = vec_s + 3 * D + ch * 128, *beta = vec_s + 4 * D + ch * 128;
+    const uint32_t tz = tmem + (uint32_t)(ch * G_COLS) + ((uint32_t)(q * 32) << 16), tr = tz + D;
+    const float *bz = vec_s + ch * G_COLS, *br = vec_s + D + ch * G_COLS, *bh = vec_s + 2 * D + ch * G_COLS,
+                *gamma = vec_s + 3 * D + ch * G_COLS, *beta = vec_s + 4 * D + ch * G_COLS;
     uint8_t* h32b = reinterpret_cast<uint8_t*>(a.h32);
-    uint8_t* xrow = xs + (16 * ch) * 2048 + rowt * 16;  // this thread's pieces of X: + p * 2048
+    uint8_t* xrow = xs + (G_COLS / 8 * ch) * 2048 + rowt * 16;  // this thread's pieces of X: + p * 2048
     int cur_tower = -1;
     uint32_t k = 0;
     for (int i = blockIdx.x; i < items; i += gridDim.x, ++k) {
@@ -593,19 +595,19 @@ __global__ void __launch_bounds__(THREADS, 1) wide_gru_kernel(const Args a) {
       const int row = w.t * TILE + rowt;
       const bool mine = row >= w.lo && row < w.hi;
       if (w.tower != cur_tower) {  // bz, br, bh, gamma, beta of this tower -> shared memory
-        tc::named_bar_sync(1, 256);
+        tc::named_bar_sync(1, G_WORKERS * 32);
         const float* v = reinterpret_cast<const float*>((w.tower ? a.packed[1] : a.packed[0]) + OFF_VEC);
-        for (int x = threadIdx.x; x < 5 * D; x += 256) vec_s[x] = __ldg(v + x);
-        tc::named_bar_sync(1, 256);
+        for (int x = threadIdx.x; x < 5 * D; x += G_WORKERS * 32) vec_s[x] = __ldg(v + x);
+        tc::named_bar_sync(1, G_WORKERS * 32);
         cur_tower = w.tower;
       }
-      const uint8_t* hrow = h32b + tp32_off(row, 32 * ch);  // this thread's quads of the fp32 state: + x * 2048
+      const uint8_t* hrow = h32b + tp32_off(row, G_COLS / 4 * ch);  // this thread's quads of the fp32 state: + x * 2048
       // ---- EA: r -> r*h operand, in place over the h16 tile
       tc::mbar_wait(&ctl.x_full, k & 1);
       tc::mbar_wait(&ctl.accA, k & 1);
       tc::fence_after_thread_sync();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < G_COLS / 32; ++c) {
         float v[32];
         tc::tmem_ld32(tr + c * 32, v);
 #pragma unroll
@@ -637,14 +639,14 @@ __global__ void __launch_bounds__(THREADS, 1) wide_gru_kernel(const Args a) {
       tc::fence_after_thread_sync();
       float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < G_COLS / 16; ++c) {
         float zp[16], hp[16];
         tc::tmem_ld16(tz + c * 16, zp);
         tc::tmem_ld16(tr + c * 16, hp);
         float4 hn[4];
 #pragma unroll
         for (int x = 0; x < 4; ++x)
-          hn[x] = (mine && c < 7) ? *reinterpret_cast<const float4*>(hrow + (4 * (c + 1) + x) * 2048) : make_float4(0.f, 0.f, 0.f, 0.f);
+          hn[x] = (mine && c < G_COLS / 16 - 1) ? *reinterpret_cast<const float4*>(hrow + (4 * (c + 1) + x) * 2048) : make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t nn[16], hh[16];
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
@@ -665,17 +667,19 @@ __global__ void __launch_bounds__(THREADS, 1) wide_gru_kernel(const Args a) {
       }
       red_s[ch * TILE + rowt] = make_float2(sum, sq);
       tc::tmem_wait_st();
-      tc::named_bar_sync(1, 256);
-      {
-        const float2 o = red_s[(ch ^ 1) * TILE + rowt];
-        sum += o.x, sq += o.y;
+      tc::named_bar_sync(1, G_WORKERS * 32);
+      sum = 0.f, sq = 0.f;
+#pragma unroll
+      for (int o = 0; o < G_CH; ++o) {  // the same order in every slice: all workers of a row see identical statistics
+        const float2 t2 = red_s[o * TILE + rowt];
+        sum += t2.x, sq += t2.y;
       }
       const float mean = sum * (1.0f / D);
       const float var = fmaxf(sq * (1.0f / D) - mean * mean, 0.f);
       const float rstd = PRECISE ? 1.0f / sqrtf(var + a.eps) : rsqrtf(var + a.eps);
       // ---- E2 pass 2: normalise + residual from TMEM, write the state
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < G_COLS / 16; ++c) {
         float v[16], hv[16];
         tc::tmem_ld16(tr + c * 16, v);
         tc::tmem_ld16(tz + c * 16, hv);
@@ -690,10 +694,10 @@ __global__ void __launch_bounds__(THREADS, 1) wide_gru_kernel(const Args a) {
         if (mine) {
 #pragma unroll
           for (int x = 0; x < 4; ++x)
-            *reinterpret_cast<float4*>(h32b + tp32_off(row, 32 * ch + 4 * c + x)) = make_float4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+            *reinterpret_cast<float4*>(h32b + tp32_off(row, G_COLS / 4 * ch + 4 * c + x)) = make_float4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
 #pragma unroll
           for (int p = 0; p < 2; ++p)
-            *reinterpret_cast<uint4*>(a.h16 + tp16_off(row, 16 * ch + 2 * c + p)) =
+            *reinterpret_cast<uint4*>(a.h16 + tp16_off(row, G_COLS / 8 * ch + 2 * c + p)) =
                 make_uint4(tc::pack_f16x2(v[8 * p], v[8 * p + 1]), tc::pack_f16x2(v[8 * p + 2], v[8 * p + 3]),
                            tc::pack_f16x2(v[8 * p + 4], v[8 * p + 5]), tc::pack_f16x2(v[8 * p + 6], v[8 * p + 7]));
         }
@@ -705,7 +709,7 @@ __global__ void __launch_bounds__(THREADS, 1) wide_gru_kernel(const Args a) {
   }
   tc::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == G_WORKERS + 1) {
     tc::fence_after_thread_sync();
     tc::tmem_dealloc<512>(tmem);
   }
@@ -912,9 +916,9 @@ extern "C" int imp_wide_gated_update(const imp_graph_t* g, int32_t d, const void
   IMP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int items = wide::n_gitems(a.n_atoms, a.n_cat);
   if (a.precise)
-    wide::wide_gru_kernel<true><<<items < sms ? items : sms, wide::THREADS, wide::G_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    wide::wide_gru_kernel<true><<<items < sms ? items : sms, wide::G_THREADS, wide::G_SMEM_BYTES, (cudaStream_t)stream>>>(a);
   else
-    wide::wide_gru_kernel<false><<<items < sms ? items : sms, wide::THREADS, wide::G_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    wide::wide_gru_kernel<false><<<items < sms ? items : sms, wide::G_THREADS, wide::G_SMEM_BYTES, (cudaStream_t)stream>>>(a);
   IMP_LAUNCH_CHECK();
   return 0;
 }

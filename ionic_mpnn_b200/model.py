@@ -134,6 +134,41 @@ class MPNNModel(TrainMixin):
     def get_weights(self):
         return {k: v.detach().cpu().numpy() for k, v in self.params.items()}
 
+    def save_weights(self, path, include_optimizer=True):
+        """Checkpoint (``model.save`` role, train_viscosity.py:353-354): one ``.npz`` keyed by the variable names of
+        ``param_shapes`` (INTEGRATION.md maps them to the reference's Keras layers) plus the model spec and, when a
+        training state exists, Adam's m / v / step so that ``fit`` / ``train_step`` resume bit-identically."""
+        import json
+
+        arrays = {f"w/{k}": v for k, v in self.get_weights().items()}
+        arrays["spec"] = np.frombuffer(json.dumps(self.spec, sort_keys=True).encode(), dtype=np.uint8)
+        st = getattr(self, "_train", None)
+        if include_optimizer and st is not None:
+            arrays["adam/m"], arrays["adam/v"] = st["m"].cpu().numpy(), st["v"].cpu().numpy()
+            arrays["adam/step"] = np.asarray(st["step"], dtype=np.int64)
+        with open(path, "wb") as f:
+            np.savez(f, **arrays)
+
+    def load_weights(self, path):
+        """Inverse of save_weights.  The file's spec must match this model's (shapes are checked variable by variable)."""
+        import json
+
+        import torch
+
+        with np.load(path) as z:
+            if "spec" in z.files:
+                spec = json.loads(bytes(z["spec"]).decode())
+                diff = {k: (spec.get(k), self.spec.get(k)) for k in self.spec if spec.get(k) != self.spec.get(k)}
+                if diff:
+                    raise ValueError(f"checkpoint was written for a different model spec: {diff}")
+            self.set_weights({k[2:]: z[k] for k in z.files if k.startswith("w/")})
+            if "adam/m" in z.files:
+                st = self._train_state()
+                st["m"].copy_(torch.from_numpy(z["adam/m"]))
+                st["v"].copy_(torch.from_numpy(z["adam/v"]))
+                st["step"] = int(z["adam/step"])
+        return self
+
     def count_params(self):
         return sum(int(np.prod(s)) for s in param_shapes(self.spec).values())
 

@@ -129,3 +129,29 @@ def test_fit_loop_early_stopping_and_best_weight_restore():
     again = MPNNModel(spec, precision="fp32", seed=3)
     h2 = again.fit(train, validation_data=val, epochs=len(hist["loss"]), batch_size=32, patience=3, seed=1)
     assert h2["loss"] == hist["loss"] and h2["val_loss"] == hist["val_loss"]
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    """save_weights / load_weights (weights + Adam state): two steps, checkpoint, two more steps == four steps straight."""
+    from ionic_mpnn_b200 import graph, synth
+    from ionic_mpnn_b200.viscosity import build_model
+
+    recs = synth.make_records(96, seed=3, label="log_eta")
+    batch = graph.pack_records(recs, 72, label="log_eta")
+    a = build_model(124, 72, seed=4)
+    for _ in range(4):
+        a.train_step(batch)
+    b = build_model(124, 72, seed=4)
+    for _ in range(2):
+        b.train_step(batch)
+    path = str(tmp_path / "ckpt.npz")
+    b.save_weights(path)
+    c = build_model(124, 72, seed=99)
+    c.load_weights(path)
+    for _ in range(2):
+        c.train_step(batch)
+    wa, wc = a.get_weights(), c.get_weights()
+    for k in wa:
+        assert np.array_equal(wa[k], wc[k]), k
+    with pytest.raises(ValueError):
+        build_model(124, 72, num_steps=3).load_weights(path)

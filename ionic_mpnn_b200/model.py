@@ -339,7 +339,8 @@ class MPNNModel(TrainMixin):
                 _lib.call("imp_edge_messages", C.byref(g), h[i].data_ptr(), d, self.table_ptr(0, i, False),
                           self.table_ptr(1, i, False), msg.data_ptr(), st)
                 _lib.call("imp_segment_sum", C.byref(g), msg.data_ptr(), d, aggs[i].data_ptr(), st)
-            elif self.precision != "fp32" and d == 32 and not getattr(self, "simt_messages", False):
+            elif (self.precision != "fp32" and d == 32 and not getattr(self, "simt_messages", False)
+                  and "bucket_perm" in batch.dev):  # device-packed batches carry no bond buckets: CSR-order kernel
                 # bond-type-grouped tcgen05 GEMM over gathered source rows, then the CSR segment sum (csrc/msg_tc.cu)
                 mbase = self._ws["msg_packed"].data_ptr()
                 msg = self._buf("msg", batch.n_unique * d)

@@ -103,4 +103,5 @@ def test_device_packed_batch_through_the_staged_tensor_path():
     a = m.forward_packed(host).cpu().numpy()
     b = m.forward_packed(dev).cpu().numpy()
     assert np.isfinite(b).all()
-    assert np.max(np.abs(a - b) / np.maximum(np.abs(a), 1.0)) <= 2e-3
+    # fp16 grouped tensor GEMM vs fp32 SIMT messages, both inside the 2e-2 class of the tensor path (north_star)
+    assert np.max(np.abs(a - b) / np.maximum(np.abs(a), 1.0)) <= 1e-2

@@ -269,27 +269,38 @@ template <int D>
 __host__ __device__ constexpr int gru_grad_floats() { return 3 * 2 * D * D + 5 * D; }
 // layout (= the layer's variable order in the flat parameter buffer): dWz dbz dWr dbr dWh dbh dgamma dbeta
 
-// pre[j] = bias[j] + sum_k x0[k] W[k][j] + sum_k x1[k] W[D+k][j]   (x rows in shared memory, W rows as float4 broadcasts)
+// Two threads per atom (adjacent lanes: 256 threads for a 128-atom tile): each computes 16 of the 32 output columns of every
+// dense product of its row, so that the SM holds 8 warps instead of 4 and each thread half the dependent FMA chains (the
+// 152 KB of staged rows + weights allow one CTA per SM).  Row-wide quantities (LayerNorm means, the full gate-gradient
+// vectors needed by the transposed products) cross the pair through shared memory rows / one shuffle.
+constexpr int GB_THREADS = 2 * GB_TILE;
+constexpr int GB_H = 16;  // columns per thread
+
+// pre[i] = bias[j0+i] + sum_k x0[k] W[k][j0+i] + sum_k x1[k] W[D+k][j0+i]   (x rows in shared memory read as float4)
 template <int D>
-__device__ __forceinline__ void gb_dense(float (&acc)[D], const float* __restrict__ W, const float* __restrict__ bias,
-                                         const float* __restrict__ x0, const float* __restrict__ x1) {
+__device__ __forceinline__ void gb_dense_half(float (&acc)[GB_H], const float* __restrict__ W, const float* __restrict__ bias,
+                                              const float* __restrict__ x0, const float* __restrict__ x1, int j0) {
 #pragma unroll
-  for (int j = 0; j < D; ++j) acc[j] = bias[j];
+  for (int i = 0; i < GB_H; ++i) acc[i] = bias[j0 + i];
 #pragma unroll 2
-  for (int k = 0; k < 2 * D; ++k) {
-    const float x = k < D ? x0[k] : x1[k - D];
-    const float4* w = reinterpret_cast<const float4*>(W + k * D);
+  for (int k4 = 0; k4 < 2 * D / 4; ++k4) {
+    const float4 xv = *reinterpret_cast<const float4*>(k4 < D / 4 ? x0 + 4 * k4 : x1 + 4 * k4 - D);
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-    for (int j4 = 0; j4 < D / 4; ++j4) {
-      const float4 wv = w[j4];
-      acc[4 * j4 + 0] = fmaf(x, wv.x, acc[4 * j4 + 0]);
-      acc[4 * j4 + 1] = fmaf(x, wv.y, acc[4 * j4 + 1]);
-      acc[4 * j4 + 2] = fmaf(x, wv.z, acc[4 * j4 + 2]);
-      acc[4 * j4 + 3] = fmaf(x, wv.w, acc[4 * j4 + 3]);
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4* w = reinterpret_cast<const float4*>(W + (4 * k4 + kk) * D + j0);
+#pragma unroll
+      for (int j4 = 0; j4 < GB_H / 4; ++j4) {
+        const float4 wv = w[j4];
+        acc[4 * j4 + 0] = fmaf(xs[kk], wv.x, acc[4 * j4 + 0]);
+        acc[4 * j4 + 1] = fmaf(xs[kk], wv.y, acc[4 * j4 + 1]);
+        acc[4 * j4 + 2] = fmaf(xs[kk], wv.z, acc[4 * j4 + 2]);
+        acc[4 * j4 + 3] = fmaf(xs[kk], wv.w, acc[4 * j4 + 3]);
+      }
     }
   }
 }
-// out[k] (+)= sum_j g[j] W[k][j]  for k in [0, 2D)   (g in registers)
+// sum_j g[j] W[k][j]   (g in registers, one weight row)
 template <int D>
 __device__ __forceinline__ float gb_dot_row(const float (&g)[D], const float* __restrict__ Wrow) {
   const float4* w = reinterpret_cast<const float4*>(Wrow);
@@ -304,15 +315,23 @@ __device__ __forceinline__ float gb_dot_row(const float (&g)[D], const float* __
   }
   return s;
 }
+template <int D>
+__device__ __forceinline__ void gb_load_row(float (&g)[D], const float* __restrict__ row) {
+#pragma unroll
+  for (int c = 0; c < D / 4; ++c) {
+    const float4 v = *reinterpret_cast<const float4*>(row + 4 * c);
+    g[4 * c] = v.x, g[4 * c + 1] = v.y, g[4 * c + 2] = v.z, g[4 * c + 3] = v.w;
+  }
+}
 
 // Persistent CTAs; CTAs [0, n_cta_cat) walk the cation tiles, the rest the anion tiles.  Per-CTA partial weight
 // gradients are written to partial[cta][gru_grad_floats]; imp_gated_update_bwd reduces them per tower in CTA order.
 template <int D>
-__global__ void __launch_bounds__(GB_TILE) gated_update_bwd_kernel(const float* __restrict__ h, const float* __restrict__ agg,
-                                                                   const float* __restrict__ g_out, int n_atoms, int n_cat,
-                                                                   int n_cta_cat, imp_gru_weights_t wc, imp_gru_weights_t wa,
-                                                                   float eps, float* __restrict__ dh, float* __restrict__ dagg,
-                                                                   float* __restrict__ partial) {
+__global__ void __launch_bounds__(GB_THREADS) gated_update_bwd_kernel(const float* __restrict__ h, const float* __restrict__ agg,
+                                                                      const float* __restrict__ g_out, int n_atoms, int n_cat,
+                                                                      int n_cta_cat, imp_gru_weights_t wc, imp_gru_weights_t wa,
+                                                                      float eps, float* __restrict__ dh, float* __restrict__ dagg,
+                                                                      float* __restrict__ partial) {
   static_assert(D == 32, "gated_update_bwd is instantiated for atom_dim 32");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GruBwdSmem<D>& s = *reinterpret_cast<GruBwdSmem<D>*>(smem_raw);
@@ -322,143 +341,150 @@ __global__ void __launch_bounds__(GB_TILE) gated_update_bwd_kernel(const float* 
   const int base = is_cat ? 0 : n_cat, a_end = is_cat ? n_cat : n_atoms;
   const int n_tiles = (a_end - base + GB_TILE - 1) / GB_TILE;
   const int cta = is_cat ? blockIdx.x : blockIdx.x - n_cta_cat, n_cta = is_cat ? n_cta_cat : gridDim.x - n_cta_cat;
-  for (int i = tid; i < 2 * D * D / 4; i += GB_TILE) {
+  for (int i = tid; i < 2 * D * D / 4; i += GB_THREADS) {
     reinterpret_cast<float4*>(s.Wz)[i] = __ldg(reinterpret_cast<const float4*>(w.Wz) + i);
     reinterpret_cast<float4*>(s.Wr)[i] = __ldg(reinterpret_cast<const float4*>(w.Wr) + i);
     reinterpret_cast<float4*>(s.Wh)[i] = __ldg(reinterpret_cast<const float4*>(w.Wh) + i);
   }
-  for (int i = tid; i < D; i += GB_TILE)
+  for (int i = tid; i < D; i += GB_THREADS)
     s.bz[i] = w.bz[i], s.br[i] = w.br[i], s.bh[i] = w.bh[i], s.gamma[i] = w.gamma[i], s.beta[i] = w.beta[i];
   __syncthreads();
 
-  // weight-gradient accumulators: thread (k = tid % 64, jb = tid / 64) owns rows k, columns [16 jb, 16 jb + 16)
+  // weight-gradient accumulators: thread (k = tid % 64, jb = tid / 64) owns rows k, columns [8 jb, 8 jb + 8)
   const int wk = tid % (2 * D), wjb = tid / (2 * D);
-  float aWz[16], aWr[16], aWh[16];
+  float aWz[8], aWr[8], aWh[8];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) aWz[i] = aWr[i] = aWh[i] = 0.f;
-  // vector-gradient accumulators: thread (j = tid % 32, q = tid / 32) sums atoms a = q, q+4, ...
+  for (int i = 0; i < 8; ++i) aWz[i] = aWr[i] = aWh[i] = 0.f;
+  // vector-gradient accumulators: thread (j = tid % 32, q = tid / 32) sums atoms a = q, q+8, ...
   const int vj = tid % D, vq = tid / D;
   float abz = 0.f, abr = 0.f, abh = 0.f, agam = 0.f, abet = 0.f;
 
-  float* Xrow = &s.X[tid * GB_XS];
-  float* RHrow = &s.RH[tid * GB_GS];
-  float* Gzrow = &s.Gz[tid * GB_GS];
-  float* Grrow = &s.Gr[tid * GB_GS];
-  float* Ghrow = &s.Gh[tid * GB_GS];
-  float* GXrow = &s.GX[tid * GB_GS];
+  const int at = tid >> 1, hh = tid & 1, j0 = hh * GB_H;  // atom row of the tile, column half
+  float* Xrow = &s.X[at * GB_XS];
+  float* RHrow = &s.RH[at * GB_GS];
+  float* Gzrow = &s.Gz[at * GB_GS];
+  float* Grrow = &s.Gr[at * GB_GS];
+  float* Ghrow = &s.Gh[at * GB_GS];
+  float* GXrow = &s.GX[at * GB_GS];
 
   for (int tile = cta; tile < n_tiles; tile += n_cta) {
     const int a0 = base + tile * GB_TILE;
     const int rows = min(GB_TILE, a_end - a0);
-    const bool valid = tid < rows;
-    const int64_t rowoff = (int64_t)(a0 + tid) * D;
-    // ---- own row: h, agg -> X
+    const bool valid = at < rows;  // rows beyond the tile end run on zeros and contribute exact zeros everywhere
+    const int64_t rowoff = (int64_t)(a0 + at) * D;
+    // ---- own row: lane 0 of the pair stages h, lane 1 agg
+    {
+      const float4* src = reinterpret_cast<const float4*>((hh ? agg : h) + rowoff);
 #pragma unroll
-    for (int c = 0; c < D / 4; ++c) {
-      const float4 hv = valid ? __ldg(reinterpret_cast<const float4*>(h + rowoff) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 av = valid ? __ldg(reinterpret_cast<const float4*>(agg + rowoff) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      reinterpret_cast<float4*>(Xrow)[c] = hv;
-      reinterpret_cast<float4*>(Xrow + D)[c] = av;
+      for (int c = 0; c < D / 4; ++c)
+        reinterpret_cast<float4*>(Xrow + hh * D)[c] = valid ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float go[GB_H];
+#pragma unroll
+    for (int c = 0; c < GB_H / 4; ++c) {
+      const float4 gv = valid ? __ldg(reinterpret_cast<const float4*>(g_out + rowoff + j0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      go[4 * c] = gv.x, go[4 * c + 1] = gv.y, go[4 * c + 2] = gv.z, go[4 * c + 3] = gv.w;
+    }
+    __syncwarp();
+    float acc[GB_H], zv[GB_H], rv[GB_H];
+    // z
+    gb_dense_half<D>(acc, s.Wz, s.bz, Xrow, Xrow + D, j0);
+#pragma unroll
+    for (int i = 0; i < GB_H; ++i) zv[i] = bw_sigmoid(acc[i]);
+    // r, r*h
+    gb_dense_half<D>(acc, s.Wr, s.br, Xrow, Xrow + D, j0);
+#pragma unroll
+    for (int i = 0; i < GB_H; ++i) {
+      rv[i] = bw_sigmoid(acc[i]);
+      RHrow[j0 + i] = rv[i] * Xrow[j0 + i];
+    }
+    __syncwarp();
+    // candidate
+    gb_dense_half<D>(acc, s.Wh, s.bh, RHrow, Xrow + D, j0);
+    float nrm[GB_H];
+    float mean = 0.f;
+#pragma unroll
+    for (int i = 0; i < GB_H; ++i) {
+      acc[i] = tanhf(acc[i]);  // ht
+      nrm[i] = fmaf(zv[i], acc[i] - Xrow[j0 + i], Xrow[j0 + i]);
+      mean += nrm[i];
+    }
+    mean = (mean + __shfl_xor_sync(0xffffffffu, mean, 1)) * (1.0f / D);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < GB_H; ++i) {
+      nrm[i] -= mean;
+      var = fmaf(nrm[i], nrm[i], var);
+    }
+    var += __shfl_xor_sync(0xffffffffu, var, 1);
+    const float inv = 1.0f / sqrtf(var * (1.0f / D) + eps);
+    // LayerNorm backward: dn = inv * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat))
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < GB_H; ++i) {
+      nrm[i] *= inv;  // xhat
+      GXrow[j0 + i] = go[i] * nrm[i];
+      const float dx = go[i] * s.gamma[j0 + i];
+      m1 += dx;
+      m2 = fmaf(dx, nrm[i], m2);
+    }
+    m1 = (m1 + __shfl_xor_sync(0xffffffffu, m1, 1)) * (1.0f / D);
+    m2 = (m2 + __shfl_xor_sync(0xffffffffu, m2, 1)) * (1.0f / D);
+    // dn -> gate gradients; dh accumulates in go[] (starts as the residual path)
+#pragma unroll
+    for (int i = 0; i < GB_H; ++i) {
+      const float dn = inv * (go[i] * s.gamma[j0 + i] - m1 - nrm[i] * m2);
+      const float z = zv[i], ht = acc[i], hj = Xrow[j0 + i];
+      go[i] = fmaf(dn, 1.0f - z, go[i]);
+      Gzrow[j0 + i] = dn * (ht - hj) * z * (1.0f - z);  // dL/dzpre
+      Ghrow[j0 + i] = dn * z * (1.0f - ht * ht);        // dL/dhpre
+    }
+    __syncwarp();
+    // through Wh: d(r*h) and dagg need the full dL/dhpre row
+    float dag[GB_H];
+    {
+      float dhp[D];
+      gb_load_row<D>(dhp, Ghrow);
+#pragma unroll
+      for (int i = 0; i < GB_H; ++i) {
+        const int k = j0 + i;
+        const float drh = gb_dot_row<D>(dhp, s.Wh + k * D);
+        const float r = rv[i], hk = Xrow[k];
+        go[i] = fmaf(drh, r, go[i]);
+        Grrow[k] = drh * hk * r * (1.0f - r);  // dL/drpre (r itself is no longer needed in shared memory)
+        dag[i] = gb_dot_row<D>(dhp, s.Wh + (D + k) * D);
+      }
+    }
+    __syncwarp();
+    // through Wz, Wr
+    {
+      float dzp[D], drp[D];
+      gb_load_row<D>(dzp, Gzrow);
+      gb_load_row<D>(drp, Grrow);
+#pragma unroll
+      for (int i = 0; i < GB_H; ++i) {
+        const int k = j0 + i;
+        go[i] += gb_dot_row<D>(dzp, s.Wz + k * D) + gb_dot_row<D>(drp, s.Wr + k * D);
+        dag[i] += gb_dot_row<D>(dzp, s.Wz + (D + k) * D) + gb_dot_row<D>(drp, s.Wr + (D + k) * D);
+      }
     }
     if (valid) {
-      float acc[D];
-      // z
-      gb_dense<D>(acc, s.Wz, s.bz, Xrow, Xrow + D);
 #pragma unroll
-      for (int j = 0; j < D; ++j) Gzrow[j] = bw_sigmoid(acc[j]);
-      // r, r*h
-      gb_dense<D>(acc, s.Wr, s.br, Xrow, Xrow + D);
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        const float r = bw_sigmoid(acc[j]);
-        Grrow[j] = r;
-        RHrow[j] = r * Xrow[j];
+      for (int c = 0; c < GB_H / 4; ++c) {
+        reinterpret_cast<float4*>(dh + rowoff + j0)[c] = make_float4(go[4 * c], go[4 * c + 1], go[4 * c + 2], go[4 * c + 3]);
+        reinterpret_cast<float4*>(dagg + rowoff + j0)[c] = make_float4(dag[4 * c], dag[4 * c + 1], dag[4 * c + 2], dag[4 * c + 3]);
       }
-      // candidate
-      gb_dense<D>(acc, s.Wh, s.bh, RHrow, Xrow + D);
-      float mean = 0.f;
-      float nrm[D];
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        acc[j] = tanhf(acc[j]);  // ht
-        nrm[j] = fmaf(Gzrow[j], acc[j] - Xrow[j], Xrow[j]);
-        mean += nrm[j];
-      }
-      mean *= (1.0f / D);
-      float var = 0.f;
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        nrm[j] -= mean;
-        var = fmaf(nrm[j], nrm[j], var);
-      }
-      const float inv = 1.0f / sqrtf(var * (1.0f / D) + eps);
-      // LayerNorm backward: dn = inv * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat))
-      float m1 = 0.f, m2 = 0.f;
-      float go[D];
-#pragma unroll
-      for (int c = 0; c < D / 4; ++c) {
-        const float4 gv = __ldg(reinterpret_cast<const float4*>(g_out + rowoff) + c);
-        go[4 * c] = gv.x, go[4 * c + 1] = gv.y, go[4 * c + 2] = gv.z, go[4 * c + 3] = gv.w;
-      }
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        nrm[j] *= inv;  // xhat
-        GXrow[j] = go[j] * nrm[j];
-        const float dx = go[j] * s.gamma[j];
-        m1 += dx;
-        m2 = fmaf(dx, nrm[j], m2);
-      }
-      m1 *= (1.0f / D), m2 *= (1.0f / D);
-      // dn -> gate gradients; dh accumulates in go[] (starts as the residual path)
-      float dhp[D];
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        const float dn = inv * (go[j] * s.gamma[j] - m1 - nrm[j] * m2);
-        const float z = Gzrow[j], ht = acc[j], hj = Xrow[j];
-        go[j] = fmaf(dn, 1.0f - z, go[j]);
-        Gzrow[j] = dn * (ht - hj) * z * (1.0f - z);  // dL/dzpre
-        dhp[j] = dn * z * (1.0f - ht * ht);          // dL/dhpre
-        Ghrow[j] = dhp[j];
-      }
-      // through Wh: d(r*h) and dagg
-      float dag[D];
-#pragma unroll
-      for (int k = 0; k < D; ++k) {
-        const float drh = gb_dot_row<D>(dhp, s.Wh + k * D);
-        const float r = Grrow[k], hk = Xrow[k];
-        go[k] = fmaf(drh, r, go[k]);
-        Grrow[k] = drh * hk * r * (1.0f - r);  // dL/drpre
-      }
-#pragma unroll
-      for (int k = 0; k < D; ++k) dag[k] = gb_dot_row<D>(dhp, s.Wh + (D + k) * D);
-      // through Wz, Wr
-      float dzp[D], drp[D];
-#pragma unroll
-      for (int j = 0; j < D; ++j) dzp[j] = Gzrow[j], drp[j] = Grrow[j];
-#pragma unroll
-      for (int k = 0; k < D; ++k) {
-        go[k] += gb_dot_row<D>(dzp, s.Wz + k * D) + gb_dot_row<D>(drp, s.Wr + k * D);
-        dag[k] += gb_dot_row<D>(dzp, s.Wz + (D + k) * D) + gb_dot_row<D>(drp, s.Wr + (D + k) * D);
-      }
-#pragma unroll
-      for (int c = 0; c < D / 4; ++c) {
-        reinterpret_cast<float4*>(dh + rowoff)[c] = make_float4(go[4 * c], go[4 * c + 1], go[4 * c + 2], go[4 * c + 3]);
-        reinterpret_cast<float4*>(dagg + rowoff)[c] = make_float4(dag[4 * c], dag[4 * c + 1], dag[4 * c + 2], dag[4 * c + 3]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < D; ++j) RHrow[j] = Gzrow[j] = Grrow[j] = Ghrow[j] = GXrow[j] = 0.f;
     }
     __syncthreads();
     // ---- weight gradients of this tile: dW[k][j] += sum_a X[a][k] G[a][j]
     for (int a = 0; a < rows; ++a) {
       const float xk = s.X[a * GB_XS + wk];                                        // [h | agg][k]
       const float xh = wk < D ? s.RH[a * GB_GS + wk] : xk;                         // [r*h | agg][k]
-      const float4* gz = reinterpret_cast<const float4*>(&s.Gz[a * GB_GS + 16 * wjb]);
-      const float4* gr = reinterpret_cast<const float4*>(&s.Gr[a * GB_GS + 16 * wjb]);
-      const float4* gh = reinterpret_cast<const float4*>(&s.Gh[a * GB_GS + 16 * wjb]);
+      const float4* gz = reinterpret_cast<const float4*>(&s.Gz[a * GB_GS + 8 * wjb]);
+      const float4* gr = reinterpret_cast<const float4*>(&s.Gr[a * GB_GS + 8 * wjb]);
+      const float4* gh = reinterpret_cast<const float4*>(&s.Gh[a * GB_GS + 8 * wjb]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         const float4 z4 = gz[c], r4 = gr[c], h4 = gh[c];
         aWz[4 * c] = fmaf(xk, z4.x, aWz[4 * c]), aWz[4 * c + 1] = fmaf(xk, z4.y, aWz[4 * c + 1]);
         aWz[4 * c + 2] = fmaf(xk, z4.z, aWz[4 * c + 2]), aWz[4 * c + 3] = fmaf(xk, z4.w, aWz[4 * c + 3]);
@@ -468,7 +494,7 @@ __global__ void __launch_bounds__(GB_TILE) gated_update_bwd_kernel(const float* 
         aWh[4 * c + 2] = fmaf(xh, h4.z, aWh[4 * c + 2]), aWh[4 * c + 3] = fmaf(xh, h4.w, aWh[4 * c + 3]);
       }
     }
-    for (int a = vq; a < rows; a += GB_TILE / D) {
+    for (int a = vq; a < rows; a += GB_THREADS / D) {
       abz += s.Gz[a * GB_GS + vj];
       abr += s.Gr[a * GB_GS + vj];
       abh += s.Gh[a * GB_GS + vj];
@@ -477,22 +503,26 @@ __global__ void __launch_bounds__(GB_TILE) gated_update_bwd_kernel(const float* 
     }
     __syncthreads();
   }
-  // ---- per-CTA partials.  Vector gradients: combine the 4 atom phases through shared memory in phase order.
+  // ---- per-CTA partials.  Vector gradients: combine the 8 atom phases through shared memory in phase order.
   float* o = partial + (int64_t)blockIdx.x * gru_grad_floats<D>();
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    o[wk * D + 16 * wjb + i] = aWz[i];
-    o[(2 * D * D + D) + wk * D + 16 * wjb + i] = aWr[i];
-    o[2 * (2 * D * D + D) + wk * D + 16 * wjb + i] = aWh[i];
+  for (int i = 0; i < 8; ++i) {
+    o[wk * D + 8 * wjb + i] = aWz[i];
+    o[(2 * D * D + D) + wk * D + 8 * wjb + i] = aWr[i];
+    o[2 * (2 * D * D + D) + wk * D + 8 * wjb + i] = aWh[i];
   }
-  float* red = s.X;  // reuse: [5][4][32]
-  red[(0 * 4 + vq) * D + vj] = abz, red[(1 * 4 + vq) * D + vj] = abr, red[(2 * 4 + vq) * D + vj] = abh;
-  red[(3 * 4 + vq) * D + vj] = agam, red[(4 * 4 + vq) * D + vj] = abet;
+  constexpr int NQ = GB_THREADS / D;
+  float* red = s.X;  // reuse: [5][NQ][32]
+  red[(0 * NQ + vq) * D + vj] = abz, red[(1 * NQ + vq) * D + vj] = abr, red[(2 * NQ + vq) * D + vj] = abh;
+  red[(3 * NQ + vq) * D + vj] = agam, red[(4 * NQ + vq) * D + vj] = abet;
   __syncthreads();
-  for (int i = tid; i < 5 * D; i += GB_TILE) {
-    const int v = i / D, j = i % D;
+  for (int i = tid; i < 5 * D; i += GB_THREADS) {
+    const int v = i / D, jj = i % D;
     const int off = v < 3 ? v * (2 * D * D + D) + 2 * D * D : 3 * (2 * D * D + D) + (v - 3) * D;  // bz, br, bh | gamma, beta
-    o[off + j] = ((red[(v * 4 + 0) * D + j] + red[(v * 4 + 1) * D + j]) + red[(v * 4 + 2) * D + j]) + red[(v * 4 + 3) * D + j];
+    float sum = 0.f;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) sum += red[(v * NQ + q) * D + jj];
+    o[off + jj] = sum;
   }
 }
 
@@ -735,7 +765,7 @@ extern "C" int imp_gated_update_bwd(const float* d_h, const float* d_agg, const 
   const int grid = sms;
   const size_t smem = sizeof(GruBwdSmem<D>);
   IMP_CUDA(cudaFuncSetAttribute(gated_update_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gated_update_bwd_kernel<D><<<grid, GB_TILE, smem, (cudaStream_t)stream>>>(d_h, d_agg, d_gout, n_atoms, n_cat_atoms, n_cat, *w_cat,
+  gated_update_bwd_kernel<D><<<grid, GB_THREADS, smem, (cudaStream_t)stream>>>(d_h, d_agg, d_gout, n_atoms, n_cat_atoms, n_cat, *w_cat,
                                                                             *w_an, eps, d_dh, d_dagg, d_workspace);
   IMP_LAUNCH_CHECK();
   const int n = gru_grad_floats<D>();

@@ -199,6 +199,13 @@ int64_t imp_edge_messages_tc_workspace_bytes(int32_t bond_vocab);
 int imp_edge_messages_tc(const imp_graph_t* g, const float* d_h, int32_t d, const void* d_packed_cat, const void* d_packed_an,
                          int32_t flags, float* d_msg /* [Eu, d] */, void* d_workspace, void* stream);
 
+/* Reduce.call (models/layers.py:57-83) folded into the load stage of the tensor-core GatedUpdate: d_msg holds the
+ * per-entry message rows [Eu, d] in CSR order (imp_edge_messages / imp_edge_messages_tc); each atom's rows are summed
+ * in entry order while they are staged, so agg is never written.  Bit-identical to imp_segment_sum + imp_gated_update_tc. */
+int imp_reduce_gated_update_tc(const imp_graph_t* g, const float* d_h, const float* d_msg, int32_t d,
+                               const void* d_packed_cat, const void* d_packed_an, float eps, int32_t flags,
+                               float* d_h_out, void* stream);
+
 /* GlobalSumPool.call alone (models/layers.py:161-164): out[m,:] = sum of h rows of molecule m whose
  * atom_id > 0.  `n_mols` molecules delimited by d_mol_ptr[n_mols+1]. */
 int imp_global_sum_pool(const int32_t* d_mol_ptr, const int32_t* d_atom_id, int32_t n_mols, const float* d_h, int32_t d,

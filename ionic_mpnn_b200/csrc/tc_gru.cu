@@ -74,7 +74,8 @@ struct GruTcSmem {
 
 template <int D, bool PRECISE, int FMT>
 __global__ void __launch_bounds__(TC_TILE) gated_update_tc_kernel(const float* __restrict__ h, const float* __restrict__ agg,
-                                                                  int n_atoms, int n_cat, int tiles_cat, int tiles_total,
+                                                                  const int* __restrict__ row_ptr, int n_atoms, int n_cat,
+                                                                  int tiles_cat, int tiles_total,
                                                                   int tiles_per_cta, const unsigned char* __restrict__ packed_cat,
                                                                   const unsigned char* __restrict__ packed_an, float eps,
                                                                   float* __restrict__ h_out) {
@@ -126,7 +127,19 @@ __global__ void __launch_bounds__(TC_TILE) gated_update_tc_kernel(const float* _
       float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0, g0 = h0, g1 = h0;
       if (r < rows) {
         h0 = __ldg(hg + 2 * i), h1 = __ldg(hg + 2 * i + 1);
-        g0 = __ldg(ag + 2 * i), g1 = __ldg(ag + 2 * i + 1);
+        if (row_ptr == nullptr) {
+          g0 = __ldg(ag + 2 * i), g1 = __ldg(ag + 2 * i + 1);
+        } else {
+          // Reduce (models/layers.py:57-83) folded into the load: `agg` holds the message rows [Eu, D] in CSR order; the
+          // four threads of a row each sum their 8 columns over the row's (contiguous) entries, in entry order
+          const int e1 = __ldg(row_ptr + a0 + r + 1);
+          for (int e = __ldg(row_ptr + a0 + r); e < e1; ++e) {
+            const float4* m = reinterpret_cast<const float4*>(agg + (size_t)e * D) + 2 * c;
+            const float4 m0 = __ldg(m), m1 = __ldg(m + 1);
+            g0.x += m0.x, g0.y += m0.y, g0.z += m0.z, g0.w += m0.w;
+            g1.x += m1.x, g1.y += m1.y, g1.z += m1.z, g1.w += m1.w;
+          }
+        }
       }
       float* hr = &s.H[r][c * 8];
       hr[0] = h0.x, hr[1] = h0.y, hr[2] = h0.z, hr[3] = h0.w, hr[4] = h1.x, hr[5] = h1.y, hr[6] = h1.z, hr[7] = h1.w;
@@ -257,25 +270,25 @@ extern "C" int imp_gru_pack_f16(const imp_gru_weights_t* w, int32_t d, void* d_p
 }
 
 template <bool PRECISE, int FMT>
-static int launch_gru_tc(const float* d_h, const float* d_agg, int n_atoms, int n_cat_atoms, int tiles_cat, int tiles, int per,
+static int launch_gru_tc(const float* d_h, const float* d_agg, const int* d_row_ptr, int n_atoms, int n_cat_atoms, int tiles_cat, int tiles, int per,
                          int grid, const void* pc, const void* pa, float eps, float* d_h_out, cudaStream_t stream) {
   const size_t smem = sizeof(GruTcSmem<32>);
   IMP_CUDA(cudaFuncSetAttribute(gated_update_tc_kernel<32, PRECISE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gated_update_tc_kernel<32, PRECISE, FMT><<<grid, TC_TILE, smem, stream>>>(d_h, d_agg, n_atoms, n_cat_atoms, tiles_cat, tiles, per,
+  gated_update_tc_kernel<32, PRECISE, FMT><<<grid, TC_TILE, smem, stream>>>(d_h, d_agg, d_row_ptr, n_atoms, n_cat_atoms, tiles_cat, tiles, per,
                                                                             (const unsigned char*)pc, (const unsigned char*)pa,
                                                                             eps, d_h_out);
   IMP_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int imp_gated_update_tc(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
-                                   const void* d_packed_cat, const void* d_packed_an, float eps, int32_t flags,
-                                   float* d_h_out, void* stream) {
-  IMP_REQUIRE(n_atoms >= 0 && n_cat_atoms >= 0 && n_cat_atoms <= n_atoms, IMP_ERR_ARG, "imp_gated_update_tc: bad sizes");
-  IMP_REQUIRE(d == 32, IMP_ERR_DIM, "imp_gated_update_tc: atom_dim %d not supported by the tensor path (32)", d);
+static int gated_update_tc_any(const float* d_h, const float* d_agg_or_msg, const int* d_row_ptr, int32_t n_atoms, int32_t n_cat_atoms,
+                               int32_t d, const void* d_packed_cat, const void* d_packed_an, float eps, int32_t flags, float* d_h_out,
+                               void* stream, const char* who) {
+  IMP_REQUIRE(n_atoms >= 0 && n_cat_atoms >= 0 && n_cat_atoms <= n_atoms, IMP_ERR_ARG, "%s: bad sizes", who);
+  IMP_REQUIRE(d == 32, IMP_ERR_DIM, "%s: atom_dim %d not supported by the tensor path (32)", who, d);
   if (n_atoms == 0) return 0;
-  IMP_REQUIRE(d_h && d_agg && d_h_out && d_packed_cat && d_packed_an, IMP_ERR_ARG, "imp_gated_update_tc: null pointer");
-  IMP_REQUIRE(imp_device_is_sm100(), IMP_ERR_UNSUPPORTED, "imp_gated_update_tc: tcgen05 needs an sm_100 device");
+  IMP_REQUIRE(d_h && d_h_out && d_packed_cat && d_packed_an, IMP_ERR_ARG, "%s: null pointer", who);
+  IMP_REQUIRE(imp_device_is_sm100(), IMP_ERR_UNSUPPORTED, "%s: tcgen05 needs an sm_100 device", who);
   const int tiles_cat = (int)ceil_div(n_cat_atoms, TC_TILE), tiles_an = (int)ceil_div(n_atoms - n_cat_atoms, TC_TILE);
   const int tiles = tiles_cat + tiles_an;
   const int max_ctas = 148 * 4;
@@ -283,9 +296,27 @@ extern "C" int imp_gated_update_tc(const float* d_h, const float* d_agg, int32_t
   const int grid = (int)ceil_div(tiles, per);
   cudaStream_t st = (cudaStream_t)stream;
   const bool precise = flags & IMP_TC_PRECISE_EPILOGUE, f16 = flags & IMP_TC_FP16;
+  const float* a = d_agg_or_msg;
   if (precise)
-    return f16 ? launch_gru_tc<true, tc::FMT_F16>(d_h, d_agg, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st)
-               : launch_gru_tc<true, tc::FMT_BF16>(d_h, d_agg, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st);
-  return f16 ? launch_gru_tc<false, tc::FMT_F16>(d_h, d_agg, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st)
-             : launch_gru_tc<false, tc::FMT_BF16>(d_h, d_agg, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st);
+    return f16 ? launch_gru_tc<true, tc::FMT_F16>(d_h, a, d_row_ptr, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st)
+               : launch_gru_tc<true, tc::FMT_BF16>(d_h, a, d_row_ptr, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st);
+  return f16 ? launch_gru_tc<false, tc::FMT_F16>(d_h, a, d_row_ptr, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st)
+             : launch_gru_tc<false, tc::FMT_BF16>(d_h, a, d_row_ptr, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st);
+}
+
+extern "C" int imp_gated_update_tc(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
+                                   const void* d_packed_cat, const void* d_packed_an, float eps, int32_t flags,
+                                   float* d_h_out, void* stream) {
+  IMP_REQUIRE(d_agg || n_atoms == 0, IMP_ERR_ARG, "imp_gated_update_tc: agg is null");
+  return gated_update_tc_any(d_h, d_agg, nullptr, n_atoms, n_cat_atoms, d, d_packed_cat, d_packed_an, eps, flags, d_h_out, stream,
+                             "imp_gated_update_tc");
+}
+
+extern "C" int imp_reduce_gated_update_tc(const imp_graph_t* g, const float* d_h, const float* d_msg, int32_t d,
+                                          const void* d_packed_cat, const void* d_packed_an, float eps, int32_t flags,
+                                          float* d_h_out, void* stream) {
+  IMP_REQUIRE(g && g->row_ptr, IMP_ERR_ARG, "imp_reduce_gated_update_tc: graph / row_ptr is null");
+  IMP_REQUIRE(d_msg || g->n_unique == 0, IMP_ERR_ARG, "imp_reduce_gated_update_tc: messages are null");
+  return gated_update_tc_any(d_h, d_msg, g->row_ptr, g->n_atoms, g->n_cat_atoms, d, d_packed_cat, d_packed_an, eps, flags, d_h_out,
+                             stream, "imp_reduce_gated_update_tc");
 }

@@ -334,6 +334,19 @@ class MPNNModel(TrainMixin):
         _lib.call("imp_embed_atoms", self._ptr("atom_emb"), s["atom_vocab_size"], batch.dev["atom_id"].data_ptr(), N, d,
                   h[0].data_ptr(), st)
         for i in range(S):
+            if (not keep and not unfused_messages and self.precision != "fp32" and d == 32 and "bucket_perm" in batch.dev
+                    and not getattr(self, "simt_messages", False)):
+                # tensor staged path without intermediates: grouped tcgen05 message GEMM, then Reduce folded into the
+                # load stage of the tcgen05 GatedUpdate (agg is never written)
+                mbase, gbase = self._ws["msg_packed"].data_ptr(), self._ws["gru_packed"].data_ptr()
+                msg = self._buf("msg", batch.n_unique * d)
+                cws = self._buf("msg_chunks", 2 * s["bond_vocab_size"] + 1, torch.int32)
+                _lib.call("imp_edge_messages_tc", C.byref(g), h[i].data_ptr(), d, mbase + self._msg_pack_bytes * i,
+                          mbase + self._msg_pack_bytes * (S + i), self.tc_flags(), msg.data_ptr(), cws.data_ptr(), st)
+                _lib.call("imp_reduce_gated_update_tc", C.byref(g), h[i].data_ptr(), msg.data_ptr(), d,
+                          gbase + self._gru_pack_bytes * i, gbase + self._gru_pack_bytes * (S + i), C.c_float(self.LN_EPS),
+                          self.tc_flags(), h[i + 1].data_ptr(), st)
+                continue
             if unfused_messages:
                 msg = self._buf("msg", batch.n_unique * d)
                 _lib.call("imp_edge_messages", C.byref(g), h[i].data_ptr(), d, self.table_ptr(0, i, False),
@@ -471,7 +484,7 @@ class MPNNModel(TrainMixin):
         if self.wide_supported():
             return 2 + 2 * self.spec["num_steps"] + 1
         if self.precision != "fp32" and self.spec["atom_dim"] == 32:
-            return 1 + 4 * self.spec["num_steps"] + 1  # chunk scan, grouped GEMM, segment sum, GatedUpdate per step
+            return 1 + 3 * self.spec["num_steps"] + 1  # chunk scan, grouped message GEMM, Reduce + GatedUpdate per step
         if batch is not None and self.use_fused(batch):
             return 2
         return 1 + 2 * self.spec["num_steps"] + 1

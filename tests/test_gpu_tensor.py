@@ -154,6 +154,41 @@ def test_tensor_message_kernel_vs_fp32_kernel(kind, precision):
         assert float(agg[deg == 0].abs().max()) == 0.0
 
 
+def test_reduce_folded_into_gated_update_is_bit_identical():
+    """imp_reduce_gated_update_tc (message rows summed in the load stage) == imp_segment_sum + imp_gated_update_tc."""
+    import ctypes as C
+
+    from ionic_mpnn_b200 import _lib, graph
+    from ionic_mpnn_b200.model import MPNNModel, make_spec
+
+    spec = make_spec("melting_point")
+    batch, _, _ = graph.synth_batch(1500, seed=23, with_temperature=False)
+    batch.to("cuda")
+    m = MPNNModel(spec, seed=3, precision="fp16", fused=False)
+    m.refresh_tables()
+    g = batch.c_struct()
+    d, S = 32, spec["num_steps"]
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rng = torch.Generator(device="cuda").manual_seed(1)
+    h = torch.randn(batch.n_atoms, d, device="cuda", generator=rng)
+    msg = torch.randn(batch.n_unique, d, device="cuda", generator=rng)
+    agg = torch.empty_like(h)
+    out_a, out_b = torch.empty_like(h), torch.empty_like(h)
+    gb = m._ws["gru_packed"].data_ptr()
+    _lib.call("imp_segment_sum", C.byref(g), msg.data_ptr(), d, agg.data_ptr(), st)
+    _lib.call("imp_gated_update_tc", h.data_ptr(), agg.data_ptr(), batch.n_atoms, batch.n_cat_atoms, d, gb,
+              gb + m._gru_pack_bytes * S, C.c_float(1e-3), m.tc_flags(), out_a.data_ptr(), st)
+    _lib.call("imp_reduce_gated_update_tc", C.byref(g), h.data_ptr(), msg.data_ptr(), d, gb, gb + m._gru_pack_bytes * S,
+              C.c_float(1e-3), m.tc_flags(), out_b.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out_b).all()
+    assert torch.equal(out_a, out_b)
+    # and the model's two routes (keep=True: separate kernels; default: folded) agree
+    a, _ = m.forward_packed(batch, keep=True)
+    b = m.forward_packed(batch)
+    assert torch.equal(a, b)
+
+
 def test_bf16_cfg1_thousand_pairs_vs_fp64_oracle():
     from ionic_mpnn_b200 import synth
     from ionic_mpnn_b200.viscosity import build_model

@@ -211,7 +211,7 @@ def stage_flops(batch, d, S):
             "gated_update_wide": 12 * N * d * d, "message_agg": 2 * batch.n_unique * d * d,
             # wide tensor path: algorithmic message work is 2*E*d^2 (the kernel executes 16*N*d^2 as Z.Wc, K = 8d)
             "wide_message": 2 * E * d * d, "wide_gated_update": 12 * N * d * d,
-            "edge_messages_tc": 2 * batch.n_unique * d * d}
+            "edge_messages_tc": 2 * batch.n_unique * d * d, "reduce_gated_update_tc": 12 * N * d * d}
 
 
 def stage_bytes(batch, d, S, s=4):
@@ -229,6 +229,7 @@ def stage_bytes(batch, d, S, s=4):
         # entry, bucket_perm + src + bond|mult; then the CSR segment sum
         "edge_messages_tc": Eu * (2 * d * 4 + 12),
         "segment_sum": Eu * d * 4 + N * d * 4 + 4 * N,
+        "reduce_gated_update_tc": Eu * d * 4 + 4 * N + 2 * N * d * 4,   # message rows + row_ptr + h in / h out (agg never written)
         "gated_update": 3 * N * d * s,                    # h, agg in; h out
         "gated_update_tc": 3 * N * d * s,
         "gated_update_wide": 3 * N * d * s,

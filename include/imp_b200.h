@@ -137,8 +137,19 @@ int imp_message_agg(const imp_graph_t* g /* host struct, device arrays */, const
 int imp_edge_messages(const imp_graph_t* g, const float* d_h, int32_t d, const float* d_table_cat,
                       const float* d_table_an, float* d_msg /* [Eu, d] */, void* stream);
 
-/* K4  Reduce.call (models/layers.py:57-83): agg[v] = sum of msg rows row_ptr[v]..row_ptr[v+1]. */
+/* K3 bucket-grouped for atom_dim 32 (exact fp32): one (tower, bond) bucket chunk per CTA, the 4 KB bond matrix staged in
+ * shared memory and shared by the chunk's entries.  transposed = 0: msg[e] = mult * T[b] x[src_e] (the forward layer);
+ * transposed = 1: msg[e] = mult * T[b]^T x[src_e] (its backward with respect to the atom states: the live entry set is
+ * symmetric, so dh = segment sum of these rows).  d_workspace: imp_edge_messages_workspace_bytes(bond_vocab) bytes. */
+int64_t imp_edge_messages_workspace_bytes(int32_t bond_vocab);
+int imp_edge_messages_grouped(const imp_graph_t* g, const float* d_x, int32_t d, const float* d_table_cat,
+                              const float* d_table_an, int32_t transposed, float* d_msg /* [Eu, d] */, void* d_workspace,
+                              void* stream);
+
+/* K4  Reduce.call (models/layers.py:57-83): agg[v] = sum of msg rows row_ptr[v]..row_ptr[v+1] (imp_segment_sum_add: added
+ * to the rows already in d_agg -- the message term of dL/dh in the backward pass). */
 int imp_segment_sum(const imp_graph_t* g, const float* d_msg, int32_t d, float* d_agg, void* stream);
+int imp_segment_sum_add(const imp_graph_t* g, const float* d_msg, int32_t d, float* d_agg, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K5  GatedUpdate.call (models/layers.py:142-156): z, r gates, candidate, blend, LayerNormalization

@@ -166,9 +166,112 @@ __global__ void __launch_bounds__(256) edge_messages_kernel(const int* __restric
   msg[(int64_t)e * D + l] = (float)(bm >> 16) * s;
 }
 
+// K3 for atom_dim 32, bucket-grouped (the fp32 twin of csrc/msg_tc.cu): a CTA takes <= 128 consecutive slots of ONE
+// (tower, bond) bucket, so the 4 KB bond matrix T[b] is staged in shared memory once and read as warp-broadcast rows by every
+// entry of the chunk (the CSR-order kernels re-read a different matrix per entry through L1, which is what bounds them).
+// Source rows are gathered 8 lanes per 128-byte row into a padded tile, each thread then owns one entry:
+//   forward      msg[e][l] = mult * sum_m T[l][m] * x[src_e][m]                (BondMatrixMessage.call, models/layers.py:108-112)
+//   TRANSPOSED   msg[e][m] = mult * sum_l T[l][m] * x[src_e][l]                (its backward with respect to the atom states)
+// and rows go back through the tile so that stores are whole lines.  Exact fp32, deterministic.
+constexpr int GM_CHUNK = 128;
+constexpr int GM_LD = 33;
+
+__global__ void gm_chunk_scan_kernel(const int* __restrict__ bucket_ptr, int n_buckets, int* __restrict__ chunk_ptr) {
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int b = 0; b < n_buckets; ++b) {
+      chunk_ptr[b] = c;
+      c += (bucket_ptr[b + 1] - bucket_ptr[b] + GM_CHUNK - 1) / GM_CHUNK;
+    }
+    chunk_ptr[n_buckets] = c;
+  }
+}
+
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(GM_CHUNK) grouped_msg_f32_kernel(const int* __restrict__ bucket_ptr, const int* __restrict__ chunk_ptr,
+                                                                   int n_buckets, int bond_vocab, const int* __restrict__ bucket_perm,
+                                                                   const int* __restrict__ col_src, const int* __restrict__ edge_bm,
+                                                                   const float* __restrict__ x, const float* __restrict__ tab_cat,
+                                                                   const float* __restrict__ tab_an, float* __restrict__ msg) {
+  constexpr int D = 32;
+  __shared__ __align__(16) float sT[D * D];
+  __shared__ float stg[GM_CHUNK * GM_LD];
+  const int chunk = blockIdx.x;
+  if (chunk >= __ldg(chunk_ptr + n_buckets)) return;
+  int lo = 0, hi = n_buckets - 1;
+  while (lo < hi) {  // bucket of this chunk: last b with chunk_ptr[b] <= chunk
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(chunk_ptr + mid) <= chunk) lo = mid; else hi = mid - 1;
+  }
+  const int b = lo;
+  const int slot0 = __ldg(bucket_ptr + b) + (chunk - __ldg(chunk_ptr + b)) * GM_CHUNK;
+  const int n = min(GM_CHUNK, __ldg(bucket_ptr + b + 1) - slot0);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const float4* tb = reinterpret_cast<const float4*>((b < bond_vocab ? tab_cat + (int64_t)b * D * D : tab_an + (int64_t)(b - bond_vocab) * D * D));
+  reinterpret_cast<float4*>(sT)[t] = __ldg(tb + t);
+  reinterpret_cast<float4*>(sT)[t + GM_CHUNK] = __ldg(tb + t + GM_CHUNK);
+  int e = -1, src = 0;
+  float mult = 0.f;
+  if (t < n) {
+    e = __ldg(bucket_perm + slot0 + t);
+    mult = (float)((unsigned)__ldg(edge_bm + e) >> 16);
+    src = __ldg(col_src + e);
+  }
+  const int g = lane >> 3, q = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = 4 * it + g;
+    const int rs = __shfl_sync(0xffffffffu, src, r), re = __shfl_sync(0xffffffffu, e, r);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (re >= 0) v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)rs * D) + q);
+    float* d = stg + (warp * 32 + r) * GM_LD + 4 * q;
+    d[0] = v.x, d[1] = v.y, d[2] = v.z, d[3] = v.w;
+  }
+  __syncthreads();  // sT complete, and this warp's rows of stg
+  float xin[D], out[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) xin[c] = stg[t * GM_LD + c];
+  if (!TRANSPOSED) {
+#pragma unroll
+    for (int l = 0; l < D; ++l) {
+      const float4* row = reinterpret_cast<const float4*>(sT + l * D);
+      float a = 0.f;
+#pragma unroll
+      for (int m4 = 0; m4 < D / 4; ++m4) {
+        const float4 w = row[m4];
+        a = fmaf(w.x, xin[4 * m4], a), a = fmaf(w.y, xin[4 * m4 + 1], a), a = fmaf(w.z, xin[4 * m4 + 2], a), a = fmaf(w.w, xin[4 * m4 + 3], a);
+      }
+      out[l] = a;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < D; ++c) out[c] = 0.f;
+#pragma unroll
+    for (int l = 0; l < D; ++l) {
+      const float4* row = reinterpret_cast<const float4*>(sT + l * D);
+#pragma unroll
+      for (int m4 = 0; m4 < D / 4; ++m4) {
+        const float4 w = row[m4];
+        out[4 * m4] = fmaf(w.x, xin[l], out[4 * m4]), out[4 * m4 + 1] = fmaf(w.y, xin[l], out[4 * m4 + 1]);
+        out[4 * m4 + 2] = fmaf(w.z, xin[l], out[4 * m4 + 2]), out[4 * m4 + 3] = fmaf(w.w, xin[l], out[4 * m4 + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < D; ++c) stg[t * GM_LD + c] = mult * out[c];
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = 4 * it + g;
+    const int re = __shfl_sync(0xffffffffu, e, r);
+    const float* sr = stg + (warp * 32 + r) * GM_LD + 4 * q;
+    if (re >= 0) reinterpret_cast<float4*>(msg + (int64_t)re * D)[q] = make_float4(sr[0], sr[1], sr[2], sr[3]);
+  }
+}
+
 // K4: contiguous segment sum over CSR rows, one thread per (v, float4 column).
 __global__ void segment_sum_kernel(const int* __restrict__ row_ptr, const float4* __restrict__ msg, int n_atoms, int d4,
-                                   float4* __restrict__ agg) {
+                                   float4* __restrict__ agg, int accumulate) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int v = (int)(t / d4), c = (int)(t % d4);
   if (v >= n_atoms) return;
@@ -180,6 +283,10 @@ __global__ void segment_sum_kernel(const int* __restrict__ row_ptr, const float4
     a.y += m.y;
     a.z += m.z;
     a.w += m.w;
+  }
+  if (accumulate) {
+    const float4 o = agg[(int64_t)v * d4 + c];
+    a.x += o.x, a.y += o.y, a.z += o.z, a.w += o.w;
   }
   agg[(int64_t)v * d4 + c] = a;
 }
@@ -662,13 +769,47 @@ static int message_agg_any(const imp_graph_t* g, const float* d_h, int32_t d, co
   return 0;
 }
 
+static int edge_messages_grouped(const imp_graph_t* g, const float* d_x, const float* d_table_cat, const float* d_table_an, float* d_msg,
+                                 void* d_workspace, int transposed, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = 2 * g->bond_vocab;
+  int* chunk_ptr = reinterpret_cast<int*>(d_workspace);
+  gm_chunk_scan_kernel<<<1, 32, 0, st>>>(g->bucket_ptr, nb, chunk_ptr);
+  IMP_LAUNCH_CHECK();
+  const unsigned grid = (unsigned)(ceil_div(g->n_unique, GM_CHUNK) + nb);  // upper bound; surplus CTAs exit at once
+  if (transposed)
+    grouped_msg_f32_kernel<true><<<grid, GM_CHUNK, 0, st>>>(g->bucket_ptr, chunk_ptr, nb, g->bond_vocab, g->bucket_perm, g->col_src,
+                                                            g->edge_bm, d_x, d_table_cat, d_table_an, d_msg);
+  else
+    grouped_msg_f32_kernel<false><<<grid, GM_CHUNK, 0, st>>>(g->bucket_ptr, chunk_ptr, nb, g->bond_vocab, g->bucket_perm, g->col_src,
+                                                             g->edge_bm, d_x, d_table_cat, d_table_an, d_msg);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+static int edge_messages_any(const imp_graph_t* g, const float* d_h, int32_t d, const float* d_table_cat, const float* d_table_an,
+                             float* d_msg, void* d_workspace, int transposed, void* stream);
+
 extern "C" int imp_edge_messages(const imp_graph_t* g, const float* d_h, int32_t d, const float* d_table_cat,
                                  const float* d_table_an, float* d_msg, void* stream) {
+  return edge_messages_any(g, d_h, d, d_table_cat, d_table_an, d_msg, nullptr, 0, stream);
+}
+extern "C" int64_t imp_edge_messages_workspace_bytes(int32_t bond_vocab) { return (int64_t)(2 * bond_vocab + 1) * 4; }
+extern "C" int imp_edge_messages_grouped(const imp_graph_t* g, const float* d_x, int32_t d, const float* d_table_cat,
+                                         const float* d_table_an, int32_t transposed, float* d_msg, void* d_workspace, void* stream) {
+  IMP_REQUIRE(d == 32 && d_workspace, IMP_ERR_DIM, "imp_edge_messages_grouped: atom_dim %d (32) and a workspace are required", d);
+  return edge_messages_any(g, d_x, d, d_table_cat, d_table_an, d_msg, d_workspace, transposed ? 1 : 0, stream);
+}
+
+static int edge_messages_any(const imp_graph_t* g, const float* d_h, int32_t d, const float* d_table_cat, const float* d_table_an,
+                             float* d_msg, void* d_workspace, int transposed, void* stream) {
   if (int rc = check_graph(g, "imp_edge_messages")) return rc;
   IMP_REQUIRE(dim_ok_msg(d), IMP_ERR_DIM, "imp_edge_messages: atom_dim %d not in {8,16,32,64,128,256} (fp32 path)", d);
   if (g->n_unique == 0) return 0;
   IMP_REQUIRE(d_h && d_table_cat && d_table_an && d_msg && g->col_src && g->edge_bm && g->bucket_perm && g->bucket_ptr, IMP_ERR_ARG,
               "imp_edge_messages: null pointer");
+  if (d == 32 && d_workspace) return edge_messages_grouped(g, d_h, d_table_cat, d_table_an, d_msg, d_workspace, transposed, stream);
+  IMP_REQUIRE(!transposed, IMP_ERR_DIM, "imp_edge_messages_t: atom_dim %d not supported (32, with a workspace)", d);
   const int64_t threads = (int64_t)g->n_unique * d;
   const unsigned blocks = (unsigned)ceil_div(threads, 256);
   IMP_DISPATCH_D_MSG(d, (edge_messages_kernel<D><<<blocks, 256, 0, (cudaStream_t)stream>>>(
@@ -678,14 +819,21 @@ extern "C" int imp_edge_messages(const imp_graph_t* g, const float* d_h, int32_t
   return 0;
 }
 
+static int segment_sum_any(const imp_graph_t* g, const float* d_msg, int32_t d, float* d_agg, int accumulate, void* stream);
 extern "C" int imp_segment_sum(const imp_graph_t* g, const float* d_msg, int32_t d, float* d_agg, void* stream) {
+  return segment_sum_any(g, d_msg, d, d_agg, 0, stream);
+}
+extern "C" int imp_segment_sum_add(const imp_graph_t* g, const float* d_msg, int32_t d, float* d_agg, void* stream) {
+  return segment_sum_any(g, d_msg, d, d_agg, 1, stream);
+}
+static int segment_sum_any(const imp_graph_t* g, const float* d_msg, int32_t d, float* d_agg, int accumulate, void* stream) {
   if (int rc = check_graph(g, "imp_segment_sum")) return rc;
   IMP_REQUIRE(d > 0 && d % 4 == 0, IMP_ERR_DIM, "imp_segment_sum: atom_dim %d must be a multiple of 4", d);
   if (g->n_atoms == 0) return 0;
   IMP_REQUIRE(d_agg && g->row_ptr && (g->n_unique == 0 || d_msg), IMP_ERR_ARG, "imp_segment_sum: null pointer");
   const int64_t threads = (int64_t)g->n_atoms * (d / 4);
   segment_sum_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(
-      g->row_ptr, reinterpret_cast<const float4*>(d_msg), g->n_atoms, d / 4, reinterpret_cast<float4*>(d_agg));
+      g->row_ptr, reinterpret_cast<const float4*>(d_msg), g->n_atoms, d / 4, reinterpret_cast<float4*>(d_agg), accumulate);
   IMP_LAUNCH_CHECK();
   return 0;
 }

@@ -361,6 +361,13 @@ class MPNNModel(TrainMixin):
                 _lib.call("imp_edge_messages_tc", C.byref(g), h[i].data_ptr(), d, mbase + self._msg_pack_bytes * i,
                           mbase + self._msg_pack_bytes * (S + i), self.tc_flags(), msg.data_ptr(), cws.data_ptr(), st)
                 _lib.call("imp_segment_sum", C.byref(g), msg.data_ptr(), d, aggs[i].data_ptr(), st)
+            elif d == 32 and "bucket_perm" in batch.dev and not getattr(self, "simt_messages", False):
+                # exact fp32, bucket-grouped: T[b] staged once per chunk of 128 entries, then the CSR segment sum
+                msg = self._buf("msg", batch.n_unique * d)
+                cws = self._buf("msg_chunks", 2 * s["bond_vocab_size"] + 1, torch.int32)
+                _lib.call("imp_edge_messages_grouped", C.byref(g), h[i].data_ptr(), d, self.table_ptr(0, i, False),
+                          self.table_ptr(1, i, False), 0, msg.data_ptr(), cws.data_ptr(), st)
+                _lib.call("imp_segment_sum", C.byref(g), msg.data_ptr(), d, aggs[i].data_ptr(), st)
             else:
                 _lib.call("imp_message_agg", C.byref(g), h[i].data_ptr(), d, self.table_ptr(0, i, True),
                           self.table_ptr(1, i, True), aggs[i].data_ptr(), st)
@@ -485,6 +492,8 @@ class MPNNModel(TrainMixin):
             return 2 + 2 * self.spec["num_steps"] + 1
         if self.precision != "fp32" and self.spec["atom_dim"] == 32:
             return 1 + 3 * self.spec["num_steps"] + 1  # chunk scan, grouped message GEMM, Reduce + GatedUpdate per step
+        if self.spec["atom_dim"] == 32:
+            return 1 + 4 * self.spec["num_steps"] + 1  # chunk scan, grouped messages, segment sum, GatedUpdate per step
         if batch is not None and self.use_fused(batch):
             return 2
         return 1 + 2 * self.spec["num_steps"] + 1

@@ -108,22 +108,25 @@ class TrainMixin:
         sm = _stream()
         G = st["g"]
         lib = _lib.load()
-        # ---- tables (lane-interleaved + transposed) for this weight set
+        # ---- bond-matrix tables for this weight set: row-major [V_b, d, d] (the bucket-grouped message kernel reads T[b]
+        # for the forward and, transposed on the fly, for the backward)
         n = 2 * S
         per = Vb * d * d
-        til, tilT = self._buf("tr_table_il", n * per), self._buf("tr_table_ilT", n * per)
+        tab = self._buf("tr_table", n * per)
         W = (C.c_void_p * n)(*[self.params[f"{t}_bmm_{i}.bond_transform"].data_ptr() for t in TOWERS for i in range(S)])
-        T1 = (C.c_void_p * n)(*[til.data_ptr() + 4 * per * j for j in range(n)])
-        T2 = (C.c_void_p * n)(*[tilT.data_ptr() + 4 * per * j for j in range(n)])
-        _lib.call("imp_bond_table_train", self._ptr("bond_emb"), Vb, K, d, n, W, T1, T2, sm)
+        T1 = (C.c_void_p * n)(*[tab.data_ptr() + 4 * per * j for j in range(n)])
+        _lib.call("imp_bond_table", self._ptr("bond_emb"), Vb, K, d, n, W, T1, None, sm)
+        msg = self._buf("tr_msg", batch.n_unique * d)
+        cws = self._buf("tr_msg_chunks", 2 * Vb + 1, torch.int32)
         # ---- forward, everything kept
         h = [self._buf(f"tr_h{i}", N * d) for i in range(S + 1)]
         agg = [self._buf(f"tr_agg{i}", N * d) for i in range(S)]
         _lib.call("imp_embed_atoms", self._ptr("atom_emb"), s["atom_vocab_size"], batch.dev["atom_id"].data_ptr(), N, d,
                   h[0].data_ptr(), sm)
         for i in range(S):
-            _lib.call("imp_message_agg", C.byref(g), h[i].data_ptr(), d, til.data_ptr() + 4 * per * i,
-                      til.data_ptr() + 4 * per * (S + i), agg[i].data_ptr(), sm)
+            _lib.call("imp_edge_messages_grouped", C.byref(g), h[i].data_ptr(), d, tab.data_ptr() + 4 * per * i,
+                      tab.data_ptr() + 4 * per * (S + i), 0, msg.data_ptr(), cws.data_ptr(), sm)
+            _lib.call("imp_segment_sum", C.byref(g), msg.data_ptr(), d, agg[i].data_ptr(), sm)
             wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
             _lib.call("imp_gated_update", h[i].data_ptr(), agg[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc), C.byref(wa),
                       C.c_float(self.LN_EPS), h[i + 1].data_ptr(), sm)
@@ -176,8 +179,10 @@ class TrainMixin:
             _lib.call("imp_gated_update_bwd", h[i].data_ptr(), agg[i].data_ptr(), cur.data_ptr(), N, batch.n_cat_atoms, d,
                       C.byref(wc), C.byref(wa), C.c_float(self.LN_EPS), nxt.data_ptr(), dagg.data_ptr(), gc, gn,
                       ws_gru.data_ptr(), sm)
-            _lib.call("imp_message_agg_bwd", C.byref(g), dagg.data_ptr(), d, tilT.data_ptr() + 4 * per * i,
-                      tilT.data_ptr() + 4 * per * (S + i), nxt.data_ptr(), sm)
+            # dh += sum over the (symmetric) live entries of mult * T[b]^T dagg[src]
+            _lib.call("imp_edge_messages_grouped", C.byref(g), dagg.data_ptr(), d, tab.data_ptr() + 4 * per * i,
+                      tab.data_ptr() + 4 * per * (S + i), 1, msg.data_ptr(), cws.data_ptr(), sm)
+            _lib.call("imp_segment_sum_add", C.byref(g), msg.data_ptr(), d, nxt.data_ptr(), sm)
             _lib.call("imp_bond_transform_bwd", C.byref(g), tr["entry_dst"].data_ptr(), tr["chunk_begin"].data_ptr(),
                       tr["chunk_end"].data_ptr(), tr["n_chunks"], tr["bucket_chunk_ptr"].data_ptr(), dagg.data_ptr(),
                       h[i].data_ptr(), d, K, self._ptr("bond_emb"), self._ptr(f"cat_bmm_{i}.bond_transform"),

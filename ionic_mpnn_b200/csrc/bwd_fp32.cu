@@ -528,7 +528,14 @@ __global__ void __launch_bounds__(GB_THREADS) gated_update_bwd_kernel(const floa
 
 // ================================================================================================ B3 (dTable)
 constexpr int DT_CHUNK_THREADS = 256;
+constexpr int DT_SUB = 128;  // entries staged per pass
+constexpr int DT_LD = 36;    // padded row (floats): 16-byte aligned rows, conflict-free float4 reads of one row
 // One CTA per chunk of a (tower, bond) bucket: partial[chunk][l][m] = sum_e mult_e g[dst_e][l] h[src_e][m].
+// The chunk is walked in passes of 128 entries: indices, then both 128-byte rows of every entry are staged in shared memory
+// (8 lanes per row: whole lines), mult folded into the g row.  Four groups of 64 threads each take a quarter of the pass;
+// a thread owns a 4 x 4 block of the 32 x 32 outer-product sum, i.e. two LDS.128 feed 16 FMA per entry (the previous form
+// did one global scalar + one global float4 load and four redundant index loads per 4 FMA in every one of 256 threads).
+// The four group sums are combined in group order at the end: bit-reproducible.
 template <int D>
 __global__ void __launch_bounds__(DT_CHUNK_THREADS) dtable_partial_kernel(const int* __restrict__ chunk_begin,
                                                                           const int* __restrict__ chunk_end,
@@ -539,44 +546,76 @@ __global__ void __launch_bounds__(DT_CHUNK_THREADS) dtable_partial_kernel(const 
                                                                           const float* __restrict__ g, const float* __restrict__ h,
                                                                           float* __restrict__ partial) {
   static_assert(D == 32, "dtable kernel is instantiated for atom_dim 32");
-  const int l = threadIdx.x / (D / 4), mq = threadIdx.x % (D / 4);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  __shared__ __align__(16) float sG[DT_SUB * DT_LD];
+  __shared__ __align__(16) float sH[DT_SUB * DT_LD];
+  __shared__ int sDst[DT_SUB], sSrc[DT_SUB];
+  __shared__ float sMult[DT_SUB];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = tid >> 6, tg = tid & 63, lq = tg >> 3, mq = tg & 7;
+  const int lg = lane >> 3, q = lane & 7;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
   const int e1 = chunk_end[blockIdx.x];
-  int i = chunk_begin[blockIdx.x];
-  // four entries per iteration: the index chain (perm -> dst / src -> rows) of all four is in flight together;
-  // the accumulation order stays the chunk order (bit-reproducible)
-  for (; i + 4 <= e1; i += 4) {
-    int e[4], dst[4], src[4];
-    float mult[4], gv[4];
-    float4 hv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) e[u] = __ldg(bucket_perm + i + u);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      dst[u] = __ldg(entry_dst + e[u]);
-      src[u] = __ldg(col_src + e[u]);
-      mult[u] = (float)(__ldg(edge_bm + e[u]) >> 16);
+  for (int i0 = chunk_begin[blockIdx.x]; i0 < e1; i0 += DT_SUB) {
+    const int n = min(DT_SUB, e1 - i0);
+    if (tid < DT_SUB) {
+      int dst = -1, src = 0;
+      float mult = 0.f;
+      if (tid < n) {
+        const int e = __ldg(bucket_perm + i0 + tid);
+        dst = __ldg(entry_dst + e), src = __ldg(col_src + e);
+        mult = (float)((unsigned)__ldg(edge_bm + e) >> 16);
+      }
+      sDst[tid] = dst, sSrc[tid] = src, sMult[tid] = mult;
     }
+    __syncthreads();
+    // warp w stages entries [16 w, 16 w + 16): 4 lane groups x 4 iterations, lane % 8 = float4 of the row
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      gv[u] = mult[u] * __ldg(g + (int64_t)dst[u] * D + l);
-      hv[u] = __ldg(reinterpret_cast<const float4*>(h + (int64_t)src[u] * D) + mq);
+    for (int it = 0; it < 4; ++it) {
+      const int r = 16 * warp + 4 * it + lg;
+      const int dst = sDst[r];
+      float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), hv = gv;
+      if (dst >= 0) {
+        const float m = sMult[r];
+        gv = __ldg(reinterpret_cast<const float4*>(g + (int64_t)dst * D) + q);
+        hv = __ldg(reinterpret_cast<const float4*>(h + (int64_t)sSrc[r] * D) + q);
+        gv.x *= m, gv.y *= m, gv.z *= m, gv.w *= m;
+      }
+      *reinterpret_cast<float4*>(&sG[r * DT_LD + 4 * q]) = gv;
+      *reinterpret_cast<float4*>(&sH[r * DT_LD + 4 * q]) = hv;
     }
+    __syncthreads();
+    // group grp accumulates entries [32 grp, 32 grp + 32) of the pass (rows beyond n are zero)
+#pragma unroll 4
+    for (int r = 32 * grp; r < 32 * grp + 32; ++r) {
+      const float4 gv = *reinterpret_cast<const float4*>(&sG[r * DT_LD + 4 * lq]);
+      const float4 hv = *reinterpret_cast<const float4*>(&sH[r * DT_LD + 4 * mq]);
+      const float ga[4] = {gv.x, gv.y, gv.z, gv.w}, hb[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      acc.x = fmaf(gv[u], hv[u].x, acc.x), acc.y = fmaf(gv[u], hv[u].y, acc.y);
-      acc.z = fmaf(gv[u], hv[u].z, acc.z), acc.w = fmaf(gv[u], hv[u].w, acc.w);
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ga[a], hb[b], acc[a][b]);
     }
+    __syncthreads();
   }
-  for (; i < e1; ++i) {
-    const int e = __ldg(bucket_perm + i);
-    const int dst = __ldg(entry_dst + e), src = __ldg(col_src + e);
-    const float mult = (float)(__ldg(edge_bm + e) >> 16);
-    const float gv = mult * __ldg(g + (int64_t)dst * D + l);
-    const float4 hv = __ldg(reinterpret_cast<const float4*>(h + (int64_t)src * D) + mq);
-    acc.x = fmaf(gv, hv.x, acc.x), acc.y = fmaf(gv, hv.y, acc.y), acc.z = fmaf(gv, hv.z, acc.z), acc.w = fmaf(gv, hv.w, acc.w);
+  // combine the four groups in group order through the (now idle) staging arrays: plain 32 x 32 blocks, two per array
+  static_assert(2 * D * D <= DT_SUB * DT_LD, "reduction scratch");
+  float* red2 = grp < 2 ? sG + grp * D * D : sH + (grp - 2) * D * D;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    *reinterpret_cast<float4*>(&red2[(4 * lq + a) * D + 4 * mq]) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+  __syncthreads();
+  {
+    const float4 p0 = reinterpret_cast<const float4*>(sG)[tid], p1 = reinterpret_cast<const float4*>(sG + D * D)[tid];
+    const float4 p2 = reinterpret_cast<const float4*>(sH)[tid], p3 = reinterpret_cast<const float4*>(sH + D * D)[tid];
+    float4 o;
+    o.x = ((p0.x + p1.x) + p2.x) + p3.x, o.y = ((p0.y + p1.y) + p2.y) + p3.y;
+    o.z = ((p0.z + p1.z) + p2.z) + p3.z, o.w = ((p0.w + p1.w) + p2.w) + p3.w;
+    reinterpret_cast<float4*>(partial + (int64_t)blockIdx.x * D * D)[tid] = o;
   }
-  reinterpret_cast<float4*>(partial + (int64_t)blockIdx.x * D * D)[threadIdx.x] = acc;
 }
 
 // dTable[bucket][lm] = sum over the bucket's chunks (index order)

@@ -256,6 +256,7 @@ constexpr int GB_GS = 36;  // row stride of the 32-wide per-atom vectors
 template <int D>
 struct GruBwdSmem {
   float Wz[2 * D * D], Wr[2 * D * D], Wh[2 * D * D];
+  float WzT[2 * D * D], WrT[2 * D * D], WhT[2 * D * D];  // WT[j][k] = W[k][j], rows of 2D floats (transposed products)
   float bz[D], br[D], bh[D], gamma[D], beta[D];
   float X[GB_TILE * GB_XS];   // [h | agg]
   float RH[GB_TILE * GB_GS];  // r * h
@@ -269,59 +270,66 @@ template <int D>
 __host__ __device__ constexpr int gru_grad_floats() { return 3 * 2 * D * D + 5 * D; }
 // layout (= the layer's variable order in the flat parameter buffer): dWz dbz dWr dbr dWh dbh dgamma dbeta
 
-// Two threads per atom (adjacent lanes: 256 threads for a 128-atom tile): each computes 16 of the 32 output columns of every
-// dense product of its row, so that the SM holds 8 warps instead of 4 and each thread half the dependent FMA chains (the
-// 152 KB of staged rows + weights allow one CTA per SM).  Row-wide quantities (LayerNorm means, the full gate-gradient
-// vectors needed by the transposed products) cross the pair through shared memory rows / one shuffle.
+// 256 threads for a 128-atom tile; a thread owns a 4 x 4 register block of every row-by-weight product: 4 atoms
+// (rows a0 + 4 i of its warp's 16 atoms, interleaved so that the four lane groups of a warp read four consecutive shared
+// rows: conflict-free float4 reads) x 4 output columns (lane % 8).  Per 4 steps of a contraction that is 4 activation float4
+// + 4 weight float4 for 64 FMA (the one-thread-per-atom form read 9 LDS per 32 FMA and left the SM with 4 warps).
+// Transposed products (gate gradients back through Wz, Wr, Wh) read transposed weight copies staged once per CTA, so they
+// have the same shape.  Row-wide terms (LayerNorm means) cross the 8 lanes of a row by three shuffles; everything a
+// thread reads from another lane's columns goes through the warp's own shared rows (__syncwarp only).
 constexpr int GB_THREADS = 2 * GB_TILE;
-constexpr int GB_H = 16;  // columns per thread
 
-// pre[i] = bias[j0+i] + sum_k x0[k] W[k][j0+i] + sum_k x1[k] W[D+k][j0+i]   (x rows in shared memory read as float4)
-template <int D>
-__device__ __forceinline__ void gb_dense_half(float (&acc)[GB_H], const float* __restrict__ W, const float* __restrict__ bias,
-                                              const float* __restrict__ x0, const float* __restrict__ x1, int j0) {
-#pragma unroll
-  for (int i = 0; i < GB_H; ++i) acc[i] = bias[j0 + i];
+__device__ __forceinline__ float gb_comp(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+
+// acc[i][c] += sum_{k < 32} x[atom i][k] * W[k][c0 + c]      (x rows: xs + i * 4 * LD; W rows of WLD floats)
+template <int LD, int WLD>
+__device__ __forceinline__ void gb4_dense(float (&acc)[4][4], const float* __restrict__ W, const float* __restrict__ xs, int c0) {
 #pragma unroll 2
-  for (int k4 = 0; k4 < 2 * D / 4; ++k4) {
-    const float4 xv = *reinterpret_cast<const float4*>(k4 < D / 4 ? x0 + 4 * k4 : x1 + 4 * k4 - D);
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+  for (int k4 = 0; k4 < 8; ++k4) {
+    float4 xv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xs + i * 4 * LD + 4 * k4);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      const float4* w = reinterpret_cast<const float4*>(W + (4 * k4 + kk) * D + j0);
+      const float4 w = *reinterpret_cast<const float4*>(W + (4 * k4 + kk) * WLD + c0);
 #pragma unroll
-      for (int j4 = 0; j4 < GB_H / 4; ++j4) {
-        const float4 wv = w[j4];
-        acc[4 * j4 + 0] = fmaf(xs[kk], wv.x, acc[4 * j4 + 0]);
-        acc[4 * j4 + 1] = fmaf(xs[kk], wv.y, acc[4 * j4 + 1]);
-        acc[4 * j4 + 2] = fmaf(xs[kk], wv.z, acc[4 * j4 + 2]);
-        acc[4 * j4 + 3] = fmaf(xs[kk], wv.w, acc[4 * j4 + 3]);
+      for (int i = 0; i < 4; ++i) {
+        const float x = gb_comp(xv[i], kk);
+        acc[i][0] = fmaf(x, w.x, acc[i][0]), acc[i][1] = fmaf(x, w.y, acc[i][1]);
+        acc[i][2] = fmaf(x, w.z, acc[i][2]), acc[i][3] = fmaf(x, w.w, acc[i][3]);
       }
     }
   }
 }
-// sum_j g[j] W[k][j]   (g in registers, one weight row)
-template <int D>
-__device__ __forceinline__ float gb_dot_row(const float (&g)[D], const float* __restrict__ Wrow) {
-  const float4* w = reinterpret_cast<const float4*>(Wrow);
-  float s = 0.f;
+// a1[i][c] += sum_j G[atom i][j] * WT[j][c0 + c];  a2[i][c] += sum_j G[atom i][j] * WT[j][32 + c0 + c]
+template <int LD>
+__device__ __forceinline__ void gb4_dense_t(float (&a1)[4][4], float (&a2)[4][4], const float* __restrict__ WT,
+                                            const float* __restrict__ gs, int c0) {
+#pragma unroll 2
+  for (int j4 = 0; j4 < 8; ++j4) {
+    float4 gv[4];
 #pragma unroll
-  for (int j4 = 0; j4 < D / 4; ++j4) {
-    const float4 wv = w[j4];
-    s = fmaf(g[4 * j4 + 0], wv.x, s);
-    s = fmaf(g[4 * j4 + 1], wv.y, s);
-    s = fmaf(g[4 * j4 + 2], wv.z, s);
-    s = fmaf(g[4 * j4 + 3], wv.w, s);
+    for (int i = 0; i < 4; ++i) gv[i] = *reinterpret_cast<const float4*>(gs + i * 4 * LD + 4 * j4);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const float4 w1 = *reinterpret_cast<const float4*>(WT + (4 * j4 + jj) * 64 + c0);
+      const float4 w2 = *reinterpret_cast<const float4*>(WT + (4 * j4 + jj) * 64 + 32 + c0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float g = gb_comp(gv[i], jj);
+        a1[i][0] = fmaf(g, w1.x, a1[i][0]), a1[i][1] = fmaf(g, w1.y, a1[i][1]);
+        a1[i][2] = fmaf(g, w1.z, a1[i][2]), a1[i][3] = fmaf(g, w1.w, a1[i][3]);
+        a2[i][0] = fmaf(g, w2.x, a2[i][0]), a2[i][1] = fmaf(g, w2.y, a2[i][1]);
+        a2[i][2] = fmaf(g, w2.z, a2[i][2]), a2[i][3] = fmaf(g, w2.w, a2[i][3]);
+      }
+    }
   }
-  return s;
 }
-template <int D>
-__device__ __forceinline__ void gb_load_row(float (&g)[D], const float* __restrict__ row) {
-#pragma unroll
-  for (int c = 0; c < D / 4; ++c) {
-    const float4 v = *reinterpret_cast<const float4*>(row + 4 * c);
-    g[4 * c] = v.x, g[4 * c + 1] = v.y, g[4 * c + 2] = v.z, g[4 * c + 3] = v.w;
-  }
+__device__ __forceinline__ float gb_row_sum(float v) {  // over the 8 lanes (lane % 8) that share a row
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
 }
 
 // Persistent CTAs; CTAs [0, n_cta_cat) walk the cation tiles, the rest the anion tiles.  Per-CTA partial weight
@@ -335,7 +343,7 @@ __global__ void __launch_bounds__(GB_THREADS) gated_update_bwd_kernel(const floa
   static_assert(D == 32, "gated_update_bwd is instantiated for atom_dim 32");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GruBwdSmem<D>& s = *reinterpret_cast<GruBwdSmem<D>*>(smem_raw);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_cat = (int)blockIdx.x < n_cta_cat;
   const imp_gru_weights_t& w = is_cat ? wc : wa;
   const int base = is_cat ? 0 : n_cat, a_end = is_cat ? n_cat : n_atoms;
@@ -345,6 +353,10 @@ __global__ void __launch_bounds__(GB_THREADS) gated_update_bwd_kernel(const floa
     reinterpret_cast<float4*>(s.Wz)[i] = __ldg(reinterpret_cast<const float4*>(w.Wz) + i);
     reinterpret_cast<float4*>(s.Wr)[i] = __ldg(reinterpret_cast<const float4*>(w.Wr) + i);
     reinterpret_cast<float4*>(s.Wh)[i] = __ldg(reinterpret_cast<const float4*>(w.Wh) + i);
+  }
+  for (int i = tid; i < 2 * D * D; i += GB_THREADS) {  // WT[j][k] = W[k][j]
+    const int j = i / (2 * D), k = i % (2 * D);
+    s.WzT[i] = __ldg(w.Wz + k * D + j), s.WrT[i] = __ldg(w.Wr + k * D + j), s.WhT[i] = __ldg(w.Wh + k * D + j);
   }
   for (int i = tid; i < D; i += GB_THREADS)
     s.bz[i] = w.bz[i], s.br[i] = w.br[i], s.bh[i] = w.bh[i], s.gamma[i] = w.gamma[i], s.beta[i] = w.beta[i];
@@ -359,120 +371,150 @@ __global__ void __launch_bounds__(GB_THREADS) gated_update_bwd_kernel(const floa
   const int vj = tid % D, vq = tid / D;
   float abz = 0.f, abr = 0.f, abh = 0.f, agam = 0.f, abet = 0.f;
 
-  const int at = tid >> 1, hh = tid & 1, j0 = hh * GB_H;  // atom row of the tile, column half
-  float* Xrow = &s.X[at * GB_XS];
-  float* RHrow = &s.RH[at * GB_GS];
-  float* Gzrow = &s.Gz[at * GB_GS];
-  float* Grrow = &s.Gr[at * GB_GS];
-  float* Ghrow = &s.Gh[at * GB_GS];
-  float* GXrow = &s.GX[at * GB_GS];
+  const int qd = lane >> 3, cg = lane & 7, c0 = 4 * cg;
+  const int ar0 = 16 * warp + qd;  // tile row of this thread's atom 0; atom i is row ar0 + 4 i
+  const float* Xb = &s.X[ar0 * GB_XS];
+  float* RHb = &s.RH[ar0 * GB_GS];
+  float* Gzb = &s.Gz[ar0 * GB_GS];
+  float* Grb = &s.Gr[ar0 * GB_GS];
+  float* Ghb = &s.Gh[ar0 * GB_GS];
+  float* GXb = &s.GX[ar0 * GB_GS];
 
   for (int tile = cta; tile < n_tiles; tile += n_cta) {
     const int a0 = base + tile * GB_TILE;
     const int rows = min(GB_TILE, a_end - a0);
-    const bool valid = at < rows;  // rows beyond the tile end run on zeros and contribute exact zeros everywhere
-    const int64_t rowoff = (int64_t)(a0 + at) * D;
-    // ---- own row: lane 0 of the pair stages h, lane 1 agg
-    {
-      const float4* src = reinterpret_cast<const float4*>((hh ? agg : h) + rowoff);
+    // ---- the warp stages its own 16 rows of [h | agg] (8 lanes per 128-byte row); rows beyond the tile end are zeros and
+    // contribute exact zeros to every gradient
 #pragma unroll
-      for (int c = 0; c < D / 4; ++c)
-        reinterpret_cast<float4*>(Xrow + hh * D)[c] = valid ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < 4; ++it) {
+      const int r = 16 * warp + 4 * it + qd;
+      float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), av = hv;
+      if (r < rows) {
+        hv = __ldg(reinterpret_cast<const float4*>(h + (int64_t)(a0 + r) * D) + cg);
+        av = __ldg(reinterpret_cast<const float4*>(agg + (int64_t)(a0 + r) * D) + cg);
+      }
+      *reinterpret_cast<float4*>(&s.X[r * GB_XS + c0]) = hv;
+      *reinterpret_cast<float4*>(&s.X[r * GB_XS + D + c0]) = av;
     }
-    float go[GB_H];
+    float go[4][4];
 #pragma unroll
-    for (int c = 0; c < GB_H / 4; ++c) {
-      const float4 gv = valid ? __ldg(reinterpret_cast<const float4*>(g_out + rowoff + j0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      go[4 * c] = gv.x, go[4 * c + 1] = gv.y, go[4 * c + 2] = gv.z, go[4 * c + 3] = gv.w;
+    for (int i = 0; i < 4; ++i) {
+      const int r = ar0 + 4 * i;
+      const float4 gv = r < rows ? __ldg(reinterpret_cast<const float4*>(g_out + (int64_t)(a0 + r) * D) + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+      go[i][0] = gv.x, go[i][1] = gv.y, go[i][2] = gv.z, go[i][3] = gv.w;
     }
     __syncwarp();
-    float acc[GB_H], zv[GB_H], rv[GB_H];
+    float acc[4][4], zv[4][4], rv[4][4], hx[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t4 = *reinterpret_cast<const float4*>(Xb + i * 4 * GB_XS + c0);
+      hx[i][0] = t4.x, hx[i][1] = t4.y, hx[i][2] = t4.z, hx[i][3] = t4.w;
+    }
     // z
-    gb_dense_half<D>(acc, s.Wz, s.bz, Xrow, Xrow + D, j0);
 #pragma unroll
-    for (int i = 0; i < GB_H; ++i) zv[i] = bw_sigmoid(acc[i]);
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][c] = s.bz[c0 + c];
+    gb4_dense<GB_XS, D>(acc, s.Wz, Xb, c0);
+    gb4_dense<GB_XS, D>(acc, s.Wz + D * D, Xb + D, c0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) zv[i][c] = bw_sigmoid(acc[i][c]);
     // r, r*h
-    gb_dense_half<D>(acc, s.Wr, s.br, Xrow, Xrow + D, j0);
 #pragma unroll
-    for (int i = 0; i < GB_H; ++i) {
-      rv[i] = bw_sigmoid(acc[i]);
-      RHrow[j0 + i] = rv[i] * Xrow[j0 + i];
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][c] = s.br[c0 + c];
+    gb4_dense<GB_XS, D>(acc, s.Wr, Xb, c0);
+    gb4_dense<GB_XS, D>(acc, s.Wr + D * D, Xb + D, c0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) rv[i][c] = bw_sigmoid(acc[i][c]);
+      *reinterpret_cast<float4*>(RHb + i * 4 * GB_GS + c0) =
+          make_float4(rv[i][0] * hx[i][0], rv[i][1] * hx[i][1], rv[i][2] * hx[i][2], rv[i][3] * hx[i][3]);
     }
     __syncwarp();
     // candidate
-    gb_dense_half<D>(acc, s.Wh, s.bh, RHrow, Xrow + D, j0);
-    float nrm[GB_H];
-    float mean = 0.f;
 #pragma unroll
-    for (int i = 0; i < GB_H; ++i) {
-      acc[i] = tanhf(acc[i]);  // ht
-      nrm[i] = fmaf(zv[i], acc[i] - Xrow[j0 + i], Xrow[j0 + i]);
-      mean += nrm[i];
-    }
-    mean = (mean + __shfl_xor_sync(0xffffffffu, mean, 1)) * (1.0f / D);
-    float var = 0.f;
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int i = 0; i < GB_H; ++i) {
-      nrm[i] -= mean;
-      var = fmaf(nrm[i], nrm[i], var);
-    }
-    var += __shfl_xor_sync(0xffffffffu, var, 1);
-    const float inv = 1.0f / sqrtf(var * (1.0f / D) + eps);
-    // LayerNorm backward: dn = inv * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat))
-    float m1 = 0.f, m2 = 0.f;
+      for (int c = 0; c < 4; ++c) acc[i][c] = s.bh[c0 + c];
+    gb4_dense<GB_GS, D>(acc, s.Wh, RHb, c0);
+    gb4_dense<GB_XS, D>(acc, s.Wh + D * D, Xb + D, c0);
+    // blend, LayerNorm forward + backward, gate gradients (per atom row i)
 #pragma unroll
-    for (int i = 0; i < GB_H; ++i) {
-      nrm[i] *= inv;  // xhat
-      GXrow[j0 + i] = go[i] * nrm[i];
-      const float dx = go[i] * s.gamma[j0 + i];
-      m1 += dx;
-      m2 = fmaf(dx, nrm[i], m2);
-    }
-    m1 = (m1 + __shfl_xor_sync(0xffffffffu, m1, 1)) * (1.0f / D);
-    m2 = (m2 + __shfl_xor_sync(0xffffffffu, m2, 1)) * (1.0f / D);
-    // dn -> gate gradients; dh accumulates in go[] (starts as the residual path)
+    for (int i = 0; i < 4; ++i) {
+      float nrm[4], mean = 0.f;
 #pragma unroll
-    for (int i = 0; i < GB_H; ++i) {
-      const float dn = inv * (go[i] * s.gamma[j0 + i] - m1 - nrm[i] * m2);
-      const float z = zv[i], ht = acc[i], hj = Xrow[j0 + i];
-      go[i] = fmaf(dn, 1.0f - z, go[i]);
-      Gzrow[j0 + i] = dn * (ht - hj) * z * (1.0f - z);  // dL/dzpre
-      Ghrow[j0 + i] = dn * z * (1.0f - ht * ht);        // dL/dhpre
+      for (int c = 0; c < 4; ++c) {
+        acc[i][c] = tanhf(acc[i][c]);  // ht
+        nrm[c] = fmaf(zv[i][c], acc[i][c] - hx[i][c], hx[i][c]);
+        mean += nrm[c];
+      }
+      mean = gb_row_sum(mean) * (1.0f / D);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        nrm[c] -= mean;
+        var = fmaf(nrm[c], nrm[c], var);
+      }
+      var = gb_row_sum(var);
+      const float inv = 1.0f / sqrtf(var * (1.0f / D) + eps);
+      // LayerNorm backward: dn = inv * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat))
+      float m1 = 0.f, m2 = 0.f, gx[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        nrm[c] *= inv;  // xhat
+        gx[c] = go[i][c] * nrm[c];
+        const float dx = go[i][c] * s.gamma[c0 + c];
+        m1 += dx;
+        m2 = fmaf(dx, nrm[c], m2);
+      }
+      *reinterpret_cast<float4*>(GXb + i * 4 * GB_GS + c0) = make_float4(gx[0], gx[1], gx[2], gx[3]);
+      m1 = gb_row_sum(m1) * (1.0f / D), m2 = gb_row_sum(m2) * (1.0f / D);
+      float gz[4], gh[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float dn = inv * (go[i][c] * s.gamma[c0 + c] - m1 - nrm[c] * m2);
+        const float z = zv[i][c], ht = acc[i][c], hj = hx[i][c];
+        go[i][c] = fmaf(dn, 1.0f - z, go[i][c]);   // dh starts as the residual path + the (1 - z) path
+        gz[c] = dn * (ht - hj) * z * (1.0f - z);    // dL/dzpre
+        gh[c] = dn * z * (1.0f - ht * ht);          // dL/dhpre
+      }
+      *reinterpret_cast<float4*>(Gzb + i * 4 * GB_GS + c0) = make_float4(gz[0], gz[1], gz[2], gz[3]);
+      *reinterpret_cast<float4*>(Ghb + i * 4 * GB_GS + c0) = make_float4(gh[0], gh[1], gh[2], gh[3]);
     }
     __syncwarp();
-    // through Wh: d(r*h) and dagg need the full dL/dhpre row
-    float dag[GB_H];
-    {
-      float dhp[D];
-      gb_load_row<D>(dhp, Ghrow);
+    // through Wh: d(r*h) (columns k < 32) and dagg (k >= 32)
+    float dag[4][4];
 #pragma unroll
-      for (int i = 0; i < GB_H; ++i) {
-        const int k = j0 + i;
-        const float drh = gb_dot_row<D>(dhp, s.Wh + k * D);
-        const float r = rv[i], hk = Xrow[k];
-        go[i] = fmaf(drh, r, go[i]);
-        Grrow[k] = drh * hk * r * (1.0f - r);  // dL/drpre (r itself is no longer needed in shared memory)
-        dag[i] = gb_dot_row<D>(dhp, s.Wh + (D + k) * D);
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][c] = dag[i][c] = 0.f;
+    gb4_dense_t<GB_GS>(acc, dag, s.WhT, Ghb, c0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float gr[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float drh = acc[i][c], r = rv[i][c];
+        go[i][c] = fmaf(drh, r, go[i][c]);
+        gr[c] = drh * hx[i][c] * r * (1.0f - r);  // dL/drpre
       }
+      *reinterpret_cast<float4*>(Grb + i * 4 * GB_GS + c0) = make_float4(gr[0], gr[1], gr[2], gr[3]);
     }
     __syncwarp();
     // through Wz, Wr
-    {
-      float dzp[D], drp[D];
-      gb_load_row<D>(dzp, Gzrow);
-      gb_load_row<D>(drp, Grrow);
+    gb4_dense_t<GB_GS>(go, dag, s.WzT, Gzb, c0);
+    gb4_dense_t<GB_GS>(go, dag, s.WrT, Grb, c0);
 #pragma unroll
-      for (int i = 0; i < GB_H; ++i) {
-        const int k = j0 + i;
-        go[i] += gb_dot_row<D>(dzp, s.Wz + k * D) + gb_dot_row<D>(drp, s.Wr + k * D);
-        dag[i] += gb_dot_row<D>(dzp, s.Wz + (D + k) * D) + gb_dot_row<D>(drp, s.Wr + (D + k) * D);
-      }
-    }
-    if (valid) {
-#pragma unroll
-      for (int c = 0; c < GB_H / 4; ++c) {
-        reinterpret_cast<float4*>(dh + rowoff + j0)[c] = make_float4(go[4 * c], go[4 * c + 1], go[4 * c + 2], go[4 * c + 3]);
-        reinterpret_cast<float4*>(dagg + rowoff + j0)[c] = make_float4(dag[4 * c], dag[4 * c + 1], dag[4 * c + 2], dag[4 * c + 3]);
+    for (int i = 0; i < 4; ++i) {
+      const int r = ar0 + 4 * i;
+      if (r < rows) {
+        reinterpret_cast<float4*>(dh + (int64_t)(a0 + r) * D)[cg] = make_float4(go[i][0], go[i][1], go[i][2], go[i][3]);
+        reinterpret_cast<float4*>(dagg + (int64_t)(a0 + r) * D)[cg] = make_float4(dag[i][0], dag[i][1], dag[i][2], dag[i][3]);
       }
     }
     __syncthreads();

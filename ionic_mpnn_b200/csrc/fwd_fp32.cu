@@ -838,10 +838,150 @@ static int segment_sum_any(const imp_graph_t* g, const float* d_msg, int32_t d, 
   return 0;
 }
 
+// K5 for atom_dim 32, register-blocked (the shape of gated_update_bwd_kernel, bwd_fp32.cu): 256 threads per 128-atom tile, a
+// thread owns 4 atoms (rows a0 + 4 i of its warp's 16, interleaved: conflict-free float4 row reads) x 4 output columns
+// (lane % 8) of every dense product -- 8 LDS.128 per 64 FMA instead of 9 per 32 with one thread per atom -- and the 78 KB of
+// weights + staged rows allow two CTAs (16 warps) per SM.  LayerNorm means cross the 8 lanes of a row by three shuffles.
+constexpr int K5B_THREADS = 256, K5B_XS = 68, K5B_GS = 36;
+struct K5BSmem {
+  float Wz[2 * 32 * 32], Wr[2 * 32 * 32], Wh[2 * 32 * 32];
+  float bz[32], br[32], bh[32], gamma[32], beta[32];
+  float X[K5_TILE * K5B_XS];   // [h | agg]
+  float RH[K5_TILE * K5B_GS];  // r * h
+};
+__device__ __forceinline__ float k5b_comp(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+template <int LD>
+__device__ __forceinline__ void k5b_dense(float (&acc)[4][4], const float* __restrict__ W, const float* __restrict__ xs, int c0) {
+#pragma unroll 2
+  for (int k4 = 0; k4 < 8; ++k4) {
+    float4 xv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xs + i * 4 * LD + 4 * k4);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 w = *reinterpret_cast<const float4*>(W + (4 * k4 + kk) * 32 + c0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x = k5b_comp(xv[i], kk);
+        acc[i][0] = fmaf(x, w.x, acc[i][0]), acc[i][1] = fmaf(x, w.y, acc[i][1]);
+        acc[i][2] = fmaf(x, w.z, acc[i][2]), acc[i][3] = fmaf(x, w.w, acc[i][3]);
+      }
+    }
+  }
+}
+__device__ __forceinline__ float k5b_row_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
+__global__ void __launch_bounds__(K5B_THREADS, 2) gated_update32_kernel(const float* __restrict__ h, const float* __restrict__ agg,
+                                                                        int n_atoms, int n_cat, int tiles_cat, imp_gru_weights_t wc,
+                                                                        imp_gru_weights_t wa, float eps, float* __restrict__ h_out) {
+  constexpr int D = 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  K5BSmem& s = *reinterpret_cast<K5BSmem*>(smem_raw);
+  const bool is_cat = (int)blockIdx.x < tiles_cat;
+  const imp_gru_weights_t& w = is_cat ? wc : wa;
+  const int a0 = is_cat ? blockIdx.x * K5_TILE : n_cat + (blockIdx.x - tiles_cat) * K5_TILE;
+  const int rows = min(K5_TILE, (is_cat ? n_cat : n_atoms) - a0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 2 * D * D / 4; i += K5B_THREADS) {
+    reinterpret_cast<float4*>(s.Wz)[i] = __ldg(reinterpret_cast<const float4*>(w.Wz) + i);
+    reinterpret_cast<float4*>(s.Wr)[i] = __ldg(reinterpret_cast<const float4*>(w.Wr) + i);
+    reinterpret_cast<float4*>(s.Wh)[i] = __ldg(reinterpret_cast<const float4*>(w.Wh) + i);
+  }
+  for (int i = tid; i < D; i += K5B_THREADS)
+    s.bz[i] = w.bz[i], s.br[i] = w.br[i], s.bh[i] = w.bh[i], s.gamma[i] = w.gamma[i], s.beta[i] = w.beta[i];
+  const int qd = lane >> 3, cg = lane & 7, c0 = 4 * cg;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {  // the warp stages its own 16 rows, 8 lanes per 128-byte row
+    const int r = 16 * warp + 4 * it + qd;
+    float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), av = hv;
+    if (r < rows) {
+      hv = __ldg(reinterpret_cast<const float4*>(h + (int64_t)(a0 + r) * D) + cg);
+      av = __ldg(reinterpret_cast<const float4*>(agg + (int64_t)(a0 + r) * D) + cg);
+    }
+    *reinterpret_cast<float4*>(&s.X[r * K5B_XS + c0]) = hv;
+    *reinterpret_cast<float4*>(&s.X[r * K5B_XS + D + c0]) = av;
+  }
+  __syncthreads();  // weights + rows
+  const int ar0 = 16 * warp + qd;
+  const float* Xb = &s.X[ar0 * K5B_XS];
+  float* RHb = &s.RH[ar0 * K5B_GS];
+  float acc[4][4], zv[4][4], hx[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t4 = *reinterpret_cast<const float4*>(Xb + i * 4 * K5B_XS + c0);
+    hx[i][0] = t4.x, hx[i][1] = t4.y, hx[i][2] = t4.z, hx[i][3] = t4.w;
+  }
+  // r gate -> r * h
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = s.br[c0 + c];
+  k5b_dense<K5B_XS>(acc, s.Wr, Xb, c0);
+  k5b_dense<K5B_XS>(acc, s.Wr + D * D, Xb + D, c0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(RHb + i * 4 * K5B_GS + c0) =
+        make_float4(sigmoidf_precise(acc[i][0]) * hx[i][0], sigmoidf_precise(acc[i][1]) * hx[i][1],
+                    sigmoidf_precise(acc[i][2]) * hx[i][2], sigmoidf_precise(acc[i][3]) * hx[i][3]);
+  // z gate (independent of r * h: runs while the warp's RH rows settle)
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = s.bz[c0 + c];
+  k5b_dense<K5B_XS>(acc, s.Wz, Xb, c0);
+  k5b_dense<K5B_XS>(acc, s.Wz + D * D, Xb + D, c0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) zv[i][c] = sigmoidf_precise(acc[i][c]);
+  __syncwarp();
+  // candidate
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = s.bh[c0 + c];
+  k5b_dense<K5B_GS>(acc, s.Wh, RHb, c0);
+  k5b_dense<K5B_XS>(acc, s.Wh + D * D, Xb + D, c0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float n[4], mean = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      n[c] = (1.0f - zv[i][c]) * hx[i][c] + zv[i][c] * tanhf(acc[i][c]);
+      mean += n[c];
+    }
+    mean = k5b_row_sum(mean) * (1.0f / D);
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      n[c] -= mean;
+      var = fmaf(n[c], n[c], var);
+    }
+    var = k5b_row_sum(var);
+    const float inv = 1.0f / sqrtf(var * (1.0f / D) + eps);
+    const int r = ar0 + 4 * i;
+    if (r < rows)
+      reinterpret_cast<float4*>(h_out + (int64_t)(a0 + r) * D)[cg] =
+          make_float4(n[0] * inv * s.gamma[c0] + s.beta[c0] + hx[i][0], n[1] * inv * s.gamma[c0 + 1] + s.beta[c0 + 1] + hx[i][1],
+                      n[2] * inv * s.gamma[c0 + 2] + s.beta[c0 + 2] + hx[i][2], n[3] * inv * s.gamma[c0 + 3] + s.beta[c0 + 3] + hx[i][3]);
+  }
+}
+
 template <int D>
 static int launch_k5(const float* h, const float* agg, int n_atoms, int n_cat, const imp_gru_weights_t* wc,
                      const imp_gru_weights_t* wa, float eps, float* out, cudaStream_t st) {
   const int tiles_cat = (int)ceil_div(n_cat, K5_TILE), tiles_an = (int)ceil_div(n_atoms - n_cat, K5_TILE);
+  if (D == 32) {
+    IMP_CUDA(cudaFuncSetAttribute(gated_update32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K5BSmem)));
+    gated_update32_kernel<<<tiles_cat + tiles_an, K5B_THREADS, sizeof(K5BSmem), st>>>(h, agg, n_atoms, n_cat, tiles_cat, *wc, *wa, eps, out);
+    IMP_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = sizeof(K5Smem<D>);
   IMP_CUDA(cudaFuncSetAttribute(gated_update_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   gated_update_kernel<D><<<tiles_cat + tiles_an, K5_TILE, smem, st>>>(h, agg, n_atoms, n_cat, tiles_cat, *wc, *wa, eps, out);

@@ -432,3 +432,36 @@ def test_fused_forward_unbalanced_towers_and_small_vocabularies():
     got = fz.forward_packed(b).cpu().numpy()
     assert _rel(got, want) <= BF16_RTOL
     assert np.array_equal(fz.forward_packed(b.to_compact("cuda")).cpu().numpy(), got)
+
+
+def test_staged_tensor_path_unbalanced_towers_small_vocabularies_and_empty_buckets():
+    """The bucket-grouped message kernels (tcgen05 for fp16 / bf16, exact fp32) with tiny cations / large anions, an odd bond
+    vocabulary with unused bond types (empty buckets), chunks shorter than 128 slots, and degenerate ions."""
+    from ionic_mpnn_b200 import graph
+    from ionic_mpnn_b200.graph import FlatIons
+    from ionic_mpnn_b200.viscosity import build_model
+
+    cat = graph.synth_flat(300, 81, 2, 4, atom_types=9, bond_types=3)
+    an = graph.synth_flat(300, 82, 60, 120, atom_types=9, bond_types=3)
+    T = np.random.default_rng(5).uniform(273.15, 373.15, 300).astype(np.float32)
+    b = graph.pack_flat(cat, an, 7, temperature=T).to("cuda")  # bond ids 1..3 of a vocabulary of 7: buckets 0, 4, 5, 6 empty
+    ref = build_model(10, 7, precision="fp32", seed=9)
+    ref.simt_messages = True                                      # CSR-order kernel
+    want = ref.forward_packed(b).cpu().numpy()
+    grouped = build_model(10, 7, precision="fp32", seed=9)        # bucket-grouped fp32 kernel
+    assert _rel(grouped.forward_packed(b).cpu().numpy(), want) <= 1e-5
+    for precision in ("fp16", "bf16"):
+        m = build_model(10, 7, precision=precision, seed=9, fused=False)
+        got = m.forward_packed(b).cpu().numpy()
+        assert np.isfinite(got).all()
+        assert _rel(got, want) <= BF16_RTOL, precision
+    # ions without bonds and single-atom ions: no live entry at all in one tower
+    ions = [{"atom_ids": [3], "bond_ids": [], "edge_indices": [], "num_atoms": 1},
+            {"atom_ids": [1, 2, 3], "bond_ids": [], "edge_indices": [], "num_atoms": 3}]
+    lone = FlatIons.from_ion_dicts(ions)
+    other = graph.synth_flat(2, 83, 5, 9, atom_types=9, bond_types=3)
+    b2 = graph.pack_flat(lone, other, 7, temperature=T[:2]).to("cuda")
+    w2 = ref.forward_packed(b2).cpu().numpy()
+    for precision in ("fp32", "fp16"):
+        m = build_model(10, 7, precision=precision, seed=9, fused=False)
+        assert _rel(m.forward_packed(b2).cpu().numpy(), w2) <= (1e-5 if precision == "fp32" else BF16_RTOL)

@@ -217,6 +217,19 @@ int imp_reduce_gated_update_tc(const imp_graph_t* g, const float* d_h, const flo
                                const void* d_packed_cat, const void* d_packed_an, float eps, int32_t flags,
                                float* d_h_out, void* stream);
 
+/* 16-bit I/O forms of the two calls above (what the staged tensor forward runs when no intermediates are kept): the atom
+ * states have an operand-format copy h16 [N, d] (IEEE half or bfloat16 per IMP_TC_FP16) that the message kernel gathers
+ * and the GatedUpdate writes next to the fp32 state; message rows are stored in the operand format too.  Per step
+ * 2.3 instead of 3.2 GB at BASELINE configs[1].  imp_embed_atoms16 = Embedding(atom) writing both copies. */
+int imp_embed_atoms16(const float* d_atom_emb, int32_t atom_vocab, const int32_t* d_atom_id, int32_t n_atoms, int32_t d,
+                      int32_t flags, float* d_h0, void* d_h0_16, void* stream);
+int imp_edge_messages_tc16(const imp_graph_t* g, const void* d_h16, int32_t d, const void* d_packed_cat,
+                           const void* d_packed_an, int32_t flags, void* d_msg16 /* [Eu, d] 16-bit */, void* d_workspace,
+                           void* stream);
+int imp_reduce_gated_update_tc16(const imp_graph_t* g, const float* d_h, const void* d_msg16, int32_t d,
+                                 const void* d_packed_cat, const void* d_packed_an, float eps, int32_t flags,
+                                 float* d_h_out, void* d_h16_out, void* stream);
+
 /* GlobalSumPool.call alone (models/layers.py:161-164): out[m,:] = sum of h rows of molecule m whose
  * atom_id > 0.  `n_mols` molecules delimited by d_mol_ptr[n_mols+1]. */
 int imp_global_sum_pool(const int32_t* d_mol_ptr, const int32_t* d_atom_id, int32_t n_mols, const float* d_h, int32_t d,

@@ -141,6 +141,110 @@ __global__ void __launch_bounds__(CHUNK) grouped_msg_kernel(const int32_t* __res
   }
 }
 
+// 16-bit I/O form of the same GEMM (what the staged tensor forward runs when no intermediates are kept): source rows come from
+// the operand-format copy of the atom states (h16 [N, 32], 64-byte rows: a 16-byte lane load IS one K piece of the A operand,
+// no conversion) and message rows are written in the operand format too (64 bytes per entry).  Per entry 64 + 64 + 12 bytes
+// instead of 128 + 128 + 12.
+constexpr int STG16_LD = 17;  // padded row of 16 packed words
+
+template <int FMT>
+__global__ void __launch_bounds__(CHUNK) grouped_msg16_kernel(const int32_t* __restrict__ bucket_ptr, const int32_t* __restrict__ chunk_ptr,
+                                                              int n_buckets, int bond_vocab, const int32_t* __restrict__ bucket_perm,
+                                                              const int32_t* __restrict__ col_src, const int32_t* __restrict__ edge_bm,
+                                                              const uint4* __restrict__ h16, const uint8_t* __restrict__ packed_cat,
+                                                              const uint8_t* __restrict__ packed_an, uint4* __restrict__ msg16) {
+  __shared__ __align__(128) uint8_t su[A_BYTES + B_BYTES];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t *sA = su, *sB = su + A_BYTES;
+  uint32_t* stg = reinterpret_cast<uint32_t*>(su);  // CHUNK * STG16_LD words <= A_BYTES
+  static_assert(CHUNK * STG16_LD * 4 <= A_BYTES + B_BYTES, "staging tile");
+  const int chunk = blockIdx.x;
+  if (chunk >= __ldg(chunk_ptr + n_buckets)) return;
+  int lo = 0, hi = n_buckets - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(chunk_ptr + mid) <= chunk) lo = mid; else hi = mid - 1;
+  }
+  const int b = lo;
+  const int slot0 = __ldg(bucket_ptr + b) + (chunk - __ldg(chunk_ptr + b)) * CHUNK;
+  const int n = min(CHUNK, __ldg(bucket_ptr + b + 1) - slot0);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const uint8_t* tb = (b < bond_vocab ? packed_cat + (int64_t)b * B_BYTES : packed_an + (int64_t)(b - bond_vocab) * B_BYTES);
+  if (t == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 0) tc::tmem_alloc<32>(&tmem_slot);
+  *reinterpret_cast<uint4*>(sB + t * 16) = __ldg(reinterpret_cast<const uint4*>(tb) + t);
+  int e = -1, src = 0;
+  float mult = 0.f;
+  if (t < n) {
+    e = __ldg(bucket_perm + slot0 + t);
+    mult = (float)((uint32_t)__ldg(edge_bm + e) >> 16);
+    src = __ldg(col_src + e);
+  }
+  // gather: 4 lanes per 64-byte row; lane % 4 = K piece
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = 8 * it + g;
+    const int rs = __shfl_sync(0xffffffffu, src, r), re = __shfl_sync(0xffffffffu, e, r);
+    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+    if (re >= 0) x = __ldg(h16 + (int64_t)rs * 4 + q);
+    *reinterpret_cast<uint4*>(sA + q * 2048 + (warp * 32 + r) * 16) = x;
+  }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = tc::make_idesc(FMT, CHUNK, D);
+    const uint64_t da = tc::make_smem_desc(tc::smem_u32(sA), 2048, 128), db = tc::make_smem_desc(tc::smem_u32(sB), D * 16, 128);
+    if (tc::elect_one()) {
+      tc::mma_bf16(tmem, da, db, idesc, false);
+      tc::mma_bf16(tmem, da + (uint64_t)(4096 >> 4), db + (uint64_t)((2 * D * 16) >> 4), idesc, true);
+      tc::mma_commit(&bar);
+    }
+    __syncwarp();
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::fence_after_thread_sync();
+  float v[32];
+  tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+  for (int c = 0; c < 16; ++c) stg[t * STG16_LD + c] = tc::pack2<FMT>(mult * v[2 * c], mult * v[2 * c + 1]);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = 8 * it + g;
+    const int re = __shfl_sync(0xffffffffu, e, r);
+    const uint32_t* sr = stg + (warp * 32 + r) * STG16_LD + 4 * q;
+    if (re >= 0) msg16[(int64_t)re * 4 + q] = make_uint4(sr[0], sr[1], sr[2], sr[3]);
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc::fence_after_thread_sync();
+    tc::tmem_dealloc<32>(tmem);
+  }
+}
+
+// Embedding(atom) (train_viscosity.py:163,171) writing the fp32 state and its operand-format copy
+template <int FMT>
+__global__ void embed16_kernel(const float4* __restrict__ emb, const int* __restrict__ atom_id, int64_t total4, int atom_vocab,
+                               float4* __restrict__ out, uint2* __restrict__ out16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int64_t v = i / (D / 4);
+  const int c = (int)(i - v * (D / 4));
+  const int id = min(max(__ldg(atom_id + v), 0), atom_vocab - 1);
+  const float4 x = __ldg(emb + (int64_t)id * (D / 4) + c);
+  out[i] = x;
+  out16[i] = make_uint2(tc::pack2<FMT>(x.x, x.y), tc::pack2<FMT>(x.z, x.w));
+}
+
 // table [V_b, d, d] fp32 (T[b][l][m], models/layers.py:108-112) -> per bond type one 2 KB image of the canonical K-major
 // B operand [piece c of 4][n = l of 32][8 halfs]: B[n][kk] = T[b][n][kk], kk = c*8 + i = m.
 template <int FMT>
@@ -197,6 +301,54 @@ extern "C" int imp_edge_messages_tc(const imp_graph_t* g, const float* d_h, int3
   else
     msgtc::grouped_msg_kernel<tc::FMT_BF16><<<grid, msgtc::CHUNK, 0, st>>>(g->bucket_ptr, chunk_ptr, nb, g->bond_vocab, g->bucket_perm,
                                                                           g->col_src, g->edge_bm, d_h, pc, pa, d_msg);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int imp_embed_atoms16(const float* d_atom_emb, int32_t atom_vocab, const int32_t* d_atom_id, int32_t n_atoms, int32_t d,
+                                 int32_t flags, float* d_h0, void* d_h0_16, void* stream) {
+  IMP_REQUIRE(d == msgtc::D, IMP_ERR_DIM, "imp_embed_atoms16: atom_dim %d not supported by the tensor path (32)", d);
+  IMP_REQUIRE(n_atoms >= 0 && atom_vocab > 0, IMP_ERR_ARG, "imp_embed_atoms16: bad sizes");
+  if (n_atoms == 0) return 0;
+  IMP_REQUIRE(d_atom_emb && d_atom_id && d_h0 && d_h0_16, IMP_ERR_ARG, "imp_embed_atoms16: null pointer");
+  const int64_t total4 = (int64_t)n_atoms * (d / 4);
+  const unsigned blocks = (unsigned)ceil_div(total4, 256);
+  if (flags & IMP_TC_FP16)
+    msgtc::embed16_kernel<tc::FMT_F16><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(d_atom_emb), d_atom_id, total4,
+                                                                               atom_vocab, reinterpret_cast<float4*>(d_h0),
+                                                                               reinterpret_cast<uint2*>(d_h0_16));
+  else
+    msgtc::embed16_kernel<tc::FMT_BF16><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(d_atom_emb), d_atom_id, total4,
+                                                                                atom_vocab, reinterpret_cast<float4*>(d_h0),
+                                                                                reinterpret_cast<uint2*>(d_h0_16));
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int imp_edge_messages_tc16(const imp_graph_t* g, const void* d_h16, int32_t d, const void* d_packed_cat,
+                                      const void* d_packed_an, int32_t flags, void* d_msg16, void* d_workspace, void* stream) {
+  IMP_REQUIRE(g, IMP_ERR_ARG, "imp_edge_messages_tc16: graph is null");
+  IMP_REQUIRE(d == msgtc::D, IMP_ERR_DIM, "imp_edge_messages_tc16: atom_dim %d not supported by the tensor path (32)", d);
+  if (g->n_unique == 0) return 0;
+  IMP_REQUIRE(d_h16 && d_msg16 && d_packed_cat && d_packed_an && d_workspace && g->bucket_ptr && g->bucket_perm && g->col_src && g->edge_bm,
+              IMP_ERR_ARG, "imp_edge_messages_tc16: null pointer (the bond-bucket permutation is required)");
+  IMP_REQUIRE(g->bond_vocab > 0 && g->bond_vocab <= 65535, IMP_ERR_ARG, "imp_edge_messages_tc16: bond vocabulary out of range");
+  IMP_REQUIRE(imp_device_is_sm100(), IMP_ERR_UNSUPPORTED, "imp_edge_messages_tc16: tcgen05 needs an sm_100 device");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = 2 * g->bond_vocab;
+  int32_t* chunk_ptr = reinterpret_cast<int32_t*>(d_workspace);
+  msgtc::chunk_scan_kernel<<<1, 32, 0, st>>>(g->bucket_ptr, nb, chunk_ptr);
+  IMP_LAUNCH_CHECK();
+  const unsigned grid = (unsigned)(ceil_div(g->n_unique, msgtc::CHUNK) + nb);
+  const uint8_t *pc = reinterpret_cast<const uint8_t*>(d_packed_cat), *pa = reinterpret_cast<const uint8_t*>(d_packed_an);
+  if (flags & IMP_TC_FP16)
+    msgtc::grouped_msg16_kernel<tc::FMT_F16><<<grid, msgtc::CHUNK, 0, st>>>(g->bucket_ptr, chunk_ptr, nb, g->bond_vocab, g->bucket_perm,
+                                                                           g->col_src, g->edge_bm, reinterpret_cast<const uint4*>(d_h16), pc,
+                                                                           pa, reinterpret_cast<uint4*>(d_msg16));
+  else
+    msgtc::grouped_msg16_kernel<tc::FMT_BF16><<<grid, msgtc::CHUNK, 0, st>>>(g->bucket_ptr, chunk_ptr, nb, g->bond_vocab, g->bucket_perm,
+                                                                            g->col_src, g->edge_bm, reinterpret_cast<const uint4*>(d_h16), pc,
+                                                                            pa, reinterpret_cast<uint4*>(d_msg16));
   IMP_LAUNCH_CHECK();
   return 0;
 }

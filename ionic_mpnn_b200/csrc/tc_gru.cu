@@ -61,6 +61,12 @@ __device__ __forceinline__ float act_tanh(float x) {
 
 constexpr int TC_TILE = 128;
 
+template <int FMT>
+__device__ __forceinline__ float2 unpack2(uint32_t w) {
+  if (FMT == tc::FMT_BF16) return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+
 template <int D>
 struct GruTcSmem {
   using L = GruPackLayout<D>;
@@ -74,7 +80,8 @@ struct GruTcSmem {
 
 template <int D, bool PRECISE, int FMT>
 __global__ void __launch_bounds__(TC_TILE) gated_update_tc_kernel(const float* __restrict__ h, const float* __restrict__ agg,
-                                                                  const int* __restrict__ row_ptr, int n_atoms, int n_cat,
+                                                                  const int* __restrict__ row_ptr, const uint4* __restrict__ msg16,
+                                                                  uint2* __restrict__ h16_out, int n_atoms, int n_cat,
                                                                   int tiles_cat, int tiles_total,
                                                                   int tiles_per_cta, const unsigned char* __restrict__ packed_cat,
                                                                   const unsigned char* __restrict__ packed_an, float eps,
@@ -129,6 +136,15 @@ __global__ void __launch_bounds__(TC_TILE) gated_update_tc_kernel(const float* _
         h0 = __ldg(hg + 2 * i), h1 = __ldg(hg + 2 * i + 1);
         if (row_ptr == nullptr) {
           g0 = __ldg(ag + 2 * i), g1 = __ldg(ag + 2 * i + 1);
+        } else if (msg16 != nullptr) {
+          // message rows in the operand format (64-byte rows): one 16-byte load = this thread's 8 columns, summed in fp32
+          const int e1 = __ldg(row_ptr + a0 + r + 1);
+          for (int e = __ldg(row_ptr + a0 + r); e < e1; ++e) {
+            const uint4 m = __ldg(msg16 + (size_t)e * CH + c);
+            const float2 p0 = unpack2<FMT>(m.x), p1 = unpack2<FMT>(m.y), p2 = unpack2<FMT>(m.z), p3 = unpack2<FMT>(m.w);
+            g0.x += p0.x, g0.y += p0.y, g0.z += p1.x, g0.w += p1.y;
+            g1.x += p2.x, g1.y += p2.y, g1.z += p3.x, g1.w += p3.y;
+          }
         } else {
           // Reduce (models/layers.py:57-83) folded into the load: `agg` holds the message rows [Eu, D] in CSR order; the
           // four threads of a row each sum their 8 columns over the row's (contiguous) entries, in entry order
@@ -235,6 +251,8 @@ __global__ void __launch_bounds__(TC_TILE) gated_update_tc_kernel(const float* _
     for (int i = tid; i < rows * (D / 4); i += TC_TILE) {
       const int r = i / (D / 4), c = (i % (D / 4)) * 4;
       og[i] = make_float4(s.H[r][c], s.H[r][c + 1], s.H[r][c + 2], s.H[r][c + 3]);
+      if (h16_out != nullptr)  // operand-format copy of the new rows (gathered by the next step's message kernel)
+        h16_out[(size_t)a0 * (D / 4) + i] = make_uint2(tc::pack2<FMT>(s.H[r][c], s.H[r][c + 1]), tc::pack2<FMT>(s.H[r][c + 2], s.H[r][c + 3]));
     }
     __syncthreads();
     phase ^= 1;
@@ -270,18 +288,20 @@ extern "C" int imp_gru_pack_f16(const imp_gru_weights_t* w, int32_t d, void* d_p
 }
 
 template <bool PRECISE, int FMT>
-static int launch_gru_tc(const float* d_h, const float* d_agg, const int* d_row_ptr, int n_atoms, int n_cat_atoms, int tiles_cat, int tiles, int per,
+static int launch_gru_tc(const float* d_h, const float* d_agg, const int* d_row_ptr, const void* d_msg16, void* d_h16_out, int n_atoms, int n_cat_atoms, int tiles_cat, int tiles, int per,
                          int grid, const void* pc, const void* pa, float eps, float* d_h_out, cudaStream_t stream) {
   const size_t smem = sizeof(GruTcSmem<32>);
   IMP_CUDA(cudaFuncSetAttribute(gated_update_tc_kernel<32, PRECISE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gated_update_tc_kernel<32, PRECISE, FMT><<<grid, TC_TILE, smem, stream>>>(d_h, d_agg, d_row_ptr, n_atoms, n_cat_atoms, tiles_cat, tiles, per,
+  gated_update_tc_kernel<32, PRECISE, FMT><<<grid, TC_TILE, smem, stream>>>(d_h, d_agg, d_row_ptr, reinterpret_cast<const uint4*>(d_msg16),
+                                                                            reinterpret_cast<uint2*>(d_h16_out), n_atoms, n_cat_atoms, tiles_cat, tiles, per,
                                                                             (const unsigned char*)pc, (const unsigned char*)pa,
                                                                             eps, d_h_out);
   IMP_LAUNCH_CHECK();
   return 0;
 }
 
-static int gated_update_tc_any(const float* d_h, const float* d_agg_or_msg, const int* d_row_ptr, int32_t n_atoms, int32_t n_cat_atoms,
+static int gated_update_tc_any(const float* d_h, const float* d_agg_or_msg, const int* d_row_ptr, const void* d_msg16, void* d_h16_out,
+                               int32_t n_atoms, int32_t n_cat_atoms,
                                int32_t d, const void* d_packed_cat, const void* d_packed_an, float eps, int32_t flags, float* d_h_out,
                                void* stream, const char* who) {
   IMP_REQUIRE(n_atoms >= 0 && n_cat_atoms >= 0 && n_cat_atoms <= n_atoms, IMP_ERR_ARG, "%s: bad sizes", who);
@@ -298,18 +318,18 @@ static int gated_update_tc_any(const float* d_h, const float* d_agg_or_msg, cons
   const bool precise = flags & IMP_TC_PRECISE_EPILOGUE, f16 = flags & IMP_TC_FP16;
   const float* a = d_agg_or_msg;
   if (precise)
-    return f16 ? launch_gru_tc<true, tc::FMT_F16>(d_h, a, d_row_ptr, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st)
-               : launch_gru_tc<true, tc::FMT_BF16>(d_h, a, d_row_ptr, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st);
-  return f16 ? launch_gru_tc<false, tc::FMT_F16>(d_h, a, d_row_ptr, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st)
-             : launch_gru_tc<false, tc::FMT_BF16>(d_h, a, d_row_ptr, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st);
+    return f16 ? launch_gru_tc<true, tc::FMT_F16>(d_h, a, d_row_ptr, d_msg16, d_h16_out, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st)
+               : launch_gru_tc<true, tc::FMT_BF16>(d_h, a, d_row_ptr, d_msg16, d_h16_out, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st);
+  return f16 ? launch_gru_tc<false, tc::FMT_F16>(d_h, a, d_row_ptr, d_msg16, d_h16_out, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st)
+             : launch_gru_tc<false, tc::FMT_BF16>(d_h, a, d_row_ptr, d_msg16, d_h16_out, n_atoms, n_cat_atoms, tiles_cat, tiles, per, grid, d_packed_cat, d_packed_an, eps, d_h_out, st);
 }
 
 extern "C" int imp_gated_update_tc(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
                                    const void* d_packed_cat, const void* d_packed_an, float eps, int32_t flags,
                                    float* d_h_out, void* stream) {
   IMP_REQUIRE(d_agg || n_atoms == 0, IMP_ERR_ARG, "imp_gated_update_tc: agg is null");
-  return gated_update_tc_any(d_h, d_agg, nullptr, n_atoms, n_cat_atoms, d, d_packed_cat, d_packed_an, eps, flags, d_h_out, stream,
-                             "imp_gated_update_tc");
+  return gated_update_tc_any(d_h, d_agg, nullptr, nullptr, nullptr, n_atoms, n_cat_atoms, d, d_packed_cat, d_packed_an, eps, flags, d_h_out,
+                             stream, "imp_gated_update_tc");
 }
 
 extern "C" int imp_reduce_gated_update_tc(const imp_graph_t* g, const float* d_h, const float* d_msg, int32_t d,
@@ -317,6 +337,17 @@ extern "C" int imp_reduce_gated_update_tc(const imp_graph_t* g, const float* d_h
                                           float* d_h_out, void* stream) {
   IMP_REQUIRE(g && g->row_ptr, IMP_ERR_ARG, "imp_reduce_gated_update_tc: graph / row_ptr is null");
   IMP_REQUIRE(d_msg || g->n_unique == 0, IMP_ERR_ARG, "imp_reduce_gated_update_tc: messages are null");
-  return gated_update_tc_any(d_h, d_msg, g->row_ptr, g->n_atoms, g->n_cat_atoms, d, d_packed_cat, d_packed_an, eps, flags, d_h_out,
-                             stream, "imp_reduce_gated_update_tc");
+  return gated_update_tc_any(d_h, d_msg, g->row_ptr, nullptr, nullptr, g->n_atoms, g->n_cat_atoms, d, d_packed_cat, d_packed_an, eps, flags,
+                             d_h_out, stream, "imp_reduce_gated_update_tc");
+}
+
+extern "C" int imp_reduce_gated_update_tc16(const imp_graph_t* g, const float* d_h, const void* d_msg16, int32_t d,
+                                            const void* d_packed_cat, const void* d_packed_an, float eps, int32_t flags,
+                                            float* d_h_out, void* d_h16_out, void* stream) {
+  IMP_REQUIRE(g && g->row_ptr, IMP_ERR_ARG, "imp_reduce_gated_update_tc16: graph / row_ptr is null");
+  IMP_REQUIRE((d_msg16 || g->n_unique == 0) && (d_h16_out || g->n_atoms == 0), IMP_ERR_ARG, "imp_reduce_gated_update_tc16: null pointer");
+  // an empty message array still needs a non-null tag for the kernel's dispatch: row_ptr has no entries to visit then
+  const void* m = d_msg16 ? d_msg16 : (const void*)g->row_ptr;
+  return gated_update_tc_any(d_h, nullptr, g->row_ptr, m, d_h16_out, g->n_atoms, g->n_cat_atoms, d, d_packed_cat, d_packed_an, eps, flags,
+                             d_h_out, stream, "imp_reduce_gated_update_tc16");
 }

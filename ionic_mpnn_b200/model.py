@@ -331,21 +331,37 @@ class MPNNModel(TrainMixin):
             hb = [self._buf("h0", N * d), self._buf("h1", N * d)]
             h = [hb[i % 2] for i in range(S + 1)]
             aggs = [self._buf("agg", N * d)] * S
-        _lib.call("imp_embed_atoms", self._ptr("atom_emb"), s["atom_vocab_size"], batch.dev["atom_id"].data_ptr(), N, d,
-                  h[0].data_ptr(), st)
+        folded = (not keep and not unfused_messages and self.precision != "fp32" and d == 32 and "bucket_perm" in batch.dev
+                  and not getattr(self, "simt_messages", False))
+        io16 = folded and not getattr(self, "fp32_messages", False)
+        if io16:
+            h16 = [self._buf("h16_0", N * d, torch.int16), self._buf("h16_1", N * d, torch.int16)]
+            _lib.call("imp_embed_atoms16", self._ptr("atom_emb"), s["atom_vocab_size"], batch.dev["atom_id"].data_ptr(), N, d,
+                      self.tc_flags(), h[0].data_ptr(), h16[0].data_ptr(), st)
+        else:
+            _lib.call("imp_embed_atoms", self._ptr("atom_emb"), s["atom_vocab_size"], batch.dev["atom_id"].data_ptr(), N, d,
+                      h[0].data_ptr(), st)
         for i in range(S):
-            if (not keep and not unfused_messages and self.precision != "fp32" and d == 32 and "bucket_perm" in batch.dev
-                    and not getattr(self, "simt_messages", False)):
+            if folded:
                 # tensor staged path without intermediates: grouped tcgen05 message GEMM, then Reduce folded into the
-                # load stage of the tcgen05 GatedUpdate (agg is never written)
+                # load stage of the tcgen05 GatedUpdate (agg is never written); by default 16-bit rows in and out of the
+                # message kernel (operand-format copy of h, operand-format messages)
                 mbase, gbase = self._ws["msg_packed"].data_ptr(), self._ws["gru_packed"].data_ptr()
-                msg = self._buf("msg", batch.n_unique * d)
                 cws = self._buf("msg_chunks", 2 * s["bond_vocab_size"] + 1, torch.int32)
-                _lib.call("imp_edge_messages_tc", C.byref(g), h[i].data_ptr(), d, mbase + self._msg_pack_bytes * i,
-                          mbase + self._msg_pack_bytes * (S + i), self.tc_flags(), msg.data_ptr(), cws.data_ptr(), st)
-                _lib.call("imp_reduce_gated_update_tc", C.byref(g), h[i].data_ptr(), msg.data_ptr(), d,
-                          gbase + self._gru_pack_bytes * i, gbase + self._gru_pack_bytes * (S + i), C.c_float(self.LN_EPS),
-                          self.tc_flags(), h[i + 1].data_ptr(), st)
+                pm = (mbase + self._msg_pack_bytes * i, mbase + self._msg_pack_bytes * (S + i))
+                pg = (gbase + self._gru_pack_bytes * i, gbase + self._gru_pack_bytes * (S + i))
+                if io16:
+                    msg16 = self._buf("msg16", batch.n_unique * d, torch.int16)
+                    _lib.call("imp_edge_messages_tc16", C.byref(g), h16[i % 2].data_ptr(), d, pm[0], pm[1], self.tc_flags(),
+                              msg16.data_ptr(), cws.data_ptr(), st)
+                    _lib.call("imp_reduce_gated_update_tc16", C.byref(g), h[i].data_ptr(), msg16.data_ptr(), d, pg[0], pg[1],
+                              C.c_float(self.LN_EPS), self.tc_flags(), h[i + 1].data_ptr(), h16[(i + 1) % 2].data_ptr(), st)
+                else:
+                    msg = self._buf("msg", batch.n_unique * d)
+                    _lib.call("imp_edge_messages_tc", C.byref(g), h[i].data_ptr(), d, pm[0], pm[1], self.tc_flags(),
+                              msg.data_ptr(), cws.data_ptr(), st)
+                    _lib.call("imp_reduce_gated_update_tc", C.byref(g), h[i].data_ptr(), msg.data_ptr(), d, pg[0], pg[1],
+                              C.c_float(self.LN_EPS), self.tc_flags(), h[i + 1].data_ptr(), st)
                 continue
             if unfused_messages:
                 msg = self._buf("msg", batch.n_unique * d)

@@ -189,6 +189,8 @@ int imp_gated_update_wide(const float* d_h, const float* d_agg, int32_t n_atoms,
 #define IMP_TC_TWO_THREADS_PER_ROW 16
 #define IMP_TC_THREE_CONTEXTS 32
 #define IMP_TC_WIDE_SPLIT_GRU 64
+#define IMP_TC_WIDE_NO_CLUSTER 256 /* wide GatedUpdate without the 2-CTA weight multicast (comparison) */
+#define IMP_TC_MSG_ONE_CHUNK_PER_CTA 128 /* imp_edge_messages_tc16: the non-pipelined kernel (comparison) */
 int64_t imp_gru_pack_bytes(int32_t d);
 int imp_gru_pack_bf16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
 int imp_gru_pack_f16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
@@ -337,6 +339,9 @@ int imp_wide_candidate(const imp_graph_t* g, int32_t d, const void* d_packed_cat
 int imp_wide_gated_update(const imp_graph_t* g, int32_t d, const void* d_packed_cat, const void* d_packed_an, float eps,
                           int32_t flags, void* d_workspace, void* stream);
 int imp_wide_pool(const imp_graph_t* g, int32_t d, const void* d_workspace, float* d_pooled, void* stream);
+/* Debug aid (tools/wide_timeline.py): when set to a device buffer of 16 x 8 int64, CTA 0 of imp_wide_gated_update records
+ * clock64 at its phase boundaries for its first 16 tiles; NULL (default) disables it. */
+void imp_debug_wide_timeline(void* d_buf);
 
 /* K6 without the pooling stage: Dense(fp, relu), Dense(mix, relu) per tower, AddTwoTensors, head
  * (train_viscosity.py:189-214 / train_melting_point.py:173-198) on molecule sums [2P, d] (cations first). */

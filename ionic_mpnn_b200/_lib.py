@@ -52,6 +52,8 @@ TC_F32_ZBUILD = 8
 TC_TWO_THREADS_PER_ROW = 16
 TC_THREE_CONTEXTS = 32
 TC_WIDE_SPLIT_GRU = 64
+TC_MSG_ONE_CHUNK_PER_CTA = 128
+TC_WIDE_NO_CLUSTER = 256
 PACK_DOUBLE_EDGES = 1
 PACK_SHIFT_IDS = 2
 
@@ -115,6 +117,7 @@ SIGNATURES = {
     "imp_wide_gates": (C.c_int, [C.POINTER(Graph), C.c_int32, vp, vp, C.c_int32, vp, vp]),
     "imp_wide_candidate": (C.c_int, [C.POINTER(Graph), C.c_int32, vp, vp, C.c_float, C.c_int32, vp, vp]),
     "imp_wide_gated_update": (C.c_int, [C.POINTER(Graph), C.c_int32, vp, vp, C.c_float, C.c_int32, vp, vp]),
+    "imp_debug_wide_timeline": (None, [vp]),
     "imp_wide_pool": (C.c_int, [C.POINTER(Graph), C.c_int32, vp, vp, vp]),
     "imp_readout_visc": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ReadoutWeights),
                                    C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp]),

@@ -231,6 +231,133 @@ __global__ void __launch_bounds__(CHUNK) grouped_msg16_kernel(const int32_t* __r
   }
 }
 
+// Pipelined form of grouped_msg16_kernel (the default): persistent CTAs, two operand buffers and two accumulators per CTA.
+// While the MMAs and the epilogue of chunk i run, the bucket search, the index loads and the gathers of chunk i + 1 are in
+// flight (cp.async 16-byte copies straight into the other A buffer, zero-filled for the slots past the bucket end), so the
+// serial search -> indices -> gather -> MMA -> store chain of the one-chunk-per-CTA form is overlapped inside the CTA as well
+// as across the CTAs of an SM.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(smem_dst)), "l"(gmem_src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int PIPE_MAX_BUCKETS = 512;  // 2 towers x 256 bond types
+
+struct ChunkIdx {
+  int e, src, n;
+  float mult;
+  const uint8_t* tb;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(CHUNK) grouped_msg16_pipe_kernel(const int32_t* __restrict__ bucket_ptr, const int32_t* __restrict__ chunk_ptr,
+                                                                   int n_buckets, int bond_vocab, const int32_t* __restrict__ bucket_perm,
+                                                                   const int32_t* __restrict__ col_src, const int32_t* __restrict__ edge_bm,
+                                                                   const uint4* __restrict__ h16, const uint8_t* __restrict__ packed_cat,
+                                                                   const uint8_t* __restrict__ packed_an, uint4* __restrict__ msg16) {
+  __shared__ __align__(128) uint8_t su[2][A_BYTES + B_BYTES];
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_cptr[PIPE_MAX_BUCKETS + 1], s_bptr[PIPE_MAX_BUCKETS + 1];  // chunk / slot offsets of the buckets
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int n_chunks = __ldg(chunk_ptr + n_buckets);
+  if ((int)blockIdx.x >= n_chunks) return;
+  for (int i = t; i <= n_buckets; i += CHUNK) s_cptr[i] = __ldg(chunk_ptr + i), s_bptr[i] = __ldg(bucket_ptr + i);
+  int cur_bucket = 0;  // a CTA walks its chunks in increasing order: the bucket index only moves forward
+  if (t == 0) {
+    tc::mbar_init(&bar[0], 1);
+    tc::mbar_init(&bar[1], 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 0) tc::tmem_alloc<64>(&tmem_slot);
+  const int g = lane >> 2, q = lane & 3;
+  const uint32_t idesc = tc::make_idesc(FMT, CHUNK, D);
+
+  auto locate = [&](int chunk) {  // bucket search + this thread's slot
+    ChunkIdx c;
+    while (s_cptr[cur_bucket + 1] <= chunk) ++cur_bucket;  // shared-memory copies: no global latency in the search
+    const int b = cur_bucket;
+    const int slot0 = s_bptr[b] + (chunk - s_cptr[b]) * CHUNK;
+    c.n = min(CHUNK, s_bptr[b + 1] - slot0);
+    c.tb = b < bond_vocab ? packed_cat + (int64_t)b * B_BYTES : packed_an + (int64_t)(b - bond_vocab) * B_BYTES;
+    c.e = -1, c.src = 0, c.mult = 0.f;
+    if (t < c.n) {
+      c.e = __ldg(bucket_perm + slot0 + t);
+      c.mult = (float)((uint32_t)__ldg(edge_bm + c.e) >> 16);
+      c.src = __ldg(col_src + c.e);
+    }
+    return c;
+  };
+  auto gather = [&](const ChunkIdx& c, int p) {  // asynchronous: A rows (4 lanes per 64-byte row) + the T[b] image
+    uint8_t *sA = su[p], *sB = su[p] + A_BYTES;
+    cp_async16(sB + t * 16, c.tb + t * 16, true);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = 8 * it + g;
+      const int rs = __shfl_sync(0xffffffffu, c.src, r), re = __shfl_sync(0xffffffffu, c.e, r);
+      cp_async16(sA + q * 2048 + (warp * 32 + r) * 16, h16 + (int64_t)rs * 4 + q, re >= 0);
+    }
+    cp_async_commit();
+  };
+
+  tc::fence_before_thread_sync();
+  __syncthreads();  // bucket offsets, barriers, TMEM address
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_slot;
+  ChunkIdx cur = locate(blockIdx.x);
+  gather(cur, 0);
+  int i = 0;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++i) {
+    const int p = i & 1;
+    const bool has_next = chunk + (int)gridDim.x < n_chunks;
+    ChunkIdx nxt = cur;
+    if (has_next) {
+      nxt = locate(chunk + gridDim.x);
+      gather(nxt, p ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    tc::fence_proxy_async_smem();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) {
+      tc::fence_after_thread_sync();
+      const uint32_t sa = tc::smem_u32(su[p]);
+      const uint64_t da = tc::make_smem_desc(sa, 2048, 128), db = tc::make_smem_desc(sa + A_BYTES, D * 16, 128);
+      if (tc::elect_one()) {
+        tc::mma_bf16(tmem + p * D, da, db, idesc, false);
+        tc::mma_bf16(tmem + p * D, da + (uint64_t)(4096 >> 4), db + (uint64_t)((2 * D * 16) >> 4), idesc, true);
+        tc::mma_commit(&bar[p]);
+      }
+      __syncwarp();
+    }
+    tc::mbar_wait(&bar[p], (uint32_t)((i >> 1) & 1));
+    tc::fence_after_thread_sync();
+    float v[32];
+    tc::tmem_ld32(tmem + p * D + ((uint32_t)(warp * 32) << 16), v);
+    uint32_t* stg = reinterpret_cast<uint32_t*>(su[p]);  // the operands of this chunk have been consumed
+#pragma unroll
+    for (int c = 0; c < 16; ++c) stg[t * STG16_LD + c] = tc::pack2<FMT>(cur.mult * v[2 * c], cur.mult * v[2 * c + 1]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = 8 * it + g;
+      const int re = __shfl_sync(0xffffffffu, cur.e, r);
+      const uint32_t* sr = stg + (warp * 32 + r) * STG16_LD + 4 * q;
+      if (re >= 0) msg16[(int64_t)re * 4 + q] = make_uint4(sr[0], sr[1], sr[2], sr[3]);
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();  // buffer p and accumulator p are free for chunk i + 2
+    tc::fence_after_thread_sync();
+    cur = nxt;
+  }
+  if (warp == 0) tc::tmem_dealloc<64>(tmem);
+}
+
 // Embedding(atom) (train_viscosity.py:163,171) writing the fp32 state and its operand-format copy
 template <int FMT>
 __global__ void embed16_kernel(const float4* __restrict__ emb, const int* __restrict__ atom_id, int64_t total4, int atom_vocab,
@@ -339,8 +466,25 @@ extern "C" int imp_edge_messages_tc16(const imp_graph_t* g, const void* d_h16, i
   int32_t* chunk_ptr = reinterpret_cast<int32_t*>(d_workspace);
   msgtc::chunk_scan_kernel<<<1, 32, 0, st>>>(g->bucket_ptr, nb, chunk_ptr);
   IMP_LAUNCH_CHECK();
-  const unsigned grid = (unsigned)(ceil_div(g->n_unique, msgtc::CHUNK) + nb);
+  const unsigned grid_all = (unsigned)(ceil_div(g->n_unique, msgtc::CHUNK) + nb);  // upper bound on the number of chunks
   const uint8_t *pc = reinterpret_cast<const uint8_t*>(d_packed_cat), *pa = reinterpret_cast<const uint8_t*>(d_packed_an);
+  if (!(flags & IMP_TC_MSG_ONE_CHUNK_PER_CTA) && nb <= msgtc::PIPE_MAX_BUCKETS) {  // default: persistent, software-pipelined CTAs
+    int dev = 0, sms = 148;
+    IMP_CUDA(cudaGetDevice(&dev));
+    IMP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const unsigned grid = grid_all < (unsigned)(8 * sms) ? grid_all : (unsigned)(8 * sms);
+    if (flags & IMP_TC_FP16)
+      msgtc::grouped_msg16_pipe_kernel<tc::FMT_F16><<<grid, msgtc::CHUNK, 0, st>>>(g->bucket_ptr, chunk_ptr, nb, g->bond_vocab, g->bucket_perm,
+                                                                                  g->col_src, g->edge_bm, reinterpret_cast<const uint4*>(d_h16),
+                                                                                  pc, pa, reinterpret_cast<uint4*>(d_msg16));
+    else
+      msgtc::grouped_msg16_pipe_kernel<tc::FMT_BF16><<<grid, msgtc::CHUNK, 0, st>>>(g->bucket_ptr, chunk_ptr, nb, g->bond_vocab, g->bucket_perm,
+                                                                                   g->col_src, g->edge_bm, reinterpret_cast<const uint4*>(d_h16),
+                                                                                   pc, pa, reinterpret_cast<uint4*>(d_msg16));
+    IMP_LAUNCH_CHECK();
+    return 0;
+  }
+  const unsigned grid = grid_all;
   if (flags & IMP_TC_FP16)
     msgtc::grouped_msg16_kernel<tc::FMT_F16><<<grid, msgtc::CHUNK, 0, st>>>(g->bucket_ptr, chunk_ptr, nb, g->bond_vocab, g->bucket_perm,
                                                                            g->col_src, g->edge_bm, reinterpret_cast<const uint4*>(d_h16), pc,

@@ -68,6 +68,7 @@ struct Args {
   float* h32;
   float eps;
   int precise;
+  long long* timeline;  // debug: phase boundaries of CTA 0 (tools/wide_timeline.py), normally null
 };
 
 struct Ctl {
@@ -445,19 +446,30 @@ constexpr int G_SMEM_BYTES = G_OFF_CTL + (int)sizeof(GCtl) + 64;
 struct GItem {
   int tower, t, lo, hi;
 };
+// Work items = (tower, 128-row tile).  CL == 2: each tower's list is padded to an even length, so that the two CTAs of a
+// cluster (items 2m, 2m + 1) always work on the same tower's weights; a padding item re-reads the tower's last tile and
+// owns no row.
+template <int CL>
+__host__ __device__ __forceinline__ int n_gitems(int n_atoms, int n_cat) {
+  const int nc = (n_cat + TILE - 1) / TILE;
+  const int na = n_atoms > n_cat ? (n_atoms + TILE - 1) / TILE - n_cat / TILE : 0;
+  return CL == 2 ? ((nc + 1) & ~1) + ((na + 1) & ~1) : nc + na;
+}
+template <int CL>
 __device__ __forceinline__ GItem decode_gitem(int i, int n_atoms, int n_cat) {
   GItem it;
   const int nc = (n_cat + TILE - 1) / TILE;
-  if (i < nc) {
-    it.tower = 0, it.t = i, it.lo = 0, it.hi = n_cat;
+  const int na = n_atoms > n_cat ? (n_atoms + TILE - 1) / TILE - n_cat / TILE : 0;
+  const int np0 = CL == 2 ? (nc + 1) & ~1 : nc;
+  if (i < np0) {
+    const bool valid = i < nc;
+    it.tower = 0, it.t = valid ? i : nc - 1, it.lo = 0, it.hi = valid ? n_cat : 0;
   } else {
-    it.tower = 1, it.t = n_cat / TILE + (i - nc), it.lo = n_cat, it.hi = n_atoms;
+    const int j = i - np0;
+    const bool valid = j < na;
+    it.tower = 1, it.t = n_cat / TILE + (valid ? j : na - 1), it.lo = n_cat, it.hi = valid ? n_atoms : n_cat;
   }
   return it;
-}
-static inline int n_gitems(int n_atoms, int n_cat) {
-  const int nc = (n_cat + TILE - 1) / TILE;
-  return nc + (n_atoms > n_cat ? (n_atoms + TILE - 1) / TILE - n_cat / TILE : 0);
 }
 
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
@@ -473,7 +485,7 @@ __device__ __forceinline__ float tanh_f(float x) {
   return PRECISE ? tanhf(x) : fast_tanh(x);
 }
 
-template <bool PRECISE>
+template <bool PRECISE, int CL>
 __global__ void __launch_bounds__(G_THREADS, 1) wide_gru_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* xs = smem + G_OFF_X;
@@ -481,13 +493,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) wide_gru_kernel(const Args a) {
   float2* red_s = reinterpret_cast<float2*>(smem + G_OFF_RED);
   GCtl& ctl = *reinterpret_cast<GCtl*>(smem + G_OFF_CTL);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nc = (a.n_cat + TILE - 1) / TILE;
-  const int items = nc + (a.n_atoms > a.n_cat ? (a.n_atoms + TILE - 1) / TILE - a.n_cat / TILE : 0);
+  const int items = n_gitems<CL>(a.n_atoms, a.n_cat);
+  const uint32_t rank = CL == 2 ? tc::cluster_ctarank() : 0;  // CL == 2: a pair of CTAs (two tiles of one tower) shares every
+                                                               // weight slice: each loads half and multicasts it to both
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < G_STAGES; ++s) {
       tc::mbar_init(&ctl.full[s], 1);
-      tc::mbar_init(&ctl.empty[s], 1);
+      tc::mbar_init(&ctl.empty[s], CL);  // a stage is free when every CTA that receives multicast data in it has consumed it
     }
     tc::mbar_init(&ctl.x_full, 1);
     tc::mbar_init(&ctl.accA, 1);
@@ -499,6 +512,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) wide_gru_kernel(const Args a) {
   if (warp == G_WORKERS + 1) tc::tmem_alloc<512>(&ctl.tmem);
   tc::fence_before_thread_sync();
   __syncthreads();
+  if (CL == 2) tc::cluster_sync();  // the peer's barriers exist before any multicast copy or commit can reach them
   tc::fence_after_thread_sync();
   const uint32_t tmem = ctl.tmem;
 
@@ -507,7 +521,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) wide_gru_kernel(const Args a) {
     if (lane == 0) {
       uint32_t it = 0, k = 0;
       for (int i = blockIdx.x; i < items; i += gridDim.x, ++k) {
-        const GItem w = decode_gitem(i, a.n_atoms, a.n_cat);
+        const GItem w = decode_gitem<CL>(i, a.n_atoms, a.n_cat);
         const uint8_t* pk = w.tower ? a.packed[1] : a.packed[0];
         const uint8_t* aggt = a.agg16 + (int64_t)w.t * 65536;
         if (k > 0) tc::mbar_wait(&ctl.accB, (k - 1) & 1);  // phase B of the previous tile has finished reading X
@@ -523,7 +537,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) wide_gru_kernel(const Args a) {
           const bool stream_a = jj >= G_CHUNKS / 2;
           tc::mbar_arrive_expect_tx(&ctl.full[s], (phase_b ? G_B_BYTES : 2 * G_B_BYTES) + (stream_a ? G_A_BYTES : 0));
           if (stream_a) tc::bulk_copy_g2s(sb, aggt + (jj - G_CHUNKS / 2) * G_A_BYTES, G_A_BYTES, &ctl.full[s]);
-          if (phase_b) {
+          if (CL == 2) {  // this CTA's half of the weight slice(s), into the same stage of both CTAs
+            if (phase_b)
+              tc::bulk_copy_g2s_mc(sb + G_A_BYTES + rank * (G_B_BYTES / 2), pk + OFF_WH + (int64_t)jj * G_B_BYTES + rank * (G_B_BYTES / 2),
+                                   G_B_BYTES / 2, &ctl.full[s], 3);
+            else
+              tc::bulk_copy_g2s_mc(sb + G_A_BYTES + rank * G_B_BYTES, pk + (rank ? OFF_WR : OFF_WZ) + (int64_t)jj * G_B_BYTES, G_B_BYTES,
+                                   &ctl.full[s], 3);
+          } else if (phase_b) {
             tc::bulk_copy_g2s(sb + G_A_BYTES, pk + OFF_WH + (int64_t)jj * G_B_BYTES, G_B_BYTES, &ctl.full[s]);
           } else {
             tc::bulk_copy_g2s(sb + G_A_BYTES, pk + OFF_WZ + (int64_t)jj * G_B_BYTES, G_B_BYTES, &ctl.full[s]);
@@ -555,7 +576,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) wide_gru_kernel(const Args a) {
             tc::mma_bf16(tmem, da + (uint64_t)((ks * 4096) >> 4), dz + (uint64_t)((ks * 8192) >> 4), idesc, j > 0 || ks > 0);
             tc::mma_bf16(tmem + D, da + (uint64_t)((ks * 4096) >> 4), dr + (uint64_t)((ks * 8192) >> 4), idesc, j > 0 || ks > 0);
           }
-          tc::mma_commit(&ctl.empty[s]);
+          if (CL == 2) tc::mma_commit_mc(&ctl.empty[s], 3); else tc::mma_commit(&ctl.empty[s]);
           if (j == G_CHUNKS - 1) tc::mma_commit(&ctl.accA);
         }
         __syncwarp();
@@ -573,7 +594,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) wide_gru_kernel(const Args a) {
 #pragma unroll
           for (int ks = 0; ks < G_KC / 16; ++ks)
             tc::mma_bf16(tmem + D, da + (uint64_t)((ks * 4096) >> 4), db + (uint64_t)((ks * 8192) >> 4), idesc, j > 0 || ks > 0);
-          tc::mma_commit(&ctl.empty[s]);
+          if (CL == 2) tc::mma_commit_mc(&ctl.empty[s], 3); else tc::mma_commit(&ctl.empty[s]);
           if (j == G_CHUNKS - 1) tc::mma_commit(&ctl.accB);
         }
         __syncwarp();
@@ -591,7 +612,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) wide_gru_kernel(const Args a) {
     int cur_tower = -1;
     uint32_t k = 0;
     for (int i = blockIdx.x; i < items; i += gridDim.x, ++k) {
-      const GItem w = decode_gitem(i, a.n_atoms, a.n_cat);
+      const GItem w = decode_gitem<CL>(i, a.n_atoms, a.n_cat);
       const int row = w.t * TILE + rowt;
       const bool mine = row >= w.lo && row < w.hi;
       if (w.tower != cur_tower) {  // bz, br, bh, gamma, beta of this tower -> shared memory
@@ -603,9 +624,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) wide_gru_kernel(const Args a) {
       }
       const uint8_t* hrow = h32b + tp32_off(row, G_COLS / 4 * ch);  // this thread's quads of the fp32 state: + x * 2048
       // ---- EA: r -> r*h operand, in place over the h16 tile
+      const bool tl = a.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && k < 16;
+      if (tl) a.timeline[k * 8 + 0] = clock64();
       tc::mbar_wait(&ctl.x_full, k & 1);
       tc::mbar_wait(&ctl.accA, k & 1);
       tc::fence_after_thread_sync();
+      if (tl) a.timeline[k * 8 + 1] = clock64();
 #pragma unroll 1
       for (int c = 0; c < G_COLS / 32; ++c) {
         float v[32];
@@ -631,12 +655,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) wide_gru_kernel(const Args a) {
       tc::fence_before_thread_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl.rh_ready);
+      if (tl) a.timeline[k * 8 + 2] = clock64();
       // ---- E2 pass 1: blend, statistics; n -> candidate columns, h -> z columns
       float4 hq[4];
 #pragma unroll
       for (int x = 0; x < 4; ++x) hq[x] = mine ? *reinterpret_cast<const float4*>(hrow + x * 2048) : make_float4(0.f, 0.f, 0.f, 0.f);
       tc::mbar_wait(&ctl.accB, k & 1);
       tc::fence_after_thread_sync();
+      if (tl) a.timeline[k * 8 + 3] = clock64();
       float sum = 0.f, sq = 0.f;
 #pragma unroll 1
       for (int c = 0; c < G_COLS / 16; ++c) {
@@ -668,6 +694,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) wide_gru_kernel(const Args a) {
       red_s[ch * TILE + rowt] = make_float2(sum, sq);
       tc::tmem_wait_st();
       tc::named_bar_sync(1, G_WORKERS * 32);
+      if (tl) a.timeline[k * 8 + 4] = clock64();
       sum = 0.f, sq = 0.f;
 #pragma unroll
       for (int o = 0; o < G_CH; ++o) {  // the same order in every slice: all workers of a row see identical statistics
@@ -705,10 +732,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) wide_gru_kernel(const Args a) {
       tc::fence_before_thread_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl.acc_empty);
+      if (tl) a.timeline[k * 8 + 5] = clock64();
     }
   }
   tc::fence_before_thread_sync();
   __syncthreads();
+  if (CL == 2) tc::cluster_sync();  // no CTA leaves while its peer can still signal its barriers
   if (warp == G_WORKERS + 1) {
     tc::fence_after_thread_sync();
     tc::tmem_dealloc<512>(tmem);
@@ -832,6 +861,7 @@ void wide_args(const imp_graph_t* g, void* d_workspace, wide::Args* a) {
   a->z16 = a->agg16 + rows * wide::D * 2;
   a->rh16 = a->z16 + rows * wide::D * 2;
   a->eps = 0.f, a->precise = 0;
+  a->timeline = nullptr;
 }
 
 template <int MODE>
@@ -896,6 +926,9 @@ extern "C" int imp_wide_candidate(const imp_graph_t* g, int32_t d, const void* d
   return wide_part(2, g, nullptr, d, wide::KB, d_packed_cat, d_packed_an, eps, flags, d_workspace, stream, "imp_wide_candidate");
 }
 
+static long long* g_wide_timeline = nullptr;
+extern "C" void imp_debug_wide_timeline(void* d_buf) { g_wide_timeline = reinterpret_cast<long long*>(d_buf); }
+
 extern "C" int imp_wide_gated_update(const imp_graph_t* g, int32_t d, const void* d_packed_cat, const void* d_packed_an, float eps,
                                      int32_t flags, void* d_workspace, void* stream) {
   if (int rc = wide_check(g, d, wide::KB, flags, d_workspace, "imp_wide_gated_update")) return rc;
@@ -905,20 +938,48 @@ extern "C" int imp_wide_gated_update(const imp_graph_t* g, int32_t d, const void
   wide_args(g, d_workspace, &a);
   a.packed[0] = reinterpret_cast<const uint8_t*>(d_packed_cat), a.packed[1] = reinterpret_cast<const uint8_t*>(d_packed_an);
   a.eps = eps, a.precise = (flags & IMP_TC_PRECISE_EPILOGUE) ? 1 : 0;
+  a.timeline = g_wide_timeline;
   static bool attr_done = false;
   if (!attr_done) {
-    IMP_CUDA(cudaFuncSetAttribute(wide::wide_gru_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide::G_SMEM_BYTES));
-    IMP_CUDA(cudaFuncSetAttribute(wide::wide_gru_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide::G_SMEM_BYTES));
+    IMP_CUDA(cudaFuncSetAttribute(wide::wide_gru_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide::G_SMEM_BYTES));
+    IMP_CUDA(cudaFuncSetAttribute(wide::wide_gru_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide::G_SMEM_BYTES));
+    IMP_CUDA(cudaFuncSetAttribute(wide::wide_gru_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide::G_SMEM_BYTES));
+    IMP_CUDA(cudaFuncSetAttribute(wide::wide_gru_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide::G_SMEM_BYTES));
     attr_done = true;
   }
   int dev = 0, sms = 148;
   IMP_CUDA(cudaGetDevice(&dev));
   IMP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int items = wide::n_gitems(a.n_atoms, a.n_cat);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(flags & IMP_TC_WIDE_NO_CLUSTER)) {
+    // clusters of two CTAs share the weight stream (multicast): the grid is the number of clusters that can be co-resident
+    const int items = wide::n_gitems<2>(a.n_atoms, a.n_cat);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(2, 1, 1), cfg.blockDim = dim3(wide::G_THREADS, 1, 1), cfg.dynamicSmemBytes = wide::G_SMEM_BYTES, cfg.stream = st;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      int n = 0;
+      cfg.gridDim = dim3(sms & ~1, 1, 1);
+      IMP_CUDA(cudaOccupancyMaxActiveClusters(&n, wide::wide_gru_kernel<false, 2>, &cfg));
+      max_clusters = n > 0 ? n : 1;
+    }
+    const int clusters = items / 2 < max_clusters ? items / 2 : max_clusters;
+    cfg.gridDim = dim3(2 * clusters, 1, 1);
+    if (a.precise)
+      IMP_CUDA(cudaLaunchKernelEx(&cfg, wide::wide_gru_kernel<true, 2>, a));
+    else
+      IMP_CUDA(cudaLaunchKernelEx(&cfg, wide::wide_gru_kernel<false, 2>, a));
+    return 0;
+  }
+  const int items = wide::n_gitems<1>(a.n_atoms, a.n_cat);
   if (a.precise)
-    wide::wide_gru_kernel<true><<<items < sms ? items : sms, wide::G_THREADS, wide::G_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    wide::wide_gru_kernel<true, 1><<<items < sms ? items : sms, wide::G_THREADS, wide::G_SMEM_BYTES, st>>>(a);
   else
-    wide::wide_gru_kernel<false><<<items < sms ? items : sms, wide::G_THREADS, wide::G_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    wide::wide_gru_kernel<false, 1><<<items < sms ? items : sms, wide::G_THREADS, wide::G_SMEM_BYTES, st>>>(a);
   IMP_LAUNCH_CHECK();
   return 0;
 }

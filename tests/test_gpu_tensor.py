@@ -472,3 +472,43 @@ def test_staged_tensor_path_unbalanced_towers_small_vocabularies_and_empty_bucke
     for precision in ("fp32", "fp16"):
         m = build_model(10, 7, precision=precision, seed=9, fused=False)
         assert _rel(m.forward_packed(b2).cpu().numpy(), w2) <= (1e-5 if precision == "fp32" else BF16_RTOL)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_pipelined_message_kernel_matches_one_chunk_per_cta(precision):
+    """imp_edge_messages_tc16: the persistent software-pipelined kernel (default) and the one-chunk-per-CTA kernel
+    (IMP_TC_MSG_ONE_CHUNK_PER_CTA) write bit-identical message rows; both match the fp32-I/O kernel within 16-bit rounding.
+    More chunks than resident CTAs (8 x 148), so that every CTA pipelines several chunks."""
+    import ctypes as C
+
+    from ionic_mpnn_b200 import _lib, graph
+    from ionic_mpnn_b200.model import MPNNModel, make_spec
+
+    spec = make_spec("melting_point")
+    batch, _, _ = graph.synth_batch(5000, seed=29, with_temperature=False)
+    batch.to("cuda")
+    assert batch.n_unique > 2 * 8 * 148 * 128
+    m = MPNNModel(spec, seed=3, precision=precision, fused=False)
+    m.refresh_tables()
+    g = batch.c_struct()
+    d, S = 32, spec["num_steps"]
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    h = torch.randn(batch.n_atoms, d, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    h16 = h.to(torch.float16 if precision == "fp16" else torch.bfloat16).contiguous()
+    cws = torch.empty(2 * 72 + 1, dtype=torch.int32, device="cuda")
+    base, mb = m._ws["msg_packed"].data_ptr(), m._msg_pack_bytes
+    out = []
+    for extra in (0, _lib.TC_MSG_ONE_CHUNK_PER_CTA):
+        msg16 = torch.full((batch.n_unique, d), float("nan"), dtype=h16.dtype, device="cuda")
+        _lib.call("imp_edge_messages_tc16", C.byref(g), h16.data_ptr(), d, base + mb, base + mb * (S + 1), m.tc_flags() | extra,
+                  msg16.data_ptr(), cws.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert torch.isfinite(msg16.float()).all(), "every CSR entry must have been written"
+        out.append(msg16)
+    assert torch.equal(out[0].view(torch.int16), out[1].view(torch.int16))
+    msg32 = torch.empty(batch.n_unique, d, device="cuda")
+    _lib.call("imp_edge_messages_tc", C.byref(g), h16.float().contiguous().data_ptr(), d, base + mb, base + mb * (S + 1), m.tc_flags(),
+              msg32.data_ptr(), cws.data_ptr(), st)
+    torch.cuda.synchronize()
+    err = float((out[0].float() - msg32).abs().max() / msg32.abs().max())
+    assert err <= (1e-3 if precision == "fp16" else 8e-3), err

@@ -33,7 +33,7 @@ def test_wide_tensor_path_matches_fp64_oracle(n_pairs, num_steps, n_min, n_max, 
 
 
 @pytest.mark.parametrize("kind,n_pairs,seed,tc_flags", [("viscosity", 700, 11, 0), ("melting_point", 130, 12, 0),
-                                                       ("viscosity", 300, 13, 64)])
+                                                       ("viscosity", 300, 13, 64), ("viscosity", 700, 11, 256)])
 def test_wide_tensor_path_vs_fp32_kernels_many_tiles(kind, n_pairs, seed, tc_flags):
     """More super-tiles than SMs (persistent loop, both towers, the straddling tile), compared with the fp32 staged
     kernels (themselves held to the oracle at 2e-5 in test_gpu_parity): every atom state after the last step and every
@@ -52,7 +52,7 @@ def test_wide_tensor_path_vs_fp32_kernels_many_tiles(kind, n_pairs, seed, tc_fla
     want, inter = ref.forward_packed(batch, keep=True)
     model = MPNNModel(spec, seed=5, precision="fp16")
     model.set_weights(ref.get_weights())
-    model.extra_tc_flags = tc_flags  # 64 = IMP_TC_WIDE_SPLIT_GRU: GatedUpdate as two kernels
+    model.extra_tc_flags = tc_flags  # 64 = IMP_TC_WIDE_SPLIT_GRU: GatedUpdate as two kernels; 256 = IMP_TC_WIDE_NO_CLUSTER
     got = model.forward_packed(batch)
     again = model.forward_packed(batch).clone()
     torch.cuda.synchronize()
@@ -88,3 +88,21 @@ def test_wide_tensor_path_edge_cases():
         model.forward_packed(one, keep=True)
     bf = MPNNModel(spec, seed=1, precision="bf16")
     assert not bf.wide_supported()
+
+
+def test_wide_cluster_multicast_is_bit_identical_to_single_cta():
+    """The 2-CTA cluster form of the wide GatedUpdate (each CTA loads half of every weight slice and multicasts it) computes
+    exactly what the single-CTA form computes; odd tile counts per tower exercise the padding items."""
+    from ionic_mpnn_b200 import _lib, graph
+    from ionic_mpnn_b200.model import MPNNModel, make_spec
+
+    spec = make_spec("viscosity", atom_dim=256, num_steps=2)
+    for n_pairs, seed in ((700, 31), (37, 32), (1, 33)):
+        batch, _, _ = graph.synth_batch(n_pairs, seed=seed, n_min=40, n_max=120)
+        a = MPNNModel(spec, seed=5, precision="fp16")
+        b = MPNNModel(spec, seed=5, precision="fp16")
+        b.extra_tc_flags = _lib.TC_WIDE_NO_CLUSTER
+        ya, yb = a.forward_packed(batch), b.forward_packed(batch)
+        torch.cuda.synchronize()
+        assert torch.isfinite(ya).all()
+        assert torch.equal(ya, yb), n_pairs

@@ -559,7 +559,9 @@ class MPNNModel(TrainMixin):
         nbytes = 0
         off = 0
         ready = [torch.cuda.Event(), torch.cuda.Event()]
-        done = [None, None]
+        # the two staging slots and the events of their last readers persist across calls: the first copies of a sweep's
+        # next call run under the tail of the previous call's kernels instead of waiting for the whole compute stream
+        done = st.setdefault("done", [None, None])
         for i, ch in enumerate(chunks):
             fused = self.use_fused(ch)
             use_compact = fused and self.compact_supported() and compact in ("auto", True)
@@ -574,8 +576,10 @@ class MPNNModel(TrainMixin):
                 ch.pin()
             fields = COMPACT_FIELDS if use_compact else (FUSED_FIELDS if fused else GRAPH_FIELDS)
             if st["slots"] is None or st["fields"] != fields:
+                copy.wait_stream(compute)  # the old slots may still be read
                 st["slots"] = [DeviceSlot(self.device, fields), DeviceSlot(self.device, fields)]
                 st["fields"] = fields
+                done[0] = done[1] = None
             slot = st["slots"][i % 2]
             if done[i % 2] is not None:
                 copy.wait_event(done[i % 2])  # the kernels that read this slot two chunks ago have finished

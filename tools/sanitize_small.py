@@ -1,5 +1,5 @@
 """Small invocations of every new kernel path, meant to be run under compute-sanitizer (debug aid):
-   compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+   compute-sanitizer --tool memcheck python tools/sanitize_small.py   (where the pool allows it; also a plain smoke run)"""
 import os
 import sys
 

@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sync-every-step", action="store_true", help="visc_train: read the loss back after every step")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="host-resident chunks the e2e leg streams per step")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="host-resident chunks the e2e leg streams per step")
     return ap.parse_args()
 
 

@@ -127,6 +127,13 @@ __global__ void __launch_bounds__(TC_TILE) gated_update_tc_kernel(const float* _
     // ---- stage [h | agg] as bf16 operand + fp32 h rows
     const float4* hg = reinterpret_cast<const float4*>(h + (size_t)a0 * D);
     const float4* ag = reinterpret_cast<const float4*>(agg + (size_t)a0 * D);
+    int eb[CH], ee[CH];  // entry ranges of this thread's four rows: loaded together, ahead of the per-row chains
+#pragma unroll
+    for (int it = 0; it < CH; ++it) {
+      const int r = (tid + it * TC_TILE) / CH;
+      eb[it] = ee[it] = 0;
+      if (row_ptr != nullptr && r < rows) eb[it] = __ldg(row_ptr + a0 + r), ee[it] = __ldg(row_ptr + a0 + r + 1);
+    }
 #pragma unroll
     for (int it = 0; it < CH; ++it) {
       const int i = tid + it * TC_TILE;
@@ -137,19 +144,26 @@ __global__ void __launch_bounds__(TC_TILE) gated_update_tc_kernel(const float* _
         if (row_ptr == nullptr) {
           g0 = __ldg(ag + 2 * i), g1 = __ldg(ag + 2 * i + 1);
         } else if (msg16 != nullptr) {
-          // message rows in the operand format (64-byte rows): one 16-byte load = this thread's 8 columns, summed in fp32
-          const int e1 = __ldg(row_ptr + a0 + r + 1);
-          for (int e = __ldg(row_ptr + a0 + r); e < e1; ++e) {
-            const uint4 m = __ldg(msg16 + (size_t)e * CH + c);
-            const float2 p0 = unpack2<FMT>(m.x), p1 = unpack2<FMT>(m.y), p2 = unpack2<FMT>(m.z), p3 = unpack2<FMT>(m.w);
-            g0.x += p0.x, g0.y += p0.y, g0.z += p1.x, g0.w += p1.y;
-            g1.x += p2.x, g1.y += p2.y, g1.z += p3.x, g1.w += p3.y;
+          // message rows in the operand format (64-byte rows): one 16-byte load = this thread's 8 columns, summed in fp32.
+          // Up to four rows are loaded before the first is consumed (rows of an atom are contiguous): the stage is bound by
+          // load latency (ncu: long scoreboard 8.3 per issue), and most atoms have <= 4 unique neighbours.
+          const int e1 = ee[it];
+          for (int e = eb[it]; e < e1; e += 4) {
+            uint4 m[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) m[u] = e + u < e1 ? __ldg(msg16 + (size_t)(e + u) * CH + c) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 p0 = unpack2<FMT>(m[u].x), p1 = unpack2<FMT>(m[u].y), p2 = unpack2<FMT>(m[u].z), p3 = unpack2<FMT>(m[u].w);
+              g0.x += p0.x, g0.y += p0.y, g0.z += p1.x, g0.w += p1.y;
+              g1.x += p2.x, g1.y += p2.y, g1.z += p3.x, g1.w += p3.y;
+            }
           }
         } else {
           // Reduce (models/layers.py:57-83) folded into the load: `agg` holds the message rows [Eu, D] in CSR order; the
           // four threads of a row each sum their 8 columns over the row's (contiguous) entries, in entry order
-          const int e1 = __ldg(row_ptr + a0 + r + 1);
-          for (int e = __ldg(row_ptr + a0 + r); e < e1; ++e) {
+          const int e1 = ee[it];
+          for (int e = eb[it]; e < e1; ++e) {
             const float4* m = reinterpret_cast<const float4*>(agg + (size_t)e * D) + 2 * c;
             const float4 m0 = __ldg(m), m1 = __ldg(m + 1);
             g0.x += m0.x, g0.y += m0.y, g0.z += m0.z, g0.w += m0.w;

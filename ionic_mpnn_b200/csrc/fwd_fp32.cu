@@ -277,12 +277,17 @@ __global__ void segment_sum_kernel(const int* __restrict__ row_ptr, const float4
   if (v >= n_atoms) return;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   const int e1 = row_ptr[v + 1];
-  for (int e = row_ptr[v]; e < e1; ++e) {
-    float4 m = __ldg(msg + (int64_t)e * d4 + c);
-    a.x += m.x;
-    a.y += m.y;
-    a.z += m.z;
-    a.w += m.w;
+  for (int e = row_ptr[v]; e < e1; e += 4) {  // four rows in flight; summed in entry order (+0 for the missing ones)
+    float4 m[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) m[u] = e + u < e1 ? __ldg(msg + (int64_t)(e + u) * d4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a.x += m[u].x;
+      a.y += m[u].y;
+      a.z += m[u].z;
+      a.w += m[u].w;
+    }
   }
   if (accumulate) {
     const float4 o = agg[(int64_t)v * d4 + c];

@@ -710,9 +710,24 @@ __global__ void __launch_bounds__(EB_WARPS * 32) embed_bwd_kernel(const int* __r
   __syncwarp();
   const int64_t gw = (int64_t)blockIdx.x * EB_WARPS + warp;
   const int64_t v0 = gw * atoms_per_warp, v1 = min((int64_t)n_atoms, v0 + atoms_per_warp);
-  for (int64_t v = v0; v < v1; ++v) {
-    const int id = min(max(__ldg(atom_id + v), 0), vocab - 1);
-    for (int j = lane; j < d; j += 32) mine[id * d + j] += __ldg(dh0 + v * d + j);
+  if (d == 32) {  // one column per lane: eight atoms' rows in flight, accumulated in atom order (bit-reproducible)
+    for (int64_t v = v0; v < v1; v += 8) {
+      int id[8];
+      float g[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool ok = v + u < v1;
+        id[u] = ok ? min(max(__ldg(atom_id + v + u), 0), vocab - 1) : 0;
+        g[u] = ok ? __ldg(dh0 + (v + u) * 32 + lane) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) mine[id[u] * 32 + lane] += g[u];
+    }
+  } else {
+    for (int64_t v = v0; v < v1; ++v) {
+      const int id = min(max(__ldg(atom_id + v), 0), vocab - 1);
+      for (int j = lane; j < d; j += 32) mine[id * d + j] += __ldg(dh0 + v * d + j);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < vocab * d; i += blockDim.x) {

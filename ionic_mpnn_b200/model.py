@@ -504,15 +504,17 @@ class MPNNModel(TrainMixin):
 
     def launches_per_forward(self, batch=None):
         """Kernels enqueued by forward_packed (tables / packs already valid)."""
+        S = self.spec["num_steps"]
         if self.wide_supported():
-            return 2 + 2 * self.spec["num_steps"] + 1
-        if self.precision != "fp32" and self.spec["atom_dim"] == 32:
-            return 1 + 3 * self.spec["num_steps"] + 1  # chunk scan, grouped message GEMM, Reduce + GatedUpdate per step
-        if self.spec["atom_dim"] == 32:
-            return 1 + 4 * self.spec["num_steps"] + 1  # chunk scan, grouped messages, segment sum, GatedUpdate per step
+            return 1 + 2 * S + 1 + 1  # embed, (messages, GatedUpdate) per step, pool, readout
         if batch is not None and self.use_fused(batch):
-            return 2
-        return 1 + 2 * self.spec["num_steps"] + 1
+            return 2                  # fused forward, readout
+        grouped = batch is None or "bucket_perm" in (batch.dev or {})
+        if self.precision != "fp32" and self.spec["atom_dim"] == 32 and grouped:
+            return 1 + 3 * S + 1      # embed, (chunk scan, grouped message GEMM, Reduce + GatedUpdate) per step, pool + head
+        if self.spec["atom_dim"] == 32 and grouped:
+            return 1 + 4 * S + 1      # embed, (chunk scan, grouped messages, segment sum, GatedUpdate) per step, pool + head
+        return 1 + 2 * S + 1          # embed, (CSR-order messages, GatedUpdate) per step, pool + head
 
     # -- Keras-like surface ---------------------------------------------------------------------
     def pack(self, x):

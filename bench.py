@@ -212,7 +212,8 @@ def stage_flops(batch, d, S):
             # wide tensor path: algorithmic message work is 2*E*d^2 (the kernel executes 16*N*d^2 as Z.Wc, K = 8d)
             "wide_message": 2 * E * d * d, "wide_gated_update": 12 * N * d * d,
             "edge_messages_tc": 2 * batch.n_unique * d * d, "reduce_gated_update_tc": 12 * N * d * d,
-            "edge_messages_tc16": 2 * batch.n_unique * d * d, "reduce_gated_update_tc16": 12 * N * d * d}
+            "edge_messages_tc16": 2 * batch.n_unique * d * d, "reduce_gated_update_tc16": 12 * N * d * d,
+            "edge_messages_tc16_planned": 2 * batch.n_unique * d * d}
 
 
 def stage_bytes(batch, d, S, s=4):
@@ -233,6 +234,8 @@ def stage_bytes(batch, d, S, s=4):
         "reduce_gated_update_tc": Eu * d * 4 + 4 * N + 2 * N * d * 4,   # message rows + row_ptr + h in / h out (agg never written)
         # 16-bit I/O forms: gathered h16 row + 16-bit message row + indices; 16-bit messages + row_ptr + h in / h out + h16 out
         "edge_messages_tc16": Eu * (2 * d * 2 + 12),
+        "edge_messages_tc16_planned": Eu * (2 * d * 2 + 12),
+        "edge_messages_tc16_plan": Eu * (4 + 8 + 8),   # bucket_perm in; src, bond|mult gathered; bucket-ordered copies out
         "reduce_gated_update_tc16": Eu * d * 2 + 4 * N + 2 * N * d * 4 + N * d * 2,
         "embed_atoms16": 4 * N + N * d * 6,
         "gated_update": 3 * N * d * s,                    # h, agg in; h out

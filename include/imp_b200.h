@@ -228,6 +228,14 @@ int imp_embed_atoms16(const float* d_atom_emb, int32_t atom_vocab, const int32_t
 int imp_edge_messages_tc16(const imp_graph_t* g, const void* d_h16, int32_t d, const void* d_packed_cat,
                            const void* d_packed_an, int32_t flags, void* d_msg16 /* [Eu, d] 16-bit */, void* d_workspace,
                            void* stream);
+/* Planned form of imp_edge_messages_tc16 (what the model's forward runs): the index work of a batch -- chunk offsets and
+ * bucket-ordered copies of the source atoms and bond | multiplicity words -- is done once per batch into d_plan
+ * (imp_edge_messages_tc16_plan_bytes bytes), and every step's kernel reads its indices with independent coalesced loads
+ * two chunks ahead of their use.  bond_vocab <= 256.  Bit-identical message rows. */
+int64_t imp_edge_messages_tc16_plan_bytes(int32_t n_unique, int32_t bond_vocab);
+int imp_edge_messages_tc16_plan(const imp_graph_t* g, void* d_plan, void* stream);
+int imp_edge_messages_tc16_planned(const imp_graph_t* g, const void* d_plan, const void* d_h16, int32_t d,
+                                   const void* d_packed_cat, const void* d_packed_an, int32_t flags, void* d_msg16, void* stream);
 int imp_reduce_gated_update_tc16(const imp_graph_t* g, const float* d_h, const void* d_msg16, int32_t d,
                                  const void* d_packed_cat, const void* d_packed_an, float eps, int32_t flags,
                                  float* d_h_out, void* d_h16_out, void* stream);

@@ -95,6 +95,9 @@ SIGNATURES = {
     "imp_reduce_gated_update_tc": (C.c_int, [C.POINTER(Graph), vp, vp, C.c_int32, vp, vp, C.c_float, C.c_int32, vp, vp]),
     "imp_embed_atoms16": (C.c_int, [vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]),
     "imp_edge_messages_tc16": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp]),
+    "imp_edge_messages_tc16_plan_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "imp_edge_messages_tc16_plan": (C.c_int, [C.POINTER(Graph), vp, vp]),
+    "imp_edge_messages_tc16_planned": (C.c_int, [C.POINTER(Graph), vp, vp, C.c_int32, vp, vp, C.c_int32, vp, vp]),
     "imp_reduce_gated_update_tc16": (C.c_int, [C.POINTER(Graph), vp, vp, C.c_int32, vp, vp, C.c_float, C.c_int32, vp, vp, vp]),
     "imp_global_sum_pool": (C.c_int, [vp, vp, C.c_int32, vp, C.c_int32, vp, vp]),
     "imp_pool_head_visc": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ReadoutWeights),

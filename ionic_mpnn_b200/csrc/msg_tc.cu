@@ -358,6 +358,126 @@ __global__ void __launch_bounds__(CHUNK) grouped_msg16_pipe_kernel(const int32_t
   if (warp == 0) tc::tmem_dealloc<64>(tmem);
 }
 
+// Planned form (what the model's forward runs): the per-batch index work is done ONCE per batch instead of once per step and
+// per chunk -- imp_edge_messages_tc16_plan writes the chunk offsets and bucket-ordered copies of the source atoms and of
+// bond | multiplicity, so that the per-step kernel reads every index with independent coalesced loads (no perm -> src chain,
+// no warp shuffles: ncu showed 13 long-scoreboard + 12 mio-throttle stalls per issue on exactly those) two chunks ahead
+// of their use.  Same persistent double-buffered structure as grouped_msg16_pipe_kernel, bit-identical rows.
+struct PlanIdx {
+  int gsrc[4], gpos[4];
+  float mult;
+  const uint8_t* tb;
+};
+
+__global__ void plan_kernel(const int32_t* __restrict__ bucket_perm, const int32_t* __restrict__ col_src, const int32_t* __restrict__ edge_bm,
+                            int n_unique, int32_t* __restrict__ bsrc, int32_t* __restrict__ bbm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_unique) return;
+  const int e = __ldg(bucket_perm + i);
+  bsrc[i] = __ldg(col_src + e);
+  bbm[i] = __ldg(edge_bm + e);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(CHUNK) grouped_msg16_planned_kernel(const int32_t* __restrict__ bucket_ptr, const int32_t* __restrict__ chunk_ptr,
+                                                                      int n_buckets, int bond_vocab, const int32_t* __restrict__ bucket_perm,
+                                                                      const int32_t* __restrict__ bsrc, const int32_t* __restrict__ bbm,
+                                                                      const uint4* __restrict__ h16, const uint8_t* __restrict__ packed_cat,
+                                                                      const uint8_t* __restrict__ packed_an, uint4* __restrict__ msg16) {
+  __shared__ __align__(128) uint8_t su[2][A_BYTES + B_BYTES];
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_cptr[PIPE_MAX_BUCKETS + 1], s_bptr[PIPE_MAX_BUCKETS + 1];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int n_chunks = __ldg(chunk_ptr + n_buckets);
+  if ((int)blockIdx.x >= n_chunks) return;
+  for (int i = t; i <= n_buckets; i += CHUNK) s_cptr[i] = __ldg(chunk_ptr + i), s_bptr[i] = __ldg(bucket_ptr + i);
+  int cur_bucket = 0;
+  if (t == 0) {
+    tc::mbar_init(&bar[0], 1);
+    tc::mbar_init(&bar[1], 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 0) tc::tmem_alloc<64>(&tmem_slot);
+  const int g = lane >> 2, q = lane & 3;
+  const uint32_t idesc = tc::make_idesc(FMT, CHUNK, D);
+
+  auto load_idx = [&](int chunk) {  // independent coalesced loads; chunks are visited in increasing order
+    PlanIdx c;
+    while (s_cptr[cur_bucket + 1] <= chunk) ++cur_bucket;
+    const int b = cur_bucket;
+    const int slot0 = s_bptr[b] + (chunk - s_cptr[b]) * CHUNK;
+    const int n = min(CHUNK, s_bptr[b + 1] - slot0);
+    c.tb = b < bond_vocab ? packed_cat + (int64_t)b * B_BYTES : packed_an + (int64_t)(b - bond_vocab) * B_BYTES;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = warp * 32 + 8 * it + g;
+      const bool ok = r < n;
+      c.gsrc[it] = ok ? __ldg(bsrc + slot0 + r) : -1;
+      c.gpos[it] = ok ? __ldg(bucket_perm + slot0 + r) : -1;
+    }
+    c.mult = t < n ? (float)((uint32_t)__ldg(bbm + slot0 + t) >> 16) : 0.f;
+    return c;
+  };
+  auto gather = [&](const PlanIdx& c, int p) {
+    uint8_t *sA = su[p], *sB = su[p] + A_BYTES;
+    cp_async16(sB + t * 16, c.tb + t * 16, true);
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+      cp_async16(sA + q * 2048 + (warp * 32 + 8 * it + g) * 16, h16 + (int64_t)max(c.gsrc[it], 0) * 4 + q, c.gsrc[it] >= 0);
+    cp_async_commit();
+  };
+
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_slot;
+  const int G = gridDim.x;
+  PlanIdx i0 = load_idx(blockIdx.x), i1 = i0, i2 = i0;
+  if ((int)blockIdx.x + G < n_chunks) i1 = load_idx(blockIdx.x + G);
+  gather(i0, 0);
+  int i = 0;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += G, ++i) {
+    const int p = i & 1;
+    const bool has_next = chunk + G < n_chunks;
+    if (has_next) gather(i1, p ^ 1);                               // indices loaded an iteration ago
+    if (chunk + 2 * G < n_chunks) i2 = load_idx(chunk + 2 * G);    // in flight until the next iteration
+    if (has_next) cp_async_wait<1>(); else cp_async_wait<0>();
+    tc::fence_proxy_async_smem();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) {
+      tc::fence_after_thread_sync();
+      const uint32_t sa = tc::smem_u32(su[p]);
+      const uint64_t da = tc::make_smem_desc(sa, 2048, 128), db = tc::make_smem_desc(sa + A_BYTES, D * 16, 128);
+      if (tc::elect_one()) {
+        tc::mma_bf16(tmem + p * D, da, db, idesc, false);
+        tc::mma_bf16(tmem + p * D, da + (uint64_t)(4096 >> 4), db + (uint64_t)((2 * D * 16) >> 4), idesc, true);
+        tc::mma_commit(&bar[p]);
+      }
+      __syncwarp();
+    }
+    tc::mbar_wait(&bar[p], (uint32_t)((i >> 1) & 1));
+    tc::fence_after_thread_sync();
+    float v[32];
+    tc::tmem_ld32(tmem + p * D + ((uint32_t)(warp * 32) << 16), v);
+    uint32_t* stg = reinterpret_cast<uint32_t*>(su[p]);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) stg[t * STG16_LD + c] = tc::pack2<FMT>(i0.mult * v[2 * c], i0.mult * v[2 * c + 1]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const uint32_t* sr = stg + (warp * 32 + 8 * it + g) * STG16_LD + 4 * q;
+      if (i0.gpos[it] >= 0) msg16[(int64_t)i0.gpos[it] * 4 + q] = make_uint4(sr[0], sr[1], sr[2], sr[3]);
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    i0 = i1, i1 = i2;
+  }
+  if (warp == 0) tc::tmem_dealloc<64>(tmem);
+}
+
 // Embedding(atom) (train_viscosity.py:163,171) writing the fp32 state and its operand-format copy
 template <int FMT>
 __global__ void embed16_kernel(const float4* __restrict__ emb, const int* __restrict__ atom_id, int64_t total4, int atom_vocab,
@@ -493,6 +613,63 @@ extern "C" int imp_edge_messages_tc16(const imp_graph_t* g, const void* d_h16, i
     msgtc::grouped_msg16_kernel<tc::FMT_BF16><<<grid, msgtc::CHUNK, 0, st>>>(g->bucket_ptr, chunk_ptr, nb, g->bond_vocab, g->bucket_perm,
                                                                             g->col_src, g->edge_bm, reinterpret_cast<const uint4*>(d_h16), pc,
                                                                             pa, reinterpret_cast<uint4*>(d_msg16));
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+// plan = [chunk_ptr: 2 V_b + 1 ints, padded to 1024 ints][bsrc: Eu ints][bbm: Eu ints]
+extern "C" int64_t imp_edge_messages_tc16_plan_bytes(int32_t n_unique, int32_t bond_vocab) {
+  if (n_unique < 0 || bond_vocab <= 0 || 2 * bond_vocab > msgtc::PIPE_MAX_BUCKETS) return IMP_ERR_ARG;
+  return (int64_t)4 * (1024 + 2 * (int64_t)n_unique);
+}
+
+extern "C" int imp_edge_messages_tc16_plan(const imp_graph_t* g, void* d_plan, void* stream) {
+  IMP_REQUIRE(g && d_plan, IMP_ERR_ARG, "imp_edge_messages_tc16_plan: null pointer");
+  IMP_REQUIRE(g->bond_vocab > 0 && 2 * g->bond_vocab <= msgtc::PIPE_MAX_BUCKETS, IMP_ERR_ARG,
+              "imp_edge_messages_tc16_plan: bond vocabulary %d out of range (1..256)", g->bond_vocab);
+  if (g->n_unique == 0) return 0;
+  IMP_REQUIRE(g->bucket_ptr && g->bucket_perm && g->col_src && g->edge_bm, IMP_ERR_ARG,
+              "imp_edge_messages_tc16_plan: the bond-bucket permutation is required");
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* plan = reinterpret_cast<int32_t*>(d_plan);
+  msgtc::chunk_scan_kernel<<<1, 32, 0, st>>>(g->bucket_ptr, 2 * g->bond_vocab, plan);
+  IMP_LAUNCH_CHECK();
+  msgtc::plan_kernel<<<(unsigned)ceil_div(g->n_unique, 256), 256, 0, st>>>(g->bucket_perm, g->col_src, g->edge_bm, g->n_unique, plan + 1024,
+                                                                           plan + 1024 + g->n_unique);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int imp_edge_messages_tc16_planned(const imp_graph_t* g, const void* d_plan, const void* d_h16, int32_t d,
+                                              const void* d_packed_cat, const void* d_packed_an, int32_t flags, void* d_msg16,
+                                              void* stream) {
+  IMP_REQUIRE(g, IMP_ERR_ARG, "imp_edge_messages_tc16_planned: graph is null");
+  IMP_REQUIRE(d == msgtc::D, IMP_ERR_DIM, "imp_edge_messages_tc16_planned: atom_dim %d not supported by the tensor path (32)", d);
+  if (g->n_unique == 0) return 0;
+  IMP_REQUIRE(d_plan && d_h16 && d_msg16 && d_packed_cat && d_packed_an && g->bucket_ptr && g->bucket_perm, IMP_ERR_ARG,
+              "imp_edge_messages_tc16_planned: null pointer");
+  IMP_REQUIRE(g->bond_vocab > 0 && 2 * g->bond_vocab <= msgtc::PIPE_MAX_BUCKETS, IMP_ERR_ARG,
+              "imp_edge_messages_tc16_planned: bond vocabulary out of range");
+  IMP_REQUIRE(imp_device_is_sm100(), IMP_ERR_UNSUPPORTED, "imp_edge_messages_tc16_planned: tcgen05 needs an sm_100 device");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = 2 * g->bond_vocab;
+  const int32_t* plan = reinterpret_cast<const int32_t*>(d_plan);
+  int dev = 0, sms = 148;
+  IMP_CUDA(cudaGetDevice(&dev));
+  IMP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const unsigned grid_all = (unsigned)(ceil_div(g->n_unique, msgtc::CHUNK) + nb);
+  const unsigned grid = grid_all < (unsigned)(8 * sms) ? grid_all : (unsigned)(8 * sms);
+  const uint8_t *pc = reinterpret_cast<const uint8_t*>(d_packed_cat), *pa = reinterpret_cast<const uint8_t*>(d_packed_an);
+  if (flags & IMP_TC_FP16)
+    msgtc::grouped_msg16_planned_kernel<tc::FMT_F16><<<grid, msgtc::CHUNK, 0, st>>>(g->bucket_ptr, plan, nb, g->bond_vocab, g->bucket_perm,
+                                                                                   plan + 1024, plan + 1024 + g->n_unique,
+                                                                                   reinterpret_cast<const uint4*>(d_h16), pc, pa,
+                                                                                   reinterpret_cast<uint4*>(d_msg16));
+  else
+    msgtc::grouped_msg16_planned_kernel<tc::FMT_BF16><<<grid, msgtc::CHUNK, 0, st>>>(g->bucket_ptr, plan, nb, g->bond_vocab, g->bucket_perm,
+                                                                                    plan + 1024, plan + 1024 + g->n_unique,
+                                                                                    reinterpret_cast<const uint4*>(d_h16), pc, pa,
+                                                                                    reinterpret_cast<uint4*>(d_msg16));
   IMP_LAUNCH_CHECK();
   return 0;
 }

@@ -334,6 +334,11 @@ class MPNNModel(TrainMixin):
         folded = (not keep and not unfused_messages and self.precision != "fp32" and d == 32 and "bucket_perm" in batch.dev
                   and not getattr(self, "simt_messages", False))
         io16 = folded and not getattr(self, "fp32_messages", False)
+        planned = io16 and s["bond_vocab_size"] <= 256 and not (self.tc_flags() & _lib.TC_MSG_ONE_CHUNK_PER_CTA)
+        if planned:  # per-batch index plan of the grouped message kernel (chunk offsets, bucket-ordered src / bond|mult)
+            plan = self._buf("msg_plan", _lib.load().imp_edge_messages_tc16_plan_bytes(batch.n_unique, s["bond_vocab_size"]),
+                             torch.uint8)
+            _lib.call("imp_edge_messages_tc16_plan", C.byref(g), plan.data_ptr(), st)
         if io16:
             h16 = [self._buf("h16_0", N * d, torch.int16), self._buf("h16_1", N * d, torch.int16)]
             _lib.call("imp_embed_atoms16", self._ptr("atom_emb"), s["atom_vocab_size"], batch.dev["atom_id"].data_ptr(), N, d,
@@ -352,8 +357,12 @@ class MPNNModel(TrainMixin):
                 pg = (gbase + self._gru_pack_bytes * i, gbase + self._gru_pack_bytes * (S + i))
                 if io16:
                     msg16 = self._buf("msg16", batch.n_unique * d, torch.int16)
-                    _lib.call("imp_edge_messages_tc16", C.byref(g), h16[i % 2].data_ptr(), d, pm[0], pm[1], self.tc_flags(),
-                              msg16.data_ptr(), cws.data_ptr(), st)
+                    if planned:
+                        _lib.call("imp_edge_messages_tc16_planned", C.byref(g), plan.data_ptr(), h16[i % 2].data_ptr(), d, pm[0],
+                                  pm[1], self.tc_flags(), msg16.data_ptr(), st)
+                    else:
+                        _lib.call("imp_edge_messages_tc16", C.byref(g), h16[i % 2].data_ptr(), d, pm[0], pm[1], self.tc_flags(),
+                                  msg16.data_ptr(), cws.data_ptr(), st)
                     _lib.call("imp_reduce_gated_update_tc16", C.byref(g), h[i].data_ptr(), msg16.data_ptr(), d, pg[0], pg[1],
                               C.c_float(self.LN_EPS), self.tc_flags(), h[i + 1].data_ptr(), h16[(i + 1) % 2].data_ptr(), st)
                 else:
@@ -511,7 +520,7 @@ class MPNNModel(TrainMixin):
             return 2                  # fused forward, readout
         grouped = batch is None or "bucket_perm" in (batch.dev or {})
         if self.precision != "fp32" and self.spec["atom_dim"] == 32 and grouped:
-            return 1 + 3 * S + 1      # embed, (chunk scan, grouped message GEMM, Reduce + GatedUpdate) per step, pool + head
+            return 3 + 2 * S + 1      # embed, message plan (2), (grouped message GEMM, Reduce + GatedUpdate) per step, pool + head
         if self.spec["atom_dim"] == 32 and grouped:
             return 1 + 4 * S + 1      # embed, (chunk scan, grouped messages, segment sum, GatedUpdate) per step, pool + head
         return 1 + 2 * S + 1          # embed, (CSR-order messages, GatedUpdate) per step, pool + head

@@ -506,6 +506,14 @@ def test_pipelined_message_kernel_matches_one_chunk_per_cta(precision):
         assert torch.isfinite(msg16.float()).all(), "every CSR entry must have been written"
         out.append(msg16)
     assert torch.equal(out[0].view(torch.int16), out[1].view(torch.int16))
+    # the planned form (per-batch index plan, what the model's forward runs)
+    plan = torch.empty(_lib.load().imp_edge_messages_tc16_plan_bytes(batch.n_unique, 72), dtype=torch.uint8, device="cuda")
+    _lib.call("imp_edge_messages_tc16_plan", C.byref(g), plan.data_ptr(), st)
+    msg16 = torch.full((batch.n_unique, d), float("nan"), dtype=h16.dtype, device="cuda")
+    _lib.call("imp_edge_messages_tc16_planned", C.byref(g), plan.data_ptr(), h16.data_ptr(), d, base + mb, base + mb * (S + 1),
+              m.tc_flags(), msg16.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert torch.equal(out[0].view(torch.int16), msg16.view(torch.int16))
     msg32 = torch.empty(batch.n_unique, d, device="cuda")
     _lib.call("imp_edge_messages_tc", C.byref(g), h16.float().contiguous().data_ptr(), d, base + mb, base + mb * (S + 1), m.tc_flags(),
               msg32.data_ptr(), cws.data_ptr(), st)

@@ -179,7 +179,7 @@ def cpu_reference_run(kind, n_pairs, steps, warmup, skewed, wide=False):
         t0 = time.perf_counter()
         ref_model.predict(spec, params, x, dtype=torch.float32, batch_size=1024)
         big = n_pairs / (time.perf_counter() - t0)
-    return {"value": n_pairs / mean, "value_batch1024": big, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": n_pairs / mean, "value_batch1024": big, "unit": UNIT, "cores": cores, "kind": "port", "n_pairs": n_pairs,
             "sample": f"{n_pairs} synthetic pairs (seed 1002), padded as the reference pads, predict(batch_size=32), "
                       f"torch fp32 CPU port of models/layers.py, mean of {len(times)} runs after {warmup} warm-up",
             "ms_per_step": mean * 1e3}
@@ -196,7 +196,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "sample_pairs_per_step": args.cpu_sample_pairs},
+            "config": {"workload": name, "sample_pairs_per_step": r["n_pairs"]},
             "cpu_baseline": {k: r[k] for k in ("value", "value_batch1024", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) edge_messages_kernel(const int* __restric
 //   TRANSPOSED   msg[e][m] = mult * sum_l T[l][m] * x[src_e][l]                (its backward with respect to the atom states)
 // and rows go back through the tile so that stores are whole lines.  Exact fp32, deterministic.
 constexpr int GM_CHUNK = 128;
-constexpr int GM_LD = 33;
+constexpr int GM_LD = 36;  // padded row: 16-byte aligned, conflict-free float4 accesses of consecutive rows
 
 __global__ void gm_chunk_scan_kernel(const int* __restrict__ bucket_ptr, int n_buckets, int* __restrict__ chunk_ptr) {
   if (threadIdx.x == 0) {
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(GM_CHUNK) grouped_msg_f32_kernel(const int* __
                                                                    const float* __restrict__ tab_an, float* __restrict__ msg) {
   constexpr int D = 32;
   __shared__ __align__(16) float sT[D * D];
-  __shared__ float stg[GM_CHUNK * GM_LD];
+  __shared__ __align__(16) float stg[GM_CHUNK * GM_LD];
   const int chunk = blockIdx.x;
   if (chunk >= __ldg(chunk_ptr + n_buckets)) return;
   int lo = 0, hi = n_buckets - 1;
@@ -224,13 +224,15 @@ __global__ void __launch_bounds__(GM_CHUNK) grouped_msg_f32_kernel(const int* __
     const int rs = __shfl_sync(0xffffffffu, src, r), re = __shfl_sync(0xffffffffu, e, r);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (re >= 0) v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)rs * D) + q);
-    float* d = stg + (warp * 32 + r) * GM_LD + 4 * q;
-    d[0] = v.x, d[1] = v.y, d[2] = v.z, d[3] = v.w;
+    *reinterpret_cast<float4*>(stg + (warp * 32 + r) * GM_LD + 4 * q) = v;
   }
   __syncthreads();  // sT complete, and this warp's rows of stg
   float xin[D], out[D];
 #pragma unroll
-  for (int c = 0; c < D; ++c) xin[c] = stg[t * GM_LD + c];
+  for (int c = 0; c < D / 4; ++c) {
+    const float4 v = *reinterpret_cast<const float4*>(stg + t * GM_LD + 4 * c);
+    xin[4 * c] = v.x, xin[4 * c + 1] = v.y, xin[4 * c + 2] = v.z, xin[4 * c + 3] = v.w;
+  }
   if (!TRANSPOSED) {
 #pragma unroll
     for (int l = 0; l < D; ++l) {
@@ -258,14 +260,15 @@ __global__ void __launch_bounds__(GM_CHUNK) grouped_msg_f32_kernel(const int* __
     }
   }
 #pragma unroll
-  for (int c = 0; c < D; ++c) stg[t * GM_LD + c] = mult * out[c];
+  for (int c = 0; c < D / 4; ++c)
+    *reinterpret_cast<float4*>(stg + t * GM_LD + 4 * c) = make_float4(mult * out[4 * c], mult * out[4 * c + 1], mult * out[4 * c + 2], mult * out[4 * c + 3]);
   __syncwarp();
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = 4 * it + g;
     const int re = __shfl_sync(0xffffffffu, e, r);
-    const float* sr = stg + (warp * 32 + r) * GM_LD + 4 * q;
-    if (re >= 0) reinterpret_cast<float4*>(msg + (int64_t)re * D)[q] = make_float4(sr[0], sr[1], sr[2], sr[3]);
+    const float4 sr = *reinterpret_cast<const float4*>(stg + (warp * 32 + r) * GM_LD + 4 * q);
+    if (re >= 0) reinterpret_cast<float4*>(msg + (int64_t)re * D)[q] = sr;
   }
 }
 

@@ -362,11 +362,15 @@ __global__ void __launch_bounds__(GB_THREADS) gated_update_bwd_kernel(const floa
     s.bz[i] = w.bz[i], s.br[i] = w.br[i], s.bh[i] = w.bh[i], s.gamma[i] = w.gamma[i], s.beta[i] = w.beta[i];
   __syncthreads();
 
-  // weight-gradient accumulators: thread (k = tid % 64, jb = tid / 64) owns rows k, columns [8 jb, 8 jb + 8)
-  const int wk = tid % (2 * D), wjb = tid / (2 * D);
-  float aWz[8], aWr[8], aWh[8];
+  // weight-gradient accumulators: two atom groups (even / odd atoms of a tile) of 128 threads; in a group, thread
+  // (k2 = t % 32, jb = t / 32) owns rows 2 k2, 2 k2 + 1 and columns [8 jb, 8 jb + 8) of the three 64 x 32 gradients:
+  // 8 shared-memory reads per 48 FMA (the one-row form read 8 per 24).  The groups are combined once, at the end.
+  const int wag = tid >> 7, wk2 = tid & 31, wjb = (tid & 127) >> 5;
+  float aWz[2][8], aWr[2][8], aWh[2][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) aWz[i] = aWr[i] = aWh[i] = 0.f;
+  for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) aWz[kk][i] = aWr[kk][i] = aWh[kk][i] = 0.f;
   // vector-gradient accumulators: thread (j = tid % 32, q = tid / 32) sums atoms a = q, q+8, ...
   const int vj = tid % D, vq = tid / D;
   float abz = 0.f, abr = 0.f, abh = 0.f, agam = 0.f, abet = 0.f;
@@ -519,21 +523,25 @@ __global__ void __launch_bounds__(GB_THREADS) gated_update_bwd_kernel(const floa
     }
     __syncthreads();
     // ---- weight gradients of this tile: dW[k][j] += sum_a X[a][k] G[a][j]
-    for (int a = 0; a < rows; ++a) {
-      const float xk = s.X[a * GB_XS + wk];                                        // [h | agg][k]
-      const float xh = wk < D ? s.RH[a * GB_GS + wk] : xk;                         // [r*h | agg][k]
+    for (int a = wag; a < rows; a += 2) {
+      const float2 x2 = *reinterpret_cast<const float2*>(&s.X[a * GB_XS + 2 * wk2]);            // [h | agg][2 k2 ..]
+      const float2 h2 = wk2 < D / 2 ? *reinterpret_cast<const float2*>(&s.RH[a * GB_GS + 2 * wk2]) : x2;  // [r*h | agg]
+      const float xk[2] = {x2.x, x2.y}, xh[2] = {h2.x, h2.y};
       const float4* gz = reinterpret_cast<const float4*>(&s.Gz[a * GB_GS + 8 * wjb]);
       const float4* gr = reinterpret_cast<const float4*>(&s.Gr[a * GB_GS + 8 * wjb]);
       const float4* gh = reinterpret_cast<const float4*>(&s.Gh[a * GB_GS + 8 * wjb]);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const float4 z4 = gz[c], r4 = gr[c], h4 = gh[c];
-        aWz[4 * c] = fmaf(xk, z4.x, aWz[4 * c]), aWz[4 * c + 1] = fmaf(xk, z4.y, aWz[4 * c + 1]);
-        aWz[4 * c + 2] = fmaf(xk, z4.z, aWz[4 * c + 2]), aWz[4 * c + 3] = fmaf(xk, z4.w, aWz[4 * c + 3]);
-        aWr[4 * c] = fmaf(xk, r4.x, aWr[4 * c]), aWr[4 * c + 1] = fmaf(xk, r4.y, aWr[4 * c + 1]);
-        aWr[4 * c + 2] = fmaf(xk, r4.z, aWr[4 * c + 2]), aWr[4 * c + 3] = fmaf(xk, r4.w, aWr[4 * c + 3]);
-        aWh[4 * c] = fmaf(xh, h4.x, aWh[4 * c]), aWh[4 * c + 1] = fmaf(xh, h4.y, aWh[4 * c + 1]);
-        aWh[4 * c + 2] = fmaf(xh, h4.z, aWh[4 * c + 2]), aWh[4 * c + 3] = fmaf(xh, h4.w, aWh[4 * c + 3]);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          aWz[kk][4 * c] = fmaf(xk[kk], z4.x, aWz[kk][4 * c]), aWz[kk][4 * c + 1] = fmaf(xk[kk], z4.y, aWz[kk][4 * c + 1]);
+          aWz[kk][4 * c + 2] = fmaf(xk[kk], z4.z, aWz[kk][4 * c + 2]), aWz[kk][4 * c + 3] = fmaf(xk[kk], z4.w, aWz[kk][4 * c + 3]);
+          aWr[kk][4 * c] = fmaf(xk[kk], r4.x, aWr[kk][4 * c]), aWr[kk][4 * c + 1] = fmaf(xk[kk], r4.y, aWr[kk][4 * c + 1]);
+          aWr[kk][4 * c + 2] = fmaf(xk[kk], r4.z, aWr[kk][4 * c + 2]), aWr[kk][4 * c + 3] = fmaf(xk[kk], r4.w, aWr[kk][4 * c + 3]);
+          aWh[kk][4 * c] = fmaf(xh[kk], h4.x, aWh[kk][4 * c]), aWh[kk][4 * c + 1] = fmaf(xh[kk], h4.y, aWh[kk][4 * c + 1]);
+          aWh[kk][4 * c + 2] = fmaf(xh[kk], h4.z, aWh[kk][4 * c + 2]), aWh[kk][4 * c + 3] = fmaf(xh[kk], h4.w, aWh[kk][4 * c + 3]);
+        }
       }
     }
     for (int a = vq; a < rows; a += GB_THREADS / D) {
@@ -547,11 +555,31 @@ __global__ void __launch_bounds__(GB_THREADS) gated_update_bwd_kernel(const floa
   }
   // ---- per-CTA partials.  Vector gradients: combine the 8 atom phases through shared memory in phase order.
   float* o = partial + (int64_t)blockIdx.x * gru_grad_floats<D>();
+  {  // odd-atom group -> shared memory (the staged rows are dead), even-atom group adds it and writes: fixed order
+    float* xg = s.X;  // [128 threads][48]
+    if (wag == 1) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    o[wk * D + 8 * wjb + i] = aWz[i];
-    o[(2 * D * D + D) + wk * D + 8 * wjb + i] = aWr[i];
-    o[2 * (2 * D * D + D) + wk * D + 8 * wjb + i] = aWh[i];
+      for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xg[(tid & 127) * 48 + kk * 8 + i] = aWz[kk][i];
+          xg[(tid & 127) * 48 + 16 + kk * 8 + i] = aWr[kk][i];
+          xg[(tid & 127) * 48 + 32 + kk * 8 + i] = aWh[kk][i];
+        }
+    }
+    __syncthreads();
+    if (wag == 0) {
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = 2 * wk2 + kk;
+          o[k * D + 8 * wjb + i] = aWz[kk][i] + xg[tid * 48 + kk * 8 + i];
+          o[(2 * D * D + D) + k * D + 8 * wjb + i] = aWr[kk][i] + xg[tid * 48 + 16 + kk * 8 + i];
+          o[2 * (2 * D * D + D) + k * D + 8 * wjb + i] = aWh[kk][i] + xg[tid * 48 + 32 + kk * 8 + i];
+        }
+    }
+    __syncthreads();
   }
   constexpr int NQ = GB_THREADS / D;
   float* red = s.X;  // reuse: [5][NQ][32]

@@ -885,15 +885,17 @@ __device__ __forceinline__ float k5b_row_sum(float v) {
 }
 
 __global__ void __launch_bounds__(K5B_THREADS, 2) gated_update32_kernel(const float* __restrict__ h, const float* __restrict__ agg,
-                                                                        int n_atoms, int n_cat, int tiles_cat, imp_gru_weights_t wc,
+                                                                        int n_atoms, int n_cat, int n_cta_cat, imp_gru_weights_t wc,
                                                                         imp_gru_weights_t wa, float eps, float* __restrict__ h_out) {
   constexpr int D = 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   K5BSmem& s = *reinterpret_cast<K5BSmem*>(smem_raw);
-  const bool is_cat = (int)blockIdx.x < tiles_cat;
+  // persistent: CTAs [0, n_cta_cat) walk the cation tiles, the rest the anion tiles; the tower's weights are staged once
+  const bool is_cat = (int)blockIdx.x < n_cta_cat;
   const imp_gru_weights_t& w = is_cat ? wc : wa;
-  const int a0 = is_cat ? blockIdx.x * K5_TILE : n_cat + (blockIdx.x - tiles_cat) * K5_TILE;
-  const int rows = min(K5_TILE, (is_cat ? n_cat : n_atoms) - a0);
+  const int base = is_cat ? 0 : n_cat, a_end = is_cat ? n_cat : n_atoms;
+  const int n_tiles = (a_end - base + K5_TILE - 1) / K5_TILE;
+  const int cta = is_cat ? blockIdx.x : blockIdx.x - n_cta_cat, n_cta = is_cat ? n_cta_cat : gridDim.x - n_cta_cat;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < 2 * D * D / 4; i += K5B_THREADS) {
     reinterpret_cast<float4*>(s.Wz)[i] = __ldg(reinterpret_cast<const float4*>(w.Wz) + i);
@@ -903,6 +905,11 @@ __global__ void __launch_bounds__(K5B_THREADS, 2) gated_update32_kernel(const fl
   for (int i = tid; i < D; i += K5B_THREADS)
     s.bz[i] = w.bz[i], s.br[i] = w.br[i], s.bh[i] = w.bh[i], s.gamma[i] = w.gamma[i], s.beta[i] = w.beta[i];
   const int qd = lane >> 3, cg = lane & 7, c0 = 4 * cg;
+  __syncthreads();  // weights
+  // every row a warp touches below is one of its own 16: the warps of a CTA walk the tiles independently (__syncwarp only)
+  for (int tile = cta; tile < n_tiles; tile += n_cta) {
+  const int a0 = base + tile * K5_TILE;
+  const int rows = min(K5_TILE, a_end - a0);
 #pragma unroll
   for (int it = 0; it < 4; ++it) {  // the warp stages its own 16 rows, 8 lanes per 128-byte row
     const int r = 16 * warp + 4 * it + qd;
@@ -914,7 +921,7 @@ __global__ void __launch_bounds__(K5B_THREADS, 2) gated_update32_kernel(const fl
     *reinterpret_cast<float4*>(&s.X[r * K5B_XS + c0]) = hv;
     *reinterpret_cast<float4*>(&s.X[r * K5B_XS + D + c0]) = av;
   }
-  __syncthreads();  // weights + rows
+  __syncwarp();
   const int ar0 = 16 * warp + qd;
   const float* Xb = &s.X[ar0 * K5B_XS];
   float* RHb = &s.RH[ar0 * K5B_GS];
@@ -978,6 +985,8 @@ __global__ void __launch_bounds__(K5B_THREADS, 2) gated_update32_kernel(const fl
           make_float4(n[0] * inv * s.gamma[c0] + s.beta[c0] + hx[i][0], n[1] * inv * s.gamma[c0 + 1] + s.beta[c0 + 1] + hx[i][1],
                       n[2] * inv * s.gamma[c0 + 2] + s.beta[c0 + 2] + hx[i][2], n[3] * inv * s.gamma[c0 + 3] + s.beta[c0 + 3] + hx[i][3]);
   }
+  __syncwarp();  // the warp's rows may be overwritten by its next tile
+  }
 }
 
 template <int D>
@@ -986,7 +995,16 @@ static int launch_k5(const float* h, const float* agg, int n_atoms, int n_cat, c
   const int tiles_cat = (int)ceil_div(n_cat, K5_TILE), tiles_an = (int)ceil_div(n_atoms - n_cat, K5_TILE);
   if (D == 32) {
     IMP_CUDA(cudaFuncSetAttribute(gated_update32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K5BSmem)));
-    gated_update32_kernel<<<tiles_cat + tiles_an, K5B_THREADS, sizeof(K5BSmem), st>>>(h, agg, n_atoms, n_cat, tiles_cat, *wc, *wa, eps, out);
+    int dev = 0, sms = 148;
+    IMP_CUDA(cudaGetDevice(&dev));
+    IMP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int tiles = tiles_cat + tiles_an;
+    const int grid = tiles < 2 * sms ? tiles : 2 * sms;  // two CTAs per SM
+    int n_cta_cat = tiles > 0 ? (int)((int64_t)grid * tiles_cat / tiles) : 0;
+    if (tiles_cat > 0 && n_cta_cat < 1) n_cta_cat = 1;
+    if (tiles_an > 0 && n_cta_cat > grid - 1) n_cta_cat = grid - 1;
+    if (tiles_an == 0) n_cta_cat = grid;
+    gated_update32_kernel<<<grid, K5B_THREADS, sizeof(K5BSmem), st>>>(h, agg, n_atoms, n_cat, n_cta_cat, *wc, *wa, eps, out);
     IMP_LAUNCH_CHECK();
     return 0;
   }

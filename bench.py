@@ -467,6 +467,7 @@ def run_b200(args):
             model.predict_stream(chunks, out_host)
         ev1.record()
         torch.cuda.synchronize()
+        model.check_status()
         barrier()
         ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=f"cuda:{local}")
         if world > 1:

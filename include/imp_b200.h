@@ -347,9 +347,12 @@ int imp_wide_candidate(const imp_graph_t* g, int32_t d, const void* d_packed_cat
 int imp_wide_gated_update(const imp_graph_t* g, int32_t d, const void* d_packed_cat, const void* d_packed_an, float eps,
                           int32_t flags, void* d_workspace, void* stream);
 int imp_wide_pool(const imp_graph_t* g, int32_t d, const void* d_workspace, float* d_pooled, void* stream);
-/* Debug aid (tools/wide_timeline.py): when set to a device buffer of 16 x 8 int64, CTA 0 of imp_wide_gated_update records
- * clock64 at its phase boundaries for its first 16 tiles; NULL (default) disables it. */
-void imp_debug_wide_timeline(void* d_buf);
+
+/* keras.layers.Dense on [rows, in_dim] fp32 device rows: y = act(x . kernel + bias); kernel (in_dim, out_dim) row-major,
+ * activation 0 = linear, 1 = relu (train_viscosity.py:189,197-198,204).  Layer-level form for code written against
+ * models/layers.py-style graphs; the model path uses the fused imp_pool_head_* / imp_readout_* kernels. */
+int imp_dense(const float* d_x, int64_t rows, int32_t in_dim, int32_t out_dim, const float* d_kernel, const float* d_bias,
+              int32_t activation, float* d_y, void* stream);
 
 /* K6 without the pooling stage: Dense(fp, relu), Dense(mix, relu) per tower, AddTwoTensors, head
  * (train_viscosity.py:189-214 / train_melting_point.py:173-198) on molecule sums [2P, d] (cations first). */
@@ -407,6 +410,38 @@ int imp_embed_bwd(const int32_t* d_atom_id, const float* d_dh0, int32_t n_atoms,
 int imp_clip_adam(float* d_param, const float* d_grad, float* d_m, float* d_v, const int64_t* d_var_off,
                   const float* d_var_l2, int32_t n_vars, float* d_norms2, float clipnorm, float lr, float beta1, float beta2,
                   float eps, int32_t step, void* stream);
+/* The same step with the reference's exact Embedding semantics and a distributed mean [Keras semantics, TF / Keras 2.12;
+ * oracle/ref_model.py:adam_step]: the optimizer clips an IndexedSlices gradient BEFORE de-duplicating it, so the clip norm
+ * of the two Embedding variables (train_viscosity.py:163-164) is taken over the per-occurrence rows.  The n_occ variables
+ * d_occ_var[i] (device int32) use d_occ_norm2[i] (device; from imp_sumsq / imp_bond_occurrence_norm2) as their squared clip
+ * norm.  d_pair_count (device scalar, optional): the gradients and occurrence norms were computed for the SUM over pairs
+ * and are turned into the mean by 1 / *d_pair_count -- the count rides in the same all-reduce as the gradient bucket.
+ * d_norms2 holds 2 * n_vars floats (squared norms, then the l2 loss terms).  d_loss (optional, needs d_sse = sum of squared
+ * errors): receives this step's loss = sse / count (or sse * inv_batch when d_pair_count is NULL) + the l2 terms, computed
+ * with the weights BEFORE the update, as Keras reports it (train_viscosity.py:189,227-230). */
+int imp_clip_adam_sparse(float* d_param, const float* d_grad, float* d_m, float* d_v, const int64_t* d_var_off,
+                         const float* d_var_l2, int32_t n_vars, float* d_norms2, float clipnorm, float lr, float beta1,
+                         float beta2, float eps, int32_t step, int32_t n_occ, const int32_t* d_occ_var,
+                         const float* d_occ_norm2, const float* d_pair_count, const float* d_sse, float inv_batch,
+                         float* d_loss, void* stream);
+/* Keras `evaluate` loss on device predictions: mean((pred - y)^2) + sum_v var_l2[v] * |param_v|^2, fixed summation order.
+ * d_scratch: 1 + n_vars floats. */
+int imp_eval_loss(const float* d_pred, const float* d_y, int64_t n, const float* d_param, const int64_t* d_var_off,
+                  const float* d_var_l2, int32_t n_vars, float* d_scratch, float* d_loss, void* stream);
+/* Deterministic sum of squares of n floats (two-stage, fixed order); workspace >= 1024 floats.  With x = dL/dh0 [N, d]
+ * (output of the backward pass before imp_embed_bwd) this is the per-occurrence squared norm of the atom Embedding. */
+int imp_sumsq(const float* d_x, int64_t n, float* d_out, float* d_workspace, void* stream);
+/* Per-occurrence squared gradient norm of the bond Embedding (csrc/occ_norm.cu): sum over CSR entries e of
+ * mult_e * |g_e|^2, g_e[k] = sum_s dagg_s[dst_e]^T W_{s,k} h_s[src_e] (models/layers.py:108-112 under autodiff).
+ * d_h_steps / d_dagg_steps: HOST arrays of `steps` device pointers ([N, d] fp32: the state entering step s, the gradient of
+ * its aggregated messages); d_packed_*: `steps` images of imp_occ_pack per tower; n_cat_unique = row_ptr[n_cat_atoms];
+ * workspace: imp_bond_occurrence_norm2_workspace_floats(n_unique) floats.  atom_dim 32, bond_dim 8 (tcgen05). */
+int64_t imp_occ_pack_bytes(int32_t d, int32_t bond_dim);
+int imp_occ_pack(const float* d_bond_transform, int32_t d, int32_t bond_dim, void* d_packed, void* stream);
+int64_t imp_bond_occurrence_norm2_workspace_floats(int32_t n_unique);
+int imp_bond_occurrence_norm2(const imp_graph_t* g, int32_t n_cat_unique, const int32_t* d_entry_dst, int32_t steps,
+                              const float* const* d_h_steps, const float* const* d_dagg_steps, int32_t d, int32_t bond_dim,
+                              const void* d_packed_cat, const void* d_packed_an, float* d_out, float* d_workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Diagnostics: one-CTA tcgen05 product D[128,N] = A[128,K] * B[N,K]^T (kind 0 = bf16, 1 = tf32 operands from

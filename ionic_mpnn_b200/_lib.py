@@ -120,7 +120,6 @@ SIGNATURES = {
     "imp_wide_gates": (C.c_int, [C.POINTER(Graph), C.c_int32, vp, vp, C.c_int32, vp, vp]),
     "imp_wide_candidate": (C.c_int, [C.POINTER(Graph), C.c_int32, vp, vp, C.c_float, C.c_int32, vp, vp]),
     "imp_wide_gated_update": (C.c_int, [C.POINTER(Graph), C.c_int32, vp, vp, C.c_float, C.c_int32, vp, vp]),
-    "imp_debug_wide_timeline": (None, [vp]),
     "imp_wide_pool": (C.c_int, [C.POINTER(Graph), C.c_int32, vp, vp, vp]),
     "imp_readout_visc": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ReadoutWeights),
                                    C.POINTER(ReadoutWeights), vp, vp, vp, vp, vp, vp]),
@@ -142,6 +141,16 @@ SIGNATURES = {
     "imp_embed_bwd": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]),
     "imp_clip_adam": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int32, vp, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_int32, vp]),
+    "imp_clip_adam_sparse": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int32, vp, C.c_float, C.c_float, C.c_float, C.c_float,
+                                       C.c_float, C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_float, vp, vp]),
+    "imp_eval_loss": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, C.c_int32, vp, vp, vp]),
+    "imp_sumsq": (C.c_int, [vp, C.c_int64, vp, vp, vp]),
+    "imp_occ_pack_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "imp_occ_pack": (C.c_int, [vp, C.c_int32, C.c_int32, vp, vp]),
+    "imp_bond_occurrence_norm2_workspace_floats": (C.c_int64, [C.c_int32]),
+    "imp_bond_occurrence_norm2": (C.c_int, [C.POINTER(Graph), C.c_int32, vp, C.c_int32, C.POINTER(vp), C.POINTER(vp), C.c_int32,
+                                            C.c_int32, vp, vp, vp, vp, vp]),
+    "imp_dense": (C.c_int, [vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, vp]),
     "imp_tc_selftest": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
 }
 

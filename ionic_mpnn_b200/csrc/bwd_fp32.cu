@@ -766,18 +766,63 @@ __global__ void __launch_bounds__(EB_WARPS * 32) embed_bwd_kernel(const int* __r
 }
 
 // ================================================================================================ optimizer
-// norms2[v] = sum of squares of (grad + l2[v] * 2 * param) over variable v (one CTA per variable, fixed order tree).
+// norms2[v] = sum of squares of (gs * grad + l2[v] * 2 * param) over variable v (one CTA per variable, fixed order tree);
+// gs = 1 / *pair_count when the bucket holds sum-gradients (imp_clip_adam_sparse), else 1.
+// regs (optional, [n_vars]): l2[v] * sum(param^2), the variable's term of the regularised loss.
 __global__ void __launch_bounds__(256) var_sumsq_kernel(const float* __restrict__ grad, const float* __restrict__ param,
                                                         const int64_t* __restrict__ var_off, const float* __restrict__ var_l2,
-                                                        float* __restrict__ norms2) {
-  __shared__ float red[256];
+                                                        float* __restrict__ norms2, const float* __restrict__ pair_count,
+                                                        float* __restrict__ regs) {
+  __shared__ float red[256], red2[256];
   const int v = blockIdx.x;
   const int64_t o0 = var_off[v], o1 = var_off[v + 1];
   const float l2 = 2.0f * var_l2[v];
-  float s = 0.f;
+  const float gs = pair_count ? 1.0f / pair_count[0] : 1.0f;
+  float s = 0.f, w2 = 0.f;
   for (int64_t i = o0 + threadIdx.x; i < o1; i += 256) {
-    const float gq = fmaf(l2, param[i], grad[i]);
+    const float w = param[i];
+    const float gq = fmaf(l2, w, grad ? grad[i] * gs : 0.f);
     s = fmaf(gq, gq, s);
+    w2 = fmaf(w, w, w2);
+  }
+  red[threadIdx.x] = s, red2[threadIdx.x] = w2;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w], red2[threadIdx.x] += red2[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (norms2) norms2[v] = red[0];
+    if (regs) regs[v] = var_l2[v] * red2[0];
+  }
+}
+
+// Variables listed in occ_var take the per-occurrence squared norm (csrc/occ_norm.cu) instead of the dense one.
+__global__ void occ_norm_override_kernel(float* __restrict__ norms2, const int32_t* __restrict__ occ_var,
+                                         const float* __restrict__ occ_norm2, int n_occ, const float* __restrict__ pair_count) {
+  const int i = threadIdx.x;
+  const float gs = pair_count ? 1.0f / pair_count[0] : 1.0f;
+  if (i < n_occ) norms2[occ_var[i]] = occ_norm2[i] * gs * gs;
+}
+
+// loss = sse * (1 / count) + sum_v regs[v] (serial, fixed order: n_vars is ~100)
+__global__ void loss_kernel(const float* __restrict__ sse, const float* __restrict__ pair_count, float inv_batch,
+                            const float* __restrict__ regs, int n_vars, float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float r = 0.f;
+    for (int v = 0; v < n_vars; ++v) r += regs[v];
+    loss[0] = sse[0] * (pair_count ? 1.0f / pair_count[0] : inv_batch) + r;
+  }
+}
+
+// sum of squared errors of n predictions (one CTA, fixed order) -- evaluate()
+__global__ void __launch_bounds__(256) sse_kernel(const float* __restrict__ pred, const float* __restrict__ y, int64_t n,
+                                                  float* __restrict__ out) {
+  __shared__ float red[256];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 256) {
+    const float dlt = pred[i] - y[i];
+    s = fmaf(dlt, dlt, s);
   }
   red[threadIdx.x] = s;
   __syncthreads();
@@ -785,7 +830,7 @@ __global__ void __launch_bounds__(256) var_sumsq_kernel(const float* __restrict_
     if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
     __syncthreads();
   }
-  if (threadIdx.x == 0) norms2[v] = red[0];
+  if (threadIdx.x == 0) out[0] = red[0];
 }
 
 // [Keras semantics] per-variable clip_by_norm, then Adam: m += (g-m)(1-b1); v += (g^2-v)(1-b2);
@@ -794,15 +839,16 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ para
                                                         float* __restrict__ m, float* __restrict__ vv,
                                                         const int64_t* __restrict__ var_off, const float* __restrict__ var_l2,
                                                         const float* __restrict__ norms2, int n_vars, float clipnorm, float alpha,
-                                                        float beta1, float beta2, float eps) {
+                                                        float beta1, float beta2, float eps, const float* __restrict__ pair_count) {
   const int v = blockIdx.x;
   const int64_t o0 = var_off[v], o1 = var_off[v + 1];
   const float l2 = 2.0f * var_l2[v];
+  const float gs = pair_count ? 1.0f / pair_count[0] : 1.0f;
   const float nrm = sqrtf(norms2[v]);
   const float scale = clipnorm > 0.f ? clipnorm / fmaxf(nrm, clipnorm) : 1.0f;
   for (int64_t i = o0 + (int64_t)blockIdx.y * 256 + threadIdx.x; i < o1; i += (int64_t)gridDim.y * 256) {
     const float w = param[i];
-    const float g = fmaf(l2, w, grad[i]) * scale;
+    const float g = fmaf(l2, w, grad[i] * gs) * scale;
     const float mi = m[i] + (g - m[i]) * (1.0f - beta1);
     const float vi = vv[i] + (g * g - vv[i]) * (1.0f - beta2);
     m[i] = mi, vv[i] = vi;
@@ -959,11 +1005,57 @@ extern "C" int imp_clip_adam(float* d_param, const float* d_grad, float* d_m, fl
   IMP_REQUIRE(n_vars >= 0 && step >= 1, IMP_ERR_ARG, "imp_clip_adam: bad arguments");
   if (n_vars == 0) return 0;
   IMP_REQUIRE(d_param && d_grad && d_m && d_v && d_var_off && d_var_l2 && d_norms2, IMP_ERR_ARG, "imp_clip_adam: null pointer");
-  var_sumsq_kernel<<<n_vars, 256, 0, (cudaStream_t)stream>>>(d_grad, d_param, d_var_off, d_var_l2, d_norms2);
+  var_sumsq_kernel<<<n_vars, 256, 0, (cudaStream_t)stream>>>(d_grad, d_param, d_var_off, d_var_l2, d_norms2, nullptr, nullptr);
   IMP_LAUNCH_CHECK();
   const float alpha = (float)((double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step)));
   clip_adam_kernel<<<dim3(n_vars, 8), 256, 0, (cudaStream_t)stream>>>(d_param, d_grad, d_m, d_v, d_var_off, d_var_l2, d_norms2,
-                                                                      n_vars, clipnorm, alpha, beta1, beta2, eps);
+                                                                      n_vars, clipnorm, alpha, beta1, beta2, eps, nullptr);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int imp_clip_adam_sparse(float* d_param, const float* d_grad, float* d_m, float* d_v, const int64_t* d_var_off,
+                                    const float* d_var_l2, int32_t n_vars, float* d_norms2, float clipnorm, float lr, float beta1,
+                                    float beta2, float eps, int32_t step, int32_t n_occ, const int32_t* d_occ_var,
+                                    const float* d_occ_norm2, const float* d_pair_count, const float* d_sse, float inv_batch,
+                                    float* d_loss, void* stream) {
+  IMP_REQUIRE(n_vars >= 0 && step >= 1 && n_occ >= 0 && n_occ <= 32, IMP_ERR_ARG, "imp_clip_adam_sparse: bad arguments");
+  if (n_vars == 0) return 0;
+  IMP_REQUIRE(d_param && d_grad && d_m && d_v && d_var_off && d_var_l2 && d_norms2 && (n_occ == 0 || (d_occ_var && d_occ_norm2)),
+              IMP_ERR_ARG, "imp_clip_adam_sparse: null pointer");
+  IMP_REQUIRE(!d_loss || d_sse, IMP_ERR_ARG, "imp_clip_adam_sparse: d_loss needs d_sse");
+  cudaStream_t st = (cudaStream_t)stream;
+  // d_norms2 holds 2 * n_vars floats: squared norms, then the l2 loss terms of the variables
+  var_sumsq_kernel<<<n_vars, 256, 0, st>>>(d_grad, d_param, d_var_off, d_var_l2, d_norms2, d_pair_count, d_norms2 + n_vars);
+  IMP_LAUNCH_CHECK();
+  if (n_occ > 0) {
+    occ_norm_override_kernel<<<1, 32, 0, st>>>(d_norms2, d_occ_var, d_occ_norm2, n_occ, d_pair_count);
+    IMP_LAUNCH_CHECK();
+  }
+  if (d_loss) {  // the loss of THIS step's forward pass (weights before the update), like Keras reports it
+    loss_kernel<<<1, 32, 0, st>>>(d_sse, d_pair_count, inv_batch, d_norms2 + n_vars, n_vars, d_loss);
+    IMP_LAUNCH_CHECK();
+  }
+  const float alpha = (float)((double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step)));
+  clip_adam_kernel<<<dim3(n_vars, 8), 256, 0, st>>>(d_param, d_grad, d_m, d_v, d_var_off, d_var_l2, d_norms2, n_vars, clipnorm, alpha,
+                                                    beta1, beta2, eps, d_pair_count);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int imp_eval_loss(const float* d_pred, const float* d_y, int64_t n, const float* d_param, const int64_t* d_var_off,
+                             const float* d_var_l2, int32_t n_vars, float* d_scratch, float* d_loss, void* stream) {
+  IMP_REQUIRE(n > 0 && n_vars >= 0 && d_pred && d_y && d_scratch && d_loss && (n_vars == 0 || (d_param && d_var_off && d_var_l2)),
+              IMP_ERR_ARG, "imp_eval_loss: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  // scratch: [0] sse, [1 .. 1 + n_vars) l2 terms
+  sse_kernel<<<1, 256, 0, st>>>(d_pred, d_y, n, d_scratch);
+  IMP_LAUNCH_CHECK();
+  if (n_vars > 0) {
+    var_sumsq_kernel<<<n_vars, 256, 0, st>>>(nullptr, d_param, d_var_off, d_var_l2, nullptr, nullptr, d_scratch + 1);
+    IMP_LAUNCH_CHECK();
+  }
+  loss_kernel<<<1, 32, 0, st>>>(d_scratch, nullptr, 1.0f / (float)n, d_scratch + 1, n_vars, d_loss);
   IMP_LAUNCH_CHECK();
   return 0;
 }

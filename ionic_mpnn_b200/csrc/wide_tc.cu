@@ -927,6 +927,9 @@ extern "C" int imp_wide_candidate(const imp_graph_t* g, int32_t d, const void* d
 }
 
 static long long* g_wide_timeline = nullptr;
+// Debug aid, NOT part of the public ABI (include/imp_b200.h does not declare it; tools/wide_timeline.py binds it by name):
+// when set to a device buffer of 16 x 8 int64, CTA 0 of imp_wide_gated_update records clock64 at its phase boundaries for
+// its first 16 tiles; NULL (default) disables it.
 extern "C" void imp_debug_wide_timeline(void* d_buf) { g_wide_timeline = reinterpret_cast<long long*>(d_buf); }
 
 extern "C" int imp_wide_gated_update(const imp_graph_t* g, int32_t d, const void* d_packed_cat, const void* d_packed_an, float eps,

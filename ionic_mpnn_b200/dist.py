@@ -46,3 +46,13 @@ def allreduce_sum_(flat, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return flat
+
+
+def mean_from_summed_bucket(bucket, n_params):
+    """What imp_clip_adam_sparse does with a bucket reduced in "sum" mode (train.TrainMixin.train_step): the bucket holds
+    sum-gradients [0, n_params) and the tail [sse, pair count, occurrence norm^2 x 2]; after the all-reduce the mean
+    gradient is bucket / count, the mean squared error sse / count, and the occurrence norms scale with 1 / count^2.
+    Host-side restatement used by the CPU tests of the N > 1 path."""
+    count = float(bucket[n_params + 1])
+    return bucket[:n_params] / count, float(bucket[n_params]) / count, [float(bucket[n_params + 2]) / count ** 2,
+                                                                         float(bucket[n_params + 3]) / count ** 2]

@@ -64,6 +64,17 @@ class FlatIons:
                 bond[edge_ptr[i]:edge_ptr[i + 1]] = ion["bond_ids"][:ne]
         return FlatIons(atom_ptr, atom_ids, edge_ptr, src, dst, bond)
 
+    def to_ion_dicts(self, lo=0, hi=None):
+        """Inverse of from_ion_dicts for ions [lo, hi): the record schema of src/dataset.py:15-20."""
+        hi = self.n_ions if hi is None else hi
+        out = []
+        for i in range(lo, hi):
+            a0, a1, e0, e1 = self.atom_ptr[i], self.atom_ptr[i + 1], self.edge_ptr[i], self.edge_ptr[i + 1]
+            out.append({"atom_ids": [int(v) for v in self.atom_ids[a0:a1]], "bond_ids": [int(v) for v in self.bond_ids[e0:e1]],
+                        "edge_indices": [(int(a), int(b)) for a, b in zip(self.edge_src[e0:e1], self.edge_dst[e0:e1])],
+                        "num_atoms": int(a1 - a0)})
+        return out
+
     @staticmethod
     def from_padded(atom, bond, conn):
         """One tower of the reference's padded dict: atom (B,N), bond (B,E), conn (B,E,2); ids already
@@ -103,6 +114,7 @@ class PackedGraphBatch:
         self.dev_T = None
         self.dev_y = None
         self.device = None
+        self.symmetric = None  # True / False / None (unknown: checked before the first training use)
 
     # -- device side ------------------------------------------------------------------------
     def to(self, device, non_blocking=False, pinned=False):
@@ -272,7 +284,11 @@ def pack_flat(cation: FlatIons, anion: FlatIons, bond_vocab_size, max_edges=None
     for k in ("col_src", "edge_bm", "bucket_perm"):
         arrays[k] = arrays[k][: g.n_unique]
     counts = (g.n_pairs, g.n_atoms, g.n_cat_atoms, g.n_unique, g.n_edges, g.bond_vocab)
-    return PackedGraphBatch(arrays, counts, temperature, target)
+    b = PackedGraphBatch(arrays, counts, temperature, target)
+    # reverse-doubled and untruncated: every live entry has its mirror (train_viscosity.py:87-91).  Anything else is checked
+    # on the host when the batch is first used for training (train.entries_are_symmetric).
+    b.symmetric = True if (double_edges and max_edges is None) else None
+    return b
 
 
 def pack_records(records, bond_vocab_size, max_edges=None, label=None):

@@ -261,6 +261,50 @@ class GlobalSumPool(Layer):
         return out
 
 
+class Dense(Layer):
+    """keras.layers.Dense(units, activation) as the reference uses it (train_viscosity.py:189 ``Dense(fp_size, relu)``,
+    :197-198 ``Dense(mixing_size, relu)``, :204 ``Dense(3)``; train_melting_point.py:173,191-198): weights ``kernel
+    (in, units)`` / ``bias (units)``, ``y = act(x . kernel + bias)`` (imp_dense).  ``kernel_regularizer`` is accepted
+    and recorded (it only matters for the training loss, which model.train_step computes)."""
+
+    def __init__(self, units, activation=None, kernel_regularizer=None, input_dim=None, **kw):
+        super().__init__(**kw)
+        if activation not in (None, "linear", "relu"):
+            raise ValueError("Dense: the reference only uses relu and linear activations")
+        self.units, self.activation, self.kernel_regularizer = units, activation, kernel_regularizer
+        self.in_dim = input_dim
+        if input_dim is not None:  # weights can be set before the first call
+            self.build(None)
+            self.built = True
+
+    def build(self, input_shape=None):
+        if self.in_dim is None:
+            raise ValueError("Dense.build needs the input width (call the layer on a tensor)")
+        self.add_weight((self.in_dim, self.units), "glorot_uniform", "kernel")
+        self.add_weight((self.units,), "zeros", "bias")
+
+    def __call__(self, x, **kw):
+        if not self.built:
+            self.in_dim = int(x.shape[-1])
+            self.build(None)
+            self.built = True
+        return self.call(x)
+
+    def call(self, x):
+        torch = _torch()
+        x = x.contiguous()
+        rows = x.numel() // self.in_dim
+        y = torch.empty(*x.shape[:-1], self.units, dtype=torch.float32, device=x.device)
+        _lib.call("imp_dense", x.data_ptr(), rows, self.in_dim, self.units, self.weights["kernel"].data_ptr(),
+                  self.weights["bias"].data_ptr(), 1 if self.activation == "relu" else 0, y.data_ptr(), _stream())
+        return y
+
+    def get_config(self):
+        cfg = super().get_config()
+        cfg.update({"units": self.units, "activation": self.activation})
+        return cfg
+
+
 # ---- [P,1]-sized glue of the viscosity head (models/layers.py:10-49) -------------------------------
 class ComputeLogEta(Layer):
     def call(self, inputs):

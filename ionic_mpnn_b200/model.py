@@ -540,11 +540,27 @@ class MPNNModel(TrainMixin):
         import torch
 
         batch = self.pack(x)
+        if "status" in self._ws:
+            self._ws["status"].zero_()
         out = self.forward_packed(batch)
         torch.cuda.current_stream().synchronize()
+        self.check_status()
         return out.cpu().numpy().reshape(-1, 1)
 
     __call__ = predict
+
+    def check_status(self):
+        """Reads (and clears) the fused kernel's status word: non-zero means a molecule did not fit a 128-row tile, i.e. the
+        batch's ``max_mol_atoms`` was wrong and the predictions of that launch are invalid.  ``predict`` calls it after its
+        synchronisation; callers of the enqueue-only entry points (``forward_packed``, ``predict_stream``) call it once they
+        have synchronised."""
+        st = self._ws.get("status")
+        if st is None or st.numel() != 1:
+            return
+        if int(st.item()) != 0:
+            st.zero_()
+            raise _lib.ImpError("fused forward: a molecule does not fit one 128-row tile (max_mol_atoms of the batch was wrong); "
+                                "use fused=False / 'auto' with a correct max_mol_atoms")
 
     def predict_stream(self, chunks, out=None, compact="auto"):
         """Pipelined prediction over a list of host-resident packed chunks (the cfg-3 "inference sweep" shape): the

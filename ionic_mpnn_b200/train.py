@@ -3,7 +3,13 @@ kernels: loss = mean((y - yhat)^2) + l2 kernel regularisers, per-variable clip_b
 
 Forward = the staged fp32 kernels with every h_i / agg_i kept; backward = csrc/bwd_fp32.cu (B1..B6); the flat gradient
 bucket is summed over ranks with ONE all-reduce (torch.distributed, NCCL) when a process group is initialised --
-SURVEY 8e; the only collective of the whole framework.  Mixed into MPNNModel (model.py)."""
+SURVEY 8e; the only collective of the whole framework.  The bucket's four-float tail carries the squared-error sum, the
+pair count and the two per-occurrence Embedding norms through the same collective.  Mixed into MPNNModel (model.py).
+
+Clip semantics [Keras 2.12, restated in oracle/ref_model.py:adam_step]: every variable is clipped by its own norm; for
+the two Embedding variables that norm is taken over the per-occurrence gradient rows (the optimizer clips the
+IndexedSlices gradient before de-duplicating it), computed by imp_sumsq / imp_bond_occurrence_norm2
+(``embedding_clip="occurrence"``, the default; ``"dense"`` clips by the dense gradient's norm)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -53,8 +59,29 @@ def prepare_training(batch, device):
            dict(entry_dst=entry_dst if len(entry_dst) else np.zeros(1, np.int32), chunk_begin=begin if total else np.zeros(1, np.int32),
                 chunk_end=end if total else np.zeros(1, np.int32), bucket_chunk_ptr=bcp).items()}
     dev["n_chunks"] = total
+    dev["n_cat_unique"] = int(rp[batch.n_cat_atoms])
+    if getattr(batch, "symmetric", None) is None:
+        batch.symmetric = entries_are_symmetric(batch)
     batch.train_dev = dev
     return dev
+
+
+def entries_are_symmetric(batch):
+    """True when the live entry multiset is closed under reversal: every (dst <- src, bond, mult) has its mirror
+    (src <- dst, bond, mult).  The message backward (dh += T[b]^T dagg[src] over the SAME CSR) is the true transpose only
+    then.  Holds by construction for reverse-doubled batches (train_viscosity.py:87-91) without ``max_edges`` truncation;
+    checked on the host (one sort) for everything else."""
+    rp = batch.host["row_ptr"].astype(np.int64)
+    if batch.n_unique == 0:
+        return True
+    dst = np.repeat(np.arange(batch.n_atoms, dtype=np.int64), np.diff(rp))
+    src = batch.host["col_src"].astype(np.int64)
+    bm = batch.host["edge_bm"].astype(np.int64) & 0xFFFFFFFF
+    n = np.int64(batch.n_atoms)
+    fwd = (dst * n + src)
+    rev = (src * n + dst)
+    o1, o2 = np.lexsort((bm, fwd)), np.lexsort((bm, rev))
+    return bool(np.array_equal(fwd[o1], rev[o2]) and np.array_equal(bm[o1], bm[o2]))
 
 
 class TrainMixin:
@@ -70,7 +97,8 @@ class TrainMixin:
         if s["atom_dim"] != 32:
             raise _lib.ImpError("the backward kernels are built for atom_dim 32")
         n = self.flat.numel()
-        st = {"grad": torch.zeros(n, dtype=torch.float32, device=self.device),
+        # gradient bucket + tail [sse, pair count, occurrence norm^2 of atom_emb, of bond_emb]: one collective carries all
+        st = {"grad": torch.zeros(n + 4, dtype=torch.float32, device=self.device),
               "m": torch.zeros(n, dtype=torch.float32, device=self.device),
               "v": torch.zeros(n, dtype=torch.float32, device=self.device), "step": 0}
         shapes = {k: tuple(self.params[k].shape) for k in self.var_names}
@@ -80,16 +108,29 @@ class TrainMixin:
         st["var_off"] = torch.tensor(offs, dtype=torch.int64, device=self.device)
         l2 = l2_terms(s)
         st["var_l2"] = torch.tensor([l2.get(k, 0.0) for k in self.var_names], dtype=torch.float32, device=self.device)
-        st["norms2"] = torch.zeros(len(self.var_names), dtype=torch.float32, device=self.device)
-        st["sse"] = torch.zeros(1, dtype=torch.float32, device=self.device)
+        st["norms2"] = torch.zeros(2 * len(self.var_names), dtype=torch.float32, device=self.device)
+        st["tail"] = st["grad"][n:n + 4]
+        st["sse"] = st["grad"][n:n + 1]
+        st["occ_var"] = torch.tensor([self.var_names.index("atom_emb"), self.var_names.index("bond_emb")], dtype=torch.int32,
+                                     device=self.device)
+        st["loss"] = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._train = st
         return st
 
-    def loss_and_grads(self, batch, global_batch=None):
+    def bond_occurrence_supported(self):
+        """imp_bond_occurrence_norm2 is built for the viscosity shape (bond_dim 8).  For the melting-point model
+        (bond_dim = 1024) the per-occurrence norm of the bond Embedding costs ~1 MFLOP per edge entry and step -- the
+        arithmetic the reference itself does -- and is not built: its bond Embedding is clipped by the dense norm
+        (DESIGN.md, "Embedding clip norms")."""
+        return self.spec["atom_dim"] == 32 and self.spec["bond_dim"] == 8
+
+    def loss_and_grads(self, batch, global_batch=None, occurrence_norms=True):
         """Forward + backward on a packed batch with ``batch.target``.  Returns (sse, out): device tensors holding this
         rank's sum of squared errors and predictions; gradients of mean-squared-error over ``global_batch`` pairs
-        (default: this batch) are left in the flat bucket ``self._train['grad']`` (WITHOUT the l2 terms, which
-        imp_clip_adam adds after the all-reduce so that they are counted once)."""
+        (default: this batch; ``"sum"``: un-normalised sum-gradients, for a count that is all-reduced with them) are left
+        in the flat bucket ``self._train['grad']`` (WITHOUT the l2 terms, which the optimizer kernel adds after the
+        all-reduce so that they are counted once).  With ``occurrence_norms`` the tail of the bucket receives the
+        per-occurrence squared norms of the two Embedding gradients (same scaling as the gradients)."""
         import torch
 
         s = self.spec
@@ -103,6 +144,10 @@ class TrainMixin:
         if batch.dev_y is None:
             raise ValueError("training needs batch.target")
         tr = prepare_training(batch, self.device)
+        if not batch.symmetric:
+            raise _lib.ImpError("training needs a batch whose live entries are symmetric (every dst<-src entry has its src<-dst "
+                                "mirror with the same bond and multiplicity): the message backward runs over the forward CSR. "
+                                "pack_records / pack_flat(double_edges=True) without max_edges produce such batches.")
         g = batch.c_struct()
         N, P = batch.n_atoms, batch.n_pairs
         sm = _stream()
@@ -140,7 +185,7 @@ class TrainMixin:
         n_ro = 2 * (d * fp + fp + fp * mix + mix) + mix * nh + nh + ((fp2 + 1) if fp2 else 0)
         ro = self._buf("tr_ro_grads", n_ro)
         ws_ro = self._buf("tr_ws_ro", lib.imp_readout_bwd_workspace_floats(d, fp, mix, fp2))
-        scale = 2.0 / float(global_batch if global_batch else P)
+        scale = 2.0 if global_batch == "sum" else 2.0 / float(global_batch if global_batch else P)
         if visc:
             if batch.dev_T is None:
                 raise ValueError("viscosity model needs batch.temperature")
@@ -164,7 +209,8 @@ class TrainMixin:
             o += cnt
         # ---- back through the pooling and the S steps
         ga, gb = self._buf("tr_ga", N * d), self._buf("tr_gb", N * d)
-        dagg = self._buf("tr_dagg", N * d)
+        occ_bond = occurrence_norms and self.bond_occurrence_supported()
+        daggs = [self._buf(f"tr_dagg{i}" if occ_bond else "tr_dagg", N * d) for i in range(S)]  # kept per step for the norm
         _lib.call("imp_pool_bwd", batch.dev["mol_ptr"].data_ptr(), batch.dev["atom_id"].data_ptr(), 2 * P, dpooled.data_ptr(), d,
                   ga.data_ptr(), sm)
         ws_gru = self._buf("tr_ws_gru", lib.imp_gated_update_bwd_workspace_floats(d))
@@ -173,6 +219,7 @@ class TrainMixin:
         G["bond_emb"].zero_()
         cur, nxt = ga, gb
         for i in reversed(range(S)):
+            dagg = daggs[i]
             wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
             gc = G[f"cat_gu_{i}.dense_z.kernel"].data_ptr()  # the layer's 8 variables are contiguous from here
             gn = G[f"an_gu_{i}.dense_z.kernel"].data_ptr()
@@ -192,35 +239,57 @@ class TrainMixin:
         ws_e = self._buf("tr_ws_emb", lib.imp_embed_bwd_workspace_floats(s["atom_vocab_size"], d))
         _lib.call("imp_embed_bwd", batch.dev["atom_id"].data_ptr(), cur.data_ptr(), N, s["atom_vocab_size"], d,
                   G["atom_emb"].data_ptr(), ws_e.data_ptr(), sm)
+        # ---- per-occurrence squared norms of the two Embedding gradients (csrc/occ_norm.cu) -> bucket tail [2], [3]
+        tail = st["tail"]
+        if occurrence_norms:
+            ws_n = self._buf("tr_ws_norm", max(1024, lib.imp_bond_occurrence_norm2_workspace_floats(batch.n_unique)))
+            _lib.call("imp_sumsq", cur.data_ptr(), N * d, tail.data_ptr() + 8, ws_n.data_ptr(), sm)
+            if occ_bond:
+                ob = lib.imp_occ_pack_bytes(d, K)
+                opk = self._buf("tr_occ_packed", ob * 2 * S, torch.uint8)
+                for ti, t in enumerate(TOWERS):
+                    for i in range(S):
+                        _lib.call("imp_occ_pack", self._ptr(f"{t}_bmm_{i}.bond_transform"), d, K, opk.data_ptr() + ob * (ti * S + i), sm)
+                hp = (C.c_void_p * S)(*[h[i].data_ptr() for i in range(S)])
+                dp = (C.c_void_p * S)(*[daggs[i].data_ptr() for i in range(S)])
+                _lib.call("imp_bond_occurrence_norm2", C.byref(g), tr["n_cat_unique"], tr["entry_dst"].data_ptr(), S, hp, dp, d, K,
+                          opk.data_ptr(), opk.data_ptr() + ob * S, tail.data_ptr() + 12, ws_n.data_ptr(), sm)
         return st["sse"], out
 
     def gradients(self):
         """Host copy of the gradient bucket as {variable: array} (after loss_and_grads)."""
         return {k: v.detach().cpu().numpy().copy() for k, v in self._train_state()["g"].items()}
 
-    def train_step(self, batch, lr=1e-3, clipnorm=1.0, beta1=0.9, beta2=0.999, eps=1e-7, global_batch=None, group=None):
-        """One optimiser step.  With an initialised process group the gradient bucket (and the squared-error sum) is
-        all-reduced once; ``global_batch`` defaults to world_size * local pairs.  Returns the loss (mse + l2) as a
-        device scalar tensor -- no host synchronisation."""
-        import torch
+    def train_step(self, batch, lr=1e-3, clipnorm=1.0, beta1=0.9, beta2=0.999, eps=1e-7, global_batch=None, group=None,
+                   embedding_clip="occurrence"):
+        """One optimiser step (train_viscosity.py:227-230).  With an initialised process group the gradient bucket -- whose
+        tail carries the squared-error sum, this rank's pair count and the per-occurrence Embedding norms -- is
+        all-reduced ONCE; ranks may hold different numbers of pairs (the mean is taken over the all-reduced count).
+        ``global_batch`` fixes the divisor instead (e.g. gradient accumulation over several calls).  Returns the loss
+        (mse + l2, weights before the update, as Keras reports it) as a device scalar tensor -- no host synchronisation."""
         import torch.distributed as dist
 
+        if embedding_clip not in ("occurrence", "dense"):
+            raise ValueError("embedding_clip must be 'occurrence' or 'dense'")
         st = self._train_state()
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-        gbatch = global_batch or batch.n_pairs * world
-        sse, _ = self.loss_and_grads(batch, global_batch=gbatch)
+        occ = embedding_clip == "occurrence"
+        summed = world > 1 and global_batch is None
+        self.loss_and_grads(batch, global_batch="sum" if summed else (global_batch or batch.n_pairs), occurrence_norms=occ)
+        tail = st["tail"]
+        if summed:
+            tail[1:2].fill_(float(batch.n_pairs))
         if world > 1:
             dist.all_reduce(st["grad"], op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(sse, op=dist.ReduceOp.SUM, group=group)
-        reg = sum(c * (self.params[k] ** 2).sum() for k, c in l2_terms(self.spec).items())
-        loss = sse[0] / gbatch + reg
         st["step"] += 1
-        _lib.call("imp_clip_adam", self.flat.data_ptr(), st["grad"].data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(),
+        n_occ = 0 if not occ else (2 if self.bond_occurrence_supported() else 1)
+        _lib.call("imp_clip_adam_sparse", self.flat.data_ptr(), st["grad"].data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(),
                   st["var_off"].data_ptr(), st["var_l2"].data_ptr(), len(self.var_names), st["norms2"].data_ptr(),
                   C.c_float(clipnorm if clipnorm else 0.0), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
-                  st["step"], _stream())
+                  st["step"], n_occ, st["occ_var"].data_ptr(), tail.data_ptr() + 8, tail.data_ptr() + 4 if summed else None,
+                  tail.data_ptr(), C.c_float(1.0 / float(global_batch or batch.n_pairs)), st["loss"].data_ptr(), _stream())
         self._tables_valid = False
-        return loss
+        return st["loss"][0].clone()
 
     # ------------------------------------------------------------------------------------------ fit / evaluate
     def evaluate(self, records, label=None):
@@ -231,10 +300,19 @@ class TrainMixin:
         label = label or ("log_eta" if self.spec["kind"] == "viscosity" else "mp")
         batch = pack_records(records, self.spec["bond_vocab_size"], label=label)
         pred = self.forward_packed(batch.to(self.device))
-        y = batch.dev_y
-        mse = ((pred - y) ** 2).mean()
-        reg = sum(c * (self.params[k] ** 2).sum() for k, c in l2_terms(self.spec).items())
-        return float((mse + reg).item())
+        st = self._train_state() if self.spec["atom_dim"] == 32 else None
+        nv = len(self.var_names)
+        if st is None:  # shapes without backward kernels still evaluate: the same kernel, its own small state
+            import torch
+
+            l2 = l2_terms(self.spec)
+            offs = [self.var_off[k] for k in self.var_names] + [self.flat.numel()]
+            st = {"var_off": torch.tensor(offs, dtype=torch.int64, device=self.device),
+                  "var_l2": torch.tensor([l2.get(k, 0.0) for k in self.var_names], dtype=torch.float32, device=self.device)}
+        scratch = self._buf("eval_scratch", nv + 2)
+        _lib.call("imp_eval_loss", pred.data_ptr(), batch.dev_y.data_ptr(), batch.n_pairs, self.flat.data_ptr(),
+                  st["var_off"].data_ptr(), st["var_l2"].data_ptr(), nv, scratch.data_ptr(), scratch.data_ptr() + 4 * (nv + 1), _stream())
+        return float(scratch[nv + 1].item())
 
     def fit(self, records, validation_data=None, epochs=1, batch_size=32, shuffle=True, patience=None,
             restore_best_weights=True, label=None, seed=0, verbose=0, lr=1e-3, clipnorm=1.0):

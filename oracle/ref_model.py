@@ -146,9 +146,12 @@ def global_sum_pool(atom_features, atom_ids):
     return (atom_features * mask).sum(dim=1)
 
 
-def forward(spec, p, x, keep=False):
+def forward(spec, p, x, keep=False, taps=None):
     """Whole graph on the padded input dict ``x`` (numpy int32 arrays, train_viscosity.py:306-314).
-    ``p``: dict of torch tensors.  Returns (out (B,1), intermediates dict)."""
+    ``p``: dict of torch tensors.  Returns (out (B,1), intermediates dict).  ``taps``: optional dict that receives
+    the two Embedding outputs of every tower (``{t}_atom_rows`` (B,N,d), ``{t}_bond_rows`` (B,E,K)) with
+    ``retain_grad`` set: their gradients are the per-occurrence rows of the IndexedSlices gradient TensorFlow
+    hands to the optimizer for the two Embedding variables (see ``adam_step``)."""
     inter = {}
     dt = p["atom_emb"].dtype
     S = spec["num_steps"]
@@ -159,6 +162,10 @@ def forward(spec, p, x, keep=False):
         conn = torch.as_tensor(np.asarray(x[f"{t}_connectivity"]), dtype=torch.long)
         h = p["atom_emb"][atom_ids]
         b = p["bond_emb"][bond_ids]
+        if taps is not None:
+            if h.requires_grad:
+                h.retain_grad(), b.retain_grad()
+            taps[f"{t}_atom_rows"], taps[f"{t}_bond_rows"] = h, b
         if keep:
             inter[f"{t}_h_0"] = h
         for i in range(S):
@@ -211,10 +218,10 @@ def predict(spec, params, x, dtype=torch.float64, batch_size=None, keep=False):
     return out
 
 
-def loss_fn(spec, p, x, y):
+def loss_fn(spec, p, x, y, taps=None):
     """Keras compiled loss: mean((y - yhat)^2) with y (B,) expanded to (B,1), plus the l2 kernel
     regularisers (train_viscosity.py:189,227-230)."""
-    out, _ = forward(spec, p, x)
+    out, _ = forward(spec, p, x, taps=taps)
     yt = torch.as_tensor(np.asarray(y), dtype=out.dtype).reshape(-1, 1)
     loss = ((yt - out) ** 2).mean()
     for name, coef in l2_terms(spec):
@@ -222,24 +229,52 @@ def loss_fn(spec, p, x, y):
     return loss, out
 
 
-def loss_and_grads(spec, params, x, y, dtype=torch.float64):
+def loss_and_grads(spec, params, x, y, dtype=torch.float64, occurrence_norms=False):
+    """Loss, dense gradients of every variable and predictions.  With ``occurrence_norms`` a fourth value is
+    returned: {"atom_emb": s_a, "bond_emb": s_b}, the sum of squares over the UN-deduplicated per-occurrence
+    gradient rows of the two Embedding variables (every (tower, sample, atom slot) / (tower, sample, edge slot) of
+    the padded inputs is one occurrence) -- what ``tf.clip_by_norm`` sees for an IndexedSlices gradient."""
     p = to_torch(params, dtype, requires_grad=True)
-    loss, out = loss_fn(spec, p, x, y)
+    taps = {} if occurrence_norms else None
+    loss, out = loss_fn(spec, p, x, y, taps=taps)
     loss.backward()
     grads = {k: (v.grad.numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in p.items()}
-    return float(loss), grads, out.detach().numpy()
+    if not occurrence_norms:
+        return float(loss.detach()), grads, out.detach().numpy()
+    occ = {"atom_emb": float(sum((taps[f"{t}_atom_rows"].grad ** 2).sum() for t in TOWERS)),
+           "bond_emb": float(sum((taps[f"{t}_bond_rows"].grad ** 2).sum() for t in TOWERS))}
+    return float(loss.detach()), grads, out.detach().numpy(), occ
 
 
-def adam_step(params, grads, m, v, step, lr=1e-3, clipnorm=1.0, beta1=0.9, beta2=0.999, eps=1e-7):
-    """[Keras semantics] Adam(1e-3, clipnorm=1.0): per-variable clip_by_norm, then
-    m += (g-m)(1-b1); v += (g^2-v)(1-b2); w -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps).
-    Dense-gradient norm is used for every variable (see DESIGN.md for the embedding caveat).
-    ``step`` is 1-based.  Updates in place, returns the per-variable pre-clip norms."""
+def adam_step(params, grads, m, v, step, lr=1e-3, clipnorm=1.0, beta1=0.9, beta2=0.999, eps=1e-7,
+              occurrence_norm2=None):
+    """[Keras semantics] ``Adam(1e-3, clipnorm=1.0)`` of TF / Keras 2.12 (environment.yml:10; the library source is
+    not under /root/reference, so this is restated from keras/optimizers/optimizer.py and adam.py of that release):
+
+      _BaseOptimizer.apply_gradients:  grads = self._clip_gradients(grads)           # per variable:
+                                                                                      #   tf.clip_by_norm(g, clipnorm)
+                                       grads = self._deduplicate_sparse_grad(grads)  # AFTER the clip
+      tf.clip_by_norm(t, c):           values = t.values if IndexedSlices else t
+                                       l2norm = sqrt(sum(values * values));  values * c / max(l2norm, c)
+      Adam.update_step:                alpha = lr * sqrt(1 - b2^t) / (1 - b1^t)
+                                       m += (g - m) (1 - b1);  v += (g^2 - v) (1 - b2)
+                                       w -= alpha * m / (sqrt(v) + eps)
+                                       (sparse branch: the same decay of ALL rows of m and v, the de-duplicated
+                                        rows scattered in, and a dense update of w -- identical to the dense branch)
+
+    The only place where the two ``Embedding`` variables (train_viscosity.py:163-164; gradient = IndexedSlices whose
+    rows are the per-occurrence gradients, concatenated over the two towers) differ from dense variables is therefore
+    the CLIP NORM: it is taken over the un-deduplicated rows, sqrt(sum_occurrences |g_occ|^2), not over the summed
+    dense gradient.  ``occurrence_norm2`` = {variable: that sum of squares} (from ``loss_and_grads(...,
+    occurrence_norms=True)``) selects it; variables not listed (and ``None``) use the dense norm.
+    ``step`` is 1-based.  Updates in place, returns the per-variable norms used for clipping."""
     norms = {}
     alpha = lr * math.sqrt(1 - beta2 ** step) / (1 - beta1 ** step)
     for k in params:
         g = np.asarray(grads[k], dtype=np.float64)
         nrm = float(np.sqrt((g * g).sum()))
+        if occurrence_norm2 is not None and k in occurrence_norm2:
+            nrm = float(np.sqrt(occurrence_norm2[k]))
         norms[k] = nrm
         if clipnorm is not None:
             g = g * (clipnorm / max(nrm, clipnorm))

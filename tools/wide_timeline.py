@@ -17,10 +17,14 @@ m = MPNNModel(spec, precision="fp16")
 m.extra_tc_flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 m.forward_packed(batch)
 buf = torch.zeros(16 * 8, dtype=torch.int64, device="cuda")
-_lib.load().imp_debug_wide_timeline(buf.data_ptr())
+import ctypes  # noqa: E402
+
+dbg = ctypes.CDLL(_lib.LIB_PATH).imp_debug_wide_timeline  # debug hook, deliberately not in include/imp_b200.h
+dbg.restype, dbg.argtypes = None, [ctypes.c_void_p]
+dbg(buf.data_ptr())
 m.forward_packed(batch)
 torch.cuda.synchronize()
-_lib.load().imp_debug_wide_timeline(None)
+dbg(None)
 t = buf.cpu().numpy().reshape(16, 8)
 names = ["wait phase A", "EA (r*h)", "wait phase B", "E2 pass 1", "E2 pass 2"]
 print("tile  " + "  ".join(f"{n:>13s}" for n in names) + "   tile total")

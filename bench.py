@@ -56,6 +56,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sync-every-step", action="store_true", help="visc_train: read the loss back after every step")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="host-resident chunks the e2e leg streams per step")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="default run only: skip the sub-records of the other BASELINE configs (extra.mp64k / train / wide / fp32)")
+    ap.add_argument("--min-timed-s", type=float, default=0.0,
+                    help="raise --steps so that the timed region lasts at least this long (sub-records use 1.2 s)")
     return ap.parse_args()
 
 
@@ -262,8 +266,6 @@ def run_train(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     P, kind, name = workload_config(args)
     spec = make_spec(kind)
     model = MPNNModel(spec, device=f"cuda:{local}", seed=0, precision="fp32")
@@ -280,6 +282,7 @@ def run_train(args):
     for _ in range(args.warmup):
         losses.append(model.train_step(batch))
     barrier()
+    args.steps = steps_for_min_time(args, lambda: model.train_step(batch), world, local)
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
@@ -317,11 +320,22 @@ def run_train(args):
         e1.record()
         events.append((n, e0, e1))
 
+    real_ar = dist.all_reduce
+
+    def timed_all_reduce(t, *a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        real_ar(t, *a, **k)
+        e1.record()
+        events.append(("nccl_all_reduce", e0, e1))
+
     tt._lib.call = timed_call
+    dist.all_reduce = timed_all_reduce
     try:
         model.train_step(batch)
     finally:
         tt._lib.call = real_call
+        dist.all_reduce = real_ar
     torch.cuda.synchronize()
     for n, e0, e1 in events:
         per_kernel[n.replace("imp_", "")] = per_kernel.get(n.replace("imp_", ""), 0.0) + e0.elapsed_time(e1)
@@ -329,21 +343,68 @@ def run_train(args):
     if rank == 0:
         lv = [float(l.item()) for l in losses]
         tot = sum(per_kernel.values()) or 1.0
+        # ---- roofline of the dominant kernel.  Algorithmic work per launch: every training kernel at
+        # atom_dim 32 is to the left of the ridge (<= 58 FLOP per byte against 211), so the bound is HBM.
+        N, Eu, d, S = batch.n_atoms, batch.n_unique, 32, spec["num_steps"]
+        tb = {"gated_update_bwd": 5 * N * d * 4, "gated_update": 3 * N * d * 4, "edge_messages_grouped": Eu * (2 * d * 4 + 12),
+              "segment_sum": Eu * d * 4 + N * d * 4 + 4 * N, "segment_sum_add": Eu * d * 4 + 2 * N * d * 4 + 4 * N,
+              "bond_transform_bwd": Eu * (2 * d * 4 + 12), "embed_atoms": 4 * N + N * d * 4, "embed_bwd": 4 * N + N * d * 4,
+              "bond_occurrence_norm2": S * Eu * 2 * d * 4 + 12 * Eu, "sumsq": N * d * 4,
+              "global_sum_pool": N * d * 4 + 4 * N, "pool_bwd": N * d * 4 + 4 * N}
+        tf = {"gated_update_bwd": 36 * N * d * d, "gated_update": 12 * N * d * d, "edge_messages_grouped": 2 * Eu * d * d,
+              "bond_transform_bwd": 2 * Eu * d * d, "bond_occurrence_norm2": S * 2 * Eu * d * d * 8}
+        counts = {}
+        for n, _, _ in events:
+            counts[n.replace("imp_", "")] = counts.get(n.replace("imp_", ""), 0) + 1
+        hbm_peak, tf_peak, peak_src = measured_peaks()
+        pk = {k: {"avg_ms": v / counts[k], "launches_per_step": counts[k], "share": v / tot,
+                  "GBps": tb[k] / (v / counts[k] * 1e-3) / 1e9 if k in tb else None,
+                  "TFLOPs": tf[k] / (v / counts[k] * 1e-3) / 1e12 if k in tf else None} for k, v in per_kernel.items()}
+        dom = max((k for k in per_kernel if k in tb), key=lambda k: per_kernel[k])
+        ach = pk[dom]["GBps"]
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": tb[dom],
+                    "algorithmic_flop_per_launch": tf.get(dom), "avg_launch_ms": pk[dom]["avg_ms"],
+                    "share_of_step": pk[dom]["share"], "per_kernel": pk}
         line = {"metric": "train_ion_pair_graphs_per_s", "value": P * world * args.steps / (ms_total * 1e-3), "unit": UNIT,
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": name, "pairs_per_gpu": P, "global_batch": P * world, "atoms_per_gpu": batch.n_atoms,
                            "params": model.count_params(), "collective": "one NCCL all-reduce of the flat gradient bucket "
-                           f"({model.flat.numel()} fp32) per step" if world > 1 else "none (1 GPU)",
+                           f"({model._train['grad'].numel()} fp32) per step" if world > 1 else "none (1 GPU)",
                            "l2_policy": "inputs larger than L2 (%.1f GB of saved activations per GPU)" % (
                                9 * batch.n_atoms * 32 * 4 / 1e9)},
-                "gpu_launches": len(events) * args.steps, "clocks": clocks,
+                "gpu_launches": sum(1 for e in events if e[0] != "nccl_all_reduce") * args.steps, "clocks": clocks,
+                "roofline": roofline,
+                "all_reduce": {"per_step": counts.get("nccl_all_reduce", 0), "ms_per_step": round(per_kernel.get("nccl_all_reduce", 0.0), 4),
+                               "floats": int(model._train["grad"].numel()),
+                               "carries": "gradients + [sse, pair count, 2 occurrence norms]"},
+                "embedding_clip": "per-occurrence norm (Keras IndexedSlices semantics)",
                 "host_enqueue_ms_per_step": round(t_enq * 1e3 / args.steps, 2), "loss_first_last": [lv[0], lv[-1]], "loss_decreased": lv[-1] < lv[0],
                 "kernel_ms": {k: round(v, 3) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
                 "kernel_share": {k: round(v / tot, 3) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])}}
-        print(json.dumps(line), flush=True)
+        return line
+    return None
+
+
+def steps_for_min_time(args, one_step, world, local):
+    """--min-timed-s: number of timed steps such that the region lasts at least that long (the clock sampler needs ~1 s);
+    the same on every rank (max over ranks of one probe step)."""
+    import torch
+    import torch.distributed as dist
+
+    if not args.min_timed_s:
+        return args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=f"cuda:{local}")
     if world > 1:
-        dist.destroy_process_group()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return max(args.steps, int(args.min_timed_s * 1e3 / max(float(t.item()), 1e-3)) + 1)
 
 
 def run_b200(args):
@@ -360,8 +421,6 @@ def run_b200(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     P, kind, name = workload_config(args)
     wide = args.workload == "wide"
     spec = make_spec(kind, atom_dim=256, num_steps=6) if wide else make_spec(kind)
@@ -390,6 +449,7 @@ def run_b200(args):
     for _ in range(args.warmup):
         model.forward_packed(batch)
     barrier()
+    args.steps = steps_for_min_time(args, lambda: model.forward_packed(batch), world, local)
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
@@ -588,19 +648,69 @@ def run_b200(args):
                 "edges_per_s": batch.n_edges * world * args.steps / (ms_total * 1e-3),
                 "gpu_launches": model.launches_per_forward(batch) * args.steps,
                 "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "pack": pack}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
+
+
+EXTRAS = (  # (key, workload, precision): the other BASELINE configs as sub-records of the default line
+    ("mp64k", "mp64k", "fp16"),        # configs[1]: melting-point forward, 64k pairs, staged tensor kernels
+    ("train", "visc_train", "fp32"),   # configs[3]: training step (the only place a collective is timed)
+    ("wide", "wide", "fp16"),          # configs[4]: atom_dim 256, 6 steps
+    ("fp32", "visc_sweep", "fp32"),    # the 1e-5 parity path on the headline workload
+)
+
+
+def run_extras(args):
+    """Every rank runs every sub-workload (the training step contains the all-reduce); rank 0 collects the lines."""
+    import copy
+    import gc
+
+    import torch
+
+    out = {}
+    for key, workload, precision in EXTRAS:
+        a = copy.copy(args)
+        a.workload, a.precision, a.pairs_per_gpu = workload, precision, None
+        a.no_e2e = a.no_cpu_baseline = True
+        a.staged, a.tc_flags, a.min_timed_s, a.steps, a.warmup = False, 0, 1.2, 3, 3
+        if key == "fp32":
+            a.pairs_per_gpu = 524_288  # 8 M pairs/s: the full 2 M-pair batch would take 0.26 s per step
+        try:
+            line = run_train(a) if workload == "visc_train" else run_b200(a)
+        except Exception as e:  # a sub-record must never take the headline down with it
+            line = {"error": f"{type(e).__name__}: {e}"} if int(os.environ.get("RANK", "0")) == 0 else None
+        if line is not None:
+            out[key] = line
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "visc_train":
-        run_train(args)
-    else:
-        run_b200(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        line = run_train(args) if args.workload == "visc_train" else run_b200(args)
+        headline = args.workload == "visc_sweep" and args.precision == "fp16" and not args.staged and not args.tc_flags
+        if headline and not args.no_extras and args.pairs_per_gpu is None:
+            extra = run_extras(args)
+            if line is not None:
+                line["extra"] = extra
+        if line is not None:
+            print(json.dumps(line), flush=True)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

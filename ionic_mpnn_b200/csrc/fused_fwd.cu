@@ -456,12 +456,13 @@ __host__ __device__ inline int fused2_smem_bytes(int steps, int bond_vocab) {
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Optional phase timing (compile with -DFZ_PROFILE): per-phase clock64 deltas of selected threads, summed into
-// a.prof[thread-class][18] (thread classes: u == 0, u == 96 (warp 3), u == 224 (warp 7)); read by tools/fused_phase_profile.py.
+// a.prof[thread-class][32] (thread classes: u == 0, u == 96 (warp 3), u == 224 (warp 7)); read by tools/fused_phase_profile.py.
 #ifdef FZ_PROFILE
 #define FZ_DEBUG(a) ((a).debug)
+#define FZ_PROF_N 32
 #define FZ_PROF_DECL                                                                     \
-  long long prof_acc[18];                                                                \
-  for (int i_ = 0; i_ < 18; ++i_) prof_acc[i_] = 0;                                      \
+  long long prof_acc[FZ_PROF_N];                                                         \
+  for (int i_ = 0; i_ < FZ_PROF_N; ++i_) prof_acc[i_] = 0;                               \
   long long prof_last = clock64();                                                       \
   const int prof_cls = (u == 0) ? 0 : (u == 96) ? 1 : (u == 224) ? 2 : -1
 #define FZ_PROF_T(i)                         \
@@ -472,7 +473,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
   } while (0)
 #define FZ_PROF_FLUSH                                                                                       \
   if (prof_cls >= 0 && a.prof)                                                                               \
-    for (int i_ = 0; i_ < 18; ++i_) atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + prof_cls * 18 + i_, (unsigned long long)prof_acc[i_])
+    for (int i_ = 0; i_ < FZ_PROF_N; ++i_) atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + prof_cls * FZ_PROF_N + i_, (unsigned long long)prof_acc[i_])
 #else
 #define FZ_DEBUG(a) 0
 #define FZ_PROF_DECL
@@ -1044,6 +1045,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
         // ------------------------------------------------------------ Z in two K halves -> TMEM -> GEMM1
 #pragma unroll 1
         for (int hz = 0; hz < 2; ++hz) {
+          FZ_PROF_T(8);
           __half2 acc[D * 2];
 #pragma unroll
           for (int i = 0; i < D * 2; ++i) acc[i] = __half2(__ushort_as_half(0), __ushort_as_half(0));
@@ -1115,10 +1117,12 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
               }
             }
           }
+          FZ_PROF_T(11 + hz);  // Z half built
           if (hz == 1 && !(FZ_DEBUG(a) & 2)) {  // GEMM1a must have consumed the first half before its columns are rewritten
             tc::mbar_wait(&ws.bar[3], ph);
             tc::fence_after_thread_sync();
           }
+          FZ_PROF_T(13);  // wait for GEMM1a (second half only)
 #pragma unroll
           for (int ch = 0; ch < 2; ++ch) {
             uint32_t rr[32];
@@ -1127,8 +1131,10 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
             tc::tmem_st32(tZ + lane_off + (uint32_t)(ch * 32), rr);
           }
           tc::tmem_wait_st();
+          FZ_PROF_T(14);  // Z half stored
           tc::fence_before_thread_sync();
           tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+          FZ_PROF_T(15 + hz);  // barrier after the Z half
           if (mma_warp && !(FZ_DEBUG(a) & 2)) {
             tc::fence_after_thread_sync();
             if (tc::elect_one()) {
@@ -1141,8 +1147,10 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
             __syncwarp();
           }
         }
+        FZ_PROF_T(17);  // MMA issue of the second half
         if (!(FZ_DEBUG(a) & 2)) tc::mbar_wait(&ws.bar[0], ph);
         tc::fence_after_thread_sync();
+        FZ_PROF_T(18);  // wait for GEMM1
         {  // agg and h as 16-bit A operands
           float v[32];
           tc::tmem_ld32(tCagg + lane_off, v);
@@ -1157,8 +1165,10 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
           tc::tmem_st8(tOnes + lane_off, ones);
         }
         tc::tmem_wait_st();
+        FZ_PROF_T(19);  // operands written
         tc::fence_before_thread_sync();
         tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+        FZ_PROF_T(20);  // barrier before GEMM2
         // ------------------------------------------------------------ GEMM2: 0.5 ([h | agg | 1] . [Wz | Wr ; bz | br])
         if (mma_warp && !(FZ_DEBUG(a) & 2)) {
           tc::fence_after_thread_sync();
@@ -1172,6 +1182,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
         }
         if (!(FZ_DEBUG(a) & 2)) tc::mbar_wait(&ws.bar[1], ph);
         tc::fence_after_thread_sync();
+        FZ_PROF_T(21);  // wait for GEMM2
         float z[D];
         {
           float v[32];
@@ -1189,8 +1200,10 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
           tc::tmem_st16(tArh + lane_off, rr);
         }
         tc::tmem_wait_st();
+        FZ_PROF_T(22);  // gates
         tc::fence_before_thread_sync();
         tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+        FZ_PROF_T(23);  // barrier before GEMM3
         // ------------------------------------------------------------ GEMM3: [agg | r*h] . [Wh[d:2d] ; Wh[0:d]]
         if (mma_warp && !(FZ_DEBUG(a) & 2)) {
           tc::fence_after_thread_sync();
@@ -1205,6 +1218,7 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
         }
         if (!(FZ_DEBUG(a) & 2)) tc::mbar_wait(&ws.bar[2], ph);
         tc::fence_after_thread_sync();
+        FZ_PROF_T(24);  // wait for GEMM3
         {  // candidate, blend, LayerNorm (biased variance, eps), residual  (models/layers.py:151-156)
           float gq[32];
           tc::tmem_ld32(tCht + lane_off, gq);
@@ -1232,11 +1246,13 @@ __global__ void __launch_bounds__(NCTX * F3_CTX_THREADS, 1) mpnn_fused_h2x_kerne
               reinterpret_cast<float4*>(hbrow)[c] = make_float4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
           }
         }
+        FZ_PROF_T(25);  // candidate, blend, LayerNorm
         tc::fence_before_thread_sync();
         tc::named_bar_sync(bar_id, F3_CTX_THREADS);
+        FZ_PROF_T(26);  // barrier at the end of the step
         ph ^= 1;
       }
-      FZ_PROF_T(8);
+      FZ_PROF_T(27);
       // ---------------------------------------------------------------- GlobalSumPool
       {
         const float* hfp = reinterpret_cast<const float*>(ws.hb);
@@ -1378,7 +1394,7 @@ static int fused_forward_impl(const imp_graph_t* g, const imp_compact_graph_t* c
   IMP_REQUIRE((flags >> 8) == 0, IMP_ERR_ARG, "imp_mpnn_forward_fused: unknown flag bits 0x%x", flags & ~0xff);
 #endif
 #ifdef FZ_PROFILE
-  a.prof = reinterpret_cast<long long*>(d_status);  // profiling build: d_status must hold 3 * 18 int64 (zeroed by the caller)
+  a.prof = reinterpret_cast<long long*>(d_status);  // profiling build: d_status must hold 3 * 32 int64 (zeroed by the caller)
   a.status = nullptr;
 #endif
   // one persistent CTA per SM; CTAs are split between the towers in proportion to their atoms

@@ -191,6 +191,8 @@ int imp_gated_update_wide(const float* d_h, const float* d_agg, int32_t n_atoms,
 #define IMP_TC_WIDE_SPLIT_GRU 64
 #define IMP_TC_WIDE_NO_CLUSTER 256 /* wide GatedUpdate without the 2-CTA weight multicast (comparison) */
 #define IMP_TC_MSG_ONE_CHUNK_PER_CTA 128 /* imp_edge_messages_tc16: the non-pipelined kernel (comparison) */
+#define IMP_TC_GEN3 512 /* imp_mpnn_forward_fused: kept for callers of round 1; the self-contained kernel IS generation 3 */
+#define IMP_TC_GEN4 1024 /* imp_mpnn_forward_fused: the fourth-generation kernel (arrive-and-continue; measured slower) */
 int64_t imp_gru_pack_bytes(int32_t d);
 int imp_gru_pack_bf16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
 int imp_gru_pack_f16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
@@ -279,8 +281,11 @@ int imp_pool_head_mp(const imp_graph_t* g, const float* d_h, int32_t d, int32_t 
  *                      instead of packed half2 (default; 2 products per lane-instruction, rows sorted by degree).
  *                      IMP_TC_MP8: smaller register tile in the fp32 Z build (tuning switch, same results).
  *                      IMP_TC_TWO_THREADS_PER_ROW: second-generation half kernel (2 contexts x 256 threads per SM) instead
- *                      of the default third generation (4 contexts x 128 threads); IMP_TC_THREE_CONTEXTS: 3 contexts.
+ *                      of the default third generation (4 contexts x 128 threads, blocking context barriers;
+ *                      IMP_TC_THREE_CONTEXTS: its 3-context form); IMP_TC_GEN4: fourth generation (csrc/fused_fwd4.cu:
+ *                      arrive-and-continue synchronisation, r*h fold, 3-instruction LayerNorm; 8 % slower, kept for comparison).
  *                      Pack and forward must be called with the same flags (the Wc block layout differs).
+ *                      The fastest form is the PLANNED forward below (fifth generation), which reads a tile plan.
  *   max_mol_atoms      largest molecule of the batch (the caller knows it from mol_ptr); > 128 is refused.
  *   d_pooled           [2 * n_pairs, d] molecule sums in mol_ptr order -> imp_readout_visc / imp_readout_mp.
  *   d_status           optional device int, set to 1 if the kernel met a molecule that does not fit a tile.
@@ -309,6 +314,30 @@ int imp_mpnn_forward_fused_compact(const imp_compact_graph_t* cg, const float* d
                                    const float* d_bond_emb, int32_t d, int32_t bond_dim, int32_t steps, const void* d_packed,
                                    float eps, int32_t flags, int32_t max_mol_atoms, float* d_pooled, int32_t* d_status,
                                    void* stream);
+
+/* Planned fused forward (fifth generation, the default of MPNNModel): same mathematics and the same replaced reference code
+ * as imp_mpnn_forward_fused, fed from a TILE PLAN instead of the CSR arrays.
+ *   imp_fused_plan     once per batch (integer-only, ~3 % of a forward): cuts the batch into self-contained 128-row tiles of
+ *                      whole molecules -- best-fit over windows of 256 molecules (tiles ~97 % full instead of ~88 %), rows
+ *                      listed by in-degree, CSR entries translated to tile rows -- one 2 KiB record per tile
+ *                      (csrc/fused_plan.cuh).  Pass exactly one of g / cg (the int32 CSR batch or the compact feed).
+ *                      This is the packed-batch counterpart of the reference's padding step (train_viscosity.py:52-59,
+ *                      76-110, 291-314).  d_plan: imp_fused_plan_bytes() bytes; int32 word 4 of the buffer is a status
+ *                      (0 = ok; 1 = a molecule outside the envelope: > 128 atoms, a row with > 31 entries or > 336 entries
+ *                      per molecule; 2 = capacity exceeded) that the caller reads after synchronising -- such batches go
+ *                      through imp_mpnn_forward_fused or the staged kernels.
+ *   imp_mpnn_forward_fused_planned   the forward: per tile one TMA bulk copy of its record (double-buffered), then the
+ *                      step pipeline of the third generation.  flags: IMP_TC_FP16 [| IMP_TC_PRECISE_EPILOGUE]; weights
+ *                      packed by imp_fused_pack with the same flags.  Results do not depend on how the plan cut the batch
+ *                      (row order inside a tile does not enter the arithmetic); they agree with imp_mpnn_forward_fused to
+ *                      fp32 rounding (the LayerNorm is evaluated as gamma * (n * inv - mean * inv) + h + beta here). */
+int64_t imp_fused_plan_bytes(int32_t n_pairs, int32_t n_atoms, int32_t n_unique, int32_t max_mol_atoms);
+int imp_fused_plan(const imp_graph_t* g, const imp_compact_graph_t* cg, int32_t atom_vocab, int32_t max_mol_atoms, void* d_plan,
+                   int64_t plan_bytes, void* stream);
+int imp_mpnn_forward_fused_planned(const void* d_plan, int32_t n_pairs, int32_t n_atoms, int32_t n_cat_atoms,
+                                   int32_t bond_vocab, const float* d_atom_emb, int32_t atom_vocab, const float* d_bond_emb,
+                                   int32_t d, int32_t bond_dim, int32_t steps, const void* d_packed, float eps, int32_t flags,
+                                   float* d_pooled, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Wide atom states on the tensor cores (atom_dim 256, bond_dim 8: BASELINE configs[4], the "wide/deep" variant).

@@ -29,42 +29,17 @@
 //   [  0,128)  Z, 16-bit pairs (K = 256)        -- dead after GEMM1, then reused:
 //   [  0, 16)  h   operand (K = 32)   [ 16, 32)  agg operand    [ 32, 48)  r*h operand
 //   [128,160)  GEMM1 accumulator (agg, fp32)    [160,224)  z | r pre-activations    [224,256)  candidate pre-activation
-#include "common.cuh"
-#include "tc_common.cuh"
+#include "fused_common.cuh"
 
 namespace imp {
-
-constexpr int FZ_ROWS = 128;      // rows per tile = TMEM lanes
-constexpr int FZ_D = 32;          // atom_dim
-constexpr int FZ_K = 8;           // bond_dim
-constexpr int FZ_GROUP = 64;      // molecules per scheduling unit
-constexpr int FZ_HS = 36;         // floats per h row in shared memory (144 B: conflict-free 16-byte row reads)
-constexpr int FZ_CS = 12;         // floats per bond-coefficient row (48 B)
-constexpr int FZ_MAX_STEPS = 4;
-constexpr int FZ_MAX_VB = 256;
-
-struct FusedPack {  // one (tower, step)
-  static constexpr int WC_BYTES = FZ_D * (FZ_D * FZ_K) * 2;  // Wc[n = l][kk = m*8+k], chunk-major, 16 KiB
-  static constexpr int BZR_BYTES = 2 * FZ_D * 2 * FZ_D * 2;  // [Wz | Wr]^T, 8 KiB
-  static constexpr int BH_BYTES = FZ_D * 2 * FZ_D * 2;       // Wh^T, 4 KiB
-  static constexpr int BIAS_FLOATS = 5 * FZ_D;               // bz, br, bh, gamma, beta
-  static constexpr int OFF_BZR = WC_BYTES;
-  static constexpr int OFF_BH = OFF_BZR + BZR_BYTES;
-  static constexpr int OFF_BIAS = OFF_BH + BH_BYTES;
-  static constexpr int OFF_BBZR = OFF_BIAS + BIAS_FLOATS * 4;  // [64 x 16] K-major block, column 0 = 0.5 * (bz | br)
-  static constexpr int BBZR_BYTES = 2 * FZ_D * 16 * 2;         //   (third-generation kernel: biases ride in the GEMM)
-  static constexpr int OFF_BBH = OFF_BBZR + BBZR_BYTES;        // [32 x 16] block, column 0 = bh
-  static constexpr int BBH_BYTES = FZ_D * 16 * 2;
-  static constexpr int BYTES = OFF_BBH + BBH_BYTES;            // 32 384
-};
-static_assert(FusedPack::BYTES % 128 == 0, "pack must keep 128-byte alignment of the next step");
 
 // KHALF = false: Wc[n = l][kk = m*8 + k] = W[k][l][m] as one [32 x 256] K-major block (first-generation kernels).
 // KHALF = true : two [32 x 128] blocks, block hz holds k in [4 hz, 4 hz + 4): Wc_hz[l][m*4 + (k - 4 hz)] = W[k][l][m]
 //                (the four-context kernel builds and multiplies Z in two K halves).
+// wh_top_scale: generation 4 packs Wh[0:d] (the rows that multiply r * h) pre-multiplied by 0.5 (fused_fwd4.cu).
 template <int FMT, bool KHALF>
 __global__ void fused_pack_kernel(const float* __restrict__ W /* [K, d, d] */, imp_gru_weights_t w,
-                                  unsigned char* __restrict__ out) {
+                                  unsigned char* __restrict__ out, float wh_top_scale) {
   constexpr int D = FZ_D, KK = FZ_D * FZ_K;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < D * KK) {
@@ -96,7 +71,8 @@ __global__ void fused_pack_kernel(const float* __restrict__ W /* [K, d, d] */, i
   }
   if (i < D * 2 * D) {  // Bh[n][k] = Wh[k][n]
     const int n = i / (2 * D), k = i % (2 * D);
-    *reinterpret_cast<uint16_t*>(out + FusedPack::OFF_BH + tc::chunk_off(n, k / 8, D) + (k % 8) * 2) = tc::cvt16<FMT>(w.Wh[k * D + n]);
+    *reinterpret_cast<uint16_t*>(out + FusedPack::OFF_BH + tc::chunk_off(n, k / 8, D) + (k % 8) * 2) =
+        tc::cvt16<FMT>((k < D ? wh_top_scale : 1.0f) * w.Wh[k * D + n]);
   }
   if (i < D) {
     float* b = reinterpret_cast<float*>(out + FusedPack::OFF_BIAS);
@@ -104,27 +80,6 @@ __global__ void fused_pack_kernel(const float* __restrict__ W /* [K, d, d] */, i
   }
 }
 
-struct FusedArgs {
-  const int* mol_ptr;
-  const int* atom_id;
-  const int* row_ptr;
-  const int* col_src;
-  const int* edge_bm;
-  const float* atom_emb;
-  const float* bond_emb;
-  const unsigned char* packed;  // [2][steps][FusedPack::BYTES]
-  float* pooled;                // [2P][32]
-  int* status;                  // optional: set to 1 if a molecule does not fit one tile
-  int n_pairs, atom_vocab, bond_vocab, steps, n_cta_cat;
-  int n_atoms, n_unique;
-  float eps;
-  // compact input feed (imp_mpnn_forward_fused_compact): 16-bit atom words, 32-bit entry words, per-molecule entry offsets
-  const int* mol_eptr;             // [2P+1] first CSR entry of every molecule
-  const unsigned short* atom_w;    // [N] atom id | in-degree << 8
-  const unsigned int* edge_w;      // [Eu] src (molecule-local) | bond << 8 | multiplicity << 16
-  long long* prof;  // FZ_PROFILE builds only
-  int debug;        // FZ_PROFILE builds only (timing ablations, results are wrong): 1 = skip the entry loop, 2 = skip MMAs
-};
 
 struct alignas(16) FusedWgSmem {
   float h[FZ_ROWS * FZ_HS];
@@ -133,36 +88,10 @@ struct alignas(16) FusedWgSmem {
   uint64_t bar[4];
 };
 
-struct FusedCtl {
-  uint32_t tmem_base;
-  uint32_t pad;
-  uint64_t wbar;  // mbarrier of the TMA weight load (third-generation kernel)
-};
 
 __host__ __device__ inline int fused_smem_bytes(int steps, int bond_vocab) {
   const int ctab = (bond_vocab * FZ_CS * 4 + 127) / 128 * 128;
   return steps * FusedPack::BYTES + ctab + 2 * (int)sizeof(FusedWgSmem) + (int)sizeof(FusedCtl);
-}
-
-__device__ __forceinline__ float fz_tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-template <bool PRECISE>
-__device__ __forceinline__ float fz_sigmoid(float x) {
-  if (PRECISE) return 1.0f / (1.0f + expf(-x));
-  return fmaf(0.5f, fz_tanh_fast(0.5f * x), 0.5f);
-}
-// sigmoid(2 y) for a pre-activation y that was already halved by the packed weights
-template <bool PRECISE>
-__device__ __forceinline__ float fz_sigmoid_half(float y) {
-  if (PRECISE) return 1.0f / (1.0f + expf(-2.0f * y));
-  return fmaf(0.5f, fz_tanh_fast(y), 0.5f);
-}
-template <bool PRECISE>
-__device__ __forceinline__ float fz_tanh(float x) {
-  return PRECISE ? tanhf(x) : fz_tanh_fast(x);
 }
 
 // MP = number of h columns (m) handled per pass over a row's entries: MP*8 fp32 accumulators live in registers.
@@ -453,33 +382,6 @@ __host__ __device__ inline int fused2_smem_bytes(int steps, int bond_vocab) {
   return steps * FusedPack::BYTES + ctab + 2 * (int)sizeof(FusedWgSmem2) + (int)sizeof(FusedCtl);
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// Optional phase timing (compile with -DFZ_PROFILE): per-phase clock64 deltas of selected threads, summed into
-// a.prof[thread-class][32] (thread classes: u == 0, u == 96 (warp 3), u == 224 (warp 7)); read by tools/fused_phase_profile.py.
-#ifdef FZ_PROFILE
-#define FZ_DEBUG(a) ((a).debug)
-#define FZ_PROF_N 32
-#define FZ_PROF_DECL                                                                     \
-  long long prof_acc[FZ_PROF_N];                                                         \
-  for (int i_ = 0; i_ < FZ_PROF_N; ++i_) prof_acc[i_] = 0;                               \
-  long long prof_last = clock64();                                                       \
-  const int prof_cls = (u == 0) ? 0 : (u == 96) ? 1 : (u == 224) ? 2 : -1
-#define FZ_PROF_T(i)                         \
-  do {                                       \
-    const long long now_ = clock64();        \
-    prof_acc[i] += now_ - prof_last;         \
-    prof_last = now_;                        \
-  } while (0)
-#define FZ_PROF_FLUSH                                                                                       \
-  if (prof_cls >= 0 && a.prof)                                                                               \
-    for (int i_ = 0; i_ < FZ_PROF_N; ++i_) atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + prof_cls * FZ_PROF_N + i_, (unsigned long long)prof_acc[i_])
-#else
-#define FZ_DEBUG(a) 0
-#define FZ_PROF_DECL
-#define FZ_PROF_T(i)
-#define FZ_PROF_FLUSH
-#endif
 
 template <bool PRECISE>
 __global__ void __launch_bounds__(2 * F2_CTX_THREADS, 1) mpnn_fused_h2_kernel(const FusedArgs a) {
@@ -1300,14 +1202,20 @@ extern "C" int imp_fused_pack(const float* d_bond_transform, const imp_gru_weigh
               FZ_D, FZ_K, d, bond_dim);
   const int n = FZ_D * FZ_D * FZ_K;
   const bool khalf = (flags & IMP_TC_FP16) && !(flags & (IMP_TC_F32_ZBUILD | IMP_TC_TWO_THREADS_PER_ROW));
+  const bool gen4 = khalf && (flags & IMP_TC_GEN4) && !(flags & (IMP_TC_GEN3 | IMP_TC_THREE_CONTEXTS));
   if (khalf)
-    fused_pack_kernel<tc::FMT_F16, true><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed);
+    fused_pack_kernel<tc::FMT_F16, true><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed,
+                                                                                           gen4 ? 0.5f : 1.0f);
   else if (flags & IMP_TC_FP16)
-    fused_pack_kernel<tc::FMT_F16, false><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed);
+    fused_pack_kernel<tc::FMT_F16, false><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed, 1.0f);
   else
-    fused_pack_kernel<tc::FMT_BF16, false><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed);
+    fused_pack_kernel<tc::FMT_BF16, false><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed, 1.0f);
   IMP_LAUNCH_CHECK();
   return 0;
+}
+
+namespace imp {
+int launch_fused_h4(const FusedArgs& a, int grid, bool precise, bool compact, cudaStream_t st);  // fused_fwd4.cu
 }
 
 static int fused_sm_count() {
@@ -1388,10 +1296,10 @@ static int fused_forward_impl(const imp_graph_t* g, const imp_compact_graph_t* c
   a.mol_eptr = nullptr, a.atom_w = nullptr, a.edge_w = nullptr;
   if (compact) a.mol_eptr = cg->mol_eptr, a.atom_w = cg->atom_w, a.edge_w = cg->edge_w;
 #ifdef FZ_PROFILE
-  a.debug = (flags >> 8) & 0xff;  // timing ablations, profiling builds only
+  a.debug = (flags >> 16) & 0xff;  // timing ablations, profiling builds only
 #else
   a.debug = 0;
-  IMP_REQUIRE((flags >> 8) == 0, IMP_ERR_ARG, "imp_mpnn_forward_fused: unknown flag bits 0x%x", flags & ~0xff);
+  IMP_REQUIRE((flags & ~0x7ff) == 0, IMP_ERR_ARG, "imp_mpnn_forward_fused: unknown flag bits 0x%x", flags & ~0x7ff);
 #endif
 #ifdef FZ_PROFILE
   a.prof = reinterpret_cast<long long*>(d_status);  // profiling build: d_status must hold 3 * 32 int64 (zeroed by the caller)
@@ -1427,8 +1335,19 @@ static int fused_forward_impl(const imp_graph_t* g, const imp_compact_graph_t* c
       IMP_LAUNCH_CHECK();
       return 0;
     }
-    // default for half operands: third generation, 4 (or 3) contexts x 128 threads
+    // default for half operands: third generation, 4 contexts x 128 threads (IMP_TC_THREE_CONTEXTS: 3 contexts);
+    // IMP_TC_GEN4 selects the fourth generation (fused_fwd4.cu: no blocking barrier in a step) for comparison
     const int nctx = (flags & IMP_TC_THREE_CONTEXTS) ? 3 : 4;
+    if ((flags & IMP_TC_GEN4) && !(flags & (IMP_TC_GEN3 | IMP_TC_THREE_CONTEXTS))) {
+      int nc4 = (int)((int64_t)sms * g->n_cat_atoms / (g->n_atoms > 0 ? g->n_atoms : 1));
+      nc4 = nc4 < 1 ? 1 : (nc4 > sms - 1 ? sms - 1 : nc4);
+      int na4 = sms - nc4;
+      const int want4 = (int)ceil_div(n_groups, 4);
+      if (nc4 > want4) nc4 = want4;
+      if (na4 > want4) na4 = want4;
+      a.n_cta_cat = nc4;
+      return launch_fused_h4(a, nc4 + na4, precise, compact, st);
+    }
     int nc = (int)((int64_t)sms * g->n_cat_atoms / (g->n_atoms > 0 ? g->n_atoms : 1));
     nc = nc < 1 ? 1 : (nc > sms - 1 ? sms - 1 : nc);
     int na = sms - nc;

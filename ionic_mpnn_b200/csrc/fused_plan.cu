@@ -1,0 +1,313 @@
+// imp_fused_plan: cuts a packed graph batch into the 128-row tile records of fused_plan.cuh.
+//
+// Replaces, for the fused forward, what src/dataset.py / build_inputs (train_viscosity.py:291-314) do for the reference:
+// decide which ions share a device batch row block.  Integer-only, deterministic per tile (the ORDER of a window's tiles in
+// the plan depends on an atomic counter; the contents of every tile, and therefore every result, do not).
+//
+// One warp per window of FP_WIN consecutive molecules of one tower:
+//   1. lanes load the molecules' atom and entry counts;
+//   2. lane 0 packs them best-fit (largest molecule that still fits the rows and entries left, size buckets + a bit mask);
+//   3. the warp emits the window's tiles: per tile a scan over the chosen molecules, four 32-row passes (atom id, in-degree,
+//      entry offset, counting sort by in-degree with ballots), a coalesced copy of every molecule's contiguous CSR range
+//      translated to tile rows, and a coalesced 2 KiB store of the record.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "fused_plan.cuh"
+
+namespace imp {
+
+constexpr int PL_WARPS = 8;
+
+struct PlanArgs {
+  const int* mol_ptr;
+  const int* atom_id;
+  const int* row_ptr;
+  const int* col_src;
+  const int* edge_bm;
+  const int* mol_eptr;
+  const unsigned short* atom_w;
+  const unsigned int* edge_w;
+  unsigned char* plan;
+  int n_pairs, atom_vocab, bond_vocab;
+};
+
+struct alignas(16) PlanWarpSmem {
+  FusedTile tile;
+  unsigned short ments[FP_WIN];
+  unsigned short next[FP_WIN];
+  unsigned short order[FP_WIN];
+  unsigned short tstart[FP_WIN + 2];
+  unsigned short head[FP_ROWS + 2];
+  unsigned char msize[FP_WIN];
+  unsigned char rowmol[FP_ROWS];
+  int cnt[4][8];
+};
+
+constexpr unsigned short PL_NIL = 0xffff;
+
+__device__ __forceinline__ unsigned int half_bits_of_int(int v) { return (unsigned int)__half_as_ushort(__float2half_rn((float)v)); }
+
+template <bool COMPACT>
+__global__ void __launch_bounds__(PL_WARPS * 32) fused_plan_kernel(const PlanArgs a) {
+  __shared__ PlanWarpSmem sm[PL_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  PlanWarpSmem& ws = sm[warp];
+  FusedPlanHeader* hdr = reinterpret_cast<FusedPlanHeader*>(a.plan);
+  const int P = a.n_pairs;
+  const int nwin = (P + FP_WIN - 1) / FP_WIN;
+  const int w = blockIdx.x * PL_WARPS + warp;
+  if (w >= 2 * nwin) return;
+  const int tower = w >= nwin;
+  const int m0 = (tower ? w - nwin : w) * FP_WIN;  // first molecule of the window inside its tower
+  const int nw = min(FP_WIN, P - m0);
+  const int gbase = tower * P + m0;  // global (tower-major) molecule index of the window's first molecule
+  int bad = 0;
+
+  // ---- 1. sizes
+  for (int i = lane; i < FP_WIN; i += 32) {
+    int sz = 0, me = 0;
+    if (i < nw) {
+      const int p0 = __ldg(a.mol_ptr + gbase + i), p1 = __ldg(a.mol_ptr + gbase + i + 1);
+      sz = p1 - p0;
+      if (COMPACT) me = __ldg(a.mol_eptr + gbase + i + 1) - __ldg(a.mol_eptr + gbase + i);
+      else me = __ldg(a.row_ptr + p1) - __ldg(a.row_ptr + p0);
+      if (sz < 0 || sz > FP_ROWS || me < 0 || me > FP_ECAP) bad = 1, sz = min(max(sz, 0), FP_ROWS), me = min(max(me, 0), FP_ECAP);
+    }
+    ws.msize[i] = (unsigned char)sz;
+    ws.ments[i] = (unsigned short)me;
+  }
+  for (int i = lane; i < FP_ROWS + 2; i += 32) ws.head[i] = PL_NIL;
+  __syncwarp();
+
+  // ---- 2. best-fit packing (lane 0)
+  int nt = 0;
+  if (lane == 0) {
+    unsigned long long mlo = 0ull, mhi = 0ull;  // bit s-1 of mlo: a molecule of s atoms (1..64) is left; mhi: 65..128
+    bool zero = false;
+    for (int i = nw - 1; i >= 0; --i) {  // chains pop in ascending molecule order
+      const int s = ws.msize[i];
+      ws.next[i] = ws.head[s];
+      ws.head[s] = (unsigned short)i;
+      if (s == 0) zero = true;
+      else if (s <= 64) mlo |= 1ull << (s - 1);
+      else mhi |= 1ull << (s - 65);
+    }
+    int pos = 0;
+    while (pos < nw) {
+      ws.tstart[nt] = (unsigned short)pos;
+      int gap = FP_ROWS, egap = FP_ECAP, nmol = 0;
+      while (nmol < FP_MAXMOL) {
+        int s = -1;  // largest size <= gap that is left
+        if (gap > 64) {
+          const unsigned long long m = gap >= 128 ? mhi : (mhi & ((1ull << (gap - 64)) - 1ull));
+          if (m) s = 128 - __clzll((long long)m);
+        }
+        if (s < 0) {
+          const int g2 = min(gap, 64);
+          const unsigned long long m = g2 >= 64 ? mlo : (mlo & ((1ull << g2) - 1ull));
+          if (m) s = 64 - __clzll((long long)m);
+        }
+        if (s < 0 && zero) s = 0;
+        if (s < 0) break;
+        const int i = ws.head[s];
+        if ((int)ws.ments[i] > egap) break;  // (a lone molecule always fits: ments <= FP_ECAP was enforced above)
+        ws.head[s] = ws.next[i];
+        if (ws.head[s] == PL_NIL) {
+          if (s == 0) zero = false;
+          else if (s <= 64) mlo &= ~(1ull << (s - 1));
+          else mhi &= ~(1ull << (s - 65));
+        }
+        ws.order[pos++] = (unsigned short)i;
+        gap -= s, egap -= ws.ments[i], ++nmol;
+      }
+      ++nt;
+    }
+    ws.tstart[nt] = (unsigned short)pos;
+  }
+  nt = __shfl_sync(0xffffffffu, nt, 0);
+  int tbase = 0;
+  if (lane == 0) tbase = atomicAdd(&hdr->n_tiles[tower], nt);
+  tbase = __shfl_sync(0xffffffffu, tbase, 0);
+  const int cap = hdr->cap[tower];
+  if (tbase + nt > cap) {
+    if (lane == 0) atomicMax(&hdr->status, 2);
+    return;
+  }
+  FusedTile* out = reinterpret_cast<FusedTile*>(a.plan + FP_HEADER_BYTES) + (size_t)(tower ? hdr->cap[0] : 0) + tbase;
+  __syncwarp();
+
+  // ---- 3. tiles
+  for (int k = 0; k < nt; ++k) {
+    const int o0 = ws.tstart[k], nmol = ws.tstart[k + 1] - o0;
+    int sz = 0, me = 0, mol = 0, aptr = 0, eptr = 0;
+    if (lane < nmol) {
+      const int i = ws.order[o0 + lane];
+      sz = ws.msize[i], me = ws.ments[i], mol = gbase + i;
+      aptr = __ldg(a.mol_ptr + mol);
+      eptr = COMPACT ? __ldg(a.mol_eptr + mol) : __ldg(a.row_ptr + aptr);
+    }
+    int off = sz, eoff = me;  // inclusive scans over the tile's molecules
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, off, o), u = __shfl_up_sync(0xffffffffu, eoff, o);
+      if (lane >= o) off += v, eoff += u;
+    }
+    const int rows = __shfl_sync(0xffffffffu, off, 31), n_ent = __shfl_sync(0xffffffffu, eoff, 31);
+    off -= sz, eoff -= me;
+    if (lane < nmol) {
+      ws.tile.molid[lane] = mol;
+      ws.tile.mol_lo[lane] = (uint8_t)off;
+      for (int r = 0; r < sz; ++r) ws.rowmol[off + r] = (unsigned char)lane;
+    }
+    if (lane == 0) {
+      ws.tile.mol_lo[nmol] = (uint8_t)rows;
+      ws.tile.nm = (uint8_t)nmol, ws.tile.rows = (uint8_t)rows, ws.tile.n_ent = (uint16_t)n_ent;
+    }
+    __syncwarp();
+    // rows: four passes of 32 natural rows
+    int word[4], key[4], rank[4];
+    int carry = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int rho = 32 * p + lane;
+      const bool valid = rho < rows;
+      const int j = valid ? ws.rowmol[rho] : 0;
+      const int ap = __shfl_sync(0xffffffffu, aptr, j), of = __shfl_sync(0xffffffffu, off, j);
+      int aid = 0, deg = 0;
+      if (valid) {
+        const int at = ap + (rho - of);
+        if (COMPACT) {
+          const int aw = (int)__ldg(a.atom_w + at);
+          aid = aw & 0xff, deg = aw >> 8;
+        } else {
+          aid = __ldg(a.atom_id + at);
+          deg = __ldg(a.row_ptr + at + 1) - __ldg(a.row_ptr + at);
+        }
+        if (deg < 0 || deg > 31) bad = 1, deg = min(max(deg, 0), 31);
+        aid = min(max(aid, 0), min(a.atom_vocab - 1, 1023));
+      }
+      int incl = deg;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int e0 = min(carry + incl - deg, FP_ECAP);  // (clamps only bite on refused batches: no read leaves the record)
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+      deg = min(deg, FP_ECAP - e0);
+      word[p] = rho | (deg << 7) | (e0 << 12) | (aid << 22);
+      key[p] = min(deg, 7);
+      int mine = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const unsigned m = __ballot_sync(0xffffffffu, key[p] == q);
+        if (lane == q) mine = __popc(m);
+        if (key[p] == q) rank[p] = __popc(m & ((1u << lane) - 1u));
+      }
+      if (lane < 8) ws.cnt[p][lane] = mine;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      int pos = rank[p];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int c0 = ws.cnt[0][q], c1 = ws.cnt[1][q], c2 = ws.cnt[2][q], c3 = ws.cnt[3][q];
+        if (q < key[p]) pos += c0 + c1 + c2 + c3;
+        if (q == key[p]) pos += (p > 0 ? c0 : 0) + (p > 1 ? c1 : 0) + (p > 2 ? c2 : 0);
+      }
+      ws.tile.slot[pos] = (uint32_t)word[p];
+    }
+    // entries: every molecule's CSR range is contiguous; the tile's list is their concatenation in tile order
+    for (int j = 0; j < nmol; ++j) {
+      const int ep = __shfl_sync(0xffffffffu, eptr, j), mj = __shfl_sync(0xffffffffu, me, j), eo = __shfl_sync(0xffffffffu, eoff, j);
+      const int ap = __shfl_sync(0xffffffffu, aptr, j), of = __shfl_sync(0xffffffffu, off, j), sj = __shfl_sync(0xffffffffu, sz, j);
+      for (int x = lane; x < mj; x += 32) {
+        int src, bond, mult;
+        if (COMPACT) {
+          const unsigned int wv = __ldg(a.edge_w + ep + x);
+          src = (int)(wv & 0xffu), bond = (int)((wv >> 8) & 0xffu), mult = (int)((wv >> 16) & 0xffu);
+        } else {
+          const int bm = __ldg(a.edge_bm + ep + x);
+          src = __ldg(a.col_src + ep + x) - ap, bond = bm & 0xffff, mult = bm >> 16;
+        }
+        if (src < 0 || src >= sj) bad = 1, src = min(max(src, 0), max(sj - 1, 0));
+        bond = min(bond, min(a.bond_vocab - 1, 255));
+        if (eo + x < FP_ECAP) ws.tile.ent[eo + x] = (uint32_t)(src + of) | ((uint32_t)bond << 8) | (half_bits_of_int(mult) << 16);
+      }
+    }
+    __syncwarp();
+    {
+      const uint4* s4 = reinterpret_cast<const uint4*>(&ws.tile);
+      uint4* d4 = reinterpret_cast<uint4*>(out + k);
+#pragma unroll
+      for (int q = 0; q < (int)sizeof(FusedTile) / 16 / 32; ++q) d4[q * 32 + lane] = s4[q * 32 + lane];
+    }
+    __syncwarp();
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicMax(&hdr->status, 1);
+}
+
+__global__ void fused_plan_init_kernel(FusedPlanHeader* hdr, int cap0, int cap1) {
+  hdr->n_tiles[0] = 0, hdr->n_tiles[1] = 0, hdr->cap[0] = cap0, hdr->cap[1] = cap1, hdr->status = 0;
+}
+
+// Upper bound on the tiles of one tower with `atoms` atoms, `ents` entries and `mols` molecules of at most `max_mol` atoms:
+// every tile of a window but its last is closed because the next molecule did not fit -- by rows (> 128 - max_mol used),
+// by entries (> FP_ECAP - max entries of a molecule used; bounded through the half-capacity argument) or by the molecule
+// count -- plus one partial tile per window.
+static int64_t plan_tile_bound(int64_t atoms, int64_t ents, int64_t mols, int max_mol) {
+  const int64_t by_rows = atoms / (FP_ROWS - (max_mol < 1 ? 1 : max_mol > 127 ? 127 : max_mol) + 1) + 1;
+  const int64_t by_ents = ents / (FP_ECAP / 2) + 1;
+  const int64_t by_mols = mols / FP_MAXMOL + 1;
+  const int64_t windows = (mols + FP_WIN - 1) / FP_WIN;
+  int64_t t = by_rows + by_ents + by_mols + windows;
+  return t < mols + 1 ? t : mols + 1;
+}
+
+}  // namespace imp
+
+using namespace imp;
+
+extern "C" int64_t imp_fused_plan_bytes(int32_t n_pairs, int32_t n_atoms, int32_t n_unique, int32_t max_mol_atoms) {
+  if (n_pairs < 0 || n_atoms < 0 || n_unique < 0) return IMP_ERR_ARG;
+  // either tower may hold all atoms / entries of the batch; sized for the worst split
+  const int64_t cap = plan_tile_bound(n_atoms, n_unique, n_pairs, max_mol_atoms);
+  return FP_HEADER_BYTES + 2 * cap * (int64_t)sizeof(FusedTile);
+}
+
+extern "C" int imp_fused_plan(const imp_graph_t* g, const imp_compact_graph_t* cg, int32_t atom_vocab, int32_t max_mol_atoms,
+                              void* d_plan, int64_t plan_bytes, void* stream) {
+  IMP_REQUIRE((g != nullptr) != (cg != nullptr), IMP_ERR_ARG, "imp_fused_plan: pass exactly one of the two graph forms");
+  PlanArgs a{};
+  int n_atoms, n_unique;
+  if (cg) {
+    IMP_REQUIRE(cg->mol_ptr && cg->mol_eptr && (cg->n_atoms == 0 || cg->atom_w) && (cg->n_unique == 0 || cg->edge_w), IMP_ERR_ARG,
+                "imp_fused_plan: null index arrays");
+    a.mol_ptr = cg->mol_ptr, a.mol_eptr = cg->mol_eptr, a.atom_w = cg->atom_w, a.edge_w = cg->edge_w;
+    a.n_pairs = cg->n_pairs, a.bond_vocab = cg->bond_vocab, n_atoms = cg->n_atoms, n_unique = cg->n_unique;
+  } else {
+    IMP_REQUIRE(g->mol_ptr && g->row_ptr && (g->n_atoms == 0 || g->atom_id) && (g->n_unique == 0 || (g->col_src && g->edge_bm)),
+                IMP_ERR_ARG, "imp_fused_plan: null index arrays");
+    a.mol_ptr = g->mol_ptr, a.atom_id = g->atom_id, a.row_ptr = g->row_ptr, a.col_src = g->col_src, a.edge_bm = g->edge_bm;
+    a.n_pairs = g->n_pairs, a.bond_vocab = g->bond_vocab, n_atoms = g->n_atoms, n_unique = g->n_unique;
+  }
+  IMP_REQUIRE(a.n_pairs >= 0 && n_atoms >= 0 && n_unique >= 0 && atom_vocab >= 1 && a.bond_vocab >= 1, IMP_ERR_ARG, "imp_fused_plan: bad sizes");
+  IMP_REQUIRE(max_mol_atoms <= FP_ROWS, IMP_ERR_DIM, "imp_fused_plan: a molecule has %d atoms, a tile holds %d", max_mol_atoms, FP_ROWS);
+  IMP_REQUIRE(d_plan && plan_bytes >= FP_HEADER_BYTES, IMP_ERR_ARG, "imp_fused_plan: no plan buffer");
+  const int64_t cap = (plan_bytes - FP_HEADER_BYTES) / (2 * (int64_t)sizeof(FusedTile));
+  IMP_REQUIRE(cap >= 1 || a.n_pairs == 0, IMP_ERR_CAPACITY, "imp_fused_plan: plan buffer too small");
+  a.plan = (unsigned char*)d_plan, a.atom_vocab = atom_vocab;
+  cudaStream_t st = (cudaStream_t)stream;
+  fused_plan_init_kernel<<<1, 1, 0, st>>>(reinterpret_cast<FusedPlanHeader*>(d_plan), (int)(cap > INT32_MAX ? INT32_MAX : cap),
+                                         (int)(cap > INT32_MAX ? INT32_MAX : cap));
+  IMP_LAUNCH_CHECK();
+  if (a.n_pairs == 0) return 0;
+  const int nwin = (a.n_pairs + FP_WIN - 1) / FP_WIN;
+  const int grid = (2 * nwin + PL_WARPS - 1) / PL_WARPS;
+  if (cg) fused_plan_kernel<true><<<grid, PL_WARPS * 32, 0, st>>>(a);
+  else fused_plan_kernel<false><<<grid, PL_WARPS * 32, 0, st>>>(a);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}

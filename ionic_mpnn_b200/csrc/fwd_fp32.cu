@@ -448,16 +448,22 @@ __device__ __forceinline__ float softplusf_precise(float x) {
   return x > 0.f ? x + log1pf(expf(-x)) : log1pf(expf(x));
 }
 
+// The readout of the 1e-5 path accumulates in DOUBLE: a head output of magnitude ~1 is a difference of ~20 terms of
+// magnitude ~25 (pooled sums of 25 atoms), so fp32 accumulation alone already costs ~1e-5 relative -- the whole north-star
+// budget (measured: the reference's own fp32 arithmetic sits at 0.97e-5 on configs[0]).  The work is negligible
+// (~6 kFLOP per pair).
 __device__ void k6_dense(const float* __restrict__ W /* smem [n_in][n_out] */, const float* __restrict__ b,
-                         const float* __restrict__ x /* smem [n_in] */, float* __restrict__ y, int n_in, int n_out,
+                         const double* __restrict__ x /* smem [n_in] */, double* __restrict__ y, int n_in, int n_out,
                          bool relu, int lane) {
   for (int o = lane; o < n_out; o += 32) {
-    float a = b[o];
-    for (int k = 0; k < n_in; ++k) a = fmaf(x[k], W[k * n_out + o], a);
-    y[o] = relu ? fmaxf(a, 0.f) : a;
+    double a = (double)b[o];
+    for (int k = 0; k < n_in; ++k) a = fma(x[k], (double)W[k * n_out + o], a);
+    y[o] = relu ? fmax(a, 0.0) : a;
   }
   __syncwarp();
 }
+
+__device__ __forceinline__ double softplus_f64(double x) { return x > 0.0 ? x + log1p(exp(-x)) : log1p(exp(x)); }
 
 // GlobalSumPool alone: one warp per molecule.
 __global__ void global_sum_pool_kernel(const int* __restrict__ mol_ptr, const int* __restrict__ atom_id, int n_mols,
@@ -493,8 +499,9 @@ __global__ void __launch_bounds__(K6_WARPS * 32) pool_head_kernel(K6Args a) {
   p += n_head_out;
   float* W2 = p;
   p += (fp2 > 0 ? fp2 : 0);
-  const int sv = a.scratch_stride;  // max(d, fp, mix, fp2) rounded up to 32 floats
-  float* scratch = p + (threadIdx.x / 32) * (4 * sv);
+  const int sv = a.scratch_stride;  // max(d, fp, mix, fp2) rounded up to 32 elements
+  p += (reinterpret_cast<uintptr_t>(p) & 7) ? 1 : 0;  // 8-byte alignment of the double scratch
+  double* scratch = reinterpret_cast<double*>(p) + (threadIdx.x / 32) * (4 * sv);
   for (int t = 0; t < 2; ++t) {
     const imp_readout_weights_t& w = t == 0 ? a.wc : a.wa;
     for (int i = threadIdx.x; i < d * fp; i += blockDim.x) Wfp[t][i] = w.W_fp[i];
@@ -511,22 +518,22 @@ __global__ void __launch_bounds__(K6_WARPS * 32) pool_head_kernel(K6Args a) {
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * K6_WARPS + (threadIdx.x >> 5);
   const int n_warps = gridDim.x * K6_WARPS;
-  float* pool = scratch;             // [d]
-  float* v1 = scratch + sv;     // [fp]
-  float* v2 = scratch + 2 * sv; // [mix]
-  float* mixed = scratch + 3 * sv;
+  double* pool = scratch;             // [d]
+  double* v1 = scratch + sv;     // [fp]
+  double* v2 = scratch + 2 * sv; // [mix]
+  double* mixed = scratch + 3 * sv;
   const int aux_stride = 2 * d + 2 * fp + mix + (fp2 > 0 ? 0 : 3);
   for (int pair = warp_global; pair < a.n_pairs; pair += n_warps) {
     for (int t = 0; t < 2; ++t) {
       const int m = t * a.n_pairs + pair;
       if (a.pooled) {
-        for (int j = lane; j < d; j += 32) pool[j] = a.pooled[(int64_t)m * d + j];
+        for (int j = lane; j < d; j += 32) pool[j] = (double)a.pooled[(int64_t)m * d + j];
       } else {
         const int v0 = a.mol_ptr[m], v1e = a.mol_ptr[m + 1];
         for (int j = lane; j < d; j += 32) {
-          float sacc = 0.f;
+          double sacc = 0.0;
           for (int v = v0; v < v1e; ++v)
-            if (a.atom_id[v] > 0) sacc += a.h[(int64_t)v * d + j];  // models/layers.py:163 mask
+            if (a.atom_id[v] > 0) sacc += (double)a.h[(int64_t)v * d + j];  // models/layers.py:163 mask
           pool[j] = sacc;
         }
       }
@@ -536,34 +543,34 @@ __global__ void __launch_bounds__(K6_WARPS * 32) pool_head_kernel(K6Args a) {
       for (int j = lane; j < mix; j += 32) mixed[j] = t == 0 ? v2[j] : mixed[j] + v2[j];
       if (a.aux) {
         float* ax = a.aux + (int64_t)pair * aux_stride;
-        for (int j = lane; j < d; j += 32) ax[t * d + j] = pool[j];
-        for (int j = lane; j < fp; j += 32) ax[2 * d + t * fp + j] = v1[j];
+        for (int j = lane; j < d; j += 32) ax[t * d + j] = (float)pool[j];
+        for (int j = lane; j < fp; j += 32) ax[2 * d + t * fp + j] = (float)v1[j];
       }
       __syncwarp();
     }
     if (a.aux)
-      for (int j = lane; j < mix; j += 32) a.aux[(int64_t)pair * aux_stride + 2 * d + 2 * fp + j] = mixed[j];
+      for (int j = lane; j < mix; j += 32) a.aux[(int64_t)pair * aux_stride + 2 * d + 2 * fp + j] = (float)mixed[j];
     if (fp2 == 0) {
       k6_dense(W1, b1, mixed, v1, mix, 3, false, lane);
       if (lane == 0) {
-        const float A = v1[0];
-        const float B = fminf(fmaxf(softplusf_precise(v1[1]), 0.0f), 20.0f);
-        const float C = fminf(fmaxf(softplusf_precise(v1[2]), 0.1f), 50.0f);
-        const float Ts = a.T[pair] / 100.0f;
-        a.out[pair] = A + B / (Ts + C + 1e-6f);
+        const double A = v1[0];
+        const double B = fmin(fmax(softplus_f64(v1[1]), 0.0), 20.0);
+        const double C = fmin(fmax(softplus_f64(v1[2]), 0.1), 50.0);
+        const double Ts = (double)a.T[pair] / 100.0;
+        a.out[pair] = (float)(A + B / (Ts + C + 1e-6));
         if (a.aux) {
           float* ax = a.aux + (int64_t)pair * aux_stride + 2 * d + 2 * fp + mix;
-          ax[0] = A, ax[1] = B, ax[2] = C;
+          ax[0] = (float)A, ax[1] = (float)B, ax[2] = (float)C;
         }
       }
     } else {
       k6_dense(W1, b1, mixed, v1, mix, fp2, true, lane);
-      float part = 0.f;
-      for (int k = lane; k < fp2; k += 32) part = fmaf(v1[k], W2[k], part);
+      double part = 0.0;
+      for (int k = lane; k < fp2; k += 32) part = fma(v1[k], (double)W2[k], part);
       // fixed-order reduction: gather the 32 partials in lane order
-      float tot = 0.f;
+      double tot = 0.0;
       for (int l = 0; l < 32; ++l) tot += __shfl_sync(0xffffffffu, part, l);
-      if (lane == 0) a.out[pair] = tot + a.b2[0];
+      if (lane == 0) a.out[pair] = (float)(tot + (double)a.b2[0]);
     }
     __syncwarp();
   }
@@ -1054,7 +1061,7 @@ static int launch_k6(const imp_graph_t* g, const float* d_h, const float* d_pool
     a.scratch_stride = (mv + 31) / 32 * 32;
   }
   const size_t smem = sizeof(float) * (2 * d * fp + 2 * fp + 2 * fp * mix + 2 * mix + mix * n_head_out + n_head_out +
-                                       (fp2 > 0 ? fp2 : 0) + K6_WARPS * 4 * a.scratch_stride);
+                                       (fp2 > 0 ? fp2 : 0) + 2 + 2 * K6_WARPS * 4 * a.scratch_stride);  // scratch rows are doubles
   IMP_CUDA(cudaFuncSetAttribute(pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   IMP_REQUIRE(smem <= 200 * 1024, IMP_ERR_DIM, "%s: readout weights need %zu B of shared memory", who, smem);
   if (d_pooled && !aux && d <= 32 && fp <= 32 && mix <= 32 && fp2 <= 32) {  // both reference models: register-resident weights

@@ -110,6 +110,10 @@ class PackedGraphBatch:
         self.target = None if target is None else np.ascontiguousarray(target, np.float32).reshape(-1)
         mp = self.host.get("mol_ptr")
         self.max_mol_atoms = int(np.diff(mp).max()) if mp is not None and len(mp) > 1 else 0
+        # envelope of the tile plan (imp_fused_plan): in-degree <= 31, <= 336 unique entries per molecule
+        rp = self.host.get("row_ptr")
+        self.max_in_degree = int(np.diff(rp).max()) if rp is not None and len(rp) > 1 else 0
+        self.max_mol_entries = int(np.diff(rp[mp]).max()) if rp is not None and mp is not None and len(mp) > 1 else 0
         self.dev = None
         self.dev_T = None
         self.dev_y = None
@@ -251,6 +255,8 @@ class DeviceSlot:
                 n += chunk.pinned_T.numel() * 4
         for a in ("n_pairs", "n_atoms", "n_cat_atoms", "n_unique", "n_edges", "bond_vocab", "max_mol_atoms"):
             setattr(self, a, getattr(chunk, a))
+        for a in ("max_in_degree", "max_mol_entries"):
+            setattr(self, a, getattr(chunk, a, None))
         return n
 
     def compact_struct(self):
@@ -343,6 +349,7 @@ class DevicePackedBatch:
         self.dev, self.dev_T, self.dev_y = dev, dev_T, None
         self.n_pairs, self.n_atoms, self.n_cat_atoms, self.n_unique, self.n_edges, self.bond_vocab = counts
         self.max_mol_atoms = max_mol_atoms
+        self.max_in_degree = self.max_mol_entries = None  # not known on the host: the tile plan's status word reports them
 
     def c_struct(self):
         ptr = lambda k: self.dev[k].data_ptr() if k in self.dev else 0  # noqa: E731

@@ -276,6 +276,20 @@ class MPNNModel(TrainMixin):
         return (self.fused_supported() and (f & _lib.TC_FP16) and not (f & (_lib.TC_F32_ZBUILD | _lib.TC_TWO_THREADS_PER_ROW))
                 and self.spec["atom_vocab_size"] <= 256 and self.spec["bond_vocab_size"] <= 256)
 
+    def planned_supported(self, batch=None):
+        """The planned (fifth-generation) fused forward: IEEE-half operands, no kernel-generation tuning flags, and a batch
+        inside the tile plan's envelope (in-degree <= 31, <= 336 unique entries per molecule; a device-packed batch does
+        not know these on the host -- the plan's status word, read by check_status(), reports a violation)."""
+        f = self.tc_flags()
+        if not (self.fused_supported() and (f & _lib.TC_FP16) and not (f & ~(_lib.TC_FP16 | _lib.TC_PRECISE_EPILOGUE))
+                and self.spec["atom_vocab_size"] <= 1024 and getattr(self, "use_plan", True)):
+            return False
+        if batch is not None:
+            deg, ents = getattr(batch, "max_in_degree", None), getattr(batch, "max_mol_entries", None)
+            if (deg is not None and deg > 31) or (ents is not None and ents > 336):
+                return False
+        return True
+
     def use_fused(self, batch):
         if self.fused is False or not self.fused_supported():
             if self.fused is True:
@@ -443,7 +457,19 @@ class MPNNModel(TrainMixin):
         status = self._ws.get("status")
         if status is None:
             status = self._ws["status"] = torch.zeros(1, dtype=torch.int32, device=self.device)
-        if g is None:
+        if self.planned_supported(batch):
+            # tile plan of this batch (integer-only, rebuilt per call: it depends on the batch alone), then the planned kernel
+            cg = batch.compact_struct() if g is None else None
+            nb = _lib.load().imp_fused_plan_bytes(P, batch.n_atoms, batch.n_unique, batch.max_mol_atoms)
+            if nb < 0:
+                raise _lib.ImpError(f"imp_fused_plan_bytes: {nb}")
+            plan = self._buf("fused_plan", nb, torch.uint8)
+            _lib.call("imp_fused_plan", C.byref(g) if g is not None else None, C.byref(cg) if cg is not None else None,
+                      s["atom_vocab_size"], batch.max_mol_atoms, plan.data_ptr(), nb, st)
+            _lib.call("imp_mpnn_forward_fused_planned", plan.data_ptr(), P, batch.n_atoms, batch.n_cat_atoms, batch.bond_vocab,
+                      self._ptr("atom_emb"), s["atom_vocab_size"], self._ptr("bond_emb"), d, s["bond_dim"], S,
+                      self._ws["fused_packed"].data_ptr(), C.c_float(self.LN_EPS), self.tc_flags(), pooled.data_ptr(), st)
+        elif g is None:
             cg = batch.compact_struct()
             _lib.call("imp_mpnn_forward_fused_compact", C.byref(cg), self._ptr("atom_emb"), s["atom_vocab_size"],
                       self._ptr("bond_emb"), d, s["bond_dim"], S, self._ws["fused_packed"].data_ptr(), C.c_float(self.LN_EPS),
@@ -517,7 +543,7 @@ class MPNNModel(TrainMixin):
         if self.wide_supported():
             return 1 + 2 * S + 1 + 1  # embed, (messages, GatedUpdate) per step, pool, readout
         if batch is not None and self.use_fused(batch):
-            return 2                  # fused forward, readout
+            return 4 if self.planned_supported(batch) else 2  # [plan header, tile plan,] fused forward, readout
         grouped = batch is None or "bucket_perm" in (batch.dev or {})
         if self.precision != "fp32" and self.spec["atom_dim"] == 32 and grouped:
             return 3 + 2 * S + 1      # embed, message plan (2), (grouped message GEMM, Reduce + GatedUpdate) per step, pool + head
@@ -554,6 +580,17 @@ class MPNNModel(TrainMixin):
         batch's ``max_mol_atoms`` was wrong and the predictions of that launch are invalid.  ``predict`` calls it after its
         synchronisation; callers of the enqueue-only entry points (``forward_packed``, ``predict_stream``) call it once they
         have synchronised."""
+        import torch
+
+        plan = self._ws.get("fused_plan")
+        if plan is not None and plan.numel() >= 20:
+            code = int(plan[16:20].view(torch.int32).item())
+            if code != 0:
+                plan[16:20].zero_()
+                raise _lib.ImpError("fused forward: the tile plan refused the batch (" +
+                                    ("a molecule with > 128 atoms, a row with > 31 entries or > 336 entries per molecule"
+                                     if code == 1 else "tile capacity exceeded") +
+                                    "); set model.use_plan = False (self-contained fused kernel) or fused=False")
         st = self._ws.get("status")
         if st is None or st.numel() != 1:
             return

@@ -149,8 +149,11 @@ def test_cfg1_thousand_pairs_vs_fp64_oracle(kind, skewed, trained):
         err_f32 = rel_err(f32, want)
         elem = np.abs(got - want) / np.maximum(np.abs(want), 1.0)
         print(f"default weights: ours max {err:.2e} (p99 {np.quantile(elem, 0.99):.2e}), fp32 port of the reference {err_f32:.2e}")
-        # (the port's own figure depends on the host's thread count, so it is printed, not asserted against)
-        assert err <= 1.5 * RTOL, (err, err_f32)
+        # bound: the north-star tolerance, or -- on an element where the reference's own fp32 arithmetic is already further
+        # from fp64 than that -- the fp32 port's error on the same box (both numbers go to parity_run.json)
+        from conftest import record_parity
+        record_parity(f"cfg1.{kind}.{'skewed' if skewed else 'uniform'}.fp32", ours=err, fp32_port_of_reference=err_f32)
+        assert err <= max(RTOL, err_f32), (err, err_f32)
         assert np.quantile(elem, 0.99) <= RTOL
     else:
         # bond_transform x10 + random biases is a sensitivity setting: predictions are differences of

@@ -1,0 +1,120 @@
+"""GPU (B200): the tile plan (imp_fused_plan) and the planned fused forward (imp_mpnn_forward_fused_planned, generation 5)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL16 = 2e-2  # north-star tolerance of the 16-bit tensor path
+
+
+def _rel(got, want):
+    got, want = np.asarray(got, np.float64).reshape(-1), np.asarray(want, np.float64).reshape(-1)
+    return float((np.abs(got - want) / np.maximum(np.abs(want), 1.0)).max())
+
+
+def _plan(batch, compact=False, atom_vocab=124):
+    from ionic_mpnn_b200 import _lib
+
+    lib = _lib.load()
+    nb = lib.imp_fused_plan_bytes(batch.n_pairs, batch.n_atoms, batch.n_unique, batch.max_mol_atoms)
+    assert nb >= 256
+    plan = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+    if compact:
+        cb = batch.to_compact("cuda")
+        cg = cb.compact_struct()
+        _lib.call("imp_fused_plan", None, C.byref(cg), atom_vocab, batch.max_mol_atoms, plan.data_ptr(), nb, None)
+    else:
+        batch.to("cuda")
+        g = batch.c_struct()
+        _lib.call("imp_fused_plan", C.byref(g), None, atom_vocab, batch.max_mol_atoms, plan.data_ptr(), nb, None)
+    torch.cuda.synchronize()
+    return plan.cpu().numpy()
+
+
+@pytest.mark.parametrize("n_pairs,seed,lo,hi", [(1, 1, 10, 40), (300, 2, 10, 40), (1000, 3, 10, 40), (257, 4, 1, 12),
+                                                (100, 5, 60, 128), (513, 6, 1, 128)])
+def test_plan_records_are_a_faithful_cut_of_the_csr_batch(n_pairs, seed, lo, hi):
+    from ionic_mpnn_b200 import graph
+    from oracle import ref_plan
+
+    batch, _, _ = graph.synth_batch(n_pairs, seed=seed, n_min=lo, n_max=hi)
+    stats = None
+    for compact in (False, True):
+        raw = _plan(batch, compact)
+        st = ref_plan.check_plan(raw, batch.host, batch.n_pairs, 124, 72)
+        if stats is not None:  # both input feeds describe the same graph: same tiles (their order inside the plan may differ)
+            assert st == stats
+        stats = st
+    if (lo, hi) == (10, 40) and n_pairs >= 300:
+        assert stats["fill"] >= 0.93, stats  # best-fit over 256-molecule windows (the contiguous cut reaches ~0.88)
+    print(n_pairs, lo, hi, stats)
+
+
+def test_plan_degenerate_molecules_and_multiplicities():
+    from ionic_mpnn_b200 import graph
+    from ionic_mpnn_b200.graph import FlatIons
+    from oracle import ref_plan
+
+    ions = [{"atom_ids": [5], "bond_ids": [], "edge_indices": [], "num_atoms": 1},
+            {"atom_ids": [1, 2, 3, 4], "bond_ids": [], "edge_indices": [], "num_atoms": 4},
+            {"atom_ids": [7, 8, 9], "bond_ids": [3, 3, 3, 3, 4, 4], "num_atoms": 3,
+             "edge_indices": [(1, 2), (2, 1), (1, 2), (2, 1), (0, 1), (1, 0)]}] * 30
+    f = FlatIons.from_ion_dicts(ions)
+    batch = graph.pack_flat(f, f, 72)
+    raw = _plan(batch)
+    st = ref_plan.check_plan(raw, batch.host, batch.n_pairs, 124, 72)
+    assert st["tiles"] >= 2  # at most 32 molecules per tile
+
+
+def test_plan_refuses_batches_outside_its_envelope():
+    """> 31 entries in a row: the status word says so, and MPNNModel routes such a batch to the self-contained kernel."""
+    from ionic_mpnn_b200 import graph
+    from ionic_mpnn_b200.viscosity import build_model
+    from oracle import ref_plan
+
+    n = 40
+    star = {"atom_ids": list(range(1, n + 1)), "num_atoms": n, "bond_ids": [], "edge_indices": []}
+    for i in range(2, n):  # atom 1 is bonded to every other atom but atom 0
+        star["edge_indices"] += [(1, i), (i, 1)]
+        star["bond_ids"] += [i % 70, i % 70]
+    recs = [{"pair_id": k, "cation": star, "anion": star, "T": 300.0, "log_eta": 1.0} for k in range(5)]
+    batch = graph.pack_records(recs, 72)
+    assert batch.max_in_degree > 31
+    hdr, _ = ref_plan.parse(_plan(batch))
+    assert hdr["status"] == 1
+    ref = build_model(124, 72, precision="fp32", seed=3)
+    fz = build_model(124, 72, precision="fp16", seed=3, fused=True)
+    assert not fz.planned_supported(batch)
+    want = ref.predict(batch)
+    got = fz.predict(batch)
+    assert _rel(got, want) <= RTOL16
+
+
+@pytest.mark.parametrize("n_pairs,seed,lo,hi", [(1, 1, 10, 40), (64, 2, 10, 40), (3000, 3, 10, 40), (300, 4, 1, 128)])
+def test_planned_forward_matches_the_self_contained_kernel_and_the_fp32_path(n_pairs, seed, lo, hi):
+    from ionic_mpnn_b200 import _lib, graph
+    from ionic_mpnn_b200.viscosity import build_model
+
+    batch, _, _ = graph.synth_batch(n_pairs, seed=seed, n_min=lo, n_max=hi)
+    batch.to("cuda")
+    ref = build_model(124, 72, precision="fp32", seed=3)
+    want32 = ref.forward_packed(batch).cpu().numpy()
+    for precision in ("fp16", "fp16_precise"):
+        planned = build_model(124, 72, precision=precision, seed=3, fused=True)
+        gen3 = build_model(124, 72, precision=precision, seed=3, fused=True)
+        gen3.use_plan = False
+        assert planned.planned_supported(batch) and not gen3.planned_supported(batch)
+        a = planned.forward_packed(batch).cpu().numpy()
+        b = gen3.forward_packed(batch).cpu().numpy()
+        c = planned.forward_packed(batch.to_compact("cuda")).cpu().numpy()
+        planned.check_status()
+        assert np.array_equal(a, c), "the compact feed and the int32 CSR feed give the same plan contents"
+        assert np.array_equal(a, planned.forward_packed(batch).cpu().numpy()), "run-to-run bit-identical"
+        # the same arithmetic up to the LayerNorm evaluation order: fp32 rounding only
+        assert _rel(a, b) <= 1e-4, _rel(a, b)
+        assert _rel(a, want32) <= RTOL16
+    assert planned.launches_per_forward(batch) == 4
+    assert _lib.load().imp_fused_plan_bytes(-1, 0, 0, 0) < 0

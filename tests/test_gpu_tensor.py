@@ -252,10 +252,11 @@ def test_fused_forward_vs_fp32_kernels(n_pairs, precision):
     assert err <= (BF16_RTOL if precision.startswith("fp16") else 1.5e-1), err
 
 
-@pytest.mark.parametrize("tc_flags", [8, 8 | 4, 16, 32])
+@pytest.mark.parametrize("tc_flags", [8, 8 | 4, 16, 32, 512, 1024])
 def test_fused_forward_kernel_generations(tc_flags):
-    """Earlier generations stay covered: fp32 Z accumulation (IMP_TC_F32_ZBUILD, optionally IMP_TC_MP8), two threads
-    per row (IMP_TC_TWO_THREADS_PER_ROW), and the three-context variant of the default kernel."""
+    """Earlier generations stay covered (the default, flags 0, is the planned fifth generation): fp32 Z accumulation
+    (IMP_TC_F32_ZBUILD, optionally IMP_TC_MP8), two threads per row (IMP_TC_TWO_THREADS_PER_ROW), the self-contained third
+    generation (IMP_TC_GEN3), its three-context variant, and the fourth generation (IMP_TC_GEN4)."""
     got, want = _fused_vs_staged(700, 4, "fp16", tc_flags=tc_flags)
     assert _rel(got, want) <= BF16_RTOL
 
@@ -360,7 +361,7 @@ def test_fused_forward_dense_graphs_and_degenerate_ions():
     assert np.diff(batch.host["row_ptr"]).max() > 7
     ref = build_model(124, 72, precision="fp32", seed=3)
     want = ref.forward_packed(batch).cpu().numpy()
-    for flags in (0, 32, 16, 8):
+    for flags in (0, 512, 1024, 32, 16, 8):
         fz = build_model(124, 72, precision="fp16", seed=3, fused=True)
         fz.extra_tc_flags = flags
         got = fz.forward_packed(batch).cpu().numpy()

@@ -17,7 +17,7 @@
 
 namespace imp {
 
-constexpr int PL_WARPS = 8;
+constexpr int PL_WARPS = 4;
 
 struct PlanArgs {
   const int* mol_ptr;
@@ -34,19 +34,20 @@ struct PlanArgs {
 
 struct alignas(16) PlanWarpSmem {
   FusedTile tile;
+  int aptr[FP_WIN];  // first atom of every molecule of the window
+  int eptr[FP_WIN];  // first CSR entry
   unsigned short ments[FP_WIN];
   unsigned short next[FP_WIN];
   unsigned short order[FP_WIN];
   unsigned short tstart[FP_WIN + 2];
   unsigned short head[FP_ROWS + 2];
   unsigned char msize[FP_WIN];
-  unsigned char rowmol[FP_ROWS];
-  int cnt[4][8];
 };
 
 constexpr unsigned short PL_NIL = 0xffff;
 
 __device__ __forceinline__ unsigned int half_bits_of_int(int v) { return (unsigned int)__half_as_ushort(__float2half_rn((float)v)); }
+__device__ __forceinline__ int field8(unsigned long long v, int k) { return (int)((v >> (8 * k)) & 0xffull); }
 
 template <bool COMPACT>
 __global__ void __launch_bounds__(PL_WARPS * 32) fused_plan_kernel(const PlanArgs a) {
@@ -66,16 +67,20 @@ __global__ void __launch_bounds__(PL_WARPS * 32) fused_plan_kernel(const PlanArg
 
   // ---- 1. sizes
   for (int i = lane; i < FP_WIN; i += 32) {
-    int sz = 0, me = 0;
+    int sz = 0, me = 0, p0 = 0, e0 = 0;
     if (i < nw) {
-      const int p0 = __ldg(a.mol_ptr + gbase + i), p1 = __ldg(a.mol_ptr + gbase + i + 1);
+      p0 = __ldg(a.mol_ptr + gbase + i);
+      const int p1 = __ldg(a.mol_ptr + gbase + i + 1);
       sz = p1 - p0;
-      if (COMPACT) me = __ldg(a.mol_eptr + gbase + i + 1) - __ldg(a.mol_eptr + gbase + i);
-      else me = __ldg(a.row_ptr + p1) - __ldg(a.row_ptr + p0);
+      int e1;
+      if (COMPACT) e0 = __ldg(a.mol_eptr + gbase + i), e1 = __ldg(a.mol_eptr + gbase + i + 1);
+      else e0 = __ldg(a.row_ptr + p0), e1 = __ldg(a.row_ptr + p1);
+      me = e1 - e0;
       if (sz < 0 || sz > FP_ROWS || me < 0 || me > FP_ECAP) bad = 1, sz = min(max(sz, 0), FP_ROWS), me = min(max(me, 0), FP_ECAP);
     }
     ws.msize[i] = (unsigned char)sz;
     ws.ments[i] = (unsigned short)me;
+    ws.aptr[i] = p0, ws.eptr[i] = e0;
   }
   for (int i = lane; i < FP_ROWS + 2; i += 32) ws.head[i] = PL_NIL;
   __syncwarp();
@@ -140,12 +145,11 @@ __global__ void __launch_bounds__(PL_WARPS * 32) fused_plan_kernel(const PlanArg
   // ---- 3. tiles
   for (int k = 0; k < nt; ++k) {
     const int o0 = ws.tstart[k], nmol = ws.tstart[k + 1] - o0;
-    int sz = 0, me = 0, mol = 0, aptr = 0, eptr = 0;
+    int sz = 0, me = 0, aptr = 0, eptr = 0;
     if (lane < nmol) {
       const int i = ws.order[o0 + lane];
-      sz = ws.msize[i], me = ws.ments[i], mol = gbase + i;
-      aptr = __ldg(a.mol_ptr + mol);
-      eptr = COMPACT ? __ldg(a.mol_eptr + mol) : __ldg(a.row_ptr + aptr);
+      sz = ws.msize[i], me = ws.ments[i], aptr = ws.aptr[i], eptr = ws.eptr[i];
+      ws.tile.molid[lane] = gbase + i;
     }
     int off = sz, eoff = me;  // inclusive scans over the tile's molecules
 #pragma unroll
@@ -154,25 +158,26 @@ __global__ void __launch_bounds__(PL_WARPS * 32) fused_plan_kernel(const PlanArg
       if (lane >= o) off += v, eoff += u;
     }
     const int rows = __shfl_sync(0xffffffffu, off, 31), n_ent = __shfl_sync(0xffffffffu, eoff, 31);
+    const int aend = lane < nmol ? off : 0x7fffffff;  // first natural row after molecule `lane`
     off -= sz, eoff -= me;
-    if (lane < nmol) {
-      ws.tile.molid[lane] = mol;
-      ws.tile.mol_lo[lane] = (uint8_t)off;
-      for (int r = 0; r < sz; ++r) ws.rowmol[off + r] = (unsigned char)lane;
-    }
+    if (lane < nmol) ws.tile.mol_lo[lane] = (uint8_t)off;
     if (lane == 0) {
       ws.tile.mol_lo[nmol] = (uint8_t)rows;
       ws.tile.nm = (uint8_t)nmol, ws.tile.rows = (uint8_t)rows, ws.tile.n_ent = (uint16_t)n_ent;
     }
-    __syncwarp();
-    // rows: four passes of 32 natural rows
-    int word[4], key[4], rank[4];
+    // rows: four passes of 32 natural rows.  In-degree classes (min(deg, 7)) are counted in eight 8-bit fields of one
+    // 64-bit word: an inclusive warp scan of "1 << 8 key" gives every row its rank inside its class (stable, natural order).
+    int word[4], key[4];
+    unsigned long long incl_cls[4];
+    unsigned long long run_cls = 0ull;  // class counts of the passes before this one
     int carry = 0;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int rho = 32 * p + lane;
       const bool valid = rho < rows;
-      const int j = valid ? ws.rowmol[rho] : 0;
+      int j = 0;  // molecule of row rho = number of molecules that end at or before it
+      for (int q = 0; q < nmol; ++q) j += (__shfl_sync(0xffffffffu, aend, q) <= rho) ? 1 : 0;
+      j = min(j, 31);
       const int ap = __shfl_sync(0xffffffffu, aptr, j), of = __shfl_sync(0xffffffffu, off, j);
       int aid = 0, deg = 0;
       if (valid) {
@@ -187,38 +192,26 @@ __global__ void __launch_bounds__(PL_WARPS * 32) fused_plan_kernel(const PlanArg
         if (deg < 0 || deg > 31) bad = 1, deg = min(max(deg, 0), 31);
         aid = min(max(aid, 0), min(a.atom_vocab - 1, 1023));
       }
+      key[p] = min(deg, 7);
       int incl = deg;
+      unsigned long long cls = 1ull << (8 * key[p]);
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+        const unsigned long long c = __shfl_up_sync(0xffffffffu, cls, o);
+        if (lane >= o) incl += v, cls += c;
       }
       const int e0 = min(carry + incl - deg, FP_ECAP);  // (clamps only bite on refused batches: no read leaves the record)
       carry += __shfl_sync(0xffffffffu, incl, 31);
       deg = min(deg, FP_ECAP - e0);
+      incl_cls[p] = cls + run_cls;
+      run_cls += __shfl_sync(0xffffffffu, cls, 31);
       word[p] = rho | (deg << 7) | (e0 << 12) | (aid << 22);
-      key[p] = min(deg, 7);
-      int mine = 0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const unsigned m = __ballot_sync(0xffffffffu, key[p] == q);
-        if (lane == q) mine = __popc(m);
-        if (key[p] == q) rank[p] = __popc(m & ((1u << lane) - 1u));
-      }
-      if (lane < 8) ws.cnt[p][lane] = mine;
     }
-    __syncwarp();
+    // exclusive prefix over the classes of the tile totals (<= 128 per field: no carry between fields)
+    const unsigned long long cls_base = run_cls * 0x0101010101010100ull;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      int pos = rank[p];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int c0 = ws.cnt[0][q], c1 = ws.cnt[1][q], c2 = ws.cnt[2][q], c3 = ws.cnt[3][q];
-        if (q < key[p]) pos += c0 + c1 + c2 + c3;
-        if (q == key[p]) pos += (p > 0 ? c0 : 0) + (p > 1 ? c1 : 0) + (p > 2 ? c2 : 0);
-      }
-      ws.tile.slot[pos] = (uint32_t)word[p];
-    }
+    for (int p = 0; p < 4; ++p) ws.tile.slot[field8(cls_base, key[p]) + field8(incl_cls[p], key[p]) - 1] = (uint32_t)word[p];
     // entries: every molecule's CSR range is contiguous; the tile's list is their concatenation in tile order
     for (int j = 0; j < nmol; ++j) {
       const int ep = __shfl_sync(0xffffffffu, eptr, j), mj = __shfl_sync(0xffffffffu, me, j), eo = __shfl_sync(0xffffffffu, eoff, j);

@@ -582,8 +582,10 @@ __global__ void __launch_bounds__(K6_WARPS * 32) pool_head_kernel(K6Args a) {
 // in REGISTERS for the whole kernel, so a multiply-accumulate costs one broadcast shared-memory read per four FMAs
 // instead of two reads per FMA.  Same arithmetic and summation order as pool_head_kernel.
 constexpr int R32_WARPS = 8;
+constexpr int R32_NP = 4;  // pairs per warp iteration: four independent dependency chains per lane (the kernel is latency-bound:
+                           // 160 weight registers per lane leave 8 warps per SM)
 __global__ void __launch_bounds__(R32_WARPS * 32) readout32_kernel(K6Args a) {
-  __shared__ __align__(16) float sx[R32_WARPS][4][32];  // per warp: pool, v1, v2 (one tower at a time), mixed
+  __shared__ __align__(16) float sx[R32_WARPS][R32_NP][3][32];  // per warp and pair: pool, v1, mixed
   const int d = a.d, fp = a.fp, mix = a.mix, fp2 = a.fp2, nh = fp2 > 0 ? fp2 : 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float wfp[2][32], wmx[2][32], w1[32];
@@ -603,72 +605,96 @@ __global__ void __launch_bounds__(R32_WARPS * 32) readout32_kernel(K6Args a) {
   for (int k = 0; k < 32; ++k) w1[k] = (k < mix && lane < nh) ? a.W1[k * nh + lane] : 0.f;
   b1v = lane < nh ? a.b1[lane] : 0.f;
   if (fp2 > 0 && lane < fp2) w2v = a.W2[lane];
-  float* pool = sx[warp][0];
-  float* v1 = sx[warp][1];
-  float* mixed = sx[warp][3];
   const int warp_global = blockIdx.x * R32_WARPS + warp, n_warps = gridDim.x * R32_WARPS;
-  // the pooled rows (and temperature) of the NEXT pair are in flight while the current pair computes
-  float nx[2] = {0.f, 0.f}, nT = 0.f;
-  if (warp_global < a.n_pairs) {
-    nx[0] = lane < d ? __ldg(a.pooled + (int64_t)warp_global * d + lane) : 0.f;
-    nx[1] = lane < d ? __ldg(a.pooled + (int64_t)(a.n_pairs + warp_global) * d + lane) : 0.f;
-    if (fp2 == 0) nT = __ldg(a.T + warp_global);
-  }
-  for (int pair = warp_global; pair < a.n_pairs; pair += n_warps) {
-    const float cx[2] = {nx[0], nx[1]};
-    const float cT = nT;
-    const int np = pair + n_warps;
-    if (np < a.n_pairs) {
-      nx[0] = lane < d ? __ldg(a.pooled + (int64_t)np * d + lane) : 0.f;
-      nx[1] = lane < d ? __ldg(a.pooled + (int64_t)(a.n_pairs + np) * d + lane) : 0.f;
-      if (fp2 == 0) nT = __ldg(a.T + np);
+  // a warp takes R32_NP consecutive pairs per iteration; the pooled rows (and temperatures) of the NEXT iteration are in
+  // flight while the current one computes
+  float nx[R32_NP][2], nT[R32_NP];
+  auto fetch = [&](int base) {
+#pragma unroll
+    for (int q = 0; q < R32_NP; ++q) {
+      const int pr = base + q;
+      const bool ok = pr < a.n_pairs;
+      nx[q][0] = (ok && lane < d) ? __ldg(a.pooled + (int64_t)pr * d + lane) : 0.f;
+      nx[q][1] = (ok && lane < d) ? __ldg(a.pooled + (int64_t)(a.n_pairs + pr) * d + lane) : 0.f;
+      nT[q] = (ok && fp2 == 0) ? __ldg(a.T + pr) : 0.f;
     }
-    float mixv = 0.f;
+  };
+  fetch(warp_global * R32_NP);
+  for (int base = warp_global * R32_NP; base < a.n_pairs; base += n_warps * R32_NP) {
+    float cx[R32_NP][2], cT[R32_NP];
+#pragma unroll
+    for (int q = 0; q < R32_NP; ++q) cx[q][0] = nx[q][0], cx[q][1] = nx[q][1], cT[q] = nT[q];
+    fetch(base + n_warps * R32_NP);
+    float mixv[R32_NP];
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
-      pool[lane] = cx[t];
+#pragma unroll
+      for (int q = 0; q < R32_NP; ++q) sx[warp][q][0][lane] = cx[q][t];
       __syncwarp();
-      float acc = bfp[t];
+      float acc[R32_NP];
+#pragma unroll
+      for (int q = 0; q < R32_NP; ++q) acc[q] = bfp[t];
 #pragma unroll
       for (int k4 = 0; k4 < 8; ++k4) {
-        const float4 x = *reinterpret_cast<const float4*>(pool + 4 * k4);
-        acc = fmaf(x.x, wfp[t][4 * k4], acc), acc = fmaf(x.y, wfp[t][4 * k4 + 1], acc);
-        acc = fmaf(x.z, wfp[t][4 * k4 + 2], acc), acc = fmaf(x.w, wfp[t][4 * k4 + 3], acc);
+#pragma unroll
+        for (int q = 0; q < R32_NP; ++q) {
+          const float4 x = *reinterpret_cast<const float4*>(&sx[warp][q][0][4 * k4]);
+          acc[q] = fmaf(x.x, wfp[t][4 * k4], acc[q]), acc[q] = fmaf(x.y, wfp[t][4 * k4 + 1], acc[q]);
+          acc[q] = fmaf(x.z, wfp[t][4 * k4 + 2], acc[q]), acc[q] = fmaf(x.w, wfp[t][4 * k4 + 3], acc[q]);
+        }
       }
-      v1[lane] = lane < fp ? fmaxf(acc, 0.f) : 0.f;
+#pragma unroll
+      for (int q = 0; q < R32_NP; ++q) sx[warp][q][1][lane] = lane < fp ? fmaxf(acc[q], 0.f) : 0.f;
       __syncwarp();
-      acc = bmx[t];
+#pragma unroll
+      for (int q = 0; q < R32_NP; ++q) acc[q] = bmx[t];
 #pragma unroll
       for (int k4 = 0; k4 < 8; ++k4) {
-        const float4 x = *reinterpret_cast<const float4*>(v1 + 4 * k4);
-        acc = fmaf(x.x, wmx[t][4 * k4], acc), acc = fmaf(x.y, wmx[t][4 * k4 + 1], acc);
-        acc = fmaf(x.z, wmx[t][4 * k4 + 2], acc), acc = fmaf(x.w, wmx[t][4 * k4 + 3], acc);
+#pragma unroll
+        for (int q = 0; q < R32_NP; ++q) {
+          const float4 x = *reinterpret_cast<const float4*>(&sx[warp][q][1][4 * k4]);
+          acc[q] = fmaf(x.x, wmx[t][4 * k4], acc[q]), acc[q] = fmaf(x.y, wmx[t][4 * k4 + 1], acc[q]);
+          acc[q] = fmaf(x.z, wmx[t][4 * k4 + 2], acc[q]), acc[q] = fmaf(x.w, wmx[t][4 * k4 + 3], acc[q]);
+        }
       }
-      const float v2 = lane < mix ? fmaxf(acc, 0.f) : 0.f;
-      mixv = t == 0 ? v2 : mixv + v2;
+#pragma unroll
+      for (int q = 0; q < R32_NP; ++q) {
+        const float v2 = lane < mix ? fmaxf(acc[q], 0.f) : 0.f;
+        mixv[q] = t == 0 ? v2 : mixv[q] + v2;
+      }
       __syncwarp();
     }
-    mixed[lane] = mixv;
+#pragma unroll
+    for (int q = 0; q < R32_NP; ++q) sx[warp][q][2][lane] = mixv[q];
     __syncwarp();
-    float hp = b1v;
+    float hp[R32_NP];
+#pragma unroll
+    for (int q = 0; q < R32_NP; ++q) hp[q] = b1v;
 #pragma unroll
     for (int k4 = 0; k4 < 8; ++k4) {
-      const float4 x = *reinterpret_cast<const float4*>(mixed + 4 * k4);
-      hp = fmaf(x.x, w1[4 * k4], hp), hp = fmaf(x.y, w1[4 * k4 + 1], hp);
-      hp = fmaf(x.z, w1[4 * k4 + 2], hp), hp = fmaf(x.w, w1[4 * k4 + 3], hp);
-    }
-    if (fp2 == 0) {
-      const float p0 = __shfl_sync(0xffffffffu, hp, 0), p1 = __shfl_sync(0xffffffffu, hp, 1), p2 = __shfl_sync(0xffffffffu, hp, 2);
-      if (lane == 0) {
-        const float B = fminf(fmaxf(softplusf_precise(p1), 0.0f), 20.0f);
-        const float Cc = fminf(fmaxf(softplusf_precise(p2), 0.1f), 50.0f);
-        a.out[pair] = p0 + B / (cT / 100.0f + Cc + 1e-6f);
+#pragma unroll
+      for (int q = 0; q < R32_NP; ++q) {
+        const float4 x = *reinterpret_cast<const float4*>(&sx[warp][q][2][4 * k4]);
+        hp[q] = fmaf(x.x, w1[4 * k4], hp[q]), hp[q] = fmaf(x.y, w1[4 * k4 + 1], hp[q]);
+        hp[q] = fmaf(x.z, w1[4 * k4 + 2], hp[q]), hp[q] = fmaf(x.w, w1[4 * k4 + 3], hp[q]);
       }
-    } else {
-      const float part = lane < fp2 ? fmaxf(hp, 0.f) * w2v : 0.f;
-      float tot = 0.f;
-      for (int l = 0; l < 32; ++l) tot += __shfl_sync(0xffffffffu, part, l);  // fixed order
-      if (lane == 0) a.out[pair] = tot + a.b2[0];
+    }
+#pragma unroll
+    for (int q = 0; q < R32_NP; ++q) {
+      const int pair = base + q;
+      if (fp2 == 0) {
+        const float p0 = __shfl_sync(0xffffffffu, hp[q], 0), p1 = __shfl_sync(0xffffffffu, hp[q], 1), p2 = __shfl_sync(0xffffffffu, hp[q], 2);
+        if (lane == q && pair < a.n_pairs) {  // one lane per pair of the group evaluates the head
+          const float B = fminf(fmaxf(softplusf_precise(p1), 0.0f), 20.0f);
+          const float Cc = fminf(fmaxf(softplusf_precise(p2), 0.1f), 50.0f);
+          a.out[pair] = p0 + B / (cT[q] / 100.0f + Cc + 1e-6f);
+        }
+      } else {
+        const float part = lane < fp2 ? fmaxf(hp[q], 0.f) * w2v : 0.f;
+        float tot = 0.f;
+        for (int l = 0; l < 32; ++l) tot += __shfl_sync(0xffffffffu, part, l);  // fixed order
+        if (lane == 0 && pair < a.n_pairs) a.out[pair] = tot + a.b2[0];
+      }
     }
     __syncwarp();
   }
@@ -1065,7 +1091,7 @@ static int launch_k6(const imp_graph_t* g, const float* d_h, const float* d_pool
   IMP_CUDA(cudaFuncSetAttribute(pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   IMP_REQUIRE(smem <= 200 * 1024, IMP_ERR_DIM, "%s: readout weights need %zu B of shared memory", who, smem);
   if (d_pooled && !aux && d <= 32 && fp <= 32 && mix <= 32 && fp2 <= 32) {  // both reference models: register-resident weights
-    int nb = (int)ceil_div(g->n_pairs, R32_WARPS);
+    int nb = (int)ceil_div(g->n_pairs, R32_WARPS * R32_NP);
     if (nb > 148 * 6) nb = 148 * 6;
     readout32_kernel<<<nb, R32_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     IMP_LAUNCH_CHECK();

@@ -113,8 +113,9 @@ def test_planned_forward_matches_the_self_contained_kernel_and_the_fp32_path(n_p
         planned.check_status()
         assert np.array_equal(a, c), "the compact feed and the int32 CSR feed give the same plan contents"
         assert np.array_equal(a, planned.forward_packed(batch).cpu().numpy()), "run-to-run bit-identical"
-        # the same arithmetic up to the LayerNorm evaluation order: fp32 rounding only
-        assert _rel(a, b) <= 1e-4, _rel(a, b)
+        # the same arithmetic up to the LayerNorm evaluation order; an fp32 rounding difference can flip the 16-bit rounding
+        # of an operand, so the two kernels agree to a few operand ulps (2^-11), not to fp32 rounding
+        assert _rel(a, b) <= 2e-3, _rel(a, b)
         assert _rel(a, want32) <= RTOL16
     assert planned.launches_per_forward(batch) == 4
     assert _lib.load().imp_fused_plan_bytes(-1, 0, 0, 0) < 0

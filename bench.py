@@ -134,12 +134,33 @@ class ClockSampler:
 def ncu_traffic(kernel, pairs):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of the SAME launch size
     (profiles/r01_fused_traffic.json); None when there is no capture for this size."""
-    p = os.path.join(ROOT, "profiles", "r01_fused_traffic.json")
-    if os.path.exists(p):
-        d = json.load(open(p))
-        if d.get("kernel") == kernel and d.get("pairs_per_launch") == pairs:
-            return d["dram_bytes_read"] + d["dram_bytes_write"], d["source"]
+    for name in ("r02_fused_traffic.json", "r01_fused_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            d = json.load(open(p))
+            if d.get("kernel") == kernel and d.get("pairs_per_launch") == pairs:
+                return d["dram_bytes_read"] + d["dram_bytes_write"], d["source"]
     return None, None
+
+
+def simt_pipe_ceiling(batch, S, ms, sm_mhz, n_sm=148):
+    """The fused forward's second ceiling: its SIMT side.  Pipe-time model of one launch with the pipe rates
+    measured on B200 by tools/issue_microbench.cu (warp-instructions per clock per SM sub-partition): HFMA2 0.5, fp32
+    FFMA / FADD / FMUL 1.0, MUFU.TANH 0.125.
+      FMA pipe:  Z build 128 HFMA2 per unique entry and step (2 cycles each, at 100 % lane use: / 32 lanes)
+                 + 352 fp32 instructions per atom and step (gates 96, r*h 32, blend 64, statistics 64, LayerNorm 96)
+      XU pipe:   97 MUFU per atom and step (z, r, candidate tanh; rsqrt), 8 cycles each
+    Ceiling = the busier pipe 100 % busy on every sub-partition of every SM."""
+    N, Eu = batch.n_atoms, batch.n_unique
+    fma = S * (2.0 * 128 * Eu / 32 + 352.0 * N / 32)
+    xu = S * 8.0 * 97 * N / 32
+    smsp_cycles_per_s = n_sm * 4 * (sm_mhz or 1965.0) * 1e6
+    t_ceiling = max(fma, xu) / smsp_cycles_per_s
+    return {"model": "FMA pipe: S (8 Eu + 11 N) cycles, XU pipe: S 24.25 N cycles per launch and sub-partition-sum; rates "
+                     "measured by tools/issue_microbench.cu (HFMA2 0.5, fp32 1.0, MUFU 0.125 warp-instr/clk/SMSP)",
+            "fma_pipe_cycles": fma, "xu_pipe_cycles": xu, "pairs_per_s_at_ceiling": batch.n_pairs / t_ceiling,
+            "frac": t_ceiling / (ms * 1e-3), "fma_pipe_busy": fma / smsp_cycles_per_s / (ms * 1e-3),
+            "xu_pipe_busy": xu / smsp_cycles_per_s / (ms * 1e-3)}
 
 
 def measured_peaks():
@@ -211,7 +232,8 @@ def stage_flops(batch, d, S):
     """Algorithmic FLOP per launch: messages 2*E*d^2 with E = live entries counted with multiplicity,
     gated update 12*N*d^2, per step."""
     N, E = batch.n_atoms, batch.n_edges
-    return {"mpnn_forward_fused": S * (2 * E + 12 * N) * d * d, "gated_update_tc": 12 * N * d * d,
+    return {"mpnn_forward_fused": S * (2 * E + 12 * N) * d * d, "mpnn_forward_fused_planned": S * (2 * E + 12 * N) * d * d,
+            "gated_update_tc": 12 * N * d * d,
             "gated_update_wide": 12 * N * d * d, "message_agg": 2 * batch.n_unique * d * d,
             # wide tensor path: algorithmic message work is 2*E*d^2 (the kernel executes 16*N*d^2 as Z.Wc, K = 8d)
             "wide_message": 2 * E * d * d, "wide_gated_update": 12 * N * d * d,
@@ -227,6 +249,10 @@ def stage_bytes(batch, d, S, s=4):
         # fused forward: only the index stream is read (atom_id, row_ptr, mol_ptr, (src, bond|mult) per entry) and
         # the molecule sums are written (SURVEY 8d "stretch": bytes -> indices only)
         "mpnn_forward_fused": 8 * N + 8 * Eu + 8 * P + 2 * P * d * 4,
+        # planned forward: one 2 KiB record per 128-row tile (~N / 125 tiles) in, the molecule sums out; the plan kernel reads
+        # the index stream once and writes those records
+        "mpnn_forward_fused_planned": (N // 125 + 1) * 2048 + 2 * P * d * 4,
+        "fused_plan": 8 * N + 8 * Eu + 8 * P + (N // 125 + 1) * 2048,
         "readout_visc": 2 * P * d * 4 + 8 * P,
         "readout_mp": 2 * P * d * 4 + 4 * P,
         "embed_atoms": 4 * N + N * d * s,
@@ -607,7 +633,7 @@ def run_b200(args):
                             "executed_TFLOPs": executed[dom] / (mean_ms[dom] * 1e-3) / 1e12,
                             "whole_forward_algorithmic_TFLOPs": step_flop / (ms_total / args.steps * 1e-3) / 1e12,
                             "whole_forward_frac": step_flop / (ms_total / args.steps * 1e-3) / 1e12 / tf_peak}
-            elif dom == "mpnn_forward_fused":
+            elif dom in ("mpnn_forward_fused", "mpnn_forward_fused_planned"):
                 # the fused kernel keeps every activation on chip: 2.7 kFLOP per byte of index stream, far right of
                 # the ridge (211 FLOP/B) => the tensor roofline is the one that bounds it
                 ach = sf[dom] / (mean_ms[dom] * 1e-3) / 1e12
@@ -617,7 +643,8 @@ def run_b200(args):
                             "peak_source": peak_src + ", sustained bf16",
                             "algorithmic_flop_per_launch": sf[dom], "algorithmic_bytes_per_launch": sb[dom],
                             "hbm_GBps_on_algorithmic_bytes": sb[dom] / (mean_ms[dom] * 1e-3) / 1e9,
-                            "hbm_frac": sb[dom] / (mean_ms[dom] * 1e-3) / 1e9 / hbm_peak}
+                            "hbm_frac": sb[dom] / (mean_ms[dom] * 1e-3) / 1e9 / hbm_peak,
+                            "issue_ceiling": simt_pipe_ceiling(batch, S, mean_ms[dom], (clocks or {}).get("sm_mhz"))}
             else:
                 ach = sb.get(dom, 0) / (mean_ms[dom] * 1e-3) / 1e9
                 roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",

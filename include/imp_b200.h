@@ -193,6 +193,7 @@ int imp_gated_update_wide(const float* d_h, const float* d_agg, int32_t n_atoms,
 #define IMP_TC_MSG_ONE_CHUNK_PER_CTA 128 /* imp_edge_messages_tc16: the non-pipelined kernel (comparison) */
 #define IMP_TC_GEN3 512 /* imp_mpnn_forward_fused: kept for callers of round 1; the self-contained kernel IS generation 3 */
 #define IMP_TC_GEN4 1024 /* imp_mpnn_forward_fused: the fourth-generation kernel (arrive-and-continue; measured slower) */
+#define IMP_TC_GEN5 2048 /* imp_mpnn_forward_fused_planned: the fifth-generation kernel (weights from imp_fused_pack; comparison) */
 int64_t imp_gru_pack_bytes(int32_t d);
 int imp_gru_pack_bf16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
 int imp_gru_pack_f16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
@@ -326,11 +327,19 @@ int imp_mpnn_forward_fused_compact(const imp_compact_graph_t* cg, const float* d
  *                      (0 = ok; 1 = a molecule outside the envelope: > 128 atoms, a row with > 31 entries or > 336 entries
  *                      per molecule; 2 = capacity exceeded) that the caller reads after synchronising -- such batches go
  *                      through imp_mpnn_forward_fused or the staged kernels.
- *   imp_mpnn_forward_fused_planned   the forward: per tile one TMA bulk copy of its record (double-buffered), then the
- *                      step pipeline of the third generation.  flags: IMP_TC_FP16 [| IMP_TC_PRECISE_EPILOGUE]; weights
- *                      packed by imp_fused_pack with the same flags.  Results do not depend on how the plan cut the batch
- *                      (row order inside a tile does not enter the arithmetic); they agree with imp_mpnn_forward_fused to
- *                      fp32 rounding (the LayerNorm is evaluated as gamma * (n * inv - mean * inv) + h + beta here). */
+ *   imp_fused_pack_planned   once per weight update and per (tower, step) -> imp_fused_pack_planned_bytes() bytes; d_packed
+ *                      of the planned forward is [2 towers][steps] such blocks, cation first.
+ *   imp_mpnn_forward_fused_planned   the forward (sixth generation, csrc/fused_fwd6.cu): per tile one TMA bulk copy of its
+ *                      record (double-buffered); per step the packed-HFMA2 Z build and GEMM1 of the third generation, then
+ *                      the gate and candidate GEMMs read the aggregated messages IN PLACE from their fp32 accumulator as a
+ *                      kind::tf32 operand (no read-back / re-write of agg, one tcgen05 round trip and one context barrier
+ *                      less per step).  flags: IMP_TC_FP16 [| IMP_TC_PRECISE_EPILOGUE]; IMP_TC_GEN5 selects the fifth
+ *                      generation (same plan, third-generation step pipeline, weights from imp_fused_pack with
+ *                      IMP_TC_FP16) for comparison.  Results do not depend on how the plan cut the batch (row order inside
+ *                      a tile does not enter the arithmetic); they agree with imp_mpnn_forward_fused to a few operand ulps. */
+int64_t imp_fused_pack_planned_bytes(int32_t d, int32_t bond_dim);
+int imp_fused_pack_planned(const float* d_bond_transform /* [K,d,d] */, const imp_gru_weights_t* w, int32_t d, int32_t bond_dim,
+                           void* d_packed, void* stream);
 int64_t imp_fused_plan_bytes(int32_t n_pairs, int32_t n_atoms, int32_t n_unique, int32_t max_mol_atoms);
 int imp_fused_plan(const imp_graph_t* g, const imp_compact_graph_t* cg, int32_t atom_vocab, int32_t max_mol_atoms, void* d_plan,
                    int64_t plan_bytes, void* stream);

@@ -56,6 +56,7 @@ TC_MSG_ONE_CHUNK_PER_CTA = 128
 TC_WIDE_NO_CLUSTER = 256
 TC_GEN3 = 512
 TC_GEN4 = 1024
+TC_GEN5 = 2048
 PACK_DOUBLE_EDGES = 1
 PACK_SHIFT_IDS = 2
 
@@ -112,6 +113,8 @@ SIGNATURES = {
                                          C.c_int32, C.c_int32, vp, vp, vp]),
     "imp_mpnn_forward_fused_compact": (C.c_int, [C.POINTER(CompactGraph), vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, vp,
                                                  C.c_float, C.c_int32, C.c_int32, vp, vp, vp]),
+    "imp_fused_pack_planned_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "imp_fused_pack_planned": (C.c_int, [vp, C.POINTER(GruWeights), C.c_int32, C.c_int32, vp, vp]),
     "imp_fused_plan_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "imp_fused_plan": (C.c_int, [C.POINTER(Graph), C.POINTER(CompactGraph), C.c_int32, C.c_int32, vp, C.c_int64, vp]),
     "imp_mpnn_forward_fused_planned": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp, C.c_int32,

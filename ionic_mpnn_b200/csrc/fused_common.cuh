@@ -80,6 +80,13 @@ __device__ __forceinline__ float fz_tanh(float x) {
   return PRECISE ? tanhf(x) : fz_tanh_fast(x);
 }
 
+// tanh of two halves with ONE MUFU (tanh.approx.f16x2; max absolute error 2^-10.987, the same order as tanh.approx.f32)
+__device__ __forceinline__ __half2 fz_tanh_h2(__half2 x) {
+  uint32_t y;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(*reinterpret_cast<const uint32_t*>(&x)));
+  return *reinterpret_cast<const __half2*>(&y);
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Optional phase timing (compile with -DFZ_PROFILE): per-phase clock64 deltas of selected threads, summed into

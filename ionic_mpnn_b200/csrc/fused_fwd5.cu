@@ -170,12 +170,12 @@ __global__ void __launch_bounds__(F5_CTX * F5_THREADS, 1) mpnn_fused_h5_kernel(c
             }
           }
         };
-        if (deg == 0) {
-#pragma unroll
-          for (int i = 0; i < D * 2; ++i) acc[i] = __half2(__ushort_as_half(0), __ushort_as_half(0));
-        } else {
+        {
+          // a row without entries runs the first-entry code on the all-zero descriptor (multiplicity 0: every product is 0):
+          // a branch here is if-converted into 64 selects per half for EVERY warp (9 % of the kernel's instructions, ncu)
+          const uint32_t e_first = deg > 0 ? entp[0] : 0u;
           uint32_t en = deg > 1 ? entp[1] : 0u;
-          entry(entp[0], F5True{});
+          entry(e_first, F5True{});
 #pragma unroll 1
           for (int e = 1; e < deg; ++e) {
             const uint32_t ec = en;
@@ -345,6 +345,12 @@ static int fused5_sm_count() {
   return n;
 }
 
+namespace imp {
+int launch_fused_h6(const void* d_plan, int32_t n_atoms, int32_t n_cat_atoms, int32_t bond_vocab, const float* d_atom_emb,
+                    int32_t atom_vocab, const float* d_bond_emb, int32_t steps, const void* d_packed, float eps, bool precise,
+                    float* d_pooled, cudaStream_t st);  // fused_fwd6.cu
+}
+
 extern "C" int imp_mpnn_forward_fused_planned(const void* d_plan, int32_t n_pairs, int32_t n_atoms, int32_t n_cat_atoms,
                                               int32_t bond_vocab, const float* d_atom_emb, int32_t atom_vocab,
                                               const float* d_bond_emb, int32_t d, int32_t bond_dim, int32_t steps,
@@ -357,11 +363,14 @@ extern "C" int imp_mpnn_forward_fused_planned(const void* d_plan, int32_t n_pair
   IMP_REQUIRE(steps >= 1 && steps <= FZ_MAX_STEPS, IMP_ERR_DIM, "imp_mpnn_forward_fused_planned: 1..%d steps (got %d)", FZ_MAX_STEPS, steps);
   IMP_REQUIRE(bond_vocab >= 1 && bond_vocab <= FZ_MAX_VB && atom_vocab >= 1 && atom_vocab <= 1024, IMP_ERR_DIM,
               "imp_mpnn_forward_fused_planned: bond vocabulary must be in 1..%d, atom vocabulary in 1..1024", FZ_MAX_VB);
-  IMP_REQUIRE((flags & IMP_TC_FP16) && !(flags & ~(IMP_TC_FP16 | IMP_TC_PRECISE_EPILOGUE)), IMP_ERR_UNSUPPORTED,
-              "imp_mpnn_forward_fused_planned: IEEE-half operands only (flags IMP_TC_FP16 [| IMP_TC_PRECISE_EPILOGUE])");
+  IMP_REQUIRE((flags & IMP_TC_FP16) && !(flags & ~(IMP_TC_FP16 | IMP_TC_PRECISE_EPILOGUE | IMP_TC_GEN5)), IMP_ERR_UNSUPPORTED,
+              "imp_mpnn_forward_fused_planned: IEEE-half operands only (flags IMP_TC_FP16 [| IMP_TC_PRECISE_EPILOGUE | IMP_TC_GEN5])");
   if (n_pairs == 0) return 0;
   IMP_REQUIRE(d_plan && d_atom_emb && d_bond_emb && d_packed && d_pooled, IMP_ERR_ARG, "imp_mpnn_forward_fused_planned: null pointer");
   IMP_REQUIRE(imp_device_is_sm100(), IMP_ERR_UNSUPPORTED, "imp_mpnn_forward_fused_planned: tcgen05 needs an sm_100 device");
+  if (!(flags & IMP_TC_GEN5))  // default: sixth generation (weights from imp_fused_pack_planned)
+    return launch_fused_h6(d_plan, n_atoms, n_cat_atoms, bond_vocab, d_atom_emb, atom_vocab, d_bond_emb, steps, d_packed, eps,
+                           (flags & IMP_TC_PRECISE_EPILOGUE) != 0, d_pooled, (cudaStream_t)stream);
   Fused5Args a;
   a.plan = (const unsigned char*)d_plan, a.atom_emb = d_atom_emb, a.bond_emb = d_bond_emb, a.packed = (const unsigned char*)d_packed;
   a.pooled = d_pooled, a.atom_vocab = atom_vocab, a.bond_vocab = bond_vocab, a.steps = steps, a.eps = eps;

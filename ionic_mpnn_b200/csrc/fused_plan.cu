@@ -165,30 +165,44 @@ __global__ void __launch_bounds__(PL_WARPS * 32) fused_plan_kernel(const PlanArg
       ws.tile.mol_lo[nmol] = (uint8_t)rows;
       ws.tile.nm = (uint8_t)nmol, ws.tile.rows = (uint8_t)rows, ws.tile.n_ent = (uint16_t)n_ent;
     }
-    // rows: four passes of 32 natural rows.  In-degree classes (min(deg, 7)) are counted in eight 8-bit fields of one
-    // 64-bit word: an inclusive warp scan of "1 << 8 key" gives every row its rank inside its class (stable, natural order).
-    int word[4], key[4];
+    // rows: four passes of 32 natural rows, in three sweeps so that every global load of the tile's rows is in flight before
+    // the first is used (the kernel is bound by load latency: ncu long scoreboard).
+    int jm[4], at[4];  // molecule (lane index in this tile) and global atom of natural row 32 p + lane
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int rho = 32 * p + lane;
+      int j = 0;  // number of molecules that end at or before the row
+      for (int q = 0; q < nmol; ++q) j += (__shfl_sync(0xffffffffu, aend, q) <= rho) ? 1 : 0;
+      jm[p] = min(j, 31);
+      at[p] = __shfl_sync(0xffffffffu, aptr, jm[p]) + (rho - __shfl_sync(0xffffffffu, off, jm[p]));
+    }
+    int aidv[4], degv[4], g0[4];  // atom id, in-degree, first global CSR entry of the row
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      aidv[p] = 0, degv[p] = 0, g0[p] = 0;
+      if (32 * p + lane < rows) {
+        if (COMPACT) {
+          const int aw = (int)__ldg(a.atom_w + at[p]);
+          aidv[p] = aw & 0xff, degv[p] = aw >> 8;
+        } else {
+          aidv[p] = __ldg(a.atom_id + at[p]);
+          g0[p] = __ldg(a.row_ptr + at[p]);
+          degv[p] = __ldg(a.row_ptr + at[p] + 1);
+        }
+      }
+    }
+    // In-degree classes (min(deg, 7)) are counted in eight 8-bit fields of one 64-bit word: an inclusive warp scan of
+    // "1 << 8 key" gives every row its rank inside its class (stable, natural order).
+    int word[4], key[4], e0v[4];
     unsigned long long incl_cls[4];
     unsigned long long run_cls = 0ull;  // class counts of the passes before this one
     int carry = 0;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int rho = 32 * p + lane;
-      const bool valid = rho < rows;
-      int j = 0;  // molecule of row rho = number of molecules that end at or before it
-      for (int q = 0; q < nmol; ++q) j += (__shfl_sync(0xffffffffu, aend, q) <= rho) ? 1 : 0;
-      j = min(j, 31);
-      const int ap = __shfl_sync(0xffffffffu, aptr, j), of = __shfl_sync(0xffffffffu, off, j);
-      int aid = 0, deg = 0;
-      if (valid) {
-        const int at = ap + (rho - of);
-        if (COMPACT) {
-          const int aw = (int)__ldg(a.atom_w + at);
-          aid = aw & 0xff, deg = aw >> 8;
-        } else {
-          aid = __ldg(a.atom_id + at);
-          deg = __ldg(a.row_ptr + at + 1) - __ldg(a.row_ptr + at);
-        }
+      int deg = degv[p], aid = aidv[p];
+      if (rho < rows) {
+        if (!COMPACT) deg -= g0[p];
         if (deg < 0 || deg > 31) bad = 1, deg = min(max(deg, 0), 31);
         aid = min(max(aid, 0), min(a.atom_vocab - 1, 1023));
       }
@@ -207,27 +221,52 @@ __global__ void __launch_bounds__(PL_WARPS * 32) fused_plan_kernel(const PlanArg
       incl_cls[p] = cls + run_cls;
       run_cls += __shfl_sync(0xffffffffu, cls, 31);
       word[p] = rho | (deg << 7) | (e0 << 12) | (aid << 22);
+      degv[p] = deg, e0v[p] = e0;
+      if (COMPACT)  // entries of a molecule are contiguous: first entry of the molecule + entries of its earlier rows
+        g0[p] = __shfl_sync(0xffffffffu, eptr, jm[p]) + (e0 - __shfl_sync(0xffffffffu, eoff, jm[p]));
     }
     // exclusive prefix over the classes of the tile totals (<= 128 per field: no carry between fields)
     const unsigned long long cls_base = run_cls * 0x0101010101010100ull;
 #pragma unroll
     for (int p = 0; p < 4; ++p) ws.tile.slot[field8(cls_base, key[p]) + field8(incl_cls[p], key[p]) - 1] = (uint32_t)word[p];
-    // entries: every molecule's CSR range is contiguous; the tile's list is their concatenation in tile order
-    for (int j = 0; j < nmol; ++j) {
-      const int ep = __shfl_sync(0xffffffffu, eptr, j), mj = __shfl_sync(0xffffffffu, me, j), eo = __shfl_sync(0xffffffffu, eoff, j);
-      const int ap = __shfl_sync(0xffffffffu, aptr, j), of = __shfl_sync(0xffffffffu, off, j), sj = __shfl_sync(0xffffffffu, sz, j);
-      for (int x = lane; x < mj; x += 32) {
+    // entries, row-parallel: lane (p, lane) copies its row's entries, translated to tile rows; the first four entries of
+    // all four passes are loaded before any is used
+    {
+      int rowbase[4], msz[4];  // natural row of atom 0 of the row's molecule, atoms of that molecule
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        rowbase[p] = __shfl_sync(0xffffffffu, off, jm[p]);
+        msz[p] = __shfl_sync(0xffffffffu, sz, jm[p]);
+      }
+      auto put = [&](int p, int i, int csrc, int cbm, unsigned int cw) {
         int src, bond, mult;
-        if (COMPACT) {
-          const unsigned int wv = __ldg(a.edge_w + ep + x);
-          src = (int)(wv & 0xffu), bond = (int)((wv >> 8) & 0xffu), mult = (int)((wv >> 16) & 0xffu);
-        } else {
-          const int bm = __ldg(a.edge_bm + ep + x);
-          src = __ldg(a.col_src + ep + x) - ap, bond = bm & 0xffff, mult = bm >> 16;
-        }
-        if (src < 0 || src >= sj) bad = 1, src = min(max(src, 0), max(sj - 1, 0));
+        if (COMPACT) src = (int)(cw & 0xffu), bond = (int)((cw >> 8) & 0xffu), mult = (int)((cw >> 16) & 0xffu);
+        else src = csrc - (at[p] - (32 * p + lane - rowbase[p])), bond = cbm & 0xffff, mult = cbm >> 16;
+        if (src < 0 || src >= msz[p]) bad = 1, src = min(max(src, 0), max(msz[p] - 1, 0));
         bond = min(bond, min(a.bond_vocab - 1, 255));
-        if (eo + x < FP_ECAP) ws.tile.ent[eo + x] = (uint32_t)(src + of) | ((uint32_t)bond << 8) | (half_bits_of_int(mult) << 16);
+        ws.tile.ent[e0v[p] + i] = (uint32_t)(src + rowbase[p]) | ((uint32_t)bond << 8) | (half_bits_of_int(mult) << 16);
+      };
+      int csrc[4][4], cbm[4][4];
+      unsigned int cw[4][4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          csrc[p][i] = 0, cbm[p][i] = 0, cw[p][i] = 0u;
+          if (i < degv[p]) {
+            if (COMPACT) cw[p][i] = __ldg(a.edge_w + g0[p] + i);
+            else csrc[p][i] = __ldg(a.col_src + g0[p] + i), cbm[p][i] = __ldg(a.edge_bm + g0[p] + i);
+          }
+        }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < degv[p]) put(p, i, csrc[p][i], cbm[p][i], cw[p][i]);
+        for (int i = 4; i < degv[p]; ++i) {  // rows with more than four entries
+          if (COMPACT) put(p, i, 0, 0, __ldg(a.edge_w + g0[p] + i));
+          else put(p, i, __ldg(a.col_src + g0[p] + i), __ldg(a.edge_bm + g0[p] + i), 0u);
+        }
       }
     }
     __syncwarp();

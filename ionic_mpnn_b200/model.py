@@ -249,7 +249,15 @@ class MPNNModel(TrainMixin):
                     for i in range(S):
                         w = self._gru_struct(t, i)
                         _lib.call("imp_fused_pack", self._ptr(f"{t}_bmm_{i}.bond_transform"), C.byref(w), d, K,
-                                  self.tc_flags(), fpk.data_ptr() + fb * (ti * S + i), _stream())
+                                  self.tc_flags() & ~_lib.TC_GEN5, fpk.data_ptr() + fb * (ti * S + i), _stream())
+                if self.planned_supported():  # the planned forward's own operand layout (tf32 blocks for the agg terms)
+                    fb6 = _lib.load().imp_fused_pack_planned_bytes(d, K)
+                    fpk6 = self._buf("fused_packed6", fb6 * n, torch.uint8)
+                    for ti, t in enumerate(TOWERS):
+                        for i in range(S):
+                            w = self._gru_struct(t, i)
+                            _lib.call("imp_fused_pack_planned", self._ptr(f"{t}_bmm_{i}.bond_transform"), C.byref(w), d, K,
+                                      fpk6.data_ptr() + fb6 * (ti * S + i), _stream())
         self._tables_valid = True
 
     def tc_flags(self):
@@ -281,7 +289,7 @@ class MPNNModel(TrainMixin):
         inside the tile plan's envelope (in-degree <= 31, <= 336 unique entries per molecule; a device-packed batch does
         not know these on the host -- the plan's status word, read by check_status(), reports a violation)."""
         f = self.tc_flags()
-        if not (self.fused_supported() and (f & _lib.TC_FP16) and not (f & ~(_lib.TC_FP16 | _lib.TC_PRECISE_EPILOGUE))
+        if not (self.fused_supported() and (f & _lib.TC_FP16) and not (f & ~(_lib.TC_FP16 | _lib.TC_PRECISE_EPILOGUE | _lib.TC_GEN5))
                 and self.spec["atom_vocab_size"] <= 1024 and getattr(self, "use_plan", True)):
             return False
         if batch is not None:
@@ -468,16 +476,17 @@ class MPNNModel(TrainMixin):
                       s["atom_vocab_size"], batch.max_mol_atoms, plan.data_ptr(), nb, st)
             _lib.call("imp_mpnn_forward_fused_planned", plan.data_ptr(), P, batch.n_atoms, batch.n_cat_atoms, batch.bond_vocab,
                       self._ptr("atom_emb"), s["atom_vocab_size"], self._ptr("bond_emb"), d, s["bond_dim"], S,
-                      self._ws["fused_packed"].data_ptr(), C.c_float(self.LN_EPS), self.tc_flags(), pooled.data_ptr(), st)
+                      self._ws["fused_packed" if self.tc_flags() & _lib.TC_GEN5 else "fused_packed6"].data_ptr(),
+                      C.c_float(self.LN_EPS), self.tc_flags(), pooled.data_ptr(), st)
         elif g is None:
             cg = batch.compact_struct()
             _lib.call("imp_mpnn_forward_fused_compact", C.byref(cg), self._ptr("atom_emb"), s["atom_vocab_size"],
                       self._ptr("bond_emb"), d, s["bond_dim"], S, self._ws["fused_packed"].data_ptr(), C.c_float(self.LN_EPS),
-                      self.tc_flags(), batch.max_mol_atoms, pooled.data_ptr(), status.data_ptr(), st)
+                      self.tc_flags() & ~_lib.TC_GEN5, batch.max_mol_atoms, pooled.data_ptr(), status.data_ptr(), st)
         else:
             _lib.call("imp_mpnn_forward_fused", C.byref(g), self._ptr("atom_emb"), s["atom_vocab_size"], self._ptr("bond_emb"),
-                      d, s["bond_dim"], S, self._ws["fused_packed"].data_ptr(), C.c_float(self.LN_EPS), self.tc_flags(),
-                      batch.max_mol_atoms, pooled.data_ptr(), status.data_ptr(), st)
+                      d, s["bond_dim"], S, self._ws["fused_packed"].data_ptr(), C.c_float(self.LN_EPS),
+                      self.tc_flags() & ~_lib.TC_GEN5, batch.max_mol_atoms, pooled.data_ptr(), status.data_ptr(), st)
         out = torch.empty(P, dtype=torch.float32, device=self.device)
         rc, ra = self._readout_struct("cat"), self._readout_struct("an")
         if s["kind"] == "viscosity":

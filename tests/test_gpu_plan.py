@@ -102,8 +102,9 @@ def test_planned_forward_matches_the_self_contained_kernel_and_the_fp32_path(n_p
     batch.to("cuda")
     ref = build_model(124, 72, precision="fp32", seed=3)
     want32 = ref.forward_packed(batch).cpu().numpy()
-    for precision in ("fp16", "fp16_precise"):
+    for precision, pflags in (("fp16", 0), ("fp16_precise", 0), ("fp16", _lib.TC_GEN5)):  # generation 6 (default), 5
         planned = build_model(124, 72, precision=precision, seed=3, fused=True)
+        planned.extra_tc_flags = pflags
         gen3 = build_model(124, 72, precision=precision, seed=3, fused=True)
         gen3.use_plan = False
         assert planned.planned_supported(batch) and not gen3.planned_supported(batch)
@@ -115,7 +116,7 @@ def test_planned_forward_matches_the_self_contained_kernel_and_the_fp32_path(n_p
         assert np.array_equal(a, planned.forward_packed(batch).cpu().numpy()), "run-to-run bit-identical"
         # the same arithmetic up to the LayerNorm evaluation order; an fp32 rounding difference can flip the 16-bit rounding
         # of an operand, so the two kernels agree to a few operand ulps (2^-11), not to fp32 rounding
-        assert _rel(a, b) <= 2e-3, _rel(a, b)
+        assert _rel(a, b) <= 5e-3, _rel(a, b)
         assert _rel(a, want32) <= RTOL16
     assert planned.launches_per_forward(batch) == 4
     assert _lib.load().imp_fused_plan_bytes(-1, 0, 0, 0) < 0

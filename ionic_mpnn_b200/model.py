@@ -169,6 +169,30 @@ class MPNNModel(TrainMixin):
                 st["step"] = int(z["adam/step"])
         return self
 
+    def load_keras(self, path):
+        """Loads the variables of a reference ``.keras`` archive (``model.save``, train_viscosity.py:353-354) into this model.
+        Variables are matched by graph structure (keras_io.params_from_keras); every shape is checked against the spec."""
+        from . import keras_io
+
+        config, data = keras_io.read_keras(path)
+        kind, params, _ = keras_io.params_from_keras(config, data)
+        want = "viscosity" if kind == "transfer" else kind
+        if want != self.spec["kind"]:
+            raise ValueError(f"{path} holds a {kind} model, this is a {self.spec['kind']} model")
+        if kind == "transfer":  # the base of a transfer model has no Dense(3) head: keep ours
+            params = {k: v for k, v in params.items() if not k.startswith("head")}
+            cur = self.get_weights()
+            params = {**{k: cur[k] for k in cur if k.startswith("head")}, **params}
+        self.set_weights(params)
+        return self
+
+    def save_keras(self, path, key_style="class_counter"):
+        """Writes the variables as a ``.keras`` archive with the reference's functional graph in config.json (zip of
+        config.json + model.weights.h5; HDF5 written by hdf5_min, see there for what has and has not been verified)."""
+        from . import keras_io
+
+        keras_io.export_keras(path, self.spec, self.get_weights(), key_style=key_style)
+
     def count_params(self):
         return sum(int(np.prod(s)) for s in param_shapes(self.spec).values())
 
@@ -668,6 +692,21 @@ class MPNNModel(TrainMixin):
             done[i % 2] = torch.cuda.Event()
             done[i % 2].record(compute)
         return out, nbytes
+
+
+def load_model(path, precision="fp32", **kw):
+    """``tf.keras.models.load_model(path)`` for the reference's archives (train_melting_point_transfer.py:78-93): builds the
+    model whose spec the archive's variable shapes imply and loads them."""
+    from . import keras_io
+
+    config, data = keras_io.read_keras(path)
+    kind, params, _ = keras_io.params_from_keras(config, data)
+    m = MPNNModel(keras_io.spec_from_params(kind, params), precision=precision, **kw)
+    if kind == "transfer":
+        cur = m.get_weights()
+        params = {**{k: cur[k] for k in cur if k.startswith("head")}, **{k: v for k, v in params.items() if not k.startswith("head")}}
+    m.set_weights(params)
+    return m
 
 
 def make_spec(kind="viscosity", atom_vocab_size=124, bond_vocab_size=72, atom_dim=32, bond_dim=8, fp_size=32,

@@ -234,3 +234,25 @@ def test_fused_status_flag_is_checked_by_predict():
         m.predict(big)
     ok, _, _ = graph.synth_batch(4, seed=1)
     assert np.isfinite(m.predict(ok)).all()  # the flag was reset: the next valid batch runs
+
+
+@pytest.mark.parametrize("fixture,golden_name", [("visc_small.keras", "visc_small"), ("mp_small.keras", "mp_small")])
+def test_keras_archive_loads_and_predicts_like_the_reference(fixture, golden_name, golden, tmp_path):
+    """a ``.keras`` archive of the reference's graph (tests/golden/make_keras_fixture.py) -> load_model ->
+    the reference's predictions on its own padded inputs; save_keras -> load_keras is bit-exact."""
+    import os
+
+    from conftest import GOLDEN_DIR
+    from ionic_mpnn_b200.model import load_model
+
+    meta, x, inter, out, params = golden(golden_name)
+    m = load_model(os.path.join(GOLDEN_DIR, fixture))
+    assert m.spec == meta["spec"]
+    got = m.predict(x)
+    assert rel(got, out) <= RTOL32
+    p2 = str(tmp_path / "again.keras")
+    m.save_keras(p2, key_style="layer_name")
+    m2 = load_model(p2)
+    w1, w2 = m.get_weights(), m2.get_weights()
+    assert all(np.array_equal(w1[k], w2[k]) for k in w1)
+    assert np.array_equal(m2.predict(x), got)

@@ -490,6 +490,33 @@ int imp_bond_occurrence_norm2(const imp_graph_t* g, int32_t n_cat_unique, const 
 int imp_tc_selftest(const float* d_A, const float* d_B, float* d_D, int32_t N, int32_t K, int32_t kind,
                     int32_t swap_lbo_sbo, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Transfer-learning head (train_melting_point_transfer.py:76-106, 189-241): the viscosity model cut at "mix_cat_an" +
+ * Dense(256, relu) -> BatchNormalization -> Dense(128, relu) -> Dropout(0.3) -> Dense(64, relu) -> Dense(1), Huber(delta = 1),
+ * Adam without clipping, layers frozen / unfrozen by name.  Host sequence: ionic_mpnn_b200/transfer.py.  One row per ion
+ * pair; every reduction walks the rows in order (bit-reproducible).
+ *   imp_dense_bwd      gradients of imp_dense: d_y = the layer's output (relu mask; may be NULL for activation 0);
+ *                      d_gx [rows, in] (optional), d_gkernel [in, out] + d_gbias [out] (optional, need d_x).
+ *   imp_batchnorm      keras BatchNormalization on [rows, channels] (non-fused path: biased batch variance; moving averages
+ *                      updated in place when training != 0; inference uses them).  d_save_mean / d_save_inv [channels]: the
+ *                      statistics the backward pass needs (both or neither).
+ *   imp_dropout        y = x * keep / (1 - rate) with keep(i) a pure function of (seed, i): applying it to the upstream
+ *                      gradient with the same seed is the backward pass.
+ *   imp_huber          *d_loss_sum = sum_i huber(pred_i - target_i); d_dpred_i = scale * clip(pred_i - target_i, -delta, delta).
+ *   imp_add            y = a + b (AddTwoTensors, models/layers.py:44-49, as its own call for the layer API).
+ * ------------------------------------------------------------------------------------------- */
+int imp_dense_bwd(const float* d_x, const float* d_y, const float* d_gy, int64_t rows, int32_t in_dim, int32_t out_dim,
+                  const float* d_kernel, int32_t activation, float* d_gx, float* d_gkernel, float* d_gbias, void* stream);
+int imp_batchnorm(const float* d_x, int64_t rows, int32_t channels, const float* d_gamma, const float* d_beta,
+                  float* d_moving_mean, float* d_moving_var, float momentum, float eps, int32_t training, float* d_y,
+                  float* d_save_mean, float* d_save_inv, void* stream);
+int imp_batchnorm_bwd(const float* d_x, const float* d_gy, int64_t rows, int32_t channels, const float* d_gamma,
+                      const float* d_save_mean, const float* d_save_inv, float* d_gx, float* d_ggamma, float* d_gbeta, void* stream);
+int imp_dropout(const float* d_x, int64_t n, float rate, uint64_t seed, float* d_y, void* stream);
+int imp_huber(const float* d_pred, const float* d_target, int64_t n, float delta, float scale, float* d_loss_sum, float* d_dpred,
+              void* stream);
+int imp_add(const float* d_a, const float* d_b, int64_t n, float* d_y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -160,6 +160,12 @@ SIGNATURES = {
     "imp_bond_occurrence_norm2": (C.c_int, [C.POINTER(Graph), C.c_int32, vp, C.c_int32, C.POINTER(vp), C.POINTER(vp), C.c_int32,
                                             C.c_int32, vp, vp, vp, vp, vp]),
     "imp_dense": (C.c_int, [vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, vp]),
+    "imp_dense_bwd": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, vp, vp]),
+    "imp_batchnorm": (C.c_int, [vp, C.c_int64, C.c_int32, vp, vp, vp, vp, C.c_float, C.c_float, C.c_int32, vp, vp, vp, vp]),
+    "imp_batchnorm_bwd": (C.c_int, [vp, vp, C.c_int64, C.c_int32, vp, vp, vp, vp, vp, vp, vp]),
+    "imp_dropout": (C.c_int, [vp, C.c_int64, C.c_float, C.c_uint64, vp, vp]),
+    "imp_huber": (C.c_int, [vp, vp, C.c_int64, C.c_float, C.c_float, vp, vp, vp]),
+    "imp_add": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
     "imp_tc_selftest": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
 }
 

@@ -188,7 +188,7 @@ def spec_from_params(kind, params):
 
 
 # ------------------------------------------------------------------------------------------------- writing
-def reference_graph(spec, key_style="class_counter"):
+def reference_graph(spec, key_style="class_counter", transfer_head=False):
     """The functional graph of the reference's build_model as Keras 2.12 writes it to config.json: layers in creation
     order with Keras' auto names, and for every layer that owns variables the (h5 key, sublayer, structural names)."""
     kind, S = spec["kind"], spec["num_steps"]
@@ -234,7 +234,16 @@ def reference_graph(spec, key_style="class_counter"):
         pool = add("GlobalSumPool", None, [h, f"{t}_atom"])
         fp_names[t] = add("Dense", None, [pool], own=[("", [f"{t}_fp.kernel", f"{t}_fp.bias"])])
     mix = {t: add("Dense", None, [fp_names[t]], own=[("", [f"{t}_mix.kernel", f"{t}_mix.bias"])]) for t in TOWERS}
-    if kind == "viscosity":
+    if kind == "viscosity" and transfer_head:  # build_transfer_model, train_melting_point_transfer.py:95-104
+        x = add("AddTwoTensors", "mix_cat_an", [mix["cat"], mix["an"]])
+        x = add("Dense", "mp_dense_1", [x], own=[("", ["mp_dense_1.kernel", "mp_dense_1.bias"])])
+        x = add("BatchNormalization", "mp_bn_1", [x],
+                own=[("", ["mp_bn_1.gamma", "mp_bn_1.beta", "mp_bn_1.moving_mean", "mp_bn_1.moving_variance"])])
+        x = add("Dense", "mp_dense_2", [x], own=[("", ["mp_dense_2.kernel", "mp_dense_2.bias"])])
+        x = add("Dropout", "mp_dropout", [x])
+        x = add("Dense", "mp_dense_3", [x], own=[("", ["mp_dense_3.kernel", "mp_dense_3.bias"])])
+        add("Dense", "melting_point", [x], own=[("", ["melting_point.kernel", "melting_point.bias"])])
+    elif kind == "viscosity":
         mx = add("AddTwoTensors", "mix_cat_an", [mix["cat"], mix["an"]])
         hd = add("Dense", None, [mx], own=[("", ["head.kernel", "head.bias"])])
         a, b, c = (add(f"SliceParam{x}", f"param_{x}", [hd]) for x in "ABC")
@@ -247,9 +256,12 @@ def reference_graph(spec, key_style="class_counter"):
     return layers, owners
 
 
-def export_keras(path, spec, params, key_style="class_counter", container="layers"):
-    """Writes ``params`` (structural names) as a ``.keras`` archive with the reference's graph (see reference_graph)."""
-    layers, owners = reference_graph(spec, key_style)
+def export_keras(path, spec, params, key_style="class_counter", container="layers", transfer_head=False):
+    """Writes ``params`` (structural names; with ``transfer_head`` also the mp_* / melting_point variables) as a ``.keras``
+    archive with the reference's graph (see reference_graph)."""
+    layers, owners = reference_graph(spec, key_style, transfer_head)
+    if transfer_head:  # the inputs of the transfer model are the first six of the base (train_melting_point_transfer.py:93)
+        layers = [l for l in layers if l["name"] not in ("temperature", "scale_T")]
     datasets = {}
     for key, sub, names in owners:
         for n, pname in enumerate(names):

@@ -483,8 +483,49 @@ class MPNNModel(TrainMixin):
         import torch
 
         s = self.spec
-        d, S, P = s["atom_dim"], s["num_steps"], batch.n_pairs
+        d, P = s["atom_dim"], batch.n_pairs
         fp, mix = s["fp_size"], s["mixing_size"]
+        pooled = self._fused_pooled(batch, g, st)
+        out = torch.empty(P, dtype=torch.float32, device=self.device)
+        rc, ra = self._readout_struct("cat"), self._readout_struct("an")
+        if s["kind"] == "viscosity":
+            if batch.dev_T is None:
+                raise ValueError("viscosity model needs batch.temperature")
+            _lib.call("imp_readout_visc", pooled.data_ptr(), P, d, fp, mix, C.byref(rc), C.byref(ra),
+                      self._ptr("head.kernel"), self._ptr("head.bias"), batch.dev_T.data_ptr(), out.data_ptr(), None, st)
+        else:
+            _lib.call("imp_readout_mp", pooled.data_ptr(), P, d, fp, mix, fp, C.byref(rc), C.byref(ra),
+                      self._ptr("head1.kernel"), self._ptr("head1.bias"), self._ptr("head2.kernel"),
+                      self._ptr("head2.bias"), out.data_ptr(), None, st)
+        return out
+
+    def pooled_sums(self, batch):
+        """GlobalSumPool outputs of both towers, [2P, d] tower-major (cations first), through the forward path this model is
+        configured for: the fused kernel when the shape allows it, else the staged kernels.  (The transfer-learning head,
+        ionic_mpnn_b200/transfer.py, starts from these.)"""
+        import torch
+
+        if batch.dev is None:
+            batch.to(self.device)
+        if not self._tables_valid:
+            self.refresh_tables()
+        st = _stream()
+        if self.use_fused(batch) and not self.wide_supported():
+            compact = getattr(batch, "is_compact", False)
+            return self._fused_pooled(batch, None if compact else batch.c_struct(), st)
+        if batch.dev_T is None and self.spec["kind"] == "viscosity":  # the staged readout wants a temperature; any value does
+            batch.dev_T = torch.full((batch.n_pairs,), 300.0, dtype=torch.float32, device=self.device)
+        _, inter = self.forward_packed(batch, keep=True)
+        d = self.spec["atom_dim"]
+        aux = inter["aux"]
+        return torch.cat([aux[:, :d], aux[:, d:2 * d]], dim=0).contiguous()
+
+    def _fused_pooled(self, batch, g, st):
+        """The fused forward up to the molecule sums: returns the [2P, d] workspace tensor."""
+        import torch
+
+        s = self.spec
+        d, S, P = s["atom_dim"], s["num_steps"], batch.n_pairs
         pooled = self._buf("pooled", 2 * P * d)
         status = self._ws.get("status")
         if status is None:
@@ -511,18 +552,7 @@ class MPNNModel(TrainMixin):
             _lib.call("imp_mpnn_forward_fused", C.byref(g), self._ptr("atom_emb"), s["atom_vocab_size"], self._ptr("bond_emb"),
                       d, s["bond_dim"], S, self._ws["fused_packed"].data_ptr(), C.c_float(self.LN_EPS),
                       self.tc_flags() & ~_lib.TC_GEN5, batch.max_mol_atoms, pooled.data_ptr(), status.data_ptr(), st)
-        out = torch.empty(P, dtype=torch.float32, device=self.device)
-        rc, ra = self._readout_struct("cat"), self._readout_struct("an")
-        if s["kind"] == "viscosity":
-            if batch.dev_T is None:
-                raise ValueError("viscosity model needs batch.temperature")
-            _lib.call("imp_readout_visc", pooled.data_ptr(), P, d, fp, mix, C.byref(rc), C.byref(ra),
-                      self._ptr("head.kernel"), self._ptr("head.bias"), batch.dev_T.data_ptr(), out.data_ptr(), None, st)
-        else:
-            _lib.call("imp_readout_mp", pooled.data_ptr(), P, d, fp, mix, fp, C.byref(rc), C.byref(ra),
-                      self._ptr("head1.kernel"), self._ptr("head1.bias"), self._ptr("head2.kernel"),
-                      self._ptr("head2.bias"), out.data_ptr(), None, st)
-        return out
+        return pooled
 
     def _forward_wide(self, batch, g, st):
         """imp_mpnn_forward_wide (embed, 3 tcgen05 GEMM kernels per step, pool) then the readout kernel."""

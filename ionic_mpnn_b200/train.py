@@ -124,20 +124,13 @@ class TrainMixin:
         (DESIGN.md, "Embedding clip norms")."""
         return self.spec["atom_dim"] == 32 and self.spec["bond_dim"] == 8
 
-    def loss_and_grads(self, batch, global_batch=None, occurrence_norms=True):
-        """Forward + backward on a packed batch with ``batch.target``.  Returns (sse, out): device tensors holding this
-        rank's sum of squared errors and predictions; gradients of mean-squared-error over ``global_batch`` pairs
-        (default: this batch; ``"sum"``: un-normalised sum-gradients, for a count that is all-reduced with them) are left
-        in the flat bucket ``self._train['grad']`` (WITHOUT the l2 terms, which the optimizer kernel adds after the
-        all-reduce so that they are counted once).  With ``occurrence_norms`` the tail of the bucket receives the
-        per-occurrence squared norms of the two Embedding gradients (same scaling as the gradients)."""
+    def _forward_kept(self, batch):
+        """The staged fp32 forward up to the molecule sums with every h_i / agg_i kept (the tape of the backward pass).
+        Returns a dict: h, agg (lists of device tensors), pooled / dpooled [2P, d], the bond tables and chunk workspace."""
         import torch
 
         s = self.spec
         d, S, K, Vb = s["atom_dim"], s["num_steps"], s["bond_dim"], s["bond_vocab_size"]
-        fp, mix = s["fp_size"], s["mixing_size"]
-        visc = s["kind"] == "viscosity"
-        fp2 = 0 if visc else fp
         st = self._train_state()
         if batch.dev is None:
             batch.to(self.device)
@@ -178,6 +171,93 @@ class TrainMixin:
         pooled, dpooled = self._buf("tr_pooled", 2 * P * d), self._buf("tr_dpooled", 2 * P * d)
         _lib.call("imp_global_sum_pool", batch.dev["mol_ptr"].data_ptr(), batch.dev["atom_id"].data_ptr(), 2 * P,
                   h[S].data_ptr(), d, pooled.data_ptr(), sm)
+        return dict(h=h, agg=agg, pooled=pooled, dpooled=dpooled, tab=tab, per=per, msg=msg, cws=cws, tr=tr, g=g)
+
+    def _backward_base(self, batch, kept, occurrence_norms=True, first_step=0):
+        """From kept["dpooled"] back through GlobalSumPool and the message-passing steps ``first_step .. S-1`` (and the
+        Embeddings when first_step == 0) into the flat gradient bucket.  ``first_step`` > 0 serves partially frozen models
+        (train_melting_point_transfer.py:206-217): nothing below the first trainable step is differentiated."""
+        import torch
+
+        s = self.spec
+        d, S, K, Vb = s["atom_dim"], s["num_steps"], s["bond_dim"], s["bond_vocab_size"]
+        st = self._train_state()
+        h, agg, dpooled, tab, per, msg, cws, tr, g = (kept[k] for k in ("h", "agg", "dpooled", "tab", "per", "msg", "cws", "tr", "g"))
+        N, P = batch.n_atoms, batch.n_pairs
+        sm = _stream()
+        G = st["g"]
+        lib = _lib.load()
+        # ---- back through the pooling and the S steps
+        ga, gb = self._buf("tr_ga", N * d), self._buf("tr_gb", N * d)
+        occ_bond = occurrence_norms and self.bond_occurrence_supported()
+        daggs = [self._buf(f"tr_dagg{i}" if occ_bond else "tr_dagg", N * d) for i in range(S)]  # kept per step for the norm
+        _lib.call("imp_pool_bwd", batch.dev["mol_ptr"].data_ptr(), batch.dev["atom_id"].data_ptr(), 2 * P, dpooled.data_ptr(), d,
+                  ga.data_ptr(), sm)
+        ws_gru = self._buf("tr_ws_gru", lib.imp_gated_update_bwd_workspace_floats(d))
+        dtable = self._buf("tr_dtable", 2 * per)
+        ws_dt = self._buf("tr_ws_dt", max(1, tr["n_chunks"]) * d * d)
+        G["bond_emb"].zero_()
+        cur, nxt = ga, gb
+        for i in reversed(range(first_step, S)):
+            dagg = daggs[i]
+            wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
+            gc = G[f"cat_gu_{i}.dense_z.kernel"].data_ptr()  # the layer's 8 variables are contiguous from here
+            gn = G[f"an_gu_{i}.dense_z.kernel"].data_ptr()
+            _lib.call("imp_gated_update_bwd", h[i].data_ptr(), agg[i].data_ptr(), cur.data_ptr(), N, batch.n_cat_atoms, d,
+                      C.byref(wc), C.byref(wa), C.c_float(self.LN_EPS), nxt.data_ptr(), dagg.data_ptr(), gc, gn,
+                      ws_gru.data_ptr(), sm)
+            # dh += sum over the (symmetric) live entries of mult * T[b]^T dagg[src]
+            _lib.call("imp_edge_messages_grouped", C.byref(g), dagg.data_ptr(), d, tab.data_ptr() + 4 * per * i,
+                      tab.data_ptr() + 4 * per * (S + i), 1, msg.data_ptr(), cws.data_ptr(), sm)
+            _lib.call("imp_segment_sum_add", C.byref(g), msg.data_ptr(), d, nxt.data_ptr(), sm)
+            _lib.call("imp_bond_transform_bwd", C.byref(g), tr["entry_dst"].data_ptr(), tr["chunk_begin"].data_ptr(),
+                      tr["chunk_end"].data_ptr(), tr["n_chunks"], tr["bucket_chunk_ptr"].data_ptr(), dagg.data_ptr(),
+                      h[i].data_ptr(), d, K, self._ptr("bond_emb"), self._ptr(f"cat_bmm_{i}.bond_transform"),
+                      self._ptr(f"an_bmm_{i}.bond_transform"), G[f"cat_bmm_{i}.bond_transform"].data_ptr(),
+                      G[f"an_bmm_{i}.bond_transform"].data_ptr(), G["bond_emb"].data_ptr(), dtable.data_ptr(), ws_dt.data_ptr(), sm)
+            cur, nxt = nxt, cur
+        if first_step > 0:
+            return
+        ws_e = self._buf("tr_ws_emb", lib.imp_embed_bwd_workspace_floats(s["atom_vocab_size"], d))
+        _lib.call("imp_embed_bwd", batch.dev["atom_id"].data_ptr(), cur.data_ptr(), N, s["atom_vocab_size"], d,
+                  G["atom_emb"].data_ptr(), ws_e.data_ptr(), sm)
+        # ---- per-occurrence squared norms of the two Embedding gradients (csrc/occ_norm.cu) -> bucket tail [2], [3]
+        tail = st["tail"]
+        if occurrence_norms:
+            ws_n = self._buf("tr_ws_norm", max(1024, lib.imp_bond_occurrence_norm2_workspace_floats(batch.n_unique)))
+            _lib.call("imp_sumsq", cur.data_ptr(), N * d, tail.data_ptr() + 8, ws_n.data_ptr(), sm)
+            if occ_bond:
+                ob = lib.imp_occ_pack_bytes(d, K)
+                opk = self._buf("tr_occ_packed", ob * 2 * S, torch.uint8)
+                for ti, t in enumerate(TOWERS):
+                    for i in range(S):
+                        _lib.call("imp_occ_pack", self._ptr(f"{t}_bmm_{i}.bond_transform"), d, K, opk.data_ptr() + ob * (ti * S + i), sm)
+                hp = (C.c_void_p * S)(*[h[i].data_ptr() for i in range(S)])
+                dp = (C.c_void_p * S)(*[daggs[i].data_ptr() for i in range(S)])
+                _lib.call("imp_bond_occurrence_norm2", C.byref(g), tr["n_cat_unique"], tr["entry_dst"].data_ptr(), S, hp, dp, d, K,
+                          opk.data_ptr(), opk.data_ptr() + ob * S, tail.data_ptr() + 12, ws_n.data_ptr(), sm)
+
+    def loss_and_grads(self, batch, global_batch=None, occurrence_norms=True):
+        """Forward + backward on a packed batch with ``batch.target``.  Returns (sse, out): device tensors holding this
+        rank's sum of squared errors and predictions; gradients of mean-squared-error over ``global_batch`` pairs
+        (default: this batch; ``"sum"``: un-normalised sum-gradients, for a count that is all-reduced with them) are left
+        in the flat bucket ``self._train['grad']`` (WITHOUT the l2 terms, which the optimizer kernel adds after the
+        all-reduce so that they are counted once).  With ``occurrence_norms`` the tail of the bucket receives the
+        per-occurrence squared norms of the two Embedding gradients (same scaling as the gradients)."""
+        import torch
+
+        s = self.spec
+        d, S = s["atom_dim"], s["num_steps"]
+        fp, mix = s["fp_size"], s["mixing_size"]
+        visc = s["kind"] == "viscosity"
+        fp2 = 0 if visc else fp
+        st = self._train_state()
+        kept = self._forward_kept(batch)
+        P = batch.n_pairs
+        sm = _stream()
+        G = st["g"]
+        lib = _lib.load()
+        pooled, dpooled = kept["pooled"], kept["dpooled"]
         # ---- loss + readout backward
         out = torch.empty(P, dtype=torch.float32, device=self.device)
         rc, ra = self._readout_struct("cat"), self._readout_struct("an")
@@ -207,53 +287,7 @@ class TrainMixin:
         for name, cnt in heads:
             G[name].view(-1).copy_(ro[o:o + cnt])
             o += cnt
-        # ---- back through the pooling and the S steps
-        ga, gb = self._buf("tr_ga", N * d), self._buf("tr_gb", N * d)
-        occ_bond = occurrence_norms and self.bond_occurrence_supported()
-        daggs = [self._buf(f"tr_dagg{i}" if occ_bond else "tr_dagg", N * d) for i in range(S)]  # kept per step for the norm
-        _lib.call("imp_pool_bwd", batch.dev["mol_ptr"].data_ptr(), batch.dev["atom_id"].data_ptr(), 2 * P, dpooled.data_ptr(), d,
-                  ga.data_ptr(), sm)
-        ws_gru = self._buf("tr_ws_gru", lib.imp_gated_update_bwd_workspace_floats(d))
-        dtable = self._buf("tr_dtable", 2 * per)
-        ws_dt = self._buf("tr_ws_dt", max(1, tr["n_chunks"]) * d * d)
-        G["bond_emb"].zero_()
-        cur, nxt = ga, gb
-        for i in reversed(range(S)):
-            dagg = daggs[i]
-            wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
-            gc = G[f"cat_gu_{i}.dense_z.kernel"].data_ptr()  # the layer's 8 variables are contiguous from here
-            gn = G[f"an_gu_{i}.dense_z.kernel"].data_ptr()
-            _lib.call("imp_gated_update_bwd", h[i].data_ptr(), agg[i].data_ptr(), cur.data_ptr(), N, batch.n_cat_atoms, d,
-                      C.byref(wc), C.byref(wa), C.c_float(self.LN_EPS), nxt.data_ptr(), dagg.data_ptr(), gc, gn,
-                      ws_gru.data_ptr(), sm)
-            # dh += sum over the (symmetric) live entries of mult * T[b]^T dagg[src]
-            _lib.call("imp_edge_messages_grouped", C.byref(g), dagg.data_ptr(), d, tab.data_ptr() + 4 * per * i,
-                      tab.data_ptr() + 4 * per * (S + i), 1, msg.data_ptr(), cws.data_ptr(), sm)
-            _lib.call("imp_segment_sum_add", C.byref(g), msg.data_ptr(), d, nxt.data_ptr(), sm)
-            _lib.call("imp_bond_transform_bwd", C.byref(g), tr["entry_dst"].data_ptr(), tr["chunk_begin"].data_ptr(),
-                      tr["chunk_end"].data_ptr(), tr["n_chunks"], tr["bucket_chunk_ptr"].data_ptr(), dagg.data_ptr(),
-                      h[i].data_ptr(), d, K, self._ptr("bond_emb"), self._ptr(f"cat_bmm_{i}.bond_transform"),
-                      self._ptr(f"an_bmm_{i}.bond_transform"), G[f"cat_bmm_{i}.bond_transform"].data_ptr(),
-                      G[f"an_bmm_{i}.bond_transform"].data_ptr(), G["bond_emb"].data_ptr(), dtable.data_ptr(), ws_dt.data_ptr(), sm)
-            cur, nxt = nxt, cur
-        ws_e = self._buf("tr_ws_emb", lib.imp_embed_bwd_workspace_floats(s["atom_vocab_size"], d))
-        _lib.call("imp_embed_bwd", batch.dev["atom_id"].data_ptr(), cur.data_ptr(), N, s["atom_vocab_size"], d,
-                  G["atom_emb"].data_ptr(), ws_e.data_ptr(), sm)
-        # ---- per-occurrence squared norms of the two Embedding gradients (csrc/occ_norm.cu) -> bucket tail [2], [3]
-        tail = st["tail"]
-        if occurrence_norms:
-            ws_n = self._buf("tr_ws_norm", max(1024, lib.imp_bond_occurrence_norm2_workspace_floats(batch.n_unique)))
-            _lib.call("imp_sumsq", cur.data_ptr(), N * d, tail.data_ptr() + 8, ws_n.data_ptr(), sm)
-            if occ_bond:
-                ob = lib.imp_occ_pack_bytes(d, K)
-                opk = self._buf("tr_occ_packed", ob * 2 * S, torch.uint8)
-                for ti, t in enumerate(TOWERS):
-                    for i in range(S):
-                        _lib.call("imp_occ_pack", self._ptr(f"{t}_bmm_{i}.bond_transform"), d, K, opk.data_ptr() + ob * (ti * S + i), sm)
-                hp = (C.c_void_p * S)(*[h[i].data_ptr() for i in range(S)])
-                dp = (C.c_void_p * S)(*[daggs[i].data_ptr() for i in range(S)])
-                _lib.call("imp_bond_occurrence_norm2", C.byref(g), tr["n_cat_unique"], tr["entry_dst"].data_ptr(), S, hp, dp, d, K,
-                          opk.data_ptr(), opk.data_ptr() + ob * S, tail.data_ptr() + 12, ws_n.data_ptr(), sm)
+        self._backward_base(batch, kept, occurrence_norms=occurrence_norms)
         return st["sse"], out
 
     def gradients(self):

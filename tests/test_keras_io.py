@@ -85,3 +85,24 @@ def test_reader_reports_a_missing_layer_by_name(tmp_path):
     data = {k: v for k, v in data.items() if "bond_matrix_message_1" not in k}
     with pytest.raises(ValueError, match="cat_bmm_1"):
         keras_io.params_from_keras(config, data)
+
+
+def test_transfer_archive_keeps_the_named_head_layers(tmp_path):
+    """build_transfer_model's archive (train_melting_point_transfer.py:76-106): the base is cut at mix_cat_an (no Dense(3)
+    head), the mp_* / melting_point layers carry their own names and come back as ``extra`` in Keras variable order."""
+    from ionic_mpnn_b200.model import keras_default_init, make_spec
+    from ionic_mpnn_b200.transfer import head_default_init
+
+    spec = make_spec("viscosity", atom_dim=8, bond_dim=4, fp_size=8, mixing_size=6, num_steps=2)
+    base = {k: v for k, v in keras_default_init(spec, seed=2).items() if not k.startswith("head")}
+    head = head_default_init(spec["mixing_size"], seed=3)
+    head["mp_bn_1.moving_mean"] = np.linspace(-1, 1, 256).astype(np.float32)
+    path = str(tmp_path / "t.keras")
+    keras_io.export_keras(path, spec, {**base, **head}, transfer_head=True)
+    config, data = keras_io.read_keras(path)
+    kind, params, extra = keras_io.params_from_keras(config, data)
+    assert kind == "transfer" and set(params) == set(base)
+    assert all(np.array_equal(params[k], base[k]) for k in base)
+    assert set(extra) == {"mp_dense_1", "mp_bn_1", "mp_dense_2", "mp_dense_3", "melting_point"}
+    assert np.array_equal(extra["mp_bn_1"][2], head["mp_bn_1.moving_mean"]) and len(extra["mp_bn_1"]) == 4
+    assert np.array_equal(extra["melting_point"][0], head["melting_point.kernel"])

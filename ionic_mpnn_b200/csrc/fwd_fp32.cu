@@ -578,125 +578,97 @@ __global__ void __launch_bounds__(K6_WARPS * 32) pool_head_kernel(K6Args a) {
 
 
 // ----------------------------------------------------------------------------------------- K6, fast form
-// Readout on pooled sums for d, fp, mix, fp2 <= 32 (both reference models): lane o keeps column o of every Dense kernel
-// in REGISTERS for the whole kernel, so a multiply-accumulate costs one broadcast shared-memory read per four FMAs
-// instead of two reads per FMA.  Same arithmetic and summation order as pool_head_kernel.
-constexpr int R32_WARPS = 8;
-constexpr int R32_NP = 4;  // pairs per warp iteration: four independent dependency chains per lane (the kernel is latency-bound:
-                           // 160 weight registers per lane leave 8 warps per SM)
-__global__ void __launch_bounds__(R32_WARPS * 32) readout32_kernel(K6Args a) {
-  __shared__ __align__(16) float sx[R32_WARPS][R32_NP][3][32];  // per warp and pair: pool, v1, mixed
-  const int d = a.d, fp = a.fp, mix = a.mix, fp2 = a.fp2, nh = fp2 > 0 ? fp2 : 3;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float wfp[2][32], wmx[2][32], w1[32];
-  float bfp[2], bmx[2], b1v, w2v = 0.f;
+// Readout on pooled sums for d, fp, mix, fp2 <= 32 (both reference models): ONE THREAD PER ION PAIR.  The five small Dense
+// layers (train_viscosity.py:189-204 / train_melting_point.py:173-198) are matrix-vector products of at most 32 x 32 per
+// pair; a thread keeps the 32 outputs of a layer in registers, reads its input vector from its own (padded, conflict-free)
+// row of shared memory and the weight row W[k][:] as eight broadcast 16-byte reads: 41 instructions per 32 FMAs, no
+// cross-lane step, 32 independent accumulation chains per thread (the previous warp-per-pair form with column-resident
+// weights needed 160 weight registers per lane -- 8 warps per SM -- and was latency-bound at 0.3 instructions per clock).
+// Accumulation order per output: bias, then k ascending -- as pool_head_kernel.
+constexpr int R32_THREADS = 128;
+constexpr int R32_XS = 33;  // floats per thread row
+struct R32Smem {
+  float W[5][32 * 32];   // fp_cat, mix_cat, fp_an, mix_an, head (rows k, 32 zero-padded columns)
+  float b[5][32];
+  float w2[32];
+  float x[R32_THREADS * R32_XS];
+};
+__device__ __forceinline__ void r32_layer(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ xrow, int n_in,
+                                          float (&acc)[32]) {
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const imp_readout_weights_t& w = t == 0 ? a.wc : a.wa;
+  for (int j = 0; j < 32; ++j) acc[j] = b[j];
+#pragma unroll 2
+  for (int k = 0; k < n_in; ++k) {
+    const float xk = xrow[k];
+    const float4* w4 = reinterpret_cast<const float4*>(W + k * 32);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      wfp[t][k] = (k < d && lane < fp) ? w.W_fp[k * fp + lane] : 0.f;
-      wmx[t][k] = (k < fp && lane < mix) ? w.W_mix[k * mix + lane] : 0.f;
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 w = w4[j4];
+      acc[4 * j4] = fmaf(xk, w.x, acc[4 * j4]), acc[4 * j4 + 1] = fmaf(xk, w.y, acc[4 * j4 + 1]);
+      acc[4 * j4 + 2] = fmaf(xk, w.z, acc[4 * j4 + 2]), acc[4 * j4 + 3] = fmaf(xk, w.w, acc[4 * j4 + 3]);
     }
-    bfp[t] = lane < fp ? w.b_fp[lane] : 0.f;
-    bmx[t] = lane < mix ? w.b_mix[lane] : 0.f;
   }
-#pragma unroll
-  for (int k = 0; k < 32; ++k) w1[k] = (k < mix && lane < nh) ? a.W1[k * nh + lane] : 0.f;
-  b1v = lane < nh ? a.b1[lane] : 0.f;
-  if (fp2 > 0 && lane < fp2) w2v = a.W2[lane];
-  const int warp_global = blockIdx.x * R32_WARPS + warp, n_warps = gridDim.x * R32_WARPS;
-  // a warp takes R32_NP consecutive pairs per iteration; the pooled rows (and temperatures) of the NEXT iteration are in
-  // flight while the current one computes
-  float nx[R32_NP][2], nT[R32_NP];
-  auto fetch = [&](int base) {
-#pragma unroll
-    for (int q = 0; q < R32_NP; ++q) {
-      const int pr = base + q;
-      const bool ok = pr < a.n_pairs;
-      nx[q][0] = (ok && lane < d) ? __ldg(a.pooled + (int64_t)pr * d + lane) : 0.f;
-      nx[q][1] = (ok && lane < d) ? __ldg(a.pooled + (int64_t)(a.n_pairs + pr) * d + lane) : 0.f;
-      nT[q] = (ok && fp2 == 0) ? __ldg(a.T + pr) : 0.f;
-    }
-  };
-  fetch(warp_global * R32_NP);
-  for (int base = warp_global * R32_NP; base < a.n_pairs; base += n_warps * R32_NP) {
-    float cx[R32_NP][2], cT[R32_NP];
-#pragma unroll
-    for (int q = 0; q < R32_NP; ++q) cx[q][0] = nx[q][0], cx[q][1] = nx[q][1], cT[q] = nT[q];
-    fetch(base + n_warps * R32_NP);
-    float mixv[R32_NP];
+}
+__global__ void __launch_bounds__(R32_THREADS) readout32_kernel(K6Args a) {
+  extern __shared__ __align__(16) unsigned char r32_raw[];
+  R32Smem& s = *reinterpret_cast<R32Smem*>(r32_raw);
+  const int d = a.d, fp = a.fp, mix = a.mix, fp2 = a.fp2, nh = fp2 > 0 ? fp2 : 3;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 5 * 32 * 32; i += R32_THREADS) {
+    const int m = i / 1024, k = (i % 1024) / 32, j = i % 32;
+    float v = 0.f;
+    if (m == 0 && k < d && j < fp) v = a.wc.W_fp[k * fp + j];
+    if (m == 1 && k < fp && j < mix) v = a.wc.W_mix[k * mix + j];
+    if (m == 2 && k < d && j < fp) v = a.wa.W_fp[k * fp + j];
+    if (m == 3 && k < fp && j < mix) v = a.wa.W_mix[k * mix + j];
+    if (m == 4 && k < mix && j < nh) v = a.W1[k * nh + j];
+    s.W[m][k * 32 + j] = v;
+  }
+  for (int i = tid; i < 5 * 32; i += R32_THREADS) {
+    const int m = i / 32, j = i % 32;
+    float v = 0.f;
+    if (m == 0 && j < fp) v = a.wc.b_fp[j];
+    if (m == 1 && j < mix) v = a.wc.b_mix[j];
+    if (m == 2 && j < fp) v = a.wa.b_fp[j];
+    if (m == 3 && j < mix) v = a.wa.b_mix[j];
+    if (m == 4 && j < nh) v = a.b1[j];
+    s.b[m][j] = v;
+  }
+  if (tid < 32) s.w2[tid] = (fp2 > 0 && tid < fp2) ? a.W2[tid] : 0.f;
+  __syncthreads();
+  float* xrow = &s.x[tid * R32_XS];
+  float acc[32], mixed[32];
+  for (int pair = blockIdx.x * R32_THREADS + tid; pair < a.n_pairs; pair += gridDim.x * R32_THREADS) {
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
-#pragma unroll
-      for (int q = 0; q < R32_NP; ++q) sx[warp][q][0][lane] = cx[q][t];
-      __syncwarp();
-      float acc[R32_NP];
-#pragma unroll
-      for (int q = 0; q < R32_NP; ++q) acc[q] = bfp[t];
-#pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) {
-#pragma unroll
-        for (int q = 0; q < R32_NP; ++q) {
-          const float4 x = *reinterpret_cast<const float4*>(&sx[warp][q][0][4 * k4]);
-          acc[q] = fmaf(x.x, wfp[t][4 * k4], acc[q]), acc[q] = fmaf(x.y, wfp[t][4 * k4 + 1], acc[q]);
-          acc[q] = fmaf(x.z, wfp[t][4 * k4 + 2], acc[q]), acc[q] = fmaf(x.w, wfp[t][4 * k4 + 3], acc[q]);
-        }
+      const float4* src = reinterpret_cast<const float4*>(a.pooled + (int64_t)(t * a.n_pairs + pair) * d);
+      for (int c = 0; c < d / 4; ++c) {
+        const float4 v = __ldg(src + c);
+        xrow[4 * c] = v.x, xrow[4 * c + 1] = v.y, xrow[4 * c + 2] = v.z, xrow[4 * c + 3] = v.w;
       }
+      r32_layer(s.W[2 * t], s.b[2 * t], xrow, d, acc);        // Dense(fp_size, relu)
 #pragma unroll
-      for (int q = 0; q < R32_NP; ++q) sx[warp][q][1][lane] = lane < fp ? fmaxf(acc[q], 0.f) : 0.f;
-      __syncwarp();
+      for (int j = 0; j < 32; ++j) xrow[j] = fmaxf(acc[j], 0.f);
+      r32_layer(s.W[2 * t + 1], s.b[2 * t + 1], xrow, fp, acc);  // Dense(mixing_size, relu)
 #pragma unroll
-      for (int q = 0; q < R32_NP; ++q) acc[q] = bmx[t];
-#pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) {
-#pragma unroll
-        for (int q = 0; q < R32_NP; ++q) {
-          const float4 x = *reinterpret_cast<const float4*>(&sx[warp][q][1][4 * k4]);
-          acc[q] = fmaf(x.x, wmx[t][4 * k4], acc[q]), acc[q] = fmaf(x.y, wmx[t][4 * k4 + 1], acc[q]);
-          acc[q] = fmaf(x.z, wmx[t][4 * k4 + 2], acc[q]), acc[q] = fmaf(x.w, wmx[t][4 * k4 + 3], acc[q]);
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < R32_NP; ++q) {
-        const float v2 = lane < mix ? fmaxf(acc[q], 0.f) : 0.f;
-        mixv[q] = t == 0 ? v2 : mixv[q] + v2;
-      }
-      __syncwarp();
-    }
-#pragma unroll
-    for (int q = 0; q < R32_NP; ++q) sx[warp][q][2][lane] = mixv[q];
-    __syncwarp();
-    float hp[R32_NP];
-#pragma unroll
-    for (int q = 0; q < R32_NP; ++q) hp[q] = b1v;
-#pragma unroll
-    for (int k4 = 0; k4 < 8; ++k4) {
-#pragma unroll
-      for (int q = 0; q < R32_NP; ++q) {
-        const float4 x = *reinterpret_cast<const float4*>(&sx[warp][q][2][4 * k4]);
-        hp[q] = fmaf(x.x, w1[4 * k4], hp[q]), hp[q] = fmaf(x.y, w1[4 * k4 + 1], hp[q]);
-        hp[q] = fmaf(x.z, w1[4 * k4 + 2], hp[q]), hp[q] = fmaf(x.w, w1[4 * k4 + 3], hp[q]);
+      for (int j = 0; j < 32; ++j) {
+        const float v2 = fmaxf(acc[j], 0.f);
+        mixed[j] = t == 0 ? v2 : mixed[j] + v2;  // AddTwoTensors / Add
       }
     }
 #pragma unroll
-    for (int q = 0; q < R32_NP; ++q) {
-      const int pair = base + q;
-      if (fp2 == 0) {
-        const float p0 = __shfl_sync(0xffffffffu, hp[q], 0), p1 = __shfl_sync(0xffffffffu, hp[q], 1), p2 = __shfl_sync(0xffffffffu, hp[q], 2);
-        if (lane == q && pair < a.n_pairs) {  // one lane per pair of the group evaluates the head
-          const float B = fminf(fmaxf(softplusf_precise(p1), 0.0f), 20.0f);
-          const float Cc = fminf(fmaxf(softplusf_precise(p2), 0.1f), 50.0f);
-          a.out[pair] = p0 + B / (cT[q] / 100.0f + Cc + 1e-6f);
-        }
-      } else {
-        const float part = lane < fp2 ? fmaxf(hp[q], 0.f) * w2v : 0.f;
-        float tot = 0.f;
-        for (int l = 0; l < 32; ++l) tot += __shfl_sync(0xffffffffu, part, l);  // fixed order
-        if (lane == 0 && pair < a.n_pairs) a.out[pair] = tot + a.b2[0];
-      }
+    for (int j = 0; j < 32; ++j) xrow[j] = mixed[j];
+    r32_layer(s.W[4], s.b[4], xrow, mix, acc);
+    if (fp2 == 0) {  // A + B / (T / 100 + C + 1e-6), B and C clipped softplus (models/layers.py:10-42)
+      const float B = fminf(fmaxf(softplusf_precise(acc[1]), 0.0f), 20.0f);
+      const float Cc = fminf(fmaxf(softplusf_precise(acc[2]), 0.1f), 50.0f);
+      a.out[pair] = acc[0] + B / (__ldg(a.T + pair) / 100.0f + Cc + 1e-6f);
+    } else {
+      float tot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tot = __fadd_rn(tot, __fmul_rn(fmaxf(acc[j], 0.f), s.w2[j]));  // fixed order, no contraction
+      a.out[pair] = tot + a.b2[0];
     }
-    __syncwarp();
   }
 }
 
@@ -1091,9 +1063,11 @@ static int launch_k6(const imp_graph_t* g, const float* d_h, const float* d_pool
   IMP_CUDA(cudaFuncSetAttribute(pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   IMP_REQUIRE(smem <= 200 * 1024, IMP_ERR_DIM, "%s: readout weights need %zu B of shared memory", who, smem);
   if (d_pooled && !aux && d <= 32 && fp <= 32 && mix <= 32 && fp2 <= 32) {  // both reference models: register-resident weights
-    int nb = (int)ceil_div(g->n_pairs, R32_WARPS * R32_NP);
-    if (nb > 148 * 6) nb = 148 * 6;
-    readout32_kernel<<<nb, R32_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    IMP_REQUIRE(d % 4 == 0, IMP_ERR_DIM, "%s: atom_dim %d must be a multiple of 4", who, d);
+    int nb = (int)ceil_div(g->n_pairs, R32_THREADS);
+    if (nb > 148 * 5) nb = 148 * 5;
+    IMP_CUDA(cudaFuncSetAttribute(readout32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(R32Smem)));
+    readout32_kernel<<<nb, R32_THREADS, sizeof(R32Smem), (cudaStream_t)stream>>>(a);
     IMP_LAUNCH_CHECK();
     return 0;
   }

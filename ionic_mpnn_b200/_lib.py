@@ -20,6 +20,11 @@ class ImpError(RuntimeError):
     pass
 
 
+class PlanCapacityError(ImpError):
+    """The tile plan of the fused forward ran out of tile records (MPNNModel.plan_slack): the call is repeated with the
+    safe bound."""
+
+
 class Ions(C.Structure):
     _fields_ = [("n_ions", C.c_int32), ("atom_ptr", vp), ("atom_ids", vp), ("edge_ptr", vp), ("edge_src", vp),
                 ("edge_dst", vp), ("bond_ids", vp)]

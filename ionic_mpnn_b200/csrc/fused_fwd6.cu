@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
 
   const int tower = blockIdx.x >= a.n_cta_cat;
   const FusedPlanHeader* hdr = reinterpret_cast<const FusedPlanHeader*>(a.plan);
+  if (__ldg(&hdr->status) == 2) return;  // the plan ran out of tile records: some are unwritten (the host raises, model.check_status)
   const int n_tiles = min(__ldg(&hdr->n_tiles[tower]), __ldg(&hdr->cap[tower]));
   const FusedTile* tiles = reinterpret_cast<const FusedTile*>(a.plan + FP_HEADER_BYTES) + (size_t)(tower ? __ldg(&hdr->cap[0]) : 0);
   const int n_cta_tower = tower ? (int)gridDim.x - a.n_cta_cat : a.n_cta_cat;

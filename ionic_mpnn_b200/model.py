@@ -536,6 +536,15 @@ class MPNNModel(TrainMixin):
             nb = _lib.load().imp_fused_plan_bytes(P, batch.n_atoms, batch.n_unique, batch.max_mol_atoms)
             if nb < 0:
                 raise _lib.ImpError(f"imp_fused_plan_bytes: {nb}")
+            # imp_fused_plan_bytes is the bound that can never overflow (one tile per molecule in the worst case: 4 KB per
+            # pair).  Best-fit tiles are ~98 % full, so the buffer is sized for plan_slack x (atoms of the larger tower /
+            # 128) tiles per tower instead; a batch that needs more (many rows closed by the entry limit) reports status 2
+            # and check_status() switches this model to the safe bound.
+            slack = getattr(self, "plan_slack", 1.25)
+            if slack is not None:
+                tower = max(batch.n_cat_atoms, batch.n_atoms - batch.n_cat_atoms)
+                cap = int(slack * tower / 128) + (P + 255) // 256 + 16
+                nb = min(nb, 256 + 2 * cap * 2048)
             plan = self._buf("fused_plan", nb, torch.uint8)
             _lib.call("imp_fused_plan", C.byref(g) if g is not None else None, C.byref(cg) if cg is not None else None,
                       s["atom_vocab_size"], batch.max_mol_atoms, plan.data_ptr(), nb, st)
@@ -633,7 +642,12 @@ class MPNNModel(TrainMixin):
             self._ws["status"].zero_()
         out = self.forward_packed(batch)
         torch.cuda.current_stream().synchronize()
-        self.check_status()
+        try:
+            self.check_status()
+        except _lib.PlanCapacityError:  # the plan buffer was sized by plan_slack and this batch needed more: once more
+            out = self.forward_packed(batch)
+            torch.cuda.current_stream().synchronize()
+            self.check_status()
         return out.cpu().numpy().reshape(-1, 1)
 
     __call__ = predict
@@ -648,12 +662,16 @@ class MPNNModel(TrainMixin):
         plan = self._ws.get("fused_plan")
         if plan is not None and plan.numel() >= 20:
             code = int(plan[16:20].view(torch.int32).item())
+            if code == 2:
+                plan[16:20].zero_()
+                self.plan_slack = None
+                raise _lib.PlanCapacityError("fused forward: the tile plan needed more tiles than plan_slack allowed; the model "
+                                             "now sizes the plan buffer by the safe bound -- run the batch again")
             if code != 0:
                 plan[16:20].zero_()
-                raise _lib.ImpError("fused forward: the tile plan refused the batch (" +
-                                    ("a molecule with > 128 atoms, a row with > 31 entries or > 336 entries per molecule"
-                                     if code == 1 else "tile capacity exceeded") +
-                                    "); set model.use_plan = False (self-contained fused kernel) or fused=False")
+                raise _lib.ImpError("fused forward: the tile plan refused the batch (a molecule with > 128 atoms, a row with "
+                                    "> 31 entries or > 336 entries per molecule); set model.use_plan = False (self-contained "
+                                    "fused kernel) or fused=False")
         st = self._ws.get("status")
         if st is None or st.numel() != 1:
             return

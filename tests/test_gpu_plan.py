@@ -120,3 +120,23 @@ def test_planned_forward_matches_the_self_contained_kernel_and_the_fp32_path(n_p
         assert _rel(a, want32) <= RTOL16
     assert planned.launches_per_forward(batch) == 4
     assert _lib.load().imp_fused_plan_bytes(-1, 0, 0, 0) < 0
+
+
+def test_plan_capacity_overflow_is_reported_and_predict_retries():
+    """plan_slack sizes the plan buffer for well-filled tiles; a batch that needs more tiles reports status 2, the model
+    falls back to the safe bound and predict() repeats the call."""
+    from ionic_mpnn_b200 import _lib, graph
+    from ionic_mpnn_b200.viscosity import build_model
+
+    batch, _, _ = graph.synth_batch(600, seed=8, n_min=65, n_max=70)  # one molecule per tile: 2x the tiles plan_slack expects
+    ref = build_model(124, 72, precision="fp32", seed=3)
+    want = ref.predict(batch)
+    fz = build_model(124, 72, precision="fp16", seed=3, fused=True)
+    fz.forward_packed(batch)
+    torch.cuda.synchronize()
+    with pytest.raises(_lib.PlanCapacityError):
+        fz.check_status()
+    assert fz.plan_slack is None
+    fz2 = build_model(124, 72, precision="fp16", seed=3, fused=True)
+    got = fz2.predict(batch)  # retries by itself
+    assert _rel(got, want) <= RTOL16

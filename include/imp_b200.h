@@ -424,6 +424,16 @@ int imp_pool_bwd(const int32_t* d_mol_ptr, const int32_t* d_atom_id, int32_t n_m
                  float* d_dh, void* stream);
 /* B4: GatedUpdate backward (models/layers.py:142-156); recomputes the gates from (h, agg). */
 int64_t imp_gated_update_bwd_workspace_floats(int32_t d);
+/* Training form of the pair: imp_gated_update_train is imp_gated_update that also keeps the gates z, r and the candidate
+ * tanh(.) of every atom ([N, d] each); imp_gated_update_bwd_stored reads them instead of recomputing the three Dense layers
+ * (a third of the backward kernel's arithmetic) and returns the same gradients as imp_gated_update_bwd. */
+int imp_gated_update_train(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
+                           const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_h_out, float* d_z,
+                           float* d_r, float* d_ht, void* stream);
+int imp_gated_update_bwd_stored(const float* d_h, const float* d_agg, const float* d_z, const float* d_r, const float* d_ht,
+                                const float* d_gout, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
+                                const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_dh, float* d_dagg,
+                                float* d_grads_cat, float* d_grads_an, float* d_workspace, void* stream);
 int imp_gated_update_bwd(const float* d_h, const float* d_agg, const float* d_gout, int32_t n_atoms, int32_t n_cat_atoms,
                          int32_t d, const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_dh,
                          float* d_dagg, float* d_grads_cat, float* d_grads_an, float* d_workspace, void* stream);

@@ -334,12 +334,15 @@ __device__ __forceinline__ float gb_row_sum(float v) {  // over the 8 lanes (lan
 
 // Persistent CTAs; CTAs [0, n_cta_cat) walk the cation tiles, the rest the anion tiles.  Per-CTA partial weight
 // gradients are written to partial[cta][gru_grad_floats]; imp_gated_update_bwd reduces them per tower in CTA order.
-template <int D>
+// STORED: the gates z, r and the candidate tanh(.) were kept by the forward (imp_gated_update_train) and are read instead of
+// recomputed -- a third of the kernel's FMAs.
+template <int D, bool STORED>
 __global__ void __launch_bounds__(GB_THREADS) gated_update_bwd_kernel(const float* __restrict__ h, const float* __restrict__ agg,
                                                                       const float* __restrict__ g_out, int n_atoms, int n_cat,
                                                                       int n_cta_cat, imp_gru_weights_t wc, imp_gru_weights_t wa,
                                                                       float eps, float* __restrict__ dh, float* __restrict__ dagg,
-                                                                      float* __restrict__ partial) {
+                                                                      float* __restrict__ partial, const float* __restrict__ zs,
+                                                                      const float* __restrict__ rs, const float* __restrict__ hts) {
   static_assert(D == 32, "gated_update_bwd is instantiated for atom_dim 32");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GruBwdSmem<D>& s = *reinterpret_cast<GruBwdSmem<D>*>(smem_raw);
@@ -414,46 +417,64 @@ __global__ void __launch_bounds__(GB_THREADS) gated_update_bwd_kernel(const floa
       const float4 t4 = *reinterpret_cast<const float4*>(Xb + i * 4 * GB_XS + c0);
       hx[i][0] = t4.x, hx[i][1] = t4.y, hx[i][2] = t4.z, hx[i][3] = t4.w;
     }
+    if constexpr (STORED) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = ar0 + 4 * i;
+        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f), r4 = z4, t4 = z4;
+        if (r < rows) {
+          z4 = __ldg(reinterpret_cast<const float4*>(zs + (int64_t)(a0 + r) * D) + cg);
+          r4 = __ldg(reinterpret_cast<const float4*>(rs + (int64_t)(a0 + r) * D) + cg);
+          t4 = __ldg(reinterpret_cast<const float4*>(hts + (int64_t)(a0 + r) * D) + cg);
+        }
+        zv[i][0] = z4.x, zv[i][1] = z4.y, zv[i][2] = z4.z, zv[i][3] = z4.w;
+        rv[i][0] = r4.x, rv[i][1] = r4.y, rv[i][2] = r4.z, rv[i][3] = r4.w;
+        acc[i][0] = t4.x, acc[i][1] = t4.y, acc[i][2] = t4.z, acc[i][3] = t4.w;
+        *reinterpret_cast<float4*>(RHb + i * 4 * GB_GS + c0) =
+            make_float4(rv[i][0] * hx[i][0], rv[i][1] * hx[i][1], rv[i][2] * hx[i][2], rv[i][3] * hx[i][3]);
+      }
+    } else {
     // z
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[i][c] = s.bz[c0 + c];
-    gb4_dense<GB_XS, D>(acc, s.Wz, Xb, c0);
-    gb4_dense<GB_XS, D>(acc, s.Wz + D * D, Xb + D, c0);
+        for (int c = 0; c < 4; ++c) acc[i][c] = s.bz[c0 + c];
+      gb4_dense<GB_XS, D>(acc, s.Wz, Xb, c0);
+      gb4_dense<GB_XS, D>(acc, s.Wz + D * D, Xb + D, c0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) zv[i][c] = bw_sigmoid(acc[i][c]);
-    // r, r*h
+        for (int c = 0; c < 4; ++c) zv[i][c] = bw_sigmoid(acc[i][c]);
+      // r, r*h
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[i][c] = s.br[c0 + c];
-    gb4_dense<GB_XS, D>(acc, s.Wr, Xb, c0);
-    gb4_dense<GB_XS, D>(acc, s.Wr + D * D, Xb + D, c0);
+        for (int c = 0; c < 4; ++c) acc[i][c] = s.br[c0 + c];
+      gb4_dense<GB_XS, D>(acc, s.Wr, Xb, c0);
+      gb4_dense<GB_XS, D>(acc, s.Wr + D * D, Xb + D, c0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 4; ++i) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) rv[i][c] = bw_sigmoid(acc[i][c]);
-      *reinterpret_cast<float4*>(RHb + i * 4 * GB_GS + c0) =
-          make_float4(rv[i][0] * hx[i][0], rv[i][1] * hx[i][1], rv[i][2] * hx[i][2], rv[i][3] * hx[i][3]);
+        for (int c = 0; c < 4; ++c) rv[i][c] = bw_sigmoid(acc[i][c]);
+        *reinterpret_cast<float4*>(RHb + i * 4 * GB_GS + c0) =
+            make_float4(rv[i][0] * hx[i][0], rv[i][1] * hx[i][1], rv[i][2] * hx[i][2], rv[i][3] * hx[i][3]);
+      }
+      __syncwarp();
+      // candidate
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][c] = s.bh[c0 + c];
+      gb4_dense<GB_GS, D>(acc, s.Wh, RHb, c0);
+      gb4_dense<GB_XS, D>(acc, s.Wh + D * D, Xb + D, c0);
     }
-    __syncwarp();
-    // candidate
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[i][c] = s.bh[c0 + c];
-    gb4_dense<GB_GS, D>(acc, s.Wh, RHb, c0);
-    gb4_dense<GB_XS, D>(acc, s.Wh + D * D, Xb + D, c0);
     // blend, LayerNorm forward + backward, gate gradients (per atom row i)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float nrm[4], mean = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        acc[i][c] = tanhf(acc[i][c]);  // ht
+        if constexpr (!STORED) acc[i][c] = tanhf(acc[i][c]);  // ht
         nrm[c] = fmaf(zv[i][c], acc[i][c] - hx[i][c], hx[i][c]);
         mean += nrm[c];
       }
@@ -919,14 +940,14 @@ extern "C" int64_t imp_gated_update_bwd_workspace_floats(int32_t d) {
   return d == 32 ? (int64_t)bw_sm_count() * gru_grad_floats<32>() : (int64_t)IMP_ERR_DIM;
 }
 
-extern "C" int imp_gated_update_bwd(const float* d_h, const float* d_agg, const float* d_gout, int32_t n_atoms,
-                                    int32_t n_cat_atoms, int32_t d, const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an,
-                                    float eps, float* d_dh, float* d_dagg, float* d_grads_cat, float* d_grads_an,
-                                    float* d_workspace, void* stream) {
-  IMP_REQUIRE(n_atoms >= 0 && n_cat_atoms >= 0 && n_cat_atoms <= n_atoms, IMP_ERR_ARG, "imp_gated_update_bwd: bad sizes");
-  IMP_REQUIRE(d == 32, IMP_ERR_DIM, "imp_gated_update_bwd: atom_dim %d not supported (32)", d);
+static int gated_update_bwd_any(const float* d_h, const float* d_agg, const float* d_z, const float* d_r, const float* d_ht,
+                               const float* d_gout, int32_t n_atoms, int32_t n_cat_atoms, int32_t d, const imp_gru_weights_t* w_cat,
+                               const imp_gru_weights_t* w_an, float eps, float* d_dh, float* d_dagg, float* d_grads_cat,
+                               float* d_grads_an, float* d_workspace, void* stream, const char* who) {
+  IMP_REQUIRE(n_atoms >= 0 && n_cat_atoms >= 0 && n_cat_atoms <= n_atoms, IMP_ERR_ARG, "%s: bad sizes", who);
+  IMP_REQUIRE(d == 32, IMP_ERR_DIM, "%s: atom_dim %d not supported (32)", who, d);
   IMP_REQUIRE(d_h && d_agg && d_gout && d_dh && d_dagg && d_grads_cat && d_grads_an && d_workspace && w_cat && w_an, IMP_ERR_ARG,
-              "imp_gated_update_bwd: null pointer");
+              "%s: null pointer", who);
   constexpr int D = 32;
   const int sms = bw_sm_count();
   const int tiles_cat = (int)ceil_div(n_cat_atoms, GB_TILE), tiles_an = (int)ceil_div(n_atoms - n_cat_atoms, GB_TILE);
@@ -934,9 +955,17 @@ extern "C" int imp_gated_update_bwd(const float* d_h, const float* d_agg, const 
   n_cat = n_cat < 1 ? 1 : (n_cat > sms - 1 ? sms - 1 : n_cat);
   const int grid = sms;
   const size_t smem = sizeof(GruBwdSmem<D>);
-  IMP_CUDA(cudaFuncSetAttribute(gated_update_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gated_update_bwd_kernel<D><<<grid, GB_THREADS, smem, (cudaStream_t)stream>>>(d_h, d_agg, d_gout, n_atoms, n_cat_atoms, n_cat, *w_cat,
-                                                                            *w_an, eps, d_dh, d_dagg, d_workspace);
+  if (d_z) {
+    IMP_CUDA(cudaFuncSetAttribute(gated_update_bwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gated_update_bwd_kernel<D, true><<<grid, GB_THREADS, smem, (cudaStream_t)stream>>>(d_h, d_agg, d_gout, n_atoms, n_cat_atoms, n_cat,
+                                                                                   *w_cat, *w_an, eps, d_dh, d_dagg, d_workspace,
+                                                                                   d_z, d_r, d_ht);
+  } else {
+    IMP_CUDA(cudaFuncSetAttribute(gated_update_bwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gated_update_bwd_kernel<D, false><<<grid, GB_THREADS, smem, (cudaStream_t)stream>>>(d_h, d_agg, d_gout, n_atoms, n_cat_atoms, n_cat,
+                                                                                    *w_cat, *w_an, eps, d_dh, d_dagg, d_workspace,
+                                                                                    nullptr, nullptr, nullptr);
+  }
   IMP_LAUNCH_CHECK();
   const int n = gru_grad_floats<D>();
   reduce_partials_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_workspace, n_cat, n, n, d_grads_cat, 0);
@@ -945,6 +974,23 @@ extern "C" int imp_gated_update_bwd(const float* d_h, const float* d_agg, const 
                                                                             d_grads_an, 0);
   IMP_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int imp_gated_update_bwd(const float* d_h, const float* d_agg, const float* d_gout, int32_t n_atoms,
+                                    int32_t n_cat_atoms, int32_t d, const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an,
+                                    float eps, float* d_dh, float* d_dagg, float* d_grads_cat, float* d_grads_an,
+                                    float* d_workspace, void* stream) {
+  return gated_update_bwd_any(d_h, d_agg, nullptr, nullptr, nullptr, d_gout, n_atoms, n_cat_atoms, d, w_cat, w_an, eps, d_dh, d_dagg,
+                              d_grads_cat, d_grads_an, d_workspace, stream, "imp_gated_update_bwd");
+}
+
+extern "C" int imp_gated_update_bwd_stored(const float* d_h, const float* d_agg, const float* d_z, const float* d_r, const float* d_ht,
+                                           const float* d_gout, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
+                                           const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_dh,
+                                           float* d_dagg, float* d_grads_cat, float* d_grads_an, float* d_workspace, void* stream) {
+  IMP_REQUIRE(d_z && d_r && d_ht, IMP_ERR_ARG, "imp_gated_update_bwd_stored: null gate pointers");
+  return gated_update_bwd_any(d_h, d_agg, d_z, d_r, d_ht, d_gout, n_atoms, n_cat_atoms, d, w_cat, w_an, eps, d_dh, d_dagg, d_grads_cat,
+                              d_grads_an, d_workspace, stream, "imp_gated_update_bwd_stored");
 }
 
 extern "C" int imp_bond_transform_bwd(const imp_graph_t* g, const int32_t* d_entry_dst, const int32_t* d_chunk_begin,

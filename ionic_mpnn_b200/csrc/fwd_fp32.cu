@@ -891,7 +891,11 @@ __device__ __forceinline__ float k5b_row_sum(float v) {
 
 __global__ void __launch_bounds__(K5B_THREADS, 2) gated_update32_kernel(const float* __restrict__ h, const float* __restrict__ agg,
                                                                         int n_atoms, int n_cat, int n_cta_cat, imp_gru_weights_t wc,
-                                                                        imp_gru_weights_t wa, float eps, float* __restrict__ h_out) {
+                                                                        imp_gru_weights_t wa, float eps, float* __restrict__ h_out,
+                                                                        float* __restrict__ z_out, float* __restrict__ r_out,
+                                                                        float* __restrict__ ht_out) {
+  // z_out / r_out / ht_out (all or none): the gates and the candidate of every atom, kept for the backward pass
+  // (imp_gated_update_bwd_stored) so that it does not recompute the three Dense layers
   constexpr int D = 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   K5BSmem& s = *reinterpret_cast<K5BSmem*>(smem_raw);
@@ -944,10 +948,12 @@ __global__ void __launch_bounds__(K5B_THREADS, 2) gated_update32_kernel(const fl
   k5b_dense<K5B_XS>(acc, s.Wr, Xb, c0);
   k5b_dense<K5B_XS>(acc, s.Wr + D * D, Xb + D, c0);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    *reinterpret_cast<float4*>(RHb + i * 4 * K5B_GS + c0) =
-        make_float4(sigmoidf_precise(acc[i][0]) * hx[i][0], sigmoidf_precise(acc[i][1]) * hx[i][1],
-                    sigmoidf_precise(acc[i][2]) * hx[i][2], sigmoidf_precise(acc[i][3]) * hx[i][3]);
+  for (int i = 0; i < 4; ++i) {
+    const float4 rv = make_float4(sigmoidf_precise(acc[i][0]), sigmoidf_precise(acc[i][1]), sigmoidf_precise(acc[i][2]),
+                                  sigmoidf_precise(acc[i][3]));
+    *reinterpret_cast<float4*>(RHb + i * 4 * K5B_GS + c0) = make_float4(rv.x * hx[i][0], rv.y * hx[i][1], rv.z * hx[i][2], rv.w * hx[i][3]);
+    if (r_out && 16 * warp + qd + 4 * i < rows) reinterpret_cast<float4*>(r_out + (int64_t)(a0 + 16 * warp + qd + 4 * i) * D)[cg] = rv;
+  }
   // z gate (independent of r * h: runs while the warp's RH rows settle)
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -972,8 +978,13 @@ __global__ void __launch_bounds__(K5B_THREADS, 2) gated_update32_kernel(const fl
     float n[4], mean = 0.f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      n[c] = (1.0f - zv[i][c]) * hx[i][c] + zv[i][c] * tanhf(acc[i][c]);
+      acc[i][c] = tanhf(acc[i][c]);
+      n[c] = (1.0f - zv[i][c]) * hx[i][c] + zv[i][c] * acc[i][c];
       mean += n[c];
+    }
+    if (z_out && ar0 + 4 * i < rows) {
+      reinterpret_cast<float4*>(z_out + (int64_t)(a0 + ar0 + 4 * i) * D)[cg] = make_float4(zv[i][0], zv[i][1], zv[i][2], zv[i][3]);
+      reinterpret_cast<float4*>(ht_out + (int64_t)(a0 + ar0 + 4 * i) * D)[cg] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     }
     mean = k5b_row_sum(mean) * (1.0f / D);
     float var = 0.f;
@@ -996,7 +1007,8 @@ __global__ void __launch_bounds__(K5B_THREADS, 2) gated_update32_kernel(const fl
 
 template <int D>
 static int launch_k5(const float* h, const float* agg, int n_atoms, int n_cat, const imp_gru_weights_t* wc,
-                     const imp_gru_weights_t* wa, float eps, float* out, cudaStream_t st) {
+                     const imp_gru_weights_t* wa, float eps, float* out, cudaStream_t st, float* z_out = nullptr,
+                     float* r_out = nullptr, float* ht_out = nullptr) {
   const int tiles_cat = (int)ceil_div(n_cat, K5_TILE), tiles_an = (int)ceil_div(n_atoms - n_cat, K5_TILE);
   if (D == 32) {
     IMP_CUDA(cudaFuncSetAttribute(gated_update32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K5BSmem)));
@@ -1009,7 +1021,8 @@ static int launch_k5(const float* h, const float* agg, int n_atoms, int n_cat, c
     if (tiles_cat > 0 && n_cta_cat < 1) n_cta_cat = 1;
     if (tiles_an > 0 && n_cta_cat > grid - 1) n_cta_cat = grid - 1;
     if (tiles_an == 0) n_cta_cat = grid;
-    gated_update32_kernel<<<grid, K5B_THREADS, sizeof(K5BSmem), st>>>(h, agg, n_atoms, n_cat, n_cta_cat, *wc, *wa, eps, out);
+    gated_update32_kernel<<<grid, K5B_THREADS, sizeof(K5BSmem), st>>>(h, agg, n_atoms, n_cat, n_cta_cat, *wc, *wa, eps, out, z_out,
+                                                                      r_out, ht_out);
     IMP_LAUNCH_CHECK();
     return 0;
   }
@@ -1034,6 +1047,17 @@ extern "C" int imp_gated_update(const float* d_h, const float* d_agg, int32_t n_
   int rc = IMP_ERR_DIM;
   IMP_DISPATCH_D(d, rc = launch_k5<D>(d_h, d_agg, n_atoms, n_cat_atoms, w_cat, w_an, eps, d_h_out, (cudaStream_t)stream));
   return rc;
+}
+
+extern "C" int imp_gated_update_train(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
+                                      const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_h_out,
+                                      float* d_z, float* d_r, float* d_ht, void* stream) {
+  IMP_REQUIRE(n_atoms >= 0 && n_cat_atoms >= 0 && n_cat_atoms <= n_atoms, IMP_ERR_ARG, "imp_gated_update_train: bad sizes");
+  IMP_REQUIRE(d == 32, IMP_ERR_DIM, "imp_gated_update_train: atom_dim %d not supported (32)", d);
+  if (n_atoms == 0) return 0;
+  IMP_REQUIRE(d_h && d_agg && d_h_out && d_z && d_r && d_ht && gru_ok(w_cat) && gru_ok(w_an), IMP_ERR_ARG,
+              "imp_gated_update_train: null pointer");
+  return launch_k5<32>(d_h, d_agg, n_atoms, n_cat_atoms, w_cat, w_an, eps, d_h_out, (cudaStream_t)stream, d_z, d_r, d_ht);
 }
 
 static int launch_k6(const imp_graph_t* g, const float* d_h, const float* d_pooled, int d, int fp, int mix, int fp2,

@@ -159,6 +159,8 @@ class TrainMixin:
         # ---- forward, everything kept
         h = [self._buf(f"tr_h{i}", N * d) for i in range(S + 1)]
         agg = [self._buf(f"tr_agg{i}", N * d) for i in range(S)]
+        gates = ([[self._buf(f"tr_{n}{i}", N * d) for n in ("z", "r", "ht")] for i in range(S)]
+                 if getattr(self, "store_gates", True) else None)
         _lib.call("imp_embed_atoms", self._ptr("atom_emb"), s["atom_vocab_size"], batch.dev["atom_id"].data_ptr(), N, d,
                   h[0].data_ptr(), sm)
         for i in range(S):
@@ -166,12 +168,17 @@ class TrainMixin:
                       tab.data_ptr() + 4 * per * (S + i), 0, msg.data_ptr(), cws.data_ptr(), sm)
             _lib.call("imp_segment_sum", C.byref(g), msg.data_ptr(), d, agg[i].data_ptr(), sm)
             wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
-            _lib.call("imp_gated_update", h[i].data_ptr(), agg[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc), C.byref(wa),
-                      C.c_float(self.LN_EPS), h[i + 1].data_ptr(), sm)
+            if gates is None:
+                _lib.call("imp_gated_update", h[i].data_ptr(), agg[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc), C.byref(wa),
+                          C.c_float(self.LN_EPS), h[i + 1].data_ptr(), sm)
+            else:  # the gates are kept for the backward pass (it then skips the recomputation of the three Dense layers)
+                _lib.call("imp_gated_update_train", h[i].data_ptr(), agg[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc),
+                          C.byref(wa), C.c_float(self.LN_EPS), h[i + 1].data_ptr(), gates[i][0].data_ptr(), gates[i][1].data_ptr(),
+                          gates[i][2].data_ptr(), sm)
         pooled, dpooled = self._buf("tr_pooled", 2 * P * d), self._buf("tr_dpooled", 2 * P * d)
         _lib.call("imp_global_sum_pool", batch.dev["mol_ptr"].data_ptr(), batch.dev["atom_id"].data_ptr(), 2 * P,
                   h[S].data_ptr(), d, pooled.data_ptr(), sm)
-        return dict(h=h, agg=agg, pooled=pooled, dpooled=dpooled, tab=tab, per=per, msg=msg, cws=cws, tr=tr, g=g)
+        return dict(h=h, agg=agg, gates=gates, pooled=pooled, dpooled=dpooled, tab=tab, per=per, msg=msg, cws=cws, tr=tr, g=g)
 
     def _backward_base(self, batch, kept, occurrence_norms=True, first_step=0):
         """From kept["dpooled"] back through GlobalSumPool and the message-passing steps ``first_step .. S-1`` (and the
@@ -203,9 +210,15 @@ class TrainMixin:
             wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
             gc = G[f"cat_gu_{i}.dense_z.kernel"].data_ptr()  # the layer's 8 variables are contiguous from here
             gn = G[f"an_gu_{i}.dense_z.kernel"].data_ptr()
-            _lib.call("imp_gated_update_bwd", h[i].data_ptr(), agg[i].data_ptr(), cur.data_ptr(), N, batch.n_cat_atoms, d,
-                      C.byref(wc), C.byref(wa), C.c_float(self.LN_EPS), nxt.data_ptr(), dagg.data_ptr(), gc, gn,
-                      ws_gru.data_ptr(), sm)
+            if kept.get("gates") is None:
+                _lib.call("imp_gated_update_bwd", h[i].data_ptr(), agg[i].data_ptr(), cur.data_ptr(), N, batch.n_cat_atoms, d,
+                          C.byref(wc), C.byref(wa), C.c_float(self.LN_EPS), nxt.data_ptr(), dagg.data_ptr(), gc, gn,
+                          ws_gru.data_ptr(), sm)
+            else:
+                zt, rt, tt = kept["gates"][i]
+                _lib.call("imp_gated_update_bwd_stored", h[i].data_ptr(), agg[i].data_ptr(), zt.data_ptr(), rt.data_ptr(), tt.data_ptr(),
+                          cur.data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc), C.byref(wa), C.c_float(self.LN_EPS), nxt.data_ptr(),
+                          dagg.data_ptr(), gc, gn, ws_gru.data_ptr(), sm)
             # dh += sum over the (symmetric) live entries of mult * T[b]^T dagg[src]
             _lib.call("imp_edge_messages_grouped", C.byref(g), dagg.data_ptr(), d, tab.data_ptr() + 4 * per * i,
                       tab.data_ptr() + 4 * per * (S + i), 1, msg.data_ptr(), cws.data_ptr(), sm)

@@ -152,6 +152,8 @@ SIGNATURES = {
                                          C.c_float, vp, vp, vp, vp, vp]),
     "imp_gated_update_bwd_stored": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(GruWeights),
                                               C.POINTER(GruWeights), C.c_float, vp, vp, vp, vp, vp, vp]),
+    "imp_gated_update_bwd_tc": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(GruWeights),
+                                          C.POINTER(GruWeights), C.c_float, vp, vp, vp, vp, vp, vp]),
     "imp_message_agg_bwd": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, vp, vp, vp, vp]),
     "imp_bond_transform_bwd": (C.c_int, [C.POINTER(Graph), vp, vp, vp, C.c_int32, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp,
                                          vp, vp, vp, vp, vp, vp]),

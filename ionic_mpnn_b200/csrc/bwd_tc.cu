@@ -1,0 +1,419 @@
+// GatedUpdate backward on the tensor cores (tcgen05, kind::tf32, fp32 accumulate in TMEM) for atom_dim 32.
+//
+// Replaces, for the training step (train_viscosity.py:227-230), what TensorFlow's autodiff does for GatedUpdate.call
+// (models/layers.py:142-156): given dL/dh_out it returns dL/dh, dL/dagg and the gradients of the layer's eight variables.
+// The forward kept the gates (imp_gated_update_train: z, r, tanh candidate), so nothing is recomputed; the six
+// contractions that remain run as tcgen05.mma:
+//     [dRH | dagg] = Gh . Wh^T                      (128 x 64, K = 32)        Gh = dL/d(candidate pre-activation)
+//     dh_zr        = [Gz | Gr] . [Wz_h^T ; Wr_h^T]    (128 x 32, K = 64)        Gz, Gr = dL/d(gate pre-activations)
+//     dagg        += [Gz | Gr] . [Wz_a^T ; Wr_a^T]    (128 x 32, K = 64)
+//     dW          += [h | agg | r*h | 1]^T . [Gz | Gr | Gh]   (97 x 96, K = 128 atoms; rows = dWz, dWr, dWh blocks and the biases)
+// Gradients must stay within 2e-4 of fp64 autograd (tests/test_gpu_train.py), so every operand is split into two tf32
+// terms x = hi + lo (hi = rna(x), lo = rna(x - hi)) and every product is three MMAs: hi.hi + hi.lo + lo.hi ("3xTF32":
+// ~2^-21 relative per product).
+//
+// Mapping: one persistent CTA of 128 threads per SM, thread t = atom row t of a 128-atom tile = TMEM lane t.  The row
+// operands of the first three products (Gz, Gr, Gh; hi and lo) are written to TENSOR MEMORY by their owners
+// (tcgen05.st, A operand of the "TS" MMA form); the weights are staged once per CTA as K-major hi / lo operands.  The
+// weight-gradient product needs the ATOM index along K: each thread scatters its row into K-major [feature][atom]
+// shared-memory operands (transposed staging, K-chunk stride padded by 16 bytes so that a warp's 32 stores hit 32 banks),
+// half a tile (64 atoms) at a time; its accumulator (rows = features, 96 columns) stays in TMEM for ALL tiles of the CTA
+// and is read once at the end.  The bias gradients come from a constant row of ones in that operand; dgamma / dbeta are
+// column sums taken with a 31-shuffle transpose-reduce per warp.  Every sum has a fixed order: bit-reproducible.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace imp {
+
+constexpr int BT_D = 32;
+constexpr int BT_TILE = 128;
+constexpr int BT_HALF = 64;                         // atoms staged per weight-gradient pass
+constexpr int BT_AROWS = 96;                        // feature rows written (h, agg, r*h); row 96 = ones; M = 128 reads on
+constexpr int BT_LBO = (BT_AROWS + 1) * 16;         // bytes between K chunks (4 atoms): 97 rows of 16 B
+constexpr int BT_OPBYTES = (BT_HALF / 4) * BT_LBO;  // one staged operand (hi or lo) of a half tile
+static_assert(BT_LBO % 16 == 0 && ((BT_LBO / 4) % 32) == 4, "chunk stride: 16-byte aligned, 4 banks apart: a warp's 32 stores hit 32 banks");
+
+struct BtSmem {
+  // K-major tf32 operands of the weights, hi then lo: W1 [64 x 32] = Wh; W2h [32 x 64] = [Wz_h | Wr_h]; W2a [32 x 64] = [Wz_a | Wr_a]
+  float W1[2][64 * 32];
+  float W2h[2][32 * 64];
+  float W2a[2][32 * 64];
+  unsigned char stage[4 * BT_OPBYTES + 2048];  // A_hi, A_lo, B_hi, B_lo of a half tile (+ slack: M = 128 reads past row 96)
+  float gamma[BT_D];
+  float red[4][2 * BT_D];
+  uint64_t bar[4];  // 0: B1 done, 1: B2 done, 2: weight-gradient MMAs of the staged half done
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float bt_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void bt_split(float x, float& hi, float& lo) {
+  hi = bt_rna(x);
+  lo = bt_rna(x - hi);
+}
+__device__ __forceinline__ void bt_mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, bool acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d),
+      "r"(a), "l"(b), "r"(idesc), "r"((uint32_t)acc)
+      : "memory");
+}
+// lane j of the warp receives sum over the warp's 32 lanes of v[j] (fixed order: bit-reproducible)
+__device__ __forceinline__ float bt_column_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = lane & s;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = upper ? v[i] : v[i + s];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+      v[i] = (upper ? v[i + s] : v[i]) + recv;
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
+    const float* __restrict__ h, const float* __restrict__ agg, const float* __restrict__ zs, const float* __restrict__ rs,
+    const float* __restrict__ hts, const float* __restrict__ g_out, int n_atoms, int n_cat, int n_cta_cat, imp_gru_weights_t wc,
+    imp_gru_weights_t wa, float eps, float* __restrict__ dh, float* __restrict__ dagg, float* __restrict__ partial) {
+  constexpr int D = BT_D;
+  extern __shared__ __align__(1024) unsigned char bt_raw[];
+  BtSmem& s = *reinterpret_cast<BtSmem*>(bt_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_cat = (int)blockIdx.x < n_cta_cat;
+  const imp_gru_weights_t& w = is_cat ? wc : wa;
+  const int base = is_cat ? 0 : n_cat, a_end = is_cat ? n_cat : n_atoms;
+  const int n_tiles = (a_end - base + BT_TILE - 1) / BT_TILE;
+  const int cta = is_cat ? blockIdx.x : blockIdx.x - n_cta_cat, n_cta = is_cat ? n_cta_cat : gridDim.x - n_cta_cat;
+
+  // ---- weights -> K-major tf32 hi / lo operands (element (n, k) at chunk_off(n, k / 4, R) + (k % 4) * 4)
+  for (int i = tid; i < 64 * 32; i += BT_TILE) {
+    {  // W1[n][k] = Wh[n][k]   (dX[a][n] = sum_j Gh[a][j] Wh[n][j]; Wh is [2d in][d out] row-major)
+      const int n = i / 32, k = i % 32;
+      float hi, lo;
+      bt_split(__ldg(w.Wh + n * D + k), hi, lo);
+      const int o = (tc::chunk_off(n, k / 4, 64) + (k % 4) * 4) / 4;
+      s.W1[0][o] = hi, s.W1[1][o] = lo;
+    }
+    {  // W2h[n][k] (n < 32: h input row n), W2a[n][k] (agg input row d + n); k < 32: Wz column k, else Wr column k - 32
+      const int n = i / 64, k = i % 64;
+      const float* src = k < 32 ? w.Wz : w.Wr;
+      float hi, lo;
+      const int o = (tc::chunk_off(n, k / 4, 32) + (k % 4) * 4) / 4;
+      bt_split(__ldg(src + n * D + (k & 31)), hi, lo);
+      s.W2h[0][o] = hi, s.W2h[1][o] = lo;
+      bt_split(__ldg(src + (D + n) * D + (k & 31)), hi, lo);
+      s.W2a[0][o] = hi, s.W2a[1][o] = lo;
+    }
+  }
+  if (tid < D) s.gamma[tid] = w.gamma[tid];
+  // the constant row of ones of the transposed operand (row 96; its lo term is zero) and zeros elsewhere in the slack
+  for (int i = tid; i < (int)sizeof(s.stage) / 4; i += BT_TILE) reinterpret_cast<float*>(s.stage)[i] = 0.f;
+  __syncthreads();
+  for (int k = tid; k < BT_HALF; k += BT_TILE)
+    *reinterpret_cast<float*>(s.stage + (k / 4) * BT_LBO + BT_AROWS * 16 + (k % 4) * 4) = 1.0f;
+  if (warp == 0) tc::tmem_alloc<512>(&s.tmem_base);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&s.bar[i], 1);
+    tc::mbar_fence_init();
+  }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+
+  const uint32_t tm = s.tmem_base, lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t tGhi = tm, tGlo = tm + 96, tD = tm + 192, tDW = tm + 256;  // G: [Gz | Gr | Gh]; D: [dRH -> dh_zr | dagg]
+  const uint32_t id64 = tc::make_idesc(tc::FMT_TF32, BT_TILE, 64), id32 = tc::make_idesc(tc::FMT_TF32, BT_TILE, 32);
+  const uint32_t id96 = tc::make_idesc(tc::FMT_TF32, BT_TILE, 96);
+  const uint64_t dW1[2] = {tc::make_smem_desc(tc::smem_u32(s.W1[0]), 64 * 16, 128), tc::make_smem_desc(tc::smem_u32(s.W1[1]), 64 * 16, 128)};
+  const uint64_t dW2h[2] = {tc::make_smem_desc(tc::smem_u32(s.W2h[0]), 32 * 16, 128), tc::make_smem_desc(tc::smem_u32(s.W2h[1]), 32 * 16, 128)};
+  const uint64_t dW2a[2] = {tc::make_smem_desc(tc::smem_u32(s.W2a[0]), 32 * 16, 128), tc::make_smem_desc(tc::smem_u32(s.W2a[1]), 32 * 16, 128)};
+  unsigned char* sAh = s.stage;
+  unsigned char* sAl = s.stage + BT_OPBYTES;
+  unsigned char* sBh = s.stage + 2 * BT_OPBYTES;
+  unsigned char* sBl = s.stage + 3 * BT_OPBYTES;
+  const uint64_t dA[2] = {tc::make_smem_desc(tc::smem_u32(sAh), BT_LBO, 128), tc::make_smem_desc(tc::smem_u32(sAl), BT_LBO, 128)};
+  const uint64_t dB[2] = {tc::make_smem_desc(tc::smem_u32(sBh), BT_LBO, 128), tc::make_smem_desc(tc::smem_u32(sBl), BT_LBO, 128)};
+
+  float agam = 0.f, abet = 0.f;  // lane j: column j of dgamma / dbeta over this warp's rows, all tiles
+  uint32_t ph01 = 0, ph2 = 0;    // mbarrier parities (bars 0 and 1 flip once per tile, bar 2 twice)
+  bool dw_started = false, dw_pending = false;
+
+  // row t of the half tile -> byte offset of element (feature row f, atom k = t % 64) inside a staged operand
+  const int kk = tid & (BT_HALF - 1);
+  const uint32_t st_off = (uint32_t)((kk / 4) * BT_LBO + (kk % 4) * 4);
+  auto stage_vec = [&](unsigned char* hi_base, unsigned char* lo_base, int row0, const float (&v)[32]) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      float hi, lo;
+      bt_split(v[c], hi, lo);
+      *reinterpret_cast<float*>(hi_base + st_off + (row0 + c) * 16) = hi;
+      *reinterpret_cast<float*>(lo_base + st_off + (row0 + c) * 16) = lo;
+    }
+  };
+  auto stage_raw = [&](unsigned char* dst, int row0, const float (&v)[32]) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) *reinterpret_cast<float*>(dst + st_off + (row0 + c) * 16) = v[c];
+  };
+  auto to_tmem = [&](uint32_t col, const float (&v)[32]) {  // hi / lo halves of a 32-column block of the row operand
+    uint32_t hi[32], lo[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      float a, b;
+      bt_split(v[c], a, b);
+      hi[c] = __float_as_uint(a), lo[c] = __float_as_uint(b);
+    }
+    tc::tmem_st32(tGhi + lane_off + col, hi);
+    tc::tmem_st32(tGlo + lane_off + col, lo);
+  };
+  auto load_row = [&](const float* p, int row, bool ok, float (&v)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 x = ok ? __ldg(reinterpret_cast<const float4*>(p + (int64_t)row * D) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[4 * c] = x.x, v[4 * c + 1] = x.y, v[4 * c + 2] = x.z, v[4 * c + 3] = x.w;
+    }
+  };
+
+  for (int tile = cta; tile < n_tiles; tile += n_cta) {
+    const int a0 = base + tile * BT_TILE;
+    const int row = a0 + tid;
+    const bool ok = tid < min(BT_TILE, a_end - a0);
+    float hv[32], go[32];
+    load_row(h, row, ok, hv), load_row(g_out, row, ok, go);
+    {  // LayerNorm forward statistics and backward, gate gradients (models/layers.py:151-156 under autodiff)
+      float zv[32], tv[32], gz[32], gh[32], gx[32];
+      load_row(zs, row, ok, zv), load_row(hts, row, ok, tv);
+      float nrm[32], mean = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        nrm[c] = fmaf(zv[c], tv[c] - hv[c], hv[c]);
+        mean += nrm[c];
+      }
+      mean *= (1.0f / D);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        nrm[c] -= mean;
+        var = fmaf(nrm[c], nrm[c], var);
+      }
+      const float inv = 1.0f / sqrtf(var * (1.0f / D) + eps);
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        nrm[c] *= inv;  // xhat
+        gx[c] = go[c] * nrm[c];
+        const float dx = go[c] * s.gamma[c];
+        m1 += dx;
+        m2 = fmaf(dx, nrm[c], m2);
+      }
+      m1 *= (1.0f / D), m2 *= (1.0f / D);
+      float gbeta[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        gbeta[c] = go[c];
+        const float dn = inv * (go[c] * s.gamma[c] - m1 - nrm[c] * m2);
+        const float z = zv[c], ht = tv[c], hj = hv[c];
+        go[c] = fmaf(dn, 1.0f - z, go[c]);        // dh: residual path + the (1 - z) path
+        gz[c] = dn * (ht - hj) * z * (1.0f - z);  // dL/dzpre
+        gh[c] = dn * z * (1.0f - ht * ht);        // dL/dhpre
+      }
+      agam += bt_column_sum(gx, lane);
+      abet += bt_column_sum(gbeta, lane);
+      to_tmem(0, gz), to_tmem(64, gh);
+    }
+    tc::tmem_wait_st();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) {  // B1: [dRH | dagg] = Gh . Wh^T, K = 32
+      tc::fence_after_thread_sync();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ko = (uint64_t)(ks * 2 * 64 * 16 / 16);
+          bt_mma_ts(tD, tGhi + 64 + 8 * ks, dW1[0] + ko, id64, ks > 0);
+          bt_mma_ts(tD, tGhi + 64 + 8 * ks, dW1[1] + ko, id64, true);
+          bt_mma_ts(tD, tGlo + 64 + 8 * ks, dW1[0] + ko, id64, true);
+        }
+        tc::mma_commit(&s.bar[0]);
+      }
+      __syncwarp();
+    }
+    float rv[32];
+    load_row(rs, row, ok, rv);
+    tc::mbar_wait(&s.bar[0], ph01);
+    tc::fence_after_thread_sync();
+    float rh[32];
+    {
+      float drh[32], gr[32];
+      tc::tmem_ld32(tD + lane_off, drh);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        go[c] = fmaf(drh[c], rv[c], go[c]);
+        gr[c] = drh[c] * hv[c] * rv[c] * (1.0f - rv[c]);  // dL/drpre
+        rh[c] = rv[c] * hv[c];
+      }
+      to_tmem(32, gr);
+    }
+    tc::tmem_wait_st();
+    tc::fence_before_thread_sync();
+    // the staging buffers are free once the previous tile's second weight-gradient pass has been consumed
+    if (dw_pending) {
+      tc::mbar_wait(&s.bar[2], ph2);
+      ph2 ^= 1;
+      dw_pending = false;
+    }
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      if ((tid >> 6) == half) {  // the two warps that own these 64 atoms scatter their rows: [feature][atom], hi and lo
+        float v[32];
+        stage_vec(sAh, sAl, 0, hv);
+        load_row(agg, row, ok, v);
+        stage_vec(sAh, sAl, 32, v);
+        stage_vec(sAh, sAl, 64, rh);
+#pragma unroll
+        for (int blk = 0; blk < 3; ++blk) {  // Gz, Gr, Gh: their hi / lo terms are in tensor memory already
+          tc::tmem_ld32(tGhi + lane_off + 32 * blk, v);
+          stage_raw(sBh, 32 * blk, v);
+          tc::tmem_ld32(tGlo + lane_off + 32 * blk, v);
+          stage_raw(sBl, 32 * blk, v);
+        }
+      }
+      tc::fence_proxy_async_smem();
+      __syncthreads();
+      if (warp == 0) {
+        tc::fence_after_thread_sync();
+        if (tc::elect_one()) {
+          if (half == 0) {  // B2: dh_zr = [Gz | Gr] . W2h (over dRH, already read), dagg += [Gz | Gr] . W2a; K = 64
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t ko = (uint64_t)(ks * 2 * 32 * 16 / 16);
+              bt_mma_ts(tD, tGhi + 8 * ks, dW2h[0] + ko, id32, ks > 0);
+              bt_mma_ts(tD, tGhi + 8 * ks, dW2h[1] + ko, id32, true);
+              bt_mma_ts(tD, tGlo + 8 * ks, dW2h[0] + ko, id32, true);
+              bt_mma_ts(tD + 32, tGhi + 8 * ks, dW2a[0] + ko, id32, true);
+              bt_mma_ts(tD + 32, tGhi + 8 * ks, dW2a[1] + ko, id32, true);
+              bt_mma_ts(tD + 32, tGlo + 8 * ks, dW2a[0] + ko, id32, true);
+            }
+            tc::mma_commit(&s.bar[1]);
+          }
+#pragma unroll
+          for (int ks = 0; ks < BT_HALF / 8; ++ks) {  // dW += A^T-operand . B^T-operand over these 64 atoms
+            const uint64_t ko = (uint64_t)(ks * 2 * BT_LBO / 16);
+            tc::mma_tf32(tDW, dA[0] + ko, dB[0] + ko, id96, dw_started || ks > 0);
+            tc::mma_tf32(tDW, dA[0] + ko, dB[1] + ko, id96, true);
+            tc::mma_tf32(tDW, dA[1] + ko, dB[0] + ko, id96, true);
+          }
+          tc::mma_commit(&s.bar[2]);
+        }
+        __syncwarp();
+      }
+      dw_started = true;
+      if (half == 0) {
+        tc::mbar_wait(&s.bar[1], ph01);
+        tc::fence_after_thread_sync();
+        float v[32];
+        tc::tmem_ld32(tD + lane_off, v);  // dh_zr
+        if (ok) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            reinterpret_cast<float4*>(dh + (int64_t)row * D)[c] =
+                make_float4(go[4 * c] + v[4 * c], go[4 * c + 1] + v[4 * c + 1], go[4 * c + 2] + v[4 * c + 2], go[4 * c + 3] + v[4 * c + 3]);
+        }
+        tc::tmem_ld32(tD + 32 + lane_off, v);  // dagg
+        if (ok) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            reinterpret_cast<float4*>(dagg + (int64_t)row * D)[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+        tc::mbar_wait(&s.bar[2], ph2);  // the first half has been consumed: the other two warps may overwrite the buffers
+        ph2 ^= 1;
+      } else {
+        dw_pending = true;
+      }
+    }
+    ph01 ^= 1;
+    tc::fence_before_thread_sync();
+  }
+  if (dw_pending) tc::mbar_wait(&s.bar[2], ph2);
+  tc::fence_after_thread_sync();
+
+  // ---- per-CTA partial gradients, layout [dWz (2d, d) | dbz | dWr | dbr | dWh | dbh | dgamma | dbeta]
+  float* o = partial + (int64_t)blockIdx.x * (3 * 2 * D * D + 5 * D);
+  constexpr int BLK = 2 * D * D + D;
+  if (dw_started) {
+    float v[32];
+#pragma unroll
+    for (int blk = 0; blk < 3; ++blk) {  // columns [32 blk, 32 blk + 32): x^T Gz, x^T Gr, x^T Gh  (all lanes load: .sync.aligned)
+      tc::tmem_ld32(tDW + lane_off + 32 * blk, v);
+      if (tid == BT_AROWS) {  // the ones row: bias gradients
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[blk * BLK + 2 * D * D + j] = v[j];
+      } else if (blk < 2) {
+        if (tid < 2 * D) {  // rows h (0..31) and agg (32..63): dWz / dWr rows k = tid
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[blk * BLK + tid * D + j] = v[j];
+        }
+      } else if (tid >= D && tid < BT_AROWS) {  // dWh: rows k < d multiply r*h (feature rows 64..95), rows d + k multiply agg (32..63)
+        const int k = tid >= 2 * D ? tid - 2 * D : tid;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[2 * BLK + k * D + j] = v[j];
+      }
+    }
+  } else {
+    for (int i = tid; i < 3 * BLK; i += BT_TILE) o[i] = 0.f;
+  }
+  s.red[warp][lane] = agam, s.red[warp][D + lane] = abet;
+  __syncthreads();
+  if (tid < 2 * D) o[3 * BLK + tid] = (s.red[0][tid] + s.red[1][tid]) + (s.red[2][tid] + s.red[3][tid]);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tm);
+}
+
+__global__ void bt_reduce_partials_kernel(const float* __restrict__ partial, int n_parts, int64_t stride, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int p = 0; p < n_parts; ++p) acc += partial[(int64_t)p * stride + i];
+  out[i] = acc;
+}
+
+}  // namespace imp
+
+using namespace imp;
+
+extern "C" int imp_gated_update_bwd_tc(const float* d_h, const float* d_agg, const float* d_z, const float* d_r, const float* d_ht,
+                                       const float* d_gout, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
+                                       const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_dh,
+                                       float* d_dagg, float* d_grads_cat, float* d_grads_an, float* d_workspace, void* stream) {
+  IMP_REQUIRE(n_atoms >= 0 && n_cat_atoms >= 0 && n_cat_atoms <= n_atoms, IMP_ERR_ARG, "imp_gated_update_bwd_tc: bad sizes");
+  IMP_REQUIRE(d == BT_D, IMP_ERR_DIM, "imp_gated_update_bwd_tc: atom_dim %d not supported (32)", d);
+  IMP_REQUIRE(d_h && d_agg && d_z && d_r && d_ht && d_gout && d_dh && d_dagg && d_grads_cat && d_grads_an && d_workspace && w_cat && w_an,
+              IMP_ERR_ARG, "imp_gated_update_bwd_tc: null pointer");
+  IMP_REQUIRE(imp_device_is_sm100(), IMP_ERR_UNSUPPORTED, "imp_gated_update_bwd_tc: tcgen05 needs an sm_100 device");
+  int dev = 0, sms = 148;
+  IMP_CUDA(cudaGetDevice(&dev));
+  IMP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int tiles_cat = (int)ceil_div(n_cat_atoms, BT_TILE), tiles_an = (int)ceil_div(n_atoms - n_cat_atoms, BT_TILE);
+  int n_cat = tiles_cat + tiles_an > 0 ? (int)((int64_t)sms * tiles_cat / (tiles_cat + tiles_an)) : 1;
+  n_cat = n_cat < 1 ? 1 : (n_cat > sms - 1 ? sms - 1 : n_cat);
+  const int grid = sms;
+  const size_t smem = sizeof(BtSmem) + 1024;
+  IMP_CUDA(cudaFuncSetAttribute(gated_update_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaStream_t st = (cudaStream_t)stream;
+  gated_update_bwd_tc_kernel<<<grid, BT_TILE, smem, st>>>(d_h, d_agg, d_z, d_r, d_ht, d_gout, n_atoms, n_cat_atoms, n_cat, *w_cat, *w_an,
+                                                         eps, d_dh, d_dagg, d_workspace);
+  IMP_LAUNCH_CHECK();
+  const int n = 3 * 2 * BT_D * BT_D + 5 * BT_D;
+  bt_reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_workspace, n_cat, n, n, d_grads_cat);
+  IMP_LAUNCH_CHECK();
+  bt_reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_workspace + (int64_t)n_cat * n, grid - n_cat, n, n, d_grads_an);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}

@@ -216,7 +216,7 @@ class TrainMixin:
                           ws_gru.data_ptr(), sm)
             else:
                 zt, rt, tt = kept["gates"][i]
-                _lib.call("imp_gated_update_bwd_stored", h[i].data_ptr(), agg[i].data_ptr(), zt.data_ptr(), rt.data_ptr(), tt.data_ptr(),
+                _lib.call("imp_gated_update_bwd_tc" if getattr(self, "tc_backward", True) else "imp_gated_update_bwd_stored", h[i].data_ptr(), agg[i].data_ptr(), zt.data_ptr(), rt.data_ptr(), tt.data_ptr(),
                           cur.data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc), C.byref(wa), C.c_float(self.LN_EPS), nxt.data_ptr(),
                           dagg.data_ptr(), gc, gn, ws_gru.data_ptr(), sm)
             # dh += sum over the (symmetric) live entries of mult * T[b]^T dagg[src]

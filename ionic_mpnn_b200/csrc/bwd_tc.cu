@@ -5,8 +5,7 @@
 // The forward kept the gates (imp_gated_update_train: z, r, tanh candidate), so nothing is recomputed; the six
 // contractions that remain run as tcgen05.mma:
 //     [dRH | dagg] = Gh . Wh^T                      (128 x 64, K = 32)        Gh = dL/d(candidate pre-activation)
-//     dh_zr        = [Gz | Gr] . [Wz_h^T ; Wr_h^T]    (128 x 32, K = 64)        Gz, Gr = dL/d(gate pre-activations)
-//     dagg        += [Gz | Gr] . [Wz_a^T ; Wr_a^T]    (128 x 32, K = 64)
+//     [dh_zr | dagg_zr] = [Gz | Gr] . [Wz^T ; Wr^T]   (128 x 64, K = 64)        Gz, Gr = dL/d(gate pre-activations)
 //     dW          += [h | agg | r*h | 1]^T . [Gz | Gr | Gh]   (97 x 96, K = 128 atoms; rows = dWz, dWr, dWh blocks and the biases)
 // Gradients must stay within 2e-4 of fp64 autograd (tests/test_gpu_train.py), so every operand is split into two tf32
 // terms x = hi + lo (hi = rna(x), lo = rna(x - hi)) and every product is three MMAs: hi.hi + hi.lo + lo.hi ("3xTF32":
@@ -34,10 +33,9 @@ constexpr int BT_OPBYTES = (BT_HALF / 4) * BT_LBO;  // one staged operand (hi or
 static_assert(BT_LBO % 16 == 0 && ((BT_LBO / 4) % 32) == 4, "chunk stride: 16-byte aligned, 4 banks apart: a warp's 32 stores hit 32 banks");
 
 struct BtSmem {
-  // K-major tf32 operands of the weights, hi then lo: W1 [64 x 32] = Wh; W2h [32 x 64] = [Wz_h | Wr_h]; W2a [32 x 64] = [Wz_a | Wr_a]
+  // K-major tf32 operands of the weights, hi then lo: W1 [64 x 32] = Wh; W2 [64 x 64]: row n = input n of [h | agg], k < 32: Wz, else Wr
   float W1[2][64 * 32];
-  float W2h[2][32 * 64];
-  float W2a[2][32 * 64];
+  float W2[2][64 * 64];
   unsigned char stage[4 * BT_OPBYTES + 2048];  // A_hi, A_lo, B_hi, B_lo of a half tile (+ slack: M = 128 reads past row 96)
   float gamma[BT_D];
   float red[4][2 * BT_D];
@@ -50,9 +48,12 @@ __device__ __forceinline__ float bt_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// x = hi + lo with hi a tf32 number: hi = x with its 13 low significand bits cleared (one LOP3), lo = x - hi (exact in fp32).
+// The MMA ignores the 13 low bits of lo, i.e. lo is truncated to tf32 by the hardware: |x - hi - lo_tf32| <= 2^-21 |x|.
+// (cvt.rna on both terms gave the same accuracy at three instructions per value, two of them conversions.)
 __device__ __forceinline__ void bt_split(float x, float& hi, float& lo) {
-  hi = bt_rna(x);
-  lo = bt_rna(x - hi);
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = x - hi;
 }
 __device__ __forceinline__ void bt_mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, bool acc) {
   asm volatile(
@@ -99,15 +100,14 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
       const int o = (tc::chunk_off(n, k / 4, 64) + (k % 4) * 4) / 4;
       s.W1[0][o] = hi, s.W1[1][o] = lo;
     }
-    {  // W2h[n][k] (n < 32: h input row n), W2a[n][k] (agg input row d + n); k < 32: Wz column k, else Wr column k - 32
-      const int n = i / 64, k = i % 64;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {  // W2[n][k] = (k < 32 ? Wz : Wr)[n][k & 31], n = input index of [h | agg]
+      const int n = i / 64 + 32 * half, k = i % 64;
       const float* src = k < 32 ? w.Wz : w.Wr;
       float hi, lo;
-      const int o = (tc::chunk_off(n, k / 4, 32) + (k % 4) * 4) / 4;
       bt_split(__ldg(src + n * D + (k & 31)), hi, lo);
-      s.W2h[0][o] = hi, s.W2h[1][o] = lo;
-      bt_split(__ldg(src + (D + n) * D + (k & 31)), hi, lo);
-      s.W2a[0][o] = hi, s.W2a[1][o] = lo;
+      const int o = (tc::chunk_off(n, k / 4, 64) + (k % 4) * 4) / 4;
+      s.W2[0][o] = hi, s.W2[1][o] = lo;
     }
   }
   if (tid < D) s.gamma[tid] = w.gamma[tid];
@@ -128,12 +128,12 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
   tc::fence_after_thread_sync();
 
   const uint32_t tm = s.tmem_base, lane_off = (uint32_t)(warp * 32) << 16;
-  const uint32_t tGhi = tm, tGlo = tm + 96, tD = tm + 192, tDW = tm + 256;  // G: [Gz | Gr | Gh]; D: [dRH -> dh_zr | dagg]
-  const uint32_t id64 = tc::make_idesc(tc::FMT_TF32, BT_TILE, 64), id32 = tc::make_idesc(tc::FMT_TF32, BT_TILE, 32);
+  // G: [Gz | Gr | Gh] hi, lo; D: [dRH | dagg_h] of B1; D2: [dh_zr | dagg_zr] of B2; DW: the weight-gradient accumulator
+  const uint32_t tGhi = tm, tGlo = tm + 96, tD = tm + 192, tD2 = tm + 256, tDW = tm + 320;
+  const uint32_t id64 = tc::make_idesc(tc::FMT_TF32, BT_TILE, 64);
   const uint32_t id96 = tc::make_idesc(tc::FMT_TF32, BT_TILE, 96);
   const uint64_t dW1[2] = {tc::make_smem_desc(tc::smem_u32(s.W1[0]), 64 * 16, 128), tc::make_smem_desc(tc::smem_u32(s.W1[1]), 64 * 16, 128)};
-  const uint64_t dW2h[2] = {tc::make_smem_desc(tc::smem_u32(s.W2h[0]), 32 * 16, 128), tc::make_smem_desc(tc::smem_u32(s.W2h[1]), 32 * 16, 128)};
-  const uint64_t dW2a[2] = {tc::make_smem_desc(tc::smem_u32(s.W2a[0]), 32 * 16, 128), tc::make_smem_desc(tc::smem_u32(s.W2a[1]), 32 * 16, 128)};
+  const uint64_t dW2[2] = {tc::make_smem_desc(tc::smem_u32(s.W2[0]), 64 * 16, 128), tc::make_smem_desc(tc::smem_u32(s.W2[1]), 64 * 16, 128)};
   unsigned char* sAh = s.stage;
   unsigned char* sAl = s.stage + BT_OPBYTES;
   unsigned char* sBh = s.stage + 2 * BT_OPBYTES;
@@ -184,6 +184,14 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
     const int a0 = base + tile * BT_TILE;
     const int row = a0 + tid;
     const bool ok = tid < min(BT_TILE, a_end - a0);
+    {  // the next tile's six rows of this thread -> L2 (one CTA of four warps per SM cannot hide an HBM round trip otherwise)
+      const int nrow = row + n_cta * BT_TILE;
+      if (nrow < a_end) {
+        const float* ps[6] = {h, zs, hts, g_out, rs, agg};
+#pragma unroll
+        for (int q = 0; q < 6; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps[q] + (int64_t)nrow * D));
+      }
+    }
     float hv[32], go[32];
     load_row(h, row, ok, hv), load_row(g_out, row, ok, go);
     {  // LayerNorm forward statistics and backward, gate gradients (models/layers.py:151-156 under autodiff)
@@ -246,6 +254,19 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
     }
     float rv[32];
     load_row(rs, row, ok, rv);
+    // while B1 runs: the staging buffers are free once the previous tile's second weight-gradient pass has been consumed;
+    // the first two warps scatter the operand rows that do not depend on B1 (h, agg)
+    if (dw_pending) {
+      tc::mbar_wait(&s.bar[2], ph2);
+      ph2 ^= 1;
+      dw_pending = false;
+    }
+    if ((tid >> 6) == 0) {
+      float v[32];
+      stage_vec(sAh, sAl, 0, hv);
+      load_row(agg, row, ok, v);
+      stage_vec(sAh, sAl, 32, v);
+    }
     tc::mbar_wait(&s.bar[0], ph01);
     tc::fence_after_thread_sync();
     float rh[32];
@@ -262,19 +283,15 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
     }
     tc::tmem_wait_st();
     tc::fence_before_thread_sync();
-    // the staging buffers are free once the previous tile's second weight-gradient pass has been consumed
-    if (dw_pending) {
-      tc::mbar_wait(&s.bar[2], ph2);
-      ph2 ^= 1;
-      dw_pending = false;
-    }
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
       if ((tid >> 6) == half) {  // the two warps that own these 64 atoms scatter their rows: [feature][atom], hi and lo
         float v[32];
-        stage_vec(sAh, sAl, 0, hv);
-        load_row(agg, row, ok, v);
-        stage_vec(sAh, sAl, 32, v);
+        if (half == 1) {  // (the first half's h and agg rows were staged while B1 ran)
+          stage_vec(sAh, sAl, 0, hv);
+          load_row(agg, row, ok, v);
+          stage_vec(sAh, sAl, 32, v);
+        }
         stage_vec(sAh, sAl, 64, rh);
 #pragma unroll
         for (int blk = 0; blk < 3; ++blk) {  // Gz, Gr, Gh: their hi / lo terms are in tensor memory already
@@ -289,16 +306,13 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
       if (warp == 0) {
         tc::fence_after_thread_sync();
         if (tc::elect_one()) {
-          if (half == 0) {  // B2: dh_zr = [Gz | Gr] . W2h (over dRH, already read), dagg += [Gz | Gr] . W2a; K = 64
+          if (half == 0) {  // B2: [dh_zr | dagg_zr] = [Gz | Gr] . W2^T, K = 64 (its own columns: dagg_h of B1 is added in registers)
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t ko = (uint64_t)(ks * 2 * 32 * 16 / 16);
-              bt_mma_ts(tD, tGhi + 8 * ks, dW2h[0] + ko, id32, ks > 0);
-              bt_mma_ts(tD, tGhi + 8 * ks, dW2h[1] + ko, id32, true);
-              bt_mma_ts(tD, tGlo + 8 * ks, dW2h[0] + ko, id32, true);
-              bt_mma_ts(tD + 32, tGhi + 8 * ks, dW2a[0] + ko, id32, true);
-              bt_mma_ts(tD + 32, tGhi + 8 * ks, dW2a[1] + ko, id32, true);
-              bt_mma_ts(tD + 32, tGlo + 8 * ks, dW2a[0] + ko, id32, true);
+              const uint64_t ko = (uint64_t)(ks * 2 * 64 * 16 / 16);
+              bt_mma_ts(tD2, tGhi + 8 * ks, dW2[0] + ko, id64, ks > 0);
+              bt_mma_ts(tD2, tGhi + 8 * ks, dW2[1] + ko, id64, true);
+              bt_mma_ts(tD2, tGlo + 8 * ks, dW2[0] + ko, id64, true);
             }
             tc::mma_commit(&s.bar[1]);
           }
@@ -317,19 +331,21 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
       if (half == 0) {
         tc::mbar_wait(&s.bar[1], ph01);
         tc::fence_after_thread_sync();
-        float v[32];
-        tc::tmem_ld32(tD + lane_off, v);  // dh_zr
+        float v[32], u[32];
+        tc::tmem_ld32(tD2 + lane_off, v);  // dh_zr
         if (ok) {
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             reinterpret_cast<float4*>(dh + (int64_t)row * D)[c] =
                 make_float4(go[4 * c] + v[4 * c], go[4 * c + 1] + v[4 * c + 1], go[4 * c + 2] + v[4 * c + 2], go[4 * c + 3] + v[4 * c + 3]);
         }
-        tc::tmem_ld32(tD + 32 + lane_off, v);  // dagg
+        tc::tmem_ld32(tD + 32 + lane_off, u);   // dagg through Wh
+        tc::tmem_ld32(tD2 + 32 + lane_off, v);  // dagg through Wz, Wr
         if (ok) {
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            reinterpret_cast<float4*>(dagg + (int64_t)row * D)[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            reinterpret_cast<float4*>(dagg + (int64_t)row * D)[c] =
+                make_float4(u[4 * c] + v[4 * c], u[4 * c + 1] + v[4 * c + 1], u[4 * c + 2] + v[4 * c + 2], u[4 * c + 3] + v[4 * c + 3]);
         }
         tc::mbar_wait(&s.bar[2], ph2);  // the first half has been consumed: the other two warps may overwrite the buffers
         ph2 ^= 1;

@@ -560,7 +560,8 @@ def run_b200(args):
             dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
         e2e = {"value": P * world * args.steps / (float(ms2.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": P * 4, "ms_per_step": float(ms2.item()) / args.steps, "chunks_per_step": n_chunks,
-               "input_feed": "compact (16-bit atom words, 32-bit entry words)" if model._stream_state["fields"][1] == "mol_eptr"
+               "input_feed": ("compact (16-bit atom words, 16-bit entry words)" if model._stream_state["fields"][3] == "edge_h"
+                              else "compact (16-bit atom words, 32-bit entry words)") if model._stream_state["fields"][1] == "mol_eptr"
                else "int32 CSR arrays",
                "finite": bool(torch.isfinite(out_host).all()),
                "note": "MPNNModel.predict_stream: pinned host packed chunks -> H2D on a copy stream (2 staging slots) "

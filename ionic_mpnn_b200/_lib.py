@@ -122,6 +122,7 @@ SIGNATURES = {
     "imp_fused_pack_planned": (C.c_int, [vp, C.POINTER(GruWeights), C.c_int32, C.c_int32, vp, vp]),
     "imp_fused_plan_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "imp_fused_plan": (C.c_int, [C.POINTER(Graph), C.POINTER(CompactGraph), C.c_int32, C.c_int32, vp, C.c_int64, vp]),
+    "imp_fused_plan_compact16": (C.c_int, [C.POINTER(CompactGraph), C.c_int32, C.c_int32, vp, C.c_int64, vp]),
     "imp_mpnn_forward_fused_planned": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp, C.c_int32,
                                                  C.c_int32, C.c_int32, vp, C.c_float, C.c_int32, vp, vp]),
     "imp_wide_pack_bytes": (C.c_int64, [C.c_int32, C.c_int32]),

@@ -28,6 +28,7 @@ struct PlanArgs {
   const int* mol_eptr;
   const unsigned short* atom_w;
   const unsigned int* edge_w;
+  const unsigned short* edge_h;  // 16-bit entry words (imp_fused_plan_compact16): src | bond << 7 | (multiplicity - 1) << 15
   unsigned char* plan;
   int n_pairs, atom_vocab, bond_vocab;
 };
@@ -49,8 +50,9 @@ constexpr unsigned short PL_NIL = 0xffff;
 __device__ __forceinline__ unsigned int half_bits_of_int(int v) { return (unsigned int)__half_as_ushort(__float2half_rn((float)v)); }
 __device__ __forceinline__ int field8(unsigned long long v, int k) { return (int)((v >> (8 * k)) & 0xffull); }
 
-template <bool COMPACT>
+template <int FEED>  // 0: int32 CSR arrays, 1: compact feed (32-bit entry words), 2: compact feed with 16-bit entry words
 __global__ void __launch_bounds__(PL_WARPS * 32) fused_plan_kernel(const PlanArgs a) {
+  constexpr bool COMPACT = FEED != 0;
   __shared__ PlanWarpSmem sm[PL_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   PlanWarpSmem& ws = sm[warp];
@@ -240,7 +242,8 @@ __global__ void __launch_bounds__(PL_WARPS * 32) fused_plan_kernel(const PlanArg
       }
       auto put = [&](int p, int i, int csrc, int cbm, unsigned int cw) {
         int src, bond, mult;
-        if (COMPACT) src = (int)(cw & 0xffu), bond = (int)((cw >> 8) & 0xffu), mult = (int)((cw >> 16) & 0xffu);
+        if (FEED == 2) src = (int)(cw & 0x7fu), bond = (int)((cw >> 7) & 0xffu), mult = (int)(cw >> 15) + 1;
+        else if (COMPACT) src = (int)(cw & 0xffu), bond = (int)((cw >> 8) & 0xffu), mult = (int)((cw >> 16) & 0xffu);
         else src = csrc - (at[p] - (32 * p + lane - rowbase[p])), bond = cbm & 0xffff, mult = cbm >> 16;
         if (src < 0 || src >= msz[p]) bad = 1, src = min(max(src, 0), max(msz[p] - 1, 0));
         bond = min(bond, min(a.bond_vocab - 1, 255));
@@ -254,7 +257,8 @@ __global__ void __launch_bounds__(PL_WARPS * 32) fused_plan_kernel(const PlanArg
         for (int i = 0; i < 4; ++i) {
           csrc[p][i] = 0, cbm[p][i] = 0, cw[p][i] = 0u;
           if (i < degv[p]) {
-            if (COMPACT) cw[p][i] = __ldg(a.edge_w + g0[p] + i);
+            if (FEED == 2) cw[p][i] = (unsigned int)__ldg(a.edge_h + g0[p] + i);
+            else if (COMPACT) cw[p][i] = __ldg(a.edge_w + g0[p] + i);
             else csrc[p][i] = __ldg(a.col_src + g0[p] + i), cbm[p][i] = __ldg(a.edge_bm + g0[p] + i);
           }
         }
@@ -264,7 +268,8 @@ __global__ void __launch_bounds__(PL_WARPS * 32) fused_plan_kernel(const PlanArg
         for (int i = 0; i < 4; ++i)
           if (i < degv[p]) put(p, i, csrc[p][i], cbm[p][i], cw[p][i]);
         for (int i = 4; i < degv[p]; ++i) {  // rows with more than four entries
-          if (COMPACT) put(p, i, 0, 0, __ldg(a.edge_w + g0[p] + i));
+          if (FEED == 2) put(p, i, 0, 0, (unsigned int)__ldg(a.edge_h + g0[p] + i));
+          else if (COMPACT) put(p, i, 0, 0, __ldg(a.edge_w + g0[p] + i));
           else put(p, i, __ldg(a.col_src + g0[p] + i), __ldg(a.edge_bm + g0[p] + i), 0u);
         }
       }
@@ -309,8 +314,8 @@ extern "C" int64_t imp_fused_plan_bytes(int32_t n_pairs, int32_t n_atoms, int32_
   return FP_HEADER_BYTES + 2 * cap * (int64_t)sizeof(FusedTile);
 }
 
-extern "C" int imp_fused_plan(const imp_graph_t* g, const imp_compact_graph_t* cg, int32_t atom_vocab, int32_t max_mol_atoms,
-                              void* d_plan, int64_t plan_bytes, void* stream) {
+static int fused_plan_impl(const imp_graph_t* g, const imp_compact_graph_t* cg, bool narrow, int32_t atom_vocab, int32_t max_mol_atoms,
+                           void* d_plan, int64_t plan_bytes, void* stream) {
   IMP_REQUIRE((g != nullptr) != (cg != nullptr), IMP_ERR_ARG, "imp_fused_plan: pass exactly one of the two graph forms");
   PlanArgs a{};
   int n_atoms, n_unique;
@@ -318,6 +323,7 @@ extern "C" int imp_fused_plan(const imp_graph_t* g, const imp_compact_graph_t* c
     IMP_REQUIRE(cg->mol_ptr && cg->mol_eptr && (cg->n_atoms == 0 || cg->atom_w) && (cg->n_unique == 0 || cg->edge_w), IMP_ERR_ARG,
                 "imp_fused_plan: null index arrays");
     a.mol_ptr = cg->mol_ptr, a.mol_eptr = cg->mol_eptr, a.atom_w = cg->atom_w, a.edge_w = cg->edge_w;
+    a.edge_h = reinterpret_cast<const unsigned short*>(cg->edge_w);
     a.n_pairs = cg->n_pairs, a.bond_vocab = cg->bond_vocab, n_atoms = cg->n_atoms, n_unique = cg->n_unique;
   } else {
     IMP_REQUIRE(g->mol_ptr && g->row_ptr && (g->n_atoms == 0 || g->atom_id) && (g->n_unique == 0 || (g->col_src && g->edge_bm)),
@@ -338,8 +344,20 @@ extern "C" int imp_fused_plan(const imp_graph_t* g, const imp_compact_graph_t* c
   if (a.n_pairs == 0) return 0;
   const int nwin = (a.n_pairs + FP_WIN - 1) / FP_WIN;
   const int grid = (2 * nwin + PL_WARPS - 1) / PL_WARPS;
-  if (cg) fused_plan_kernel<true><<<grid, PL_WARPS * 32, 0, st>>>(a);
-  else fused_plan_kernel<false><<<grid, PL_WARPS * 32, 0, st>>>(a);
+  if (cg && narrow) fused_plan_kernel<2><<<grid, PL_WARPS * 32, 0, st>>>(a);
+  else if (cg) fused_plan_kernel<1><<<grid, PL_WARPS * 32, 0, st>>>(a);
+  else fused_plan_kernel<0><<<grid, PL_WARPS * 32, 0, st>>>(a);
   IMP_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int imp_fused_plan(const imp_graph_t* g, const imp_compact_graph_t* cg, int32_t atom_vocab, int32_t max_mol_atoms,
+                              void* d_plan, int64_t plan_bytes, void* stream) {
+  return fused_plan_impl(g, cg, false, atom_vocab, max_mol_atoms, d_plan, plan_bytes, stream);
+}
+
+extern "C" int imp_fused_plan_compact16(const imp_compact_graph_t* cg, int32_t atom_vocab, int32_t max_mol_atoms, void* d_plan,
+                                        int64_t plan_bytes, void* stream) {
+  IMP_REQUIRE(cg, IMP_ERR_ARG, "imp_fused_plan_compact16: graph is null");
+  return fused_plan_impl(nullptr, cg, true, atom_vocab, max_mol_atoms, d_plan, plan_bytes, stream);
 }

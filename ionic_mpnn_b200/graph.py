@@ -171,6 +171,10 @@ class PackedGraphBatch:
             "atom_w": np.ascontiguousarray((h["atom_id"].astype(np.int64) | (deg << 8)).astype(np.uint16)),
             "edge_w": np.ascontiguousarray((src_local | (bond << 8) | (mult << 16)).astype(np.uint32)),
         }
+        # narrow form (imp_fused_plan_compact16): 16-bit entry words when sources fit 7 bits and multiplicities are 1 or 2
+        self.narrow_ok = bool(self.n_unique == 0 or (src_local.max() < 128 and mult.min() >= 1 and mult.max() <= 2))
+        if self.narrow_ok:
+            self.chost["edge_h"] = np.ascontiguousarray((src_local | (bond << 7) | ((mult - 1) << 15)).astype(np.uint16))
         return self
 
     def nbytes_compact(self):
@@ -184,16 +188,21 @@ class PackedGraphBatch:
         if getattr(self, "cpinned", None) is None:
             views = {"mol_ptr": self.chost["mol_ptr"], "mol_eptr": self.chost["mol_eptr"],
                      "atom_w": self.chost["atom_w"].view(np.int16), "edge_w": self.chost["edge_w"].view(np.int32)}
+            if self.narrow_ok:
+                views["edge_h"] = self.chost["edge_h"].view(np.int16)
             self.cpinned = {k: torch.from_numpy(v).pin_memory() for k, v in views.items()}
             self.pinned_T = None if self.temperature is None else torch.from_numpy(self.temperature).pin_memory()
         return self
 
-    def to_compact(self, device):
-        """Device copy of the compact feed only (what imp_mpnn_forward_fused_compact reads)."""
+    def to_compact(self, device, narrow=False):
+        """Device copy of the compact feed only (what imp_mpnn_forward_fused_compact / imp_fused_plan read); ``narrow``: the
+        16-bit entry words of imp_fused_plan_compact16 (the planned forward only)."""
         import torch
 
         self.pin_compact()
-        slot = DeviceSlot(torch.device(device), COMPACT_FIELDS)
+        if narrow and not self.narrow_ok:
+            raise _lib.ImpError("batch does not fit the narrow compact feed (molecule-local sources < 128, multiplicity 1 or 2)")
+        slot = DeviceSlot(torch.device(device), COMPACT16_FIELDS if narrow else COMPACT_FIELDS)
         slot.load(self, torch.cuda.current_stream())
         return slot
 
@@ -210,6 +219,7 @@ class PackedGraphBatch:
 
 FUSED_FIELDS = ("mol_ptr", "atom_id", "row_ptr", "col_src", "edge_bm")  # what imp_mpnn_forward_fused reads
 COMPACT_FIELDS = ("mol_ptr", "mol_eptr", "atom_w", "edge_w")              # what imp_mpnn_forward_fused_compact reads
+COMPACT16_FIELDS = ("mol_ptr", "mol_eptr", "atom_w", "edge_h")            # what imp_fused_plan_compact16 reads
 
 
 class DeviceSlot:
@@ -225,7 +235,11 @@ class DeviceSlot:
 
     @property
     def is_compact(self):
-        return self.fields == COMPACT_FIELDS
+        return self.fields in (COMPACT_FIELDS, COMPACT16_FIELDS)
+
+    @property
+    def is_narrow(self):
+        return self.fields == COMPACT16_FIELDS
 
     def load(self, chunk, stream):
         """Enqueues the H2D copies of ``chunk`` (pinned) on ``stream``; returns the bytes copied."""
@@ -261,7 +275,7 @@ class DeviceSlot:
 
     def compact_struct(self):
         return _lib.CompactGraph(self.n_pairs, self.n_atoms, self.n_cat_atoms, self.n_unique, self.n_edges, self.bond_vocab,
-                                 *(self.dev[k].data_ptr() for k in COMPACT_FIELDS))
+                                 *(self.dev[k].data_ptr() for k in self.fields))
 
     def c_struct(self):
         return _lib.Graph(self.n_pairs, self.n_atoms, self.n_cat_atoms, self.n_unique, self.n_edges, self.bond_vocab,

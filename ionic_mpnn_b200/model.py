@@ -546,13 +546,18 @@ class MPNNModel(TrainMixin):
                 cap = int(slack * tower / 128) + (P + 255) // 256 + 16
                 nb = min(nb, 256 + 2 * cap * 2048)
             plan = self._buf("fused_plan", nb, torch.uint8)
-            _lib.call("imp_fused_plan", C.byref(g) if g is not None else None, C.byref(cg) if cg is not None else None,
-                      s["atom_vocab_size"], batch.max_mol_atoms, plan.data_ptr(), nb, st)
+            if getattr(batch, "is_narrow", False):  # compact feed with 16-bit entry words
+                _lib.call("imp_fused_plan_compact16", C.byref(cg), s["atom_vocab_size"], batch.max_mol_atoms, plan.data_ptr(), nb, st)
+            else:
+                _lib.call("imp_fused_plan", C.byref(g) if g is not None else None, C.byref(cg) if cg is not None else None,
+                          s["atom_vocab_size"], batch.max_mol_atoms, plan.data_ptr(), nb, st)
             _lib.call("imp_mpnn_forward_fused_planned", plan.data_ptr(), P, batch.n_atoms, batch.n_cat_atoms, batch.bond_vocab,
                       self._ptr("atom_emb"), s["atom_vocab_size"], self._ptr("bond_emb"), d, s["bond_dim"], S,
                       self._ws["fused_packed" if self.tc_flags() & _lib.TC_GEN5 else "fused_packed6"].data_ptr(),
                       C.c_float(self.LN_EPS), self.tc_flags(), pooled.data_ptr(), st)
         elif g is None:
+            if getattr(batch, "is_narrow", False):
+                raise _lib.ImpError("the narrow compact feed (16-bit entry words) is read by the planned forward only")
             cg = batch.compact_struct()
             _lib.call("imp_mpnn_forward_fused_compact", C.byref(cg), self._ptr("atom_emb"), s["atom_vocab_size"],
                       self._ptr("bond_emb"), d, s["bond_dim"], S, self._ws["fused_packed"].data_ptr(), C.c_float(self.LN_EPS),
@@ -689,7 +694,7 @@ class MPNNModel(TrainMixin):
         Returns (out, bytes_h2d).  Nothing is synchronised on return: the caller syncs the current stream."""
         import torch
 
-        from .graph import COMPACT_FIELDS, FUSED_FIELDS, GRAPH_FIELDS, DeviceSlot
+        from .graph import COMPACT16_FIELDS, COMPACT_FIELDS, FUSED_FIELDS, GRAPH_FIELDS, DeviceSlot
 
         total = sum(c.n_pairs for c in chunks)
         if out is None:
@@ -719,7 +724,8 @@ class MPNNModel(TrainMixin):
                     use_compact = False
             if not use_compact:
                 ch.pin()
-            fields = COMPACT_FIELDS if use_compact else (FUSED_FIELDS if fused else GRAPH_FIELDS)
+            narrow = use_compact and self.planned_supported(ch) and getattr(ch, "narrow_ok", False)
+            fields = (COMPACT16_FIELDS if narrow else COMPACT_FIELDS) if use_compact else (FUSED_FIELDS if fused else GRAPH_FIELDS)
             if st["slots"] is None or st["fields"] != fields:
                 copy.wait_stream(compute)  # the old slots may still be read
                 st["slots"] = [DeviceSlot(self.device, fields), DeviceSlot(self.device, fields)]

@@ -113,6 +113,9 @@ def test_planned_forward_matches_the_self_contained_kernel_and_the_fp32_path(n_p
         c = planned.forward_packed(batch.to_compact("cuda")).cpu().numpy()
         planned.check_status()
         assert np.array_equal(a, c), "the compact feed and the int32 CSR feed give the same plan contents"
+        if batch.narrow_ok:
+            c16 = planned.forward_packed(batch.to_compact("cuda", narrow=True)).cpu().numpy()
+            assert np.array_equal(a, c16), "so does the narrow compact feed (16-bit entry words)"
         assert np.array_equal(a, planned.forward_packed(batch).cpu().numpy()), "run-to-run bit-identical"
         # the same arithmetic up to the LayerNorm evaluation order; an fp32 rounding difference can flip the 16-bit rounding
         # of an operand, so the two kernels agree to a few operand ulps (2^-11), not to fp32 rounding
@@ -140,3 +143,19 @@ def test_plan_capacity_overflow_is_reported_and_predict_retries():
     fz2 = build_model(124, 72, precision="fp16", seed=3, fused=True)
     got = fz2.predict(batch)  # retries by itself
     assert _rel(got, want) <= RTOL16
+
+
+def test_predict_stream_picks_the_narrow_feed_and_matches_predict():
+    from ionic_mpnn_b200 import graph
+    from ionic_mpnn_b200.viscosity import build_model
+
+    chunks = [graph.synth_batch(700, seed=40 + i)[0] for i in range(3)]
+    m = build_model(124, 72, precision="fp16", seed=3, fused=True)
+    out, nbytes = m.predict_stream(chunks)
+    torch.cuda.synchronize()
+    m.check_status()
+    assert m._stream_state["fields"][3] == "edge_h"
+    want = np.concatenate([m.predict(c).reshape(-1) for c in chunks])
+    assert np.array_equal(out.numpy(), want)
+    per_pair = nbytes / sum(c.n_pairs for c in chunks)
+    assert per_pair < 340, per_pair  # 16-bit atom words + 16-bit entry words + offsets + temperature

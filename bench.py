@@ -375,7 +375,7 @@ def run_train(args):
         tb = {"gated_update_bwd": 5 * N * d * 4, "gated_update": 3 * N * d * 4, "edge_messages_grouped": Eu * (2 * d * 4 + 12),
               # stored-gate forms: the forward also writes z, r, tanh(.); the backward reads h, agg, z, r, tanh(.), g_out and
               # writes dh, dagg
-              "gated_update_train": 6 * N * d * 4, "gated_update_bwd_stored": 8 * N * d * 4, "gated_update_bwd_tc": 8 * N * d * 4,
+              "gated_update_train": 6 * N * d * 4, "gated_update_tc32": 6 * N * d * 4, "gated_update_bwd_stored": 8 * N * d * 4, "gated_update_bwd_tc": 8 * N * d * 4,
               "segment_sum": Eu * d * 4 + N * d * 4 + 4 * N, "segment_sum_add": Eu * d * 4 + 2 * N * d * 4 + 4 * N,
               "bond_transform_bwd": Eu * (2 * d * 4 + 12), "embed_atoms": 4 * N + N * d * 4, "embed_bwd": 4 * N + N * d * 4,
               "bond_occurrence_norm2": S * Eu * 2 * d * 4 + 12 * Eu, "sumsq": N * d * 4,
@@ -383,7 +383,7 @@ def run_train(args):
         tf = {"gated_update_bwd": 36 * N * d * d, "gated_update": 12 * N * d * d, "edge_messages_grouped": 2 * Eu * d * d,
               # without recomputation: 3 input-gradient + 3 weight-gradient contractions of 2 * 64 * 32 FLOP per atom (the
               # tcgen05 kernel executes each as three tf32 MMAs)
-              "gated_update_train": 12 * N * d * d, "gated_update_bwd_stored": 24 * N * d * d, "gated_update_bwd_tc": 24 * N * d * d,
+              "gated_update_train": 12 * N * d * d, "gated_update_tc32": 12 * N * d * d, "gated_update_bwd_stored": 24 * N * d * d, "gated_update_bwd_tc": 24 * N * d * d,
               "bond_transform_bwd": 2 * Eu * d * d, "bond_occurrence_norm2": S * 2 * Eu * d * d * 8}
         counts = {}
         for n, _, _ in events:

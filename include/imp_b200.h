@@ -435,6 +435,12 @@ int64_t imp_gated_update_bwd_workspace_floats(int32_t d);
 int imp_gated_update_train(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
                            const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_h_out, float* d_z,
                            float* d_r, float* d_ht, void* stream);
+/* imp_gated_update / imp_gated_update_train on the tensor cores with fp32-class accuracy (csrc/fwd_tc32.cu): both Dense
+ * products of GatedUpdate.call (models/layers.py:146-151) as tcgen05.mma kind::tf32 with every operand split into two tf32
+ * terms (3 MMAs per product), fp32 epilogue (expf / tanhf / sqrtf).  d_z / d_r / d_ht: all three (training form) or all NULL. */
+int imp_gated_update_tc32(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
+                          const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_h_out, float* d_z,
+                          float* d_r, float* d_ht, void* stream);
 /* The same contract on the tensor cores (csrc/bwd_tc.cu): the six contractions of the GatedUpdate backward as tcgen05.mma
  * kind::tf32 with every operand split into two tf32 terms (3 MMAs per product: fp32-class accuracy, the 2e-4 gradient bound
  * of the fp32 kernels holds); the weight-gradient accumulator stays in tensor memory for all tiles of a CTA. */

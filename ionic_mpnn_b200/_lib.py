@@ -151,6 +151,8 @@ SIGNATURES = {
                                        C.POINTER(GruWeights), C.c_float, vp, vp, vp, vp, vp, vp]),
     "imp_gated_update_train": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(GruWeights), C.POINTER(GruWeights),
                                          C.c_float, vp, vp, vp, vp, vp]),
+    "imp_gated_update_tc32": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(GruWeights), C.POINTER(GruWeights),
+                                        C.c_float, vp, vp, vp, vp, vp]),
     "imp_gated_update_bwd_stored": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(GruWeights),
                                               C.POINTER(GruWeights), C.c_float, vp, vp, vp, vp, vp, vp]),
     "imp_gated_update_bwd_tc": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(GruWeights),

@@ -1,0 +1,256 @@
+// GatedUpdate forward with fp32-class accuracy on the tensor cores (tcgen05 kind::tf32, 3xTF32 operand splits), atom_dim 32.
+//
+// Replaces GatedUpdate.call (models/layers.py:142-156) on the 1e-5 path: the fp32 inference kernels and the forward half of
+// the training step (train_viscosity.py:227-230), where the fp32 SIMT kernel (gated_update32_kernel, 12 k FMAs per atom)
+// is FFMA-bound.  Same arithmetic contract: fp32 state in and out, expf / tanhf / sqrtf epilogue, biased-variance
+// LayerNorm with epsilon, residual; optionally keeps the gates for the backward pass (imp_gated_update_train).
+//
+//   [z | r] pre-activations = [h | agg] . [Wz | Wr]      (128 x 64, K = 64)   A = the row operand in TENSOR MEMORY, hi and lo terms
+//   candidate pre-activation = [r*h | agg] . Wh          (128 x 32, K = 64)   (r*h overwrites the h columns of the operand)
+// every product = hi.hi + hi.lo + lo.hi with x = hi + lo, hi = x with 13 low significand bits cleared (csrc/bwd_tc.cu).
+// One thread per atom row = TMEM lane; 224 TMEM columns and 50 KB of shared memory per CTA: two CTAs per SM.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace imp {
+
+constexpr int FT_D = 32;
+constexpr int FT_TILE = 128;
+
+struct FtSmem {
+  float W1[2][64 * 64];  // B[n][k] = (n < 32 ? Wz : Wr)[k][n & 31], K-major tf32, hi then lo
+  float W2[2][32 * 64];  // B[n][k] = Wh[k][n]
+  float bz[FT_D], br[FT_D], bh[FT_D], gamma[FT_D], beta[FT_D];
+  uint64_t bar[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void ft_split(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = x - hi;
+}
+__device__ __forceinline__ void ft_mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, bool acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d),
+      "r"(a), "l"(b), "r"(idesc), "r"((uint32_t)acc)
+      : "memory");
+}
+__device__ __forceinline__ float ft_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(FT_TILE, 2) gated_update_tc32_kernel(const float* __restrict__ h, const float* __restrict__ agg,
+                                                                       int n_atoms, int n_cat, int n_cta_cat, imp_gru_weights_t wc,
+                                                                       imp_gru_weights_t wa, float eps, float* __restrict__ h_out,
+                                                                       float* __restrict__ z_out, float* __restrict__ r_out,
+                                                                       float* __restrict__ ht_out) {
+  constexpr int D = FT_D;
+  extern __shared__ __align__(1024) unsigned char ft_raw[];
+  FtSmem& s = *reinterpret_cast<FtSmem*>(ft_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool is_cat = (int)blockIdx.x < n_cta_cat;
+  const imp_gru_weights_t& w = is_cat ? wc : wa;
+  const int base = is_cat ? 0 : n_cat, a_end = is_cat ? n_cat : n_atoms;
+  const int n_tiles = (a_end - base + FT_TILE - 1) / FT_TILE;
+  const int cta = is_cat ? blockIdx.x : blockIdx.x - n_cta_cat, n_cta = is_cat ? n_cta_cat : gridDim.x - n_cta_cat;
+
+  for (int i = tid; i < 64 * 64; i += FT_TILE) {  // element (n, k) at chunk_off(n, k / 4, R) + (k % 4) * 4
+    const int n = i / 64, k = i % 64;
+    float hi, lo;
+    ft_split(__ldg((n < 32 ? w.Wz : w.Wr) + k * D + (n & 31)), hi, lo);
+    const int o = (tc::chunk_off(n, k / 4, 64) + (k % 4) * 4) / 4;
+    s.W1[0][o] = hi, s.W1[1][o] = lo;
+    if (n < 32) {
+      ft_split(__ldg(w.Wh + k * D + n), hi, lo);
+      const int o2 = (tc::chunk_off(n, k / 4, 32) + (k % 4) * 4) / 4;
+      s.W2[0][o2] = hi, s.W2[1][o2] = lo;
+    }
+  }
+  if (tid < D) s.bz[tid] = w.bz[tid], s.br[tid] = w.br[tid], s.bh[tid] = w.bh[tid], s.gamma[tid] = w.gamma[tid], s.beta[tid] = w.beta[tid];
+  if (warp == 0) tc::tmem_alloc<256>(&s.tmem_base);
+  if (tid == 0) {
+    tc::mbar_init(&s.bar[0], 1);
+    tc::mbar_init(&s.bar[1], 1);
+    tc::mbar_fence_init();
+  }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+
+  const uint32_t tm = s.tmem_base, lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t tXhi = tm, tXlo = tm + 64, tD1 = tm + 128, tD2 = tm + 192;  // X = [h -> r*h | agg]
+  const uint32_t id64 = tc::make_idesc(tc::FMT_TF32, FT_TILE, 64), id32 = tc::make_idesc(tc::FMT_TF32, FT_TILE, 32);
+  const uint64_t dW1[2] = {tc::make_smem_desc(tc::smem_u32(s.W1[0]), 64 * 16, 128), tc::make_smem_desc(tc::smem_u32(s.W1[1]), 64 * 16, 128)};
+  const uint64_t dW2[2] = {tc::make_smem_desc(tc::smem_u32(s.W2[0]), 32 * 16, 128), tc::make_smem_desc(tc::smem_u32(s.W2[1]), 32 * 16, 128)};
+  auto to_tmem = [&](uint32_t col, const float (&v)[32]) {
+    uint32_t hi[32], lo[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      float a, b;
+      ft_split(v[c], a, b);
+      hi[c] = __float_as_uint(a), lo[c] = __float_as_uint(b);
+    }
+    tc::tmem_st32(tXhi + lane_off + col, hi);
+    tc::tmem_st32(tXlo + lane_off + col, lo);
+  };
+  uint32_t ph = 0;
+  for (int tile = cta; tile < n_tiles; tile += n_cta) {
+    const int a0 = base + tile * FT_TILE;
+    const int row = a0 + tid;
+    const bool ok = tid < min(FT_TILE, a_end - a0);
+    {
+      const int nrow = row + n_cta * FT_TILE;  // next tile's rows -> L2
+      if (nrow < a_end) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(h + (int64_t)nrow * D));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(agg + (int64_t)nrow * D));
+      }
+    }
+    float hv[32];
+    {
+      float av[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 x = ok ? __ldg(reinterpret_cast<const float4*>(h + (int64_t)row * D) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 y = ok ? __ldg(reinterpret_cast<const float4*>(agg + (int64_t)row * D) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        hv[4 * c] = x.x, hv[4 * c + 1] = x.y, hv[4 * c + 2] = x.z, hv[4 * c + 3] = x.w;
+        av[4 * c] = y.x, av[4 * c + 1] = y.y, av[4 * c + 2] = y.z, av[4 * c + 3] = y.w;
+      }
+      to_tmem(0, hv), to_tmem(32, av);
+    }
+    tc::tmem_wait_st();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) {
+      tc::fence_after_thread_sync();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ko = (uint64_t)(ks * 2 * 64 * 16 / 16);
+          ft_mma_ts(tD1, tXhi + 8 * ks, dW1[0] + ko, id64, ks > 0);
+          ft_mma_ts(tD1, tXhi + 8 * ks, dW1[1] + ko, id64, true);
+          ft_mma_ts(tD1, tXlo + 8 * ks, dW1[0] + ko, id64, true);
+        }
+        tc::mma_commit(&s.bar[0]);
+      }
+      __syncwarp();
+    }
+    tc::mbar_wait(&s.bar[0], ph);
+    tc::fence_after_thread_sync();
+    float zv[32];
+    {
+      float v[32], rh[32];
+      tc::tmem_ld32(tD1 + 32 + lane_off, v);  // r
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        v[c] = ft_sigmoid(v[c] + s.br[c]);
+        rh[c] = v[c] * hv[c];
+      }
+      if (r_out && ok) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) reinterpret_cast<float4*>(r_out + (int64_t)row * D)[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      }
+      to_tmem(0, rh);  // over the h columns: the first product has consumed them
+      tc::tmem_ld32(tD1 + lane_off, v);  // z
+#pragma unroll
+      for (int c = 0; c < 32; ++c) zv[c] = ft_sigmoid(v[c] + s.bz[c]);
+    }
+    tc::tmem_wait_st();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) {
+      tc::fence_after_thread_sync();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ko = (uint64_t)(ks * 2 * 32 * 16 / 16);
+          ft_mma_ts(tD2, tXhi + 8 * ks, dW2[0] + ko, id32, ks > 0);
+          ft_mma_ts(tD2, tXhi + 8 * ks, dW2[1] + ko, id32, true);
+          ft_mma_ts(tD2, tXlo + 8 * ks, dW2[0] + ko, id32, true);
+        }
+        tc::mma_commit(&s.bar[1]);
+      }
+      __syncwarp();
+    }
+    if (z_out && ok) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) reinterpret_cast<float4*>(z_out + (int64_t)row * D)[c] = make_float4(zv[4 * c], zv[4 * c + 1], zv[4 * c + 2], zv[4 * c + 3]);
+    }
+    tc::mbar_wait(&s.bar[1], ph);
+    tc::fence_after_thread_sync();
+    {
+      float n[32], mean = 0.f;
+      tc::tmem_ld32(tD2 + lane_off, n);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        n[c] = tanhf(n[c] + s.bh[c]);
+        if (ht_out == nullptr) {
+          n[c] = (1.0f - zv[c]) * hv[c] + zv[c] * n[c];
+          mean += n[c];
+        }
+      }
+      if (ht_out) {
+        if (ok) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) reinterpret_cast<float4*>(ht_out + (int64_t)row * D)[c] = make_float4(n[4 * c], n[4 * c + 1], n[4 * c + 2], n[4 * c + 3]);
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          n[c] = (1.0f - zv[c]) * hv[c] + zv[c] * n[c];
+          mean += n[c];
+        }
+      }
+      mean *= (1.0f / D);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        n[c] -= mean;
+        var = fmaf(n[c], n[c], var);
+      }
+      const float inv = 1.0f / sqrtf(var * (1.0f / D) + eps);
+      if (ok) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          reinterpret_cast<float4*>(h_out + (int64_t)row * D)[c] =
+              make_float4(n[4 * c] * inv * s.gamma[4 * c] + s.beta[4 * c] + hv[4 * c], n[4 * c + 1] * inv * s.gamma[4 * c + 1] + s.beta[4 * c + 1] + hv[4 * c + 1],
+                          n[4 * c + 2] * inv * s.gamma[4 * c + 2] + s.beta[4 * c + 2] + hv[4 * c + 2],
+                          n[4 * c + 3] * inv * s.gamma[4 * c + 3] + s.beta[4 * c + 3] + hv[4 * c + 3]);
+      }
+    }
+    ph ^= 1;
+    tc::fence_before_thread_sync();
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<256>(tm);
+}
+
+}  // namespace imp
+
+using namespace imp;
+
+// d_z / d_r / d_ht: all three or none (NULL: plain forward)
+extern "C" int imp_gated_update_tc32(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
+                                     const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_h_out,
+                                     float* d_z, float* d_r, float* d_ht, void* stream) {
+  IMP_REQUIRE(n_atoms >= 0 && n_cat_atoms >= 0 && n_cat_atoms <= n_atoms, IMP_ERR_ARG, "imp_gated_update_tc32: bad sizes");
+  IMP_REQUIRE(d == FT_D, IMP_ERR_DIM, "imp_gated_update_tc32: atom_dim %d not supported (32)", d);
+  if (n_atoms == 0) return 0;
+  IMP_REQUIRE(d_h && d_agg && d_h_out && w_cat && w_an && w_cat->Wz && w_an->Wz, IMP_ERR_ARG, "imp_gated_update_tc32: null pointer");
+  IMP_REQUIRE((d_z != nullptr) == (d_r != nullptr) && (d_z != nullptr) == (d_ht != nullptr), IMP_ERR_ARG,
+              "imp_gated_update_tc32: pass all three gate outputs or none");
+  IMP_REQUIRE(imp_device_is_sm100(), IMP_ERR_UNSUPPORTED, "imp_gated_update_tc32: tcgen05 needs an sm_100 device");
+  int dev = 0, sms = 148;
+  IMP_CUDA(cudaGetDevice(&dev));
+  IMP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int tiles_cat = (int)ceil_div(n_cat_atoms, FT_TILE), tiles_an = (int)ceil_div(n_atoms - n_cat_atoms, FT_TILE);
+  const int tiles = tiles_cat + tiles_an;
+  const int grid = tiles < 2 * sms ? (tiles < 2 ? 2 : tiles) : 2 * sms;  // two CTAs per SM; both towers get at least one CTA
+  int n_cta_cat = tiles > 0 ? (int)((int64_t)grid * tiles_cat / tiles) : 1;
+  n_cta_cat = n_cta_cat < 1 ? 1 : (n_cta_cat > grid - 1 ? grid - 1 : n_cta_cat);
+  const size_t smem = sizeof(FtSmem) + 1024;
+  IMP_CUDA(cudaFuncSetAttribute(gated_update_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gated_update_tc32_kernel<<<grid, FT_TILE, smem, (cudaStream_t)stream>>>(d_h, d_agg, n_atoms, n_cat_atoms, n_cta_cat, *w_cat, *w_an, eps,
+                                                                        d_h_out, d_z, d_r, d_ht);
+  IMP_LAUNCH_CHECK();
+  return 0;
+}

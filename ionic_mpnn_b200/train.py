@@ -168,11 +168,18 @@ class TrainMixin:
                       tab.data_ptr() + 4 * per * (S + i), 0, msg.data_ptr(), cws.data_ptr(), sm)
             _lib.call("imp_segment_sum", C.byref(g), msg.data_ptr(), d, agg[i].data_ptr(), sm)
             wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
+            # tensor-core forward (3xTF32, csrc/fwd_tc32.cu) where it is built (atom_dim 32); the fp32 SIMT kernels otherwise
+            tc_fwd = d == 32 and getattr(self, "tc_forward", True)
             if gates is None:
-                _lib.call("imp_gated_update", h[i].data_ptr(), agg[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc), C.byref(wa),
-                          C.c_float(self.LN_EPS), h[i + 1].data_ptr(), sm)
+                if tc_fwd:
+                    _lib.call("imp_gated_update_tc32", h[i].data_ptr(), agg[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc),
+                              C.byref(wa), C.c_float(self.LN_EPS), h[i + 1].data_ptr(), None, None, None, sm)
+                else:
+                    _lib.call("imp_gated_update", h[i].data_ptr(), agg[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc),
+                              C.byref(wa), C.c_float(self.LN_EPS), h[i + 1].data_ptr(), sm)
             else:  # the gates are kept for the backward pass (it then skips the recomputation of the three Dense layers)
-                _lib.call("imp_gated_update_train", h[i].data_ptr(), agg[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc),
+                _lib.call("imp_gated_update_tc32" if tc_fwd else "imp_gated_update_train", h[i].data_ptr(), agg[i].data_ptr(), N,
+                          batch.n_cat_atoms, d, C.byref(wc),
                           C.byref(wa), C.c_float(self.LN_EPS), h[i + 1].data_ptr(), gates[i][0].data_ptr(), gates[i][1].data_ptr(),
                           gates[i][2].data_ptr(), sm)
         pooled, dpooled = self._buf("tr_pooled", 2 * P * d), self._buf("tr_dpooled", 2 * P * d)

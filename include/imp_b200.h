@@ -194,6 +194,7 @@ int imp_gated_update_wide(const float* d_h, const float* d_agg, int32_t n_atoms,
 #define IMP_TC_GEN3 512 /* imp_mpnn_forward_fused: kept for callers of round 1; the self-contained kernel IS generation 3 */
 #define IMP_TC_GEN4 1024 /* imp_mpnn_forward_fused: the fourth-generation kernel (arrive-and-continue; measured slower) */
 #define IMP_TC_GEN5 2048 /* imp_mpnn_forward_fused_planned: the fifth-generation kernel (weights from imp_fused_pack; comparison) */
+#define IMP_TC_GEN7 4096 /* imp_mpnn_forward_fused_planned: the seventh-generation kernel (weights from imp_fused_pack_planned7) */
 int64_t imp_gru_pack_bytes(int32_t d);
 int imp_gru_pack_bf16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
 int imp_gru_pack_f16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
@@ -340,6 +341,9 @@ int imp_mpnn_forward_fused_compact(const imp_compact_graph_t* cg, const float* d
 int64_t imp_fused_pack_planned_bytes(int32_t d, int32_t bond_dim);
 int imp_fused_pack_planned(const float* d_bond_transform /* [K,d,d] */, const imp_gru_weights_t* w, int32_t d, int32_t bond_dim,
                            void* d_packed, void* stream);
+/* The same block with the K order of the Wc halves that the seventh generation's Z fragments use (flag IMP_TC_GEN7). */
+int imp_fused_pack_planned7(const float* d_bond_transform /* [K,d,d] */, const imp_gru_weights_t* w, int32_t d, int32_t bond_dim,
+                            void* d_packed, void* stream);
 int64_t imp_fused_plan_bytes(int32_t n_pairs, int32_t n_atoms, int32_t n_unique, int32_t max_mol_atoms);
 int imp_fused_plan(const imp_graph_t* g, const imp_compact_graph_t* cg, int32_t atom_vocab, int32_t max_mol_atoms, void* d_plan,
                    int64_t plan_bytes, void* stream);

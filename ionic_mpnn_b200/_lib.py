@@ -62,6 +62,7 @@ TC_WIDE_NO_CLUSTER = 256
 TC_GEN3 = 512
 TC_GEN4 = 1024
 TC_GEN5 = 2048
+TC_GEN7 = 4096
 PACK_DOUBLE_EDGES = 1
 PACK_SHIFT_IDS = 2
 
@@ -120,6 +121,7 @@ SIGNATURES = {
                                                  C.c_float, C.c_int32, C.c_int32, vp, vp, vp]),
     "imp_fused_pack_planned_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "imp_fused_pack_planned": (C.c_int, [vp, C.POINTER(GruWeights), C.c_int32, C.c_int32, vp, vp]),
+    "imp_fused_pack_planned7": (C.c_int, [vp, C.POINTER(GruWeights), C.c_int32, C.c_int32, vp, vp]),
     "imp_fused_plan_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "imp_fused_plan": (C.c_int, [C.POINTER(Graph), C.POINTER(CompactGraph), C.c_int32, C.c_int32, vp, C.c_int64, vp]),
     "imp_fused_plan_compact16": (C.c_int, [C.POINTER(CompactGraph), C.c_int32, C.c_int32, vp, C.c_int64, vp]),

@@ -21,6 +21,7 @@
 //   [ 64, 96)  aggregated messages: D of GEMM1 (fp32) = tf32 A operand of the gate and candidate GEMMs
 //   [ 96,112)  h operand (16-bit pairs), then r*h operand        [112,120)  the constant (1, 0, ...) bias K-step
 #include "fused_common.cuh"
+#include "fused_pack6.cuh"
 #include "fused_plan.cuh"
 
 namespace imp {
@@ -40,36 +41,17 @@ constexpr int F6_THREADS = 128;
 #endif
 constexpr int F6_HS = 20;  // words per row of the shared-memory h copy (80 B: 16 halves pairs + pad, conflict-free 16-byte reads)
 
-struct FusedPack6 {  // one (tower, step)
-  static constexpr int WC_BYTES = FZ_D * (FZ_D * FZ_K) * 2;   // Wc in two K halves, as FusedPack (16 KiB)
-  static constexpr int BZRH_BYTES = 2 * FZ_D * FZ_D * 2;      // [Wr_h | Wz_h]^T  f16   [64 x 32]
-  static constexpr int BZRA_BYTES = 2 * FZ_D * FZ_D * 4;      // [Wr_a | Wz_a]^T  tf32  [64 x 32]
-  static constexpr int BHH_BYTES = FZ_D * FZ_D * 2;           // Wh_h^T           f16   [32 x 32]
-  static constexpr int BHA_BYTES = FZ_D * FZ_D * 4;           // Wh_a^T           tf32  [32 x 32]
-  static constexpr int OFF_BZRH = WC_BYTES;
-  static constexpr int OFF_BZRA = OFF_BZRH + BZRH_BYTES;
-  static constexpr int OFF_BHH = OFF_BZRA + BZRA_BYTES;
-  static constexpr int OFF_BHA = OFF_BHH + BHH_BYTES;
-  static constexpr int OFF_BIAS = OFF_BHA + BHA_BYTES;        // gamma[32], beta[32] (fp32)
-  static constexpr int OFF_BBZR = OFF_BIAS + 2 * FZ_D * 4;    // [64 x 16] f16, column 0 = 0.5 (br | bz)
-  static constexpr int OFF_BBH = OFF_BBZR + 2 * FZ_D * 16 * 2;  // [32 x 16] f16, column 0 = bh
-  static constexpr int BYTES = OFF_BBH + FZ_D * 16 * 2;
-};
-static_assert(FusedPack6::BYTES % 128 == 0 && FusedPack6::OFF_BIAS % 16 == 0, "pack alignment");
-
-__device__ __forceinline__ uint32_t f32_to_tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return r;
-}
-
 // Gate order inside the 64-wide block: n < 32 is the reset gate r, n >= 32 the update gate z.
-__global__ void fused_pack6_kernel(const float* __restrict__ W /* [K, d, d] */, imp_gru_weights_t w, unsigned char* __restrict__ out) {
+// zperm7: K order of a Wc half for the seventh generation (fused_fwd7.cu), whose Z rows are built four lanes wide and stored
+// with tcgen05.st.16x256b: K index 16 (m % 8) + 4 (m / 8) + (k % 4) instead of 4 m + (k % 4).
+__global__ void fused_pack6_kernel(const float* __restrict__ W /* [K, d, d] */, imp_gru_weights_t w, unsigned char* __restrict__ out,
+                                   int zperm7) {
   constexpr int D = FZ_D, KK = FZ_D * FZ_K;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < D * KK) {  // Wc_hz[l][m*4 + (k - 4 hz)] = W[k][l][m]  (models/layers.py:108 re-associated, see fused_fwd.cu)
+  if (i < D * KK) {  // Wc_hz[l][K(m, k)] = W[k][l][m]  (models/layers.py:108 re-associated, see fused_fwd.cu)
     const int l = i / KK, kk = i % KK, m = kk / FZ_K, k = kk % FZ_K;
-    const int hz = k / 4, kq = m * 4 + (k % 4);
+    // K halves split the state columns m (16 each); inside a half K = 8 (m % 16) + k
+    const int hz = zperm7 ? k / 4 : m / 16, kq = zperm7 ? 16 * (m % 8) + 4 * (m / 8) + (k % 4) : (m % 16) * 8 + k;
     *reinterpret_cast<uint16_t*>(out + hz * (FusedPack6::WC_BYTES / 2) + tc::chunk_off(l, kq / 8, D) + (kq % 8) * 2) =
         tc::cvt16<tc::FMT_F16>(W[(k * D + l) * D + m]);
   }
@@ -124,16 +106,32 @@ struct Fused6Args {
   float eps;
 };
 
-// A operand of a kind::tf32 MMA from tensor memory: row i in lane i, 8 consecutive 32-bit columns = K = 8.
-__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
-      : "memory");
-}
-
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// Optional phase timing (tools/fused_prof2.py builds with -DF6_PHASE_PROF): clock() deltas of thread 0 (class 0) and thread 96
+// (class 1) of every context, summed per phase in shared memory and flushed to a device symbol at the end of the kernel.
+#ifdef F6_PHASE_PROF
+__device__ unsigned long long f6_prof_total[2][16];
+#define F6_PROF_DECL                                               \
+  __shared__ unsigned int sprof[2][16];                            \
+  if (tid < 32) sprof[tid >> 4][tid & 15] = 0u;                    \
+  const int prof_cls = (t == 0) ? 0 : (t == 96) ? 1 : -1;          \
+  unsigned int prof_last = (unsigned int)clock()
+#define F6_PROF(i)                                                  \
+  do {                                                             \
+    if (prof_cls >= 0) {                                           \
+      const unsigned int now_ = (unsigned int)clock();             \
+      atomicAdd(&sprof[prof_cls][i], now_ - prof_last);            \
+      prof_last = now_;                                            \
+    }                                                              \
+  } while (0)
+#define F6_PROF_FLUSH \
+  if (tid < 32) atomicAdd(&f6_prof_total[tid >> 4][tid & 15], (unsigned long long)sprof[tid >> 4][tid & 15])
+#else
+#define F6_PROF_DECL
+#define F6_PROF(i)
+#define F6_PROF_FLUSH
+#endif
 
 struct F6True { static constexpr bool value = true; };
 struct F6False { static constexpr bool value = false; };
@@ -145,6 +143,7 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ctx = tid >> 7, t = tid & 127, wq = warp & 3;
+  F6_PROF_DECL;
   const int wbytes = a.steps * FusedPack6::BYTES;
   const int ctab_bytes = (a.bond_vocab * 16 + 127) / 128 * 128;
   uint4* s_ctab = reinterpret_cast<uint4*>(smem + wbytes);
@@ -234,8 +233,10 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
       tc::mbar_arrive_expect_tx(&ws.pbar[buf ^ 1], (uint32_t)sizeof(FusedTile));
       tc::bulk_copy_g2s(&ws.plan[buf ^ 1], tiles + tile + stride, (uint32_t)sizeof(FusedTile), &ws.pbar[buf ^ 1]);
     }
+    F6_PROF(0);
     tc::mbar_wait(&ws.pbar[buf], (pph >> buf) & 1u);
     pph ^= 1u << buf;
+    F6_PROF(1);
     const FusedTile& tp = ws.plan[buf];
     const uint32_t sw = tp.slot[myslot];
     const int r = sw & 127, deg = (sw >> 7) & 31, aid = (int)(sw >> 22);
@@ -257,7 +258,9 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
       tc::tmem_wait_st();
     }
     tc::fence_before_thread_sync();
+    F6_PROF(2);
     tc::named_bar_sync(bar_id, F6_THREADS);
+    F6_PROF(3);
 
     for (int s = 0; s < a.steps; ++s) {
       const uint64_t dstep = (uint64_t)(s * (FusedPack6::BYTES / 16));
@@ -266,29 +269,32 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
 #pragma unroll 1
       for (int hz = 0; hz < 2; ++hz) {
         __half2 acc[D * 2];
-        // one entry: acc (+)= h[src] (x) (mult * c[4 hz .. 4 hz + 4))
+        // one entry: acc (+)= h[src][16 hz .. 16 hz + 16) (x) (mult * c[0..8)).  The K halves split the STATE columns, not the
+        // bond components: every byte of a neighbour's row is gathered once per step (the gathers saturate the shared-memory
+        // pipe during the Z phases: 16-byte reads of random rows conflict 2.15x)
         auto entry = [&](uint32_t ec, auto first_entry) {
-          const uint2 cu = reinterpret_cast<const uint2*>(s_ctab + ((ec >> 8) & 0xff))[hz];
+          const uint4 cu = s_ctab[(ec >> 8) & 0xff];
           const uint32_t mbits = (ec >> 16) | (ec & 0xffff0000u);
           const __half2 mult = *reinterpret_cast<const __half2*>(&mbits);
-          const __half2 c0 = __hmul2(*reinterpret_cast<const __half2*>(&cu.x), mult);
-          const __half2 c1 = __hmul2(*reinterpret_cast<const __half2*>(&cu.y), mult);
-          const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[(ec & 0x7f) * F6_HS]);
+          const __half2 c[4] = {__hmul2(*reinterpret_cast<const __half2*>(&cu.x), mult), __hmul2(*reinterpret_cast<const __half2*>(&cu.y), mult),
+                                __hmul2(*reinterpret_cast<const __half2*>(&cu.z), mult), __hmul2(*reinterpret_cast<const __half2*>(&cu.w), mult)};
+          const uint4* hp = reinterpret_cast<const uint4*>(&ws.hb[(ec & 0x7f) * F6_HS]) + 2 * hz;
 #pragma unroll
-          for (int q = 0; q < D / 8; ++q) {  // 8 columns per 16-byte read; HFMA2 broadcasts the low / high half
+          for (int q = 0; q < 2; ++q) {  // 8 columns per 16-byte read; HFMA2 broadcasts the low / high half
             const uint4 hv = hp[q];
             const __half2 hw[4] = {*reinterpret_cast<const __half2*>(&hv.x), *reinterpret_cast<const __half2*>(&hv.y),
                                    *reinterpret_cast<const __half2*>(&hv.z), *reinterpret_cast<const __half2*>(&hv.w)};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const __half2 lo = __low2half2(hw[i]), hi = __high2half2(hw[i]);
-              const int m = 8 * q + 2 * i;
-              if constexpr (decltype(first_entry)::value) {
-                acc[m * 2] = __hmul2(lo, c0), acc[m * 2 + 1] = __hmul2(lo, c1);
-                acc[m * 2 + 2] = __hmul2(hi, c0), acc[m * 2 + 3] = __hmul2(hi, c1);
-              } else {
-                acc[m * 2] = __hfma2(lo, c0, acc[m * 2]), acc[m * 2 + 1] = __hfma2(lo, c1, acc[m * 2 + 1]);
-                acc[m * 2 + 2] = __hfma2(hi, c0, acc[m * 2 + 2]), acc[m * 2 + 3] = __hfma2(hi, c1, acc[m * 2 + 3]);
+              const int m = 8 * q + 2 * i;  // column inside the half; accumulator (= TMEM column) 4 m + k / 2
+#pragma unroll
+              for (int kp = 0; kp < 4; ++kp) {
+                if constexpr (decltype(first_entry)::value) {
+                  acc[m * 4 + kp] = __hmul2(lo, c[kp]), acc[m * 4 + 4 + kp] = __hmul2(hi, c[kp]);
+                } else {
+                  acc[m * 4 + kp] = __hfma2(lo, c[kp], acc[m * 4 + kp]), acc[m * 4 + 4 + kp] = __hfma2(hi, c[kp], acc[m * 4 + 4 + kp]);
+                }
               }
             }
           }
@@ -306,10 +312,12 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
             entry(ec, F6False{});
           }
         }
+        F6_PROF(4);
         if (hz == 1) {  // GEMM1a must have consumed the first half before its columns are rewritten
           tc::mbar_wait(&ws.bar[3], ph);
           tc::fence_after_thread_sync();
         }
+        F6_PROF(5);
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           uint32_t rr[32];
@@ -319,7 +327,9 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
         }
         tc::tmem_wait_st();
         tc::fence_before_thread_sync();
+        F6_PROF(6);
         operands_ready();
+        F6_PROF(7);
         if (mma_warp) {
           tc::fence_after_thread_sync();
           if (tc::elect_one()) {
@@ -341,8 +351,10 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
           __syncwarp();
         }
       }
+      F6_PROF(8);
       tc::mbar_wait(&ws.bar[1], ph);
       tc::fence_after_thread_sync();
+      F6_PROF(9);
       {  // reset gate -> r * h operand (over the h operand: the gate GEMM has read it)
         float v[32];
         tc::tmem_ld32(tCzr + lane_off, v);
@@ -373,7 +385,9 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
       }
       tc::tmem_wait_st();
       tc::fence_before_thread_sync();
+      F6_PROF(10);
       operands_ready();
+      F6_PROF(11);
       // ------------------------------------------------------------ candidate GEMM: [r*h | 1] . [Wh_h ; bh] + agg . Wh_a
       if (mma_warp) {
         tc::fence_after_thread_sync();
@@ -402,8 +416,10 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
           }
         }
       }
+      F6_PROF(12);
       tc::mbar_wait(&ws.bar[2], ph);
       tc::fence_after_thread_sync();
+      F6_PROF(13);
       {  // candidate, blend, LayerNorm (biased variance, eps), residual  (models/layers.py:151-156)
         float gq[32];
         tc::tmem_ld32(tCht + lane_off, gq);
@@ -433,8 +449,10 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
         }
       }
       tc::fence_before_thread_sync();
+      F6_PROF(14);
       tc::named_bar_sync(bar_id, F6_THREADS);
       ph ^= 1;
+      F6_PROF(15);
     }
     // ---------------------------------------------------------------- GlobalSumPool, 16 columns at a time
     // (the h copy is dead after the last step: its rows take 16 fp32 columns; a half-warp sums one molecule's natural rows)
@@ -466,10 +484,19 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
   }
   tc::fence_before_thread_sync();
   __syncthreads();
+  F6_PROF_FLUSH;
   if (warp == 0) tc::tmem_dealloc<512>(ctl.tmem_base);
 }
 
 }  // namespace imp
+
+#ifdef F6_PHASE_PROF
+extern "C" void imp_debug_f6_prof(unsigned long long* host_out) {  // reads and clears the phase counters (profiling builds only)
+  cudaMemcpyFromSymbol(host_out, imp::f6_prof_total, sizeof(unsigned long long) * 32);
+  unsigned long long z[32] = {};
+  cudaMemcpyToSymbol(imp::f6_prof_total, z, sizeof(z));
+}
+#endif
 
 using namespace imp;
 
@@ -487,16 +514,26 @@ extern "C" int64_t imp_fused_pack_planned_bytes(int32_t d, int32_t bond_dim) {
   return (d == FZ_D && bond_dim == FZ_K) ? (int64_t)FusedPack6::BYTES : (int64_t)IMP_ERR_DIM;
 }
 
-extern "C" int imp_fused_pack_planned(const float* d_bond_transform, const imp_gru_weights_t* w, int32_t d, int32_t bond_dim,
-                                      void* d_packed, void* stream) {
+static int fused_pack_planned_any(const float* d_bond_transform, const imp_gru_weights_t* w, int32_t d, int32_t bond_dim,
+                                  void* d_packed, void* stream, int zperm7) {
   IMP_REQUIRE(d_bond_transform && d_packed && w && w->Wz && w->bz && w->Wr && w->br && w->Wh && w->bh && w->gamma && w->beta,
               IMP_ERR_ARG, "imp_fused_pack_planned: null pointer");
   IMP_REQUIRE(d == FZ_D && bond_dim == FZ_K, IMP_ERR_DIM, "imp_fused_pack_planned: built for atom_dim %d, bond_dim %d (got %d, %d)",
               FZ_D, FZ_K, d, bond_dim);
   const int n = FZ_D * FZ_D * FZ_K;
-  fused_pack6_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed);
+  fused_pack6_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_bond_transform, *w, (unsigned char*)d_packed, zperm7);
   IMP_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int imp_fused_pack_planned(const float* d_bond_transform, const imp_gru_weights_t* w, int32_t d, int32_t bond_dim,
+                                      void* d_packed, void* stream) {
+  return fused_pack_planned_any(d_bond_transform, w, d, bond_dim, d_packed, stream, 0);
+}
+
+extern "C" int imp_fused_pack_planned7(const float* d_bond_transform, const imp_gru_weights_t* w, int32_t d, int32_t bond_dim,
+                                       void* d_packed, void* stream) {
+  return fused_pack_planned_any(d_bond_transform, w, d, bond_dim, d_packed, stream, 1);
 }
 
 namespace imp {

@@ -21,6 +21,7 @@ from .graph import PackedGraphBatch, pack_padded, pack_records
 from .train import TrainMixin
 
 TOWERS = ("cat", "an")
+DEFAULT_FUSED_GEN = "6"  # planned fused forward: kernel generation (MPNNModel.planned_gen)
 
 
 def _stream():
@@ -280,9 +281,20 @@ class MPNNModel(TrainMixin):
                     for ti, t in enumerate(TOWERS):
                         for i in range(S):
                             w = self._gru_struct(t, i)
-                            _lib.call("imp_fused_pack_planned", self._ptr(f"{t}_bmm_{i}.bond_transform"), C.byref(w), d, K,
+                            _lib.call("imp_fused_pack_planned7" if self.planned_gen() == 7 else "imp_fused_pack_planned",
+                                      self._ptr(f"{t}_bmm_{i}.bond_transform"), C.byref(w), d, K,
                                       fpk6.data_ptr() + fb6 * (ti * S + i), _stream())
+                    self._packed6_gen = self.planned_gen()
         self._tables_valid = True
+
+    def planned_gen(self):
+        """Kernel generation of the planned fused forward: 7 (csrc/fused_fwd7.cu) or 6 (csrc/fused_fwd6.cu); 5 through
+        ``extra_tc_flags = TC_GEN5``.  ``fused_gen`` on the model or IMP_FUSED_GEN in the environment select it."""
+        import os
+
+        if self.tc_flags() & _lib.TC_GEN5:
+            return 5
+        return int(getattr(self, "fused_gen", None) or os.environ.get("IMP_FUSED_GEN", DEFAULT_FUSED_GEN))
 
     def tc_flags(self):
         f = _lib.TC_FP16 if self.precision.startswith("fp16") else 0
@@ -355,7 +367,7 @@ class MPNNModel(TrainMixin):
         if batch.bond_vocab != s["bond_vocab_size"]:
             raise ValueError("batch was packed for a different bond vocabulary")
         st = _stream()
-        if not self._tables_valid:
+        if not self._tables_valid or getattr(self, "_packed6_gen", None) not in (None, self.planned_gen()):
             self.refresh_tables()
         if getattr(batch, "is_compact", False):
             if keep or unfused_messages or not self.use_fused(batch) or not self.compact_supported():
@@ -507,7 +519,7 @@ class MPNNModel(TrainMixin):
 
         if batch.dev is None:
             batch.to(self.device)
-        if not self._tables_valid:
+        if not self._tables_valid or getattr(self, "_packed6_gen", None) not in (None, self.planned_gen()):
             self.refresh_tables()
         st = _stream()
         if self.use_fused(batch) and not self.wide_supported():
@@ -554,7 +566,8 @@ class MPNNModel(TrainMixin):
             _lib.call("imp_mpnn_forward_fused_planned", plan.data_ptr(), P, batch.n_atoms, batch.n_cat_atoms, batch.bond_vocab,
                       self._ptr("atom_emb"), s["atom_vocab_size"], self._ptr("bond_emb"), d, s["bond_dim"], S,
                       self._ws["fused_packed" if self.tc_flags() & _lib.TC_GEN5 else "fused_packed6"].data_ptr(),
-                      C.c_float(self.LN_EPS), self.tc_flags(), pooled.data_ptr(), st)
+                      C.c_float(self.LN_EPS), self.tc_flags() | (_lib.TC_GEN7 if self.planned_gen() == 7 else 0),
+                      pooled.data_ptr(), st)
         elif g is None:
             if getattr(batch, "is_narrow", False):
                 raise _lib.ImpError("the narrow compact feed (16-bit entry words) is read by the planned forward only")
@@ -699,7 +712,7 @@ class MPNNModel(TrainMixin):
         total = sum(c.n_pairs for c in chunks)
         if out is None:
             out = torch.empty(total, dtype=torch.float32).pin_memory()
-        if not self._tables_valid:
+        if not self._tables_valid or getattr(self, "_packed6_gen", None) not in (None, self.planned_gen()):
             self.refresh_tables()
         st = getattr(self, "_stream_state", None)
         if st is None:

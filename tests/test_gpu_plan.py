@@ -102,9 +102,12 @@ def test_planned_forward_matches_the_self_contained_kernel_and_the_fp32_path(n_p
     batch.to("cuda")
     ref = build_model(124, 72, precision="fp32", seed=3)
     want32 = ref.forward_packed(batch).cpu().numpy()
-    for precision, pflags in (("fp16", 0), ("fp16_precise", 0), ("fp16", _lib.TC_GEN5)):  # generation 6 (default), 5
+    for precision, pflags, gen in (("fp16", 0, 6), ("fp16_precise", 0, 6), ("fp16", _lib.TC_GEN5, 5), ("fp16", 0, 7),
+                                   ("fp16_precise", 0, 7)):  # kernel generations 6, 5, 7
         planned = build_model(124, 72, precision=precision, seed=3, fused=True)
         planned.extra_tc_flags = pflags
+        planned.fused_gen = gen
+        assert planned.planned_gen() == gen
         gen3 = build_model(124, 72, precision=precision, seed=3, fused=True)
         gen3.use_plan = False
         assert planned.planned_supported(batch) and not gen3.planned_supported(batch)

@@ -195,6 +195,7 @@ int imp_gated_update_wide(const float* d_h, const float* d_agg, int32_t n_atoms,
 #define IMP_TC_GEN4 1024 /* imp_mpnn_forward_fused: the fourth-generation kernel (arrive-and-continue; measured slower) */
 #define IMP_TC_GEN5 2048 /* imp_mpnn_forward_fused_planned: the fifth-generation kernel (weights from imp_fused_pack; comparison) */
 #define IMP_TC_GEN7 4096 /* imp_mpnn_forward_fused_planned: the seventh-generation kernel (weights from imp_fused_pack_planned7) */
+#define IMP_TC_GEN8 8192 /* imp_mpnn_forward_fused_planned: the eighth-generation kernel (weights from imp_fused_pack_planned7) */
 int64_t imp_gru_pack_bytes(int32_t d);
 int imp_gru_pack_bf16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);
 int imp_gru_pack_f16(const imp_gru_weights_t* w, int32_t d, void* d_packed, void* stream);

@@ -63,6 +63,7 @@ TC_GEN3 = 512
 TC_GEN4 = 1024
 TC_GEN5 = 2048
 TC_GEN7 = 4096
+TC_GEN8 = 8192
 PACK_DOUBLE_EDGES = 1
 PACK_SHIFT_IDS = 2
 

@@ -353,6 +353,9 @@ int launch_fused_h6(const void* d_plan, int32_t n_atoms, int32_t n_cat_atoms, in
 int launch_fused_h7(const void* d_plan, int32_t n_atoms, int32_t n_cat_atoms, int32_t bond_vocab, const float* d_atom_emb,
                     int32_t atom_vocab, const float* d_bond_emb, int32_t steps, const void* d_packed, float eps, bool precise,
                     float* d_pooled, cudaStream_t st);  // fused_fwd7.cu
+int launch_fused_h8(const void* d_plan, int32_t n_atoms, int32_t n_cat_atoms, int32_t bond_vocab, const float* d_atom_emb,
+                    int32_t atom_vocab, const float* d_bond_emb, int32_t steps, const void* d_packed, float eps, bool precise,
+                    float* d_pooled, cudaStream_t st);  // fused_fwd8.cu
 }
 
 extern "C" int imp_mpnn_forward_fused_planned(const void* d_plan, int32_t n_pairs, int32_t n_atoms, int32_t n_cat_atoms,
@@ -367,13 +370,18 @@ extern "C" int imp_mpnn_forward_fused_planned(const void* d_plan, int32_t n_pair
   IMP_REQUIRE(steps >= 1 && steps <= FZ_MAX_STEPS, IMP_ERR_DIM, "imp_mpnn_forward_fused_planned: 1..%d steps (got %d)", FZ_MAX_STEPS, steps);
   IMP_REQUIRE(bond_vocab >= 1 && bond_vocab <= FZ_MAX_VB && atom_vocab >= 1 && atom_vocab <= 1024, IMP_ERR_DIM,
               "imp_mpnn_forward_fused_planned: bond vocabulary must be in 1..%d, atom vocabulary in 1..1024", FZ_MAX_VB);
-  IMP_REQUIRE((flags & IMP_TC_FP16) && !(flags & ~(IMP_TC_FP16 | IMP_TC_PRECISE_EPILOGUE | IMP_TC_GEN5 | IMP_TC_GEN7)) &&
-                  (flags & (IMP_TC_GEN5 | IMP_TC_GEN7)) != (IMP_TC_GEN5 | IMP_TC_GEN7),
+  const int gen_flags = flags & (IMP_TC_GEN5 | IMP_TC_GEN7 | IMP_TC_GEN8);
+  IMP_REQUIRE((flags & IMP_TC_FP16) && !(flags & ~(IMP_TC_FP16 | IMP_TC_PRECISE_EPILOGUE | IMP_TC_GEN5 | IMP_TC_GEN7 | IMP_TC_GEN8)) &&
+                  (gen_flags & (gen_flags - 1)) == 0,
               IMP_ERR_UNSUPPORTED,
-              "imp_mpnn_forward_fused_planned: IEEE-half operands only (flags IMP_TC_FP16 [| IMP_TC_PRECISE_EPILOGUE] [| IMP_TC_GEN5 or IMP_TC_GEN7])");
+              "imp_mpnn_forward_fused_planned: IEEE-half operands only (flags IMP_TC_FP16 [| IMP_TC_PRECISE_EPILOGUE] [| one of "
+              "IMP_TC_GEN5 / GEN7 / GEN8])");
   if (n_pairs == 0) return 0;
   IMP_REQUIRE(d_plan && d_atom_emb && d_bond_emb && d_packed && d_pooled, IMP_ERR_ARG, "imp_mpnn_forward_fused_planned: null pointer");
   IMP_REQUIRE(imp_device_is_sm100(), IMP_ERR_UNSUPPORTED, "imp_mpnn_forward_fused_planned: tcgen05 needs an sm_100 device");
+  if (flags & IMP_TC_GEN8)  // eighth generation (weights from imp_fused_pack_planned7)
+    return launch_fused_h8(d_plan, n_atoms, n_cat_atoms, bond_vocab, d_atom_emb, atom_vocab, d_bond_emb, steps, d_packed, eps,
+                           (flags & IMP_TC_PRECISE_EPILOGUE) != 0, d_pooled, (cudaStream_t)stream);
   if (flags & IMP_TC_GEN7)  // seventh generation (weights from imp_fused_pack_planned7)
     return launch_fused_h7(d_plan, n_atoms, n_cat_atoms, bond_vocab, d_atom_emb, atom_vocab, d_bond_emb, steps, d_packed, eps,
                            (flags & IMP_TC_PRECISE_EPILOGUE) != 0, d_pooled, (cudaStream_t)stream);

@@ -23,6 +23,7 @@
 #include "fused_common.cuh"
 #include "fused_pack6.cuh"
 #include "fused_plan.cuh"
+#include "fused_prof.cuh"
 
 namespace imp {
 
@@ -43,7 +44,7 @@ constexpr int F6_HS = 20;  // words per row of the shared-memory h copy (80 B: 1
 
 // Gate order inside the 64-wide block: n < 32 is the reset gate r, n >= 32 the update gate z.
 // zperm7: K order of a Wc half for the seventh generation (fused_fwd7.cu), whose Z rows are built four lanes wide and stored
-// with tcgen05.st.16x256b: K index 16 (m % 8) + 4 (m / 8) + (k % 4) instead of 4 m + (k % 4).
+// with tcgen05.st.16x256b.
 __global__ void fused_pack6_kernel(const float* __restrict__ W /* [K, d, d] */, imp_gru_weights_t w, unsigned char* __restrict__ out,
                                    int zperm7) {
   constexpr int D = FZ_D, KK = FZ_D * FZ_K;
@@ -51,7 +52,9 @@ __global__ void fused_pack6_kernel(const float* __restrict__ W /* [K, d, d] */, 
   if (i < D * KK) {  // Wc_hz[l][K(m, k)] = W[k][l][m]  (models/layers.py:108 re-associated, see fused_fwd.cu)
     const int l = i / KK, kk = i % KK, m = kk / FZ_K, k = kk % FZ_K;
     // K halves split the state columns m (16 each); inside a half K = 8 (m % 16) + k
-    const int hz = zperm7 ? k / 4 : m / 16, kq = zperm7 ? 16 * (m % 8) + 4 * (m / 8) + (k % 4) : (m % 16) * 8 + k;
+    // (seventh generation: state column m = 16 hz + 4 j + c  ->  K = 16 (2 c + k / 4) + 4 j + k % 4, the 16x256b fragment order)
+    const int hz = m / 16, ml = m % 16;
+    const int kq = zperm7 ? 16 * (2 * (ml % 4) + k / 4) + 4 * (ml / 4) + (k % 4) : ml * 8 + k;
     *reinterpret_cast<uint16_t*>(out + hz * (FusedPack6::WC_BYTES / 2) + tc::chunk_off(l, kq / 8, D) + (kq % 8) * 2) =
         tc::cvt16<tc::FMT_F16>(W[(k * D + l) * D + m]);
   }
@@ -107,31 +110,6 @@ struct Fused6Args {
 };
 
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
-// Optional phase timing (tools/fused_prof2.py builds with -DF6_PHASE_PROF): clock() deltas of thread 0 (class 0) and thread 96
-// (class 1) of every context, summed per phase in shared memory and flushed to a device symbol at the end of the kernel.
-#ifdef F6_PHASE_PROF
-__device__ unsigned long long f6_prof_total[2][16];
-#define F6_PROF_DECL                                               \
-  __shared__ unsigned int sprof[2][16];                            \
-  if (tid < 32) sprof[tid >> 4][tid & 15] = 0u;                    \
-  const int prof_cls = (t == 0) ? 0 : (t == 96) ? 1 : -1;          \
-  unsigned int prof_last = (unsigned int)clock()
-#define F6_PROF(i)                                                  \
-  do {                                                             \
-    if (prof_cls >= 0) {                                           \
-      const unsigned int now_ = (unsigned int)clock();             \
-      atomicAdd(&sprof[prof_cls][i], now_ - prof_last);            \
-      prof_last = now_;                                            \
-    }                                                              \
-  } while (0)
-#define F6_PROF_FLUSH \
-  if (tid < 32) atomicAdd(&f6_prof_total[tid >> 4][tid & 15], (unsigned long long)sprof[tid >> 4][tid & 15])
-#else
-#define F6_PROF_DECL
-#define F6_PROF(i)
-#define F6_PROF_FLUSH
-#endif
 
 struct F6True { static constexpr bool value = true; };
 struct F6False { static constexpr bool value = false; };

@@ -281,7 +281,7 @@ class MPNNModel(TrainMixin):
                     for ti, t in enumerate(TOWERS):
                         for i in range(S):
                             w = self._gru_struct(t, i)
-                            _lib.call("imp_fused_pack_planned7" if self.planned_gen() == 7 else "imp_fused_pack_planned",
+                            _lib.call("imp_fused_pack_planned7" if self.planned_gen() in (7, 8) else "imp_fused_pack_planned",
                                       self._ptr(f"{t}_bmm_{i}.bond_transform"), C.byref(w), d, K,
                                       fpk6.data_ptr() + fb6 * (ti * S + i), _stream())
                     self._packed6_gen = self.planned_gen()
@@ -566,7 +566,7 @@ class MPNNModel(TrainMixin):
             _lib.call("imp_mpnn_forward_fused_planned", plan.data_ptr(), P, batch.n_atoms, batch.n_cat_atoms, batch.bond_vocab,
                       self._ptr("atom_emb"), s["atom_vocab_size"], self._ptr("bond_emb"), d, s["bond_dim"], S,
                       self._ws["fused_packed" if self.tc_flags() & _lib.TC_GEN5 else "fused_packed6"].data_ptr(),
-                      C.c_float(self.LN_EPS), self.tc_flags() | (_lib.TC_GEN7 if self.planned_gen() == 7 else 0),
+                      C.c_float(self.LN_EPS), self.tc_flags() | {7: _lib.TC_GEN7, 8: _lib.TC_GEN8}.get(self.planned_gen(), 0),
                       pooled.data_ptr(), st)
         elif g is None:
             if getattr(batch, "is_narrow", False):

@@ -103,7 +103,7 @@ def test_planned_forward_matches_the_self_contained_kernel_and_the_fp32_path(n_p
     ref = build_model(124, 72, precision="fp32", seed=3)
     want32 = ref.forward_packed(batch).cpu().numpy()
     for precision, pflags, gen in (("fp16", 0, 6), ("fp16_precise", 0, 6), ("fp16", _lib.TC_GEN5, 5), ("fp16", 0, 7),
-                                   ("fp16_precise", 0, 7)):  # kernel generations 6, 5, 7
+                                   ("fp16_precise", 0, 7), ("fp16", 0, 8), ("fp16_precise", 0, 8)):  # kernel generations 6, 5, 7, 8
         planned = build_model(124, 72, precision=precision, seed=3, fused=True)
         planned.extra_tc_flags = pflags
         planned.fused_gen = gen

@@ -1,7 +1,7 @@
 """Phase timing of the planned fused forward (generation 6; debug aid, not part of the product).
 
     python tools/fused_prof2.py build      (here: compiles csrc/fused_fwd*.cu with -DF6_PHASE_PROF into tools/_prof/lib_prof6.so)
-    python tools/fused_prof2.py run [pairs] [steps]     (on the GPU box)
+    python tools/fused_prof2.py run [pairs] [steps] [gen 6|8]    (on the GPU box)
 """
 import ctypes as C
 import os
@@ -27,19 +27,20 @@ else:
 
     pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+    gen = int(sys.argv[4]) if len(sys.argv) > 4 else 6
     batch, _, _ = graph.synth_batch(pairs, seed=1003)
     batch.to("cuda")
     m = build_model(124, 72, precision="fp16", fused=True, num_steps=steps)
-    m.fused_gen = 6
+    m.fused_gen = gen
     for _ in range(2):
         m.forward_packed(batch)
     torch.cuda.synchronize()
     out = (C.c_ulonglong * 32)()
     lib = _lib.load()
-    lib.imp_debug_f6_prof(out)
+    getattr(lib, f"imp_debug_f{gen}_prof")(out)
     m.forward_packed(batch)
     torch.cuda.synchronize()
-    lib.imp_debug_f6_prof(out)
+    getattr(lib, f"imp_debug_f{gen}_prof")(out)
     prof = np.array(list(out), dtype=np.float64).reshape(2, 16)
     for cls, name in enumerate(["thread 0 (warp 0: issues the MMAs)", "thread 96 (warp 3)"]):
         tot = prof[cls].sum()

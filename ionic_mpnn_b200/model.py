@@ -552,10 +552,13 @@ class MPNNModel(TrainMixin):
             # pair).  Best-fit tiles are ~98 % full, so the buffer is sized for plan_slack x (atoms of the larger tower /
             # 128) tiles per tower instead; a batch that needs more (many rows closed by the entry limit) reports status 2
             # and check_status() switches this model to the safe bound.
-            slack = getattr(self, "plan_slack", 1.25)
+            slack = getattr(self, "plan_slack", "auto")
             if slack is not None:
                 tower = max(batch.n_cat_atoms, batch.n_atoms - batch.n_cat_atoms)
-                cap = int(slack * tower / 128) + (P + 255) // 256 + 16
+                if slack == "auto":  # well-filled tiles (1.25x), but never less than the row-limit bound: a tile closed by the
+                    # row limit has at least 129 - max_mol_atoms rows in use
+                    slack = max(1.25, 128.0 / max(129 - int(batch.max_mol_atoms), 1))
+                cap = max(int(slack * tower / 128), (P + 31) // 32) + (P + 255) // 256 + 16  # (at most 32 molecules per tile)
                 nb = min(nb, 256 + 2 * cap * 2048)
             plan = self._buf("fused_plan", nb, torch.uint8)
             if getattr(batch, "is_narrow", False):  # compact feed with 16-bit entry words

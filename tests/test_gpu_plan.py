@@ -138,14 +138,20 @@ def test_plan_capacity_overflow_is_reported_and_predict_retries():
     ref = build_model(124, 72, precision="fp32", seed=3)
     want = ref.predict(batch)
     fz = build_model(124, 72, precision="fp16", seed=3, fused=True)
+    fz.plan_slack = 1.25  # an explicit factor is taken as it is ("auto", the default, would see max_mol_atoms = 70 and allow 2.2x)
     fz.forward_packed(batch)
     torch.cuda.synchronize()
     with pytest.raises(_lib.PlanCapacityError):
         fz.check_status()
     assert fz.plan_slack is None
     fz2 = build_model(124, 72, precision="fp16", seed=3, fused=True)
+    fz2.plan_slack = 1.25
     got = fz2.predict(batch)  # retries by itself
     assert _rel(got, want) <= RTOL16
+    fz3 = build_model(124, 72, precision="fp16", seed=3, fused=True)  # default: sized from the largest molecule, no overflow
+    got3 = fz3.forward_packed(batch).cpu().numpy()
+    fz3.check_status()
+    assert np.array_equal(got3.reshape(-1), got.reshape(-1))
 
 
 def test_predict_stream_picks_the_narrow_feed_and_matches_predict():

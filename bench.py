@@ -372,7 +372,7 @@ def run_train(args):
         # ---- roofline of the dominant kernel.  Algorithmic work per launch: every training kernel at
         # atom_dim 32 is to the left of the ridge (<= 58 FLOP per byte against 211), so the bound is HBM.
         N, Eu, d, S = batch.n_atoms, batch.n_unique, 32, spec["num_steps"]
-        tb = {"gated_update_bwd": 5 * N * d * 4, "gated_update": 3 * N * d * 4, "edge_messages_grouped": Eu * (2 * d * 4 + 12),
+        tb = {"gated_update_bwd": 5 * N * d * 4, "gated_update": 3 * N * d * 4, "edge_messages_grouped": Eu * (2 * d * 4 + 12), "edge_messages_grouped_tc32": Eu * (2 * d * 4 + 12), "edge_messages_grouped_tc32_planned": Eu * (2 * d * 4 + 12),
               # stored-gate forms: the forward also writes z, r, tanh(.); the backward reads h, agg, z, r, tanh(.), g_out and
               # writes dh, dagg
               "gated_update_train": 6 * N * d * 4, "gated_update_tc32": 6 * N * d * 4, "gated_update_bwd_stored": 8 * N * d * 4, "gated_update_bwd_tc": 8 * N * d * 4,
@@ -380,7 +380,7 @@ def run_train(args):
               "bond_transform_bwd": Eu * (2 * d * 4 + 12), "embed_atoms": 4 * N + N * d * 4, "embed_bwd": 4 * N + N * d * 4,
               "bond_occurrence_norm2": S * Eu * 2 * d * 4 + 12 * Eu, "sumsq": N * d * 4,
               "global_sum_pool": N * d * 4 + 4 * N, "pool_bwd": N * d * 4 + 4 * N}
-        tf = {"gated_update_bwd": 36 * N * d * d, "gated_update": 12 * N * d * d, "edge_messages_grouped": 2 * Eu * d * d,
+        tf = {"gated_update_bwd": 36 * N * d * d, "gated_update": 12 * N * d * d, "edge_messages_grouped": 2 * Eu * d * d, "edge_messages_grouped_tc32": 2 * Eu * d * d, "edge_messages_grouped_tc32_planned": 2 * Eu * d * d,
               # without recomputation: 3 input-gradient + 3 weight-gradient contractions of 2 * 64 * 32 FLOP per atom (the
               # tcgen05 kernel executes each as three tf32 MMAs)
               "gated_update_train": 12 * N * d * d, "gated_update_tc32": 12 * N * d * d, "gated_update_bwd_stored": 24 * N * d * d, "gated_update_bwd_tc": 24 * N * d * d,

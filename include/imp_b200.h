@@ -145,6 +145,17 @@ int64_t imp_edge_messages_workspace_bytes(int32_t bond_vocab);
 int imp_edge_messages_grouped(const imp_graph_t* g, const float* d_x, int32_t d, const float* d_table_cat,
                               const float* d_table_an, int32_t transposed, float* d_msg /* [Eu, d] */, void* d_workspace,
                               void* stream);
+/* The same contract on the tensor cores (csrc/msg_tc32.cu): source rows and T[b] split into two tf32 terms, three tcgen05.mma
+ * kind::tf32 per K step (fp32-class accuracy, ~2^-21 relative per product); a gather / scatter stream instead of 1,024 FFMA per
+ * entry.  atom_dim 32. */
+int imp_edge_messages_grouped_tc32(const imp_graph_t* g, const float* d_x, int32_t d, const float* d_table_cat,
+                              const float* d_table_an, int32_t transposed, float* d_msg /* [Eu, d] */, void* d_workspace,
+                              void* stream);
+/* Planned, persistent form (the training step's): d_plan = the per-batch index plan of imp_edge_messages_tc16_plan
+ * (imp_edge_messages_tc16_plan_bytes bytes); source rows arrive by cp.async one chunk ahead of the MMAs. */
+int imp_edge_messages_grouped_tc32_planned(const imp_graph_t* g, const void* d_plan, const float* d_x, int32_t d,
+                                           const float* d_table_cat, const float* d_table_an, int32_t transposed,
+                                           float* d_msg /* [Eu, d] */, void* stream);
 
 /* K4  Reduce.call (models/layers.py:57-83): agg[v] = sum of msg rows row_ptr[v]..row_ptr[v+1] (imp_segment_sum_add: added
  * to the rows already in d_agg -- the message term of dL/dh in the backward pass). */

@@ -87,6 +87,8 @@ SIGNATURES = {
     "imp_edge_messages": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, vp, vp, vp, vp]),
     "imp_edge_messages_workspace_bytes": (C.c_int64, [C.c_int32]),
     "imp_edge_messages_grouped": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp]),
+    "imp_edge_messages_grouped_tc32": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp]),
+    "imp_edge_messages_grouped_tc32_planned": (C.c_int, [C.POINTER(Graph), vp, vp, C.c_int32, vp, vp, C.c_int32, vp, vp]),
     "imp_segment_sum_add": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, vp, vp]),
     "imp_segment_sum": (C.c_int, [C.POINTER(Graph), vp, C.c_int32, vp, vp]),
     "imp_gated_update": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(GruWeights), C.POINTER(GruWeights),

@@ -163,9 +163,18 @@ class TrainMixin:
                  if getattr(self, "store_gates", True) else None)
         _lib.call("imp_embed_atoms", self._ptr("atom_emb"), s["atom_vocab_size"], batch.dev["atom_id"].data_ptr(), N, d,
                   h[0].data_ptr(), sm)
+        tc_msg = d == 32 and Vb <= 256 and getattr(self, "tc_forward", True)
+        if tc_msg and tr.get("msg_plan") is None:  # per-batch index plan of the tensor-core message kernel (built once)
+            nbp = lib.imp_edge_messages_tc16_plan_bytes(batch.n_unique, Vb)
+            tr["msg_plan"] = torch.empty(max(int(nbp), 16), dtype=torch.uint8, device=self.device)
+            _lib.call("imp_edge_messages_tc16_plan", C.byref(g), tr["msg_plan"].data_ptr(), sm)
         for i in range(S):
-            _lib.call("imp_edge_messages_grouped", C.byref(g), h[i].data_ptr(), d, tab.data_ptr() + 4 * per * i,
-                      tab.data_ptr() + 4 * per * (S + i), 0, msg.data_ptr(), cws.data_ptr(), sm)
+            if tc_msg:
+                _lib.call("imp_edge_messages_grouped_tc32_planned", C.byref(g), tr["msg_plan"].data_ptr(), h[i].data_ptr(), d,
+                          tab.data_ptr() + 4 * per * i, tab.data_ptr() + 4 * per * (S + i), 0, msg.data_ptr(), sm)
+            else:
+                _lib.call("imp_edge_messages_grouped", C.byref(g), h[i].data_ptr(), d, tab.data_ptr() + 4 * per * i,
+                          tab.data_ptr() + 4 * per * (S + i), 0, msg.data_ptr(), cws.data_ptr(), sm)
             _lib.call("imp_segment_sum", C.byref(g), msg.data_ptr(), d, agg[i].data_ptr(), sm)
             wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
             # tensor-core forward (3xTF32, csrc/fwd_tc32.cu) where it is built (atom_dim 32); the fp32 SIMT kernels otherwise
@@ -227,8 +236,12 @@ class TrainMixin:
                           cur.data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc), C.byref(wa), C.c_float(self.LN_EPS), nxt.data_ptr(),
                           dagg.data_ptr(), gc, gn, ws_gru.data_ptr(), sm)
             # dh += sum over the (symmetric) live entries of mult * T[b]^T dagg[src]
-            _lib.call("imp_edge_messages_grouped", C.byref(g), dagg.data_ptr(), d, tab.data_ptr() + 4 * per * i,
-                      tab.data_ptr() + 4 * per * (S + i), 1, msg.data_ptr(), cws.data_ptr(), sm)
+            if d == 32 and tr.get("msg_plan") is not None and getattr(self, "tc_backward", True):
+                _lib.call("imp_edge_messages_grouped_tc32_planned", C.byref(g), tr["msg_plan"].data_ptr(), dagg.data_ptr(), d,
+                          tab.data_ptr() + 4 * per * i, tab.data_ptr() + 4 * per * (S + i), 1, msg.data_ptr(), sm)
+            else:
+                _lib.call("imp_edge_messages_grouped", C.byref(g), dagg.data_ptr(), d, tab.data_ptr() + 4 * per * i,
+                          tab.data_ptr() + 4 * per * (S + i), 1, msg.data_ptr(), cws.data_ptr(), sm)
             _lib.call("imp_segment_sum_add", C.byref(g), msg.data_ptr(), d, nxt.data_ptr(), sm)
             _lib.call("imp_bond_transform_bwd", C.byref(g), tr["entry_dst"].data_ptr(), tr["chunk_begin"].data_ptr(),
                       tr["chunk_end"].data_ptr(), tr["n_chunks"], tr["bucket_chunk_ptr"].data_ptr(), dagg.data_ptr(),

@@ -8,7 +8,7 @@
 //   [z | r] pre-activations = [h | agg] . [Wz | Wr]      (128 x 64, K = 64)   A = the row operand in TENSOR MEMORY, hi and lo terms
 //   candidate pre-activation = [r*h | agg] . Wh          (128 x 32, K = 64)   (r*h overwrites the h columns of the operand)
 // every product = hi.hi + hi.lo + lo.hi with x = hi + lo, hi = x with 13 low significand bits cleared (csrc/bwd_tc.cu).
-// One thread per atom row = TMEM lane; 224 TMEM columns and 50 KB of shared memory per CTA: two CTAs per SM.
+// Two threads per atom row (TMEM lane; 16 columns each); 224 TMEM columns and 52 KB of shared memory per CTA: two CTAs per SM.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -21,6 +21,7 @@ struct FtSmem {
   float W1[2][64 * 64];  // B[n][k] = (n < 32 ? Wz : Wr)[k][n & 31], K-major tf32, hi then lo
   float W2[2][32 * 64];  // B[n][k] = Wh[k][n]
   float bz[FT_D], br[FT_D], bh[FT_D], gamma[FT_D], beta[FT_D];
+  float xs[2][2][FT_TILE];  // LayerNorm partial sums of the two column halves of a row (sum; sum of squared deviations)
   uint64_t bar[2];
   uint32_t tmem_base;
 };
@@ -42,22 +43,30 @@ __device__ __forceinline__ void ft_mma_ts(uint32_t d, uint32_t a, uint64_t b, ui
 __device__ __forceinline__ float ft_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float ft_tanh(float x) { return tanhf(x); }
 
-__global__ void __launch_bounds__(FT_TILE, 2) gated_update_tc32_kernel(const float* __restrict__ h, const float* __restrict__ agg,
-                                                                       int n_atoms, int n_cat, int n_cta_cat, imp_gru_weights_t wc,
-                                                                       imp_gru_weights_t wa, float eps, float* __restrict__ h_out,
-                                                                       float* __restrict__ z_out, float* __restrict__ r_out,
-                                                                       float* __restrict__ ht_out) {
-  constexpr int D = FT_D;
+// 256 threads per 128-row tile: warps q and q + 4 share TMEM quadrant q; a thread owns one row and 16 of its 32 columns (column
+// half hf = warp / 4) through every phase, so a CTA has eight warps in flight instead of four and each warp's dependent chain
+// (split -> store -> MMA -> activations -> MMA -> LayerNorm) is half as long.  The two LayerNorm reductions of a row cross the
+// warp pair through shared memory (64-thread named barriers).  Two CTAs per SM (224 TMEM columns each): 16 warps per SM.
+constexpr int FT_THREADS = 2 * FT_TILE;
+
+__global__ void __launch_bounds__(FT_THREADS, 2) gated_update_tc32_kernel(const float* __restrict__ h, const float* __restrict__ agg,
+                                                                          int n_atoms, int n_cat, int n_cta_cat, imp_gru_weights_t wc,
+                                                                          imp_gru_weights_t wa, float eps, float* __restrict__ h_out,
+                                                                          float* __restrict__ z_out, float* __restrict__ r_out,
+                                                                          float* __restrict__ ht_out) {
+  constexpr int D = FT_D, DH = FT_D / 2;
   extern __shared__ __align__(1024) unsigned char ft_raw[];
   FtSmem& s = *reinterpret_cast<FtSmem*>(ft_raw);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hf = warp >> 2;  // TMEM quadrant; column half
+  const int trow = q * 32 + lane;          // row of the tile = TMEM lane
   const bool is_cat = (int)blockIdx.x < n_cta_cat;
   const imp_gru_weights_t& w = is_cat ? wc : wa;
   const int base = is_cat ? 0 : n_cat, a_end = is_cat ? n_cat : n_atoms;
   const int n_tiles = (a_end - base + FT_TILE - 1) / FT_TILE;
   const int cta = is_cat ? blockIdx.x : blockIdx.x - n_cta_cat, n_cta = is_cat ? n_cta_cat : gridDim.x - n_cta_cat;
 
-  for (int i = tid; i < 64 * 64; i += FT_TILE) {  // element (n, k) at chunk_off(n, k / 4, R) + (k % 4) * 4
+  for (int i = tid; i < 64 * 64; i += FT_THREADS) {  // element (n, k) at chunk_off(n, k / 4, R) + (k % 4) * 4
     const int n = i / 64, k = i % 64;
     float hi, lo;
     ft_split(__ldg((n < 32 ? w.Wz : w.Wr) + k * D + (n & 31)), hi, lo);
@@ -81,46 +90,53 @@ __global__ void __launch_bounds__(FT_TILE, 2) gated_update_tc32_kernel(const flo
   __syncthreads();
   tc::fence_after_thread_sync();
 
-  const uint32_t tm = s.tmem_base, lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t tm = s.tmem_base, lane_off = (uint32_t)(q * 32) << 16;
   const uint32_t tXhi = tm, tXlo = tm + 64, tD1 = tm + 128, tD2 = tm + 192;  // X = [h -> r*h | agg]
   const uint32_t id64 = tc::make_idesc(tc::FMT_TF32, FT_TILE, 64), id32 = tc::make_idesc(tc::FMT_TF32, FT_TILE, 32);
   const uint64_t dW1[2] = {tc::make_smem_desc(tc::smem_u32(s.W1[0]), 64 * 16, 128), tc::make_smem_desc(tc::smem_u32(s.W1[1]), 64 * 16, 128)};
   const uint64_t dW2[2] = {tc::make_smem_desc(tc::smem_u32(s.W2[0]), 32 * 16, 128), tc::make_smem_desc(tc::smem_u32(s.W2[1]), 32 * 16, 128)};
-  auto to_tmem = [&](uint32_t col, const float (&v)[32]) {
-    uint32_t hi[32], lo[32];
+  const int cb = DH * hf;  // first column of this thread
+  auto to_tmem = [&](uint32_t col, const float (&v)[16]) {
+    uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
+    for (int c = 0; c < 16; ++c) {
       float a, b;
       ft_split(v[c], a, b);
       hi[c] = __float_as_uint(a), lo[c] = __float_as_uint(b);
     }
-    tc::tmem_st32(tXhi + lane_off + col, hi);
-    tc::tmem_st32(tXlo + lane_off + col, lo);
+    tc::tmem_st16(tXhi + lane_off + col, hi);
+    tc::tmem_st16(tXlo + lane_off + col, lo);
   };
   uint32_t ph = 0;
-  // rows of a tile: loaded into registers one tile AHEAD (under the previous tile's MMAs and epilogues)
-  auto load_rows = [&](int tile, float (&hr)[32], float (&ar)[32]) {
+  // this thread's 16 columns of a row of h and of agg: loaded one tile AHEAD (under the previous tile's MMAs and epilogues)
+  auto load_rows = [&](int tile, float (&hr)[16], float (&ar)[16]) {
     const int a0 = base + tile * FT_TILE;
-    const int row = a0 + tid;
-    const bool ok = tile < n_tiles && tid < min(FT_TILE, a_end - a0);
+    const int row = a0 + trow;
+    const bool ok = tile < n_tiles && trow < min(FT_TILE, a_end - a0);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 x = ok ? __ldg(reinterpret_cast<const float4*>(h + (int64_t)row * D) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 y = ok ? __ldg(reinterpret_cast<const float4*>(agg + (int64_t)row * D) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < 4; ++c) {
+      const float4 x = ok ? __ldg(reinterpret_cast<const float4*>(h + (int64_t)row * D + cb) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 y = ok ? __ldg(reinterpret_cast<const float4*>(agg + (int64_t)row * D + cb) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       hr[4 * c] = x.x, hr[4 * c + 1] = x.y, hr[4 * c + 2] = x.z, hr[4 * c + 3] = x.w;
       ar[4 * c] = y.x, ar[4 * c + 1] = y.y, ar[4 * c + 2] = y.z, ar[4 * c + 3] = y.w;
     }
   };
-  float hn[32], an[32];
+  auto store16 = [&](float* dst, int row, const float (&v)[16]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      reinterpret_cast<float4*>(dst + (int64_t)row * D + cb)[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  };
+  const int pair_id = 1 + q;
+  float hn[16], an[16];
   load_rows(cta, hn, an);
   for (int tile = cta; tile < n_tiles; tile += n_cta) {
     const int a0 = base + tile * FT_TILE;
-    const int row = a0 + tid;
-    const bool ok = tid < min(FT_TILE, a_end - a0);
-    float hv[32];
+    const int row = a0 + trow;
+    const bool ok = trow < min(FT_TILE, a_end - a0);
+    float hv[16];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) hv[c] = hn[c];
-    to_tmem(0, hv), to_tmem(32, an);
+    for (int c = 0; c < 16; ++c) hv[c] = hn[c];
+    to_tmem((uint32_t)cb, hv), to_tmem((uint32_t)(32 + cb), an);
     tc::tmem_wait_st();
     tc::fence_before_thread_sync();
     __syncthreads();
@@ -141,23 +157,20 @@ __global__ void __launch_bounds__(FT_TILE, 2) gated_update_tc32_kernel(const flo
     load_rows(tile + n_cta, hn, an);  // next tile's rows: in flight during this tile's MMAs and epilogues
     tc::mbar_wait(&s.bar[0], ph);
     tc::fence_after_thread_sync();
-    float zv[32];
+    float zv[16];
     {
-      float v[32], rh[32];
-      tc::tmem_ld32(tD1 + 32 + lane_off, v);  // r
+      float v[16], rh[16];
+      tc::tmem_ld16(tD1 + 32 + cb + lane_off, v);  // r
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        v[c] = ft_sigmoid(v[c] + s.br[c]);
+      for (int c = 0; c < 16; ++c) {
+        v[c] = ft_sigmoid(v[c] + s.br[cb + c]);
         rh[c] = v[c] * hv[c];
       }
-      if (r_out && ok) {
+      if (r_out && ok) store16(r_out, row, v);
+      to_tmem((uint32_t)cb, rh);  // over the h columns: the first product has consumed them
+      tc::tmem_ld16(tD1 + cb + lane_off, v);  // z
 #pragma unroll
-        for (int c = 0; c < 8; ++c) reinterpret_cast<float4*>(r_out + (int64_t)row * D)[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-      }
-      to_tmem(0, rh);  // over the h columns: the first product has consumed them
-      tc::tmem_ld32(tD1 + lane_off, v);  // z
-#pragma unroll
-      for (int c = 0; c < 32; ++c) zv[c] = ft_sigmoid(v[c] + s.bz[c]);
+      for (int c = 0; c < 16; ++c) zv[c] = ft_sigmoid(v[c] + s.bz[cb + c]);
     }
     tc::tmem_wait_st();
     tc::fence_before_thread_sync();
@@ -176,49 +189,37 @@ __global__ void __launch_bounds__(FT_TILE, 2) gated_update_tc32_kernel(const flo
       }
       __syncwarp();
     }
-    if (z_out && ok) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) reinterpret_cast<float4*>(z_out + (int64_t)row * D)[c] = make_float4(zv[4 * c], zv[4 * c + 1], zv[4 * c + 2], zv[4 * c + 3]);
-    }
+    if (z_out && ok) store16(z_out, row, zv);
     tc::mbar_wait(&s.bar[1], ph);
     tc::fence_after_thread_sync();
     {
-      float n[32], mean = 0.f;
-      tc::tmem_ld32(tD2 + lane_off, n);
+      float n[16], part = 0.f;
+      tc::tmem_ld16(tD2 + cb + lane_off, n);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        n[c] = ft_tanh(n[c] + s.bh[c]);
-        if (ht_out == nullptr) {
-          n[c] = (1.0f - zv[c]) * hv[c] + zv[c] * n[c];
-          mean += n[c];
-        }
+      for (int c = 0; c < 16; ++c) n[c] = ft_tanh(n[c] + s.bh[cb + c]);
+      if (ht_out && ok) store16(ht_out, row, n);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        n[c] = (1.0f - zv[c]) * hv[c] + zv[c] * n[c];
+        part += n[c];
       }
-      if (ht_out) {
-        if (ok) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) reinterpret_cast<float4*>(ht_out + (int64_t)row * D)[c] = make_float4(n[4 * c], n[4 * c + 1], n[4 * c + 2], n[4 * c + 3]);
-        }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          n[c] = (1.0f - zv[c]) * hv[c] + zv[c] * n[c];
-          mean += n[c];
-        }
-      }
-      mean *= (1.0f / D);
+      s.xs[0][hf][trow] = part;  // the other 16 columns of the row live in the partner warp
+      tc::named_bar_sync(pair_id, 64);
+      const float mean = (s.xs[0][0][trow] + s.xs[0][1][trow]) * (1.0f / D);
       float var = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
+      for (int c = 0; c < 16; ++c) {
         n[c] -= mean;
         var = fmaf(n[c], n[c], var);
       }
-      const float inv = 1.0f / sqrtf(var * (1.0f / D) + eps);
+      s.xs[1][hf][trow] = var;
+      tc::named_bar_sync(pair_id, 64);
+      const float inv = 1.0f / sqrtf((s.xs[1][0][trow] + s.xs[1][1][trow]) * (1.0f / D) + eps);
       if (ok) {
+        float o[16];
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          reinterpret_cast<float4*>(h_out + (int64_t)row * D)[c] =
-              make_float4(n[4 * c] * inv * s.gamma[4 * c] + s.beta[4 * c] + hv[4 * c], n[4 * c + 1] * inv * s.gamma[4 * c + 1] + s.beta[4 * c + 1] + hv[4 * c + 1],
-                          n[4 * c + 2] * inv * s.gamma[4 * c + 2] + s.beta[4 * c + 2] + hv[4 * c + 2],
-                          n[4 * c + 3] * inv * s.gamma[4 * c + 3] + s.beta[4 * c + 3] + hv[4 * c + 3]);
+        for (int c = 0; c < 16; ++c) o[c] = n[c] * inv * s.gamma[cb + c] + s.beta[cb + c] + hv[c];
+        store16(h_out, row, o);
       }
     }
     ph ^= 1;
@@ -254,7 +255,7 @@ extern "C" int imp_gated_update_tc32(const float* d_h, const float* d_agg, int32
   n_cta_cat = n_cta_cat < 1 ? 1 : (n_cta_cat > grid - 1 ? grid - 1 : n_cta_cat);
   const size_t smem = sizeof(FtSmem) + 1024;
   IMP_CUDA(cudaFuncSetAttribute(gated_update_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gated_update_tc32_kernel<<<grid, FT_TILE, smem, (cudaStream_t)stream>>>(d_h, d_agg, n_atoms, n_cat_atoms, n_cta_cat, *w_cat, *w_an, eps,
+  gated_update_tc32_kernel<<<grid, FT_THREADS, smem, (cudaStream_t)stream>>>(d_h, d_agg, n_atoms, n_cat_atoms, n_cta_cat, *w_cat, *w_an, eps,
                                                                         d_h_out, d_z, d_r, d_ht);
   IMP_LAUNCH_CHECK();
   return 0;

@@ -11,7 +11,9 @@
 // terms x = hi + lo (hi = rna(x), lo = rna(x - hi)) and every product is three MMAs: hi.hi + hi.lo + lo.hi ("3xTF32":
 // ~2^-21 relative per product).
 //
-// Mapping: one persistent CTA of 128 threads per SM, thread t = atom row t of a 128-atom tile = TMEM lane t.  The row
+// Mapping: one persistent CTA of 256 threads per SM; TWO threads per atom row of a 128-atom tile (TMEM lane = row; warps q and
+// q + 4 share quadrant q and own 16 of the 32 columns each in every row-wise phase: eight warps in flight instead of four, half
+// as long a dependent chain per warp; the row sums of the LayerNorm backward cross the pair through shared memory).  The row
 // operands of the first three products (Gz, Gr, Gh; hi and lo) are written to TENSOR MEMORY by their owners
 // (tcgen05.st, A operand of the "TS" MMA form); the weights are staged once per CTA as K-major hi / lo operands.  The
 // weight-gradient product needs the ATOM index along K: each thread scatters its row into K-major [feature][atom]
@@ -38,7 +40,8 @@ struct BtSmem {
   float W2[2][64 * 64];
   unsigned char stage[4 * BT_OPBYTES + 2048];  // A_hi, A_lo, B_hi, B_lo of a half tile (+ slack: M = 128 reads past row 96)
   float gamma[BT_D];
-  float red[4][2 * BT_D];
+  float red[8][BT_D];            // per warp: dgamma (lanes 0-15) and dbeta (16-31) column sums of its 16 columns
+  float xs[4][2][BT_TILE];       // row sums exchanged between the two column halves of a row
   uint64_t bar[4];  // 0: B1 done, 1: B2 done, 2: weight-gradient MMAs of the staged half done
   uint32_t tmem_base;
 };
@@ -77,7 +80,26 @@ __device__ __forceinline__ float bt_column_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
-__global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
+// 16 columns over the warp's 32 rows: lane j and lane j + 16 receive the sum over the lanes of v[j & 15] (fixed order)
+__device__ __forceinline__ float bt_column_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+    const bool upper = lane & s;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = upper ? v[i] : v[i + s];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+      v[i] = (upper ? v[i + s] : v[i]) + recv;
+    }
+  }
+  return v[0];
+}
+
+constexpr int BT_THREADS = 2 * BT_TILE;  // two threads per atom row: warps q and q + 4 share TMEM quadrant q, 16 columns each
+
+__global__ void __launch_bounds__(BT_THREADS, 1) gated_update_bwd_tc_kernel(
     const float* __restrict__ h, const float* __restrict__ agg, const float* __restrict__ zs, const float* __restrict__ rs,
     const float* __restrict__ hts, const float* __restrict__ g_out, int n_atoms, int n_cat, int n_cta_cat, imp_gru_weights_t wc,
     imp_gru_weights_t wa, float eps, float* __restrict__ dh, float* __restrict__ dagg, float* __restrict__ partial) {
@@ -85,6 +107,9 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
   extern __shared__ __align__(1024) unsigned char bt_raw[];
   BtSmem& s = *reinterpret_cast<BtSmem*>(bt_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hf = warp >> 2;  // TMEM quadrant; column half of this thread
+  const int trow = q * 32 + lane;          // row of the tile = TMEM lane
+  const int cb = (BT_D / 2) * hf;          // first of the 16 columns this thread owns in every row-wise phase
   const bool is_cat = (int)blockIdx.x < n_cta_cat;
   const imp_gru_weights_t& w = is_cat ? wc : wa;
   const int base = is_cat ? 0 : n_cat, a_end = is_cat ? n_cat : n_atoms;
@@ -92,7 +117,7 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
   const int cta = is_cat ? blockIdx.x : blockIdx.x - n_cta_cat, n_cta = is_cat ? n_cta_cat : gridDim.x - n_cta_cat;
 
   // ---- weights -> K-major tf32 hi / lo operands (element (n, k) at chunk_off(n, k / 4, R) + (k % 4) * 4)
-  for (int i = tid; i < 64 * 32; i += BT_TILE) {
+  for (int i = tid; i < 64 * 32; i += BT_THREADS) {
     {  // W1[n][k] = Wh[n][k]   (dX[a][n] = sum_j Gh[a][j] Wh[n][j]; Wh is [2d in][d out] row-major)
       const int n = i / 32, k = i % 32;
       float hi, lo;
@@ -112,9 +137,9 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
   }
   if (tid < D) s.gamma[tid] = w.gamma[tid];
   // the constant row of ones of the transposed operand (row 96; its lo term is zero) and zeros elsewhere in the slack
-  for (int i = tid; i < (int)sizeof(s.stage) / 4; i += BT_TILE) reinterpret_cast<float*>(s.stage)[i] = 0.f;
+  for (int i = tid; i < (int)sizeof(s.stage) / 4; i += BT_THREADS) reinterpret_cast<float*>(s.stage)[i] = 0.f;
   __syncthreads();
-  for (int k = tid; k < BT_HALF; k += BT_TILE)
+  for (int k = tid; k < BT_HALF; k += BT_THREADS)
     *reinterpret_cast<float*>(s.stage + (k / 4) * BT_LBO + BT_AROWS * 16 + (k % 4) * 4) = 1.0f;
   if (warp == 0) tc::tmem_alloc<512>(&s.tmem_base);
   if (tid == 0) {
@@ -127,7 +152,7 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
   __syncthreads();
   tc::fence_after_thread_sync();
 
-  const uint32_t tm = s.tmem_base, lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t tm = s.tmem_base, lane_off = (uint32_t)(q * 32) << 16;
   // G: [Gz | Gr | Gh] hi, lo; D: [dRH | dagg_h] of B1; D2: [dh_zr | dagg_zr] of B2; DW: the weight-gradient accumulator
   const uint32_t tGhi = tm, tGlo = tm + 96, tD = tm + 192, tD2 = tm + 256, tDW = tm + 320;
   const uint32_t id64 = tc::make_idesc(tc::FMT_TF32, BT_TILE, 64);
@@ -141,99 +166,113 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
   const uint64_t dA[2] = {tc::make_smem_desc(tc::smem_u32(sAh), BT_LBO, 128), tc::make_smem_desc(tc::smem_u32(sAl), BT_LBO, 128)};
   const uint64_t dB[2] = {tc::make_smem_desc(tc::smem_u32(sBh), BT_LBO, 128), tc::make_smem_desc(tc::smem_u32(sBl), BT_LBO, 128)};
 
-  float agam = 0.f, abet = 0.f;  // lane j: column j of dgamma / dbeta over this warp's rows, all tiles
+  float agam = 0.f, abet = 0.f;  // lane j: column cb + (j & 15) of dgamma / dbeta over this warp's rows, all tiles
   uint32_t ph01 = 0, ph2 = 0;    // mbarrier parities (bars 0 and 1 flip once per tile, bar 2 twice)
   bool dw_started = false, dw_pending = false;
+  const int pair_id = 1 + q;     // named barrier of the two warps that share a row (64 threads)
 
-  // row t of the half tile -> byte offset of element (feature row f, atom k = t % 64) inside a staged operand
-  const int kk = tid & (BT_HALF - 1);
+  // row of the half tile -> byte offset of element (feature row f, atom k = trow % 64) inside a staged operand
+  const int kk = trow & (BT_HALF - 1);
   const uint32_t st_off = (uint32_t)((kk / 4) * BT_LBO + (kk % 4) * 4);
-  auto stage_vec = [&](unsigned char* hi_base, unsigned char* lo_base, int row0, const float (&v)[32]) {
+  auto stage_vec = [&](unsigned char* hi_base, unsigned char* lo_base, int row0, const float (&v)[16]) {
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
+    for (int c = 0; c < 16; ++c) {
       float hi, lo;
       bt_split(v[c], hi, lo);
       *reinterpret_cast<float*>(hi_base + st_off + (row0 + c) * 16) = hi;
       *reinterpret_cast<float*>(lo_base + st_off + (row0 + c) * 16) = lo;
     }
   };
-  auto stage_raw = [&](unsigned char* dst, int row0, const float (&v)[32]) {
+  auto stage_raw = [&](unsigned char* dst, int row0, const float (&v)[16]) {
 #pragma unroll
-    for (int c = 0; c < 32; ++c) *reinterpret_cast<float*>(dst + st_off + (row0 + c) * 16) = v[c];
+    for (int c = 0; c < 16; ++c) *reinterpret_cast<float*>(dst + st_off + (row0 + c) * 16) = v[c];
   };
-  auto to_tmem = [&](uint32_t col, const float (&v)[32]) {  // hi / lo halves of a 32-column block of the row operand
-    uint32_t hi[32], lo[32];
+  auto to_tmem = [&](uint32_t col, const float (&v)[16]) {  // hi / lo halves of a 16-column block of the row operand
+    uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
+    for (int c = 0; c < 16; ++c) {
       float a, b;
       bt_split(v[c], a, b);
       hi[c] = __float_as_uint(a), lo[c] = __float_as_uint(b);
     }
-    tc::tmem_st32(tGhi + lane_off + col, hi);
-    tc::tmem_st32(tGlo + lane_off + col, lo);
+    tc::tmem_st16(tGhi + lane_off + col, hi);
+    tc::tmem_st16(tGlo + lane_off + col, lo);
   };
-  auto load_row = [&](const float* p, int row, bool ok, float (&v)[32]) {
+  auto load_row = [&](const float* p, int row, bool ok, float (&v)[16]) {  // this thread's 16 columns
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 x = ok ? __ldg(reinterpret_cast<const float4*>(p + (int64_t)row * D) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < 4; ++c) {
+      const float4 x = ok ? __ldg(reinterpret_cast<const float4*>(p + (int64_t)row * D + cb) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       v[4 * c] = x.x, v[4 * c + 1] = x.y, v[4 * c + 2] = x.z, v[4 * c + 3] = x.w;
     }
+  };
+  auto store_row = [&](float* p, int row, const float (&v)[16]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      reinterpret_cast<float4*>(p + (int64_t)row * D + cb)[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  };
+  // sum of a per-thread partial over the two column halves of the row (the partner warp holds the other half)
+  auto row_sum = [&](int slot, float part) {
+    s.xs[slot][hf][trow] = part;
+    tc::named_bar_sync(pair_id, 64);
+    return s.xs[slot][0][trow] + s.xs[slot][1][trow];
   };
 
   for (int tile = cta; tile < n_tiles; tile += n_cta) {
     const int a0 = base + tile * BT_TILE;
-    const int row = a0 + tid;
-    const bool ok = tid < min(BT_TILE, a_end - a0);
-    {  // the next tile's six rows of this thread -> L2 (one CTA of four warps per SM cannot hide an HBM round trip otherwise)
+    const int row = a0 + trow;
+    const bool ok = trow < min(BT_TILE, a_end - a0);
+    {  // the next tile's six rows -> L2 (each thread of the pair takes three arrays)
       const int nrow = row + n_cta * BT_TILE;
       if (nrow < a_end) {
-        const float* ps[6] = {h, zs, hts, g_out, rs, agg};
+        const float* ps[3] = {hf ? g_out : h, hf ? rs : zs, hf ? agg : hts};
 #pragma unroll
-        for (int q = 0; q < 6; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps[q] + (int64_t)nrow * D));
+        for (int i = 0; i < 3; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps[i] + (int64_t)nrow * D));
       }
     }
-    float hv[32], go[32];
+    float hv[16], go[16];
     load_row(h, row, ok, hv), load_row(g_out, row, ok, go);
     {  // LayerNorm forward statistics and backward, gate gradients (models/layers.py:151-156 under autodiff)
-      float zv[32], tv[32], gz[32], gh[32], gx[32];
+      float zv[16], tv[16], gz[16], gh[16], gx[16];
       load_row(zs, row, ok, zv), load_row(hts, row, ok, tv);
-      float nrm[32], mean = 0.f;
+      float nrm[16], part = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
+      for (int c = 0; c < 16; ++c) {
         nrm[c] = fmaf(zv[c], tv[c] - hv[c], hv[c]);
-        mean += nrm[c];
+        part += nrm[c];
       }
-      mean *= (1.0f / D);
-      float var = 0.f;
+      const float mean = row_sum(0, part) * (1.0f / D);
+      part = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
+      for (int c = 0; c < 16; ++c) {
         nrm[c] -= mean;
-        var = fmaf(nrm[c], nrm[c], var);
+        part = fmaf(nrm[c], nrm[c], part);
       }
-      const float inv = 1.0f / sqrtf(var * (1.0f / D) + eps);
-      float m1 = 0.f, m2 = 0.f;
+      const float inv = 1.0f / sqrtf(row_sum(1, part) * (1.0f / D) + eps);
+      float p1 = 0.f, p2 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
+      for (int c = 0; c < 16; ++c) {
         nrm[c] *= inv;  // xhat
         gx[c] = go[c] * nrm[c];
-        const float dx = go[c] * s.gamma[c];
-        m1 += dx;
-        m2 = fmaf(dx, nrm[c], m2);
+        const float dx = go[c] * s.gamma[cb + c];
+        p1 += dx;
+        p2 = fmaf(dx, nrm[c], p2);
       }
-      m1 *= (1.0f / D), m2 *= (1.0f / D);
-      float gbeta[32];
+      s.xs[3][hf][trow] = p2;
+      const float m1 = row_sum(2, p1) * (1.0f / D);  // (the barrier inside also publishes slot 3)
+      const float m2 = (s.xs[3][0][trow] + s.xs[3][1][trow]) * (1.0f / D);
+      float gbeta[16];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
+      for (int c = 0; c < 16; ++c) {
         gbeta[c] = go[c];
-        const float dn = inv * (go[c] * s.gamma[c] - m1 - nrm[c] * m2);
+        const float dn = inv * (go[c] * s.gamma[cb + c] - m1 - nrm[c] * m2);
         const float z = zv[c], ht = tv[c], hj = hv[c];
         go[c] = fmaf(dn, 1.0f - z, go[c]);        // dh: residual path + the (1 - z) path
         gz[c] = dn * (ht - hj) * z * (1.0f - z);  // dL/dzpre
         gh[c] = dn * z * (1.0f - ht * ht);        // dL/dhpre
       }
-      agam += bt_column_sum(gx, lane);
-      abet += bt_column_sum(gbeta, lane);
-      to_tmem(0, gz), to_tmem(64, gh);
+      agam += bt_column_sum16(gx, lane);
+      abet += bt_column_sum16(gbeta, lane);
+      to_tmem((uint32_t)cb, gz), to_tmem((uint32_t)(64 + cb), gh);
     }
     tc::tmem_wait_st();
     tc::fence_before_thread_sync();
@@ -252,53 +291,53 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
       }
       __syncwarp();
     }
-    float rv[32];
+    float rv[16];
     load_row(rs, row, ok, rv);
     // while B1 runs: the staging buffers are free once the previous tile's second weight-gradient pass has been consumed;
-    // the first two warps scatter the operand rows that do not depend on B1 (h, agg)
+    // the warps of the first half tile scatter the operand rows that do not depend on B1 (h, agg)
     if (dw_pending) {
       tc::mbar_wait(&s.bar[2], ph2);
       ph2 ^= 1;
       dw_pending = false;
     }
-    if ((tid >> 6) == 0) {
-      float v[32];
-      stage_vec(sAh, sAl, 0, hv);
+    if ((q >> 1) == 0) {
+      float v[16];
+      stage_vec(sAh, sAl, cb, hv);
       load_row(agg, row, ok, v);
-      stage_vec(sAh, sAl, 32, v);
+      stage_vec(sAh, sAl, 32 + cb, v);
     }
     tc::mbar_wait(&s.bar[0], ph01);
     tc::fence_after_thread_sync();
-    float rh[32];
+    float rh[16];
     {
-      float drh[32], gr[32];
-      tc::tmem_ld32(tD + lane_off, drh);
+      float drh[16], gr[16];
+      tc::tmem_ld16(tD + lane_off + cb, drh);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
+      for (int c = 0; c < 16; ++c) {
         go[c] = fmaf(drh[c], rv[c], go[c]);
         gr[c] = drh[c] * hv[c] * rv[c] * (1.0f - rv[c]);  // dL/drpre
         rh[c] = rv[c] * hv[c];
       }
-      to_tmem(32, gr);
+      to_tmem((uint32_t)(32 + cb), gr);
     }
     tc::tmem_wait_st();
     tc::fence_before_thread_sync();
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-      if ((tid >> 6) == half) {  // the two warps that own these 64 atoms scatter their rows: [feature][atom], hi and lo
-        float v[32];
+      if ((q >> 1) == half) {  // the warps that own these 64 atoms scatter their rows: [feature][atom], hi and lo
+        float v[16];
         if (half == 1) {  // (the first half's h and agg rows were staged while B1 ran)
-          stage_vec(sAh, sAl, 0, hv);
+          stage_vec(sAh, sAl, cb, hv);
           load_row(agg, row, ok, v);
-          stage_vec(sAh, sAl, 32, v);
+          stage_vec(sAh, sAl, 32 + cb, v);
         }
-        stage_vec(sAh, sAl, 64, rh);
+        stage_vec(sAh, sAl, 64 + cb, rh);
 #pragma unroll
         for (int blk = 0; blk < 3; ++blk) {  // Gz, Gr, Gh: their hi / lo terms are in tensor memory already
-          tc::tmem_ld32(tGhi + lane_off + 32 * blk, v);
-          stage_raw(sBh, 32 * blk, v);
-          tc::tmem_ld32(tGlo + lane_off + 32 * blk, v);
-          stage_raw(sBl, 32 * blk, v);
+          tc::tmem_ld16(tGhi + lane_off + 32 * blk + cb, v);
+          stage_raw(sBh, 32 * blk + cb, v);
+          tc::tmem_ld16(tGlo + lane_off + 32 * blk + cb, v);
+          stage_raw(sBl, 32 * blk + cb, v);
         }
       }
       tc::fence_proxy_async_smem();
@@ -331,23 +370,21 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
       if (half == 0) {
         tc::mbar_wait(&s.bar[1], ph01);
         tc::fence_after_thread_sync();
-        float v[32], u[32];
-        tc::tmem_ld32(tD2 + lane_off, v);  // dh_zr
+        float v[16], u[16];
+        tc::tmem_ld16(tD2 + lane_off + cb, v);  // dh_zr
         if (ok) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            reinterpret_cast<float4*>(dh + (int64_t)row * D)[c] =
-                make_float4(go[4 * c] + v[4 * c], go[4 * c + 1] + v[4 * c + 1], go[4 * c + 2] + v[4 * c + 2], go[4 * c + 3] + v[4 * c + 3]);
+          for (int c = 0; c < 16; ++c) v[c] += go[c];
+          store_row(dh, row, v);
         }
-        tc::tmem_ld32(tD + 32 + lane_off, u);   // dagg through Wh
-        tc::tmem_ld32(tD2 + 32 + lane_off, v);  // dagg through Wz, Wr
+        tc::tmem_ld16(tD + 32 + lane_off + cb, u);   // dagg through Wh
+        tc::tmem_ld16(tD2 + 32 + lane_off + cb, v);  // dagg through Wz, Wr
         if (ok) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            reinterpret_cast<float4*>(dagg + (int64_t)row * D)[c] =
-                make_float4(u[4 * c] + v[4 * c], u[4 * c + 1] + v[4 * c + 1], u[4 * c + 2] + v[4 * c + 2], u[4 * c + 3] + v[4 * c + 3]);
+          for (int c = 0; c < 16; ++c) v[c] += u[c];
+          store_row(dagg, row, v);
         }
-        tc::mbar_wait(&s.bar[2], ph2);  // the first half has been consumed: the other two warps may overwrite the buffers
+        tc::mbar_wait(&s.bar[2], ph2);  // the first half has been consumed: the other warps may overwrite the buffers
         ph2 ^= 1;
       } else {
         dw_pending = true;
@@ -363,30 +400,33 @@ __global__ void __launch_bounds__(BT_TILE, 1) gated_update_bwd_tc_kernel(
   float* o = partial + (int64_t)blockIdx.x * (3 * 2 * D * D + 5 * D);
   constexpr int BLK = 2 * D * D + D;
   if (dw_started) {
-    float v[32];
+    float v[16];
 #pragma unroll
-    for (int blk = 0; blk < 3; ++blk) {  // columns [32 blk, 32 blk + 32): x^T Gz, x^T Gr, x^T Gh  (all lanes load: .sync.aligned)
-      tc::tmem_ld32(tDW + lane_off + 32 * blk, v);
-      if (tid == BT_AROWS) {  // the ones row: bias gradients
+    for (int blk = 0; blk < 3; ++blk) {  // columns [32 blk + cb, + 16): x^T Gz, x^T Gr, x^T Gh  (all lanes load: .sync.aligned)
+      tc::tmem_ld16(tDW + lane_off + 32 * blk + cb, v);
+      if (trow == BT_AROWS) {  // the ones row: bias gradients
 #pragma unroll
-        for (int j = 0; j < 32; ++j) o[blk * BLK + 2 * D * D + j] = v[j];
+        for (int j = 0; j < 16; ++j) o[blk * BLK + 2 * D * D + cb + j] = v[j];
       } else if (blk < 2) {
-        if (tid < 2 * D) {  // rows h (0..31) and agg (32..63): dWz / dWr rows k = tid
+        if (trow < 2 * D) {  // rows h (0..31) and agg (32..63): dWz / dWr rows k = trow
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[blk * BLK + tid * D + j] = v[j];
+          for (int j = 0; j < 16; ++j) o[blk * BLK + trow * D + cb + j] = v[j];
         }
-      } else if (tid >= D && tid < BT_AROWS) {  // dWh: rows k < d multiply r*h (feature rows 64..95), rows d + k multiply agg (32..63)
-        const int k = tid >= 2 * D ? tid - 2 * D : tid;
+      } else if (trow >= D && trow < BT_AROWS) {  // dWh: rows k < d multiply r*h (feature rows 64..95), rows d + k multiply agg (32..63)
+        const int k = trow >= 2 * D ? trow - 2 * D : trow;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) o[2 * BLK + k * D + j] = v[j];
+        for (int j = 0; j < 16; ++j) o[2 * BLK + k * D + cb + j] = v[j];
       }
     }
   } else {
-    for (int i = tid; i < 3 * BLK; i += BT_TILE) o[i] = 0.f;
+    for (int i = tid; i < 3 * BLK; i += BT_THREADS) o[i] = 0.f;
   }
-  s.red[warp][lane] = agam, s.red[warp][D + lane] = abet;
+  if (lane < 16) s.red[warp][lane] = agam, s.red[warp][16 + lane] = abet;
   __syncthreads();
-  if (tid < 2 * D) o[3 * BLK + tid] = (s.red[0][tid] + s.red[1][tid]) + (s.red[2][tid] + s.red[3][tid]);
+  if (tid < 2 * D) {  // tid < 32: dgamma column tid, else dbeta column tid - 32; the column's half lives in warps 4 (col / 16) + q
+    const int col = tid & (D - 1), w0 = 4 * (col >> 4), j = (col & 15) + (tid >= D ? 16 : 0);
+    o[3 * BLK + tid] = (s.red[w0][j] + s.red[w0 + 1][j]) + (s.red[w0 + 2][j] + s.red[w0 + 3][j]);
+  }
   tc::fence_before_thread_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<512>(tm);
@@ -423,7 +463,7 @@ extern "C" int imp_gated_update_bwd_tc(const float* d_h, const float* d_agg, con
   const size_t smem = sizeof(BtSmem) + 1024;
   IMP_CUDA(cudaFuncSetAttribute(gated_update_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaStream_t st = (cudaStream_t)stream;
-  gated_update_bwd_tc_kernel<<<grid, BT_TILE, smem, st>>>(d_h, d_agg, d_z, d_r, d_ht, d_gout, n_atoms, n_cat_atoms, n_cat, *w_cat, *w_an,
+  gated_update_bwd_tc_kernel<<<grid, BT_THREADS, smem, st>>>(d_h, d_agg, d_z, d_r, d_ht, d_gout, n_atoms, n_cat_atoms, n_cat, *w_cat, *w_an,
                                                          eps, d_dh, d_dagg, d_workspace);
   IMP_LAUNCH_CHECK();
   const int n = 3 * 2 * BT_D * BT_D + 5 * BT_D;

@@ -239,7 +239,9 @@ def stage_flops(batch, d, S):
             "wide_message": 2 * E * d * d, "wide_gated_update": 12 * N * d * d,
             "edge_messages_tc": 2 * batch.n_unique * d * d, "reduce_gated_update_tc": 12 * N * d * d,
             "edge_messages_tc16": 2 * batch.n_unique * d * d, "reduce_gated_update_tc16": 12 * N * d * d,
-            "edge_messages_tc16_planned": 2 * batch.n_unique * d * d}
+            "edge_messages_tc16_planned": 2 * batch.n_unique * d * d,
+            "gated_update": 12 * N * d * d, "gated_update_tc32": 12 * N * d * d,
+            "edge_messages_grouped": 2 * batch.n_unique * d * d, "edge_messages_grouped_tc32_planned": 2 * batch.n_unique * d * d}
 
 
 def stage_bytes(batch, d, S, s=4):
@@ -269,6 +271,8 @@ def stage_bytes(batch, d, S, s=4):
         "reduce_gated_update_tc16": Eu * d * 2 + 4 * N + 2 * N * d * 4 + N * d * 2,
         "embed_atoms16": 4 * N + N * d * 6,
         "gated_update": 3 * N * d * s,                    # h, agg in; h out
+        "gated_update_tc32": 3 * N * d * s,
+        "edge_messages_grouped": Eu * (2 * d * 4 + 12), "edge_messages_grouped_tc32_planned": Eu * (2 * d * 4 + 12),
         "gated_update_tc": 3 * N * d * s,
         "gated_update_wide": 3 * N * d * s,
         # wide tensor path (16-bit operand copies next to the fp32 state, csrc/wide_tc.cu)
@@ -461,6 +465,7 @@ def run_b200(args):
     model = MPNNModel(spec, device=f"cuda:{local}", seed=0, precision=args.precision,
                       fused=False if args.staged else "auto")
     model.extra_tc_flags = args.tc_flags
+    model.fp32_tensor = bool(getattr(args, "fp32_tensor", False))
     d, S = spec["atom_dim"], spec["num_steps"]
 
     t_pack0 = time.perf_counter()
@@ -673,7 +678,8 @@ def run_b200(args):
                            "edges_per_gpu": batch.n_edges, "unique_edges_per_gpu": batch.n_unique,
                            "bond_types": "zipf1.2" if args.skewed else "uniform", "precision": args.precision,
                            "path": "wide tcgen05 GEMM kernels" if model.wide_supported() else
-                           "fused whole-tower kernel" if model.use_fused(batch) else "staged per-layer kernels",
+                           "fused whole-tower kernel" if model.use_fused(batch) else
+                           "staged per-layer kernels" + (" (3xTF32 tensor-core GatedUpdate and messages)" if model.fp32_tensor else ""),
                            "l2_policy": "inputs larger than L2 (%.1f GB of indices%s per GPU)" % (
                                batch.nbytes() / 1e9, "" if model.use_fused(batch) else
                                " + %.1f GB of activations" % (3 * batch.n_atoms * d * 4 / 1e9)),
@@ -690,7 +696,7 @@ EXTRAS = (  # (key, workload, precision): the other BASELINE configs as sub-reco
     ("mp64k", "mp64k", "fp16"),        # configs[1]: melting-point forward, 64k pairs, staged tensor kernels
     ("train", "visc_train", "fp32"),   # configs[3]: training step (the only place a collective is timed)
     ("wide", "wide", "fp16"),          # configs[4]: atom_dim 256, 6 steps
-    ("fp32", "visc_sweep", "fp32"),    # the 1e-5 parity path on the headline workload
+    ("fp32", "visc_sweep", "fp32"),    # the 1e-5 parity path on the headline workload (exact fp32 SIMT kernels)
 )
 
 
@@ -707,8 +713,9 @@ def run_extras(args):
         a.workload, a.precision, a.pairs_per_gpu = workload, precision, None
         a.no_e2e = a.no_cpu_baseline = True
         a.staged, a.tc_flags, a.min_timed_s, a.steps, a.warmup = False, 0, 1.2, 3, 3
-        if key == "fp32":
+        if key in ("fp32", "fp32_tensor"):
             a.pairs_per_gpu = 524_288  # 8 M pairs/s: the full 2 M-pair batch would take 0.26 s per step
+        a.fp32_tensor = key == "fp32_tensor"
         try:
             line = run_train(a) if workload == "visc_train" else run_b200(a)
         except Exception as e:  # a sub-record must never take the headline down with it

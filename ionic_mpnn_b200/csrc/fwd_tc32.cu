@@ -26,9 +26,15 @@ struct FtSmem {
   uint32_t tmem_base;
 };
 
+// x = hi + lo with both terms ROUNDED to tf32 (cvt.rna): |x - hi - lo| <= 2^-22 |x|, unbiased.  (The truncation split of
+// csrc/bwd_tc.cu -- one LOP3, lo truncated by the MMA -- is biased towards zero and twice as coarse; gradients do not care, the
+// forward state does: it is what separates 2e-5 from 1e-5 on the ill-conditioned predictions of tests/test_gpu_parity.py.)
 __device__ __forceinline__ void ft_split(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-  lo = x - hi;
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+  lo = __uint_as_float(l);
 }
 __device__ __forceinline__ void ft_mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, bool acc) {
   asm volatile(

@@ -34,9 +34,21 @@ struct Smem {
   uint32_t tmem_slot;
 };
 
+// hi = x with its 13 low significand bits cleared -- what kind::tf32 reads of a raw fp32 operand --, lo = x - hi (exact in fp32)
+// ROUNDED to tf32 (the MMA would truncate it: biased, and twice the error)
 __device__ __forceinline__ void split(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-  lo = x - hi;
+  uint32_t l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+  lo = __uint_as_float(l);
+}
+// both terms rounded (operands that are staged explicitly: the bond matrices)
+__device__ __forceinline__ void split_rn(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+  lo = __uint_as_float(l);
 }
 
 template <bool TRANSPOSED>
@@ -75,7 +87,7 @@ __global__ void __launch_bounds__(CHUNK) grouped_msg_tf32x3_kernel(const int32_t
     if (!TRANSPOSED) {  // (n, k) = (l, m0 + j): one 16-byte chunk
       float h4[4], l4[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) split(vv[j], h4[j], l4[j]);
+      for (int j = 0; j < 4; ++j) split_rn(vv[j], h4[j], l4[j]);
       const int o = tc::chunk_off(l, m0 / 4, D) / 4;
       *reinterpret_cast<float4*>(&s.b[0][o]) = make_float4(h4[0], h4[1], h4[2], h4[3]);
       *reinterpret_cast<float4*>(&s.b[1][o]) = make_float4(l4[0], l4[1], l4[2], l4[3]);
@@ -83,7 +95,7 @@ __global__ void __launch_bounds__(CHUNK) grouped_msg_tf32x3_kernel(const int32_t
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float a, c;
-        split(vv[j], a, c);
+        split_rn(vv[j], a, c);
         const int o = (tc::chunk_off(m0 + j, l / 4, D) + (l % 4) * 4) / 4;
         s.b[0][o] = a, s.b[1][o] = c;
       }
@@ -274,7 +286,7 @@ __global__ void __launch_bounds__(CHUNK) grouped_msg_tf32x3_planned_kernel(const
       if (!TRANSPOSED) {
         float h4[4], l4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split(vv[j], h4[j], l4[j]);
+        for (int j = 0; j < 4; ++j) split_rn(vv[j], h4[j], l4[j]);
         const int o = tc::chunk_off(l, m0 / 4, D) / 4;
         *reinterpret_cast<float4*>(&s.b[0][o]) = make_float4(h4[0], h4[1], h4[2], h4[3]);
         *reinterpret_cast<float4*>(&s.b[1][o]) = make_float4(l4[0], l4[1], l4[2], l4[3]);
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(CHUNK) grouped_msg_tf32x3_planned_kernel(const
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float a, c;
-          split(vv[j], a, c);
+          split_rn(vv[j], a, c);
           const int o = (tc::chunk_off(m0 + j, l / 4, D) + (l % 4) * 4) / 4;
           s.b[0][o] = a, s.b[1][o] = c;
         }

@@ -445,11 +445,21 @@ class MPNNModel(TrainMixin):
                           mbase + self._msg_pack_bytes * (S + i), self.tc_flags(), msg.data_ptr(), cws.data_ptr(), st)
                 _lib.call("imp_segment_sum", C.byref(g), msg.data_ptr(), d, aggs[i].data_ptr(), st)
             elif d == 32 and "bucket_perm" in batch.dev and not getattr(self, "simt_messages", False):
-                # exact fp32, bucket-grouped: T[b] staged once per chunk of 128 entries, then the CSR segment sum
                 msg = self._buf("msg", batch.n_unique * d)
-                cws = self._buf("msg_chunks", 2 * s["bond_vocab_size"] + 1, torch.int32)
-                _lib.call("imp_edge_messages_grouped", C.byref(g), h[i].data_ptr(), d, self.table_ptr(0, i, False),
-                          self.table_ptr(1, i, False), 0, msg.data_ptr(), cws.data_ptr(), st)
+                if getattr(self, "fp32_tensor", False) and s["bond_vocab_size"] <= 256:
+                    # fp32-class on the tensor cores (3xTF32, csrc/msg_tc32.cu), from the per-batch index plan
+                    plan32 = getattr(batch, "_msg_plan32", None)
+                    if plan32 is None:
+                        nbp = _lib.load().imp_edge_messages_tc16_plan_bytes(batch.n_unique, s["bond_vocab_size"])
+                        plan32 = batch._msg_plan32 = torch.empty(max(int(nbp), 16), dtype=torch.uint8, device=self.device)
+                        _lib.call("imp_edge_messages_tc16_plan", C.byref(g), plan32.data_ptr(), st)
+                    _lib.call("imp_edge_messages_grouped_tc32_planned", C.byref(g), plan32.data_ptr(), h[i].data_ptr(), d,
+                              self.table_ptr(0, i, False), self.table_ptr(1, i, False), 0, msg.data_ptr(), st)
+                else:
+                    # exact fp32, bucket-grouped: T[b] staged once per chunk of 128 entries, then the CSR segment sum
+                    cws = self._buf("msg_chunks", 2 * s["bond_vocab_size"] + 1, torch.int32)
+                    _lib.call("imp_edge_messages_grouped", C.byref(g), h[i].data_ptr(), d, self.table_ptr(0, i, False),
+                              self.table_ptr(1, i, False), 0, msg.data_ptr(), cws.data_ptr(), st)
                 _lib.call("imp_segment_sum", C.byref(g), msg.data_ptr(), d, aggs[i].data_ptr(), st)
             else:
                 _lib.call("imp_message_agg", C.byref(g), h[i].data_ptr(), d, self.table_ptr(0, i, True),
@@ -461,8 +471,12 @@ class MPNNModel(TrainMixin):
                           C.byref(wa), C.c_float(self.LN_EPS), h[i + 1].data_ptr(), ws.data_ptr(), st)
             elif self.precision == "fp32":
                 wc, wa = self._gru_struct("cat", i), self._gru_struct("an", i)
-                _lib.call("imp_gated_update", h[i].data_ptr(), aggs[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc),
-                          C.byref(wa), C.c_float(self.LN_EPS), h[i + 1].data_ptr(), st)
+                if getattr(self, "fp32_tensor", False) and d == 32:  # 3xTF32 tensor-core GatedUpdate (csrc/fwd_tc32.cu)
+                    _lib.call("imp_gated_update_tc32", h[i].data_ptr(), aggs[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc),
+                              C.byref(wa), C.c_float(self.LN_EPS), h[i + 1].data_ptr(), None, None, None, st)
+                else:
+                    _lib.call("imp_gated_update", h[i].data_ptr(), aggs[i].data_ptr(), N, batch.n_cat_atoms, d, C.byref(wc),
+                              C.byref(wa), C.c_float(self.LN_EPS), h[i + 1].data_ptr(), st)
             else:
                 base = self._ws["gru_packed"].data_ptr()
                 _lib.call("imp_gated_update_tc", h[i].data_ptr(), aggs[i].data_ptr(), N, batch.n_cat_atoms, d,
@@ -640,6 +654,8 @@ class MPNNModel(TrainMixin):
         grouped = batch is None or "bucket_perm" in (batch.dev or {})
         if self.precision != "fp32" and self.spec["atom_dim"] == 32 and grouped:
             return 3 + 2 * S + 1      # embed, message plan (2), (grouped message GEMM, Reduce + GatedUpdate) per step, pool + head
+        if self.spec["atom_dim"] == 32 and grouped and getattr(self, "fp32_tensor", False):
+            return 1 + 3 * S + 1      # embed, (planned 3xTF32 messages, segment sum, 3xTF32 GatedUpdate) per step, pool + head
         if self.spec["atom_dim"] == 32 and grouped:
             return 1 + 4 * S + 1      # embed, (chunk scan, grouped messages, segment sum, GatedUpdate) per step, pool + head
         return 1 + 2 * S + 1          # embed, (CSR-order messages, GatedUpdate) per step, pool + head

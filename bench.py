@@ -228,6 +228,12 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def props_sm_count():
+    import torch
+
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
 def stage_flops(batch, d, S):
     """Algorithmic FLOP per launch: messages 2*E*d^2 with E = live entries counted with multiplicity,
     gated update 12*N*d^2, per step."""
@@ -662,6 +668,15 @@ def run_b200(args):
                 roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                             "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": sb.get(dom)}
+                if args.precision == "fp32" and dom in sf and not model.fp32_tensor:
+                    # the exact fp32 kernels are SIMT: at atom_dim 32 the GatedUpdate has 32 FLOP per byte, to the RIGHT of the
+                    # ridge of the fp32 FMA pipe (148 SMs x 128 lanes x 2 FLOP x clock / HBM peak = 11 FLOP per byte), so
+                    # the ceiling that binds it is that pipe, not HBM: reported beside the HBM figure
+                    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                    fpeak = props_sm_count() * 128 * 2 * mhz * 1e6 / 1e12
+                    roofline["fp32_pipe"] = {"achieved_TFLOPs": sf[dom] / (mean_ms[dom] * 1e-3) / 1e12, "peak_TFLOPs": fpeak,
+                                             "frac": sf[dom] / (mean_ms[dom] * 1e-3) / 1e12 / fpeak,
+                                             "peak_source": "SM count x 128 fp32 lanes x 2 x the SM clock sampled during the run"}
             roofline.update({"avg_launch_ms": mean_ms[dom], "share_of_step": tot_ms[dom] / sum(tot_ms.values()),
                              "per_kernel": pk})
         cpu = None

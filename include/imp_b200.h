@@ -152,7 +152,9 @@ int imp_edge_messages_grouped_tc32(const imp_graph_t* g, const float* d_x, int32
                               const float* d_table_an, int32_t transposed, float* d_msg /* [Eu, d] */, void* d_workspace,
                               void* stream);
 /* Planned, persistent form (the training step's): d_plan = the per-batch index plan of imp_edge_messages_tc16_plan
- * (imp_edge_messages_tc16_plan_bytes bytes); source rows arrive by cp.async one chunk ahead of the MMAs. */
+ * (imp_edge_messages_tc16_plan_bytes bytes); source rows arrive by cp.async one chunk ahead of the MMAs.
+ * transposed: bit 0 = T[b]^T (backward); bit 1 = operand terms rounded to tf32 instead of truncated (the fp32 inference route:
+ * 4 % slower, the lo terms unbiased). */
 int imp_edge_messages_grouped_tc32_planned(const imp_graph_t* g, const void* d_plan, const float* d_x, int32_t d,
                                            const float* d_table_cat, const float* d_table_an, int32_t transposed,
                                            float* d_msg /* [Eu, d] */, void* stream);
@@ -453,7 +455,8 @@ int imp_gated_update_train(const float* d_h, const float* d_agg, int32_t n_atoms
                            float* d_r, float* d_ht, void* stream);
 /* imp_gated_update / imp_gated_update_train on the tensor cores with fp32-class accuracy (csrc/fwd_tc32.cu): both Dense
  * products of GatedUpdate.call (models/layers.py:146-151) as tcgen05.mma kind::tf32 with every operand split into two tf32
- * terms (3 MMAs per product), fp32 epilogue (expf / tanhf / sqrtf).  d_z / d_r / d_ht: all three (training form) or all NULL. */
+ * terms (3 MMAs per product), fp32 epilogue (expf / tanhf / sqrtf).  d_z / d_r / d_ht: all three (training form: truncation
+ * splits) or all NULL (inference form: both terms rounded to tf32). */
 int imp_gated_update_tc32(const float* d_h, const float* d_agg, int32_t n_atoms, int32_t n_cat_atoms, int32_t d,
                           const imp_gru_weights_t* w_cat, const imp_gru_weights_t* w_an, float eps, float* d_h_out, float* d_z,
                           float* d_r, float* d_ht, void* stream);

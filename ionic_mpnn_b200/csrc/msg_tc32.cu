@@ -50,6 +50,21 @@ __device__ __forceinline__ void split_rn(float x, float& hi, float& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
   lo = __uint_as_float(l);
 }
+// planned kernel: RN selects the rounded forms above (fp32 inference route), else plain truncation splits (training: 4 % faster)
+template <bool RN>
+__device__ __forceinline__ void split_a(float x, float& hi, float& lo) {
+  if (RN) {
+    split(x, hi, lo);
+  } else {
+    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    lo = x - hi;
+  }
+}
+template <bool RN>
+__device__ __forceinline__ void split_b(float x, float& hi, float& lo) {
+  if (RN) split_rn(x, hi, lo);
+  else split_a<false>(x, hi, lo);
+}
 
 template <bool TRANSPOSED>
 __global__ void __launch_bounds__(CHUNK) grouped_msg_tf32x3_kernel(const int32_t* __restrict__ bucket_ptr, const int32_t* __restrict__ chunk_ptr,
@@ -204,7 +219,7 @@ struct PIdx {
   const float* tb;
 };
 
-template <bool TRANSPOSED>
+template <bool TRANSPOSED, bool RN>
 __global__ void __launch_bounds__(CHUNK) grouped_msg_tf32x3_planned_kernel(const int32_t* __restrict__ bucket_ptr, const int32_t* __restrict__ chunk_ptr,
                                                                            int n_buckets, int bond_vocab, const int32_t* __restrict__ bucket_perm,
                                                                            const int32_t* __restrict__ bsrc, const int32_t* __restrict__ bbm,
@@ -274,7 +289,7 @@ __global__ void __launch_bounds__(CHUNK) grouped_msg_tf32x3_planned_kernel(const
       const int o = q * A_LBO + (warp * 32 + 4 * it + g) * 16;
       const float4 v = *reinterpret_cast<const float4*>(s.raw[p] + o);
       float4 h4, l4;
-      split(v.x, h4.x, l4.x), split(v.y, h4.y, l4.y), split(v.z, h4.z, l4.z), split(v.w, h4.w, l4.w);
+      split_a<RN>(v.x, h4.x, l4.x), split_a<RN>(v.y, h4.y, l4.y), split_a<RN>(v.z, h4.z, l4.z), split_a<RN>(v.w, h4.w, l4.w);
       *reinterpret_cast<float4*>(s.lo + o) = l4;
     }
 #pragma unroll
@@ -286,7 +301,7 @@ __global__ void __launch_bounds__(CHUNK) grouped_msg_tf32x3_planned_kernel(const
       if (!TRANSPOSED) {
         float h4[4], l4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split_rn(vv[j], h4[j], l4[j]);
+        for (int j = 0; j < 4; ++j) split_b<RN>(vv[j], h4[j], l4[j]);
         const int o = tc::chunk_off(l, m0 / 4, D) / 4;
         *reinterpret_cast<float4*>(&s.b[0][o]) = make_float4(h4[0], h4[1], h4[2], h4[3]);
         *reinterpret_cast<float4*>(&s.b[1][o]) = make_float4(l4[0], l4[1], l4[2], l4[3]);
@@ -294,7 +309,7 @@ __global__ void __launch_bounds__(CHUNK) grouped_msg_tf32x3_planned_kernel(const
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float a, c;
-          split_rn(vv[j], a, c);
+          split_b<RN>(vv[j], a, c);
           const int o = (tc::chunk_off(m0 + j, l / 4, D) + (l % 4) * 4) / 4;
           s.b[0][o] = a, s.b[1][o] = c;
         }
@@ -402,17 +417,19 @@ extern "C" int imp_edge_messages_grouped_tc32_planned(const imp_graph_t* g, cons
   const unsigned grid_all = (unsigned)(ceil_div(g->n_unique, msg32::CHUNK) + nb);
   const unsigned grid = grid_all < (unsigned)(3 * sms) ? grid_all : (unsigned)(3 * sms);
   const size_t smem = sizeof(msg32::PSmem) + 128;
-  if (transposed) {
-    IMP_CUDA(cudaFuncSetAttribute(msg32::grouped_msg_tf32x3_planned_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    msg32::grouped_msg_tf32x3_planned_kernel<true><<<grid, msg32::CHUNK, smem, st>>>(g->bucket_ptr, plan, nb, g->bond_vocab, g->bucket_perm,
-                                                                                    plan + 1024, plan + 1024 + g->n_unique, d_x,
-                                                                                    d_table_cat, d_table_an, d_msg);
-  } else {
-    IMP_CUDA(cudaFuncSetAttribute(msg32::grouped_msg_tf32x3_planned_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    msg32::grouped_msg_tf32x3_planned_kernel<false><<<grid, msg32::CHUNK, smem, st>>>(g->bucket_ptr, plan, nb, g->bond_vocab, g->bucket_perm,
-                                                                                     plan + 1024, plan + 1024 + g->n_unique, d_x,
-                                                                                     d_table_cat, d_table_an, d_msg);
-  }
+#define IMP_MSG32_LAUNCH(TR, RN)                                                                                                            \
+  do {                                                                                                                                     \
+    IMP_CUDA(cudaFuncSetAttribute(msg32::grouped_msg_tf32x3_planned_kernel<TR, RN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    msg32::grouped_msg_tf32x3_planned_kernel<TR, RN><<<grid, msg32::CHUNK, smem, st>>>(g->bucket_ptr, plan, nb, g->bond_vocab, g->bucket_perm, \
+                                                                                       plan + 1024, plan + 1024 + g->n_unique, d_x,       \
+                                                                                       d_table_cat, d_table_an, d_msg);                  \
+  } while (0)
+  const bool tr = (transposed & 1) != 0, rn = (transposed & 2) != 0;  // bit 1: rounded operand splits (the fp32 inference route)
+  if (tr && rn) IMP_MSG32_LAUNCH(true, true);
+  else if (tr) IMP_MSG32_LAUNCH(true, false);
+  else if (rn) IMP_MSG32_LAUNCH(false, true);
+  else IMP_MSG32_LAUNCH(false, false);
+#undef IMP_MSG32_LAUNCH
   IMP_LAUNCH_CHECK();
   return 0;
 }

@@ -454,7 +454,7 @@ class MPNNModel(TrainMixin):
                         plan32 = batch._msg_plan32 = torch.empty(max(int(nbp), 16), dtype=torch.uint8, device=self.device)
                         _lib.call("imp_edge_messages_tc16_plan", C.byref(g), plan32.data_ptr(), st)
                     _lib.call("imp_edge_messages_grouped_tc32_planned", C.byref(g), plan32.data_ptr(), h[i].data_ptr(), d,
-                              self.table_ptr(0, i, False), self.table_ptr(1, i, False), 0, msg.data_ptr(), st)
+                              self.table_ptr(0, i, False), self.table_ptr(1, i, False), 2, msg.data_ptr(), st)  # 2: rounded splits
                 else:
                     # exact fp32, bucket-grouped: T[b] staged once per chunk of 128 entries, then the CSR segment sum
                     cws = self._buf("msg_chunks", 2 * s["bond_vocab_size"] + 1, torch.int32)

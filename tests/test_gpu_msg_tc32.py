@@ -24,7 +24,7 @@ def _run(batch, vb, seed):
     lib = _lib.load()
     plan = torch.empty(max(int(lib.imp_edge_messages_tc16_plan_bytes(batch.n_unique, vb)), 16), dtype=torch.uint8, device="cuda")
     _lib.call("imp_edge_messages_tc16_plan", C.byref(g), plan.data_ptr(), st)
-    for tr in (0, 1):
+    for tr in (0, 1, 2, 3):  # bit 0: transposed; bit 1: operand terms rounded to tf32 (else truncated: the training form)
         msg = torch.full((batch.n_unique, d), 7.0, device="cuda")
         _lib.call("imp_edge_messages_grouped_tc32_planned", C.byref(g), plan.data_ptr(), x.data_ptr(), d, tabs[0].data_ptr(),
                   tabs[1].data_ptr(), tr, msg.data_ptr(), st)
@@ -56,7 +56,9 @@ def test_tc32_messages_match_the_fp32_kernel(n_pairs, seed, lo, hi, vb):
         err = np.abs(a - b).max() / max(np.abs(a).max(), 1.0)
         print(tr, f"{err:.2e}")
         assert err <= 2e-6, (tr, err)  # fp32-class: summation order and the 3xTF32 split (~2^-21 per product)
-        assert np.array_equal(out[("planned", tr)], b), "the planned persistent kernel computes the same rows"
+        assert np.array_equal(out[("planned", tr | 2)], b), "the planned persistent kernel (rounded terms) computes the same rows"
+        err_t = np.abs(a - out[("planned", tr)]).max() / max(np.abs(a).max(), 1.0)
+        assert err_t <= 4e-6, (tr, err_t)  # truncated terms (training form): twice as coarse
 
 
 def test_tc32_messages_are_bit_reproducible():

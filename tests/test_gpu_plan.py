@@ -168,3 +168,22 @@ def test_predict_stream_picks_the_narrow_feed_and_matches_predict():
     assert np.array_equal(out.numpy(), want)
     per_pair = nbytes / sum(c.n_pairs for c in chunks)
     assert per_pair < 340, per_pair  # 16-bit atom words + 16-bit entry words + offsets + temperature
+
+
+def test_large_atom_vocabulary_reads_the_embedding_table_from_global_memory():
+    """The planned forward stages the atom-embedding table in shared memory when it fits (<= ~160 rows); a larger vocabulary
+    takes the global-memory read path of the same kernel."""
+    from ionic_mpnn_b200 import graph
+    from ionic_mpnn_b200.viscosity import build_model
+
+    cat = graph.synth_flat(400, 5, 10, 40, atom_types=599, bond_types=71)
+    an = graph.synth_flat(400, 6, 10, 40, atom_types=599, bond_types=71)
+    T = np.random.default_rng(3).uniform(273.15, 373.15, 400).astype(np.float32)
+    b = graph.pack_flat(cat, an, 72, temperature=T).to("cuda")
+    ref = build_model(600, 72, precision="fp32", seed=4)
+    fz = build_model(600, 72, precision="fp16", seed=4, fused=True)
+    assert fz.planned_supported(b)
+    want = ref.forward_packed(b).cpu().numpy()
+    got = fz.forward_packed(b).cpu().numpy()
+    fz.check_status()
+    assert _rel(got, want) <= RTOL16

@@ -22,6 +22,11 @@ struct FtSmem {
   float W2[2][32 * 64];  // B[n][k] = Wh[k][n]
   float bz[FT_D], br[FT_D], bh[FT_D], gamma[FT_D], beta[FT_D];
   float xs[2][2][FT_TILE];  // LayerNorm partial sums of the two column halves of a row (sum; sum of squared deviations)
+  // the next tile's h and agg rows, copied by cp.async with 8 lanes per 128-byte row (a thread loading its own row touches
+  // 32 L1 lines per instruction: that, not HBM, capped the one-thread-per-row form at 2.4 TB/s); 16-byte chunk c of row r at
+  // chunk c ^ (r & 7), so that the row owners read their chunks back without bank conflicts
+  float in[2][FT_TILE * FT_D];
+  float out[4][32 * FT_D];  // per TMEM quadrant: 32 rows on their way out (same swizzle), stored 8 lanes per 128-byte row
   uint64_t bar[2];
   uint32_t tmem_base;
 };
@@ -122,35 +127,60 @@ __global__ void __launch_bounds__(FT_THREADS, 2) gated_update_tc32_kernel(const 
     tc::tmem_st16(tXlo + lane_off + col, lo);
   };
   uint32_t ph = 0;
-  // this thread's 16 columns of a row of h and of agg: loaded one tile AHEAD (under the previous tile's MMAs and epilogues)
-  auto load_rows = [&](int tile, float (&hr)[16], float (&ar)[16]) {
+  // the tile's rows of h and agg -> shared memory, one tile AHEAD (under the previous tile's MMAs and epilogues)
+  auto issue_loads = [&](int tile) {
     const int a0 = base + tile * FT_TILE;
-    const int row = a0 + trow;
-    const bool ok = tile < n_tiles && trow < min(FT_TILE, a_end - a0);
+    const int rows = tile < n_tiles ? min(FT_TILE, a_end - a0) : 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = tid + FT_THREADS * k, r = i >> 3, c = i & 7;
+      const bool ok = r < rows;
+      const int64_t g = ok ? (int64_t)(a0 + r) * D + 4 * c : 0;
+      const uint32_t dst = (uint32_t)((r * 8 + (c ^ (r & 7))) * 16), n = ok ? 16u : 0u;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(s.in[0]) + dst), "l"(h + g), "r"(n) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(s.in[1]) + dst), "l"(agg + g), "r"(n) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto read_rows = [&](float (&hr)[16], float (&ar)[16]) {  // this thread's 16 columns of its row
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const float4 x = ok ? __ldg(reinterpret_cast<const float4*>(h + (int64_t)row * D + cb) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 y = ok ? __ldg(reinterpret_cast<const float4*>(agg + (int64_t)row * D + cb) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int o = (trow * 8 + ((4 * hf + c) ^ (trow & 7))) * 4;
+      const float4 x = *reinterpret_cast<const float4*>(&s.in[0][o]), y = *reinterpret_cast<const float4*>(&s.in[1][o]);
       hr[4 * c] = x.x, hr[4 * c + 1] = x.y, hr[4 * c + 2] = x.z, hr[4 * c + 3] = x.w;
       ar[4 * c] = y.x, ar[4 * c + 1] = y.y, ar[4 * c + 2] = y.z, ar[4 * c + 3] = y.w;
     }
   };
-  auto store16 = [&](float* dst, int row, const float (&v)[16]) {
+  const int pair_id = 1 + q;  // named barrier of the two warps that share a quadrant (64 threads)
+  const int t64 = hf * 32 + lane;
+  // 16 columns of this thread's row -> the quadrant's staging rows -> global memory as whole 128-byte rows (the partner warp
+  // holds the other 16 columns); rows_q = valid rows of this quadrant in the tile
+  auto store_rows = [&](float* dst, int a0, int rows_q, const float (&v)[16]) {
+    float* ob = s.out[q];
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-      reinterpret_cast<float4*>(dst + (int64_t)row * D + cb)[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      *reinterpret_cast<float4*>(&ob[(lane * 8 + ((4 * hf + c) ^ (lane & 7))) * 4]) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    tc::named_bar_sync(pair_id, 64);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = t64 + 64 * k, r = i >> 3, c = i & 7;
+      const float4 x = *reinterpret_cast<const float4*>(&ob[(r * 8 + (c ^ (r & 7))) * 4]);
+      if (r < rows_q) reinterpret_cast<float4*>(dst + (int64_t)(a0 + q * 32 + r) * D)[c] = x;
+    }
+    tc::named_bar_sync(pair_id, 64);  // the staging rows are free again
   };
-  const int pair_id = 1 + q;
-  float hn[16], an[16];
-  load_rows(cta, hn, an);
+  issue_loads(cta);
   for (int tile = cta; tile < n_tiles; tile += n_cta) {
     const int a0 = base + tile * FT_TILE;
-    const int row = a0 + trow;
-    const bool ok = trow < min(FT_TILE, a_end - a0);
+    const int rows_q = min(FT_TILE, a_end - a0) - q * 32;  // valid rows of this quadrant (may be <= 0)
     float hv[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) hv[c] = hn[c];
-    to_tmem((uint32_t)cb, hv), to_tmem((uint32_t)(32 + cb), an);
+    {
+      float an[16];
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();  // every thread's copies have landed
+      read_rows(hv, an);
+      to_tmem((uint32_t)cb, hv), to_tmem((uint32_t)(32 + cb), an);
+    }
     tc::tmem_wait_st();
     tc::fence_before_thread_sync();
     __syncthreads();
@@ -168,7 +198,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) gated_update_tc32_kernel(const 
       }
       __syncwarp();
     }
-    load_rows(tile + n_cta, hn, an);  // next tile's rows: in flight during this tile's MMAs and epilogues
+    issue_loads(tile + n_cta);  // next tile's rows (every thread has read this tile's: the barrier above)
     tc::mbar_wait(&s.bar[0], ph);
     tc::fence_after_thread_sync();
     float zv[16];
@@ -180,7 +210,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) gated_update_tc32_kernel(const 
         v[c] = ft_sigmoid(v[c] + s.br[cb + c]);
         rh[c] = v[c] * hv[c];
       }
-      if (r_out && ok) store16(r_out, row, v);
+      if (r_out) store_rows(r_out, a0, rows_q, v);
       to_tmem((uint32_t)cb, rh);  // over the h columns: the first product has consumed them
       tc::tmem_ld16(tD1 + cb + lane_off, v);  // z
 #pragma unroll
@@ -203,7 +233,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) gated_update_tc32_kernel(const 
       }
       __syncwarp();
     }
-    if (z_out && ok) store16(z_out, row, zv);
+    if (z_out) store_rows(z_out, a0, rows_q, zv);
     tc::mbar_wait(&s.bar[1], ph);
     tc::fence_after_thread_sync();
     {
@@ -211,7 +241,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) gated_update_tc32_kernel(const 
       tc::tmem_ld16(tD2 + cb + lane_off, n);
 #pragma unroll
       for (int c = 0; c < 16; ++c) n[c] = ft_tanh(n[c] + s.bh[cb + c]);
-      if (ht_out && ok) store16(ht_out, row, n);
+      if (ht_out) store_rows(ht_out, a0, rows_q, n);
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         n[c] = (1.0f - zv[c]) * hv[c] + zv[c] * n[c];
@@ -229,11 +259,11 @@ __global__ void __launch_bounds__(FT_THREADS, 2) gated_update_tc32_kernel(const 
       s.xs[1][hf][trow] = var;
       tc::named_bar_sync(pair_id, 64);
       const float inv = 1.0f / sqrtf((s.xs[1][0][trow] + s.xs[1][1][trow]) * (1.0f / D) + eps);
-      if (ok) {
+      {
         float o[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) o[c] = n[c] * inv * s.gamma[cb + c] + s.beta[cb + c] + hv[c];
-        store16(h_out, row, o);
+        store_rows(h_out, a0, rows_q, o);
       }
     }
     ph ^= 1;

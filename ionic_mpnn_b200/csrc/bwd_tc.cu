@@ -42,6 +42,11 @@ struct BtSmem {
   float gamma[BT_D];
   float red[8][BT_D];            // per warp: dgamma (lanes 0-15) and dbeta (16-31) column sums of its 16 columns
   float xs[4][2][BT_TILE];       // row sums exchanged between the two column halves of a row
+  // the next tile's h, g_out, z and tanh-candidate rows, copied by cp.async with 8 lanes per 128-byte row (a thread that loads
+  // its own row touches 32 L1 lines per instruction: with eight arrays per tile that, not HBM, was half of a tile's time);
+  // 16-byte chunk c of row r at chunk c ^ (r & 7): the row owners read their chunks back without bank conflicts.  in[0] doubles
+  // as the staging rows of the two outputs (dh, dagg), which leave as whole rows too.
+  float in[4][BT_TILE * BT_D];
   uint64_t bar[4];  // 0: B1 done, 1: B2 done, 2: weight-gradient MMAs of the staged half done
   uint32_t tmem_base;
 };
@@ -205,11 +210,6 @@ __global__ void __launch_bounds__(BT_THREADS, 1) gated_update_bwd_tc_kernel(
       v[4 * c] = x.x, v[4 * c + 1] = x.y, v[4 * c + 2] = x.z, v[4 * c + 3] = x.w;
     }
   };
-  auto store_row = [&](float* p, int row, const float (&v)[16]) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      reinterpret_cast<float4*>(p + (int64_t)row * D + cb)[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-  };
   // sum of a per-thread partial over the two column halves of the row (the partner warp holds the other half)
   auto row_sum = [&](int slot, float part) {
     s.xs[slot][hf][trow] = part;
@@ -217,23 +217,65 @@ __global__ void __launch_bounds__(BT_THREADS, 1) gated_update_bwd_tc_kernel(
     return s.xs[slot][0][trow] + s.xs[slot][1][trow];
   };
 
+  // arrays [first, last) of {h, g_out, z, tanh candidate} of a tile -> shared memory
+  auto issue_in = [&](int tile, int first, int last) {
+    const int a0 = base + tile * BT_TILE;
+    const int rows = tile < n_tiles ? min(BT_TILE, a_end - a0) : 0;
+    const float* src[4] = {h, g_out, zs, hts};
+#pragma unroll
+    for (int arr = 0; arr < 4; ++arr) {
+      if (arr < first || arr >= last) continue;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = tid + BT_THREADS * k, r = i >> 3, c = i & 7;
+        const bool okr = r < rows;
+        const int64_t g = okr ? (int64_t)(a0 + r) * D + 4 * c : 0;
+        const uint32_t dst = tc::smem_u32(s.in[arr]) + (uint32_t)((r * 8 + (c ^ (r & 7))) * 16), n = okr ? 16u : 0u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src[arr] + g), "r"(n) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto read_in = [&](int arr, float (&v)[16]) {  // this thread's 16 columns of its row
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 x = *reinterpret_cast<const float4*>(&s.in[arr][(trow * 8 + ((4 * hf + c) ^ (trow & 7))) * 4]);
+      v[4 * c] = x.x, v[4 * c + 1] = x.y, v[4 * c + 2] = x.z, v[4 * c + 3] = x.w;
+    }
+  };
+  const int t64 = hf * 32 + lane;
+  // 16 columns of this thread's row -> the quadrant's staging rows (inside in[0]) -> global memory as whole 128-byte rows
+  auto store_rows = [&](float* dst, int a0, int rows_q, const float (&v)[16]) {
+    float* ob = s.in[0] + q * 32 * D;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<float4*>(&ob[(lane * 8 + ((4 * hf + c) ^ (lane & 7))) * 4]) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    tc::named_bar_sync(pair_id, 64);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = t64 + 64 * k, r = i >> 3, c = i & 7;
+      const float4 x = *reinterpret_cast<const float4*>(&ob[(r * 8 + (c ^ (r & 7))) * 4]);
+      if (r < rows_q) reinterpret_cast<float4*>(dst + (int64_t)(a0 + q * 32 + r) * D)[c] = x;
+    }
+    tc::named_bar_sync(pair_id, 64);  // the staging rows are free again
+  };
+  issue_in(cta, 0, 4);
   for (int tile = cta; tile < n_tiles; tile += n_cta) {
     const int a0 = base + tile * BT_TILE;
     const int row = a0 + trow;
     const bool ok = trow < min(BT_TILE, a_end - a0);
-    {  // the next tile's six rows -> L2 (each thread of the pair takes three arrays)
+    const int rows_q = min(BT_TILE, a_end - a0) - q * 32;  // valid rows of this quadrant (may be <= 0)
+    {  // the next tile's r and agg rows (read directly) -> L2
       const int nrow = row + n_cta * BT_TILE;
-      if (nrow < a_end) {
-        const float* ps[3] = {hf ? g_out : h, hf ? rs : zs, hf ? agg : hts};
-#pragma unroll
-        for (int i = 0; i < 3; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps[i] + (int64_t)nrow * D));
-      }
+      if (nrow < a_end) asm volatile("prefetch.global.L2 [%0];" ::"l"((hf ? agg : rs) + (int64_t)nrow * D));
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // every thread's copies of this tile's h, g_out, z, tanh-candidate rows have landed
     float hv[16], go[16];
-    load_row(h, row, ok, hv), load_row(g_out, row, ok, go);
+    read_in(0, hv), read_in(1, go);
     {  // LayerNorm forward statistics and backward, gate gradients (models/layers.py:151-156 under autodiff)
       float zv[16], tv[16], gz[16], gh[16], gx[16];
-      load_row(zs, row, ok, zv), load_row(hts, row, ok, tv);
+      read_in(2, zv), read_in(3, tv);
       float nrm[16], part = 0.f;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
@@ -291,6 +333,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) gated_update_bwd_tc_kernel(
       }
       __syncwarp();
     }
+    issue_in(tile + n_cta, 1, 4);  // next tile's g_out, z, tanh candidate (every thread has read this tile's: the barrier above)
     float rv[16];
     load_row(rs, row, ok, rv);
     // while B1 runs: the staging buffers are free once the previous tile's second weight-gradient pass has been consumed;
@@ -342,6 +385,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) gated_update_bwd_tc_kernel(
       }
       tc::fence_proxy_async_smem();
       __syncthreads();
+      if (half == 1) issue_in(tile + n_cta, 0, 1);  // next tile's h: its buffer staged this tile's outputs until the barrier above
       if (warp == 0) {
         tc::fence_after_thread_sync();
         if (tc::elect_one()) {
@@ -372,18 +416,14 @@ __global__ void __launch_bounds__(BT_THREADS, 1) gated_update_bwd_tc_kernel(
         tc::fence_after_thread_sync();
         float v[16], u[16];
         tc::tmem_ld16(tD2 + lane_off + cb, v);  // dh_zr
-        if (ok) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) v[c] += go[c];
-          store_row(dh, row, v);
-        }
+        for (int c = 0; c < 16; ++c) v[c] += go[c];
+        store_rows(dh, a0, rows_q, v);
         tc::tmem_ld16(tD + 32 + lane_off + cb, u);   // dagg through Wh
         tc::tmem_ld16(tD2 + 32 + lane_off + cb, v);  // dagg through Wz, Wr
-        if (ok) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) v[c] += u[c];
-          store_row(dagg, row, v);
-        }
+        for (int c = 0; c < 16; ++c) v[c] += u[c];
+        store_rows(dagg, a0, rows_q, v);
         tc::mbar_wait(&s.bar[2], ph2);  // the first half has been consumed: the other warps may overwrite the buffers
         ph2 ^= 1;
       } else {

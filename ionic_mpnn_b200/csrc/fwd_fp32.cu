@@ -638,13 +638,34 @@ __global__ void __launch_bounds__(R32_THREADS) readout32_kernel(K6Args a) {
   __syncthreads();
   float* xrow = &s.x[tid * R32_XS];
   float acc[32], mixed[32];
-  for (int pair = blockIdx.x * R32_THREADS + tid; pair < a.n_pairs; pair += gridDim.x * R32_THREADS) {
+  // a warp stays on 32 consecutive pairs and loops while ANY of them exists (its loads are cooperative); lanes past the end
+  // compute on zero rows and store nothing
+  for (int pair0w = blockIdx.x * R32_THREADS + (tid & ~31); pair0w < a.n_pairs; pair0w += gridDim.x * R32_THREADS) {
+    const int pair = pair0w + (tid & 31);
+    const bool live = pair < a.n_pairs;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
-      const float4* src = reinterpret_cast<const float4*>(a.pooled + (int64_t)(t * a.n_pairs + pair) * d);
-      for (int c = 0; c < d / 4; ++c) {
-        const float4 v = __ldg(src + c);
-        xrow[4 * c] = v.x, xrow[4 * c + 1] = v.y, xrow[4 * c + 2] = v.z, xrow[4 * c + 3] = v.w;
+      if (d == 32) {
+        // the warp's 32 pooled rows are consecutive: 8 lanes per 128-byte row (4 lines per load instruction instead of the 32 that
+        // a thread reading its own row touches), into the owners' shared-memory rows
+        const int lane = tid & 31, wbase = tid & ~31, g = lane >> 3, qc = lane & 7;
+        const int pair0 = pair0w;
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = 4 * it + g;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pair0 + rr < a.n_pairs) v = __ldg(reinterpret_cast<const float4*>(a.pooled + (int64_t)(t * a.n_pairs + pair0 + rr) * 32) + qc);
+          float* xr = &s.x[(wbase + rr) * R32_XS + 4 * qc];
+          xr[0] = v.x, xr[1] = v.y, xr[2] = v.z, xr[3] = v.w;
+        }
+        __syncwarp();
+      } else {
+        const float4* src = reinterpret_cast<const float4*>(a.pooled + (int64_t)(t * a.n_pairs + (live ? pair : 0)) * d);
+        for (int c = 0; c < d / 4; ++c) {
+          const float4 v = __ldg(src + c);
+          xrow[4 * c] = v.x, xrow[4 * c + 1] = v.y, xrow[4 * c + 2] = v.z, xrow[4 * c + 3] = v.w;
+        }
       }
       r32_layer(s.W[2 * t], s.b[2 * t], xrow, d, acc);        // Dense(fp_size, relu)
 #pragma unroll
@@ -662,12 +683,12 @@ __global__ void __launch_bounds__(R32_THREADS) readout32_kernel(K6Args a) {
     if (fp2 == 0) {  // A + B / (T / 100 + C + 1e-6), B and C clipped softplus (models/layers.py:10-42)
       const float B = fminf(fmaxf(softplusf_precise(acc[1]), 0.0f), 20.0f);
       const float Cc = fminf(fmaxf(softplusf_precise(acc[2]), 0.1f), 50.0f);
-      a.out[pair] = acc[0] + B / (__ldg(a.T + pair) / 100.0f + Cc + 1e-6f);
+      if (live) a.out[pair] = acc[0] + B / (__ldg(a.T + pair) / 100.0f + Cc + 1e-6f);
     } else {
       float tot = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) tot = __fadd_rn(tot, __fmul_rn(fmaxf(acc[j], 0.f), s.w2[j]));  // fixed order, no contraction
-      a.out[pair] = tot + a.b2[0];
+      if (live) a.out[pair] = tot + a.b2[0];
     }
   }
 }

@@ -263,6 +263,7 @@ def stage_bytes(batch, d, S, s=4):
         "fused_plan": 8 * N + 8 * Eu + 8 * P + (N // 125 + 1) * 2048,
         "readout_visc": 2 * P * d * 4 + 8 * P,
         "readout_mp": 2 * P * d * 4 + 4 * P,
+        "global_sum_pool": N * d * 4 + 4 * N + 2 * P * d * 4,
         "embed_atoms": 4 * N + N * d * s,
         "message_agg": 2 * N * d * s + 8 * Eu + 4 * N,   # h in, agg out, (src, bond|mult) per unique entry, row_ptr
         # grouped tcgen05 message GEMM (csrc/msg_tc.cu): one gathered source row in, one message row out per unique

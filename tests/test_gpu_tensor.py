@@ -180,12 +180,14 @@ def test_reduce_folded_into_gated_update_is_bit_identical():
     torch.cuda.synchronize()
     assert torch.isfinite(out_b).all()
     assert torch.equal(out_a, out_b)
-    # and the model's routes agree: keep=True (separate kernels, fp32 messages) == folded with fp32 messages, bit for bit;
+    # and the model's routes agree: keep=True (separate kernels, fp32 messages) == folded with fp32 messages -- the atom states bit
+    # for bit (above); the predictions to fp32 rounding, because keep=True reads out with the double-accumulating
+    # imp_pool_head_* (it returns the intermediates) and the plain forward with imp_global_sum_pool + the fp32 imp_readout_*;
     # the default folded route (16-bit message rows and gathers) within the tensor path's tolerance
     a, _ = m.forward_packed(batch, keep=True)
     m.fp32_messages = True
     b = m.forward_packed(batch)
-    assert torch.equal(a, b)
+    assert torch.allclose(a, b, rtol=2e-6, atol=2e-6 * float(a.abs().max()))
     m.fp32_messages = False
     c = m.forward_packed(batch)
     err = float(((c - a).abs() / a.abs().clamp(min=1.0)).max())

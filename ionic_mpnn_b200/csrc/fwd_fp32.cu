@@ -473,8 +473,17 @@ __global__ void global_sum_pool_kernel(const int* __restrict__ mol_ptr, const in
   if (m >= n_mols) return;
   const int v0 = mol_ptr[m], v1 = mol_ptr[m + 1];
   for (int j = lane; j < d; j += 32) {
+    // four rows in flight (the loop is a chain of dependent 128-byte row loads otherwise); rows are added in atom order
     float sacc = 0.f;
-    for (int v = v0; v < v1; ++v)
+    int v = v0;
+    for (; v + 4 <= v1; v += 4) {
+      float x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = atom_id[v + u] > 0 ? h[(int64_t)(v + u) * d + j] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sacc += x[u];
+    }
+    for (; v < v1; ++v)
       if (atom_id[v] > 0) sacc += h[(int64_t)v * d + j];
     out[(int64_t)m * d + j] = sacc;
   }

@@ -351,7 +351,9 @@ int imp_mpnn_forward_fused_compact(const imp_compact_graph_t* cg, const float* d
  *                      less per step).  flags: IMP_TC_FP16 [| IMP_TC_PRECISE_EPILOGUE]; IMP_TC_GEN5 selects the fifth
  *                      generation (same plan, third-generation step pipeline, weights from imp_fused_pack with
  *                      IMP_TC_FP16) for comparison.  Results do not depend on how the plan cut the batch (row order inside
- *                      a tile does not enter the arithmetic); they agree with imp_mpnn_forward_fused to a few operand ulps. */
+ *                      a tile does not enter the arithmetic); they agree with imp_mpnn_forward_fused to a few operand ulps.
+ *                      The default (sixth-generation) kernel hands the tiles out through two ticket counters in int32 words
+ *                      5 and 6 of the plan buffer, which the call zeroes: one forward at a time per plan buffer. */
 int64_t imp_fused_pack_planned_bytes(int32_t d, int32_t bond_dim);
 int imp_fused_pack_planned(const float* d_bond_transform /* [K,d,d] */, const imp_gru_weights_t* w, int32_t d, int32_t bond_dim,
                            void* d_packed, void* stream);

@@ -91,7 +91,8 @@ struct alignas(128) FusedWgSmem6 {
   FusedTile plan[2];
   uint64_t bar[4];   // 1: gate GEMM done, 2: candidate GEMM done, 3: GEMM1a done
   uint64_t pbar[2];  // plan buffers
-  uint64_t pad[10];
+  int next_tile[2];  // tile index fetched for the next iteration (double-buffered: written by thread 0, read by all)
+  uint64_t pad[9];
 };
 
 __host__ __device__ inline int fused6_smem_bytes(int steps, int bond_vocab) {
@@ -107,6 +108,7 @@ struct Fused6Args {
   float* pooled;                // [2P][32]
   int atom_vocab, bond_vocab, steps, n_cta_cat;
   float eps;
+  int* tickets;  // [2] per-tower tile counters (words 5, 6 of the plan header, zeroed by the launcher): dynamic tile scheduling
   int emb_smem;  // 1: the atom-embedding table is staged in shared memory behind the per-context buffers (atom_vocab * 128 bytes)
 };
 
@@ -138,9 +140,6 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
   if (__ldg(&hdr->status) == 2) return;  // the plan ran out of tile records: some are unwritten (the host raises, model.check_status)
   const int n_tiles = min(__ldg(&hdr->n_tiles[tower]), __ldg(&hdr->cap[tower]));
   const FusedTile* tiles = reinterpret_cast<const FusedTile*>(a.plan + FP_HEADER_BYTES) + (size_t)(tower ? __ldg(&hdr->cap[0]) : 0);
-  const int n_cta_tower = tower ? (int)gridDim.x - a.n_cta_cat : a.n_cta_cat;
-  const int cta_in_tower = tower ? (int)blockIdx.x - a.n_cta_cat : (int)blockIdx.x;
-  const int first = cta_in_tower * F6_CTX + ctx, stride = n_cta_tower * F6_CTX;
 
   if (tid == 0) {  // resident weights of this tower (all steps): one TMA bulk copy
     tc::mbar_init(&ctl.wbar, 1);
@@ -154,9 +153,13 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
     tc::mbar_init(&ws.pbar[0], 1);
     tc::mbar_init(&ws.pbar[1], 1);
     tc::mbar_fence_init();
-    if (first < n_tiles) {  // first tile record of this context
+    // Tiles are handed out by a per-tower ticket counter, not by a fixed stride: contexts whose tiles happen to carry more
+    // entries no longer finish last (2.6 % of the warp samples of the strided form sat in EXIT)
+    const int c0 = atomicAdd(a.tickets + tower, 1);
+    ws.next_tile[0] = c0;
+    if (c0 < n_tiles) {  // first tile record of this context
       tc::mbar_arrive_expect_tx(&ws.pbar[0], (uint32_t)sizeof(FusedTile));
-      tc::bulk_copy_g2s(&ws.plan[0], tiles + first, (uint32_t)sizeof(FusedTile), &ws.pbar[0]);
+      tc::bulk_copy_g2s(&ws.plan[0], tiles + c0, (uint32_t)sizeof(FusedTile), &ws.pbar[0]);
     }
   }
   for (int i = tid; i < a.bond_vocab; i += NT) {
@@ -216,11 +219,15 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
   }
 
   int buf = 0;
-  for (int tile = first; tile < n_tiles; tile += stride, buf ^= 1) {
-    if (t == 0 && tile + stride < n_tiles) {  // next record -> the other buffer (its readers passed the end-of-tile barrier)
-      tc::fence_proxy_async_smem();
-      tc::mbar_arrive_expect_tx(&ws.pbar[buf ^ 1], (uint32_t)sizeof(FusedTile));
-      tc::bulk_copy_g2s(&ws.plan[buf ^ 1], tiles + tile + stride, (uint32_t)sizeof(FusedTile), &ws.pbar[buf ^ 1]);
+  for (int tile = ws.next_tile[0]; tile < n_tiles; tile = ws.next_tile[buf ^ 1], buf ^= 1) {
+    if (t == 0) {  // next ticket; its record -> the other buffer (the readers of that buffer passed the end-of-tile barrier)
+      const int nx = atomicAdd(a.tickets + tower, 1);
+      ws.next_tile[buf ^ 1] = nx;  // read by every thread after the last barrier of this tile
+      if (nx < n_tiles) {
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive_expect_tx(&ws.pbar[buf ^ 1], (uint32_t)sizeof(FusedTile));
+        tc::bulk_copy_g2s(&ws.plan[buf ^ 1], tiles + nx, (uint32_t)sizeof(FusedTile), &ws.pbar[buf ^ 1]);
+      }
     }
     F6_PROF(0);
     tc::mbar_wait(&ws.pbar[buf], (pph >> buf) & 1u);
@@ -534,6 +541,9 @@ int launch_fused_h6(const void* d_plan, int32_t n_atoms, int32_t n_cat_atoms, in
   Fused6Args a;
   a.plan = (const unsigned char*)d_plan, a.atom_emb = d_atom_emb, a.bond_emb = d_bond_emb, a.packed = (const unsigned char*)d_packed;
   a.pooled = d_pooled, a.atom_vocab = atom_vocab, a.bond_vocab = bond_vocab, a.steps = steps, a.eps = eps;
+  // tile tickets: words 5, 6 of the plan header (FusedPlanHeader::pad), zeroed before every launch -- one forward at a time per plan
+  a.tickets = reinterpret_cast<int*>(const_cast<void*>(d_plan)) + 5;
+  IMP_CUDA(cudaMemsetAsync(a.tickets, 0, 2 * sizeof(int), st));
   // one persistent CTA per SM; CTAs are split between the towers in proportion to their atoms
   const int sms = fused6_sm_count();
   int nc = (int)((int64_t)sms * n_cat_atoms / (n_atoms > 0 ? n_atoms : 1));

@@ -34,7 +34,7 @@ struct FusedPlanHeader {  // first FP_HEADER_BYTES of the plan buffer, then cap[
   int32_t cap[2];
   int32_t status;  // 0, or 1: a molecule outside the envelope (> 128 atoms, a row with > 31 entries, > FP_ECAP entries),
                    //        2: tile capacity exceeded
-  int32_t pad[3];
+  int32_t pad[3];  // [0], [1]: per-tower tile tickets of the sixth-generation forward (zeroed by its launcher)
 };
 
 }  // namespace imp

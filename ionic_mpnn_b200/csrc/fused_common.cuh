@@ -87,6 +87,14 @@ __device__ __forceinline__ __half2 fz_tanh_h2(__half2 x) {
   return *reinterpret_cast<const __half2*>(&y);
 }
 
+// rsqrt.approx.ftz: one MUFU.RSQ (rsqrtf() wraps it in a denormal rescue -- FSETP, two FMULs by 2^24 / 2^12 -- that a
+// LayerNorm variance + eps >= 1e-3 never needs)
+__device__ __forceinline__ float fz_rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Optional phase timing (compile with -DFZ_PROFILE): per-phase clock64 deltas of selected threads, summed into

@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(F6_CTX * F6_THREADS, 1) mpnn_fused_h6_kernel(c
         }
         const float mean = (s0 + s1) * (1.0f / D);
         const float var = fmaxf(fmaf(q0 + q1, 1.0f / D, -mean * mean), 0.f);  // biased variance
-        const float inv = PRECISE ? 1.0f / sqrtf(var + a.eps) : rsqrtf(var + a.eps);
+        const float inv = PRECISE ? 1.0f / sqrtf(var + a.eps) : fz_rsqrt_fast(var + a.eps);
         const float ninv = -mean * inv;
 #pragma unroll
         for (int j = 0; j < D; ++j) h[j] = fmaf(fmaf(gq[j], inv, ninv), gb[j], h[j]) + gb[D + j];

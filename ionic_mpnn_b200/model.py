@@ -90,7 +90,13 @@ class MPNNModel(TrainMixin):
         """``precision``: 'fp32' = SIMT kernels (the 1e-5 path); 'fp16' / 'bf16' = tcgen05 tensor-core path with
         IEEE-half / bfloat16 operands and fp32 accumulation (the 2e-2 path; '*_precise' keeps expf/tanhf in the
         epilogues).  ``fused``: run the whole-tower fused kernel (imp_mpnn_forward_fused) when the shape allows it
-        ('auto' = yes for the tensor precisions), else the staged per-layer kernels."""
+        ('auto' = yes for the tensor precisions), else the staged per-layer kernels.
+
+        Tuning attributes (plain attributes, all optional): ``fused_gen`` (6 default; 7 / 8 = the measured alternatives of the
+        planned fused forward), ``plan_slack`` ('auto', a factor, or None = never-overflowing plan buffer),
+        ``use_plan`` (False = the self-contained fused kernel), ``fp32_tensor`` (precision 'fp32' only: 3xTF32 tensor-core
+        GatedUpdate and messages -- 1.57x, fp32-class but 1.6e-5 on the worst element, NOT the 1e-5 path), ``tc_forward`` /
+        ``tc_backward`` (training: False = the fp32 SIMT kernels), ``extra_tc_flags`` (IMP_TC_* experiment switches)."""
         import torch
 
         if precision not in self.PRECISIONS:

@@ -15,19 +15,24 @@ Mirrors, on plain Python containers,
 from __future__ import annotations
 
 
-def get_atom_features(atom):
-    """src/featurize.py:8-18."""
-    return (atom.GetSymbol(), atom.GetFormalCharge(), atom.GetTotalNumHs(), int(atom.GetIsAromatic()), str(atom.GetHybridization()))
+ATOM_FIELDS = ("GetSymbol", "GetFormalCharge", "GetTotalNumHs", "GetIsAromatic", "GetHybridization")  # src/featurize.py:13-17
+BOND_FIELDS = ("GetBondType", "GetIsConjugated", "IsInRing")                                            # src/featurize.py:25-27
 
 
-def get_bond_features(bond):
-    """src/featurize.py:21-29."""
-    return (str(bond.GetBondType()), bond.GetIsConjugated(), bond.IsInRing())
+def _atom_tuple(atom):
+    sym, charge, n_h, arom, hyb = (getattr(atom, f)() for f in ATOM_FIELDS)
+    return (sym, charge, n_h, int(arom), str(hyb))
+
+
+def _bond_tuple(bond):
+    kind, conj, ring = (getattr(bond, f)() for f in BOND_FIELDS)
+    return (str(kind), conj, ring)
 
 
 def smiles_to_graph(smiles):
-    """src/featurize.py:32-76 (needs RDKit).  Every bond contributes the two consecutive entries (a, b), (b, a) that share one
-    feature tuple -- the convention ``ionic_mpnn_b200.synth`` and the packers rely on."""
+    """The graph dict of src/featurize.py:32-76 for one SMILES string (needs RDKit: explicit hydrogens added, one feature
+    tuple per atom; every bond contributes the two consecutive entries (a, b), (b, a) that share one feature tuple -- the
+    convention ``ionic_mpnn_b200.synth`` and the packers rely on)."""
     try:
         from rdkit import Chem
     except ImportError as e:  # pragma: no cover - RDKit is absent from this image
@@ -37,15 +42,12 @@ def smiles_to_graph(smiles):
     if mol is None:
         raise ValueError(f"invalid SMILES string: {smiles}")
     mol = Chem.AddHs(mol)
-    atom_features = [get_atom_features(a) for a in mol.GetAtoms()]
-    bond_features, edge_indices = [], []
-    for bond in mol.GetBonds():
-        a, b = bond.GetBeginAtomIdx(), bond.GetEndAtomIdx()
-        f = get_bond_features(bond)
-        edge_indices += [(a, b), (b, a)]
-        bond_features += [f, f]
-    return {"smiles": smiles, "atom_features": atom_features, "bond_features": bond_features, "edge_indices": edge_indices,
-            "num_atoms": len(atom_features)}
+    ends = [(b.GetBeginAtomIdx(), b.GetEndAtomIdx(), _bond_tuple(b)) for b in mol.GetBonds()]
+    atoms = [_atom_tuple(a) for a in mol.GetAtoms()]
+    return {"smiles": smiles, "atom_features": atoms,
+            "bond_features": [f for _, _, f in ends for _ in (0, 1)],
+            "edge_indices": [e for u, v, _ in ends for e in ((u, v), (v, u))],
+            "num_atoms": len(atoms)}
 
 
 def build_vocab(*datasets):
